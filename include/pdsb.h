@@ -1,0 +1,178 @@
+/* pdsb.h - C-ABI of the B200-native model-to-visibility path for pdspy.
+ *
+ * Plain C: pointers, sizes, opaque handles.  No torch / numpy types cross this
+ * boundary.  Every entry point returns 0 on success and a non-zero code on failure
+ * (PDSB_ERR_*); pdsb_last_error() returns a human-readable message for the last
+ * failure on the calling thread.  Nothing throws.  There is NO CPU fallback: without
+ * a CUDA device every compute entry point fails with PDSB_ERR_CUDA.
+ *
+ * Reference interfaces replaced (paths under the reference tree, psheehan/pdspy v2.0.8):
+ *   pdsb_sample_image      galario.double.sampleImage as called by
+ *                          pdspy/interferometry/interpolate_model.py:22-30 (per-channel loop,
+ *                          row flip, conjugation, dRA/dDec phase)
+ *   pdsb_loglike*          interpolate_model (above) followed by the visibility term of
+ *                          pdspy/utils/emcee.py:31-43 == pdspy/utils/dynesty.py:47-59
+ *   pdsb_chi2              the same likelihood term on caller-supplied model arrays
+ *   pdsb_chisq             chisq()/chisq_calc  pdspy/interferometry/libinterferometry.pyx:610-633
+ *   pdsb_grid              grid()              pdspy/interferometry/libinterferometry.pyx:313-541
+ *   pdsb_freqcorrect       freqcorrect()       pdspy/interferometry/libinterferometry.pyx:587-608
+ *
+ * Threading: one calling thread per process (the reference is single-threaded Python,
+ * one MPI rank per likelihood); N processes may share a GPU.
+ *
+ * Memory kinds: every array argument is either a host pointer (PDSB_HOST; pageable or
+ * pinned) or a device pointer on the initialised device (PDSB_DEVICE); the `kind`
+ * argument next to a group of pointers says which.  Host results are valid when the
+ * call returns; device results are ordered on the library's stream (pdsb_get_stream).
+ */
+#ifndef PDSB_H
+#define PDSB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDSB_VERSION 1
+
+enum { PDSB_HOST = 0, PDSB_DEVICE = 1 };
+
+enum {
+    PDSB_OK = 0,
+    PDSB_ERR_ARG = 1,        /* bad argument (null pointer, size, enum)           */
+    PDSB_ERR_CUDA = 2,       /* CUDA runtime error, or no device                  */
+    PDSB_ERR_STATE = 3,      /* call out of order (no init, no data uploaded...)  */
+    PDSB_ERR_NOMEM = 4
+};
+
+/* convolution kernels of grid(): libinterferometry.pyx:405-417 */
+enum { PDSB_CONV_PILLBOX = 0, PDSB_CONV_EXPSINC = 1 };
+/* weighting schemes of grid(): libinterferometry.pyx:429 */
+enum { PDSB_WT_NATURAL = 0, PDSB_WT_UNIFORM = 1, PDSB_WT_SUPERUNIFORM = 2, PDSB_WT_ROBUST = 3 };
+/* mode of grid(): libinterferometry.pyx:363-367 */
+enum { PDSB_MODE_CONTINUUM = 0, PDSB_MODE_SPECTRALLINE = 1 };
+
+typedef struct pdsb_dataset pdsb_dataset;
+
+/* ---- lifecycle -------------------------------------------------------------- */
+int pdsb_version(void);
+int pdsb_device_count(int *count);
+/* Select the device, create the library stream, read SM count / clocks.  Idempotent. */
+int pdsb_init(int device);
+int pdsb_shutdown(void);
+const char *pdsb_last_error(void);
+/* cudaStream_t the library launches on, as an integer. */
+int pdsb_get_stream(uint64_t *stream);
+/* Launch on a caller-owned stream instead (e.g. torch's current stream); 0 restores the own stream. */
+int pdsb_set_stream(uint64_t stream);
+int pdsb_synchronize(void);
+int pdsb_device_info(int *sm_count, int *sm_clock_khz, int64_t *mem_bytes, int *cc_major, int *cc_minor);
+
+/* ---- raw buffers (so callers need no other CUDA binding) ---------------------- */
+int pdsb_device_alloc(void **ptr, int64_t bytes);
+int pdsb_device_free(void *ptr);
+int pdsb_host_alloc_pinned(void **ptr, int64_t bytes);
+int pdsb_host_free_pinned(void *ptr);
+/* kind_dst/kind_src: PDSB_HOST or PDSB_DEVICE; asynchronous on the library stream when the
+ * host side is pinned, then pdsb_synchronize() before touching the host buffer. */
+int pdsb_memcpy(void *dst, int kind_dst, const void *src, int kind_src, int64_t bytes);
+int pdsb_memset(void *dev_ptr, int value, int64_t bytes);
+
+/* ---- timing on the library stream (CUDA events) ------------------------------ */
+int pdsb_timer_start(void);
+int pdsb_timer_stop(double *elapsed_ms);      /* synchronises on the stop event */
+/* Per-kernel device time: when enabled every kernel launch is bracketed by events.
+ * pdsb_profile_get sums them (synchronising) for kernels whose name starts with `prefix`. */
+int pdsb_profile_enable(int on);
+int pdsb_profile_reset(void);
+int pdsb_profile_get(const char *prefix, double *total_ms, int64_t *launches);
+/* Number of kernels this library has launched since init (all kinds). */
+int pdsb_launch_count(int64_t *count);
+
+/* ---- dataset: the static part of one observation ------------------------------ */
+/* u, v: [nuv] fp64, wavelengths at the mean frequency (what interpolate_model receives).
+ * If the list is Hermitian-doubled (second half == minus first half, exactly, as the
+ * reference's readers produce: readuvfits.py:68-73) the transform is evaluated for the
+ * first half only and conjugated for the second; detected, never assumed. */
+int pdsb_dataset_create(const double *u, const double *v, int64_t nuv, int kind, pdsb_dataset **out);
+/* Observed visibilities for the likelihood: real, imag, weights [nuv, nf] fp64 row-major
+ * (libinterferometry.pyx:16-22).  Precomputes sum(log(w/2pi)) over w>0 (emcee.py:32,37). */
+int pdsb_dataset_set_data(pdsb_dataset *ds, const double *real, const double *imag,
+                          const double *weights, int nf, int kind);
+int pdsb_dataset_info(const pdsb_dataset *ds, int64_t *nuv, int64_t *nuv_unique, int *nf, int *hermitian);
+int pdsb_dataset_destroy(pdsb_dataset *ds);
+
+/* ---- image cube -> model visibilities ------------------------------------------ */
+/* image: [ny, nx, nf] fp64, channel fastest: the reference's image[ny,nx,nf,1] buffer
+ * (imaging/libimaging.pyx:11).  dxy, dRA, dDec in RADIANS (the caller applies
+ * `*arcsec`, interpolate_model.py:20,24).  out_real/out_imag: [nuv, nf] fp64, in the
+ * reference's final convention (after its imag -> -imag, interpolate_model.py:27):
+ *   V_i(u,v) = sum_{j,c} image[j,c,i] exp(+2 pi i dxy (u (c - nx/2) + v (ny/2 - 1 - j)))
+ *                                     exp(-2 pi i (u dRA + v dDec))
+ * evaluated as an exact (direct) transform: fp32 products with fp64 phase seeding and
+ * fp64 accumulation across row chunks. */
+int pdsb_sample_image(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind,
+                      double dxy, double dRA, double dDec,
+                      double *out_real, double *out_imag, int out_kind);
+
+/* Fused transform + likelihood: the model visibilities never leave the device.
+ *   chi2[nf] (nullable): sum_k w (|d - m|^2) per channel
+ *   lnlike:  -0.5*sum((d.re-m.re)^2 w) - L - 0.5*sum((d.im-m.im)^2 w) - L,
+ *            L = sum(log(w[w>0]/2pi))      (emcee.py:31-43, verbatim incl. the doubled L)
+ * Outputs are host doubles.  nf must equal the dataset's nf. */
+int pdsb_loglike(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind,
+                 double dxy, double dRA, double dDec, double *chi2, double *lnlike);
+/* nwalkers cubes [W, ny, nx, nf] against one dataset; dRA/dDec per walker [W] (host). */
+int pdsb_loglike_batch(pdsb_dataset *ds, const double *images, int nwalkers, int ny, int nx, int nf,
+                       int image_kind, double dxy, const double *dRA, const double *dDec,
+                       double *lnlike);
+
+/* ---- likelihood on caller-supplied model arrays --------------------------------- */
+/* All arrays [n] fp64 (n = nuv*nf).  out[0]=sum (d.re-m.re)^2 w, out[1]=sum (d.im-m.im)^2 w,
+ * out[2]=sum log(w[w>0]/2pi), out[3]=the emcee.py:31-43 value.  out is a host double[4]. */
+int pdsb_chi2(const double *d_real, const double *d_imag, const double *weights,
+              const double *m_real, const double *m_imag, int64_t n, int kind, double *out);
+/* chisq(): channel 0 of [nuv, nf] arrays, result rounded through a C float as the
+ * reference's `cdef float chisq_calc` does (libinterferometry.pyx:616). */
+int pdsb_chisq(const double *d_real, const double *d_imag, const double *weights,
+               const double *m_real, const double *m_imag, int64_t nuv, int nf, int kind, float *out);
+
+/* ---- convolutional gridding ------------------------------------------------------- */
+/* Inputs as grid() has them after channel/mfs selection: u, v [nuv]; freq [nf];
+ * real, imag, weights [nuv, nf] (weights NOT yet clamped: the clamp of :351 and the
+ * zeroing of :353 happen inside).  uu, vv: [G] cell centres (numpy.linspace of :370-381,
+ * computed by the caller because linspace's rounding is part of the reference result).
+ * Outputs, host or device per out_kind (any may be NULL):
+ *   out_real, out_imag, out_weights  [G*G, nch] fp64, row = v index, col = u index (:535-541)
+ *   out_i, out_j                     [nuv, nf] uint32 index maps (:388-403)
+ *   out_wmod                         [nuv, nf] fp64 weights after clamp + re-weighting
+ *   n_outside                        count of (k,n) outside the grid (the WARNING of :424)
+ * deterministic != 0: every cell is accumulated in the reference's (k, n) order, so
+ * pillbox maps are bit-exact against the reference; 0: shared-memory tiles + atomics. */
+int pdsb_grid(const double *u, const double *v, const double *freq,
+              const double *real, const double *imag, const double *weights,
+              int64_t nuv, int nf, int in_kind,
+              int gridsize, double binsize, const double *uu, const double *vv,
+              int convolution, int weighting, double robust, int npixels, int mode, int imaging,
+              int deterministic,
+              double *out_real, double *out_imag, double *out_weights,
+              uint32_t *out_i, uint32_t *out_j, double *out_wmod, int out_kind,
+              int64_t *n_outside);
+
+/* freqcorrect(): u' = (u[:,None]*freq/fbar).ravel() etc.; arrays on host or device. */
+int pdsb_freqcorrect(const double *u, const double *v, const double *freq, int64_t nuv, int nf,
+                     double new_freq, int kind, double *out_u, double *out_v);
+
+/* ---- tuning / measurement ----------------------------------------------------------- */
+/* DFT kernel variant: 0 = auto, otherwise an index into the built variants. */
+int pdsb_set_dft_variant(int variant);
+int pdsb_set_dft_split(int nsplit);          /* 0 = auto */
+/* Register-resident FMA microbenchmark on all SMs: variant 0 = FFMA, 1 = FFMA2 (f32x2).
+ * Returns achieved TFLOP/s (2 flop per FMA lane). */
+int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDSB_H */

@@ -1,0 +1,91 @@
+// Shared host-side state and helpers of libpdsb (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/pdsb.h"
+
+namespace pdsb {
+
+void set_error(const char *fmt, ...);
+
+#define PDSB_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            pdsb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),      \
+                            __FILE__, __LINE__);                                          \
+            return PDSB_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define PDSB_CHECK(expr)                       \
+    do {                                       \
+        int rc__ = (expr);                     \
+        if (rc__ != PDSB_OK) return rc__;      \
+    } while (0)
+
+#define PDSB_REQUIRE(cond, msg)                                          \
+    do {                                                                 \
+        if (!(cond)) {                                                   \
+            pdsb::set_error("bad argument: %s (%s)", msg, #cond);        \
+            return PDSB_ERR_ARG;                                         \
+        }                                                                \
+    } while (0)
+
+// Grow-only device scratch buffer.
+struct Scratch {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+struct ProfileEntry {
+    const char *name;
+    cudaEvent_t start, stop;
+};
+
+struct Context {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 0;
+    int sm_clock_khz = 0;
+    size_t mem_bytes = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool profiling = false;
+    std::vector<ProfileEntry> prof;
+    std::vector<cudaEvent_t> event_pool;
+    int64_t launches = 0;
+    int dft_variant = 0;
+    int dft_split = 0;
+    // scratch
+    Scratch img64, folded, partial, red, stage_a, stage_b, stage_c, stage_d, stage_e;
+    Scratch pinned_note;
+};
+
+Context &ctx();
+int require_init();
+
+// Kernel launch bookkeeping: counts launches, brackets them with events when profiling.
+struct LaunchScope {
+    const char *name;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    explicit LaunchScope(const char *n);
+    ~LaunchScope();
+};
+
+// Pointer staging: returns a device pointer for `p`; copies from host when kind==HOST.
+int to_device(const void *p, int kind, size_t bytes, Scratch &scratch, const void **dev);
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace pdsb

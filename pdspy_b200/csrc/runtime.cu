@@ -1,0 +1,451 @@
+// libpdsb runtime: context, stream, buffers, timing, profiling, FMA microbenchmark.
+#include "common.cuh"
+
+namespace pdsb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+Context &ctx()
+{
+    static Context c;
+    return c;
+}
+
+int require_init()
+{
+    if (!ctx().inited) {
+        int rc = pdsb_init(0);
+        if (rc != PDSB_OK) return rc;
+    }
+    return PDSB_OK;
+}
+
+int Scratch::ensure(size_t bytes)
+{
+    if (bytes <= cap) return PDSB_OK;
+    if (ptr) {
+        // the previous buffer may still be in use by queued work on the stream
+        cudaStreamSynchronize(ctx().stream);
+        cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        ptr = nullptr;
+        return PDSB_ERR_NOMEM;
+    }
+    cap = want;
+    return PDSB_OK;
+}
+
+void Scratch::release()
+{
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+static cudaEvent_t get_event()
+{
+    Context &c = ctx();
+    if (!c.event_pool.empty()) {
+        cudaEvent_t e = c.event_pool.back();
+        c.event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+LaunchScope::LaunchScope(const char *n) : name(n)
+{
+    Context &c = ctx();
+    c.launches++;
+    if (c.profiling) {
+        e0 = get_event();
+        e1 = get_event();
+        cudaEventRecord(e0, c.stream);
+    }
+}
+
+LaunchScope::~LaunchScope()
+{
+    Context &c = ctx();
+    if (e0) {
+        cudaEventRecord(e1, c.stream);
+        c.prof.push_back({name, e0, e1});
+    }
+}
+
+int to_device(const void *p, int kind, size_t bytes, Scratch &scratch, const void **dev)
+{
+    if (kind == PDSB_DEVICE) {
+        *dev = p;
+        return PDSB_OK;
+    }
+    PDSB_CHECK(scratch.ensure(bytes));
+    PDSB_CUDA(cudaMemcpyAsync(scratch.ptr, p, bytes, cudaMemcpyHostToDevice, ctx().stream));
+    *dev = scratch.ptr;
+    return PDSB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// FMA microbenchmark: register-resident dependent chains, enough independent chains per
+// thread to cover the pipe latency.  variant 0: scalar FFMA; variant 1: FFMA2 (f32x2).
+__device__ __forceinline__ unsigned long long fma2_(unsigned long long a, unsigned long long b,
+                                                    unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+template <int VAR>
+__global__ void __launch_bounds__(256) fma_bench_kernel(float *out, int iters, float seed)
+{
+    constexpr int NCH = 16;
+    float m = 1.0f + seed * 1e-9f, b = seed * 1e-9f;
+    if (VAR == 0) {
+        float acc[NCH];
+#pragma unroll
+        for (int i = 0; i < NCH; i++) acc[i] = threadIdx.x * 1e-3f + i;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int i = 0; i < NCH; i++) acc[i] = fmaf(acc[i], m, b);
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < NCH; i++) s += acc[i];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    } else {
+        unsigned long long acc[NCH / 2];
+        float2 mm = make_float2(m, m), bb = make_float2(b, b);
+        unsigned long long m2 = *reinterpret_cast<unsigned long long *>(&mm);
+        unsigned long long b2 = *reinterpret_cast<unsigned long long *>(&bb);
+#pragma unroll
+        for (int i = 0; i < NCH / 2; i++) {
+            float2 a = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i);
+            acc[i] = *reinterpret_cast<unsigned long long *>(&a);
+        }
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int i = 0; i < NCH / 2; i++) acc[i] = fma2_(acc[i], m2, b2);
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < NCH / 2; i++) {
+            float2 a = *reinterpret_cast<float2 *>(&acc[i]);
+            s += a.x + a.y;
+        }
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    }
+}
+
+}  // namespace pdsb
+
+using namespace pdsb;
+
+extern "C" {
+
+int pdsb_version(void) { return PDSB_VERSION; }
+
+const char *pdsb_last_error(void) { return g_err; }
+
+int pdsb_device_count(int *count)
+{
+    PDSB_REQUIRE(count, "count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return PDSB_ERR_CUDA;
+    }
+    *count = n;
+    return PDSB_OK;
+}
+
+int pdsb_init(int device)
+{
+    Context &c = ctx();
+    if (c.inited && c.device == device) return PDSB_OK;
+    if (c.inited) {
+        set_error("already initialised on device %d; call pdsb_shutdown first", c.device);
+        return PDSB_ERR_STATE;
+    }
+    int n = 0;
+    PDSB_CHECK(pdsb_device_count(&n));
+    if (n <= 0) {
+        set_error("no CUDA device visible: libpdsb has no CPU fallback");
+        return PDSB_ERR_CUDA;
+    }
+    PDSB_REQUIRE(device >= 0 && device < n, "device index");
+    PDSB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    PDSB_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) {
+        set_error("device %d is sm_%d%d; libpdsb is built for sm_100a only", device, p.major, p.minor);
+        return PDSB_ERR_CUDA;
+    }
+    c.device = device;
+    c.sm_count = p.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    c.sm_clock_khz = khz;
+    c.mem_bytes = p.totalGlobalMem;
+    c.cc_major = p.major;
+    c.cc_minor = p.minor;
+    PDSB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    PDSB_CUDA(cudaEventCreate(&c.t0));
+    PDSB_CUDA(cudaEventCreate(&c.t1));
+    c.inited = true;
+    return PDSB_OK;
+}
+
+int pdsb_shutdown(void)
+{
+    Context &c = ctx();
+    if (!c.inited) return PDSB_OK;
+    cudaStreamSynchronize(c.stream);
+    for (Scratch *s : {&c.img64, &c.folded, &c.partial, &c.red, &c.stage_a, &c.stage_b, &c.stage_c,
+                       &c.stage_d, &c.stage_e})
+        s->release();
+    for (auto &p : c.prof) {
+        cudaEventDestroy(p.start);
+        cudaEventDestroy(p.stop);
+    }
+    c.prof.clear();
+    for (auto e : c.event_pool) cudaEventDestroy(e);
+    c.event_pool.clear();
+    cudaEventDestroy(c.t0);
+    cudaEventDestroy(c.t1);
+    cudaStreamDestroy(c.own_stream);
+    c = Context();
+    return PDSB_OK;
+}
+
+int pdsb_get_stream(uint64_t *stream)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(stream, "stream");
+    *stream = (uint64_t)(uintptr_t)ctx().stream;
+    return PDSB_OK;
+}
+
+int pdsb_set_stream(uint64_t stream)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    c.stream = stream ? (cudaStream_t)(uintptr_t)stream : c.own_stream;
+    return PDSB_OK;
+}
+
+int pdsb_synchronize(void)
+{
+    PDSB_CHECK(require_init());
+    PDSB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return PDSB_OK;
+}
+
+int pdsb_device_info(int *sm_count, int *sm_clock_khz, int64_t *mem_bytes, int *cc_major, int *cc_minor)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    if (sm_count) *sm_count = c.sm_count;
+    if (sm_clock_khz) *sm_clock_khz = c.sm_clock_khz;
+    if (mem_bytes) *mem_bytes = (int64_t)c.mem_bytes;
+    if (cc_major) *cc_major = c.cc_major;
+    if (cc_minor) *cc_minor = c.cc_minor;
+    return PDSB_OK;
+}
+
+int pdsb_device_alloc(void **ptr, int64_t bytes)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ptr && bytes >= 0, "ptr/bytes");
+    *ptr = nullptr;
+    if (bytes == 0) return PDSB_OK;
+    cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+        return PDSB_ERR_NOMEM;
+    }
+    return PDSB_OK;
+}
+
+int pdsb_device_free(void *ptr)
+{
+    if (!ptr) return PDSB_OK;
+    PDSB_CHECK(require_init());
+    PDSB_CUDA(cudaStreamSynchronize(ctx().stream));
+    PDSB_CUDA(cudaFree(ptr));
+    return PDSB_OK;
+}
+
+int pdsb_host_alloc_pinned(void **ptr, int64_t bytes)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ptr && bytes > 0, "ptr/bytes");
+    cudaError_t e = cudaMallocHost(ptr, (size_t)bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMallocHost(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+        return PDSB_ERR_NOMEM;
+    }
+    return PDSB_OK;
+}
+
+int pdsb_host_free_pinned(void *ptr)
+{
+    if (!ptr) return PDSB_OK;
+    PDSB_CUDA(cudaFreeHost(ptr));
+    return PDSB_OK;
+}
+
+int pdsb_memcpy(void *dst, int kind_dst, const void *src, int kind_src, int64_t bytes)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(bytes >= 0, "bytes");
+    if (bytes == 0) return PDSB_OK;
+    PDSB_REQUIRE(dst && src, "dst/src");
+    cudaMemcpyKind k = kind_dst == PDSB_DEVICE
+                           ? (kind_src == PDSB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                           : (kind_src == PDSB_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    PDSB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, k, ctx().stream));
+    return PDSB_OK;
+}
+
+int pdsb_memset(void *dev_ptr, int value, int64_t bytes)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(dev_ptr && bytes >= 0, "ptr/bytes");
+    PDSB_CUDA(cudaMemsetAsync(dev_ptr, value, (size_t)bytes, ctx().stream));
+    return PDSB_OK;
+}
+
+int pdsb_timer_start(void)
+{
+    PDSB_CHECK(require_init());
+    PDSB_CUDA(cudaEventRecord(ctx().t0, ctx().stream));
+    return PDSB_OK;
+}
+
+int pdsb_timer_stop(double *elapsed_ms)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(elapsed_ms, "elapsed_ms");
+    PDSB_CUDA(cudaEventRecord(ctx().t1, ctx().stream));
+    PDSB_CUDA(cudaEventSynchronize(ctx().t1));
+    float ms = 0;
+    PDSB_CUDA(cudaEventElapsedTime(&ms, ctx().t0, ctx().t1));
+    *elapsed_ms = ms;
+    return PDSB_OK;
+}
+
+int pdsb_profile_enable(int on)
+{
+    PDSB_CHECK(require_init());
+    ctx().profiling = on != 0;
+    return PDSB_OK;
+}
+
+int pdsb_profile_reset(void)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    for (auto &p : c.prof) {
+        c.event_pool.push_back(p.start);
+        c.event_pool.push_back(p.stop);
+    }
+    c.prof.clear();
+    return PDSB_OK;
+}
+
+int pdsb_profile_get(const char *prefix, double *total_ms, int64_t *launches)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    double tot = 0;
+    int64_t n = 0;
+    size_t plen = prefix ? strlen(prefix) : 0;
+    for (auto &p : c.prof) {
+        if (plen && strncmp(p.name, prefix, plen) != 0) continue;
+        float ms = 0;
+        PDSB_CUDA(cudaEventElapsedTime(&ms, p.start, p.stop));
+        tot += ms;
+        n++;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return PDSB_OK;
+}
+
+int pdsb_launch_count(int64_t *count)
+{
+    PDSB_REQUIRE(count, "count");
+    *count = ctx().launches;
+    return PDSB_OK;
+}
+
+int pdsb_set_dft_variant(int variant)
+{
+    ctx().dft_variant = variant;
+    return PDSB_OK;
+}
+
+int pdsb_set_dft_split(int nsplit)
+{
+    PDSB_REQUIRE(nsplit >= 0, "nsplit");
+    ctx().dft_split = nsplit;
+    return PDSB_OK;
+}
+
+int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms_out)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(tflops && iters > 0, "tflops/iters");
+    Context &c = ctx();
+    int blocks = c.sm_count * 8, threads = 256;
+    PDSB_CHECK(c.red.ensure((size_t)blocks * threads * sizeof(float)));
+    for (int rep = 0; rep < 2; rep++) {
+        if (rep == 1) PDSB_CUDA(cudaEventRecord(c.t0, c.stream));
+        {
+            LaunchScope ls(variant ? "fma_bench_f32x2" : "fma_bench_f32");
+            if (variant == 0)
+                fma_bench_kernel<0><<<blocks, threads, 0, c.stream>>>(c.red.as<float>(), iters, 1.0f);
+            else
+                fma_bench_kernel<1><<<blocks, threads, 0, c.stream>>>(c.red.as<float>(), iters, 1.0f);
+        }
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CUDA(cudaEventRecord(c.t1, c.stream));
+    PDSB_CUDA(cudaEventSynchronize(c.t1));
+    float ms = 0;
+    PDSB_CUDA(cudaEventElapsedTime(&ms, c.t0, c.t1));
+    double fmas = (double)blocks * threads * (double)iters * 8.0 * 16.0;
+    *tflops = 2.0 * fmas / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return PDSB_OK;
+}
+
+}  // extern "C"

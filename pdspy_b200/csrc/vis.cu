@@ -1,0 +1,579 @@
+// Dataset handles, the visibility epilogue (centre phase, Hermitian expansion, [nuv,nf] layout),
+// the fused chi^2 / log-likelihood reductions (fp64, deterministic), and the C entry points of the
+// image -> visibility -> likelihood path.
+//
+// Reference lines: pdspy/interferometry/interpolate_model.py:11-57 (output layout [nuv,nf],
+// imag sign), pdspy/utils/emcee.py:31-43 (likelihood term), pdspy/interferometry/
+// libinterferometry.pyx:610-633 (chisq).
+#include "dft.cuh"
+#include <algorithm>
+
+struct pdsb_dataset {
+    int64_t nuv = 0, nuvh = 0;
+    int hermitian = 0;
+    double *u = nullptr, *v = nullptr;           // device, unique points [nuvh]
+    int nf = 0;
+    double *re = nullptr, *im = nullptr, *w = nullptr;   // device [nuv, nf]
+    double logsum = 0.0;                         // sum log(w/2pi) over w>0
+    bool has_data = false;
+};
+
+namespace pdsb {
+
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+// ---------------------------------------------------------------------------------
+// Block-level fp64 sum (fixed tree: deterministic for a fixed launch geometry).
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double x, double *sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = x;
+    __syncthreads();
+    double t = 0.0;
+    if (wid == 0) {
+        t = lane < THREADS / 32 ? sh[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    __syncthreads();
+    return t;   // valid in warp 0
+}
+
+// out[c] = sum_b part[b*ncol + c], b in order: one block per column, fixed tree.
+__global__ void __launch_bounds__(256) reduce_columns_kernel(const double *__restrict__ part, int nb, int ncol,
+                                                             double *__restrict__ out)
+{
+    __shared__ double sh[8];
+    const int c = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nb; b += 256) s += part[(size_t)b * ncol + c];
+    s = block_sum<256>(s, sh);
+    if (threadIdx.x == 0) out[c] = s;
+}
+
+// ---------------------------------------------------------------------------------
+// Epilogue tile: 32 unique uv points x 32 channels per block, block = (32, 8).
+// Loads the split partial sums coalesced over k, applies the centre phase
+// G_k = exp(2 pi i (u (xcen - dRA) + v (ycen - dDec))) in fp64, transposes through shared
+// memory so that the [nuv, nf] side is coalesced over channels.
+struct EpiParams {
+    const double2 *part;     // [nsplit][nf][nuvh]
+    int nsplit, nf;
+    int64_t nuvh, nuv;
+    int hermitian;
+    const double *u, *v;     // unique
+    double xs, ys;           // xcen - dRA, ycen - dDec (radians)
+};
+
+__device__ __forceinline__ void epi_load_tile(const EpiParams &P, double2 (*tile)[33])
+{
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t kh = (int64_t)blockIdx.x * 32 + tx;
+    double gs = 0.0, gc = 1.0;
+    if (kh < P.nuvh) {
+        double a = P.u[kh] * P.xs + P.v[kh] * P.ys;
+        sincospi(2.0 * (a - rint(a)), &gs, &gc);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int il = ty + 8 * m;
+        const int i = blockIdx.y * 32 + il;
+        double2 acc = make_double2(0.0, 0.0);
+        if (kh < P.nuvh && i < P.nf) {
+            for (int sp = 0; sp < P.nsplit; sp++) {
+                const double2 p = P.part[((size_t)sp * P.nf + i) * (size_t)P.nuvh + kh];
+                acc.x += p.x;
+                acc.y += p.y;
+            }
+            acc = make_double2(acc.x * gc - acc.y * gs, acc.x * gs + acc.y * gc);
+        }
+        tile[il][tx] = acc;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) finish_vis_kernel(const EpiParams P, double *__restrict__ out_re,
+                                                         double *__restrict__ out_im)
+{
+    __shared__ double2 tile[32][33];
+    epi_load_tile(P, tile);
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.y * 32 + tx;
+    if (i >= P.nf) return;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int kl = ty + 8 * m;
+        const int64_t kh = (int64_t)blockIdx.x * 32 + kl;
+        if (kh >= P.nuvh) continue;
+        const double2 val = tile[tx][kl];
+        out_re[kh * P.nf + i] = val.x;
+        out_im[kh * P.nf + i] = val.y;
+        if (P.hermitian) {
+            out_re[(kh + P.nuvh) * P.nf + i] = val.x;
+            out_im[(kh + P.nuvh) * P.nf + i] = -val.y;
+        }
+    }
+}
+
+// Fused likelihood epilogue: per block and channel, sum_k w ((d.re-m.re)^2 + (d.im-m.im)^2),
+// written to blockpart[blockIdx.x][nf]; reduce_columns_kernel sums over blocks.
+__global__ void __launch_bounds__(256) loglike_epi_kernel(const EpiParams P, const double *__restrict__ d_re,
+                                                          const double *__restrict__ d_im,
+                                                          const double *__restrict__ d_w,
+                                                          double *__restrict__ blockpart)
+{
+    __shared__ double2 tile[32][33];
+    __shared__ double red[8][33];
+    epi_load_tile(P, tile);
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.y * 32 + tx;
+    double s = 0.0;
+    if (i < P.nf) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const int kl = ty + 8 * m;
+            const int64_t kh = (int64_t)blockIdx.x * 32 + kl;
+            if (kh >= P.nuvh) continue;
+            const double2 val = tile[tx][kl];
+            {
+                const int64_t o = kh * P.nf + i;
+                const double a = d_re[o] - val.x, b = d_im[o] - val.y;
+                s += (a * a + b * b) * d_w[o];
+            }
+            if (P.hermitian) {
+                const int64_t o = (kh + P.nuvh) * P.nf + i;
+                const double a = d_re[o] - val.x, b = d_im[o] + val.y;
+                s += (a * a + b * b) * d_w[o];
+            }
+        }
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < P.nf) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) t += red[r][tx];
+        blockpart[(size_t)blockIdx.x * P.nf + i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Likelihood pieces on caller-supplied model arrays (flat [n]).
+// blockpart[b][0..2] = sum (d.re-m.re)^2 w, sum (d.im-m.im)^2 w, sum log(w/2pi) [w>0]
+__global__ void __launch_bounds__(256) chi2_flat_kernel(const double *__restrict__ dre, const double *__restrict__ dim,
+                                                        const double *__restrict__ w, const double *__restrict__ mre,
+                                                        const double *__restrict__ mim, int64_t n,
+                                                        double *__restrict__ blockpart)
+{
+    __shared__ double sh[8];
+    double sr = 0.0, si = 0.0, sl = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
+        const double ww = w[k];
+        const double a = dre[k] - mre[k], b = dim[k] - mim[k];
+        sr += a * a * ww;
+        si += b * b * ww;
+        if (ww > 0.0) sl += log(ww / kTwoPi);
+    }
+    sr = block_sum<256>(sr, sh);
+    si = block_sum<256>(si, sh);
+    sl = block_sum<256>(sl, sh);
+    if (threadIdx.x == 0) {
+        blockpart[(size_t)blockIdx.x * 3 + 0] = sr;
+        blockpart[(size_t)blockIdx.x * 3 + 1] = si;
+        blockpart[(size_t)blockIdx.x * 3 + 2] = sl;
+    }
+}
+
+__global__ void __launch_bounds__(256) logsum_kernel(const double *__restrict__ w, int64_t n,
+                                                     double *__restrict__ blockpart)
+{
+    __shared__ double sh[8];
+    double sl = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
+        const double ww = w[k];
+        if (ww > 0.0) sl += log(ww / kTwoPi);
+    }
+    sl = block_sum<256>(sl, sh);
+    if (threadIdx.x == 0) blockpart[blockIdx.x] = sl;
+}
+
+// chisq(): channel 0 of [nuv, nf]; combined sum, as chisq_calc does.
+__global__ void __launch_bounds__(256) chisq_ch0_kernel(const double *__restrict__ dre, const double *__restrict__ dim,
+                                                        const double *__restrict__ w, const double *__restrict__ mre,
+                                                        const double *__restrict__ mim, int64_t nuv, int nf,
+                                                        double *__restrict__ blockpart)
+{
+    __shared__ double sh[8];
+    double s = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < nuv; k += (int64_t)gridDim.x * 256) {
+        const int64_t o = k * nf;
+        const double a = dre[o] - mre[o], b = dim[o] - mim[o];
+        s += (a * a + b * b) * w[o];
+    }
+    s = block_sum<256>(s, sh);
+    if (threadIdx.x == 0) blockpart[blockIdx.x] = s;
+}
+
+static int reduce_blocks(const double *blockpart, int nb, int ncol, double *out_dev)
+{
+    LaunchScope ls("reduce_columns");
+    reduce_columns_kernel<<<ncol, 256, 0, ctx().stream>>>(blockpart, nb, ncol, out_dev);
+    PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// image (host or device, fp64 [ny,nx,nf]) -> split partial sums on the device.
+struct DftRun {
+    DftGeom g;
+    int nsplit;
+};
+
+static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
+                   DftRun *run)
+{
+    Context &c = ctx();
+    PDSB_REQUIRE(ds && image, "dataset/image");
+    PDSB_REQUIRE(ny > 0 && nx > 0 && nf > 0, "image shape");
+    PDSB_REQUIRE(dxy > 0.0, "dxy");
+    const int variant = dft_pick_variant();
+    const int tcp = dft_variant_tcp(variant);
+    DftGeom g = make_geom(ny, nx, nf, tcp, dxy);
+    const double *img_dev = nullptr;
+    PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
+    PDSB_CHECK(c.folded.ensure(folded_floats(g) * sizeof(float)));
+    PDSB_CHECK(launch_fold(img_dev, c.folded.as<float>(), g));
+    const int nsplit = dft_auto_split(variant, ds->nuvh, nf, g.ntile);
+    PDSB_CHECK(c.partial.ensure((size_t)nsplit * nf * ds->nuvh * sizeof(double2)));
+    DftParams p;
+    p.F = c.folded.as<float>();
+    p.u = ds->u;
+    p.v = ds->v;
+    p.nuvh = ds->nuvh;
+    p.dxy = dxy;
+    p.ntile = g.ntile;
+    p.nchunk = g.nchunk;
+    p.nsplit = nsplit;
+    p.nf = nf;
+    p.hx = g.hx2 ? 0.5 : 0.0;
+    p.hy = g.hy2 ? 0.5 : 0.0;
+    p.part = c.partial.as<double2>();
+    PDSB_CHECK(launch_dft(p, variant, nullptr));
+    run->g = g;
+    run->nsplit = nsplit;
+    return PDSB_OK;
+}
+
+static EpiParams make_epi(const pdsb_dataset *ds, const DftRun &run, double dRA, double dDec)
+{
+    EpiParams e;
+    e.part = ctx().partial.as<double2>();
+    e.nsplit = run.nsplit;
+    e.nf = run.g.nf;
+    e.nuvh = ds->nuvh;
+    e.nuv = ds->nuv;
+    e.hermitian = ds->hermitian;
+    e.u = ds->u;
+    e.v = ds->v;
+    e.xs = run.g.xcen - dRA;
+    e.ys = run.g.ycen - dDec;
+    return e;
+}
+
+// chi2 per channel for one image into chi2_dev[nf] (device)
+static int run_loglike_dev(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind,
+                           double dxy, double dRA, double dDec, double *chi2_dev)
+{
+    Context &c = ctx();
+    PDSB_REQUIRE(ds && ds->has_data, "dataset has no data (call pdsb_dataset_set_data)");
+    PDSB_REQUIRE(nf == ds->nf, "image channel count != dataset channel count");
+    DftRun run;
+    PDSB_CHECK(run_dft(ds, image, ny, nx, nf, image_kind, dxy, &run));
+    EpiParams e = make_epi(ds, run, dRA, dDec);
+    dim3 grid((unsigned)ceil_div(ds->nuvh, 32), (unsigned)ceil_div(nf, 32));
+    PDSB_CHECK(c.red.ensure((size_t)grid.x * nf * sizeof(double)));
+    {
+        LaunchScope ls("loglike_epilogue");
+        loglike_epi_kernel<<<grid, dim3(32, 8), 0, c.stream>>>(e, ds->re, ds->im, ds->w, c.red.as<double>());
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CHECK(reduce_blocks(c.red.as<double>(), (int)grid.x, nf, chi2_dev));
+    return PDSB_OK;
+}
+
+}  // namespace pdsb
+
+using namespace pdsb;
+
+extern "C" {
+
+int pdsb_dataset_create(const double *u, const double *v, int64_t nuv, int kind, pdsb_dataset **out)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(out, "out");
+    *out = nullptr;
+    PDSB_REQUIRE(nuv >= 0 && (nuv == 0 || (u && v)), "u/v/nuv");
+    Context &c = ctx();
+    std::vector<double> hu, hv;
+    const double *pu = u, *pv = v;
+    if (kind == PDSB_DEVICE && nuv > 0) {
+        hu.resize(nuv);
+        hv.resize(nuv);
+        PDSB_CUDA(cudaMemcpyAsync(hu.data(), u, nuv * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(hv.data(), v, nuv * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+        pu = hu.data();
+        pv = hv.data();
+    }
+    // Hermitian doubling (readuvfits.py:68-73): second half == -first half, exactly.
+    int herm = 0;
+    if (nuv >= 2 && nuv % 2 == 0) {
+        herm = 1;
+        const int64_t h = nuv / 2;
+        for (int64_t k = 0; k < h; k++)
+            if (pu[k + h] != -pu[k] || pv[k + h] != -pv[k]) {
+                herm = 0;
+                break;
+            }
+    }
+    pdsb_dataset *ds = new pdsb_dataset();
+    ds->nuv = nuv;
+    ds->hermitian = herm;
+    ds->nuvh = herm ? nuv / 2 : nuv;
+    if (ds->nuvh > 0) {
+        if (cudaMalloc(&ds->u, ds->nuvh * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&ds->v, ds->nuvh * sizeof(double)) != cudaSuccess) {
+            set_error("cudaMalloc of uv arrays failed");
+            cudaGetLastError();
+            pdsb_dataset_destroy(ds);
+            return PDSB_ERR_NOMEM;
+        }
+        PDSB_CUDA(cudaMemcpyAsync(ds->u, pu, ds->nuvh * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(ds->v, pv, ds->nuvh * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    *out = ds;
+    return PDSB_OK;
+}
+
+int pdsb_dataset_set_data(pdsb_dataset *ds, const double *real, const double *imag, const double *weights, int nf,
+                          int kind)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ds && real && imag && weights && nf > 0, "dataset/data");
+    Context &c = ctx();
+    const size_t n = (size_t)ds->nuv * nf;
+    if (ds->has_data) {
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+        cudaFree(ds->re);
+        cudaFree(ds->im);
+        cudaFree(ds->w);
+        ds->re = ds->im = ds->w = nullptr;
+        ds->has_data = false;
+    }
+    ds->nf = nf;
+    if (n == 0) {
+        ds->logsum = 0.0;
+        ds->has_data = true;
+        return PDSB_OK;
+    }
+    if (cudaMalloc(&ds->re, n * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&ds->im, n * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&ds->w, n * sizeof(double)) != cudaSuccess) {
+        set_error("cudaMalloc of data arrays (%zu doubles each) failed", n);
+        cudaGetLastError();
+        return PDSB_ERR_NOMEM;
+    }
+    cudaMemcpyKind mk = kind == PDSB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    PDSB_CUDA(cudaMemcpyAsync(ds->re, real, n * sizeof(double), mk, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(ds->im, imag, n * sizeof(double), mk, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(ds->w, weights, n * sizeof(double), mk, c.stream));
+    // data-only constant of the likelihood
+    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (int64_t)((n + 255) / 256));
+    PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * sizeof(double)));
+    {
+        LaunchScope ls("logsum");
+        logsum_kernel<<<nb, 256, 0, c.stream>>>(ds->w, (int64_t)n, c.red.as<double>());
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CHECK(reduce_blocks(c.red.as<double>(), nb, 1, c.red.as<double>() + nb));
+    PDSB_CUDA(cudaMemcpyAsync(&ds->logsum, c.red.as<double>() + nb, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    ds->has_data = true;
+    return PDSB_OK;
+}
+
+int pdsb_dataset_info(const pdsb_dataset *ds, int64_t *nuv, int64_t *nuv_unique, int *nf, int *hermitian)
+{
+    PDSB_REQUIRE(ds, "dataset");
+    if (nuv) *nuv = ds->nuv;
+    if (nuv_unique) *nuv_unique = ds->nuvh;
+    if (nf) *nf = ds->nf;
+    if (hermitian) *hermitian = ds->hermitian;
+    return PDSB_OK;
+}
+
+int pdsb_dataset_destroy(pdsb_dataset *ds)
+{
+    if (!ds) return PDSB_OK;
+    if (ctx().inited) cudaStreamSynchronize(ctx().stream);
+    cudaFree(ds->u);
+    cudaFree(ds->v);
+    cudaFree(ds->re);
+    cudaFree(ds->im);
+    cudaFree(ds->w);
+    delete ds;
+    return PDSB_OK;
+}
+
+int pdsb_sample_image(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
+                      double dRA, double dDec, double *out_real, double *out_imag, int out_kind)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ds && out_real && out_imag, "dataset/outputs");
+    Context &c = ctx();
+    if (ds->nuv == 0) return PDSB_OK;
+    DftRun run;
+    PDSB_CHECK(run_dft(ds, image, ny, nx, nf, image_kind, dxy, &run));
+    EpiParams e = make_epi(ds, run, dRA, dDec);
+    const size_t bytes = (size_t)ds->nuv * nf * sizeof(double);
+    double *ore = out_real, *oim = out_imag;
+    if (out_kind == PDSB_HOST) {
+        PDSB_CHECK(c.stage_a.ensure(bytes));
+        PDSB_CHECK(c.stage_b.ensure(bytes));
+        ore = c.stage_a.as<double>();
+        oim = c.stage_b.as<double>();
+    }
+    dim3 grid((unsigned)ceil_div(ds->nuvh, 32), (unsigned)ceil_div(nf, 32));
+    {
+        LaunchScope ls("finish_vis");
+        finish_vis_kernel<<<grid, dim3(32, 8), 0, c.stream>>>(e, ore, oim);
+        PDSB_CUDA(cudaGetLastError());
+    }
+    if (out_kind == PDSB_HOST) {
+        PDSB_CUDA(cudaMemcpyAsync(out_real, ore, bytes, cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, bytes, cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return PDSB_OK;
+}
+
+static int loglike_impl(pdsb_dataset *ds, const double *images, int nwalkers, int ny, int nx, int nf,
+                        int image_kind, double dxy, const double *dRA, const double *dDec, double *chi2,
+                        double *lnlike)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ds && images && dRA && dDec && nwalkers > 0, "arguments");
+    PDSB_REQUIRE(chi2 || lnlike, "no output requested");
+    PDSB_REQUIRE(ds->has_data, "dataset has no data (call pdsb_dataset_set_data)");
+    PDSB_REQUIRE(nf == ds->nf, "image channel count != dataset channel count");
+    Context &c = ctx();
+    std::vector<double> h((size_t)nwalkers * nf, 0.0);
+    if (ds->nuv > 0) {
+        PDSB_CHECK(c.stage_c.ensure((size_t)nwalkers * nf * sizeof(double)));
+        double *chi2_dev = c.stage_c.as<double>();
+        const size_t cube = (size_t)ny * nx * nf;
+        for (int wk = 0; wk < nwalkers; wk++)
+            PDSB_CHECK(run_loglike_dev(ds, images + (size_t)wk * cube, ny, nx, nf, image_kind, dxy, dRA[wk],
+                                       dDec[wk], chi2_dev + (size_t)wk * nf));
+        PDSB_CUDA(cudaMemcpyAsync(h.data(), chi2_dev, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    for (int wk = 0; wk < nwalkers; wk++) {
+        double s = 0.0;
+        for (int i = 0; i < nf; i++) {
+            s += h[(size_t)wk * nf + i];
+            if (chi2) chi2[(size_t)wk * nf + i] = h[(size_t)wk * nf + i];
+        }
+        // emcee.py:31-43: -0.5 chi2_re - L - 0.5 chi2_im - L
+        if (lnlike) lnlike[wk] = -0.5 * s - 2.0 * ds->logsum;
+    }
+    return PDSB_OK;
+}
+
+int pdsb_loglike(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
+                 double dRA, double dDec, double *chi2, double *lnlike)
+{
+    return loglike_impl(ds, image, 1, ny, nx, nf, image_kind, dxy, &dRA, &dDec, chi2, lnlike);
+}
+
+int pdsb_loglike_batch(pdsb_dataset *ds, const double *images, int nwalkers, int ny, int nx, int nf, int image_kind,
+                       double dxy, const double *dRA, const double *dDec, double *lnlike)
+{
+    return loglike_impl(ds, images, nwalkers, ny, nx, nf, image_kind, dxy, dRA, dDec, nullptr, lnlike);
+}
+
+int pdsb_chi2(const double *d_real, const double *d_imag, const double *weights, const double *m_real,
+              const double *m_imag, int64_t n, int kind, double *out)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(out && n >= 0, "out/n");
+    Context &c = ctx();
+    if (n == 0) {
+        out[0] = out[1] = out[2] = 0.0;
+        out[3] = -0.0;
+        return PDSB_OK;
+    }
+    PDSB_REQUIRE(d_real && d_imag && weights && m_real && m_imag, "arrays");
+    const size_t bytes = (size_t)n * sizeof(double);
+    const double *a, *b, *w, *mr, *mi;
+    PDSB_CHECK(to_device(d_real, kind, bytes, c.stage_a, (const void **)&a));
+    PDSB_CHECK(to_device(d_imag, kind, bytes, c.stage_b, (const void **)&b));
+    PDSB_CHECK(to_device(weights, kind, bytes, c.stage_c, (const void **)&w));
+    PDSB_CHECK(to_device(m_real, kind, bytes, c.stage_d, (const void **)&mr));
+    PDSB_CHECK(to_device(m_imag, kind, bytes, c.stage_e, (const void **)&mi));
+    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (n + 255) / 256);
+    PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * 3 * sizeof(double)));
+    {
+        LaunchScope ls("chi2_flat");
+        chi2_flat_kernel<<<nb, 256, 0, c.stream>>>(a, b, w, mr, mi, n, c.red.as<double>());
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CHECK(reduce_blocks(c.red.as<double>(), nb, 3, c.red.as<double>() + (size_t)nb * 3));
+    double h[3];
+    PDSB_CUDA(cudaMemcpyAsync(h, c.red.as<double>() + (size_t)nb * 3, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    out[0] = h[0];
+    out[1] = h[1];
+    out[2] = h[2];
+    out[3] = -0.5 * h[0] - h[2] + -0.5 * h[1] - h[2];
+    return PDSB_OK;
+}
+
+int pdsb_chisq(const double *d_real, const double *d_imag, const double *weights, const double *m_real,
+               const double *m_imag, int64_t nuv, int nf, int kind, float *out)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(out && nuv >= 0 && nf > 0, "out/nuv/nf");
+    Context &c = ctx();
+    if (nuv == 0) {
+        *out = 0.f;
+        return PDSB_OK;
+    }
+    PDSB_REQUIRE(d_real && d_imag && weights && m_real && m_imag, "arrays");
+    const size_t bytes = (size_t)nuv * nf * sizeof(double);
+    const double *a, *b, *w, *mr, *mi;
+    PDSB_CHECK(to_device(d_real, kind, bytes, c.stage_a, (const void **)&a));
+    PDSB_CHECK(to_device(d_imag, kind, bytes, c.stage_b, (const void **)&b));
+    PDSB_CHECK(to_device(weights, kind, bytes, c.stage_c, (const void **)&w));
+    PDSB_CHECK(to_device(m_real, kind, bytes, c.stage_d, (const void **)&mr));
+    PDSB_CHECK(to_device(m_imag, kind, bytes, c.stage_e, (const void **)&mi));
+    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (nuv + 255) / 256);
+    PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * sizeof(double)));
+    {
+        LaunchScope ls("chisq_ch0");
+        chisq_ch0_kernel<<<nb, 256, 0, c.stream>>>(a, b, w, mr, mi, nuv, nf, c.red.as<double>());
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CHECK(reduce_blocks(c.red.as<double>(), nb, 1, c.red.as<double>() + nb));
+    double h;
+    PDSB_CUDA(cudaMemcpyAsync(&h, c.red.as<double>() + nb, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    *out = (float)h;      // libinterferometry.pyx:616 `cdef float chisq_calc`
+    return PDSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,5 @@
+"""GPU drop-ins for the hot-path members of pdspy.interferometry
+(pdspy/interferometry/__init__.py:1-18): same names and call signatures."""
+from .visibilities import Visibilities, VisibilitiesObject
+from .interpolate_model import interpolate_model, loglike_image, loglike_images
+from .grid import grid, freqcorrect, chisq

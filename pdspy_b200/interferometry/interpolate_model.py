@@ -1,0 +1,106 @@
+"""interpolate_model: image cube -> model visibilities at (u, v), on the GPU.
+
+Drop-in for pdspy/interferometry/interpolate_model.py:11-57 (same name, positional and keyword
+arguments, return type).  The reference hands the arithmetic to galario (FFT + bilinear
+interpolation, :23-24); here `code="galario"` selects the exact direct transform on the GPU
+(include/pdsb.h:pdsb_sample_image), which is what galario's interpolation approximates, in the
+same conventions (row flip :23, dxy from model.x :20, arcsec-scaled dRA/dDec :24, imag -> -imag
+:27, unit weights :57)."""
+import ctypes
+
+import numpy
+
+from ..constants import arcsec
+from .. import _lib
+from ..device import dataset_for
+from .visibilities import Visibilities
+
+
+def _cube(model):
+    image = model.image
+    if image.ndim != 4:
+        raise ValueError("model.image must be [ny, nx, nfreq, npol]")
+    if image.shape[3] != 1:
+        image = image[:, :, :, 0:1]          # the reference reads polarisation 0 (:23)
+    return numpy.ascontiguousarray(image, dtype=numpy.float64)
+
+
+def interpolate_model(u, v, freq, model, nthreads=1, dRA=0., dDec=0.,
+                      code="galario", nxy=1024, dxy=0.01):
+
+    if code == "galario":
+        # nthreads is galario's OpenMP thread count (:18); the GPU path has no use for it.
+        dxy = (model.x[1] - model.x[0]) * arcsec
+
+        image = _cube(model)
+        ny, nx, nf = image.shape[:3]
+        if nf != len(model.freq):
+            raise ValueError("model.image has %d channels but model.freq has %d" % (nf, len(model.freq)))
+
+        u = numpy.ascontiguousarray(u, dtype=numpy.float64)
+        v = numpy.ascontiguousarray(v, dtype=numpy.float64)
+        ds = dataset_for(u, v)
+
+        real = numpy.empty((u.size, nf))
+        imag = numpy.empty((u.size, nf))
+        if u.size > 0:
+            L = _lib.lib()
+            _lib.check(L.pdsb_sample_image(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST,
+                                           float(dxy), float(dRA * arcsec), float(dDec * arcsec),
+                                           _lib.ptr(real), _lib.ptr(imag), _lib.HOST))
+
+    elif code in ("galario-unstructured", "trift"):
+        raise NotImplementedError(
+            "code=%r (unstructured images, interpolate_model.py:32-55) is not on the B200 path yet; "
+            "see DESIGN.md 'next'" % code)
+    else:
+        # the reference falls through to an UnboundLocalError on `real`; be explicit instead
+        raise ValueError("unknown code %r" % (code,))
+
+    return Visibilities(u, v, freq, real, imag, numpy.ones(real.shape))
+
+
+def loglike_image(data, model, dRA=0., dDec=0.):
+    """Fused interpolate_model + visibility log-likelihood term (pdspy/utils/emcee.py:31-43) for
+    one dataset: the model visibilities never leave the GPU.  `data` is a Visibilities with
+    u, v, real, imag, weights; `model` an Image.  Returns (lnlike, chi2_per_channel)."""
+    dxy = (model.x[1] - model.x[0]) * arcsec
+    image = _cube(model)
+    ny, nx, nf = image.shape[:3]
+    ds = dataset_for(data.u, data.v, (data.real, data.imag, data.weights))
+    chi2 = numpy.empty(nf)
+    out = ctypes.c_double()
+    L = _lib.lib()
+    _lib.check(L.pdsb_loglike(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST, float(dxy),
+                              float(dRA * arcsec), float(dDec * arcsec), _lib.ptr(chi2),
+                              ctypes.cast(ctypes.byref(out), ctypes.c_void_p)))
+    return out.value, chi2
+
+
+def loglike_images(data, models, dRA, dDec, pixelsize=None):
+    """Walker batch: `models` is a sequence of Images of identical shape, or one array
+    [W, ny, nx, nf] with `pixelsize` (arcsec) given; dRA, dDec per walker (arcsec).
+    Returns lnlike[W]."""
+    if isinstance(models, numpy.ndarray):
+        cubes = numpy.ascontiguousarray(models, dtype=numpy.float64)
+        if cubes.ndim != 4:
+            raise ValueError("cube batch must be [W, ny, nx, nf]")
+        if pixelsize is None:
+            raise ValueError("pixelsize (arcsec) is required with a raw cube batch")
+        dxy = pixelsize * arcsec
+    else:
+        cubes = numpy.stack([_cube(m)[:, :, :, 0] for m in models])
+        dxy = (models[0].x[1] - models[0].x[0]) * arcsec
+    return _loglike_batch(data, cubes, dxy, dRA, dDec)
+
+
+def _loglike_batch(data, cubes, dxy, dRA, dDec):
+    W, ny, nx, nf = cubes.shape
+    dRA = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(dRA, dtype=numpy.float64) * arcsec, (W,)))
+    dDec = numpy.ascontiguousarray(numpy.broadcast_to(numpy.asarray(dDec, dtype=numpy.float64) * arcsec, (W,)))
+    ds = dataset_for(data.u, data.v, (data.real, data.imag, data.weights))
+    out = numpy.empty(W)
+    L = _lib.lib()
+    _lib.check(L.pdsb_loglike_batch(ds.handle, _lib.ptr(cubes), W, ny, nx, nf, _lib.HOST, float(dxy),
+                                    _lib.ptr(dRA), _lib.ptr(dDec), _lib.ptr(out)))
+    return out
