@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: the fused model-to-visibility likelihood on synthetic data of the shapes
+BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2] [--impl reference]
+
+N > 1 is launched by the driver as
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+one rank per GPU; the uv list is sharded over ranks (strong scaling: the likelihood of ONE
+dataset), the image cube is replicated, and chi^2[nf] + the log term are all-reduced over NCCL.
+
+A step = one likelihood evaluation: fold the fp64 cube -> direct Fourier sampling at every uv
+point -> weighted chi^2 against the data -> scalar (pdspy: interpolate_model.py:11-57 followed by
+utils/emcee.py:31-43).  Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement".
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from pdspy_b200 import synth                      # noqa: E402
+
+A = synth.ARCSEC
+METRIC = "pixel_visibility_pairs_per_s"
+UNIT = "pairs/s"
+FLOP_PER_PAIR = 4.0          # algorithmic: 2 FMA per (pixel, uv, channel) pair
+L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
+
+
+def workload_config(name, nuv_override=None):
+    n, nf, nuv, px, dra, ddec = synth.CONFIGS[name]
+    if nuv_override:
+        nuv = nuv_override
+    return dict(name=name, npix=n, nf=nf, nuv=nuv, pixelsize=px, dRA=dra, dDec=ddec)
+
+
+def describe(cfg, world):
+    names = {"C3": "spectral-line cube 512x512x64 channels, 1M uv per channel, full chi^2 log-likelihood "
+                   "(BASELINE.json configs[2])",
+             "C2": "continuum 1024x1024 image onto 1M uv points with dRA/dDec offset + chi^2 "
+                   "(BASELINE.json configs[1])",
+             "C1": "256x256 single channel onto 50k uv points (BASELINE.json configs[0])"}
+    return {"workload": names[cfg["name"]], "npix": cfg["npix"], "channels": cfg["nf"], "nuv": cfg["nuv"],
+            "pairs_per_step": float(cfg["npix"]) ** 2 * cfg["nuv"] * cfg["nf"],
+            "partition": "uv points sharded over %d rank(s), cube replicated, all-reduce of nf+1 doubles" % world,
+            "cache": "L2 flushed (256 MB memset) before every timed step",
+            "uv": "Hermitian-doubled synthetic ALMA-like list, seed 1234 (pdspy_b200/synth.py)"}
+
+
+def make_local_data(cfg, rank, world):
+    """This rank's uv shard + synthetic data for it (noise only; the value is irrelevant to timing)."""
+    from pdspy_b200 import dist
+    u, v = synth.synth_uv(cfg["nuv"], cfg["pixelsize"] * A)
+    rows = dist.shard_rows(u, v, rank, world)
+    us, vs = np.ascontiguousarray(u[rows]), np.ascontiguousarray(v[rows])
+    re, im, w = synth.synth_data(us.size, cfg["nf"], seed=4321 + 1000 * rank + world)
+    freq = synth.synth_freq(cfg["nf"])
+    from pdspy_b200.interferometry import Visibilities
+    return Visibilities(us, vs, freq, re, im, w), (u, v)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            # "under load": samples at or above the median (the idle edges are below it)
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": float(max(power))}
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, cfg, rank, world):
+    """Reference arm: the reference's CPU path for this workload on the host cores.  galario (the
+    library pdspy calls, interpolate_model.py:23-24) is not installable here, so its algorithm is
+    timed from the restatement oracle/dft.py:galario_like (rfft2 + bilinear + phase, per channel as
+    interpolate_model.py:22 loops), followed by the verbatim numpy likelihood (emcee.py:31-43).
+    Bounded sample per step: NCH_SAMPLE of the channels, all uv points, all pixels."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import dft as od, likelihood as ol
+    cores = os.cpu_count() or 1
+    nch = min(cfg["nf"], 8)
+    u, v = synth.synth_uv(cfg["nuv"], cfg["pixelsize"] * A)
+    img = synth.synth_image(cfg["npix"], cfg["nf"], cfg["pixelsize"])[:, :, :nch, :]
+    re, im, w = synth.synth_data(cfg["nuv"], nch)
+    dxy = cfg["pixelsize"] * A
+    threads = min(cores, nch)
+
+    def one_channel(i):
+        return od.galario_like(u, v, img[:, :, i:i + 1, :], dxy, cfg["dRA"] * A, cfg["dDec"] * A)[:, 0]
+
+    def step():
+        with ThreadPoolExecutor(threads) as ex:
+            cols = list(ex.map(one_channel, range(nch)))
+        vis = np.stack(cols, axis=1)
+        return ol.lnlike_vis_numpy(re, im, w, vis.real, vis.imag)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    pairs = float(cfg["npix"]) ** 2 * cfg["nuv"] * nch * args.steps
+    value = pairs / dt
+    sample = "%d of %d channels, all %d uv points, all pixels per step" % (nch, cfg["nf"], cfg["nuv"])
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": describe(cfg, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "what": "galario algorithm (rfft2 + bilinear interpolation, restated: galario itself is "
+                                     "not installable offline) + numpy likelihood; pairs/s counts the pixel-visibility "
+                                     "pairs the result represents, not operations executed (the FFT path is "
+                                     "O(n^2 log n + nuv))"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "likelihood_evals_per_s_equiv": args.steps / dt * nch / cfg["nf"]}
+    print(json.dumps(line))
+
+
+def cpu_baseline_port(cfg):
+    """The like-for-like algorithm on the host: exact fp64 direct DFT (oracle/c/oracle.c, OpenMP, all
+    cores) + likelihood on a bounded sample of the uv points (all pixels, all channels)."""
+    from oracle.build import lib as olib
+    from oracle import likelihood as ol
+    L = olib()
+    cores = L.oracle_num_threads()
+    nuv_s = {"C3": 384, "C2": 4096, "C1": 20000}[cfg["name"]]
+    u, v = synth.synth_uv(cfg["nuv"], cfg["pixelsize"] * A)
+    u, v = np.ascontiguousarray(u[:nuv_s]), np.ascontiguousarray(v[:nuv_s])
+    img = np.ascontiguousarray(synth.synth_image(cfg["npix"], cfg["nf"], cfg["pixelsize"])[:, :, :, 0])
+    re, im, w = synth.synth_data(nuv_s, cfg["nf"])
+    ore, oim = np.empty((nuv_s, cfg["nf"])), np.empty((nuv_s, cfg["nf"]))
+    p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    t0 = time.perf_counter()
+    L.oracle_dft(p(u), p(v), nuv_s, p(img), cfg["npix"], cfg["npix"], cfg["nf"], cfg["pixelsize"] * A,
+                 cfg["dRA"] * A, cfg["dDec"] * A, p(ore), p(oim))
+    ol.lnlike_vis_numpy(re, im, w, ore, oim)
+    dt = time.perf_counter() - t0
+    pairs = float(cfg["npix"]) ** 2 * nuv_s * cfg["nf"]
+    return {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+            "sample": "first %d of %d uv points, all pixels, all %d channels, one pass (exact fp64 direct DFT, "
+                      "one sincos per pixel-visibility pair, OpenMP)" % (nuv_s, cfg["nuv"], cfg["nf"])}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3"])
+    ap.add_argument("--nuv", type=int, default=0, help="override the uv count (testing)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = workload_config(args.workload, args.nuv or None)
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    os.environ["PDSB_DEVICE"] = str(local_rank)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from pdspy_b200 import _lib, DeviceBuffer, PinnedArray
+    from pdspy_b200.dist import ShardedLikelihood
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    data, _ = make_local_data(cfg, rank, world)
+    like = ShardedLikelihood(data)            # uploads the shard; libpdsb now runs on torch's stream
+    n, nf = cfg["npix"], cfg["nf"]
+    cube = np.ascontiguousarray(synth.synth_image(n, nf, cfg["pixelsize"])[:, :, :, 0])     # [n, n, nf] fp64
+    dxy, dra, ddec = cfg["pixelsize"] * A, cfg["dRA"] * A, cfg["dDec"] * A
+    dcube = DeviceBuffer.from_numpy(cube)
+    pinned = PinnedArray(cube.shape)
+    pinned.array[...] = cube
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    pairs_step = float(n) * n * cfg["nuv"] * nf
+
+    def step_device():
+        return like(dcube, dxy, dra, ddec, kind=_lib.DEVICE, shape=(n, n))
+
+    def step_e2e():
+        return like(pinned.array, dxy, dra, ddec, kind=_lib.HOST)
+
+    # ---- device-resident leg: `value` ----
+    for _ in range(args.warmup):
+        flush.zero_()
+        ll = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.check(L.pdsb_profile_reset())
+    _lib.check(L.pdsb_profile_enable(1))
+    n0 = ctypes.c_int64()
+    L.pdsb_launch_count(ctypes.byref(n0))
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for e0, e1 in evs:
+        flush.zero_()
+        e0.record()
+        ll = step_device()
+        e1.record()
+    barrier()
+    n1 = ctypes.c_int64()
+    L.pdsb_launch_count(ctypes.byref(n1))
+    _lib.check(L.pdsb_profile_enable(0))
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    dft_ms, dft_n = ctypes.c_double(), ctypes.c_int64()
+    _lib.check(L.pdsb_profile_get(b"dft_", ctypes.byref(dft_ms), ctypes.byref(dft_n)))
+    t = torch.tensor([total_ms, dft_ms.value], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, dft_ms_max = float(t[0]), float(t[1])
+
+    # ---- end-to-end leg: host cube (pinned) -> H2D -> fold/DFT/chi^2 -> all-reduce -> host scalar ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ll_e2e = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+
+    if rank == 0:
+        sm, khz = ctypes.c_int(), ctypes.c_int()
+        L.pdsb_device_info(ctypes.byref(sm), ctypes.byref(khz), None, None, None)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max_mhz = peaks.get("sm_max_mhz") or khz.value / 1e3
+        fp32_peak = sm.value * 128 * 2 * sm_max_mhz * 1e6 / 1e12          # TFLOP/s, non-tensor FMA pipe
+        tf, ms = ctypes.c_double(), ctypes.c_double()
+        _lib.check(L.pdsb_bench_fma(1, 20000, ctypes.byref(tf), ctypes.byref(ms)))
+        hermitian = like.ds.hermitian
+        pairs_launch = float(n) * n * nf * like.ds.nuv                    # this rank's share, per launch
+        dft_avg_ms = dft_ms_max / max(dft_n.value, 1)
+        achieved = pairs_launch * FLOP_PER_PAIR / (dft_avg_ms * 1e-3) / 1e12
+        executed_flop = pairs_launch * (0.5 if hermitian else 1.0) * 2.0   # 1 FMA per pixel per unique uv
+        executed = executed_flop / (dft_avg_ms * 1e-3) / 1e12
+        value = pairs_step * args.steps / (total_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 products, f64 phase seeds and accumulation",
+            "data": "synthetic", "config": describe(cfg, world),
+            "likelihood_evals_per_s": args.steps / (total_ms * 1e-3),
+            "lnlike": ll,
+            "e2e": {"value": pairs_step * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(cube.nbytes), "d2h_bytes_per_step": int((nf + 1) * 8),
+                    "ms_per_step": e2e_s / args.steps * 1e3, "likelihood_evals_per_s": args.steps / e2e_s,
+                    "api": "pdspy_b200.dist.ShardedLikelihood.__call__ (host fp64 cube in, host scalar out)",
+                    "timer": "host wall clock around K synchronous calls, max over ranks"},
+            "gpu_launches": int(n1.value - n0.value),
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "dft_kernel (direct Fourier sampling, FP32 FMA pipe; no tensor cores)",
+                "bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp32_peak,
+                "peak_source": "nominal non-tensor FP32: SMs x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has "
+                               "no FP32 entry; its sm_max_mhz is used)",
+                "peak_measured_fma_microbench": tf.value,
+                "algorithmic_flop_per_pair": FLOP_PER_PAIR,
+                "executed": executed, "executed_frac": executed / fp32_peak,
+                "executed_note": "FMA-pipe flops the inner loop actually issues per launch: the real-image mirror "
+                                 "fold needs 1 FMA per pixel per uv point instead of 2, and a Hermitian-doubled uv "
+                                 "list is evaluated for one half; frac > 1 is those two algorithmic savings, "
+                                 "executed_frac is the pipe utilisation",
+                "launch_ms": dft_avg_ms, "launches": int(dft_n.value), "traffic": None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_port(cfg)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

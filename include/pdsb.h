@@ -123,6 +123,12 @@ int pdsb_sample_image(pdsb_dataset *ds, const double *image, int ny, int nx, int
  * Outputs are host doubles.  nf must equal the dataset's nf. */
 int pdsb_loglike(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind,
                  double dxy, double dRA, double dDec, double *chi2, double *lnlike);
+/* Asynchronous variant for multi-GPU runs: chi2 per channel is left in DEVICE memory
+ * (chi2_dev[nf]) on the library stream, ready for an NCCL all-reduce over uv shards; no host
+ * synchronisation.  pdsb_dataset_logsum returns this shard's L. */
+int pdsb_loglike_device(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind,
+                        double dxy, double dRA, double dDec, double *chi2_dev);
+int pdsb_dataset_logsum(const pdsb_dataset *ds, double *logsum);
 /* nwalkers cubes [W, ny, nx, nf] against one dataset; dRA/dDec per walker [W] (host). */
 int pdsb_loglike_batch(pdsb_dataset *ds, const double *images, int nwalkers, int ny, int nx, int nf,
                        int image_kind, double dxy, const double *dRA, const double *dDec,

@@ -118,6 +118,14 @@ double oracle_loglike(const double *dre, const double *dim, const double *w,
  * integer literal exponent under cdef double (pow(x,k) calls); the live reference is
  * built with -ffast-math so its last bits are compiler-dependent: expsinc is
  * compared at 1e-12 relative, pillbox bit for bit. */
+static size_t binned_index(uint32_t j, uint32_t i, int n, int G, int nch, int spectral)
+{
+    size_t q = ((size_t)j * G + i) * nch + (size_t)n;     /* what [l,m,n] addresses */
+    if (spectral) return q;
+    if (q >= (size_t)G * G) q = (size_t)j * G + i;
+    return q;
+}
+
 static double o_sinc(double x)
 {
     double xp = x * M_PI;
@@ -156,8 +164,10 @@ double oracle_kernel(int conv, double u, double v) { return conv ? o_exp_sinc(u,
  *   weights [nuv,nf] is MODIFIED in place by the re-weighting, as in the reference.
  * new_* are [G,G,nch] zero-initialised by the caller.
  * The reference indexes binned_weights[l,m,n] with the data channel n even in
- * continuum mode where the last dim is 1 (:472,:485) - out of bounds unless nf==1;
- * this restatement uses channel 0 there (identical when nf==1, the only defined case). */
+ * continuum mode where the last dim is 1 (:472,:485; boundscheck is off, :313).  In the
+ * contiguous [G,G,1] array that reads flat element (l*G+m)+n, i.e. the cell n columns
+ * further on: replicated here (checked against the live module); past the end of the
+ * array, where the reference reads foreign memory, channel 0 of the home cell is used. */
 void oracle_grid_core(const double *u, const double *v, const double *freq,
                       const double *real, const double *imag, double *weights,
                       int64_t nuv, int nf, const uint32_t *ii, const uint32_t *jj,
@@ -201,8 +211,7 @@ void oracle_grid_core(const double *u, const double *v, const double *freq,
             for (int64_t k = 0; k < nuv; k++)
                 for (int n = 0; n < nf; n++) {
                     if (!good[k * nf + n]) continue;
-                    int c = spectral ? n : 0;
-                    weights[k * nf + n] /= binned[((size_t)jj[k * nf + n] * G + ii[k * nf + n]) * nch + c];
+                    weights[k * nf + n] /= binned[binned_index(jj[k * nf + n], ii[k * nf + n], n, G, nch, spectral)];
                 }
         } else {
             /* f2 = (5*10**(-robust))**2 / ((binned**2).sum(axis=(0,1)) / weights.sum(axis=0))  :476-477
@@ -220,9 +229,8 @@ void oracle_grid_core(const double *u, const double *v, const double *freq,
             for (int64_t k = 0; k < nuv; k++)
                 for (int n = 0; n < nf; n++) {
                     if (!good[k * nf + n]) continue;
-                    int c = spectral ? n : 0;
                     weights[k * nf + n] /=
-                        (1 + f2[n] * binned[((size_t)jj[k * nf + n] * G + ii[k * nf + n]) * nch + c]);
+                        (1 + f2[n] * binned[binned_index(jj[k * nf + n], ii[k * nf + n], n, G, nch, spectral)]);
                 }
             free(f2);
         }

@@ -53,6 +53,8 @@ SIGNATURES = {
     "pdsb_dataset_destroy": [_P],
     "pdsb_sample_image": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _P, _c_int],
     "pdsb_loglike": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _P],
+    "pdsb_loglike_device": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P],
+    "pdsb_dataset_logsum": [_P, ctypes.POINTER(_c_dbl)],
     "pdsb_loglike_batch": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl, _P, _P, _P],
     "pdsb_chi2": [_P, _P, _P, _P, _P, _c_i64, _c_int, _P],
     "pdsb_chisq": [_P, _P, _P, _P, _P, _c_i64, _c_int, _c_int, ctypes.POINTER(ctypes.c_float)],

@@ -389,7 +389,12 @@ __global__ void __launch_bounds__(256) grid_reweight_kernel(GridParams P, const 
     if (idx >= P.nuv * P.nf) return;
     if (!P.good[idx]) return;
     const int n = (int)(idx % P.nf);
-    const double b = binned[((int64_t)P.gj[idx] * P.G + P.gi[idx]) * P.nch + (P.spectral ? n : 0)];
+    // The reference addresses binned_weights[l,m,n] with the DATA channel n even in continuum
+    // mode, where the last dimension is 1 (:472,:485, bounds checks off): in the contiguous array
+    // that is flat element (l*G+m)+n.  Replicated; past the end, channel 0 of the home cell.
+    int64_t q = ((int64_t)P.gj[idx] * P.G + P.gi[idx]) * P.nch + n;
+    if (!P.spectral && q >= (int64_t)P.G * P.G) q = (int64_t)P.gj[idx] * P.G + P.gi[idx];
+    const double b = binned[q];
     if (f2) P.w[idx] = P.w[idx] / __dadd_rn(1.0, __dmul_rn(f2[n], b));
     else P.w[idx] = P.w[idx] / b;
 }

@@ -500,6 +500,27 @@ int pdsb_loglike(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, 
     return loglike_impl(ds, image, 1, ny, nx, nf, image_kind, dxy, &dRA, &dDec, chi2, lnlike);
 }
 
+int pdsb_loglike_device(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
+                        double dRA, double dDec, double *chi2_dev)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ds && image && chi2_dev, "arguments");
+    PDSB_REQUIRE(ds->has_data, "dataset has no data (call pdsb_dataset_set_data)");
+    if (ds->nuv == 0) {
+        PDSB_CUDA(cudaMemsetAsync(chi2_dev, 0, (size_t)nf * sizeof(double), ctx().stream));
+        return PDSB_OK;
+    }
+    return run_loglike_dev(ds, image, ny, nx, nf, image_kind, dxy, dRA, dDec, chi2_dev);
+}
+
+int pdsb_dataset_logsum(const pdsb_dataset *ds, double *logsum)
+{
+    PDSB_REQUIRE(ds && logsum, "arguments");
+    PDSB_REQUIRE(ds->has_data, "dataset has no data");
+    *logsum = ds->logsum;
+    return PDSB_OK;
+}
+
 int pdsb_loglike_batch(pdsb_dataset *ds, const double *images, int nwalkers, int ny, int nx, int nf, int image_kind,
                        double dxy, const double *dRA, const double *dDec, double *lnlike)
 {

@@ -1,0 +1,107 @@
+"""Multi-GPU partitioning of the likelihood.
+
+One process per GPU.  The uv list is split across ranks; every rank holds the whole image cube
+(it is small: 67 MB fp32 for 512^2 x 64) and computes chi^2[nf] over its uv shard; the only
+exchange is one all-reduce of nf + 1 doubles (chi^2 per channel and the data-only log term).
+Walker batches are split by walker and need no reduction at all.
+
+Host logic only: works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU
+tests)."""
+import numpy as np
+
+
+def is_hermitian_doubled(u, v):
+    n = u.size
+    if n < 2 or n % 2:
+        return False
+    h = n // 2
+    return bool(np.array_equal(u[h:], -u[:h]) and np.array_equal(v[h:], -v[:h]))
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous, balanced [start, end) of n items for `rank` of `world`."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_rows(u, v, rank, world):
+    """Row indices of this rank's uv shard.  A Hermitian-doubled list (readuvfits.py:68-73) is
+    split by baseline so that each shard is again [half, -half] and the device can keep folding
+    it; anything else is split into contiguous chunks."""
+    n = u.size
+    if is_hermitian_doubled(u, v):
+        h = n // 2
+        s, e = shard_bounds(h, rank, world)
+        return np.concatenate([np.arange(s, e), np.arange(h + s, h + e)])
+    s, e = shard_bounds(n, rank, world)
+    return np.arange(s, e)
+
+
+def shard_visibilities(data, rank, world):
+    """This rank's part of a Visibilities-like object (u, v, freq, real, imag, weights)."""
+    from .interferometry import Visibilities
+    rows = shard_rows(data.u, data.v, rank, world)
+    return Visibilities(np.ascontiguousarray(data.u[rows]), np.ascontiguousarray(data.v[rows]), data.freq,
+                        np.ascontiguousarray(data.real[rows]), np.ascontiguousarray(data.imag[rows]),
+                        np.ascontiguousarray(data.weights[rows]))
+
+
+def shard_walkers(nwalkers, rank, world):
+    return shard_bounds(nwalkers, rank, world)
+
+
+def combine_lnlike(chi2_and_logsum, group=None):
+    """All-reduce (sum) a tensor holding [chi2_0..chi2_{nf-1}, logsum] over ranks and return the
+    emcee.py:31-43 value  -0.5*sum(chi2) - 2*logsum.  `chi2_and_logsum` is a torch tensor on the
+    device the process group communicates from (CUDA for NCCL, CPU for gloo)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(chi2_and_logsum, op=dist.ReduceOp.SUM, group=group)
+    t = chi2_and_logsum.double().cpu()
+    return float(-0.5 * t[:-1].sum() - 2.0 * t[-1])
+
+
+class ShardedLikelihood:
+    """Fused image -> visibilities -> chi^2 over this rank's uv shard, then one all-reduce of
+    nf+1 doubles.  torch supplies the NCCL process group and the tiny device tensor that is
+    reduced; all arithmetic is in libpdsb (pdsb_loglike_device).
+
+        like = ShardedLikelihood(shard_visibilities(data, rank, world))
+        lnlike = like(image_cube, dxy_rad, dRA_rad, dDec_rad)      # same value on every rank
+    """
+
+    def __init__(self, data_shard, group=None):
+        import ctypes
+        import torch
+        from . import _lib
+        from .device import Dataset
+        self._lib = _lib
+        self.L = _lib.lib()
+        self.group = group
+        self.torch = torch
+        # run libpdsb on torch's current stream so the collective is ordered behind the kernels
+        _lib.check(self.L.pdsb_set_stream(torch.cuda.current_stream().cuda_stream))
+        self.ds = Dataset(data_shard.u, data_shard.v)
+        self.ds.set_data(data_shard.real, data_shard.imag, data_shard.weights)
+        self.nf = data_shard.real.shape[1]
+        ls = ctypes.c_double()
+        _lib.check(self.L.pdsb_dataset_logsum(self.ds.handle, ctypes.byref(ls)))
+        self.logsum = ls.value
+        self.buf = torch.zeros(self.nf + 1, dtype=torch.float64, device="cuda")
+        self.logsum_dev = torch.tensor([ls.value], dtype=torch.float64, device="cuda")
+
+    def chi2_device(self, image, ny, nx, kind, dxy, dRA, dDec):
+        """Launch the local part; result (chi2[nf], logsum) stays in self.buf on the device."""
+        _lib = self._lib
+        _lib.check(self.L.pdsb_loglike_device(self.ds.handle, _lib.ptr(image), ny, nx, self.nf, kind, float(dxy),
+                                              float(dRA), float(dDec), self.buf.data_ptr()))
+        self.buf[self.nf:].copy_(self.logsum_dev)
+        return self.buf
+
+    def __call__(self, image, dxy, dRA=0.0, dDec=0.0, kind=0, shape=None):
+        if shape is None:
+            ny, nx = image.shape[0], image.shape[1]
+        else:
+            ny, nx = shape
+        return combine_lnlike(self.chi2_device(image, ny, nx, kind, dxy, dRA, dDec), self.group)

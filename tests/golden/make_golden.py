@@ -1,0 +1,142 @@
+"""Generate the committed golden vectors from the LIVE reference (run in the build
+container, where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+Outputs (all small):
+  fixture_720.npz      the reference's only fixture, tests/testdata.hdf5, as float64 arrays
+  grid_golden.npz      grid() of the live reference module (oracle/_ref, built from
+                       pdspy/interferometry/libinterferometry.pyx with the reference's own
+                       flags) on the fixture and on a seeded multi-channel set; outputs stored
+                       sparsely (non-zero cells), index maps in full
+  chisq_golden.npz     chisq() of the live reference
+  dft_golden.npz       exact-DFT ORACLE outputs (oracle/dft.py) on the fixture's uv points.
+                       NOT reference outputs: galario is unavailable (parity unpinned); kept as
+                       a regression anchor for the restatement itself.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from hdf5_mini import read_hdf5_flat          # noqa: E402
+from oracle import build_ref                  # noqa: E402
+from oracle import dft as od                  # noqa: E402
+from pdspy_b200 import synth                  # noqa: E402
+
+ARCSEC = 4.84813681e-6
+
+GRID_CASES_FIXTURE = {
+    # name: kwargs  (tests/test.py:9 runs invert(imsize=512, pixel_size=0.5, convolution="expsinc")
+    # -> grid(gridsize=512, binsize=1/(0.5*512*arcsec), convolution="expsinc", imaging=True))
+    "fx_pillbox_img256": dict(gridsize=256, binsize=1 / (0.5 * 256 * ARCSEC), convolution="pillbox", imaging=True),
+    "fx_expsinc_img256": dict(gridsize=256, binsize=1 / (0.5 * 256 * ARCSEC), convolution="expsinc", imaging=True),
+    "fx_expsinc_img512": dict(gridsize=512, binsize=1 / (0.5 * 512 * ARCSEC), convolution="expsinc", imaging=True),
+    "fx_default": dict(gridsize=256, binsize=2000.0),
+    "fx_uniform": dict(gridsize=256, binsize=500.0, convolution="expsinc", weighting="uniform"),
+    "fx_superuniform": dict(gridsize=256, binsize=500.0, convolution="expsinc", weighting="superuniform"),
+    "fx_robust": dict(gridsize=256, binsize=500.0, convolution="expsinc", weighting="robust", robust=2),
+    "fx_odd_robust": dict(gridsize=255, binsize=500.0, convolution="pillbox", weighting="robust", robust=0.5,
+                          npixels=1),
+}
+GRID_CASES_MULTI = {
+    "mc_expsinc_line": dict(gridsize=128, binsize=8000.0, convolution="expsinc", mode="spectralline"),
+    "mc_pillbox_line_uniform": dict(gridsize=128, binsize=8000.0, convolution="pillbox", mode="spectralline",
+                                    weighting="uniform"),
+    "mc_pillbox_cont": dict(gridsize=128, binsize=8000.0, convolution="pillbox", mode="continuum"),
+    "mc_expsinc_mfs": dict(gridsize=128, binsize=8000.0, convolution="expsinc", mfs=True),
+    "mc_expsinc_chan2_img": dict(gridsize=128, binsize=8000.0, convolution="expsinc", channel=2, imaging=True),
+    "mc_pillbox_line_robust": dict(gridsize=64, binsize=8000.0, convolution="pillbox", mode="spectralline",
+                                   weighting="robust", robust=0.5),
+}
+
+
+def multi_channel_set():
+    """Seeded multi-channel data with zero and negative weights and points off the grid."""
+    rng = np.random.default_rng(20240601)
+    n, nf = 5000, 4
+    u = rng.normal(0, 2e5, n)
+    v = rng.normal(0, 2e5, n)
+    freq = 230e9 + 1e8 * np.arange(nf)
+    re = rng.normal(size=(n, nf))
+    im = rng.normal(size=(n, nf))
+    w = rng.uniform(0.5, 2, (n, nf))
+    w[rng.random((n, nf)) < 0.01] = 0
+    w[rng.random((n, nf)) < 0.001] *= -1
+    re[17, 2] = 0.0
+    im[17, 2] = 0.0                     # exercises the (real==0)&(imag==0) zeroing of :353
+    return u, v, freq, re, im, w
+
+
+SAMPLE_ABOVE = 4000      # cases with more non-zero cells than this store every 8th one
+
+
+def sparse(a):
+    """(indices, values) of the non-zero cells; sub-sampled for the dense expsinc maps so the
+    committed file stays small.  The count and the plain sum of all non-zero cells are stored
+    beside them (make_golden.run)."""
+    flat = a.reshape(-1)
+    idx = np.flatnonzero(flat)
+    if idx.size > SAMPLE_ABOVE:
+        idx = idx[::8]
+    return idx.astype(np.int32), flat[idx]
+
+
+def main():
+    ref = build_ref.load()
+    assert ref is not None, "reference tree not available"
+    d = read_hdf5_flat("/root/reference/tests/testdata.hdf5")
+    fx = {k: d[k].astype(np.float64) for k in ("u", "v", "freq", "real", "imag", "weights")}
+    np.savez_compressed(os.path.join(HERE, "fixture_720.npz"), **fx)
+
+    out = {}
+    import contextlib
+    import io
+
+    def run(name, data, kw):
+        with contextlib.redirect_stdout(io.StringIO()):
+            g = ref.grid(data, **kw)
+        for nm in ("real", "imag", "weights"):
+            idx, val = sparse(getattr(g, nm))
+            out["%s/%s_idx" % (name, nm)] = idx
+            out["%s/%s_val" % (name, nm)] = val
+            full = getattr(g, nm)
+            out["%s/%s_nnz" % (name, nm)] = np.int64(np.count_nonzero(full))
+            out["%s/%s_sum" % (name, nm)] = np.float64(full.sum())
+        out["%s/shape" % name] = np.array(g.real.shape)
+        out["%s/freq" % name] = g.freq
+        out["%s/u_ends" % name] = g.u[[0, 1, -1]]
+
+    data = ref.Visibilities(fx["u"], fx["v"], fx["freq"], fx["real"], fx["imag"], fx["weights"])
+    for name, kw in GRID_CASES_FIXTURE.items():
+        run(name, data, kw)
+    u, v, freq, re, im, w = multi_channel_set()
+    data = ref.Visibilities(u, v, freq, re, im, w)
+    for name, kw in GRID_CASES_MULTI.items():
+        run(name, data, kw)
+    np.savez_compressed(os.path.join(HERE, "grid_golden.npz"), **out)
+
+    # chisq of the live reference (channel 0, float return)
+    rng = np.random.default_rng(99)
+    m = ref.Visibilities(fx["u"], fx["v"], fx["freq"], fx["real"] * 0.9 + 0.01 * rng.normal(size=fx["real"].shape),
+                         fx["imag"] * 1.1, fx["weights"])
+    c1 = ref.chisq(ref.Visibilities(fx["u"], fx["v"], fx["freq"], fx["real"], fx["imag"], fx["weights"]), m)
+    np.savez_compressed(os.path.join(HERE, "chisq_golden.npz"), m_real=m.real, m_imag=m.imag, chisq=np.float64(c1))
+
+    # oracle DFT outputs on the fixture's uv (regression anchor; not reference output)
+    img = synth.synth_image(64, 2, 0.5, kind="disk")
+    vis = od.exact_dft_literal(fx["u"], fx["v"], img, 0.5 * ARCSEC, 0.05 * ARCSEC, -0.03 * ARCSEC)
+    np.savez_compressed(os.path.join(HERE, "dft_golden.npz"), real=vis.real, imag=vis.imag)
+    print("golden vectors written to", HERE)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(" ", f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

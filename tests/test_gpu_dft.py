@@ -1,0 +1,183 @@
+"""Parity of the CUDA image->visibility path (through the C-ABI) against the exact-DFT oracle.
+
+Tolerance (BASELINE.json north_star): visibilities within 1e-5 relative - fp32 products with
+fp64 phase seeding and accumulation - measured against max|V| of the channel, because individual
+|V| pass through zero at nulls (hard part 2)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dft as od
+from pdspy_b200 import synth, _lib, Dataset, DeviceBuffer
+from pdspy_b200.interferometry import interpolate_model, Visibilities
+
+pytestmark = pytest.mark.gpu
+A = synth.ARCSEC
+TOL = 1e-5
+
+
+def relerr(vis, ref):
+    got = vis.real + 1j * vis.imag
+    scale = np.abs(ref).max(axis=0, keepdims=True)
+    return (np.abs(got - ref) / scale).max()
+
+
+def _model(ny, nx, nf, px, seed=0, kind="random"):
+    rng = np.random.default_rng(seed)
+    img = rng.random((ny, nx, nf, 1)) if kind == "random" else synth.synth_image(nx, nf, px)
+    m = synth.SynthImage(img, px, synth.synth_freq(nf))
+    return m
+
+
+@pytest.fixture(autouse=True)
+def _reset_tuning(gpu):
+    yield
+    gpu.pdsb_set_dft_variant(0)
+    gpu.pdsb_set_dft_split(0)
+
+
+@pytest.mark.parametrize("ny,nx,nf,nuv,herm", [
+    (64, 64, 1, 400, True),       # square even, Hermitian-doubled list (the reference's case)
+    (64, 64, 3, 401, False),      # odd count: cannot be Hermitian-doubled
+    (63, 65, 2, 333, False),      # odd sizes: self-paired middle row / column
+    (40, 72, 33, 130, True),      # rectangular, more than one 32-channel epilogue tile
+    (8, 8, 1, 5, False),          # smaller than one tile
+    (2, 2, 1, 3, False),
+    (130, 34, 65, 64, True),      # several row chunks, 65 channels
+])
+def test_parity_small_shapes(gpu, ny, nx, nf, nuv, herm):
+    px = 0.1
+    m = _model(ny, nx, nf, px, seed=ny * 131 + nx)
+    if herm:
+        u, v = synth.synth_uv(nuv, px * A)
+    else:
+        rng = np.random.default_rng(nuv)
+        u, v = rng.normal(0, 3e5, nuv), rng.normal(0, 3e5, nuv)
+    ref = od.exact_dft(u, v, m.image, px * A, 0.05 * A, -0.03 * A)
+    vis = interpolate_model(u, v, m.freq, m, dRA=0.05, dDec=-0.03)
+    assert vis.real.shape == (nuv, nf) and np.all(vis.weights == 1)
+    assert relerr(vis, ref) < TOL
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("split", [1, 3])
+def test_every_kernel_variant_and_split(gpu, variant, split):
+    gpu.pdsb_set_dft_variant(variant)
+    gpu.pdsb_set_dft_split(split)
+    m = _model(96, 96, 2, 0.05, seed=variant)
+    u, v = synth.synth_uv(1500, 0.05 * A)
+    ref = od.exact_dft(u, v, m.image, 0.05 * A, -0.11 * A, 0.07 * A)
+    vis = interpolate_model(u, v, m.freq, m, dRA=-0.11, dDec=0.07)
+    assert relerr(vis, ref) < TOL
+
+
+def test_against_literal_oracle_on_the_reference_fixture(gpu, fixture720):
+    """The reference's fixture uv points (720, Hermitian-doubled) and the literal per-pixel
+    oracle (one complex exponential per pixel-visibility pair), incl. the committed golden."""
+    f = fixture720
+    img = synth.synth_image(64, 2, 0.5, kind="disk")
+    m = synth.SynthImage(img, 0.5, synth.synth_freq(2))
+    vis = interpolate_model(f["u"], f["v"], m.freq, m, dRA=0.05, dDec=-0.03)
+    ref = od.exact_dft_literal(f["u"], f["v"], img, 0.5 * A, 0.05 * A, -0.03 * A)
+    assert relerr(vis, ref) < TOL
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dft_golden.npz"))
+    assert relerr(vis, g["real"] + 1j * g["imag"]) < TOL
+
+
+@pytest.mark.parametrize("kind", ["disk", "random"])
+def test_config1_full(gpu, kind):
+    """BASELINE.json configs[0]: 256x256 single channel onto 50k uv points, with and without
+    the dRA/dDec offset."""
+    c = synth.make_config("C1", kind=kind)
+    for dra, ddec in ((0.0, 0.0), (c["dRA"], c["dDec"])):
+        ref = od.exact_dft(c["u"], c["v"], c["model"].image, c["pixelsize"] * A, dra * A, ddec * A)
+        vis = interpolate_model(c["u"], c["v"], c["freq"], c["model"], dRA=dra, dDec=ddec)
+        assert relerr(vis, ref) < TOL
+
+
+def test_gaussian_known_answer(gpu):
+    """The reference's analytic gaussian_model (model.py:137-147) from a rendered image."""
+    n, px, x0, y0, sig, flux = 256, 0.05, 0.35, -0.2, 0.3, 2.0
+    x = (np.arange(n) - n / 2) * px
+    X, Y = np.meshgrid(x, x)
+    g = np.exp(-0.5 * ((X + x0) ** 2 + (Y - (y0 - px)) ** 2) / sig ** 2)
+    img = (g * flux / g.sum())[:, :, None, None]
+    m = synth.SynthImage(np.ascontiguousarray(img), px, synth.synth_freq(1))
+    u, v = synth.synth_uv(2000, px * A)
+    u, v = u * 0.2, v * 0.2
+    vis = interpolate_model(u, v, m.freq, m, dRA=0.1, dDec=0.2)
+    ref = flux * np.exp(-2 * np.pi ** 2 * (sig * A) ** 2 * (u ** 2 + v ** 2)) * \
+        np.exp(-2j * np.pi * (u * (x0 + 0.1) * A + v * (y0 + 0.2) * A))
+    assert np.abs(vis.real[:, 0] + 1j * vis.imag[:, 0] - ref).max() < TOL * flux
+
+
+def test_empty_uv_list(gpu):
+    m = _model(16, 16, 2, 0.1)
+    vis = interpolate_model(np.zeros(0), np.zeros(0), m.freq, m)
+    assert vis.real.shape == (0, 2)
+
+
+def test_hermitian_detection_is_exact_not_assumed(gpu):
+    u, v = synth.synth_uv(200, 0.1 * A)
+    d = Dataset(u, v)
+    assert d.hermitian and d.nuv_unique == 100
+    v2 = v.copy()
+    v2[150] = np.nextafter(v2[150], 1.0)          # one ulp off: must not be folded
+    d2 = Dataset(u, v2)
+    assert not d2.hermitian and d2.nuv_unique == 200
+    m = _model(32, 32, 1, 0.1)
+    ref = od.exact_dft(u, v2, m.image, 0.1 * A)
+    vis = interpolate_model(u, v2, m.freq, m)
+    assert relerr(vis, ref) < TOL
+
+
+def _device_sample(gpu, ds, dimg, n, nf, px, dra, ddec, nuv):
+    dre, dim_ = DeviceBuffer(nuv * nf * 8), DeviceBuffer(nuv * nf * 8)
+    _lib.check(gpu.pdsb_sample_image(ds.handle, _lib.ptr(dimg), n, n, nf, _lib.DEVICE, px * A, dra * A, ddec * A,
+                                     _lib.ptr(dre), _lib.ptr(dim_), _lib.DEVICE))
+    return dre.download((nuv, nf)) + 1j * dim_.download((nuv, nf))
+
+
+def test_config2_full_size_properties_and_subset_parity(gpu):
+    """BASELINE.json configs[1] at full size (1024^2 x 1M uv, dRA/dDec offset), device-resident
+    buffers: parity on a random 2048-point subset against the oracle, plus size-independent
+    properties on all points: linearity and Hermitian symmetry."""
+    c = synth.make_config("C2")
+    n, nuv, px = c["npix"], c["u"].size, c["pixelsize"]
+    img1 = np.ascontiguousarray(c["model"].image[:, :, :, 0])
+    img2 = np.random.default_rng(5).random(img1.shape) * img1.max()
+    ds = Dataset(c["u"], c["v"])
+    d1, d2 = DeviceBuffer.from_numpy(img1), DeviceBuffer.from_numpy(img2)
+    d3 = DeviceBuffer.from_numpy(2.0 * img1 - 0.5 * img2)
+    V1 = _device_sample(gpu, ds, d1, n, 1, px, c["dRA"], c["dDec"], nuv)
+    V2 = _device_sample(gpu, ds, d2, n, 1, px, c["dRA"], c["dDec"], nuv)
+    V3 = _device_sample(gpu, ds, d3, n, 1, px, c["dRA"], c["dDec"], nuv)
+    sub = np.random.default_rng(1).choice(nuv, 2048, replace=False)
+    ref = od.exact_dft(c["u"][sub], c["v"][sub], c["model"].image, px * A, c["dRA"] * A, c["dDec"] * A)
+    assert np.abs(V1[sub] - ref).max() / np.abs(V1).max() < TOL
+    scale = max(np.abs(V1).max(), np.abs(V2).max())
+    assert np.abs(V3 - (2.0 * V1 - 0.5 * V2)).max() / scale < 3 * TOL
+    h = nuv // 2
+    assert np.array_equal(V1[h:], np.conj(V1[:h]))
+
+
+def test_config3_shape_channels_share_uv(gpu):
+    """BASELINE.json configs[2] shape at reduced uv count (512^2 x 64 channels): every channel
+    is an independent image on the same uv points."""
+    c = synth.make_config("C3", nuv=4096)
+    ref = od.exact_dft(c["u"], c["v"], c["model"].image, c["pixelsize"] * A, c["dRA"] * A, c["dDec"] * A)
+    vis = interpolate_model(c["u"], c["v"], c["freq"], c["model"], dRA=c["dRA"], dDec=c["dDec"])
+    assert vis.real.shape == (4096, 64)
+    assert relerr(vis, ref) < TOL
+
+
+def test_dataset_cache_invalidation_on_in_place_change(gpu):
+    m = _model(32, 32, 1, 0.1)
+    u, v = synth.synth_uv(64, 0.1 * A)
+    a = interpolate_model(u, v, m.freq, m)
+    u[:] = u * 0.5
+    b = interpolate_model(u, v, m.freq, m)
+    ref = od.exact_dft(u, v, m.image, 0.1 * A)
+    assert relerr(b, ref) < TOL and relerr(a, ref) > 1e-3

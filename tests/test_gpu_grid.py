@@ -1,0 +1,174 @@
+"""Convolutional gridding on the GPU against the live reference's golden vectors and the oracle.
+
+Bars (north_star): index maps bit-exact; gridded weight (and real/imag) maps bit-exact for the
+pillbox kernel in deterministic mode; 1e-10 relative for expsinc (the reference's own last bits
+depend on its -ffast-math build, setup.py:11) and for the atomic mode."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_golden import GRID_CASES_FIXTURE, GRID_CASES_MULTI, multi_channel_set      # noqa: E402
+
+from oracle import grid as og                                                        # noqa: E402
+from pdspy_b200 import synth, _lib                                                   # noqa: E402
+from pdspy_b200.interferometry import grid, freqcorrect, Visibilities                # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _quiet(fn, *a, **kw):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        r = fn(*a, **kw)
+    return r, buf.getvalue()
+
+
+def _vs_golden(name, g, golden, exact, tol=1e-10):
+    assert tuple(golden[name + "/shape"]) == g.real.shape
+    np.testing.assert_array_equal(g.freq, golden[name + "/freq"])
+    np.testing.assert_array_equal(g.u[[0, 1, -1]], golden[name + "/u_ends"])
+    for nm in ("real", "imag", "weights"):
+        arr = getattr(g, nm)
+        idx, val = golden["%s/%s_idx" % (name, nm)], golden["%s/%s_val" % (name, nm)]
+        assert np.count_nonzero(arr) == int(golden["%s/%s_nnz" % (name, nm)])
+        got = arr.reshape(-1)[idx]
+        if exact:
+            np.testing.assert_array_equal(got, val, err_msg="%s %s" % (name, nm))
+        else:
+            assert np.abs(got - val).max() <= tol * np.abs(val).max(), (name, nm)
+
+
+@pytest.mark.parametrize("name", sorted(GRID_CASES_FIXTURE))
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_fixture_cases_vs_live_reference_golden(gpu, fixture720, grid_golden, name, deterministic):
+    f = fixture720
+    data = Visibilities(f["u"], f["v"], f["freq"], f["real"], f["imag"], f["weights"])
+    kw = GRID_CASES_FIXTURE[name]
+    g, _ = _quiet(grid, data, deterministic=deterministic, **kw)
+    exact = deterministic and kw.get("convolution", "pillbox") == "pillbox" and \
+        kw.get("weighting", "natural") != "robust" and not kw.get("imaging", False)
+    _vs_golden(name, g, grid_golden, exact)
+
+
+@pytest.mark.parametrize("name", sorted(GRID_CASES_MULTI))
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_multichannel_cases_vs_live_reference_golden(gpu, grid_golden, name, deterministic):
+    u, v, freq, re, im, w = multi_channel_set()
+    kw = GRID_CASES_MULTI[name]
+    g, out = _quiet(grid, Visibilities(u, v, freq, re, im, w), deterministic=deterministic, **kw)
+    assert out.startswith("WARNING: uv.grid was supplied with a gridsize and binsize")   # :424-425
+    exact = deterministic and kw.get("convolution", "pillbox") == "pillbox" and \
+        kw.get("weighting", "natural") != "robust" and not kw.get("imaging", False)
+    _vs_golden(name, g, grid_golden, exact)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(gridsize=128, binsize=8000., convolution="pillbox"),
+    dict(gridsize=128, binsize=8000., convolution="pillbox", mode="spectralline"),
+    dict(gridsize=127, binsize=8000., convolution="pillbox", mode="spectralline", weighting="uniform", npixels=1),
+    dict(gridsize=128, binsize=8000., convolution="pillbox", weighting="superuniform"),
+    dict(gridsize=128, binsize=8000., convolution="pillbox", mfs=True),
+    dict(gridsize=128, binsize=8000., convolution="pillbox", channel=1),
+])
+def test_pillbox_deterministic_is_bit_exact_incl_index_maps(gpu, kw):
+    rng = np.random.default_rng(7)
+    n, nf = 20000, 3
+    u, v = rng.normal(0, 2e5, n), rng.normal(0, 2e5, n)
+    freq = 230e9 + 1e8 * np.arange(nf)
+    re, im = rng.normal(size=(n, nf)), rng.normal(size=(n, nf))
+    w = rng.uniform(0.5, 2, (n, nf))
+    w[rng.random((n, nf)) < 0.01] = 0
+    w[rng.random((n, nf)) < 0.001] *= -1
+    o, _ = _quiet(og.grid, u, v, freq, re, im, w, return_maps=True, **kw)
+    (g, gi, gj, wm), _ = _quiet(grid, Visibilities(u, v, freq, re, im, w), return_maps=True, **kw)
+    np.testing.assert_array_equal(gi, o[6])
+    np.testing.assert_array_equal(gj, o[7])
+    np.testing.assert_array_equal(wm, o[9])
+    np.testing.assert_array_equal(g.weights, o[5])
+    np.testing.assert_array_equal(g.real, o[3])
+    np.testing.assert_array_equal(g.imag, o[4])
+    np.testing.assert_array_equal(g.u, o[0])
+    np.testing.assert_array_equal(g.v, o[1])
+
+
+def test_expsinc_and_atomic_modes_within_tolerance(gpu):
+    rng = np.random.default_rng(8)
+    n, nf = 30000, 2
+    u, v = rng.normal(0, 2e5, n), rng.normal(0, 2e5, n)
+    freq = 230e9 + 1e8 * np.arange(nf)
+    re, im = rng.normal(size=(n, nf)), rng.normal(size=(n, nf))
+    w = rng.uniform(0.5, 2, (n, nf))
+    d = Visibilities(u, v, freq, re, im, w)
+    for kw in (dict(gridsize=128, binsize=9000., convolution="expsinc", mode="spectralline"),
+               dict(gridsize=128, binsize=9000., convolution="expsinc", weighting="robust", robust=0.5),
+               dict(gridsize=129, binsize=9000., convolution="expsinc", imaging=True, weighting="uniform")):
+        o, _ = _quiet(og.grid, u, v, freq, re, im, w, **kw)
+        for det in (True, False):
+            g, _ = _quiet(grid, d, deterministic=det, **kw)
+            for nm, ob in zip(("real", "imag", "weights"), o[3:6]):
+                assert np.abs(getattr(g, nm) - ob).max() <= 1e-10 * np.abs(ob).max(), (kw, det, nm)
+
+
+def test_edge_cases_empty_and_all_outside(gpu):
+    e = Visibilities(np.zeros(0), np.zeros(0), np.array([230e9]), np.zeros((0, 1)), np.zeros((0, 1)), np.zeros((0, 1)))
+    g, out = _quiet(grid, e, gridsize=16, binsize=1000.)
+    assert g.real.shape == (256, 1) and not g.weights.any() and out == ""
+    far = Visibilities(np.array([1e9, -1e9]), np.array([0., 0.]), np.array([230e9]), np.ones((2, 1)), np.ones((2, 1)),
+                       np.ones((2, 1)))
+    g, out = _quiet(grid, far, gridsize=16, binsize=1000., convolution="expsinc")
+    assert not g.weights.any() and out.startswith("WARNING")
+    # negative coordinate wraps through the uint32 cast exactly like numpy (index map parity)
+    (g, gi, gj, _), _ = _quiet(grid, far, gridsize=16, binsize=1000., return_maps=True)
+    i_ref, j_ref = og.index_maps(far.u, far.v, far.freq, 16, 1000.)
+    np.testing.assert_array_equal(gi, i_ref)
+    np.testing.assert_array_equal(gj, j_ref)
+
+
+def test_point_on_cell_edge_is_dropped_by_pillbox(gpu):
+    """ones() uses strict |u| < 0.5 (libinterferometry.pyx:576-585): a point exactly between two
+    cell centres contributes to neither."""
+    d = Visibilities(np.array([500.0, 1000.0]), np.array([0.0, 0.0]), np.array([230e9]), np.ones((2, 1)),
+                     np.ones((2, 1)), np.ones((2, 1)))
+    g, _ = _quiet(grid, d, gridsize=8, binsize=1000.)
+    o, _ = _quiet(og.grid, d.u, d.v, d.freq, d.real, d.imag, d.weights, gridsize=8, binsize=1000.)
+    np.testing.assert_array_equal(g.weights, o[5])
+    assert g.weights.sum() == 1.0
+
+
+def test_freqcorrect_bit_exact(gpu):
+    u, v, freq, re, im, w = multi_channel_set()
+    d = Visibilities(u, v, freq, re, im, w)
+    r = freqcorrect(d)
+    o = og.freqcorrect(u, v, freq, re, im, w)
+    for a, nm in zip(o, ("u", "v", "freq", "real", "imag", "weights")):
+        np.testing.assert_array_equal(getattr(r, nm), a, err_msg=nm)
+    r2 = freqcorrect(d, freq=231e9)
+    o2 = og.freqcorrect(u, v, freq, re, im, w, new_freq=231e9)
+    np.testing.assert_array_equal(r2.u, o2[0])
+
+
+def test_config4_scale_properties(gpu):
+    """BASELINE.json configs[3] shape at 1M visibilities onto 2048^2 (the full 10M runs in
+    bench.py): size-independent properties.  pillbox/natural/imaging=False conserves the total
+    weight of the points that land on the grid; deterministic == atomic to rounding; index maps
+    equal numpy's."""
+    px = 0.01
+    u, v = synth.synth_uv(1_000_000, px * synth.ARCSEC)
+    re, im, w = synth.synth_data(1_000_000, 1)
+    d = Visibilities(u, v, synth.synth_freq(1), re, im, w)
+    G = 2048
+    binsize = 2.2 * np.hypot(u, v).max() / G
+    (g, gi, gj, wm), _ = _quiet(grid, d, gridsize=G, binsize=binsize, return_maps=True, deterministic=True)
+    i_ref, j_ref = og.index_maps(u, v, d.freq, G, binsize)
+    np.testing.assert_array_equal(gi, i_ref)
+    np.testing.assert_array_equal(gj, j_ref)
+    ga, _ = _quiet(grid, d, gridsize=G, binsize=binsize, deterministic=False)
+    assert np.abs(ga.weights - g.weights).max() <= 1e-12 * g.weights.max()
+    assert abs(g.weights.sum() - wm.sum()) <= 1e-9 * wm.sum()
+    ge, _ = _quiet(grid, d, gridsize=G, binsize=binsize, convolution="expsinc", deterministic=False, imaging=True)
+    assert abs(ge.weights.sum() - 1.0) < 1e-12

@@ -1,0 +1,91 @@
+"""Host-side mirrors of the reference interface: containers, argument checks, synthetic data."""
+import pickle
+
+import numpy as np
+import pytest
+
+from pdspy_b200 import synth, Image
+from pdspy_b200.interferometry import Visibilities, VisibilitiesObject
+from pdspy_b200.interferometry.interpolate_model import interpolate_model
+from pdspy_b200 import device
+
+
+def _vis(n=6, nf=2):
+    rng = np.random.default_rng(0)
+    return Visibilities(rng.normal(size=n), rng.normal(size=n), np.arange(nf) + 1.0,
+                        rng.normal(size=(n, nf)), rng.normal(size=(n, nf)), rng.uniform(1, 2, (n, nf)))
+
+
+def test_visibilities_derived_arrays_match_reference_definitions(live_ref):
+    d = _vis()
+    np.testing.assert_array_equal(d.uvdist, np.sqrt(d.u ** 2 + d.v ** 2))
+    np.testing.assert_array_equal(d.amp, np.sqrt(d.real ** 2 + d.imag ** 2))
+    np.testing.assert_array_equal(d.phase, np.arctan2(d.imag, d.real))
+    if live_ref is not None:
+        r = live_ref.Visibilities(d.u, d.v, d.freq, d.real, d.imag, d.weights)
+        for nm in ("uvdist", "amp", "phase", "weights"):
+            np.testing.assert_array_equal(getattr(d, nm), getattr(r, nm))
+        assert r.array_name == d.array_name == "CARMA"
+
+
+def test_visibilities_default_weights_and_type_checks():
+    d = Visibilities(np.zeros(3), np.zeros(3), np.ones(1), np.zeros((3, 1)), np.zeros((3, 1)))
+    assert d.weights.shape == (3, 1) and np.all(d.weights == 1)
+    with pytest.raises(ValueError):
+        Visibilities(np.zeros(3, dtype=np.float32), np.zeros(3), np.ones(1), np.zeros((3, 1)), np.zeros((3, 1)))
+    with pytest.raises(ValueError):
+        Visibilities(np.zeros(3), np.zeros(3), np.ones(1), np.zeros(3), np.zeros((3, 1)))
+    with pytest.raises(TypeError):
+        Visibilities([0.0, 1.0], np.zeros(2))
+    e = Visibilities()
+    assert e.u is None and e.amp is None
+
+
+def test_pickle_round_trip_returns_base_class_like_the_reference():
+    d = _vis()
+    d.baseline = np.arange(6)
+    r = pickle.loads(pickle.dumps(d))
+    assert type(r) is VisibilitiesObject           # libinterferometry.pyx:46-52 rebuild()
+    np.testing.assert_array_equal(r.real, d.real)
+    np.testing.assert_array_equal(r.amp, d.amp)
+    np.testing.assert_array_equal(r.baseline, d.baseline)
+
+
+def test_get_baselines():
+    d = _vis()
+    d.baseline = np.array([1, 2, 1, 2, 1, 3])
+    s = d.get_baselines(1)
+    assert s.u.size == 3 and s.real.shape == (3, 2)
+
+
+def test_image_container_derives_freq_and_wave():
+    img = Image(np.zeros((4, 4, 2, 1)), x=np.arange(4.0), y=np.arange(4.0), wave=np.array([0.1, 0.2]))
+    np.testing.assert_allclose(img.freq * img.wave, 2.99792458e10)
+    with pytest.raises(ValueError):
+        Image(np.zeros((4, 4, 2), dtype=np.float64))
+
+
+def test_interpolate_model_argument_errors_do_not_need_a_gpu():
+    c = synth.make_config("C1", nuv=16)
+    with pytest.raises(NotImplementedError):
+        interpolate_model(c["u"], c["v"], c["freq"], c["model"], code="trift")
+    with pytest.raises(ValueError):
+        interpolate_model(c["u"], c["v"], c["freq"], c["model"], code="nope")
+
+
+def test_synthetic_uv_is_hermitian_doubled_and_nyquist_limited():
+    u, v = synth.synth_uv(1000, 0.01 * synth.ARCSEC)
+    h = 500
+    np.testing.assert_array_equal(u[h:], -u[:h])
+    np.testing.assert_array_equal(v[h:], -v[:h])
+    assert np.hypot(u, v).max() <= 0.45 / (0.01 * synth.ARCSEC) * (1 + 1e-12)
+    re, im, w = synth.synth_data(1000, 3)
+    np.testing.assert_array_equal(im[h:], -im[:h])
+    assert (w == 0).any() and (w < 0).any()
+
+
+def test_fingerprint_detects_in_place_change():
+    a = np.arange(10000.0)
+    f0 = device._fingerprint(a)
+    a[0] = -1
+    assert device._fingerprint(a) != f0
