@@ -64,8 +64,10 @@ int pdsb_shutdown(void);
 const char *pdsb_last_error(void);
 /* cudaStream_t the library launches on, as an integer. */
 int pdsb_get_stream(uint64_t *stream);
-/* Launch on a caller-owned stream instead (e.g. torch's current stream); 0 restores the own stream. */
+/* Launch on a caller-owned stream instead (e.g. torch's current stream; 0 is the legacy default
+ * stream).  pdsb_reset_stream goes back to the library's own stream. */
 int pdsb_set_stream(uint64_t stream);
+int pdsb_reset_stream(void);
 int pdsb_synchronize(void);
 int pdsb_device_info(int *sm_count, int *sm_clock_khz, int64_t *mem_bytes, int *cc_major, int *cc_minor);
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "pdsb_last_error": [],
     "pdsb_get_stream": [ctypes.POINTER(ctypes.c_uint64)],
     "pdsb_set_stream": [ctypes.c_uint64],
+    "pdsb_reset_stream": [],
     "pdsb_synchronize": [],
     "pdsb_device_info": [ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), ctypes.POINTER(_c_i64),
                          ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)],

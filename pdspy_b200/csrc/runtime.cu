@@ -255,7 +255,16 @@ int pdsb_set_stream(uint64_t stream)
     PDSB_CHECK(require_init());
     Context &c = ctx();
     PDSB_CUDA(cudaStreamSynchronize(c.stream));
-    c.stream = stream ? (cudaStream_t)(uintptr_t)stream : c.own_stream;
+    c.stream = (cudaStream_t)(uintptr_t)stream;      // 0 is the legacy default stream (torch's default)
+    return PDSB_OK;
+}
+
+int pdsb_reset_stream(void)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    c.stream = c.own_stream;
     return PDSB_OK;
 }
 
