@@ -157,6 +157,64 @@ __global__ void __launch_bounds__(256) fma_bench_kernel(float *out, int iters, f
     }
 }
 
+// Pattern microbenchmarks for the DFT inner loop: acc[q][c] = fma2(x[c][t], trig[q][t], acc[q][c])
+// with the image operand x either register-resident (MODE 0) or re-loaded from shared memory by a
+// warp-broadcast LDS.128 every row (MODE 1).  UVT uv points per thread, TP trig pairs.
+template <int UVT, int TP, int MODE>
+__global__ void __launch_bounds__(128) fma_pattern_kernel(float *out, int iters, float seed)
+{
+    __shared__ __align__(16) float sm[4 * TP * 2 * 8];
+    for (int i = threadIdx.x; i < 4 * TP * 2 * 8; i += 128) sm[i] = 1.0f + 1e-6f * i * seed;
+    __syncthreads();
+    unsigned long long trig[UVT][TP], acc[UVT][4];
+#pragma unroll
+    for (int q = 0; q < UVT; q++) {
+#pragma unroll
+        for (int t = 0; t < TP; t++) {
+            float2 a = make_float2(1.0f + 1e-7f * (threadIdx.x + t + q), 1.0f - 1e-7f * (threadIdx.x + t));
+            trig[q][t] = *reinterpret_cast<unsigned long long *>(&a);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[q][c] = 0ull;
+    }
+    unsigned long long xr[4][TP];
+    if (MODE == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int t = 0; t < TP; t++) xr[c][t] = reinterpret_cast<const unsigned long long *>(sm)[c * TP + t];
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(sm + (it & 7) * (4 * TP * 2));
+#pragma unroll
+        for (int g = 0; g < TP / 2; g++) {
+            ulonglong2 x[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (MODE == 1) x[c] = row[c * (TP / 2) + g];
+                else x[c] = make_ulonglong2(xr[c][2 * g], xr[c][2 * g + 1]);
+            }
+#pragma unroll
+            for (int q = 0; q < UVT; q++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    acc[q][c] = fma2_(x[c].x, trig[q][2 * g], acc[q][c]);
+                    acc[q][c] = fma2_(x[c].y, trig[q][2 * g + 1], acc[q][c]);
+                }
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int q = 0; q < UVT; q++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float2 a = *reinterpret_cast<float2 *>(&acc[q][c]);
+            s += a.x + a.y;
+        }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace pdsb
 
 using namespace pdsb;
@@ -434,16 +492,26 @@ int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms_out)
     PDSB_CHECK(require_init());
     PDSB_REQUIRE(tflops && iters > 0, "tflops/iters");
     Context &c = ctx();
-    int blocks = c.sm_count * 8, threads = 256;
-    PDSB_CHECK(c.red.ensure((size_t)blocks * threads * sizeof(float)));
+    int blocks = c.sm_count * 8, threads = variant < 2 ? 256 : 128;
+    PDSB_CHECK(c.red.ensure((size_t)blocks * 256 * sizeof(float)));
+    double fmas_per_thread_iter = 8.0 * 16.0;
     for (int rep = 0; rep < 2; rep++) {
         if (rep == 1) PDSB_CUDA(cudaEventRecord(c.t0, c.stream));
         {
-            LaunchScope ls(variant ? "fma_bench_f32x2" : "fma_bench_f32");
-            if (variant == 0)
-                fma_bench_kernel<0><<<blocks, threads, 0, c.stream>>>(c.red.as<float>(), iters, 1.0f);
-            else
-                fma_bench_kernel<1><<<blocks, threads, 0, c.stream>>>(c.red.as<float>(), iters, 1.0f);
+            LaunchScope ls("fma_bench");
+            float *o = c.red.as<float>();
+            switch (variant) {
+                case 0: fma_bench_kernel<0><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); break;
+                case 1: fma_bench_kernel<1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); break;
+                // (UVT, trig pairs, operand source): lane-FMAs per iteration = UVT*4*TP*2
+                case 2: fma_pattern_kernel<2, 8, 0><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 2 * 4 * 8 * 2; break;
+                case 3: fma_pattern_kernel<2, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 2 * 4 * 8 * 2; break;
+                case 4: fma_pattern_kernel<4, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 4 * 4 * 8 * 2; break;
+                case 5: fma_pattern_kernel<1, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 1 * 4 * 8 * 2; break;
+                case 6: fma_pattern_kernel<4, 8, 0><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 4 * 4 * 8 * 2; break;
+                case 7: fma_pattern_kernel<3, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 3 * 4 * 8 * 2; break;
+                default: set_error("unknown fma bench variant %d", variant); return PDSB_ERR_ARG;
+            }
         }
         PDSB_CUDA(cudaGetLastError());
     }
@@ -451,7 +519,7 @@ int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms_out)
     PDSB_CUDA(cudaEventSynchronize(c.t1));
     float ms = 0;
     PDSB_CUDA(cudaEventElapsedTime(&ms, c.t0, c.t1));
-    double fmas = (double)blocks * threads * (double)iters * 8.0 * 16.0;
+    double fmas = (double)blocks * threads * (double)iters * fmas_per_thread_iter;
     *tflops = 2.0 * fmas / (ms * 1e-3) / 1e12;
     if (ms_out) *ms_out = ms;
     return PDSB_OK;

@@ -35,12 +35,18 @@ def _vs_golden(name, g, golden, exact, tol=1e-10):
     for nm in ("real", "imag", "weights"):
         arr = getattr(g, nm)
         idx, val = golden["%s/%s_idx" % (name, nm)], golden["%s/%s_val" % (name, nm)]
-        assert np.count_nonzero(arr) == int(golden["%s/%s_nnz" % (name, nm)])
         got = arr.reshape(-1)[idx]
+        nnz = int(golden["%s/%s_nnz" % (name, nm)])
         if exact:
+            assert np.count_nonzero(arr) == nnz
             np.testing.assert_array_equal(got, val, err_msg="%s %s" % (name, nm))
         else:
+            # cells where Hermitian-conjugate contributions cancel hold a rounding residue
+            # (~1e-17) in the reference and may be exactly 0 here, or vice versa
+            assert abs(np.count_nonzero(arr) - nnz) <= max(2, nnz // 1000)
             assert np.abs(got - val).max() <= tol * np.abs(val).max(), (name, nm)
+        s = float(golden["%s/%s_sum" % (name, nm)])
+        assert abs(arr.sum() - s) <= 1e-9 * max(np.abs(arr).sum(), 1e-300)
 
 
 @pytest.mark.parametrize("name", sorted(GRID_CASES_FIXTURE))

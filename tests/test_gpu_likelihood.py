@@ -91,7 +91,8 @@ def test_walker_batch_matches_single_calls(gpu):
     base = c["model"].image[:, :, :, 0]
     cubes = np.stack([base * s for s in (1.0, 0.7, 1.3)])
     dra, ddec = np.array([0.0, 0.01, -0.02]), np.array([0.0, -0.01, 0.03])
-    ll = loglike_images(data, cubes, dra, ddec, pixelsize=c["pixelsize"])
+    px = c["model"].x[1] - c["model"].x[0]          # what interpolate_model derives dxy from (:20)
+    ll = loglike_images(data, cubes, dra, ddec, pixelsize=px)
     for k in range(3):
         m = synth.SynthImage(np.ascontiguousarray(cubes[k][:, :, :, None]), c["pixelsize"], c["freq"])
         one, _ = loglike_image(data, m, dRA=dra[k], dDec=ddec[k])
