@@ -135,7 +135,10 @@ int launch_fold(const double *img_dev, float *F, const DftGeom &g)
 
 // ---------------------------------------------------------------------------------
 // DFT kernel.  grid = (uv tiles, column-tile splits, planes); 128 threads; UVT uv/thread.
-template <int UVT, int TCP, bool F2, int MINB>
+// SMS: keep the per-thread fp64 state (phase rates fu, fv and the fp64 accumulators) in shared
+// memory instead of registers; it is touched once per chunk, and the registers it frees let the
+// wide variants hold their column tables without spilling.
+template <int UVT, int TCP, bool F2, int MINB, bool SMS>
 __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_kernel(const DftParams P)
 {
     constexpr int CHUNK_FLOATS = DFT_RC * 4 * TCP;
@@ -169,21 +172,27 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_kernel(const DftParams 
     }
 
     // per-thread uv points: phase advance per pixel in turns (fp64), row rotation (fp32)
-    double fu[UVT], fv[UVT], Vr[UVT], Vi[UVT];
+    double fu_r[SMS ? 1 : UVT], fv_r[SMS ? 1 : UVT], Vr_r[SMS ? 1 : UVT], Vi_r[SMS ? 1 : UVT];
+    double *fst = reinterpret_cast<double *>(smem_raw + (size_t)DFT_NSTAGE * CHUNK_BYTES);
+#define FU(q) (SMS ? fst[(0 * UVT + (q)) * DFT_THREADS + tid] : fu_r[SMS ? 0 : (q)])
+#define FV(q) (SMS ? fst[(1 * UVT + (q)) * DFT_THREADS + tid] : fv_r[SMS ? 0 : (q)])
+#define VR(q) (SMS ? fst[(2 * UVT + (q)) * DFT_THREADS + tid] : Vr_r[SMS ? 0 : (q)])
+#define VI(q) (SMS ? fst[(3 * UVT + (q)) * DFT_THREADS + tid] : Vi_r[SMS ? 0 : (q)])
     float Dr[UVT], Di[UVT];
-    int64_t kk[UVT];
 #pragma unroll
     for (int q = 0; q < UVT; q++) {
-        kk[q] = (int64_t)blockIdx.x * (DFT_THREADS * UVT) + q * DFT_THREADS + tid;
-        const bool valid = kk[q] < P.nuvh;
-        fu[q] = valid ? P.u[kk[q]] * P.dxy : 0.0;
-        fv[q] = valid ? P.v[kk[q]] * P.dxy : 0.0;
+        const int64_t k = (int64_t)blockIdx.x * (DFT_THREADS * UVT) + q * DFT_THREADS + tid;
+        const bool valid = k < P.nuvh;
+        const double fuq = valid ? P.u[k] * P.dxy : 0.0;
+        const double fvq = valid ? P.v[k] * P.dxy : 0.0;
+        FU(q) = fuq;
+        FV(q) = fvq;
         double s, c;
-        sincospi(2.0 * (fv[q] - rint(fv[q])), &s, &c);
+        sincospi(2.0 * (fvq - rint(fvq)), &s, &c);
         Dr[q] = (float)c;
         Di[q] = (float)s;
-        Vr[q] = 0.0;
-        Vi[q] = 0.0;
+        VR(q) = 0.0;
+        VI(q) = 0.0;
     }
 
     int it = 0;
@@ -192,10 +201,11 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_kernel(const DftParams 
         float tc[UVT][TCP], ts[UVT][TCP];
 #pragma unroll
         for (int q = 0; q < UVT; q++) {
-            double a0 = fu[q] * ((double)((tile0 + tl) * TCP) + P.hx);
+            const double fuq = FU(q);
+            double a0 = fuq * ((double)((tile0 + tl) * TCP) + P.hx);
             double cr, ci, rc, rs;
             sincospi(2.0 * (a0 - rint(a0)), &ci, &cr);
-            sincospi(2.0 * (fu[q] - rint(fu[q])), &rs, &rc);
+            sincospi(2.0 * (fuq - rint(fuq)), &rs, &rc);
 #pragma unroll
             for (int t = 0; t < TCP; t++) {
                 tc[q][t] = (float)cr;
@@ -223,7 +233,7 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_kernel(const DftParams 
             float Er[UVT], Ei[UVT];
 #pragma unroll
             for (int q = 0; q < UVT; q++) {
-                double b0 = fv[q] * ((double)(ch * DFT_RC) + P.hy);
+                double b0 = FV(q) * ((double)(ch * DFT_RC) + P.hy);
                 b0 -= rint(b0);
                 sincospif((float)(2.0 * b0), &Ei[q], &Er[q]);
             }
@@ -276,8 +286,8 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_kernel(const DftParams 
                 }
 #pragma unroll
                 for (int q = 0; q < UVT; q++) {
-                    Vr[q] += (double)sum2(vre[q]);
-                    Vi[q] += (double)sum2(vim[q]);
+                    VR(q) += (double)sum2(vre[q]);
+                    VI(q) += (double)sum2(vim[q]);
                 }
             } else {
                 float vre[UVT], vim[UVT];
@@ -331,8 +341,8 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_kernel(const DftParams 
                 }
 #pragma unroll
                 for (int q = 0; q < UVT; q++) {
-                    Vr[q] += (double)vre[q];
-                    Vi[q] += (double)vim[q];
+                    VR(q) += (double)vre[q];
+                    VI(q) += (double)vim[q];
                 }
             }
 
@@ -348,26 +358,36 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_kernel(const DftParams 
     }
 
 #pragma unroll
-    for (int q = 0; q < UVT; q++)
-        if (kk[q] < P.nuvh)
-            P.part[((size_t)sp * P.nf + plane) * (size_t)P.nuvh + kk[q]] = make_double2(Vr[q], Vi[q]);
+    for (int q = 0; q < UVT; q++) {
+        const int64_t k = (int64_t)blockIdx.x * (DFT_THREADS * UVT) + q * DFT_THREADS + tid;
+        if (k < P.nuvh) P.part[((size_t)sp * P.nf + plane) * (size_t)P.nuvh + k] = make_double2(VR(q), VI(q));
+    }
+#undef FU
+#undef FV
+#undef VR
+#undef VI
 }
 
 // ---------------------------------------------------------------------------------
 struct VariantInfo {
     const char *name;
-    int uvt, tcp, f2, minb;
+    int uvt, tcp, f2, minb, sms;
 };
 static const VariantInfo kVariants[] = {
-    {"dft_f2_uv2_tc16", 2, 16, 1, 4},   // 1
-    {"dft_f2_uv4_tc16", 4, 16, 1, 2},   // 2
-    {"dft_f2_uv2_tc32", 2, 32, 1, 2},   // 3
-    {"dft_f1_uv2_tc16", 2, 16, 0, 4},   // 4
-    {"dft_f1_uv4_tc16", 4, 16, 0, 2},   // 5
-    {"dft_f2_uv1_tc32", 1, 32, 1, 4},   // 6
+    {"dft_f2_uv2_tc16", 2, 16, 1, 4, 0},       // 1
+    {"dft_f2_uv4_tc16", 4, 16, 1, 2, 0},       // 2
+    {"dft_f2_uv2_tc32", 2, 32, 1, 2, 0},       // 3
+    {"dft_f1_uv2_tc16", 2, 16, 0, 4, 0},       // 4
+    {"dft_f1_uv4_tc16", 4, 16, 0, 2, 0},       // 5
+    {"dft_f2_uv1_tc32", 1, 32, 1, 4, 0},       // 6
+    {"dft_f2_uv4_tc16_sms", 4, 16, 1, 2, 1},   // 7
+    {"dft_f2_uv3_tc16_sms", 3, 16, 1, 3, 1},   // 8
+    {"dft_f2_uv2_tc32_sms", 2, 32, 1, 2, 1},   // 9
+    {"dft_f2_uv2_tc16_sms", 2, 16, 1, 4, 1},   // 10
+    {"dft_f2_uv3_tc32_sms", 3, 32, 1, 2, 1},   // 11
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kDefaultVariant = 1;
+constexpr int kDefaultVariant = 3;
 
 int dft_variant_count() { return kNumVariants; }
 int dft_pick_variant()
@@ -391,14 +411,15 @@ int dft_auto_split(int variant, int64_t nuvh, int nf, int ntile)
     return (int)ns;
 }
 
-template <int UVT, int TCP, bool F2, int MINB>
+template <int UVT, int TCP, bool F2, int MINB, bool SMS>
 static int launch_variant(const DftParams &p, const char *name)
 {
-    constexpr size_t smem = (size_t)DFT_NSTAGE * DFT_RC * 4 * TCP * sizeof(float);
+    constexpr size_t smem = (size_t)DFT_NSTAGE * DFT_RC * 4 * TCP * sizeof(float) +
+                            (SMS ? (size_t)4 * UVT * DFT_THREADS * sizeof(double) : 0);
     static bool attr_set = false;
     if (!attr_set) {
-        PDSB_CUDA(cudaFuncSetAttribute(dft_kernel<UVT, TCP, F2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+        PDSB_CUDA(cudaFuncSetAttribute(dft_kernel<UVT, TCP, F2, MINB, SMS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     int64_t uvtiles = (p.nuvh + (int64_t)DFT_THREADS * UVT - 1) / ((int64_t)DFT_THREADS * UVT);
@@ -406,7 +427,7 @@ static int launch_variant(const DftParams &p, const char *name)
     PDSB_REQUIRE(p.nsplit <= 65535 && p.nf <= 65535, "grid y/z dimensions");
     dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)p.nf);
     LaunchScope ls(name);
-    dft_kernel<UVT, TCP, F2, MINB><<<grid, DFT_THREADS, smem, ctx().stream>>>(p);
+    dft_kernel<UVT, TCP, F2, MINB, SMS><<<grid, DFT_THREADS, smem, ctx().stream>>>(p);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
@@ -417,12 +438,17 @@ int launch_dft(const DftParams &p, int variant, int *tcp_of_variant)
     if (tcp_of_variant) *tcp_of_variant = kVariants[variant - 1].tcp;
     const char *name = kVariants[variant - 1].name;
     switch (variant) {
-        case 1: return launch_variant<2, 16, true, 4>(p, name);
-        case 2: return launch_variant<4, 16, true, 2>(p, name);
-        case 3: return launch_variant<2, 32, true, 2>(p, name);
-        case 4: return launch_variant<2, 16, false, 4>(p, name);
-        case 5: return launch_variant<4, 16, false, 2>(p, name);
-        case 6: return launch_variant<1, 32, true, 4>(p, name);
+        case 1: return launch_variant<2, 16, true, 4, false>(p, name);
+        case 2: return launch_variant<4, 16, true, 2, false>(p, name);
+        case 3: return launch_variant<2, 32, true, 2, false>(p, name);
+        case 4: return launch_variant<2, 16, false, 4, false>(p, name);
+        case 5: return launch_variant<4, 16, false, 2, false>(p, name);
+        case 6: return launch_variant<1, 32, true, 4, false>(p, name);
+        case 7: return launch_variant<4, 16, true, 2, true>(p, name);
+        case 8: return launch_variant<3, 16, true, 3, true>(p, name);
+        case 9: return launch_variant<2, 32, true, 2, true>(p, name);
+        case 10: return launch_variant<2, 16, true, 4, true>(p, name);
+        case 11: return launch_variant<3, 32, true, 2, true>(p, name);
     }
     return PDSB_ERR_ARG;
 }
