@@ -387,7 +387,7 @@ static const VariantInfo kVariants[] = {
     {"dft_f2_uv3_tc32_sms", 3, 32, 1, 2, 1},   // 11
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kDefaultVariant = 3;
+constexpr int kDefaultVariant = 11;
 
 int dft_variant_count() { return kNumVariants; }
 int dft_pick_variant()
