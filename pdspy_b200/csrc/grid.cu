@@ -10,8 +10,9 @@
 //      reference's order inside each cell; one thread per cell then adds its run sequentially
 //      with non-contracted fp64 multiplies/adds.  For the pillbox kernel (weights 0 or 1) the
 //      gridded real/imag/weight maps are bit-identical to the reference.
-//  fast: contributions are added with fp64 atomics (RED.ADD.F64); visibilities are processed in
-//      home-cell order so that concurrent atomics hit neighbouring L2 lines.
+//  fast: visibilities sorted by 8x8-cell uv tile (one or two radix passes); one CTA per tile stages
+//      them through shared memory and accumulates the tile's footprint region in registers (one
+//      cell per thread), then adds the region to the map with one fp64 atomic per cell.
 //
 // Index maps reproduce numpy's left-to-right fp64 arithmetic and its float64->uint32 cast
 // (truncation through int64, wrap mod 2^32, NaN -> 0) exactly: __dmul_rn/__ddiv_rn/__dadd_rn keep
@@ -125,22 +126,30 @@ __device__ __forceinline__ double conv_value(const GridParams &P, int64_t k, int
 // ---- contribution keys -------------------------------------------------------------------------
 // mode 0: main scatter (footprint nmin/nmax, slots with a zero kernel value are dead)
 // mode 1: box sum of weights for uniform/robust re-weighting (footprint npix/npix)
+// One thread per emitted contribution.  `compact` (pillbox main scatter): the kernel value is 1 for
+// at most one of the 9 footprint cells, so one thread per visibility scans its slots and emits only
+// that one (fp_emit = 1) - the sort then handles nvis keys instead of 9*nvis.
 __global__ void __launch_bounds__(256) grid_emit_keys_kernel(GridParams P, int mode, uint32_t lo, uint32_t hi,
-                                                             int64_t first, int64_t count, int fp,
+                                                             int64_t first, int64_t count, int fp, int compact,
                                                              uint32_t *keys, uint32_t *ids)
 {
     const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;       // contribution within the batch
-    if (t >= count * fp) return;
-    const int64_t idx = first + t / fp;                               // (k, n) flat index
-    const int f = (int)(t % fp);
+    const int fp_emit = compact ? 1 : fp;
+    if (t >= count * fp_emit) return;
+    const int64_t idx = first + t / fp_emit;                          // (k, n) flat index
     uint32_t key = KEY_DEAD;
     if (P.good[idx]) {
-        uint32_t l, m;
-        if (slot_cell(P.gi[idx], P.gj[idx], f, lo, hi, P.G, &l, &m)) {
-            const int n = (int)(idx % P.nf);
+        const int n = (int)(idx % P.nf);
+        const int f0 = compact ? 0 : (int)(t % fp), f1 = compact ? fp : f0 + 1;
+        for (int f = f0; f < f1; f++) {
+            uint32_t l, m;
+            if (!slot_cell(P.gi[idx], P.gj[idx], f, lo, hi, P.G, &l, &m)) continue;
             bool live = true;
             if (mode == 0) live = conv_value(P, idx / P.nf, n, l, m) != 0.0;
-            if (live) key = (l * (uint32_t)P.G + m) * (uint32_t)P.nch + (P.spectral ? (uint32_t)n : 0u);
+            if (live) {
+                key = (l * (uint32_t)P.G + m) * (uint32_t)P.nch + (P.spectral ? (uint32_t)n : 0u);
+                break;
+            }
         }
     }
     keys[t] = key;
@@ -168,49 +177,81 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t *__r
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];     // digit-major
 }
 
-// exclusive scan of `n` uint32 in place, single block (n = 256 * nblocks)
-__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ data, int64_t n)
+// Exclusive scan of `n` uint32 in place, three small kernels: per-segment scan + segment totals,
+// single-block scan of the totals, add-back.  SCAN_SEG elements per block.
+constexpr int SCAN_SEG = 1024 * 8;
+
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t x, uint32_t *warp_sums, uint32_t *total)
 {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024 * 4) {
-        const int64_t e0 = base + (int64_t)threadIdx.x * 4;
-        uint32_t v[4];
+    uint32_t inc = x;
 #pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = (e0 + q < n) ? data[e0 + q] : 0u;
-        const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
-        uint32_t x = tsum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = warp_sums[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            const uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
         }
-        if (lane == 31) warp_sums[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t s = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += y;
-            }
-            warp_sums[lane] = s;          // inclusive over warps
-        }
-        __syncthreads();
-        const uint32_t carry = carry_s;
-        uint32_t excl = carry + (wid ? warp_sums[wid - 1] : 0u) + (x - tsum);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (e0 + q < n) data[e0 + q] = excl;
-            excl += v[q];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
-        __syncthreads();
+        warp_sums[lane] = s;          // inclusive over warps
     }
+    __syncthreads();
+    const uint32_t base = wid ? warp_sums[wid - 1] : 0u;
+    *total = warp_sums[31];
+    __syncthreads();
+    return base + inc - x;
+}
+
+__global__ void __launch_bounds__(1024) rs_scan_seg_kernel(uint32_t *__restrict__ data, int64_t n,
+                                                           uint32_t *__restrict__ seg_totals)
+{
+    __shared__ uint32_t warp_sums[32];
+    const int64_t e0 = (int64_t)blockIdx.x * SCAN_SEG + (int64_t)threadIdx.x * 8;
+    uint32_t v[8], tsum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        v[q] = (e0 + q < n) ? data[e0 + q] : 0u;
+        tsum += v[q];
+    }
+    uint32_t total;
+    uint32_t excl = block_excl_scan_1024(tsum, warp_sums, &total);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (e0 + q < n) data[e0 + q] = excl;
+        excl += v[q];
+    }
+    if (threadIdx.x == 0) seg_totals[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of up to any number of segment totals (loops in chunks of 1024)
+__global__ void __launch_bounds__(1024) rs_scan_totals_kernel(uint32_t *__restrict__ t, int nseg)
+{
+    __shared__ uint32_t warp_sums[32];
+    uint32_t carry = 0;
+    for (int base = 0; base < nseg; base += 1024) {
+        const int e = base + threadIdx.x;
+        const uint32_t x = e < nseg ? t[e] : 0u;
+        uint32_t total;
+        const uint32_t excl = block_excl_scan_1024(x, warp_sums, &total);
+        if (e < nseg) t[e] = carry + excl;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(1024) rs_scan_add_kernel(uint32_t *__restrict__ data, int64_t n,
+                                                           const uint32_t *__restrict__ seg_offsets)
+{
+    const uint32_t off = seg_offsets[blockIdx.x];
+    const int64_t e0 = (int64_t)blockIdx.x * SCAN_SEG + (int64_t)threadIdx.x * 8;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        if (e0 + q < n) data[e0 + q] += off;
 }
 
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t *__restrict__ keys_in,
@@ -280,7 +321,12 @@ static int radix_sort(SortBufs b, int64_t n, int nbits, uint32_t **ko, uint32_t 
         }
         {
             LaunchScope ls("grid_sort_scan");
-            rs_scan_kernel<<<1, 1024, 0, c.stream>>>(b.hist, (int64_t)256 * nblocks);
+            const int64_t nh = (int64_t)256 * nblocks;
+            const int nseg = ceil_div(nh, SCAN_SEG);
+            uint32_t *seg = b.hist + nh;                  // scratch behind the histogram
+            rs_scan_seg_kernel<<<nseg, 1024, 0, c.stream>>>(b.hist, nh, seg);
+            rs_scan_totals_kernel<<<1, 1024, 0, c.stream>>>(seg, nseg);
+            rs_scan_add_kernel<<<nseg, 1024, 0, c.stream>>>(b.hist, nh, seg);
             PDSB_CUDA(cudaGetLastError());
         }
         {
@@ -308,43 +354,91 @@ __device__ __forceinline__ int64_t lower_bound_u32(const uint32_t *a, int64_t n,
     return lo;
 }
 
-// mode 0: out_re/out_im/out_w += {re,im,1} * w * c ; mode 1: out_w += w (binned weights)
-__global__ void __launch_bounds__(128) grid_accumulate_kernel(GridParams P, int mode, uint32_t lo, uint32_t hi,
-                                                              int64_t first, int fp,
-                                                              const uint32_t *__restrict__ keys,
-                                                              const uint32_t *__restrict__ ids, int64_t ncontrib,
-                                                              double *out_re, double *out_im, double *out_w)
+// Step 1 (parallel over sorted contributions): the addends, in sorted order.
+//   mode 0: val[0..2][p] = real*w*c, imag*w*c, w*c  (left to right, non-contracted  :514-520)
+//   mode 1: val[2][p] = w                           (binned weights)
+__global__ void __launch_bounds__(256) grid_values_kernel(GridParams P, int mode, int64_t first, int fp_emit,
+                                                          const uint32_t *__restrict__ keys,
+                                                          const uint32_t *__restrict__ ids, int64_t ncontrib,
+                                                          double *__restrict__ v_re, double *__restrict__ v_im,
+                                                          double *__restrict__ v_w)
+{
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= ncontrib) return;
+    const uint32_t key = keys[p];
+    if (key == KEY_DEAD) return;
+    const int64_t idx = first + ids[p] / fp_emit;
+    const double w = P.w[idx];
+    if (mode == 0) {
+        const uint32_t lm = key / (uint32_t)P.nch;
+        const double cv = conv_value(P, idx / P.nf, (int)(idx % P.nf), lm / (uint32_t)P.G, lm % (uint32_t)P.G);
+        v_re[p] = __dmul_rn(__dmul_rn(P.re[idx], w), cv);
+        v_im[p] = __dmul_rn(__dmul_rn(P.im[idx], w), cv);
+        v_w[p] = __dmul_rn(w, cv);
+    } else {
+        v_w[p] = w;
+    }
+}
+
+// Step 2: one thread per output cell adds its run in order.  The loads do not depend on the
+// running sums, so they are issued 8 ahead; the chain per element is one dependent DADD per map.
+__global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t ncell,
+                                                               const uint32_t *__restrict__ keys, int64_t ncontrib,
+                                                               const double *__restrict__ v_re,
+                                                               const double *__restrict__ v_im,
+                                                               const double *__restrict__ v_w, double *out_re,
+                                                               double *out_im, double *out_w)
 {
     const int64_t cell = (int64_t)blockIdx.x * 128 + threadIdx.x;      // (l*G+m)*nch + c
-    const int64_t ncell = (int64_t)P.G * P.G * P.nch;
     if (cell >= ncell) return;
     int64_t p = lower_bound_u32(keys, ncontrib, (uint32_t)cell);
     if (p >= ncontrib || keys[p] != (uint32_t)cell) return;
-    const uint32_t lm = (uint32_t)(cell / P.nch);
-    const uint32_t l = lm / (uint32_t)P.G, m = lm % (uint32_t)P.G;
+    int64_t e = p + 1;
+    {   // end of the run: gallop then bisect
+        int64_t step = 1;
+        while (e < ncontrib && keys[e] == (uint32_t)cell) {
+            e += step;
+            step <<= 1;
+        }
+        if (e > ncontrib) e = ncontrib;
+        int64_t lo = p, hi = e;                // keys[lo]==cell ; keys[hi]!=cell or hi==ncontrib
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (keys[mid] == (uint32_t)cell) lo = mid;
+            else hi = mid;
+        }
+        e = lo + 1;
+    }
     double sr = 0, si = 0, sw = out_w[cell];
     if (mode == 0) {
         sr = out_re[cell];
         si = out_im[cell];
-    }
-    for (; p < ncontrib && keys[p] == (uint32_t)cell; p++) {
-        const int64_t idx = first + ids[p] / fp;
-        const double w = P.w[idx];
-        if (mode == 0) {
-            const double cv = conv_value(P, idx / P.nf, (int)(idx % P.nf), l, m);
-            // new_real[l,m,c] += real[k,n]*weights[k,n]*convolve   (left to right, no FMA)  :514-520
-            sr = __dadd_rn(sr, __dmul_rn(__dmul_rn(P.re[idx], w), cv));
-            si = __dadd_rn(si, __dmul_rn(__dmul_rn(P.im[idx], w), cv));
-            sw = __dadd_rn(sw, __dmul_rn(w, cv));
-        } else {
-            sw = __dadd_rn(sw, w);
+        for (; p + 8 <= e; p += 8) {
+            double a[8], b[8], c[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                a[q] = v_re[p + q];
+                b[q] = v_im[p + q];
+                c[q] = v_w[p + q];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                sr = __dadd_rn(sr, a[q]);
+                si = __dadd_rn(si, b[q]);
+                sw = __dadd_rn(sw, c[q]);
+            }
         }
-    }
-    out_w[cell] = sw;
-    if (mode == 0) {
+        for (; p < e; p++) {
+            sr = __dadd_rn(sr, v_re[p]);
+            si = __dadd_rn(si, v_im[p]);
+            sw = __dadd_rn(sw, v_w[p]);
+        }
         out_re[cell] = sr;
         out_im[cell] = si;
+    } else {
+        for (; p < e; p++) sw = __dadd_rn(sw, v_w[p]);
     }
+    out_w[cell] = sw;
 }
 
 // ---- fast (atomic) scatter -------------------------------------------------------------------
@@ -374,6 +468,98 @@ __global__ void __launch_bounds__(256) grid_scatter_atomic_kernel(GridParams P, 
     }
 }
 
+// ---- fast mode: sorted uv tiles, on-chip accumulation, then global atomics -------------------
+// Visibilities are sorted by (channel, 8x8-cell home tile).  One CTA takes one tile's run: the
+// visibilities are staged through shared memory 128 at a time; each thread owns ONE cell of the
+// tile's footprint region ((8+lo+hi)^2 cells: 13x13 for expsinc) and accumulates it in registers,
+// so there are no atomics on chip at all; only the finished region is added to the map with one
+// fp64 atomic per cell and map (neighbouring tiles overlap in the halo).
+constexpr int GT_THREADS = 256;
+constexpr int GT_STAGE = 128;
+constexpr int GT_SUBRUN = 4096;      // visibilities one CTA handles before another CTA (blockIdx.y) takes over
+
+// start of every non-empty tile's run in the sorted key array (unordered compact list)
+__global__ void __launch_bounds__(256) grid_tile_heads_kernel(const uint32_t *__restrict__ keys, int64_t nvis,
+                                                              uint32_t *__restrict__ heads, uint32_t *count)
+{
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= nvis) return;
+    const uint32_t key = keys[p];
+    if (key == KEY_DEAD) return;
+    if (p == 0 || keys[p - 1] != key) heads[atomicAdd(count, 1u)] = (uint32_t)p;
+}
+
+__global__ void __launch_bounds__(GT_THREADS) grid_tile_kernel(GridParams P, int mode, int lo, int hi, uint32_t tg,
+                                                               const uint32_t *__restrict__ keys,
+                                                               const uint32_t *__restrict__ order, int64_t nvis,
+                                                               const uint32_t *__restrict__ heads,
+                                                               const uint32_t *__restrict__ nheads,
+                                                               double *out_re, double *out_im, double *out_w)
+{
+    __shared__ int64_t s_run[2];
+    __shared__ double s_us[GT_STAGE], s_vs[GT_STAGE], s_re[GT_STAGE], s_im[GT_STAGE], s_w[GT_STAGE];
+    __shared__ int s_i[GT_STAGE], s_j[GT_STAGE];
+    if (blockIdx.x >= *nheads) return;
+    const int64_t rs = heads[blockIdx.x];
+    const uint32_t key = keys[rs];
+    if (threadIdx.x == 0) s_run[1] = lower_bound_u32(keys, nvis, key + 1u);
+    __syncthreads();
+    const int64_t re_ = s_run[1];
+    if (rs + (int64_t)blockIdx.y * GT_SUBRUN >= re_) return;
+    const uint32_t chan = key / (tg * tg), tile = key % (tg * tg);
+    const int tl = (int)(tile / tg), tm = (int)(tile % tg);
+    const int side = 8 + lo + hi;
+    const int c = threadIdx.x;
+    const int l = tl * 8 - lo + c / side, m = tm * 8 - lo + c % side;
+    const bool active = c < side * side && l >= 0 && m >= 0 && l < P.G && m < P.G;
+    const double uu_m = active ? P.uu[m] : 0.0, vv_l = active ? P.vv[l] : 0.0;
+    double ar = 0.0, ai = 0.0, aw = 0.0;
+    for (int64_t sub = rs + (int64_t)blockIdx.y * GT_SUBRUN; sub < re_; sub += (int64_t)gridDim.y * GT_SUBRUN) {
+        const int64_t sub_end = sub + GT_SUBRUN < re_ ? sub + GT_SUBRUN : re_;
+        for (int64_t base = sub; base < sub_end; base += GT_STAGE) {
+            const int n_here = (int)(sub_end - base < GT_STAGE ? sub_end - base : GT_STAGE);
+            if (threadIdx.x < n_here) {
+                const int64_t idx = order[base + threadIdx.x];
+                const int64_t k = idx / P.nf;
+                const double f = P.freq[idx % P.nf];
+                s_us[threadIdx.x] = __dmul_rn(__dmul_rn(P.u[k], f), P.inv_freq);
+                s_vs[threadIdx.x] = __dmul_rn(__dmul_rn(P.v[k], f), P.inv_freq);
+                const double w = P.w[idx];
+                s_w[threadIdx.x] = w;
+                s_re[threadIdx.x] = P.re[idx] * w;
+                s_im[threadIdx.x] = P.im[idx] * w;
+                s_i[threadIdx.x] = (int)P.gi[idx];
+                s_j[threadIdx.x] = (int)P.gj[idx];
+            }
+            __syncthreads();
+            if (active) {
+                for (int q = 0; q < n_here; q++) {
+                    const int dj = l - s_j[q], di = m - s_i[q];
+                    if (dj < -lo || dj > hi || di < -lo || di > hi) continue;
+                    if (mode == 0) {
+                        const double du = (s_us[q] - uu_m) * P.inv_binsize, dv = (s_vs[q] - vv_l) * P.inv_binsize;
+                        const double cv = P.conv ? k_exp_sinc(du, dv) : k_ones(du, dv);
+                        ar += s_re[q] * cv;
+                        ai += s_im[q] * cv;
+                        aw += s_w[q] * cv;
+                    } else {
+                        aw += s_w[q];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (active) {
+        const int64_t cell = ((int64_t)l * P.G + m) * P.nch + chan;
+        if (mode == 0) {
+            if (ar != 0.0) atomicAdd(out_re + cell, ar);
+            if (ai != 0.0) atomicAdd(out_im + cell, ai);
+        }
+        if (aw != 0.0) atomicAdd(out_w + cell, aw);
+    }
+}
+
 // ---- re-weighting, normalisation ---------------------------------------------------------------
 __global__ void __launch_bounds__(256) fill_kernel(double *a, int64_t n, double v)
 {
@@ -399,14 +585,16 @@ __global__ void __launch_bounds__(256) grid_reweight_kernel(GridParams P, const 
     else P.w[idx] = P.w[idx] / b;
 }
 
-// column sums with stride: out[c] = sum_q f(a[q*ncol + c]); square != 0 sums a^2.  One block per column.
+// Column sums with stride, stage 1: part[b][c] = sum over this block's rows of f(a[q*ncol + c]);
+// square != 0 sums a^2.  grid = (row blocks, columns).  Stage 2 adds the row blocks in order.
+constexpr int SUM_BLOCKS = 256;
 __global__ void __launch_bounds__(256) strided_sum_kernel(const double *__restrict__ a, int64_t nrow, int ncol,
-                                                          int square, double *__restrict__ out)
+                                                          int square, double *__restrict__ part)
 {
     __shared__ double sh[8];
-    const int c = blockIdx.x;
+    const int c = blockIdx.y;
     double s = 0.0;
-    for (int64_t q = threadIdx.x; q < nrow; q += 256) {
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < nrow; q += (int64_t)gridDim.x * 256) {
         const double x = a[q * ncol + c];
         s += square ? x * x : x;
     }
@@ -417,8 +605,17 @@ __global__ void __launch_bounds__(256) strided_sum_kernel(const double *__restri
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < 8; w++) t += sh[w];
-        out[c] = t;
+        part[(size_t)blockIdx.x * ncol + c] = t;
     }
+}
+__global__ void __launch_bounds__(256) strided_sum_final_kernel(const double *__restrict__ part, int nb, int ncol,
+                                                                double *__restrict__ out)
+{
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= ncol) return;
+    double t = 0.0;
+    for (int b = 0; b < nb; b++) t += part[(size_t)b * ncol + c];
+    out[c] = t;
 }
 
 // f2[n] = (5*10**(-robust))**2 / (sumb2[c] / sumw[n])     :476-477
@@ -466,7 +663,8 @@ __global__ void __launch_bounds__(256) grid_home_keys_kernel(GridParams P, uint3
     if (idx >= P.nuv * P.nf) return;
     // coarse 8x8-cell tiles keep neighbouring visibilities together without a full-resolution sort
     const uint32_t tg = ((uint32_t)P.G + 7u) >> 3;
-    keys[idx] = P.good[idx] ? ((P.gj[idx] >> 3) * tg + (P.gi[idx] >> 3)) : KEY_DEAD;
+    const uint32_t chan = P.spectral ? (uint32_t)(idx % P.nf) : 0u;
+    keys[idx] = P.good[idx] ? (chan * tg * tg + (P.gj[idx] >> 3) * tg + (P.gi[idx] >> 3)) : KEY_DEAD;
     ids[idx] = (uint32_t)idx;
 }
 
@@ -615,6 +813,21 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
         PDSB_CUDA(cudaGetLastError());
     }
 
+    auto hist_bytes = [&](int64_t n) -> size_t {
+        const size_t nh = (size_t)256 * ceil_div(n, RS_TILE);
+        return (nh + nh / SCAN_SEG + 16) * sizeof(uint32_t) + 1024;
+    };
+    // out[c] = sum_q f(a[q*ncol + c]) in a fixed order (two stages)
+    auto sum_columns = [&](const double *a, int64_t nrow, int ncol, int square, double *out) -> int {
+        const int nb = (int)std::min<int64_t>(SUM_BLOCKS, std::max<int64_t>(1, (nrow + 255) / 256));
+        PDSB_CHECK(c.red.ensure((size_t)nb * ncol * sizeof(double)));
+        LaunchScope ls("grid_sum");
+        strided_sum_kernel<<<dim3(nb, ncol), 256, 0, c.stream>>>(a, nrow, ncol, square, c.red.as<double>());
+        strided_sum_final_kernel<<<ceil_div(ncol, 256), 256, 0, c.stream>>>(c.red.as<double>(), nb, ncol, out);
+        PDSB_CUDA(cudaGetLastError());
+        return PDSB_OK;
+    };
+
     // one engine for both scatters (mode 0 main, mode 1 binned weights)
     auto scatter = [&](int smode, uint32_t lo, uint32_t hi, double *t_re, double *t_im, double *t_w) -> int {
         if (nvis == 0) return PDSB_OK;
@@ -622,8 +835,7 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
         if (!deterministic) {
             // order visibilities by coarse home tile so concurrent atomics share L2 lines
             const uint32_t tg = ((uint32_t)G + 7u) >> 3;
-            PDSB_CHECK(c.stage_d.ensure((size_t)nvis * 4 * sizeof(uint32_t) +
-                                        (size_t)256 * ceil_div(nvis, RS_TILE) * sizeof(uint32_t) + 1024));
+            PDSB_CHECK(c.stage_d.ensure((size_t)nvis * 4 * sizeof(uint32_t) + hist_bytes(nvis)));
             uint32_t *k0 = c.stage_d.as<uint32_t>(), *v0 = k0 + nvis, *k1 = v0 + nvis, *v1 = k1 + nvis;
             uint32_t *hist = v1 + nvis;
             {
@@ -633,40 +845,69 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
             }
             uint32_t *ko, *vo;
             SortBufs sb{k0, v0, k1, v1, hist};
-            PDSB_CHECK(radix_sort(sb, nvis, bits_for((uint64_t)tg * tg), &ko, &vo));
+            const uint64_t nkeys = (uint64_t)tg * tg * (uint64_t)nch;
+            int tbits = bits_for(nkeys);
+            tbits = ((tbits + 7) / 8) * 8 > 32 ? 32 : ((tbits + 7) / 8) * 8;
+            PDSB_CHECK(radix_sort(sb, nvis, tbits, &ko, &vo));
+            const int side = 8 + (int)lo + (int)hi;
+            if (side * side <= GT_THREADS && nkeys < (uint64_t)1 << 31) {
+                const uint64_t max_heads = std::min<uint64_t>(nkeys, (uint64_t)nvis);
+                PDSB_CHECK(c.stage_e.ensure((max_heads + 4) * sizeof(uint32_t)));
+                uint32_t *heads = c.stage_e.as<uint32_t>() + 4, *nheads = c.stage_e.as<uint32_t>();
+                PDSB_CUDA(cudaMemsetAsync(nheads, 0, sizeof(uint32_t), c.stream));
+                {
+                    LaunchScope ls("grid_tile_heads");
+                    grid_tile_heads_kernel<<<ceil_div(nvis, 256), 256, 0, c.stream>>>(ko, nvis, heads, nheads);
+                    PDSB_CUDA(cudaGetLastError());
+                }
+                LaunchScope ls("grid_tile");
+                grid_tile_kernel<<<dim3((unsigned)max_heads, 8), GT_THREADS, 0, c.stream>>>(
+                    P, smode, (int)lo, (int)hi, tg, ko, vo, nvis, heads, nheads, t_re, t_im, t_w);
+                PDSB_CUDA(cudaGetLastError());
+                return PDSB_OK;
+            }
+            // footprints wider than the tile kernel's region: plain atomics in tile order
             LaunchScope ls("grid_scatter_atomic");
             grid_scatter_atomic_kernel<<<ceil_div(nvis * fp, 256), 256, 0, c.stream>>>(P, smode, lo, hi, fp, vo, t_re,
                                                                                        t_im, t_w);
             PDSB_CUDA(cudaGetLastError());
             return PDSB_OK;
         }
-        // deterministic: batches of at most 2^28 contributions, processed in (k,n) order
-        const int64_t max_contrib = (int64_t)1 << 28;
-        int64_t per_batch = std::max<int64_t>(1, max_contrib / fp);
+        // deterministic: batches of at most 2^27 contributions, processed in (k,n) order
+        const int compact = (smode == 0 && convolution == PDSB_CONV_PILLBOX) ? 1 : 0;
+        const int fp_emit = compact ? 1 : fp;
+        const int64_t max_contrib = (int64_t)1 << 27;
+        int64_t per_batch = std::max<int64_t>(1, max_contrib / fp_emit);
         const int nbits = bits_for((uint64_t)ncell);          // dead keys (all ones) sort last
         const int sort_bits = ((nbits + 7) / 8) * 8 > 32 ? 32 : ((nbits + 7) / 8) * 8;
         for (int64_t first = 0; first < nvis; first += per_batch) {
             const int64_t count = std::min(per_batch, nvis - first);
-            const int64_t ncontrib = count * fp;
-            PDSB_CHECK(c.stage_d.ensure((size_t)ncontrib * 4 * sizeof(uint32_t) +
-                                        (size_t)256 * ceil_div(ncontrib, RS_TILE) * sizeof(uint32_t) + 1024));
+            const int64_t ncontrib = count * fp_emit;
+            PDSB_CHECK(c.stage_d.ensure((size_t)ncontrib * 4 * sizeof(uint32_t) + hist_bytes(ncontrib)));
+            PDSB_CHECK(c.stage_e.ensure((size_t)ncontrib * 3 * sizeof(double)));
             uint32_t *k0 = c.stage_d.as<uint32_t>(), *v0 = k0 + ncontrib, *k1 = v0 + ncontrib, *v1 = k1 + ncontrib;
             uint32_t *hist = v1 + ncontrib;
+            double *val_re = c.stage_e.as<double>(), *val_im = val_re + ncontrib, *val_w = val_im + ncontrib;
             {
                 LaunchScope ls("grid_emit_keys");
                 grid_emit_keys_kernel<<<ceil_div(ncontrib, 256), 256, 0, c.stream>>>(P, smode, lo, hi, first, count, fp,
-                                                                                    k0, v0);
+                                                                                    compact, k0, v0);
                 PDSB_CUDA(cudaGetLastError());
             }
             uint32_t *ko, *vo;
             SortBufs sb{k0, v0, k1, v1, hist};
-            // dead keys have every bit set, so sorting on sort_bits bits still puts them last only if
-            // sort_bits covers a zero bit of every live key above... live keys < 2^nbits <= 2^sort_bits;
-            // dead keys share the low sort_bits with 2^sort_bits-1, which is >= any live key: fine.
+            // live keys are < 2^nbits <= 2^sort_bits; dead keys (all ones) compare >= any live key on
+            // the low sort_bits, so they end up behind every live run.
             PDSB_CHECK(radix_sort(sb, ncontrib, sort_bits, &ko, &vo));
-            LaunchScope ls("grid_accumulate");
-            grid_accumulate_kernel<<<ceil_div(ncell, 128), 128, 0, c.stream>>>(P, smode, lo, hi, first, fp, ko, vo,
-                                                                              ncontrib, t_re, t_im, t_w);
+            {
+                LaunchScope ls("grid_values");
+                grid_values_kernel<<<ceil_div(ncontrib, 256), 256, 0, c.stream>>>(P, smode, first, fp_emit, ko, vo,
+                                                                                 ncontrib, val_re, val_im, val_w);
+                PDSB_CUDA(cudaGetLastError());
+            }
+            LaunchScope ls("grid_ordered_sum");
+            grid_ordered_sum_kernel<<<ceil_div(ncell, 128), 128, 0, c.stream>>>(smode, ncell, ko, ncontrib, val_re,
+                                                                               val_im, val_w, t_re, t_im, t_w);
             PDSB_CUDA(cudaGetLastError());
         }
         return PDSB_OK;
@@ -684,16 +925,8 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
         const double *f2 = nullptr;
         if (weighting == PDSB_WT_ROBUST) {
             double *sumb2 = small, *sumw = small + nf, *f2w = small + 2 * nf;
-            {
-                LaunchScope ls("grid_sum");
-                strided_sum_kernel<<<nch, 256, 0, c.stream>>>(binned, (int64_t)G * G, nch, 1, sumb2);
-                PDSB_CUDA(cudaGetLastError());
-            }
-            {
-                LaunchScope ls("grid_sum");
-                strided_sum_kernel<<<nf, 256, 0, c.stream>>>(w_work, nuv, nf, 0, sumw);
-                PDSB_CUDA(cudaGetLastError());
-            }
+            PDSB_CHECK(sum_columns(binned, (int64_t)G * G, nch, 1, sumb2));
+            PDSB_CHECK(sum_columns(w_work, nuv, nf, 0, sumw));
             PDSB_REQUIRE(nf <= 1024, "robust weighting supports at most 1024 channels");
             const double ra = 5 * pow(10.0, -robust);       // host libm, as Python's 5*10**(-robust)
             robust_f2_kernel<<<1, 1024, 0, c.stream>>>(sumb2, sumw, nf, P.spectral, ra * ra, f2w);
@@ -715,12 +948,9 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
         double *wsum = small + 3 * nf;
         if (imaging) {
             PDSB_REQUIRE(nch <= nf, "channels");
-            // per-channel sum of the weight map
-            LaunchScope ls("grid_sum");
-            strided_sum_kernel<<<nch, 256, 0, c.stream>>>(o_w, (int64_t)G * G, nch, 0,
-                                                          nch == 1 ? wsum : binned);   // binned is free now
-            PDSB_CUDA(cudaGetLastError());
+            // per-channel sum of the weight map (binned is free now)
             if (nch != 1) wsum = binned;
+            PDSB_CHECK(sum_columns(o_w, (int64_t)G * G, nch, 0, wsum));
         }
         LaunchScope ls("grid_normalise");
         grid_normalise_kernel<<<ceil_div(ncell, 256), 256, 0, c.stream>>>(o_re, o_im, o_w, ncell, nch, imaging ? 1 : 0,
