@@ -50,6 +50,16 @@ __device__ __forceinline__ double k_exp_sinc(double u, double v)
     return k_sinc(u * inv_alpha1) * k_sinc(v * inv_alpha1) * k_exp(-1 * (a * a)) * k_exp(-1 * (b * b)) *
            (1. / norm);
 }
+// exp_sinc is separable: exp_sinc(u,v) = g(u) g(v) / norm with g(x) = sinc(x/1.55) exp(-(x/2.52)^2)
+// inside |x| < 3.  The fast mode evaluates 6+6 one-dimensional factors per visibility instead of
+// 36 two-dimensional values (the product order differs from the reference's at the 1e-16 level,
+// which is below the fast mode's own summation-order noise).
+__device__ __forceinline__ double k_exp_sinc_1d(double x)
+{
+    if (fabs(x) >= 3.0) return 0.;
+    const double a = x * (1. / 2.52);
+    return k_sinc(x * (1. / 1.55)) * k_exp(-1 * (a * a));
+}
 __device__ __forceinline__ double k_ones(double u, double v)
 {
     if (fabs(u) >= 0.5 || fabs(v) >= 0.5) return 0.;
@@ -380,8 +390,12 @@ __global__ void __launch_bounds__(256) grid_values_kernel(GridParams P, int mode
     }
 }
 
-// Step 2: one thread per output cell adds its run in order.  The loads do not depend on the
-// running sums, so they are issued 8 ahead; the chain per element is one dependent DADD per map.
+// Step 2: ordered sums.  A warp takes 32 consecutive cells; every lane locates its own run.
+// Short runs are added by the owning lane.  Long runs (the dense centre of the uv plane) are
+// streamed by the whole warp: 32 lanes fetch 32 consecutive addends of each map into shared
+// memory (coalesced, independent of the running sum), then the owning lane adds them in order -
+// the serial chain per element is one dependent DADD per map and nothing else.
+constexpr int OS_LONG = 96;
 __global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t ncell,
                                                                const uint32_t *__restrict__ keys, int64_t ncontrib,
                                                                const double *__restrict__ v_re,
@@ -389,56 +403,89 @@ __global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t
                                                                const double *__restrict__ v_w, double *out_re,
                                                                double *out_im, double *out_w)
 {
+    __shared__ double sbuf[4][3][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t cell = (int64_t)blockIdx.x * 128 + threadIdx.x;      // (l*G+m)*nch + c
-    if (cell >= ncell) return;
-    int64_t p = lower_bound_u32(keys, ncontrib, (uint32_t)cell);
-    if (p >= ncontrib || keys[p] != (uint32_t)cell) return;
-    int64_t e = p + 1;
-    {   // end of the run: gallop then bisect
-        int64_t step = 1;
-        while (e < ncontrib && keys[e] == (uint32_t)cell) {
-            e += step;
-            step <<= 1;
+    int64_t p = 0, e = 0;
+    if (cell < ncell) {
+        p = lower_bound_u32(keys, ncontrib, (uint32_t)cell);
+        if (p < ncontrib && keys[p] == (uint32_t)cell) {
+            e = p + 1;
+            int64_t step = 1;                      // end of the run: gallop then bisect
+            while (e < ncontrib && keys[e] == (uint32_t)cell) {
+                e += step;
+                step <<= 1;
+            }
+            if (e > ncontrib) e = ncontrib;
+            int64_t lo = p, hi = e;                // keys[lo]==cell ; keys[hi]!=cell or hi==ncontrib
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (keys[mid] == (uint32_t)cell) lo = mid;
+                else hi = mid;
+            }
+            e = lo + 1;
+        } else {
+            p = e = 0;
         }
-        if (e > ncontrib) e = ncontrib;
-        int64_t lo = p, hi = e;                // keys[lo]==cell ; keys[hi]!=cell or hi==ncontrib
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (keys[mid] == (uint32_t)cell) lo = mid;
-            else hi = mid;
-        }
-        e = lo + 1;
     }
-    double sr = 0, si = 0, sw = out_w[cell];
-    if (mode == 0) {
-        sr = out_re[cell];
-        si = out_im[cell];
-        for (; p + 8 <= e; p += 8) {
-            double a[8], b[8], c[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                a[q] = v_re[p + q];
-                b[q] = v_im[p + q];
-                c[q] = v_w[p + q];
-            }
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                sr = __dadd_rn(sr, a[q]);
-                si = __dadd_rn(si, b[q]);
-                sw = __dadd_rn(sw, c[q]);
-            }
+    const bool has = e > p;
+    double sr = 0, si = 0, sw = 0;
+    if (has) {
+        sw = out_w[cell];
+        if (mode == 0) {
+            sr = out_re[cell];
+            si = out_im[cell];
         }
+    }
+    const bool is_long = has && (e - p) > OS_LONG;
+    if (has && !is_long) {
         for (; p < e; p++) {
-            sr = __dadd_rn(sr, v_re[p]);
-            si = __dadd_rn(si, v_im[p]);
+            if (mode == 0) {
+                sr = __dadd_rn(sr, v_re[p]);
+                si = __dadd_rn(si, v_im[p]);
+            }
             sw = __dadd_rn(sw, v_w[p]);
         }
-        out_re[cell] = sr;
-        out_im[cell] = si;
-    } else {
-        for (; p < e; p++) sw = __dadd_rn(sw, v_w[p]);
     }
-    out_w[cell] = sw;
+    unsigned long_mask = __ballot_sync(0xffffffffu, is_long);
+    while (long_mask) {
+        const int owner = __ffs(long_mask) - 1;
+        long_mask &= long_mask - 1;
+        const int64_t rp = __shfl_sync(0xffffffffu, p, owner), re_ = __shfl_sync(0xffffffffu, e, owner);
+        for (int64_t base = rp; base < re_; base += 32) {
+            const int64_t q = base + lane;
+            if (q < re_) {
+                if (mode == 0) {
+                    sbuf[wid][0][lane] = v_re[q];
+                    sbuf[wid][1][lane] = v_im[q];
+                }
+                sbuf[wid][2][lane] = v_w[q];
+            }
+            __syncwarp();
+            if (lane == owner) {
+                const int n = (int)(re_ - base < 32 ? re_ - base : 32);
+                if (mode == 0) {
+#pragma unroll 8
+                    for (int t = 0; t < n; t++) {
+                        sr = __dadd_rn(sr, sbuf[wid][0][t]);
+                        si = __dadd_rn(si, sbuf[wid][1][t]);
+                        sw = __dadd_rn(sw, sbuf[wid][2][t]);
+                    }
+                } else {
+#pragma unroll 8
+                    for (int t = 0; t < n; t++) sw = __dadd_rn(sw, sbuf[wid][2][t]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (has) {
+        out_w[cell] = sw;
+        if (mode == 0) {
+            out_re[cell] = sr;
+            out_im[cell] = si;
+        }
+    }
 }
 
 // ---- fast (atomic) scatter -------------------------------------------------------------------
@@ -476,79 +523,99 @@ __global__ void __launch_bounds__(256) grid_scatter_atomic_kernel(GridParams P, 
 // fp64 atomic per cell and map (neighbouring tiles overlap in the halo).
 constexpr int GT_THREADS = 256;
 constexpr int GT_STAGE = 128;
-constexpr int GT_SUBRUN = 4096;      // visibilities one CTA handles before another CTA (blockIdx.y) takes over
+constexpr int GT_SUBRUN = 2048;      // visibilities per work item (one CTA)
 
-// start of every non-empty tile's run in the sorted key array (unordered compact list)
-__global__ void __launch_bounds__(256) grid_tile_heads_kernel(const uint32_t *__restrict__ keys, int64_t nvis,
-                                                              uint32_t *__restrict__ heads, uint32_t *count)
+// Work list: every non-empty tile's run in the sorted key array, cut into items of at most
+// GT_SUBRUN visibilities so that the dense central tiles spread over many CTAs.
+__global__ void __launch_bounds__(256) grid_tile_items_kernel(const uint32_t *__restrict__ keys, int64_t nvis,
+                                                              uint2 *__restrict__ items, uint32_t *count)
 {
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (p >= nvis) return;
     const uint32_t key = keys[p];
     if (key == KEY_DEAD) return;
-    if (p == 0 || keys[p - 1] != key) heads[atomicAdd(count, 1u)] = (uint32_t)p;
+    if (p != 0 && keys[p - 1] == key) return;                 // not a run head
+    const int64_t e = lower_bound_u32(keys, nvis, key + 1u);
+    const uint32_t nitems = (uint32_t)((e - p + GT_SUBRUN - 1) / GT_SUBRUN);
+    uint32_t slot = atomicAdd(count, nitems);
+    for (int64_t b = p; b < e; b += GT_SUBRUN)
+        items[slot++] = make_uint2((uint32_t)b, (uint32_t)(b + GT_SUBRUN < e ? b + GT_SUBRUN : e));
 }
 
 __global__ void __launch_bounds__(GT_THREADS) grid_tile_kernel(GridParams P, int mode, int lo, int hi, uint32_t tg,
                                                                const uint32_t *__restrict__ keys,
-                                                               const uint32_t *__restrict__ order, int64_t nvis,
-                                                               const uint32_t *__restrict__ heads,
-                                                               const uint32_t *__restrict__ nheads,
+                                                               const uint32_t *__restrict__ order,
+                                                               const uint2 *__restrict__ items,
+                                                               const uint32_t *__restrict__ nitems,
                                                                double *out_re, double *out_im, double *out_w)
 {
-    __shared__ int64_t s_run[2];
-    __shared__ double s_us[GT_STAGE], s_vs[GT_STAGE], s_re[GT_STAGE], s_im[GT_STAGE], s_w[GT_STAGE];
+    constexpr int MAXW = 8;            // widest footprint handled here (expsinc: 6, superuniform box: 7)
+    __shared__ double s_re[GT_STAGE], s_im[GT_STAGE], s_w[GT_STAGE];
+    __shared__ double s_fu[GT_STAGE][MAXW], s_fv[GT_STAGE][MAXW];
     __shared__ int s_i[GT_STAGE], s_j[GT_STAGE];
-    if (blockIdx.x >= *nheads) return;
-    const int64_t rs = heads[blockIdx.x];
-    const uint32_t key = keys[rs];
-    if (threadIdx.x == 0) s_run[1] = lower_bound_u32(keys, nvis, key + 1u);
-    __syncthreads();
-    const int64_t re_ = s_run[1];
-    if (rs + (int64_t)blockIdx.y * GT_SUBRUN >= re_) return;
+    if (blockIdx.x >= *nitems) return;
+    const uint2 item = items[blockIdx.x];
+    const uint32_t key = keys[item.x];
     const uint32_t chan = key / (tg * tg), tile = key % (tg * tg);
     const int tl = (int)(tile / tg), tm = (int)(tile % tg);
+    const int width = lo + hi + 1;
     const int side = 8 + lo + hi;
     const int c = threadIdx.x;
     const int l = tl * 8 - lo + c / side, m = tm * 8 - lo + c % side;
     const bool active = c < side * side && l >= 0 && m >= 0 && l < P.G && m < P.G;
-    const double uu_m = active ? P.uu[m] : 0.0, vv_l = active ? P.vv[l] : 0.0;
     double ar = 0.0, ai = 0.0, aw = 0.0;
-    for (int64_t sub = rs + (int64_t)blockIdx.y * GT_SUBRUN; sub < re_; sub += (int64_t)gridDim.y * GT_SUBRUN) {
-        const int64_t sub_end = sub + GT_SUBRUN < re_ ? sub + GT_SUBRUN : re_;
-        for (int64_t base = sub; base < sub_end; base += GT_STAGE) {
-            const int n_here = (int)(sub_end - base < GT_STAGE ? sub_end - base : GT_STAGE);
-            if (threadIdx.x < n_here) {
-                const int64_t idx = order[base + threadIdx.x];
-                const int64_t k = idx / P.nf;
-                const double f = P.freq[idx % P.nf];
-                s_us[threadIdx.x] = __dmul_rn(__dmul_rn(P.u[k], f), P.inv_freq);
-                s_vs[threadIdx.x] = __dmul_rn(__dmul_rn(P.v[k], f), P.inv_freq);
+    for (uint32_t base = item.x; base < item.y; base += GT_STAGE) {
+        const int n_here = (int)(item.y - base < GT_STAGE ? item.y - base : GT_STAGE);
+        // stage: per visibility the data and (mode 0) the one-dimensional kernel factors of its
+        // footprint columns / rows; two threads per visibility (u side, v side)
+        if (threadIdx.x < 2 * n_here) {
+            const int q = threadIdx.x >> 1, sidev = threadIdx.x & 1;
+            const int64_t idx = order[base + q];
+            const int64_t k = idx / P.nf;
+            const double f = P.freq[idx % P.nf];
+            const int home = sidev ? (int)P.gj[idx] : (int)P.gi[idx];
+            if (sidev == 0) {
                 const double w = P.w[idx];
-                s_w[threadIdx.x] = w;
-                s_re[threadIdx.x] = P.re[idx] * w;
-                s_im[threadIdx.x] = P.im[idx] * w;
-                s_i[threadIdx.x] = (int)P.gi[idx];
-                s_j[threadIdx.x] = (int)P.gj[idx];
+                s_w[q] = w;
+                s_re[q] = P.re[idx] * w;
+                s_im[q] = P.im[idx] * w;
+                s_i[q] = home;
+            } else {
+                s_j[q] = home;
             }
-            __syncthreads();
-            if (active) {
-                for (int q = 0; q < n_here; q++) {
-                    const int dj = l - s_j[q], di = m - s_i[q];
-                    if (dj < -lo || dj > hi || di < -lo || di > hi) continue;
-                    if (mode == 0) {
-                        const double du = (s_us[q] - uu_m) * P.inv_binsize, dv = (s_vs[q] - vv_l) * P.inv_binsize;
-                        const double cv = P.conv ? k_exp_sinc(du, dv) : k_ones(du, dv);
-                        ar += s_re[q] * cv;
-                        ai += s_im[q] * cv;
-                        aw += s_w[q] * cv;
-                    } else {
-                        aw += s_w[q];
+            if (mode == 0) {
+                const double pos = __dmul_rn(__dmul_rn(sidev ? P.v[k] : P.u[k], f), P.inv_freq);
+                const double *centres = sidev ? P.vv : P.uu;
+                double(*dst)[MAXW] = sidev ? s_fv : s_fu;
+                for (int o = 0; o < width; o++) {
+                    const int cell = home - lo + o;
+                    double g = 0.0;
+                    if (cell >= 0 && cell < P.G) {
+                        const double d = (pos - centres[cell]) * P.inv_binsize;
+                        // 1/norm goes with the u factor
+                        g = P.conv ? k_exp_sinc_1d(d) * (sidev ? 1.0 : (1. / 2.350016262343186))
+                                   : ((fabs(d) >= 0.5) ? 0.0 : 1.0);
                     }
+                    dst[q][o] = g;
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
+        if (active) {
+            for (int q = 0; q < n_here; q++) {
+                const int dj = l - s_j[q] + lo, di = m - s_i[q] + lo;
+                if (dj < 0 || dj >= width || di < 0 || di >= width) continue;
+                if (mode == 0) {
+                    const double cv = s_fu[q][di] * s_fv[q][dj];
+                    ar += s_re[q] * cv;
+                    ai += s_im[q] * cv;
+                    aw += s_w[q] * cv;
+                } else {
+                    aw += s_w[q];
+                }
+            }
+        }
+        __syncthreads();
     }
     if (active) {
         const int64_t cell = ((int64_t)l * P.G + m) * P.nch + chan;
@@ -850,19 +917,21 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
             tbits = ((tbits + 7) / 8) * 8 > 32 ? 32 : ((tbits + 7) / 8) * 8;
             PDSB_CHECK(radix_sort(sb, nvis, tbits, &ko, &vo));
             const int side = 8 + (int)lo + (int)hi;
-            if (side * side <= GT_THREADS && nkeys < (uint64_t)1 << 31) {
-                const uint64_t max_heads = std::min<uint64_t>(nkeys, (uint64_t)nvis);
-                PDSB_CHECK(c.stage_e.ensure((max_heads + 4) * sizeof(uint32_t)));
-                uint32_t *heads = c.stage_e.as<uint32_t>() + 4, *nheads = c.stage_e.as<uint32_t>();
-                PDSB_CUDA(cudaMemsetAsync(nheads, 0, sizeof(uint32_t), c.stream));
+            if (side * side <= GT_THREADS && (int)(lo + hi + 1) <= 8) {
+                const uint64_t max_items = std::min<uint64_t>(nkeys, (uint64_t)nvis) + (uint64_t)nvis / GT_SUBRUN + 2;
+                PDSB_REQUIRE(max_items < (uint64_t)1 << 31, "too many gridding work items");
+                PDSB_CHECK(c.stage_e.ensure((max_items + 2) * sizeof(uint2)));
+                uint32_t *nitems = c.stage_e.as<uint32_t>();
+                uint2 *items = c.stage_e.as<uint2>() + 2;
+                PDSB_CUDA(cudaMemsetAsync(nitems, 0, sizeof(uint32_t), c.stream));
                 {
-                    LaunchScope ls("grid_tile_heads");
-                    grid_tile_heads_kernel<<<ceil_div(nvis, 256), 256, 0, c.stream>>>(ko, nvis, heads, nheads);
+                    LaunchScope ls("grid_tile_items");
+                    grid_tile_items_kernel<<<ceil_div(nvis, 256), 256, 0, c.stream>>>(ko, nvis, items, nitems);
                     PDSB_CUDA(cudaGetLastError());
                 }
-                LaunchScope ls("grid_tile");
-                grid_tile_kernel<<<dim3((unsigned)max_heads, 8), GT_THREADS, 0, c.stream>>>(
-                    P, smode, (int)lo, (int)hi, tg, ko, vo, nvis, heads, nheads, t_re, t_im, t_w);
+                LaunchScope ls("grid_tile_accum");
+                grid_tile_kernel<<<(unsigned)max_items, GT_THREADS, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko, vo,
+                                                                                 items, nitems, t_re, t_im, t_w);
                 PDSB_CUDA(cudaGetLastError());
                 return PDSB_OK;
             }

@@ -32,7 +32,7 @@ for conv in ("pillbox", "expsinc"):
                 ms = ctypes.c_double(); _lib.check(L.pdsb_timer_stop(ctypes.byref(ms))); ts.append(ms.value)
             _lib.check(L.pdsb_profile_enable(0))
             parts = {}
-            for name in (b"grid_prep", b"grid_home_keys", b"grid_sort_hist", b"grid_sort_scan", b"grid_sort_scatter", b"grid_scatter_atomic", b"grid_tile_heads", b"grid_tile", b"grid_values", b"grid_ordered_sum",
+            for name in (b"grid_prep", b"grid_home_keys", b"grid_sort_hist", b"grid_sort_scan", b"grid_sort_scatter", b"grid_scatter_atomic", b"grid_tile_items", b"grid_tile_accum", b"grid_values", b"grid_ordered_sum",
                          b"grid_emit_keys", b"grid_normalise", b"grid_sum", b"grid_reweight", b"grid_fill"):
                 t, n = ctypes.c_double(), ctypes.c_int64()
                 L.pdsb_profile_get(name, ctypes.byref(t), ctypes.byref(n))
