@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(256) grid_values_kernel(GridParams P, int mode
 // memory (coalesced, independent of the running sum), then the owning lane adds them in order -
 // the serial chain per element is one dependent DADD per map and nothing else.
 constexpr int OS_LONG = 96;
+constexpr int OS_PER = 4;               // addends per lane per iteration
+constexpr int OS_CH = 32 * OS_PER;
 __global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t ncell,
                                                                const uint32_t *__restrict__ keys, int64_t ncontrib,
                                                                const double *__restrict__ v_re,
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t
                                                                const double *__restrict__ v_w, double *out_re,
                                                                double *out_im, double *out_w)
 {
-    __shared__ double sbuf[4][3][32];
+    __shared__ double sbuf[4][3][OS_CH];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t cell = (int64_t)blockIdx.x * 128 + threadIdx.x;      // (l*G+m)*nch + c
     int64_t p = 0, e = 0;
@@ -452,18 +454,33 @@ __global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t
         const int owner = __ffs(long_mask) - 1;
         long_mask &= long_mask - 1;
         const int64_t rp = __shfl_sync(0xffffffffu, p, owner), re_ = __shfl_sync(0xffffffffu, e, owner);
-        for (int64_t base = rp; base < re_; base += 32) {
-            const int64_t q = base + lane;
-            if (q < re_) {
-                if (mode == 0) {
-                    sbuf[wid][0][lane] = v_re[q];
-                    sbuf[wid][1][lane] = v_im[q];
-                }
-                sbuf[wid][2][lane] = v_w[q];
+        // OS_CH addends per iteration; the next iteration's loads are in flight (registers) while
+        // the owner adds the current ones out of shared memory
+        double nr[OS_PER], ni[OS_PER], nw[OS_PER];
+#pragma unroll
+        for (int t = 0; t < OS_PER; t++) {
+            const int64_t q = rp + t * 32 + lane;
+            nr[t] = (mode == 0 && q < re_) ? v_re[q] : 0.0;
+            ni[t] = (mode == 0 && q < re_) ? v_im[q] : 0.0;
+            nw[t] = q < re_ ? v_w[q] : 0.0;
+        }
+        for (int64_t base = rp; base < re_; base += OS_CH) {
+#pragma unroll
+            for (int t = 0; t < OS_PER; t++) {
+                sbuf[wid][0][t * 32 + lane] = nr[t];
+                sbuf[wid][1][t * 32 + lane] = ni[t];
+                sbuf[wid][2][t * 32 + lane] = nw[t];
+            }
+#pragma unroll
+            for (int t = 0; t < OS_PER; t++) {
+                const int64_t q = base + OS_CH + t * 32 + lane;
+                nr[t] = (mode == 0 && q < re_) ? v_re[q] : 0.0;
+                ni[t] = (mode == 0 && q < re_) ? v_im[q] : 0.0;
+                nw[t] = q < re_ ? v_w[q] : 0.0;
             }
             __syncwarp();
             if (lane == owner) {
-                const int n = (int)(re_ - base < 32 ? re_ - base : 32);
+                const int n = (int)(re_ - base < OS_CH ? re_ - base : OS_CH);
                 if (mode == 0) {
 #pragma unroll 8
                     for (int t = 0; t < n; t++) {
