@@ -382,7 +382,16 @@ __device__ __forceinline__ void unpack2(u64 a, float &lo, float &hi)
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
 }
 
-template <int UVP, int TCP, int MINB>
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// NCH: independent accumulator chains per (component, uv pair); column t feeds chain t % NCH, so
+// dependent FFMA2 on one accumulator are NCH times further apart (the chains are added per row).
+template <int UVP, int TCP, int MINB, int NCH>
 __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_qp_kernel(const DftParams P)
 {
     constexpr int UVT = 2 * UVP;
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_qp_kernel(const DftPara
 #pragma unroll 2
             for (int r = 0; r < DFT_RC; r++) {
                 const float4 *row = reinterpret_cast<const float4 *>(sm + r * (4 * TCP));
-                u64 a1[UVP], a2[UVP], b1[UVP], b2[UVP];
+                u64 a1[UVP][NCH], a2[UVP][NCH], b1[UVP][NCH], b2[UVP][NCH];
 #pragma unroll
                 for (int g = 0; g < TCP / 4; g++) {
                     const float4 ss = row[g], sd = row[TCP / 4 + g], ds = row[2 * (TCP / 4) + g],
@@ -506,31 +515,39 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_qp_kernel(const DftPara
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const int t = 4 * g + e;
+                        const int cn = t % NCH;
                         const u64 vss = pack2(xs[e], xs[e]), vsd = pack2(xsd[e], xsd[e]), vds = pack2(xds[e], xds[e]),
                                   vdd = pack2(xdd[e], xdd[e]);
 #pragma unroll
                         for (int qp = 0; qp < UVP; qp++) {
-                            if (t == 0) {
-                                a1[qp] = mul2(vss, tc2[qp][0]);
-                                a2[qp] = mul2(vsd, tc2[qp][0]);
-                                b1[qp] = mul2(vds, ts2[qp][0]);
-                                b2[qp] = mul2(vdd, ts2[qp][0]);
+                            if (t < NCH) {
+                                a1[qp][cn] = mul2(vss, tc2[qp][t]);
+                                a2[qp][cn] = mul2(vsd, tc2[qp][t]);
+                                b1[qp][cn] = mul2(vds, ts2[qp][t]);
+                                b2[qp][cn] = mul2(vdd, ts2[qp][t]);
                             } else {
-                                a1[qp] = fma2(vss, tc2[qp][t], a1[qp]);
-                                a2[qp] = fma2(vsd, tc2[qp][t], a2[qp]);
-                                b1[qp] = fma2(vds, ts2[qp][t], b1[qp]);
-                                b2[qp] = fma2(vdd, ts2[qp][t], b2[qp]);
+                                a1[qp][cn] = fma2(vss, tc2[qp][t], a1[qp][cn]);
+                                a2[qp][cn] = fma2(vsd, tc2[qp][t], a2[qp][cn]);
+                                b1[qp][cn] = fma2(vds, ts2[qp][t], b1[qp][cn]);
+                                b2[qp][cn] = fma2(vdd, ts2[qp][t], b2[qp][cn]);
                             }
                         }
                     }
                 }
 #pragma unroll
                 for (int qp = 0; qp < UVP; qp++) {
+#pragma unroll
+                    for (int cn = 1; cn < NCH; cn++) {
+                        a1[qp][0] = add2(a1[qp][0], a1[qp][cn]);
+                        a2[qp][0] = add2(a2[qp][0], a2[qp][cn]);
+                        b1[qp][0] = add2(b1[qp][0], b1[qp][cn]);
+                        b2[qp][0] = add2(b2[qp][0], b2[qp][cn]);
+                    }
                     const u64 nei = neg2(Ei2[qp]);
-                    vre[qp] = fma2(Er2[qp], a1[qp], vre[qp]);
-                    vre[qp] = fma2(nei, b2[qp], vre[qp]);
-                    vim[qp] = fma2(Er2[qp], b1[qp], vim[qp]);
-                    vim[qp] = fma2(Ei2[qp], a2[qp], vim[qp]);
+                    vre[qp] = fma2(Er2[qp], a1[qp][0], vre[qp]);
+                    vre[qp] = fma2(nei, b2[qp][0], vre[qp]);
+                    vim[qp] = fma2(Er2[qp], b1[qp][0], vim[qp]);
+                    vim[qp] = fma2(Ei2[qp], a2[qp][0], vim[qp]);
                     const u64 nr = fma2(nei, Di2[qp], mul2(Er2[qp], Dr2[qp]));
                     Ei2[qp] = fma2(Er2[qp], Di2[qp], mul2(Ei2[qp], Dr2[qp]));
                     Er2[qp] = nr;
@@ -591,6 +608,11 @@ static const VariantInfo kVariants[] = {
     {"dft_qp_uv4_tc24", 4, 24, 2, 2, 1},       // 15
     {"dft_qp_uv6_tc16", 6, 16, 2, 2, 1},       // 16
     {"dft_qp_uv2_tc16", 2, 16, 2, 4, 1},       // 17
+    {"dft_qp_uv4_tc16_c2", 4, 16, 2, 2, 1},    // 18  (cN: N accumulator chains per component)
+    {"dft_qp_uv2_tc32_c2", 2, 32, 2, 2, 1},    // 19
+    {"dft_qp_uv2_tc32_c4", 2, 32, 2, 2, 1},    // 20
+    {"dft_qp_uv4_tc16_c4", 4, 16, 2, 2, 1},    // 21
+    {"dft_qp_uv2_tc16_c4", 2, 16, 2, 4, 1},    // 22
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kDefaultVariant = 11;
@@ -638,7 +660,7 @@ static int launch_variant(const DftParams &p, const char *name)
     return PDSB_OK;
 }
 
-template <int UVP, int TCP, int MINB>
+template <int UVP, int TCP, int MINB, int NCH>
 static int launch_qp_variant(const DftParams &p, const char *name)
 {
     constexpr int UVT = 2 * UVP;
@@ -646,7 +668,7 @@ static int launch_qp_variant(const DftParams &p, const char *name)
                             (size_t)4 * UVT * DFT_THREADS * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        PDSB_CUDA(cudaFuncSetAttribute(dft_qp_kernel<UVP, TCP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PDSB_CUDA(cudaFuncSetAttribute(dft_qp_kernel<UVP, TCP, MINB, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         attr_set = true;
     }
@@ -655,7 +677,7 @@ static int launch_qp_variant(const DftParams &p, const char *name)
     PDSB_REQUIRE(p.nsplit <= 65535 && p.nf <= 65535, "grid y/z dimensions");
     dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)p.nf);
     LaunchScope ls(name);
-    dft_qp_kernel<UVP, TCP, MINB><<<grid, DFT_THREADS, smem, ctx().stream>>>(p);
+    dft_qp_kernel<UVP, TCP, MINB, NCH><<<grid, DFT_THREADS, smem, ctx().stream>>>(p);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
@@ -677,12 +699,17 @@ int launch_dft(const DftParams &p, int variant, int *tcp_of_variant)
         case 9: return launch_variant<2, 32, true, 2, true>(p, name);
         case 10: return launch_variant<2, 16, true, 4, true>(p, name);
         case 11: return launch_variant<3, 32, true, 2, true>(p, name);
-        case 12: return launch_qp_variant<2, 16, 2>(p, name);
-        case 13: return launch_qp_variant<1, 32, 2>(p, name);
-        case 14: return launch_qp_variant<2, 20, 2>(p, name);
-        case 15: return launch_qp_variant<2, 24, 2>(p, name);
-        case 16: return launch_qp_variant<3, 16, 2>(p, name);
-        case 17: return launch_qp_variant<1, 16, 4>(p, name);
+        case 12: return launch_qp_variant<2, 16, 2, 1>(p, name);
+        case 13: return launch_qp_variant<1, 32, 2, 1>(p, name);
+        case 14: return launch_qp_variant<2, 20, 2, 1>(p, name);
+        case 15: return launch_qp_variant<2, 24, 2, 1>(p, name);
+        case 16: return launch_qp_variant<3, 16, 2, 1>(p, name);
+        case 17: return launch_qp_variant<1, 16, 4, 1>(p, name);
+        case 18: return launch_qp_variant<2, 16, 2, 2>(p, name);
+        case 19: return launch_qp_variant<1, 32, 2, 2>(p, name);
+        case 20: return launch_qp_variant<1, 32, 2, 4>(p, name);
+        case 21: return launch_qp_variant<2, 16, 2, 4>(p, name);
+        case 22: return launch_qp_variant<1, 16, 4, 4>(p, name);
     }
     return PDSB_ERR_ARG;
 }
