@@ -215,6 +215,53 @@ __global__ void __launch_bounds__(128) fma_pattern_kernel(float *out, int iters,
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Same inner product with the image operand read from CONSTANT memory through a warp-uniform
+// index (uniform datapath: no per-lane register write, no shared-memory wavefront).  Feasibility
+// probe for a constant-bank-staged DFT kernel.
+__constant__ float c_probe[16384];
+
+template <int UVT, int TP>
+__global__ void __launch_bounds__(128) fma_const_kernel(float *out, const float *seedv, int iters)
+{
+    unsigned long long trig[UVT][TP], acc[UVT][4];
+#pragma unroll
+    for (int q = 0; q < UVT; q++) {
+#pragma unroll
+        for (int t = 0; t < TP; t++) {
+            float2 a = make_float2(seedv[(threadIdx.x + 7 * t + 3 * q) & 1023], seedv[(threadIdx.x * 3 + t + q) & 1023]);
+            trig[q][t] = *reinterpret_cast<unsigned long long *>(&a);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[q][c] = 0ull;
+    }
+    const unsigned long long *cimg = reinterpret_cast<const unsigned long long *>(c_probe);
+    const int rows = 16384 / (4 * TP * 2);          // rows of [4 comps][TP pairs]
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll 2
+        for (int r = 0; r < rows; r++) {
+            const unsigned long long *row = cimg + (size_t)r * (4 * TP);
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int t = 0; t < TP; t++) {
+                    const unsigned long long x = row[c * TP + t];
+#pragma unroll
+                    for (int q = 0; q < UVT; q++) acc[q][c] = fma2_(x, trig[q][t], acc[q][c]);
+                }
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int q = 0; q < UVT; q++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float2 a = *reinterpret_cast<float2 *>(&acc[q][c]);
+            s += a.x + a.y;
+        }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace pdsb
 
 using namespace pdsb;
@@ -493,7 +540,17 @@ int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms_out)
     PDSB_REQUIRE(tflops && iters > 0, "tflops/iters");
     Context &c = ctx();
     int blocks = c.sm_count * 8, threads = variant < 2 ? 256 : 128;
-    PDSB_CHECK(c.red.ensure((size_t)blocks * 256 * sizeof(float)));
+    PDSB_CHECK(c.red.ensure((size_t)(blocks * 256 + 1024) * sizeof(float)));
+    PDSB_CUDA(cudaMemsetAsync(c.red.as<float>() + (size_t)blocks * 256, 0x3c, 1024 * sizeof(float), c.stream));
+    if (variant >= 8) {
+        static bool filled = false;
+        if (!filled) {
+            std::vector<float> h(16384);
+            for (int i = 0; i < 16384; i++) h[i] = 1.0f + 1e-3f * (i % 97);
+            PDSB_CUDA(cudaMemcpyToSymbol(c_probe, h.data(), sizeof(float) * 16384));
+            filled = true;
+        }
+    }
     double fmas_per_thread_iter = 8.0 * 16.0;
     for (int rep = 0; rep < 2; rep++) {
         if (rep == 1) PDSB_CUDA(cudaEventRecord(c.t0, c.stream));
@@ -510,6 +567,18 @@ int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms_out)
                 case 5: fma_pattern_kernel<1, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 1 * 4 * 8 * 2; break;
                 case 6: fma_pattern_kernel<4, 8, 0><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 4 * 4 * 8 * 2; break;
                 case 7: fma_pattern_kernel<3, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 3 * 4 * 8 * 2; break;
+                case 8:
+                case 9:
+                case 10: {
+                    // iters here = passes over the 64 KB constant block
+                    const int passes = iters / 256 > 0 ? iters / 256 : 1;
+                    float *seedv = o + (size_t)blocks * 256;
+                    if (variant == 8) { fma_const_kernel<2, 8><<<blocks, 128, 0, c.stream>>>(o, seedv, passes); fmas_per_thread_iter = 2.0 * 4 * 8 * 2 * (16384 / 64); }
+                    if (variant == 9) { fma_const_kernel<4, 8><<<blocks, 128, 0, c.stream>>>(o, seedv, passes); fmas_per_thread_iter = 4.0 * 4 * 8 * 2 * (16384 / 64); }
+                    if (variant == 10) { fma_const_kernel<2, 16><<<blocks, 128, 0, c.stream>>>(o, seedv, passes); fmas_per_thread_iter = 2.0 * 4 * 16 * 2 * (16384 / 128); }
+                    iters = passes;
+                    break;
+                }
                 default: set_error("unknown fma bench variant %d", variant); return PDSB_ERR_ARG;
             }
         }
