@@ -138,7 +138,7 @@ def run_reference(args, cfg, rank, world):
     from concurrent.futures import ThreadPoolExecutor
     from oracle import dft as od, likelihood as ol
     cores = os.cpu_count() or 1
-    nch = min(cfg["nf"], 8)
+    nch = min(cfg["nf"], max(8, cores))        # one channel per host thread
     u, v = synth.synth_uv(cfg["nuv"], cfg["pixelsize"] * A)
     img = synth.synth_image(cfg["npix"], cfg["nf"], cfg["pixelsize"])[:, :, :nch, :]
     re, im, w = synth.synth_data(cfg["nuv"], nch)
@@ -224,6 +224,9 @@ def main():
         run_reference(args, cfg, rank, world)
         return
 
+    # keep stdout to the one JSON line: NCCL_DEBUG=VERSION/INFO prints its banner on stdout
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     os.environ["PDSB_DEVICE"] = str(local_rank)

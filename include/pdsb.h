@@ -172,6 +172,24 @@ int pdsb_grid(const double *u, const double *v, const double *freq,
 int pdsb_freqcorrect(const double *u, const double *v, const double *freq, int64_t nuv, int nf,
                      double new_freq, int kind, double *out_u, double *out_v);
 
+/* ---- callers either side of the path --------------------------------------- */
+/* average(): the accumulation loop of libinterferometry.pyx:262-277.  The caller does the numpy
+ * preamble exactly as the reference (weight clamp :179-181, uvdist/good filters :183-189,:254-260, bin
+ * indices bin_i/bin_j [nuv] uint32 :221-248 - numpy.round / log10 rounding is part of the reference
+ * result) and the normalisation/compaction afterwards (:279-311).  Outputs are the raw ordered sums
+ * [gj, gi, nch] (gj = 1 for radial): sum u*w, sum v*w (NULL when radial), sum real*w, sum imag*w,
+ * sum w, accumulated in the reference's (k, n) order: bit-exact. */
+int pdsb_bin_average(const uint32_t *bin_i, const uint32_t *bin_j, const double *u, const double *v,
+                     const double *real, const double *imag, const double *weights, int64_t nuv, int nf,
+                     int gi, int gj, int spectral, int radial, int in_kind,
+                     double *out_u, double *out_v, double *out_real, double *out_imag, double *out_weights,
+                     int out_kind);
+/* center(): data * conj(point model at (x0, y0)), pdspy/interferometry/center.py:5-25 with
+ * point_model of model.py:102-104 (incl. its literal 3.14159).  x0, y0 in radians. */
+int pdsb_center(const double *u, const double *v, const double *freq, const double *real, const double *imag,
+                int64_t nuv, int nf, double mean_freq, double x0_rad, double y0_rad, int kind,
+                double *out_real, double *out_imag);
+
 /* ---- tuning / measurement ----------------------------------------------------------- */
 /* DFT kernel variant: 0 = auto, otherwise an index into the built variants. */
 int pdsb_set_dft_variant(int variant);

@@ -752,6 +752,65 @@ __global__ void __launch_bounds__(256) grid_home_keys_kernel(GridParams P, uint3
     ids[idx] = (uint32_t)idx;
 }
 
+// ---- average(): nearest-cell binning with weighted mean positions (libinterferometry.pyx:262-277) ----
+__global__ void __launch_bounds__(256) avg_emit_keys_kernel(const uint32_t *__restrict__ bi,
+                                                            const uint32_t *__restrict__ bj, int64_t first,
+                                                            int64_t count, int nf, int gi, int nch, int spectral,
+                                                            uint32_t *keys, uint32_t *ids)
+{
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= count) return;
+    const int64_t idx = first + t;
+    const int64_t k = idx / nf;
+    keys[t] = (bj[k] * (uint32_t)gi + bi[k]) * (uint32_t)nch + (spectral ? (uint32_t)(idx % nf) : 0u);
+    ids[t] = (uint32_t)t;
+}
+
+// addends in sorted order: which = 0: (real*w, imag*w, w) ; which = 1: (u*w, v*w, w)
+__global__ void __launch_bounds__(256) avg_values_kernel(const double *__restrict__ u, const double *__restrict__ v,
+                                                         const double *__restrict__ re, const double *__restrict__ im,
+                                                         const double *__restrict__ w, int nf, int which, int64_t first,
+                                                         const uint32_t *__restrict__ ids, int64_t ncontrib,
+                                                         double *__restrict__ va, double *__restrict__ vb,
+                                                         double *__restrict__ vw)
+{
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= ncontrib) return;
+    const int64_t idx = first + ids[p];
+    const double ww = w[idx];
+    if (which == 0) {
+        va[p] = __dmul_rn(re[idx], ww);
+        vb[p] = __dmul_rn(im[idx], ww);
+    } else {
+        va[p] = __dmul_rn(u[idx / nf], ww);
+        vb[p] = __dmul_rn(v[idx / nf], ww);
+    }
+    vw[p] = ww;
+}
+
+// ---- center(): data * conj(point model)  (center.py:5-25, model.py:102-104) -------------------------
+__global__ void __launch_bounds__(256) center_kernel(const double *__restrict__ u, const double *__restrict__ v,
+                                                     const double *__restrict__ freq, const double *__restrict__ re,
+                                                     const double *__restrict__ im, int64_t nuv, int nf,
+                                                     double mean_freq, double x0, double y0, double *__restrict__ ore,
+                                                     double *__restrict__ oim)
+{
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= nuv * nf) return;
+    const int64_t k = idx / nf;
+    const double f = freq[idx % nf];
+    // model(data.u*data.freq[i]/data.freq.mean(), ...) -> point_model: flux*exp(-2*3.14159*(0+1j*(u*x0+v*y0)))
+    const double us = __ddiv_rn(__dmul_rn(u[k], f), mean_freq), vs = __ddiv_rn(__dmul_rn(v[k], f), mean_freq);
+    const double a = __dadd_rn(__dmul_rn(us, x0), __dmul_rn(vs, y0));
+    const double b = __dmul_rn(-2 * 3.14159, a);
+    double s, c;
+    sincos(b, &s, &c);
+    // centered = (re + i im) * conj(c + i s) = (re + i im) * (c - i s)
+    const double dr = re[idx], di = im[idx], ms = -s;
+    ore[idx] = __dsub_rn(__dmul_rn(dr, c), __dmul_rn(di, ms));
+    oim[idx] = __dadd_rn(__dmul_rn(dr, ms), __dmul_rn(di, c));
+}
+
 static int bits_for(uint64_t maxval)
 {
     int b = 1;
@@ -1091,6 +1150,134 @@ int pdsb_freqcorrect(const double *u, const double *v, const double *freq, int64
     if (kind == PDSB_HOST) {
         PDSB_CUDA(cudaMemcpyAsync(out_u, ou, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         PDSB_CUDA(cudaMemcpyAsync(out_v, ov, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return PDSB_OK;
+}
+
+int pdsb_bin_average(const uint32_t *bin_i, const uint32_t *bin_j, const double *u, const double *v,
+                     const double *real, const double *imag, const double *weights, int64_t nuv, int nf, int gi,
+                     int gj, int spectral, int radial, int in_kind, double *out_u, double *out_v, double *out_real,
+                     double *out_imag, double *out_weights, int out_kind)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    PDSB_REQUIRE(nuv >= 0 && nf > 0 && gi > 0 && gj > 0, "sizes");
+    PDSB_REQUIRE(out_real && out_imag && out_weights, "outputs");
+    PDSB_REQUIRE(radial || (out_u && out_v), "out_u/out_v");
+    const int nch = spectral ? nf : 1;
+    const int64_t ncell = (int64_t)gi * gj * nch;
+    PDSB_REQUIRE(ncell < (int64_t)KEY_DEAD, "grid too large");
+    const int64_t nvis = nuv * nf;
+    PDSB_REQUIRE(nvis < (int64_t)1 << 32, "nuv*nf must fit 32 bits");
+    // maps: re, im, w, u, v, scratch-w
+    PDSB_CHECK(c.stage_c.ensure((size_t)ncell * 6 * sizeof(double) + 256));
+    double *m_re = c.stage_c.as<double>(), *m_im = m_re + ncell, *m_w = m_im + ncell, *m_u = m_w + ncell,
+           *m_v = m_u + ncell, *m_w2 = m_v + ncell;
+    PDSB_CUDA(cudaMemsetAsync(m_re, 0, (size_t)ncell * 6 * sizeof(double), c.stream));
+    if (nvis > 0) {
+        PDSB_REQUIRE(bin_i && bin_j && u && v && real && imag && weights, "inputs");
+        const uint32_t *di = bin_i, *dj = bin_j;
+        const double *du = u, *dv = v, *dre = real, *dim = imag, *dw = weights;
+        if (in_kind == PDSB_HOST) {
+            const size_t bytes = (size_t)nuv * (2 * sizeof(uint32_t) + 2 * sizeof(double)) + (size_t)nvis * 3 * sizeof(double);
+            PDSB_CHECK(c.stage_a.ensure(bytes + 64));
+            double *p = c.stage_a.as<double>();
+            auto put = [&](const void *src, size_t nbytes, const void **dst) -> int {
+                PDSB_CUDA(cudaMemcpyAsync(p, src, nbytes, cudaMemcpyHostToDevice, c.stream));
+                *dst = p;
+                p += (nbytes + 7) / 8;
+                return PDSB_OK;
+            };
+            PDSB_CHECK(put(u, nuv * sizeof(double), (const void **)&du));
+            PDSB_CHECK(put(v, nuv * sizeof(double), (const void **)&dv));
+            PDSB_CHECK(put(real, nvis * sizeof(double), (const void **)&dre));
+            PDSB_CHECK(put(imag, nvis * sizeof(double), (const void **)&dim));
+            PDSB_CHECK(put(weights, nvis * sizeof(double), (const void **)&dw));
+            PDSB_CHECK(put(bin_i, nuv * sizeof(uint32_t), (const void **)&di));
+            PDSB_CHECK(put(bin_j, nuv * sizeof(uint32_t), (const void **)&dj));
+        }
+        const int nbits = bits_for((uint64_t)ncell);
+        const int sort_bits = ((nbits + 7) / 8) * 8 > 32 ? 32 : ((nbits + 7) / 8) * 8;
+        const int64_t per_batch = (int64_t)1 << 27;
+        for (int64_t first = 0; first < nvis; first += per_batch) {
+            const int64_t n = std::min(per_batch, nvis - first);
+            const size_t nh = (size_t)256 * ceil_div(n, RS_TILE);
+            PDSB_CHECK(c.stage_d.ensure((size_t)n * 4 * sizeof(uint32_t) + (nh + nh / SCAN_SEG + 16) * sizeof(uint32_t) + 1024));
+            PDSB_CHECK(c.stage_e.ensure((size_t)n * 3 * sizeof(double)));
+            uint32_t *k0 = c.stage_d.as<uint32_t>(), *v0 = k0 + n, *k1 = v0 + n, *v1 = k1 + n, *hist = v1 + n;
+            double *va = c.stage_e.as<double>(), *vb = va + n, *vw = vb + n;
+            {
+                LaunchScope ls("avg_emit_keys");
+                avg_emit_keys_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(di, dj, first, n, nf, gi, nch, spectral, k0, v0);
+                PDSB_CUDA(cudaGetLastError());
+            }
+            uint32_t *ko, *vo;
+            SortBufs sb{k0, v0, k1, v1, hist};
+            PDSB_CHECK(radix_sort(sb, n, sort_bits, &ko, &vo));
+            for (int which = 0; which < (radial ? 1 : 2); which++) {
+                {
+                    LaunchScope ls("avg_values");
+                    avg_values_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(du, dv, dre, dim, dw, nf, which, first, vo, n,
+                                                                              va, vb, vw);
+                    PDSB_CUDA(cudaGetLastError());
+                }
+                LaunchScope ls("grid_ordered_sum");
+                grid_ordered_sum_kernel<<<ceil_div(ncell, 128), 128, 0, c.stream>>>(
+                    0, ncell, ko, n, va, vb, vw, which ? m_u : m_re, which ? m_v : m_im, which ? m_w2 : m_w);
+                PDSB_CUDA(cudaGetLastError());
+            }
+        }
+    }
+    cudaMemcpyKind ok = out_kind == PDSB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const size_t mb = (size_t)ncell * sizeof(double);
+    PDSB_CUDA(cudaMemcpyAsync(out_real, m_re, mb, ok, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(out_imag, m_im, mb, ok, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(out_weights, m_w, mb, ok, c.stream));
+    if (out_u) PDSB_CUDA(cudaMemcpyAsync(out_u, m_u, mb, ok, c.stream));
+    if (out_v) PDSB_CUDA(cudaMemcpyAsync(out_v, m_v, mb, ok, c.stream));
+    if (out_kind == PDSB_HOST) PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    return PDSB_OK;
+}
+
+int pdsb_center(const double *u, const double *v, const double *freq, const double *real, const double *imag,
+                int64_t nuv, int nf, double mean_freq, double x0_rad, double y0_rad, int kind, double *out_real,
+                double *out_imag)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    PDSB_REQUIRE(nuv >= 0 && nf > 0 && mean_freq > 0, "sizes/mean_freq");
+    if (nuv == 0) return PDSB_OK;
+    PDSB_REQUIRE(u && v && freq && real && imag && out_real && out_imag, "arrays");
+    const int64_t n = nuv * nf;
+    const double *du = u, *dv = v, *df = freq, *dre = real, *dim = imag;
+    double *ore = out_real, *oim = out_imag;
+    if (kind == PDSB_HOST) {
+        PDSB_CHECK(c.stage_a.ensure((size_t)(2 * nuv + nf + 2 * n) * sizeof(double) + 64));
+        double *p = c.stage_a.as<double>();
+        auto put = [&](const double *src, size_t cnt, const double **dst) -> int {
+            PDSB_CUDA(cudaMemcpyAsync(p, src, cnt * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+            *dst = p;
+            p += cnt;
+            return PDSB_OK;
+        };
+        PDSB_CHECK(put(u, nuv, &du));
+        PDSB_CHECK(put(v, nuv, &dv));
+        PDSB_CHECK(put(freq, nf, &df));
+        PDSB_CHECK(put(real, n, &dre));
+        PDSB_CHECK(put(imag, n, &dim));
+        PDSB_CHECK(c.stage_b.ensure((size_t)2 * n * sizeof(double)));
+        ore = c.stage_b.as<double>();
+        oim = ore + n;
+    }
+    {
+        LaunchScope ls("center");
+        center_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(du, dv, df, dre, dim, nuv, nf, mean_freq, x0_rad, y0_rad, ore, oim);
+        PDSB_CUDA(cudaGetLastError());
+    }
+    if (kind == PDSB_HOST) {
+        PDSB_CUDA(cudaMemcpyAsync(out_real, ore, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
     return PDSB_OK;

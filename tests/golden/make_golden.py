@@ -76,6 +76,32 @@ def multi_channel_set():
 SAMPLE_ABOVE = 4000      # cases with more non-zero cells than this store every 8th one
 
 
+AVERAGE_CASES = {
+    "av_cont": dict(gridsize=64, binsize=8000.0),
+    "av_line_odd": dict(gridsize=65, binsize=8000.0, mode="spectralline"),
+    "av_radial": dict(gridsize=20, binsize=40000.0, radial=True),
+    "av_radial_log_line": dict(gridsize=20, radial=True, log=True, logmin=2400.0, logmax=1.2e6, mode="spectralline"),
+    "av_mfs": dict(gridsize=64, binsize=8000.0, mfs=True),
+}
+
+
+def load_reference_python_module(ref, name):
+    """Import one pure-Python module of the reference package (e.g. interferometry.center) without
+    running pdspy/__init__.py (which pulls in galario, h5py, ...): fake parent packages whose
+    __path__ points into /root/reference, with the compiled libinterferometry pre-seeded."""
+    import importlib
+    import types
+    root = "/root/reference/pdspy"
+    for pkg, path in (("pdspy", root), ("pdspy.interferometry", root + "/interferometry"),
+                      ("pdspy.constants", root + "/constants")):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = [path]
+            sys.modules[pkg] = m
+    sys.modules["pdspy.interferometry.libinterferometry"] = ref
+    return importlib.import_module("pdspy." + name)
+
+
 def sparse(a):
     """(indices, values) of the non-zero cells; sub-sampled for the dense expsinc maps so the
     committed file stays small.  The count and the plain sum of all non-zero cells are stored
@@ -120,6 +146,23 @@ def main():
     for name, kw in GRID_CASES_MULTI.items():
         run(name, data, kw)
     np.savez_compressed(os.path.join(HERE, "grid_golden.npz"), **out)
+
+    # average() of the live reference on the multi-channel set (one exact-zero baseline added)
+    av = {}
+    u, v, freq, re, im, w = multi_channel_set()
+    u[5] = 0.0
+    v[5] = 0.0
+    data = ref.Visibilities(u, v, freq, re, im, w)
+    for name, kw in AVERAGE_CASES.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            a = ref.average(data, **kw)
+        for nm in ("u", "v", "freq", "real", "imag", "weights"):
+            av["%s/%s" % (name, nm)] = getattr(a, nm)
+    # center() of the reference's own Python (center.py + model.py)
+    cen = load_reference_python_module(ref, "interferometry.center")
+    c = cen.center(data, [0.31, -0.17, 1.0])
+    av["center/real"], av["center/imag"] = c.real, c.imag
+    np.savez_compressed(os.path.join(HERE, "average_golden.npz"), **av)
 
     # chisq of the live reference (channel 0, float return)
     rng = np.random.default_rng(99)

@@ -114,3 +114,36 @@ def test_lnlike_c_vs_verbatim_numpy():
     a = ol.lnlike_vis_numpy(d_re, d_im, w, m_re, m_im)
     b = ol.lnlike_vis_c(d_re, d_im, w, m_re, m_im)
     assert abs(a - b) <= 1e-12 * abs(a)
+
+
+# ---- average() / center() ------------------------------------------
+from make_golden import AVERAGE_CASES                                                # noqa: E402
+from oracle import average as oa                                                     # noqa: E402
+
+
+def _avg_inputs():
+    u, v, freq, re, im, w = multi_channel_set()
+    u[5] = 0.0
+    v[5] = 0.0
+    return u, v, freq, re, im, w
+
+
+@pytest.fixture(scope="module")
+def average_golden():
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "average_golden.npz"))
+    return {k: d[k] for k in d.files}
+
+
+@pytest.mark.parametrize("name", sorted(AVERAGE_CASES))
+def test_average_oracle_vs_live_reference_golden(name, average_golden):
+    u, v, freq, re, im, w = _avg_inputs()
+    o = _quiet(oa.average, u, v, freq, re, im, w, **AVERAGE_CASES[name])
+    for a, nm in zip(o, ("u", "v", "freq", "real", "imag", "weights")):
+        np.testing.assert_array_equal(a, average_golden["%s/%s" % (name, nm)], err_msg=nm)
+
+
+def test_center_oracle_vs_reference_python_golden(average_golden):
+    u, v, freq, re, im, w = _avg_inputs()
+    cr, ci = oa.center(u, v, freq, re, im, 0.31, -0.17)
+    np.testing.assert_array_equal(cr, average_golden["center/real"])
+    np.testing.assert_array_equal(ci, average_golden["center/imag"])
