@@ -190,6 +190,14 @@ int pdsb_center(const double *u, const double *v, const double *freq, const doub
                 int64_t nuv, int nf, double mean_freq, double x0_rad, double y0_rad, int kind,
                 double *out_real, double *out_imag);
 
+/* invert(): the per-channel image synthesis of pdspy/interferometry/invert.py:63-84 from gridded
+ * visibilities (grid(..., imaging=True)): g_real, g_imag [imsize*imsize, nch]; conv [imsize, imsize] =
+ * conv_func(u, v, binsize, binsize) of :94-121 evaluated by the caller on the grid; image_out
+ * [imsize, imsize, nch] = (fftshift(ifft2(ifftshift(real+i imag))).real*imsize^2 /
+ * fftshift(ifft2(ifftshift(conv))).real)[:, ::-1].  imsize must be a power of two (<= 4096). */
+int pdsb_invert_image(const double *g_real, const double *g_imag, const double *conv, int imsize, int nch,
+                      int kind, double *image_out);
+
 /* ---- tuning / measurement ----------------------------------------------------------- */
 /* DFT kernel variant: 0 = auto, otherwise an index into the built variants. */
 int pdsb_set_dft_variant(int variant);

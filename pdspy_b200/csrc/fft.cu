@@ -1,0 +1,128 @@
+// Dirty-image synthesis for invert() (pdspy/interferometry/invert.py:63-84): per channel
+//   im       = fftshift(ifft2(ifftshift(real + i imag))).real * imsize^2
+//   convolve = fftshift(ifft2(ifftshift(conv_func(u, v)))).real
+//   image[:, :, i] = (im / convolve)[:, ::-1]
+// Hand-written fp64 radix-2 FFT: one CTA per row held in shared memory (n <= 4096), two passes with
+// the (i)fftshift index rotations and the transpose fused into the loads/stores.
+#include "common.cuh"
+
+namespace pdsb {
+
+__device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return __brev(x) >> (32 - bits); }
+
+// One row of length n (power of two) per block: out[...] = sum_c in[...] exp(+2 pi i b c / n).
+//   pass 0: row r' of the shifted input: element c comes from x[(r'+h)%n][(c+h)%n] (real/imag planes with
+//           element stride `estride`), result b goes to T[b][r']           (transpose)
+//   pass 1: row b of T, result a goes to Y[(a+h)%n][(b+h)%n]              (fftshift on output)
+__global__ void __launch_bounds__(512) ifft_rows_kernel(const double *__restrict__ in_re,
+                                                        const double *__restrict__ in_im, int64_t estride,
+                                                        const double2 *__restrict__ tin, double2 *__restrict__ tout,
+                                                        int n, int logn, int pass)
+{
+    extern __shared__ double2 srow[];
+    const int row = blockIdx.x, h = n / 2;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        double2 val;
+        if (pass == 0) {
+            const int64_t src = ((int64_t)((row + h) % n) * n + (c + h) % n) * estride;
+            val = make_double2(in_re[src], in_im ? in_im[src] : 0.0);
+        } else {
+            val = tin[(int64_t)row * n + c];
+        }
+        srow[bitrev((unsigned)c, logn)] = val;
+    }
+    __syncthreads();
+    for (int s = 1; s <= logn; s++) {
+        const int m = 1 << s, half = m >> 1;
+        for (int idx = threadIdx.x; idx < n / 2; idx += blockDim.x) {
+            const int k = idx & (half - 1);
+            const int j = ((idx >> (s - 1)) << s) + k;
+            double ws, wc;
+            sincospi(2.0 * (double)k / (double)m, &ws, &wc);        // inverse transform: +i
+            const double2 a = srow[j], b = srow[j + half];
+            const double tr = wc * b.x - ws * b.y, ti = wc * b.y + ws * b.x;
+            srow[j] = make_double2(a.x + tr, a.y + ti);
+            srow[j + half] = make_double2(a.x - tr, a.y - ti);
+        }
+        __syncthreads();
+    }
+    for (int b = threadIdx.x; b < n; b += blockDim.x) {
+        if (pass == 0) tout[(int64_t)b * n + row] = srow[b];
+        else tout[(int64_t)((b + h) % n) * n + (row + h) % n] = srow[b];
+    }
+}
+
+// image[A, n-1-B, ch] = Re(Y_im[A,B]) / (Re(Y_conv[A,B]) / n^2)        (invert.py:74-79)
+__global__ void __launch_bounds__(256) invert_combine_kernel(const double2 *__restrict__ yim,
+                                                             const double2 *__restrict__ yconv, int n, int nch, int ch,
+                                                             double *__restrict__ image)
+{
+    const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (q >= (int64_t)n * n) return;
+    const int A = (int)(q / n), B = (int)(q % n);
+    const double im = yim[q].x;                                   // ifft2 * imsize^2: the 1/n^2 cancels
+    const double cv = yconv[q].x / ((double)n * (double)n);
+    image[((int64_t)A * n + (n - 1 - B)) * nch + ch] = im / cv;
+}
+
+}  // namespace pdsb
+
+using namespace pdsb;
+
+extern "C" int pdsb_invert_image(const double *g_real, const double *g_imag, const double *conv, int imsize, int nch,
+                                 int kind, double *image_out)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    PDSB_REQUIRE(g_real && g_imag && conv && image_out, "arrays");
+    PDSB_REQUIRE(imsize >= 2 && imsize <= 4096 && (imsize & (imsize - 1)) == 0, "imsize must be a power of two <= 4096");
+    PDSB_REQUIRE(nch >= 1, "nch");
+    const int n = imsize;
+    int logn = 0;
+    while ((1 << logn) < n) logn++;
+    const int64_t nn = (int64_t)n * n;
+    const double *dre = g_real, *dim = g_imag, *dconv = conv;
+    double *dout = image_out;
+    if (kind == PDSB_HOST) {
+        PDSB_CHECK(c.stage_a.ensure((size_t)(2 * nn * nch + nn) * sizeof(double)));
+        double *p = c.stage_a.as<double>();
+        PDSB_CUDA(cudaMemcpyAsync(p, g_real, (size_t)nn * nch * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        dre = p;
+        p += nn * nch;
+        PDSB_CUDA(cudaMemcpyAsync(p, g_imag, (size_t)nn * nch * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        dim = p;
+        p += nn * nch;
+        PDSB_CUDA(cudaMemcpyAsync(p, conv, (size_t)nn * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        dconv = p;
+        PDSB_CHECK(c.stage_b.ensure((size_t)nn * nch * sizeof(double)));
+        dout = c.stage_b.as<double>();
+    }
+    PDSB_CHECK(c.stage_c.ensure((size_t)3 * nn * sizeof(double2)));
+    double2 *T = c.stage_c.as<double2>(), *Yc = T + nn, *Yi = Yc + nn;
+    const int threads = n / 2 < 512 ? (n / 2 < 32 ? 32 : n / 2) : 512;
+    const size_t smem = (size_t)n * sizeof(double2);
+    static bool attr = false;
+    if (!attr) {
+        PDSB_CUDA(cudaFuncSetAttribute(ifft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+        attr = true;
+    }
+    auto ifft2 = [&](const double *re, const double *im, int64_t estride, double2 *Y) -> int {
+        LaunchScope ls("invert_ifft2");
+        ifft_rows_kernel<<<n, threads, smem, c.stream>>>(re, im, estride, nullptr, T, n, logn, 0);
+        ifft_rows_kernel<<<n, threads, smem, c.stream>>>(nullptr, nullptr, 0, T, Y, n, logn, 1);
+        PDSB_CUDA(cudaGetLastError());
+        return PDSB_OK;
+    };
+    PDSB_CHECK(ifft2(dconv, nullptr, 1, Yc));
+    for (int ch = 0; ch < nch; ch++) {
+        PDSB_CHECK(ifft2(dre + ch, dim + ch, nch, Yi));          // gridded maps are [G*G, nch]
+        LaunchScope ls("invert_combine");
+        invert_combine_kernel<<<ceil_div(nn, 256), 256, 0, c.stream>>>(Yi, Yc, n, nch, ch, dout);
+        PDSB_CUDA(cudaGetLastError());
+    }
+    if (kind == PDSB_HOST) {
+        PDSB_CUDA(cudaMemcpyAsync(image_out, dout, (size_t)nn * nch * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return PDSB_OK;
+}

@@ -4,3 +4,4 @@ from .visibilities import Visibilities, VisibilitiesObject
 from .interpolate_model import interpolate_model, loglike_image, loglike_images
 from .grid import grid, freqcorrect, chisq
 from .average import average, center
+from .invert import invert

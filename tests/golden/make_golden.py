@@ -102,6 +102,34 @@ def load_reference_python_module(ref, name):
     return importlib.import_module("pdspy." + name)
 
 
+INVERT_CASES = {
+    # tests/test.py:9 of the reference
+    "test_py": dict(imsize=512, pixel_size=0.5, convolution="expsinc"),
+    "pillbox_256": dict(imsize=256, pixel_size=0.5, convolution="pillbox"),
+    "robust_centered_128": dict(imsize=128, pixel_size=1.0, convolution="expsinc", weighting="robust", robust=0.5,
+                                centering=[0.3, -0.2, 1.0]),
+    "beam_128": dict(imsize=128, pixel_size=1.0, convolution="expsinc", beam=True, uvtaper=30.0),
+}
+
+
+def load_reference_invert(ref):
+    """The reference's own invert.py (scipy.fftpack) with the compiled grid(); pdspy.imaging is replaced
+    by a minimal Image stub (the real one needs h5py/astropy)."""
+    import importlib
+    import types
+    cen = load_reference_python_module(ref, "interferometry.center")
+    sys.modules["pdspy.interferometry"].center = cen.center          # what `from . import center` resolves to
+    if "pdspy.imaging" not in sys.modules:
+        img = types.ModuleType("pdspy.imaging")
+
+        class Image:
+            def __init__(self, image, x=None, y=None, freq=None, **kw):
+                self.image, self.x, self.y, self.freq = image, x, y, freq
+        img.Image = Image
+        sys.modules["pdspy.imaging"] = img
+    return importlib.import_module("pdspy.interferometry.invert")
+
+
 def sparse(a):
     """(indices, values) of the non-zero cells; sub-sampled for the dense expsinc maps so the
     committed file stays small.  The count and the plain sum of all non-zero cells are stored
@@ -163,6 +191,19 @@ def main():
     c = cen.center(data, [0.31, -0.17, 1.0])
     av["center/real"], av["center/imag"] = c.real, c.imag
     np.savez_compressed(os.path.join(HERE, "average_golden.npz"), **av)
+
+    # invert() of the reference (invert.py + compiled grid + scipy.fftpack) on the fixture
+    inv = load_reference_invert(ref)
+    fxdata = ref.Visibilities(fx["u"], fx["v"], fx["freq"], fx["real"], fx["imag"], fx["weights"])
+    iv = {}
+    for name, kw in INVERT_CASES.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = inv.invert(fxdata, **kw)
+        im = r.image[:, :, 0, 0]
+        iv[name + "/sample"] = im[::4, ::4].copy() if im.shape[0] > 128 else im.copy()     # keep the file small
+        iv[name + "/stats"] = np.array([im.sum(), im.max(), im.min(), np.abs(im).sum()])
+        iv[name + "/x"] = r.x
+    np.savez_compressed(os.path.join(HERE, "invert_golden.npz"), **iv)
 
     # chisq of the live reference (channel 0, float return)
     rng = np.random.default_rng(99)
