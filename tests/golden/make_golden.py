@@ -194,9 +194,11 @@ def main():
 
     # invert() of the reference (invert.py + compiled grid + scipy.fftpack) on the fixture
     inv = load_reference_invert(ref)
-    fxdata = ref.Visibilities(fx["u"], fx["v"], fx["freq"], fx["real"], fx["imag"], fx["weights"])
     iv = {}
     for name, kw in INVERT_CASES.items():
+        # fresh copies: invert(beam=True) overwrites the caller's real/imag arrays in place (:18-19)
+        fxdata = ref.Visibilities(fx["u"].copy(), fx["v"].copy(), fx["freq"].copy(), fx["real"].copy(),
+                                  fx["imag"].copy(), fx["weights"].copy())
         with contextlib.redirect_stdout(io.StringIO()):
             r = inv.invert(fxdata, **kw)
         im = r.image[:, :, 0, 0]
