@@ -35,10 +35,12 @@ METRIC = "pixel_visibility_pairs_per_s"
 UNIT = "pairs/s"
 FLOP_PER_PAIR = 4.0          # algorithmic: 2 FMA per (pixel, uv, channel) pair
 L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
+# DRAM bytes per DFT launch measured by ncu (bytes), keyed by (workload, n_gpus)
+NCU_TRAFFIC_BYTES = {("C3", 1): 571.6e6, ("C2", 1): 12.27e6}
 
 
 def workload_config(name, nuv_override=None):
-    n, nf, nuv, px, dra, ddec = synth.CONFIGS[name]
+    n, nf, nuv, px, dra, ddec = synth.CONFIGS["C3" if name == "C5" else name]
     if nuv_override:
         nuv = nuv_override
     return dict(name=name, npix=n, nf=nf, nuv=nuv, pixelsize=px, dRA=dra, dDec=ddec)
@@ -49,7 +51,9 @@ def describe(cfg, world):
                    "(BASELINE.json configs[2])",
              "C2": "continuum 1024x1024 image onto 1M uv points with dRA/dDec offset + chi^2 "
                    "(BASELINE.json configs[1])",
-             "C1": "256x256 single channel onto 50k uv points (BASELINE.json configs[0])"}
+             "C1": "256x256 single channel onto 50k uv points (BASELINE.json configs[0])",
+             "C5": "batched likelihood for emcee walkers x 512x512x64-channel cubes, walkers sharded over the GPUs "
+                   "(BASELINE.json configs[4])"}
     return {"workload": names[cfg["name"]], "npix": cfg["npix"], "channels": cfg["nf"], "nuv": cfg["nuv"],
             "pairs_per_step": float(cfg["npix"]) ** 2 * cfg["nuv"] * cfg["nf"],
             "partition": "uv points sharded over %d rank(s), cube replicated, all-reduce of nf+1 doubles" % world,
@@ -202,6 +206,83 @@ def cpu_baseline_port(cfg):
                       "one sincos per pixel-visibility pair, OpenMP)" % (nuv_s, cfg["nuv"], cfg["nf"])}
 
 
+def run_walker_batch(args, cfg, rank, local_rank, world):
+    """BASELINE.json configs[4]: W walkers' cubes against ONE dataset; walkers are split over the ranks,
+    every rank holds the whole dataset, no collective on the data path (one gather of W doubles)."""
+    import torch
+    import torch.distributed as dist
+    from pdspy_b200 import _lib, DeviceBuffer, PinnedArray, dist as pdist
+    from pdspy_b200.device import Dataset
+    L = _lib.lib()
+    _lib.check(L.pdsb_set_stream(torch.cuda.current_stream().cuda_stream))
+    n, nf = cfg["npix"], cfg["nf"]
+    u, v = synth.synth_uv(cfg["nuv"], cfg["pixelsize"] * A)
+    re, im, w = synth.synth_data(cfg["nuv"], nf)
+    ds = Dataset(u, v)
+    ds.set_data(re, im, w)
+    del re, im, w
+    ws, we = pdist.shard_walkers(args.walkers, rank, world)
+    nw = we - ws
+    base = np.ascontiguousarray(synth.synth_image(n, nf, cfg["pixelsize"])[:, :, :, 0])
+    pinned = PinnedArray((max(nw, 1), n, n, nf))
+    for k in range(nw):
+        pinned.array[k] = base * (1.0 + 0.01 * (ws + k))
+    dcubes = DeviceBuffer.from_numpy(pinned.array[:max(nw, 1)])
+    dxy = cfg["pixelsize"] * A
+    dra = np.ascontiguousarray(np.full(max(nw, 1), cfg["dRA"] * A))
+    ddec = np.ascontiguousarray(np.full(max(nw, 1), cfg["dDec"] * A))
+    out = np.empty(max(nw, 1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(cubes, kind):
+        if nw > 0:
+            _lib.check(L.pdsb_loglike_batch(ds.handle, _lib.ptr(cubes), nw, n, n, nf, kind, float(dxy), _lib.ptr(dra),
+                                            _lib.ptr(ddec), _lib.ptr(out)))
+
+    step(dcubes, _lib.DEVICE)                       # warm-up: one full batch
+    barrier()
+    n0 = ctypes.c_int64()
+    L.pdsb_launch_count(ctypes.byref(n0))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(dcubes, _lib.DEVICE)
+    e1.record()
+    barrier()
+    n1 = ctypes.c_int64()
+    L.pdsb_launch_count(ctypes.byref(n1))
+    dev_ms = e0.elapsed_time(e1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(pinned.array, _lib.HOST)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        pairs = float(n) * n * cfg["nuv"] * nf * args.walkers * args.steps
+        cfgd = describe(cfg, world)
+        cfgd.update({"walkers": args.walkers, "walkers_per_rank": nw,
+                     "partition": "%d walkers split over %d rank(s), dataset replicated, no data-path collective"
+                                  % (args.walkers, world), "cache": "each cube (134 MB fp64) exceeds the L2"})
+        print(json.dumps({
+            "metric": METRIC, "value": pairs / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": 1, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 products, f64 phase seeds and accumulation", "data": "synthetic",
+            "config": cfgd, "likelihood_evals_per_s": args.walkers * args.steps / (dev_ms * 1e-3),
+            "e2e": {"value": pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nw * base.nbytes),
+                    "d2h_bytes_per_step": int(nw * nf * 8), "ms_per_step": e2e_s / args.steps * 1e3,
+                    "likelihood_evals_per_s": args.walkers * args.steps / e2e_s,
+                    "api": "pdsb_loglike_batch (host fp64 cubes in, host lnlike[W] out)"},
+            "gpu_launches": int(n1.value - n0.value), "lnlike0": float(out[0])}))
+
+
 # ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -209,7 +290,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--walkers", type=int, default=128, help="C5: total emcee walkers (sharded over ranks)")
     ap.add_argument("--nuv", type=int, default=0, help="override the uv count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -238,6 +320,12 @@ def main():
     from pdspy_b200 import _lib, DeviceBuffer, PinnedArray
     from pdspy_b200.dist import ShardedLikelihood
     L = _lib.lib()
+    if args.workload == "C5":
+        run_walker_batch(args, cfg, rank, local_rank, world)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     def barrier():
         if world > 1:
@@ -353,7 +441,11 @@ def main():
                                  "fold needs 1 FMA per pixel per uv point instead of 2, and a Hermitian-doubled uv "
                                  "list is evaluated for one half; frac > 1 is those two algorithmic savings, "
                                  "executed_frac is the pipe utilisation",
-                "launch_ms": dft_avg_ms, "launches": int(dft_n.value), "traffic": None},
+                "launch_ms": dft_avg_ms, "launches": int(dft_n.value),
+                "traffic": NCU_TRAFFIC_BYTES.get((cfg["name"], world)),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this "
+                                  "launch (profiles/r01_dft_ncu_c3_default.md, r01_dft_ncu.md); null where not captured",
+                "algorithmic_bytes": float(n) * n * nf * 4 + like.ds.nuv_unique * 16.0 * (1 + nf)},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(cfg)
