@@ -178,7 +178,7 @@ def run_reference(args, cfg, rank, world):
                                      "O(n^2 log n + nuv))"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "likelihood_evals_per_s_equiv": args.steps / dt * nch / cfg["nf"]}
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline_port(cfg):
@@ -271,7 +271,7 @@ def run_walker_batch(args, cfg, rank, local_rank, world):
         cfgd.update({"walkers": args.walkers, "walkers_per_rank": nw,
                      "partition": "%d walkers split over %d rank(s), dataset replicated, no data-path collective"
                                   % (args.walkers, world), "cache": "each cube (134 MB fp64) exceeds the L2"})
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": pairs / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": 1, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 products, f64 phase seeds and accumulation", "data": "synthetic",
@@ -280,11 +280,30 @@ def run_walker_batch(args, cfg, rank, local_rank, world):
                     "d2h_bytes_per_step": int(nw * nf * 8), "ms_per_step": e2e_s / args.steps * 1e3,
                     "likelihood_evals_per_s": args.walkers * args.steps / e2e_s,
                     "api": "pdsb_loglike_batch (host fp64 cubes in, host lnlike[W] out)"},
-            "gpu_launches": int(n1.value - n0.value), "lnlike0": float(out[0])}))
+            "gpu_launches": int(n1.value - n0.value), "lnlike0": float(out[0])})
 
 
 # ------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Keep stdout to the one JSON line: NCCL prints its version banner (and libraries their notices) on
+    # fd 1, so fd 1 is pointed at stderr for the whole run and the result goes to a saved copy.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -306,9 +325,6 @@ def main():
         run_reference(args, cfg, rank, world)
         return
 
-    # keep stdout to the one JSON line: NCCL_DEBUG=VERSION/INFO prints its banner on stdout
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     os.environ["PDSB_DEVICE"] = str(local_rank)
@@ -449,7 +465,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(cfg)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
