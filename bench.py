@@ -40,6 +40,8 @@ NCU_TRAFFIC_BYTES = {("C3", 1): 571.6e6, ("C2", 1): 12.27e6}
 
 
 def workload_config(name, nuv_override=None):
+    if name == "C4":
+        return dict(name="C4", npix=2048, nf=1, nuv=nuv_override or 10_000_000, pixelsize=0.01, dRA=0.0, dDec=0.0)
     n, nf, nuv, px, dra, ddec = synth.CONFIGS["C3" if name == "C5" else name]
     if nuv_override:
         nuv = nuv_override
@@ -139,6 +141,36 @@ def run_reference(args, cfg, rank, world):
     Bounded sample per step: NCH_SAMPLE of the channels, all uv points, all pixels."""
     if rank != 0:
         return
+    if cfg["name"] == "C4":
+        # the reference's own compiled grid() (oracle/_ref), serial by construction
+        from oracle import build_ref
+        ref = build_ref.load()
+        if ref is None:
+            emit({"impl": "reference", "unavailable": "oracle/_ref (the reference's compiled grid) is not built"})
+            return
+        nvis, G = cfg["nuv"], cfg["npix"]
+        ns = min(nvis, 300_000)
+        u, v = synth.synth_uv(nvis, cfg["pixelsize"] * A)
+        re, im, w = synth.synth_data(ns, 1)
+        binsize = 2.2 * np.hypot(u, v).max() / G
+        dd = ref.Visibilities(u[:ns].copy(), v[:ns].copy(), synth.synth_freq(1), re, im, w)
+        for _ in range(args.warmup):
+            ref.grid(dd, gridsize=G, binsize=binsize, convolution="expsinc")
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ref.grid(dd, gridsize=G, binsize=binsize, convolution="expsinc")
+        dt = time.perf_counter() - t0
+        value = ns * args.steps / dt
+        emit({"impl": "reference", "metric": "gridded_visibilities_per_s", "value": value, "unit": "vis/s",
+              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+              "higher_is_better": True, "scaling": "replicas only (not sharded)", "vs_baseline": None, "dtype": "f64",
+              "data": "synthetic",
+              "config": {"workload": "grid() of 10M visibilities onto 2048x2048, exp*sinc convolution kernel, natural "
+                                     "weights (BASELINE.json configs[3])", "nvis": nvis, "gridsize": G},
+              "cpu_baseline": {"value": value, "unit": "vis/s", "cores": 1, "kind": "reference",
+                               "sample": "first %d of %d visibilities per step" % (ns, nvis)},
+              "e2e": {"value": value, "unit": "vis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
     from concurrent.futures import ThreadPoolExecutor
     from oracle import dft as od, likelihood as ol
     cores = os.cpu_count() or 1
@@ -204,6 +236,103 @@ def cpu_baseline_port(cfg):
     return {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
             "sample": "first %d of %d uv points, all pixels, all %d channels, one pass (exact fp64 direct DFT, "
                       "one sincos per pixel-visibility pair, OpenMP)" % (nuv_s, cfg["nuv"], cfg["nf"])}
+
+
+def run_gridding(args, cfg, rank, world):
+    """BASELINE.json configs[3]: grid() of 10M visibilities onto 2048^2 with the exp*sinc convolution
+    kernel and weights (fast mode).  Metric: visibilities/s; roofline: HBM on the algorithmic bytes
+    (40 B per visibility + 24 B per cell)."""
+    if rank != 0:
+        return                                        # the path is not sharded: one GPU (DESIGN.md section 5)
+    from pdspy_b200 import _lib, DeviceBuffer
+    from pdspy_b200.interferometry import grid as grid_py, Visibilities
+    from oracle import grid as og
+    L = _lib.lib()
+    nvis, G = cfg["nuv"], cfg["npix"]
+    u, v = synth.synth_uv(nvis, cfg["pixelsize"] * A)
+    re, im, w = synth.synth_data(nvis, 1)
+    freq = synth.synth_freq(1)
+    binsize = 2.2 * np.hypot(u, v).max() / G
+    uu, vv = og.cell_centres(G, binsize)               # numpy.linspace of libinterferometry.pyx:370-381
+    d = {k: DeviceBuffer.from_numpy(a) for k, a in dict(u=u, v=v, freq=freq, re=re, im=im, w=w, uu=uu, vv=vv).items()}
+    o_re, o_im, o_w = (DeviceBuffer(G * G * 8) for _ in range(3))
+    flush = DeviceBuffer(L2_FLUSH_BYTES)
+    nout = ctypes.c_int64()
+
+    def step():
+        _lib.check(L.pdsb_grid(_lib.ptr(d["u"]), _lib.ptr(d["v"]), _lib.ptr(d["freq"]), _lib.ptr(d["re"]), _lib.ptr(d["im"]),
+                               _lib.ptr(d["w"]), nvis, 1, _lib.DEVICE, G, float(binsize), _lib.ptr(d["uu"]), _lib.ptr(d["vv"]),
+                               _lib.CONV["expsinc"], _lib.WEIGHTING["natural"], 2.0, 0, 0, 0, 0,
+                               _lib.ptr(o_re), _lib.ptr(o_im), _lib.ptr(o_w), None, None, None, _lib.DEVICE, None))
+
+    for _ in range(args.warmup):
+        step()
+    _lib.check(L.pdsb_profile_reset())
+    _lib.check(L.pdsb_profile_enable(1))
+    sampler = ClockSampler(0)
+    sampler.start()
+    n0 = ctypes.c_int64()
+    L.pdsb_launch_count(ctypes.byref(n0))
+    total_ms = 0.0
+    for _ in range(args.steps):
+        _lib.check(L.pdsb_memset(_lib.ptr(flush), 0, L2_FLUSH_BYTES))
+        _lib.check(L.pdsb_timer_start())
+        step()
+        ms = ctypes.c_double()
+        _lib.check(L.pdsb_timer_stop(ctypes.byref(ms)))
+        total_ms += ms.value
+    n1 = ctypes.c_int64()
+    L.pdsb_launch_count(ctypes.byref(n1))
+    _lib.check(L.pdsb_profile_enable(0))
+    clocks = sampler.stop()
+    tile_ms, tile_n = ctypes.c_double(), ctypes.c_int64()
+    _lib.check(L.pdsb_profile_get(b"grid_tile_accum", ctypes.byref(tile_ms), ctypes.byref(tile_n)))
+    # end to end through the Python mirror: host numpy arrays in, gridded Visibilities out
+    data = Visibilities(u, v, freq, re, im, w)
+    grid_py(data, gridsize=G, binsize=binsize, convolution="expsinc", deterministic=False)
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        grid_py(data, gridsize=G, binsize=binsize, convolution="expsinc", deterministic=False)
+    e2e_s = (time.perf_counter() - t0) / max(1, args.steps // 2)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    alg_bytes = nvis * 40.0 + G * G * 24.0
+    step_ms = total_ms / args.steps
+    line = {"metric": "gridded_visibilities_per_s", "value": nvis / (step_ms * 1e-3), "unit": "vis/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "replicas only (not sharded)", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "grid() of 10M visibilities onto 2048x2048, exp*sinc convolution kernel, natural "
+                                   "weights, fast (sorted-tile) mode (BASELINE.json configs[3])",
+                       "nvis": nvis, "gridsize": G, "cache": "L2 flushed (256 MB memset) before every timed step"},
+            "e2e": {"value": nvis / e2e_s, "unit": "vis/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(nvis * 40 + 2 * G * 8), "d2h_bytes_per_step": int(3 * G * G * 8),
+                    "api": "pdspy_b200.interferometry.grid(data, ..., deterministic=False) (numpy in, Visibilities out)"},
+            "gpu_launches": int(n1.value - n0.value), "clocks": clocks,
+            "roofline": {"kernel": "whole grid() step (prep + tile sort + grid_tile_kernel + normalise)", "bound": "hbm",
+                         "achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / hbm,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes": alg_bytes, "tile_kernel_ms": tile_ms.value / max(tile_n.value, 1),
+                         "traffic": None,
+                         "note": "36 fp64 read-modify-writes per visibility make on-chip accumulation, not HBM, the "
+                                 "limiter (SURVEY.md section 8d caveat)"}}
+    if not args.no_cpu_baseline:
+        from oracle import build_ref
+        ref = build_ref.load()
+        ns = 500_000
+        if ref is not None:
+            dd = ref.Visibilities(u[:ns].copy(), v[:ns].copy(), freq, re[:ns].copy(), im[:ns].copy(), w[:ns].copy())
+            t0 = time.perf_counter()
+            ref.grid(dd, gridsize=G, binsize=binsize, convolution="expsinc")
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": ns / dt, "unit": "vis/s", "cores": 1, "kind": "reference", "seconds": dt,
+                                    "sample": "first %d of %d visibilities, the reference's own compiled grid() "
+                                              "(oracle/_ref), serial by construction" % (ns, nvis)}
+    emit(line)
 
 
 def run_walker_batch(args, cfg, rank, local_rank, world):
@@ -309,7 +438,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--walkers", type=int, default=128, help="C5: total emcee walkers (sharded over ranks)")
     ap.add_argument("--nuv", type=int, default=0, help="override the uv count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -323,6 +452,10 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, cfg, rank, world)
+        return
+    if args.workload == "C4":
+        os.environ["PDSB_DEVICE"] = str(local_rank)
+        run_gridding(args, cfg, rank, world)
         return
 
     import torch

@@ -1,0 +1,105 @@
+"""BASELINE.json configurations at FULL size on one B200, through size-independent properties
+(the oracle cannot finish these sizes): configs[2] (512^2 x 64 ch x 1M uv likelihood),
+configs[3] (10M visibilities onto 2048^2), and a slice of configs[4] (walker batch)."""
+import contextlib
+import ctypes
+import io
+
+import numpy as np
+import pytest
+
+from oracle import dft as od, likelihood as ol, grid as og
+from pdspy_b200 import synth, _lib, Dataset, DeviceBuffer
+from pdspy_b200.interferometry import Visibilities, grid, loglike_image
+
+pytestmark = pytest.mark.gpu
+A = synth.ARCSEC
+
+
+def test_config3_full_likelihood(gpu):
+    """Full C3: the fused likelihood equals (a) chi^2 recomputed with numpy from the GPU's own
+    visibilities (1e-12), (b) the oracle chain on a random 1024-point subset of the uv list, and is
+    (c) linear: chi^2 of data == model is ~0 relative to chi^2 against zero data."""
+    c = synth.make_config("C3")
+    n, nf, nuv, px = c["npix"], c["nf"], c["u"].size, c["pixelsize"]
+    cube = np.ascontiguousarray(c["model"].image[:, :, :, 0])
+    ds = Dataset(c["u"], c["v"])
+    dcube = DeviceBuffer.from_numpy(cube)
+    dre, dim_ = DeviceBuffer(nuv * nf * 8), DeviceBuffer(nuv * nf * 8)
+    _lib.check(gpu.pdsb_sample_image(ds.handle, _lib.ptr(dcube), n, n, nf, _lib.DEVICE, px * A, c["dRA"] * A,
+                                     c["dDec"] * A, _lib.ptr(dre), _lib.ptr(dim_), _lib.DEVICE))
+    vre, vim = dre.download((nuv, nf)), dim_.download((nuv, nf))
+    # (b) subset parity against the exact oracle, relative to the channel maxima of the full set
+    sub = np.random.default_rng(3).choice(nuv, 1024, replace=False)
+    ref = od.exact_dft(c["u"][sub], c["v"][sub], c["model"].image, px * A, c["dRA"] * A, c["dDec"] * A)
+    scale = np.abs(vre + 1j * vim).max(axis=0)
+    assert (np.abs((vre + 1j * vim)[sub] - ref) / scale).max() < 1e-5
+    # Hermitian halves
+    h = nuv // 2
+    assert np.array_equal(vre[h:], vre[:h]) and np.array_equal(vim[h:], -vim[:h])
+    # (a) fused likelihood vs numpy on the GPU's own visibilities
+    re, im, w = synth.synth_data(nuv, nf)
+    ds.set_data(re, im, w)
+    chi2 = np.empty(nf)
+    ll = ctypes.c_double()
+    _lib.check(gpu.pdsb_loglike(ds.handle, _lib.ptr(dcube), n, n, nf, _lib.DEVICE, px * A, c["dRA"] * A, c["dDec"] * A,
+                                _lib.ptr(chi2), ctypes.cast(ctypes.byref(ll), ctypes.c_void_p)))
+    exp = ol.lnlike_vis_numpy(re, im, w, vre, vim)
+    assert abs(ll.value - exp) <= 1e-11 * abs(exp)
+    exp_chi2 = ol.chi2_per_channel_numpy(re, im, w, vre, vim)
+    assert np.all(np.abs(chi2 - exp_chi2) <= 1e-11 * np.abs(exp_chi2))
+    # (c) data == model: chi^2 collapses to rounding level
+    ds.set_data(vre, vim, np.abs(w) + 0.5)
+    _lib.check(gpu.pdsb_loglike(ds.handle, _lib.ptr(dcube), n, n, nf, _lib.DEVICE, px * A, c["dRA"] * A, c["dDec"] * A,
+                                _lib.ptr(chi2), ctypes.cast(ctypes.byref(ll), ctypes.c_void_p)))
+    assert chi2.max() == 0.0          # same kernels, same order: bit-identical model both times
+
+
+def test_config4_full_gridding(gpu):
+    """Full C4: 10M visibilities onto 2048^2.  Index maps equal numpy's; pillbox ordered == fast mode to
+    rounding; total weight conserved; expsinc imaging map sums to 1; a 1%-subset re-gridded by the oracle
+    equals gridding the same subset on the GPU bit for bit (pillbox)."""
+    px = 0.01
+    nvis, G = 10_000_000, 2048
+    u, v = synth.synth_uv(nvis, px * A)
+    re, im, w = synth.synth_data(nvis, 1)
+    freq = synth.synth_freq(1)
+    d = Visibilities(u, v, freq, re, im, w)
+    binsize = 2.2 * np.hypot(u, v).max() / G
+    with contextlib.redirect_stdout(io.StringIO()):
+        g, gi, gj, wm = grid(d, gridsize=G, binsize=binsize, return_maps=True, deterministic=True)
+        gf = grid(d, gridsize=G, binsize=binsize, deterministic=False)
+        ge = grid(d, gridsize=G, binsize=binsize, convolution="expsinc", imaging=True, deterministic=False)
+    i_ref, j_ref = og.index_maps(u, v, freq, G, binsize)
+    assert np.array_equal(gi, i_ref) and np.array_equal(gj, j_ref)
+    assert np.abs(gf.weights - g.weights).max() <= 1e-12 * g.weights.max()
+    assert np.abs(gf.real - g.real).max() <= 1e-9 * np.abs(g.real).max()
+    assert abs(g.weights.sum() - wm.sum()) <= 1e-9 * wm.sum()
+    assert abs(ge.weights.sum() - 1.0) < 1e-12
+    sel = np.arange(0, nvis, 100)
+    ds = Visibilities(u[sel].copy(), v[sel].copy(), freq, re[sel].copy(), im[sel].copy(), w[sel].copy())
+    with contextlib.redirect_stdout(io.StringIO()):
+        gs = grid(ds, gridsize=G, binsize=binsize)
+        o = og.grid(ds.u, ds.v, freq, ds.real, ds.imag, ds.weights, gridsize=G, binsize=binsize)
+    assert np.array_equal(gs.weights, o[5]) and np.array_equal(gs.real, o[3]) and np.array_equal(gs.imag, o[4])
+
+
+def test_config5_walker_slice(gpu):
+    """configs[4] shape, 3 walkers of the 128: the batch entry point equals three single calls."""
+    c = synth.make_config("C3", nuv=100_000)
+    n, nf, px = c["npix"], c["nf"], c["pixelsize"]
+    re, im, w = synth.synth_data(c["u"].size, nf)
+    ds = Dataset(c["u"], c["v"])
+    ds.set_data(re, im, w)
+    base = np.ascontiguousarray(c["model"].image[:, :, :, 0])
+    cubes = np.stack([base * (1 + 0.01 * k) for k in range(3)])
+    dra = np.ascontiguousarray(np.array([0.0, 0.01, -0.02]) * A)
+    ddec = np.ascontiguousarray(np.array([0.0, -0.01, 0.03]) * A)
+    out = np.empty(3)
+    _lib.check(gpu.pdsb_loglike_batch(ds.handle, _lib.ptr(cubes), 3, n, n, nf, _lib.HOST, px * A, _lib.ptr(dra),
+                                      _lib.ptr(ddec), _lib.ptr(out)))
+    for k in range(3):
+        one = ctypes.c_double()
+        _lib.check(gpu.pdsb_loglike(ds.handle, _lib.ptr(np.ascontiguousarray(cubes[k])), n, n, nf, _lib.HOST, px * A,
+                                    float(dra[k]), float(ddec[k]), None, ctypes.cast(ctypes.byref(one), ctypes.c_void_p)))
+        assert one.value == out[k]
