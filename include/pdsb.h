@@ -156,6 +156,7 @@ int pdsb_chisq(const double *d_real, const double *d_imag, const double *weights
  *   out_i, out_j                     [nuv, nf] uint32 index maps (:388-403)
  *   out_wmod                         [nuv, nf] fp64 weights after clamp + re-weighting
  *   n_outside                        count of (k,n) outside the grid (the WARNING of :424)
+ * imaging: 0 / 1 as the reference's flag; 2 = leave the raw sums (see pdsb_grid_normalise).
  * deterministic != 0: every cell is accumulated in the reference's (k, n) order, so
  * pillbox maps are bit-exact against the reference; 0: shared-memory tiles + atomics. */
 int pdsb_grid(const double *u, const double *v, const double *freq,
@@ -167,6 +168,11 @@ int pdsb_grid(const double *u, const double *v, const double *freq,
               double *out_real, double *out_imag, double *out_weights,
               uint32_t *out_i, uint32_t *out_j, double *out_wmod, int out_kind,
               int64_t *n_outside);
+
+/* Multi-GPU gridding (throughput mode): every rank grids its share of the
+ * visibilities with imaging = 2 (raw sums, no normalisation) into device maps, the maps are summed
+ * over ranks (NCCL all-reduce), then this applies the :525-533 normalisation on the device maps. */
+int pdsb_grid_normalise(double *real, double *imag, double *weights, int gridsize, int nch, int imaging);
 
 /* freqcorrect(): u' = (u[:,None]*freq/fbar).ravel() etc.; arrays on host or device. */
 int pdsb_freqcorrect(const double *u, const double *v, const double *freq, int64_t nuv, int nf,

@@ -62,6 +62,7 @@ SIGNATURES = {
     "pdsb_grid": [_P, _P, _P, _P, _P, _P, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _P, _P, _c_int, _c_int,
                   _c_dbl, _c_int, _c_int, _c_int, _c_int, _P, _P, _P, _P, _P, _P, _c_int,
                   ctypes.POINTER(_c_i64)],
+    "pdsb_grid_normalise": [_P, _P, _P, _c_int, _c_int, _c_int],
     "pdsb_freqcorrect": [_P, _P, _P, _c_i64, _c_int, _c_dbl, _c_int, _P, _P],
     "pdsb_bin_average": [_P, _P, _P, _P, _P, _P, _P, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                          _P, _P, _P, _P, _P, _c_int],

@@ -1088,8 +1088,8 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
     // ---- main scatter (:489-521) ----
     PDSB_CHECK(scatter(0, P.nmin, P.nmax, o_re, o_im, o_w));
 
-    // ---- normalisation (:525-533) ----
-    {
+    // ---- normalisation (:525-533); imaging == 2 leaves the raw sums (multi-GPU: reduce first) ----
+    if (imaging != 2) {
         double *wsum = small + 3 * nf;
         if (imaging) {
             PDSB_REQUIRE(nch <= nf, "channels");
@@ -1280,6 +1280,29 @@ int pdsb_center(const double *u, const double *v, const double *freq, const doub
         PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
+    return PDSB_OK;
+}
+
+// Normalisation step of grid() on DEVICE maps [G*G, nch] (after a multi-GPU reduction of raw sums).
+int pdsb_grid_normalise(double *real, double *imag, double *weights, int gridsize, int nch, int imaging)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    PDSB_REQUIRE(real && imag && weights && gridsize > 0 && nch > 0, "arguments");
+    const int64_t ncell = (int64_t)gridsize * gridsize * nch;
+    PDSB_CHECK(c.stage_b.ensure((size_t)(nch + SUM_BLOCKS * nch + 8) * sizeof(double)));
+    double *wsum = c.stage_b.as<double>(), *part = wsum + nch;
+    if (imaging) {
+        const int64_t nrow = (int64_t)gridsize * gridsize;
+        const int nb = (int)std::min<int64_t>(SUM_BLOCKS, std::max<int64_t>(1, (nrow + 255) / 256));
+        LaunchScope ls("grid_sum");
+        strided_sum_kernel<<<dim3(nb, nch), 256, 0, c.stream>>>(weights, nrow, nch, 0, part);
+        strided_sum_final_kernel<<<ceil_div(nch, 256), 256, 0, c.stream>>>(part, nb, nch, wsum);
+        PDSB_CUDA(cudaGetLastError());
+    }
+    LaunchScope ls("grid_normalise");
+    grid_normalise_kernel<<<ceil_div(ncell, 256), 256, 0, c.stream>>>(real, imag, weights, ncell, nch, imaging ? 1 : 0, wsum);
+    PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
 

@@ -105,3 +105,53 @@ class ShardedLikelihood:
         else:
             ny, nx = shape
         return combine_lnlike(self.chi2_device(image, ny, nx, kind, dxy, dRA, dDec), self.group)
+
+
+def sharded_grid(data_shard, gridsize=256, binsize=2000.0, convolution="pillbox", imaging=False, mode="continuum",
+                 group=None):
+    """grid() of a data set whose visibilities are split over the ranks (SURVEY.md section 8e,
+    throughput mode): each rank grids its shard into private raw-sum maps on its GPU (fast mode), the
+    three maps are all-reduced over NCCL, then normalised on the device.  Natural weighting only
+    (uniform / robust weights need the global binned-weight map first).  Every rank returns the full
+    gridded Visibilities.  Summation order differs from the serial reference: 1e-15-level differences,
+    like the single-GPU fast mode.  The mean frequency must be the same on every rank (it is: the
+    shards share `freq`)."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .interferometry import Visibilities
+    from .interferometry.grid import _WARNING
+    L = _lib.lib()
+    _lib.check(L.pdsb_set_stream(torch.cuda.current_stream().cuda_stream))
+    u, v, freq = data_shard.u, data_shard.v, data_shard.freq
+    nuv, nf = u.size, freq.size
+    nch = 1 if mode == "continuum" else nf
+    G = int(gridsize)
+    if G % 2 == 0:                                   # numpy.linspace of libinterferometry.pyx:370-381
+        uu = np.linspace(-G * binsize / 2, (G / 2 - 1) * binsize, G)
+    else:
+        uu = np.linspace(-(G - 1) * binsize / 2, (G - 1) * binsize / 2, G)
+    vv = uu.copy()
+    maps = torch.zeros((3, G * G, nch), dtype=torch.float64, device="cuda")
+    n_out = ctypes.c_int64(0)
+    _lib.check(L.pdsb_grid(_lib.ptr(_lib.f64(u)), _lib.ptr(_lib.f64(v)), _lib.ptr(_lib.f64(freq)),
+                           _lib.ptr(_lib.f64(data_shard.real)), _lib.ptr(_lib.f64(data_shard.imag)),
+                           _lib.ptr(_lib.f64(data_shard.weights)), nuv, nf, _lib.HOST, G, float(binsize),
+                           _lib.ptr(uu), _lib.ptr(vv), _lib.CONV[convolution], 0, 2.0, 0, _lib.MODE[mode],
+                           2, 0,                         # imaging = 2: raw sums; fast mode
+                           maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), None, None, None,
+                           _lib.DEVICE, ctypes.byref(n_out)))
+    nout = torch.tensor([n_out.value], dtype=torch.int64, device="cuda")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(maps, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(nout, op=dist.ReduceOp.SUM, group=group)
+    _lib.check(L.pdsb_grid_normalise(maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), G, nch,
+                                     1 if imaging else 0))
+    host = maps.cpu().numpy()
+    if int(nout.item()) > 0:
+        print(_WARNING)
+    new_u, new_v = np.meshgrid(uu, vv)
+    out_freq = np.array([freq.sum() / freq.size]) if mode == "continuum" else freq
+    return Visibilities(new_u.reshape(G * G), new_v.reshape(G * G), out_freq, np.ascontiguousarray(host[0]),
+                        np.ascontiguousarray(host[1]), np.ascontiguousarray(host[2]))
