@@ -262,6 +262,37 @@ __global__ void __launch_bounds__(128) fma_const_kernel(float *out, const float 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Legacy warp-level tensor-core path probe: mma.sync m16n8k8 TF32 (register fragments), 8 independent
+// accumulator tiles per warp.  Measures what the non-tcgen05 MMA path sustains on sm_100a.
+__global__ void __launch_bounds__(256) mma_tf32_bench_kernel(float *out, int iters, float seed)
+{
+    unsigned a[4], b[2];
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = __float_as_uint(1.0f + seed * 1e-3f * (threadIdx.x + i));
+#pragma unroll
+    for (int i = 0; i < 2; i++) b[i] = __float_as_uint(1.0f - seed * 1e-3f * (threadIdx.x + i));
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[t][i] = 0.f;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    float s = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) s += acc[t][i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace pdsb
 
 using namespace pdsb;
@@ -579,6 +610,12 @@ int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms_out)
                     iters = passes;
                     break;
                 }
+                case 11:
+                    // per thread-iteration: 4*8 MMAs of 16x8x8 = 1024 MAC per warp each -> per thread 32 MAC
+                    mma_tf32_bench_kernel<<<blocks, 256, 0, c.stream>>>(o, iters, 1.0f);
+                    threads = 256;
+                    fmas_per_thread_iter = 4.0 * 8.0 * (16.0 * 8.0 * 8.0) / 32.0;
+                    break;
                 default: set_error("unknown fma bench variant %d", variant); return PDSB_ERR_ARG;
             }
         }

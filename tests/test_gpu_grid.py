@@ -178,3 +178,20 @@ def test_config4_scale_properties(gpu):
     assert abs(g.weights.sum() - wm.sum()) <= 1e-9 * wm.sum()
     ge, _ = _quiet(grid, d, gridsize=G, binsize=binsize, convolution="expsinc", deterministic=False, imaging=True)
     assert abs(ge.weights.sum() - 1.0) < 1e-12
+
+
+def test_sharded_grid_single_rank_equals_grid(gpu):
+    """pdspy_b200.dist.sharded_grid (multi-GPU throughput mode) with one rank and no process group:
+    raw-sum maps -> device normalisation must equal the ordinary grid()."""
+    from pdspy_b200 import dist as pdist
+    u, v, freq, re, im, w = multi_channel_set()
+    d = Visibilities(u, v, freq, re, im, w)
+    for kw in (dict(gridsize=128, binsize=8000., convolution="expsinc", mode="spectralline", imaging=True),
+               dict(gridsize=128, binsize=8000., convolution="pillbox")):
+        a, out = _quiet(pdist.sharded_grid, pdist.shard_visibilities(d, 0, 1), **kw)
+        b, _ = _quiet(grid, d, **kw)
+        assert out.startswith("WARNING")
+        for nm in ("u", "v", "freq"):
+            np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm))
+        for nm in ("real", "imag", "weights"):
+            assert np.abs(getattr(a, nm) - getattr(b, nm)).max() <= 1e-12 * np.abs(getattr(b, nm)).max()
