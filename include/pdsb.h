@@ -125,6 +125,19 @@ int pdsb_sample_image(pdsb_dataset *ds, const double *image, int ny, int nx, int
  * Outputs are host doubles.  nf must equal the dataset's nf. */
 int pdsb_loglike(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind,
                  double dxy, double dRA, double dDec, double *chi2, double *lnlike);
+/* The same two calls with the model modifiers the reference applies in host passes around
+ * interpolate_model folded into the device epilogue:
+ *   chan_scale[nf] (host, nullable): V_i *= chan_scale[i] - the flux-calibration factor
+ *       (run_disk_model.py:319, run_flared_model.py:303) times the per-channel extinction exp(-tau_i)
+ *       (run_flared_model.py:286-299); scaling the image and scaling its transform are the same thing;
+ *   ff_flux, ff_x0, ff_y0 (radians): free-free point source, added to the REAL part only, every channel:
+ *       real += ff_flux*cos(2*3.14159*(u*ff_x0 + v*ff_y0))   (run_disk_model.py:329-334, model.py:102-104). */
+int pdsb_sample_image_ex(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind,
+                         double dxy, double dRA, double dDec, const double *chan_scale, double ff_flux,
+                         double ff_x0, double ff_y0, double *out_real, double *out_imag, int out_kind);
+int pdsb_loglike_ex(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind,
+                    double dxy, double dRA, double dDec, const double *chan_scale, double ff_flux,
+                    double ff_x0, double ff_y0, double *chi2, double *lnlike);
 /* Asynchronous variant for multi-GPU runs: chi2 per channel is left in DEVICE memory
  * (chi2_dev[nf]) on the library stream, ready for an NCCL all-reduce over uv shards; no host
  * synchronisation.  pdsb_dataset_logsum returns this shard's L. */

@@ -54,6 +54,10 @@ SIGNATURES = {
     "pdsb_dataset_destroy": [_P],
     "pdsb_sample_image": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _P, _c_int],
     "pdsb_loglike": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _P],
+    "pdsb_sample_image_ex": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _c_dbl, _c_dbl, _c_dbl,
+                             _P, _P, _c_int],
+    "pdsb_loglike_ex": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _c_dbl, _c_dbl, _c_dbl,
+                        _P, _P],
     "pdsb_loglike_device": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P],
     "pdsb_dataset_logsum": [_P, ctypes.POINTER(_c_dbl)],
     "pdsb_loglike_batch": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl, _P, _P, _P],

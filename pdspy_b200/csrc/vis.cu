@@ -66,16 +66,21 @@ struct EpiParams {
     int hermitian;
     const double *u, *v;     // unique
     double xs, ys;           // xcen - dRA, ycen - dDec (radians)
+    // optional model modifiers applied here instead of in host passes over the image / visibilities:
+    const double *chan_scale;   // [nf] device or null: V_i *= chan_scale[i]  (flux_unc, exp(-tau_i))
+    double ff_flux, ff_x0, ff_y0;   // point source added to the REAL part only (run_disk_model.py:329-334)
 };
 
 __device__ __forceinline__ void epi_load_tile(const EpiParams &P, double2 (*tile)[33])
 {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t kh = (int64_t)blockIdx.x * 32 + tx;
-    double gs = 0.0, gc = 1.0;
+    double gs = 0.0, gc = 1.0, ff = 0.0;
     if (kh < P.nuvh) {
         double a = P.u[kh] * P.xs + P.v[kh] * P.ys;
         sincospi(2.0 * (a - rint(a)), &gs, &gc);
+        // free-free term: real part of flux*exp(-2*3.14159*(0+1j*(u*x0+v*y0)))  (model.py:102-104)
+        if (P.ff_flux != 0.0) ff = P.ff_flux * cos(-2 * 3.14159 * (P.u[kh] * P.ff_x0 + P.v[kh] * P.ff_y0));
     }
 #pragma unroll
     for (int m = 0; m < 4; m++) {
@@ -89,6 +94,12 @@ __device__ __forceinline__ void epi_load_tile(const EpiParams &P, double2 (*tile
                 acc.y += p.y;
             }
             acc = make_double2(acc.x * gc - acc.y * gs, acc.x * gs + acc.y * gc);
+            if (P.chan_scale) {
+                const double sc = P.chan_scale[i];
+                acc.x *= sc;
+                acc.y *= sc;
+            }
+            acc.x += ff;
         }
         tile[il][tx] = acc;
     }
@@ -280,7 +291,31 @@ static EpiParams make_epi(const pdsb_dataset *ds, const DftRun &run, double dRA,
     e.v = ds->v;
     e.xs = run.g.xcen - dRA;
     e.ys = run.g.ycen - dDec;
+    e.chan_scale = nullptr;
+    e.ff_flux = e.ff_x0 = e.ff_y0 = 0.0;
     return e;
+}
+
+// Model modifiers of the *_ex entry points (set for the duration of one call).
+struct Mods {
+    const double *chan_scale_host = nullptr;
+    double ff_flux = 0.0, ff_x0 = 0.0, ff_y0 = 0.0;
+};
+static Mods g_mods;
+
+static int apply_mods(EpiParams &e, int nf)
+{
+    Context &c = ctx();
+    e.ff_flux = g_mods.ff_flux;
+    e.ff_x0 = g_mods.ff_x0;
+    e.ff_y0 = g_mods.ff_y0;
+    if (g_mods.chan_scale_host) {
+        PDSB_CHECK(c.pinned_note.ensure((size_t)nf * sizeof(double)));
+        PDSB_CUDA(cudaMemcpyAsync(c.pinned_note.ptr, g_mods.chan_scale_host, (size_t)nf * sizeof(double),
+                                  cudaMemcpyHostToDevice, c.stream));
+        e.chan_scale = c.pinned_note.as<double>();
+    }
+    return PDSB_OK;
 }
 
 // chi2 per channel for one image into chi2_dev[nf] (device)
@@ -293,6 +328,7 @@ static int run_loglike_dev(pdsb_dataset *ds, const double *image, int ny, int nx
     DftRun run;
     PDSB_CHECK(run_dft(ds, image, ny, nx, nf, image_kind, dxy, &run));
     EpiParams e = make_epi(ds, run, dRA, dDec);
+    PDSB_CHECK(apply_mods(e, nf));
     dim3 grid((unsigned)ceil_div(ds->nuvh, 32), (unsigned)ceil_div(nf, 32));
     PDSB_CHECK(c.red.ensure((size_t)grid.x * nf * sizeof(double)));
     {
@@ -439,6 +475,7 @@ int pdsb_sample_image(pdsb_dataset *ds, const double *image, int ny, int nx, int
     DftRun run;
     PDSB_CHECK(run_dft(ds, image, ny, nx, nf, image_kind, dxy, &run));
     EpiParams e = make_epi(ds, run, dRA, dDec);
+    PDSB_CHECK(apply_mods(e, nf));
     const size_t bytes = (size_t)ds->nuv * nf * sizeof(double);
     double *ore = out_real, *oim = out_imag;
     if (out_kind == PDSB_HOST) {
@@ -498,6 +535,32 @@ int pdsb_loglike(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, 
                  double dRA, double dDec, double *chi2, double *lnlike)
 {
     return loglike_impl(ds, image, 1, ny, nx, nf, image_kind, dxy, &dRA, &dDec, chi2, lnlike);
+}
+
+int pdsb_sample_image_ex(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
+                         double dRA, double dDec, const double *chan_scale, double ff_flux, double ff_x0,
+                         double ff_y0, double *out_real, double *out_imag, int out_kind)
+{
+    g_mods.chan_scale_host = chan_scale;
+    g_mods.ff_flux = ff_flux;
+    g_mods.ff_x0 = ff_x0;
+    g_mods.ff_y0 = ff_y0;
+    const int rc = pdsb_sample_image(ds, image, ny, nx, nf, image_kind, dxy, dRA, dDec, out_real, out_imag, out_kind);
+    g_mods = Mods();
+    return rc;
+}
+
+int pdsb_loglike_ex(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
+                    double dRA, double dDec, const double *chan_scale, double ff_flux, double ff_x0, double ff_y0,
+                    double *chi2, double *lnlike)
+{
+    g_mods.chan_scale_host = chan_scale;
+    g_mods.ff_flux = ff_flux;
+    g_mods.ff_x0 = ff_x0;
+    g_mods.ff_y0 = ff_y0;
+    const int rc = pdsb_loglike(ds, image, ny, nx, nf, image_kind, dxy, dRA, dDec, chi2, lnlike);
+    g_mods = Mods();
+    return rc;
 }
 
 int pdsb_loglike_device(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,

@@ -60,20 +60,52 @@ def interpolate_model(u, v, freq, model, nthreads=1, dRA=0., dDec=0.,
     return Visibilities(u, v, freq, real, imag, numpy.ones(real.shape))
 
 
-def loglike_image(data, model, dRA=0., dDec=0.):
+def _mods(nf, flux_unc, extinction, freefree, dRA, dDec):
+    scale = None
+    if flux_unc != 1.0 or extinction is not None:
+        scale = numpy.full(nf, float(flux_unc))
+        if extinction is not None:
+            scale = scale * numpy.asarray(extinction, dtype=numpy.float64)
+        scale = numpy.ascontiguousarray(scale)
+    ff = float(freefree) if freefree is not None else 0.0
+    return scale, ff, float(dRA * arcsec), float(dDec * arcsec)
+
+
+def model_visibilities(u, v, freq, model, dRA=0., dDec=0., flux_unc=1.0, extinction=None, freefree=None):
+    """interpolate_model plus the host passes the reference wraps around it, in one device pass:
+    image *= flux_unc (run_disk_model.py:319), image[:,:,i] *= extinction[i] (run_flared_model.py:286-299),
+    real += point-source free-free flux at (dRA, dDec) (run_disk_model.py:329-334).  Returns Visibilities."""
+    dxy = (model.x[1] - model.x[0]) * arcsec
+    image = _cube(model)
+    ny, nx, nf = image.shape[:3]
+    u = numpy.ascontiguousarray(u, dtype=numpy.float64)
+    v = numpy.ascontiguousarray(v, dtype=numpy.float64)
+    ds = dataset_for(u, v)
+    real, imag = numpy.empty((u.size, nf)), numpy.empty((u.size, nf))
+    scale, ff, x0, y0 = _mods(nf, flux_unc, extinction, freefree, dRA, dDec)
+    if u.size > 0:
+        L = _lib.lib()
+        _lib.check(L.pdsb_sample_image_ex(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST, float(dxy), x0, y0,
+                                          _lib.ptr(scale), ff, x0, y0, _lib.ptr(real), _lib.ptr(imag), _lib.HOST))
+    return Visibilities(u, v, freq, real, imag, numpy.ones(real.shape))
+
+
+def loglike_image(data, model, dRA=0., dDec=0., flux_unc=1.0, extinction=None, freefree=None):
     """Fused interpolate_model + visibility log-likelihood term (pdspy/utils/emcee.py:31-43) for
     one dataset: the model visibilities never leave the GPU.  `data` is a Visibilities with
-    u, v, real, imag, weights; `model` an Image.  Returns (lnlike, chi2_per_channel)."""
+    u, v, real, imag, weights; `model` an Image.  flux_unc / extinction / freefree as in
+    model_visibilities.  Returns (lnlike, chi2_per_channel)."""
     dxy = (model.x[1] - model.x[0]) * arcsec
     image = _cube(model)
     ny, nx, nf = image.shape[:3]
     ds = dataset_for(data.u, data.v, (data.real, data.imag, data.weights))
     chi2 = numpy.empty(nf)
     out = ctypes.c_double()
+    scale, ff, x0, y0 = _mods(nf, flux_unc, extinction, freefree, dRA, dDec)
     L = _lib.lib()
-    _lib.check(L.pdsb_loglike(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST, float(dxy),
-                              float(dRA * arcsec), float(dDec * arcsec), _lib.ptr(chi2),
-                              ctypes.cast(ctypes.byref(out), ctypes.c_void_p)))
+    _lib.check(L.pdsb_loglike_ex(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST, float(dxy), x0, y0,
+                                 _lib.ptr(scale), ff, x0, y0, _lib.ptr(chi2),
+                                 ctypes.cast(ctypes.byref(out), ctypes.c_void_p)))
     return out.value, chi2
 
 

@@ -124,3 +124,34 @@ def test_lnlike_signature_with_injected_model_runner(gpu):
     pars = {"x0": {"fixed": False}, "y0": {"fixed": False}, "z": {"fixed": True}}
     got2 = utils.dynesty.lnlike([0.05, -0.03], visibilities, {"file": []}, {}, pars, False, run_model=runner)
     assert got2 == got
+
+
+def test_model_modifiers_fused_into_the_epilogue(gpu):
+    """flux_unc scaling, per-channel extinction and the free-free point source (SURVEY.md section 8f
+    rank 2) applied on the device equal the reference's host passes around interpolate_model:
+    image *= flux_unc (run_disk_model.py:319); image[:,:,i] *= extinction[i] (run_flared_model.py:286-299);
+    real += F*exp(-2*3.14159*1j*(u*x0+v*y0)).real (run_disk_model.py:329-334)."""
+    from pdspy_b200.interferometry import model_visibilities
+    c = synth.make_config("C3", nuv=3000)
+    nf = c["nf"]
+    rng = np.random.default_rng(4)
+    ext = np.exp(-rng.uniform(0, 2, nf))
+    flux_unc, F, x0, y0 = 1.07, 0.0123, c["dRA"], c["dDec"]
+    img = c["model"].image * flux_unc
+    img = img * ext[None, None, :, None]
+    ref = od.exact_dft(c["u"], c["v"], img, c["pixelsize"] * A, x0 * A, y0 * A)
+    ff = F * np.exp(-2 * 3.14159 * (0 + 1j * (c["u"] * x0 * A + c["v"] * y0 * A)))
+    ref_re = ref.real + ff.real[:, None]
+    vis = model_visibilities(c["u"], c["v"], c["freq"], c["model"], dRA=x0, dDec=y0, flux_unc=flux_unc, extinction=ext,
+                             freefree=F)
+    scale = np.abs(ref).max(axis=0)
+    assert (np.abs(vis.real - ref_re) / scale).max() < 1e-5 and (np.abs(vis.imag - ref.imag) / scale).max() < 1e-5
+    re, im, w = synth.synth_data(3000, nf, model=(ref_re, ref.imag))
+    data = Visibilities(c["u"], c["v"], c["freq"], re, im, w)
+    ll, _ = loglike_image(data, c["model"], dRA=x0, dDec=y0, flux_unc=flux_unc, extinction=ext, freefree=F)
+    exp = ol.lnlike_vis_numpy(re, im, w, ref_re, ref.imag)
+    assert abs(ll - exp) <= 1e-7 * abs(exp)
+    # and without modifiers nothing changes
+    a = model_visibilities(c["u"], c["v"], c["freq"], c["model"], dRA=x0, dDec=y0)
+    b = interpolate_model(c["u"], c["v"], c["freq"], c["model"], dRA=x0, dDec=y0)
+    assert np.array_equal(a.real, b.real) and np.array_equal(a.imag, b.imag)
