@@ -69,7 +69,7 @@ struct Context {
     int dft_split = 0;
     // scratch
     Scratch img64, folded, partial, red, stage_a, stage_b, stage_c, stage_d, stage_e;
-    Scratch pinned_note;
+    Scratch small_dev;     // tiny per-call device arrays (channel scale factors)
 };
 
 Context &ctx();

@@ -362,7 +362,7 @@ int pdsb_shutdown(void)
     if (!c.inited) return PDSB_OK;
     cudaStreamSynchronize(c.stream);
     for (Scratch *s : {&c.img64, &c.folded, &c.partial, &c.red, &c.stage_a, &c.stage_b, &c.stage_c,
-                       &c.stage_d, &c.stage_e})
+                       &c.stage_d, &c.stage_e, &c.small_dev})
         s->release();
     for (auto &p : c.prof) {
         cudaEventDestroy(p.start);

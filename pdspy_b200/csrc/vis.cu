@@ -310,10 +310,10 @@ static int apply_mods(EpiParams &e, int nf)
     e.ff_x0 = g_mods.ff_x0;
     e.ff_y0 = g_mods.ff_y0;
     if (g_mods.chan_scale_host) {
-        PDSB_CHECK(c.pinned_note.ensure((size_t)nf * sizeof(double)));
-        PDSB_CUDA(cudaMemcpyAsync(c.pinned_note.ptr, g_mods.chan_scale_host, (size_t)nf * sizeof(double),
+        PDSB_CHECK(c.small_dev.ensure((size_t)nf * sizeof(double)));
+        PDSB_CUDA(cudaMemcpyAsync(c.small_dev.ptr, g_mods.chan_scale_host, (size_t)nf * sizeof(double),
                                   cudaMemcpyHostToDevice, c.stream));
-        e.chan_scale = c.pinned_note.as<double>();
+        e.chan_scale = c.small_dev.as<double>();
     }
     return PDSB_OK;
 }

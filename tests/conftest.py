@@ -12,6 +12,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the C-ABI library is built in-tree (git-ignored): build it when a fresh checkout has none
+    from pdspy_b200.csrc import build as _b
+    if _b.needs_build():
+        try:
+            _b.build()
+        except Exception as e:                      # no nvcc: the ABI tests will say so
+            print("could not build libpdsb.so:", e)
 
 
 @pytest.fixture(scope="session")
