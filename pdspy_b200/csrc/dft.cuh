@@ -83,4 +83,11 @@ int dft_variant_count();
 int dft_pick_variant();
 int dft_auto_split(int variant, int64_t nuvh, int nf, int ntile);
 
+// experimental tensor-core variant (dft_mma.cu), selected with pdsb_set_dft_variant(100)
+constexpr int DFT_VARIANT_MMA = 100;
+size_t mma_operand_bytes(int ny, int nx, int nf);
+int launch_fold_half(const double *img_dev, unsigned char *B, double *scale_ws, int ny, int nx, int nf);
+int mma_auto_split(int64_t nuvh, int nf, int nx);
+int launch_dft_mma(DftParams p, const unsigned char *B, int ny, int nx);
+
 }  // namespace pdsb

@@ -293,6 +293,36 @@ __global__ void __launch_bounds__(256) mma_tf32_bench_kernel(float *out, int ite
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// fp16 inputs, fp32 accumulate: mma.sync m16n8k16
+__global__ void __launch_bounds__(256) mma_f16_bench_kernel(float *out, int iters, float seed)
+{
+    unsigned a[4], b[2];
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = 0x3c003c00u + (unsigned)(seed * (threadIdx.x + i));
+#pragma unroll
+    for (int i = 0; i < 2; i++) b[i] = 0x3c003c00u + (unsigned)(seed * (threadIdx.x * 3 + i));
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[t][i] = 0.f;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    float s = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) s += acc[t][i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace pdsb
 
 using namespace pdsb;
@@ -362,7 +392,7 @@ int pdsb_shutdown(void)
     if (!c.inited) return PDSB_OK;
     cudaStreamSynchronize(c.stream);
     for (Scratch *s : {&c.img64, &c.folded, &c.partial, &c.red, &c.stage_a, &c.stage_b, &c.stage_c,
-                       &c.stage_d, &c.stage_e, &c.small_dev})
+                       &c.stage_d, &c.stage_e, &c.small_dev, &c.mma_ws})
         s->release();
     for (auto &p : c.prof) {
         cudaEventDestroy(p.start);
@@ -615,6 +645,11 @@ int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms_out)
                     mma_tf32_bench_kernel<<<blocks, 256, 0, c.stream>>>(o, iters, 1.0f);
                     threads = 256;
                     fmas_per_thread_iter = 4.0 * 8.0 * (16.0 * 8.0 * 8.0) / 32.0;
+                    break;
+                case 12:
+                    mma_f16_bench_kernel<<<blocks, 256, 0, c.stream>>>(o, iters, 1.0f);
+                    threads = 256;
+                    fmas_per_thread_iter = 4.0 * 8.0 * (16.0 * 8.0 * 16.0) / 32.0;
                     break;
                 default: set_error("unknown fma bench variant %d", variant); return PDSB_ERR_ARG;
             }

@@ -68,6 +68,7 @@ struct EpiParams {
     double xs, ys;           // xcen - dRA, ycen - dDec (radians)
     // optional model modifiers applied here instead of in host passes over the image / visibilities:
     const double *chan_scale;   // [nf] device or null: V_i *= chan_scale[i]  (flux_unc, exp(-tau_i))
+    const double *plane_unscale;   // [nf] device or null: undo the tensor-core variant's operand scaling
     double ff_flux, ff_x0, ff_y0;   // point source added to the REAL part only (run_disk_model.py:329-334)
 };
 
@@ -94,6 +95,11 @@ __device__ __forceinline__ void epi_load_tile(const EpiParams &P, double2 (*tile
                 acc.y += p.y;
             }
             acc = make_double2(acc.x * gc - acc.y * gs, acc.x * gs + acc.y * gc);
+            if (P.plane_unscale) {
+                const double us = P.plane_unscale[i];
+                acc.x *= us;
+                acc.y *= us;
+            }
             if (P.chan_scale) {
                 const double sc = P.chan_scale[i];
                 acc.x *= sc;
@@ -241,6 +247,7 @@ static int reduce_blocks(const double *blockpart, int nb, int ncol, double *out_
 struct DftRun {
     DftGeom g;
     int nsplit;
+    const double *plane_unscale = nullptr;   // experimental tensor-core variant: V_i *= plane_unscale[i]
 };
 
 static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
@@ -250,11 +257,38 @@ static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf
     PDSB_REQUIRE(ds && image, "dataset/image");
     PDSB_REQUIRE(ny > 0 && nx > 0 && nf > 0, "image shape");
     PDSB_REQUIRE(dxy > 0.0, "dxy");
+    const double *img_dev = nullptr;
+    PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
+    if (c.dft_variant == DFT_VARIANT_MMA) {
+        // experimental: fp16-split operands on the warp-level tensor-core path (dft_mma.cu)
+        DftGeom g = make_geom(ny, nx, nf, 32, dxy);
+        PDSB_CHECK(c.folded.ensure(mma_operand_bytes(ny, nx, nf)));
+        PDSB_CHECK(c.mma_ws.ensure((size_t)3 * nf * sizeof(double)));
+        PDSB_CHECK(launch_fold_half(img_dev, c.folded.as<unsigned char>(), c.mma_ws.as<double>(), ny, nx, nf));
+        const int nsplit = mma_auto_split(ds->nuvh, nf, nx);
+        PDSB_CHECK(c.partial.ensure((size_t)nsplit * nf * ds->nuvh * sizeof(double2)));
+        DftParams p;
+        p.F = nullptr;
+        p.u = ds->u;
+        p.v = ds->v;
+        p.nuvh = ds->nuvh;
+        p.dxy = dxy;
+        p.ntile = 0;
+        p.nchunk = g.nchunk;
+        p.nsplit = nsplit;
+        p.nf = nf;
+        p.hx = g.hx2 ? 0.5 : 0.0;
+        p.hy = g.hy2 ? 0.5 : 0.0;
+        p.part = c.partial.as<double2>();
+        PDSB_CHECK(launch_dft_mma(p, c.folded.as<unsigned char>(), ny, nx));
+        run->g = g;
+        run->nsplit = nsplit;
+        run->plane_unscale = c.mma_ws.as<double>() + 2 * nf;
+        return PDSB_OK;
+    }
     const int variant = dft_pick_variant();
     const int tcp = dft_variant_tcp(variant);
     DftGeom g = make_geom(ny, nx, nf, tcp, dxy);
-    const double *img_dev = nullptr;
-    PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
     PDSB_CHECK(c.folded.ensure(folded_floats(g) * sizeof(float)));
     PDSB_CHECK(launch_fold(img_dev, c.folded.as<float>(), g));
     const int nsplit = dft_auto_split(variant, ds->nuvh, nf, g.ntile);
@@ -292,6 +326,7 @@ static EpiParams make_epi(const pdsb_dataset *ds, const DftRun &run, double dRA,
     e.xs = run.g.xcen - dRA;
     e.ys = run.g.ycen - dDec;
     e.chan_scale = nullptr;
+    e.plane_unscale = run.plane_unscale;
     e.ff_flux = e.ff_x0 = e.ff_y0 = 0.0;
     return e;
 }

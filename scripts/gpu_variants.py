@@ -17,7 +17,7 @@ for wl, nuv in (("C2", None), ("C3", 250_000)):
     pairs = float(n) * n * nf * nuv
     sub = np.random.default_rng(1).choice(nuv, 256, replace=False)
     ref = od.exact_dft(c["u"][sub], c["v"][sub], c["model"].image, c["pixelsize"] * A, c["dRA"] * A, c["dDec"] * A)
-    for var in (11, 13, 18, 19, 20, 21, 22):
+    for var in (11, 100):
         L.pdsb_set_dft_variant(var)
         ts = []
         for rep in range(3):
