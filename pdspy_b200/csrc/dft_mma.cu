@@ -150,9 +150,11 @@ __global__ void __launch_bounds__(256) fold_half_kernel(const double *__restrict
 }
 
 // ---- the kernel: 128 threads = 4 warps; a warp owns MT m16 tiles = 16*MT uv points ----
-template <int MT>
-__global__ void __launch_bounds__(DFT_THREADS, 3) dft_mma_kernel(const DftParams P, const unsigned char *__restrict__ Bg,
-                                                                 int nkt)
+// NACC = 1: the three split products accumulate into one fp32 tile (a chain of 6 dependent MMAs per
+// K tile); NACC = 3: one accumulator per split product (independent chains, summed in the epilogue).
+template <int MT, int NACC, int MINB, int UNR>
+__global__ void __launch_bounds__(DFT_THREADS, MINB) dft_mma_kernel(const DftParams P,
+                                                                    const unsigned char *__restrict__ Bg, int nkt)
 {
     constexpr int NQ = 2 * MT;                    // uv points this thread contributes to (rows g and g+8 of each tile)
     constexpr int UVB = 4 * 16 * MT;              // uv points per block
@@ -254,15 +256,17 @@ __global__ void __launch_bounds__(DFT_THREADS, 3) dft_mma_kernel(const DftParams
             }
             const uint32_t sbase = m_smem_u32(smem_raw + (size_t)st * MMA_CHUNK_BYTES);
 
-#pragma unroll 1
+#pragma unroll UNR
             for (int ng = 0; ng < DFT_RC / 4; ng++) {
-                float C[2][MT][4];
+                float C[NACC][2][MT][4];
 #pragma unroll
-                for (int ty = 0; ty < 2; ty++)
+                for (int a = 0; a < NACC; a++)
 #pragma unroll
-                    for (int m = 0; m < MT; m++)
+                    for (int ty = 0; ty < 2; ty++)
 #pragma unroll
-                        for (int e = 0; e < 4; e++) C[ty][m][e] = 0.f;
+                        for (int m = 0; m < MT; m++)
+#pragma unroll
+                            for (int e = 0; e < 4; e++) C[a][ty][m][e] = 0.f;
 #pragma unroll
                 for (int ty = 0; ty < 2; ty++) {
                     const uint32_t rowaddr = sbase + (uint32_t)((ng * 16 + ty * 8) * MMA_ROW_BYTES) + ld_off;
@@ -275,16 +279,23 @@ __global__ void __launch_bounds__(DFT_THREADS, 3) dft_mma_kernel(const DftParams
                         for (int ks = 0; ks < 2; ks++) {
                             const uint32_t(&ahi)[4] = ty ? Ash[m][ks] : Ach[m][ks];
                             const uint32_t(&alo)[4] = ty ? Asl[m][ks] : Acl[m][ks];
-                            mma16816(C[ty][m], ahi, bh[2 * ks], bh[2 * ks + 1]);
-                            mma16816(C[ty][m], ahi, bl[2 * ks], bl[2 * ks + 1]);
-                            mma16816(C[ty][m], alo, bh[2 * ks], bh[2 * ks + 1]);
+                            mma16816(C[0][ty][m], ahi, bh[2 * ks], bh[2 * ks + 1]);
+                            mma16816(C[NACC > 1 ? 1 : 0][ty][m], ahi, bl[2 * ks], bl[2 * ks + 1]);
+                            mma16816(C[NACC > 1 ? 2 : 0][ty][m], alo, bh[2 * ks], bh[2 * ks + 1]);
                         }
                 }
                 // row-phase epilogue for this thread's row (s = ch*32 + ng*4 + j) of each of its uv points
 #pragma unroll
                 for (int q = 0; q < NQ; q++) {
                     const int m = q >> 1, h = q & 1;
-                    const float SS = C[0][m][2 * h], SD = C[0][m][2 * h + 1], DS = C[1][m][2 * h], DD = C[1][m][2 * h + 1];
+                    float SS = C[0][0][m][2 * h], SD = C[0][0][m][2 * h + 1], DS = C[0][1][m][2 * h],
+                          DD = C[0][1][m][2 * h + 1];
+                    if (NACC > 1) {
+                        SS += C[1][0][m][2 * h] + C[NACC - 1][0][m][2 * h];
+                        SD += C[1][0][m][2 * h + 1] + C[NACC - 1][0][m][2 * h + 1];
+                        DS += C[1][1][m][2 * h] + C[NACC - 1][1][m][2 * h];
+                        DD += C[1][1][m][2 * h + 1] + C[NACC - 1][1][m][2 * h + 1];
+                    }
                     vre[q] = fmaf(Er[q], SS, vre[q]);
                     vre[q] = fmaf(-Ei[q], DD, vre[q]);
                     vim[q] = fmaf(Er[q], DS, vim[q]);
@@ -359,10 +370,12 @@ int launch_fold_half(const double *img_dev, unsigned char *B, double *scale_ws /
     return PDSB_OK;
 }
 
+static int mma_mt(int variant) { return variant == 101 || variant == 103 ? 4 : 2; }
+
 int mma_auto_split(int64_t nuvh, int nf, int nx)
 {
     Context &c = ctx();
-    constexpr int UVB = 4 * 16 * 2;
+    const int UVB = 4 * 16 * mma_mt(c.dft_variant);
     const int nkt = ((nx + 1) / 2 + MMA_KT - 1) / MMA_KT;
     if (c.dft_split > 0) return c.dft_split < nkt ? c.dft_split : nkt;
     const int64_t uvtiles = (nuvh + UVB - 1) / UVB;
@@ -371,29 +384,45 @@ int mma_auto_split(int64_t nuvh, int nf, int nx)
     return (int)(ns < 1 ? 1 : (ns > nkt ? nkt : ns));
 }
 
-int launch_dft_mma(DftParams p, const unsigned char *B, int ny, int nx)
+template <int MT, int NACC, int MINB, int UNR>
+static int launch_mma_variant(DftParams p, const unsigned char *B, int nkt, const char *name)
 {
     Context &c = ctx();
-    constexpr int MT = 2;
-    const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
-    const int nkt = (npx + MMA_KT - 1) / MMA_KT;
-    p.nchunk = (npy + DFT_RC - 1) / DFT_RC;
     constexpr int UVB = 4 * 16 * MT;
     constexpr size_t smem = (size_t)DFT_NSTAGE * MMA_CHUNK_BYTES + (size_t)4 * (2 * MT) * DFT_THREADS * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        PDSB_CUDA(cudaFuncSetAttribute(dft_mma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PDSB_CUDA(cudaFuncSetAttribute(dft_mma_kernel<MT, NACC, MINB, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
         attr_set = true;
     }
     const int64_t uvtiles = (p.nuvh + UVB - 1) / UVB;
     if (uvtiles <= 0) return PDSB_OK;
-    PDSB_REQUIRE(p.nsplit >= 1 && p.nsplit <= nkt, "mma split");
-    PDSB_REQUIRE(p.nf <= 65535, "grid z dimension");
     dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)p.nf);
-    LaunchScope ls("dft_mma_f16x3");
-    dft_mma_kernel<MT><<<grid, DFT_THREADS, smem, c.stream>>>(p, B, nkt);
+    LaunchScope ls(name);
+    dft_mma_kernel<MT, NACC, MINB, UNR><<<grid, DFT_THREADS, smem, c.stream>>>(p, B, nkt);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
+}
+
+int launch_dft_mma(DftParams p, const unsigned char *B, int ny, int nx)
+{
+    Context &c = ctx();
+    const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
+    const int nkt = (npx + MMA_KT - 1) / MMA_KT;
+    p.nchunk = (npy + DFT_RC - 1) / DFT_RC;
+    PDSB_REQUIRE(p.nsplit >= 1 && p.nsplit <= nkt, "mma split");
+    PDSB_REQUIRE(p.nf <= 65535, "grid z dimension");
+    switch (c.dft_variant) {
+        case 100: return launch_mma_variant<2, 1, 3, 1>(p, B, nkt, "dft_mma_mt2");
+        case 101: return launch_mma_variant<4, 1, 2, 1>(p, B, nkt, "dft_mma_mt4");
+        case 102: return launch_mma_variant<2, 3, 3, 1>(p, B, nkt, "dft_mma_mt2_acc3");
+        case 103: return launch_mma_variant<4, 1, 2, 2>(p, B, nkt, "dft_mma_mt4_unr2");
+        case 104: return launch_mma_variant<2, 1, 3, 2>(p, B, nkt, "dft_mma_mt2_unr2");
+        case 105: return launch_mma_variant<2, 3, 2, 2>(p, B, nkt, "dft_mma_mt2_acc3_unr2");
+    }
+    set_error("unknown tensor-core DFT variant %d", c.dft_variant);
+    return PDSB_ERR_ARG;
 }
 
 }  // namespace pdsb

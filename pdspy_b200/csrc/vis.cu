@@ -259,7 +259,7 @@ static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf
     PDSB_REQUIRE(dxy > 0.0, "dxy");
     const double *img_dev = nullptr;
     PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
-    if (c.dft_variant == DFT_VARIANT_MMA) {
+    if (c.dft_variant >= DFT_VARIANT_MMA) {
         // experimental: fp16-split operands on the warp-level tensor-core path (dft_mma.cu)
         DftGeom g = make_geom(ny, nx, nf, 32, dxy);
         PDSB_CHECK(c.folded.ensure(mma_operand_bytes(ny, nx, nf)));
