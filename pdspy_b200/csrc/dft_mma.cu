@@ -150,14 +150,16 @@ __global__ void __launch_bounds__(256) fold_half_kernel(const double *__restrict
 }
 
 // ---- the kernel: 128 threads = 4 warps; a warp owns MT m16 tiles = 16*MT uv points ----
-// NACC = 1: the three split products accumulate into one fp32 tile (a chain of 6 dependent MMAs per
-// K tile); NACC = 3: one accumulator per split product (independent chains, summed in the epilogue).
-template <int MT, int NACC, int MINB, int UNR>
+// One CTA: 4 warps x MT m16 tiles of uv points, a range of K tiles (column tiles) and a GROUP of `pg`
+// planes (channels share uv points, hence the trig fragments: they are generated once per K tile and
+// reused for every plane of the group).  Loop order: K tile > plane > chunk of 32 row pairs.
+template <int MT, int MINB, int UNR>
 __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_mma_kernel(const DftParams P,
-                                                                    const unsigned char *__restrict__ Bg, int nkt)
+                                                                    const unsigned char *__restrict__ Bg, int nkt, int pg)
 {
     constexpr int NQ = 2 * MT;                    // uv points this thread contributes to (rows g and g+8 of each tile)
     constexpr int UVB = 4 * 16 * MT;              // uv points per block
+    constexpr int RESEED = 4;                     // chunks between fp64-seeded row phases (32 rotations of D^4)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *fst = reinterpret_cast<double *>(smem_raw + (size_t)DFT_NSTAGE * MMA_CHUNK_BYTES);
     __shared__ __align__(8) uint64_t full_bar[DFT_NSTAGE];
@@ -167,11 +169,17 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_mma_kernel(const DftPar
 #define MVI(q) fst[(3 * NQ + (q)) * DFT_THREADS + tid]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, j = lane & 3;
-    const int plane = blockIdx.z, sp = blockIdx.y;
+    const int plane0 = blockIdx.z * pg, sp = blockIdx.y;
+    const int npl = (P.nf - plane0) < pg ? (P.nf - plane0) : pg;
     const int kt0 = (int)(((int64_t)sp * nkt) / P.nsplit), kt1 = (int)(((int64_t)(sp + 1) * nkt) / P.nsplit);
     const int nkl = kt1 - kt0;
-    const int nit = nkl * P.nchunk;
-    const unsigned char *gbase = Bg + ((size_t)plane * nkt + kt0) * (size_t)P.nchunk * MMA_CHUNK_BYTES;
+    const int per_k = npl * P.nchunk;
+    const int nit = nkl * per_k;
+    auto chunk_src = [&](int it) -> const unsigned char * {
+        const int kl = it / per_k, rem = it - kl * per_k;
+        const int pl = rem / P.nchunk, ch = rem - pl * P.nchunk;
+        return Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)P.nchunk + ch) * MMA_CHUNK_BYTES;
+    };
 
     if (tid == 0) {
 #pragma unroll
@@ -184,8 +192,7 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_mma_kernel(const DftPar
         for (int s = 0; s < DFT_NSTAGE; s++)
             if (s < nit) {
                 m_mbar_expect_tx(&full_bar[s], MMA_CHUNK_BYTES);
-                m_tma_load_1d(smem_raw + (size_t)s * MMA_CHUNK_BYTES, gbase + (size_t)s * MMA_CHUNK_BYTES, MMA_CHUNK_BYTES,
-                              &full_bar[s]);
+                m_tma_load_1d(smem_raw + (size_t)s * MMA_CHUNK_BYTES, chunk_src(s), MMA_CHUNK_BYTES, &full_bar[s]);
             }
     }
 
@@ -198,8 +205,6 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_mma_kernel(const DftPar
         const double fuq = valid ? P.u[k] * P.dxy : 0.0, fvq = valid ? P.v[k] * P.dxy : 0.0;
         MFU(q) = fuq;
         MFV(q) = fvq;
-        MVR(q) = 0.0;
-        MVI(q) = 0.0;
         const double a4 = 4.0 * fvq;             // this thread's rows advance by 4 per n-group
         double s, c;
         sincospi(2.0 * (a4 - rint(a4)), &s, &c);
@@ -212,25 +217,37 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_mma_kernel(const DftPar
 
     int it = 0;
     for (int kl = 0; kl < nkl; kl++) {
-        // ---- A fragments of this K tile: trig[uv, t] split into fp16 hi + lo ----
+        // ---- A fragments of this K tile: trig[uv, t] split into fp16 hi + lo.  Per uv point one seed
+        //      at column t0 = 32 kt + 2j and an fp64 rotation through the 8 columns this lane needs
+        //      (offsets 0,1,8,9,16,17,24,25: steps +1,+7,+1,+7,...).
         uint32_t Ach[MT][2][4], Acl[MT][2][4], Ash[MT][2][4], Asl[MT][2][4];
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
             const double fuq = MFU(q);
             const int m = q >> 1, h = q & 1;
+            double a0 = fuq * ((double)((kt0 + kl) * MMA_KT + 2 * j) + P.hx);
+            double a1 = fuq, a7 = 7.0 * fuq;
+            a0 -= rint(a0);
+            a1 -= rint(a1);
+            a7 -= rint(a7);
+            float sf, cf;
+            sincospif((float)(2.0 * a0), &sf, &cf);
+            double cr = cf, ci = sf;
+            sincospif((float)(2.0 * a1), &sf, &cf);
+            const double r1c = cf, r1s = sf;
+            sincospif((float)(2.0 * a7), &sf, &cf);
+            const double r7c = cf, r7s = sf;
 #pragma unroll
             for (int pi = 0; pi < 4; pi++) {
-                // t pair pi: columns (kt*32 + 2j + 8*pi, +1)
-                const double t0 = (double)((kt0 + kl) * MMA_KT + 2 * j + 8 * pi) + P.hx;
                 __half ch[2], cl[2], sh[2], sl[2];
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    double a = fuq * (t0 + e);
-                    a -= rint(a);
-                    float s, c;
-                    sincospif((float)(2.0 * a), &s, &c);
-                    split_half(c, ch[e], cl[e]);
-                    split_half(s, sh[e], sl[e]);
+                    split_half((float)cr, ch[e], cl[e]);
+                    split_half((float)ci, sh[e], sl[e]);
+                    const double rc = e ? r7c : r1c, rs = e ? r7s : r1s;     // +1 then +7
+                    const double nr = cr * rc - ci * rs;
+                    ci = cr * rs + ci * rc;
+                    cr = nr;
                 }
                 const int ks = pi >> 1, reg = (pi & 1) * 2 + h;
                 Ach[m][ks][reg] = pack_half2(ch[0], ch[1]);
@@ -240,96 +257,108 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_mma_kernel(const DftPar
             }
         }
 
-        for (int ch = 0; ch < P.nchunk; ch++, it++) {
-            const int st = it % DFT_NSTAGE;
-            const uint32_t parity = (uint32_t)((it / DFT_NSTAGE) & 1);
-            float Er[NQ], Ei[NQ], vre[NQ], vim[NQ];
+        for (int pl = 0; pl < npl; pl++) {
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
-                double b0 = MFV(q) * ((double)(ch * DFT_RC + j) + P.hy);      // this thread's first row: j
-                b0 -= rint(b0);
-                sincospif((float)(2.0 * b0), &Ei[q], &Er[q]);
-                vre[q] = 0.f;
-                vim[q] = 0.f;
+                MVR(q) = 0.0;
+                MVI(q) = 0.0;
             }
-            while (!m_mbar_try_wait(&full_bar[st], parity)) {
-            }
-            const uint32_t sbase = m_smem_u32(smem_raw + (size_t)st * MMA_CHUNK_BYTES);
+            float Er[NQ], Ei[NQ];
+            for (int ch = 0; ch < P.nchunk; ch++, it++) {
+                const int st = it % DFT_NSTAGE;
+                const uint32_t parity = (uint32_t)((it / DFT_NSTAGE) & 1);
+                float vre[NQ], vim[NQ];
+                if (ch % RESEED == 0) {
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        double b0 = MFV(q) * ((double)(ch * DFT_RC + j) + P.hy);      // this thread's rows: j mod 4
+                        b0 -= rint(b0);
+                        sincospif((float)(2.0 * b0), &Ei[q], &Er[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    vre[q] = 0.f;
+                    vim[q] = 0.f;
+                }
+                while (!m_mbar_try_wait(&full_bar[st], parity)) {
+                }
+                const uint32_t sbase = m_smem_u32(smem_raw + (size_t)st * MMA_CHUNK_BYTES);
 
 #pragma unroll UNR
-            for (int ng = 0; ng < DFT_RC / 4; ng++) {
-                float C[NACC][2][MT][4];
-#pragma unroll
-                for (int a = 0; a < NACC; a++)
+                for (int ng = 0; ng < DFT_RC / 4; ng++) {
+                    float C[2][MT][4];
 #pragma unroll
                     for (int ty = 0; ty < 2; ty++)
 #pragma unroll
                         for (int m = 0; m < MT; m++)
 #pragma unroll
-                            for (int e = 0; e < 4; e++) C[a][ty][m][e] = 0.f;
+                            for (int e = 0; e < 4; e++) C[ty][m][e] = 0.f;
 #pragma unroll
-                for (int ty = 0; ty < 2; ty++) {
-                    const uint32_t rowaddr = sbase + (uint32_t)((ng * 16 + ty * 8) * MMA_ROW_BYTES) + ld_off;
-                    uint32_t bh[4], bl[4];
-                    ldmatrix_x4(rowaddr, bh[0], bh[1], bh[2], bh[3]);
-                    ldmatrix_x4(rowaddr + MMA_PART_BYTES, bl[0], bl[1], bl[2], bl[3]);
+                    for (int ty = 0; ty < 2; ty++) {
+                        const uint32_t rowaddr = sbase + (uint32_t)((ng * 16 + ty * 8) * MMA_ROW_BYTES) + ld_off;
+                        uint32_t bh[4], bl[4];
+                        ldmatrix_x4(rowaddr, bh[0], bh[1], bh[2], bh[3]);
+                        ldmatrix_x4(rowaddr + MMA_PART_BYTES, bl[0], bl[1], bl[2], bl[3]);
 #pragma unroll
-                    for (int m = 0; m < MT; m++)
+                        for (int m = 0; m < MT; m++)
 #pragma unroll
-                        for (int ks = 0; ks < 2; ks++) {
-                            const uint32_t(&ahi)[4] = ty ? Ash[m][ks] : Ach[m][ks];
-                            const uint32_t(&alo)[4] = ty ? Asl[m][ks] : Acl[m][ks];
-                            mma16816(C[0][ty][m], ahi, bh[2 * ks], bh[2 * ks + 1]);
-                            mma16816(C[NACC > 1 ? 1 : 0][ty][m], ahi, bl[2 * ks], bl[2 * ks + 1]);
-                            mma16816(C[NACC > 1 ? 2 : 0][ty][m], alo, bh[2 * ks], bh[2 * ks + 1]);
-                        }
+                            for (int ks = 0; ks < 2; ks++) {
+                                const uint32_t(&ahi)[4] = ty ? Ash[m][ks] : Ach[m][ks];
+                                const uint32_t(&alo)[4] = ty ? Asl[m][ks] : Acl[m][ks];
+                                mma16816(C[ty][m], ahi, bh[2 * ks], bh[2 * ks + 1]);
+                                mma16816(C[ty][m], ahi, bl[2 * ks], bl[2 * ks + 1]);
+                                mma16816(C[ty][m], alo, bh[2 * ks], bh[2 * ks + 1]);
+                            }
+                    }
+                    // row-phase epilogue for this thread's row (s = ch*32 + ng*4 + j) of each of its uv points
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        const int m = q >> 1, h = q & 1;
+                        const float SS = C[0][m][2 * h], SD = C[0][m][2 * h + 1], DS = C[1][m][2 * h],
+                                    DD = C[1][m][2 * h + 1];
+                        vre[q] = fmaf(Er[q], SS, vre[q]);
+                        vre[q] = fmaf(-Ei[q], DD, vre[q]);
+                        vim[q] = fmaf(Er[q], DS, vim[q]);
+                        vim[q] = fmaf(Ei[q], SD, vim[q]);
+                        const float nr = Er[q] * D4r[q] - Ei[q] * D4i[q];
+                        Ei[q] = Er[q] * D4i[q] + Ei[q] * D4r[q];
+                        Er[q] = nr;
+                    }
                 }
-                // row-phase epilogue for this thread's row (s = ch*32 + ng*4 + j) of each of its uv points
 #pragma unroll
                 for (int q = 0; q < NQ; q++) {
-                    const int m = q >> 1, h = q & 1;
-                    float SS = C[0][0][m][2 * h], SD = C[0][0][m][2 * h + 1], DS = C[0][1][m][2 * h],
-                          DD = C[0][1][m][2 * h + 1];
-                    if (NACC > 1) {
-                        SS += C[1][0][m][2 * h] + C[NACC - 1][0][m][2 * h];
-                        SD += C[1][0][m][2 * h + 1] + C[NACC - 1][0][m][2 * h + 1];
-                        DS += C[1][1][m][2 * h] + C[NACC - 1][1][m][2 * h];
-                        DD += C[1][1][m][2 * h + 1] + C[NACC - 1][1][m][2 * h + 1];
-                    }
-                    vre[q] = fmaf(Er[q], SS, vre[q]);
-                    vre[q] = fmaf(-Ei[q], DD, vre[q]);
-                    vim[q] = fmaf(Er[q], DS, vim[q]);
-                    vim[q] = fmaf(Ei[q], SD, vim[q]);
-                    const float nr = Er[q] * D4r[q] - Ei[q] * D4i[q];
-                    Ei[q] = Er[q] * D4i[q] + Ei[q] * D4r[q];
-                    Er[q] = nr;
+                    MVR(q) += (double)vre[q];
+                    MVI(q) += (double)vim[q];
+                }
+                __syncthreads();
+                if (tid == 0 && it + DFT_NSTAGE < nit) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    m_mbar_expect_tx(&full_bar[st], MMA_CHUNK_BYTES);
+                    m_tma_load_1d(smem_raw + (size_t)st * MMA_CHUNK_BYTES, chunk_src(it + DFT_NSTAGE), MMA_CHUNK_BYTES,
+                                  &full_bar[st]);
                 }
             }
+            // this (K tile, plane) pass is complete: the four lanes of a quad hold the sums over rows = j mod 4
+            // of the same uv points; reduce and add into the partial-sum array (this thread owns the entry)
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
-                MVR(q) += (double)vre[q];
-                MVI(q) += (double)vim[q];
-            }
-            __syncthreads();
-            if (tid == 0 && it + DFT_NSTAGE < nit) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                m_mbar_expect_tx(&full_bar[st], MMA_CHUNK_BYTES);
-                m_tma_load_1d(smem_raw + (size_t)st * MMA_CHUNK_BYTES, gbase + (size_t)(it + DFT_NSTAGE) * MMA_CHUNK_BYTES,
-                              MMA_CHUNK_BYTES, &full_bar[st]);
+                double vr = MVR(q), vi = MVI(q);
+                vr += __shfl_xor_sync(0xffffffffu, vr, 1);
+                vi += __shfl_xor_sync(0xffffffffu, vi, 1);
+                vr += __shfl_xor_sync(0xffffffffu, vr, 2);
+                vi += __shfl_xor_sync(0xffffffffu, vi, 2);
+                const int64_t k = (int64_t)blockIdx.x * UVB + warp * (16 * MT) + (q >> 1) * 16 + ((q & 1) ? g + 8 : g);
+                if (j == 0 && k < P.nuvh) {
+                    double2 *dst = P.part + ((size_t)sp * P.nf + (plane0 + pl)) * (size_t)P.nuvh + k;
+                    if (kl == 0) *dst = make_double2(vr, vi);
+                    else {
+                        const double2 o = *dst;
+                        *dst = make_double2(o.x + vr, o.y + vi);
+                    }
+                }
             }
         }
-    }
-
-    // the four lanes of a quad hold the partial sums of rows = j mod 4 of the same uv points
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        double vr = MVR(q), vi = MVI(q);
-        vr += __shfl_xor_sync(0xffffffffu, vr, 1);
-        vi += __shfl_xor_sync(0xffffffffu, vi, 1);
-        vr += __shfl_xor_sync(0xffffffffu, vr, 2);
-        vi += __shfl_xor_sync(0xffffffffu, vi, 2);
-        const int64_t k = (int64_t)blockIdx.x * UVB + warp * (16 * MT) + (q >> 1) * 16 + ((q & 1) ? g + 8 : g);
-        if (j == 0 && k < P.nuvh) P.part[((size_t)sp * P.nf + plane) * (size_t)P.nuvh + k] = make_double2(vr, vi);
     }
 #undef MFU
 #undef MFV
@@ -371,6 +400,7 @@ int launch_fold_half(const double *img_dev, unsigned char *B, double *scale_ws /
 }
 
 static int mma_mt(int variant) { return variant == 101 || variant == 103 ? 4 : 2; }
+static int mma_pg(int nf) { return nf < 8 ? nf : 8; }      // planes per CTA (share the trig fragments)
 
 int mma_auto_split(int64_t nuvh, int nf, int nx)
 {
@@ -379,12 +409,13 @@ int mma_auto_split(int64_t nuvh, int nf, int nx)
     const int nkt = ((nx + 1) / 2 + MMA_KT - 1) / MMA_KT;
     if (c.dft_split > 0) return c.dft_split < nkt ? c.dft_split : nkt;
     const int64_t uvtiles = (nuvh + UVB - 1) / UVB;
-    const int64_t capacity = (int64_t)c.sm_count * 3, base = std::max<int64_t>(1, uvtiles * nf);
+    const int pgroups = (nf + mma_pg(nf) - 1) / mma_pg(nf);
+    const int64_t capacity = (int64_t)c.sm_count * 3, base = std::max<int64_t>(1, uvtiles * pgroups);
     const int64_t ns = (20 * capacity + base - 1) / base;
     return (int)(ns < 1 ? 1 : (ns > nkt ? nkt : ns));
 }
 
-template <int MT, int NACC, int MINB, int UNR>
+template <int MT, int MINB, int UNR>
 static int launch_mma_variant(DftParams p, const unsigned char *B, int nkt, const char *name)
 {
     Context &c = ctx();
@@ -392,15 +423,16 @@ static int launch_mma_variant(DftParams p, const unsigned char *B, int nkt, cons
     constexpr size_t smem = (size_t)DFT_NSTAGE * MMA_CHUNK_BYTES + (size_t)4 * (2 * MT) * DFT_THREADS * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        PDSB_CUDA(cudaFuncSetAttribute(dft_mma_kernel<MT, NACC, MINB, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PDSB_CUDA(cudaFuncSetAttribute(dft_mma_kernel<MT, MINB, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         attr_set = true;
     }
     const int64_t uvtiles = (p.nuvh + UVB - 1) / UVB;
     if (uvtiles <= 0) return PDSB_OK;
-    dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)p.nf);
+    const int pg = mma_pg(p.nf);
+    dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)((p.nf + pg - 1) / pg));
     LaunchScope ls(name);
-    dft_mma_kernel<MT, NACC, MINB, UNR><<<grid, DFT_THREADS, smem, c.stream>>>(p, B, nkt);
+    dft_mma_kernel<MT, MINB, UNR><<<grid, DFT_THREADS, smem, c.stream>>>(p, B, nkt, pg);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
@@ -412,14 +444,13 @@ int launch_dft_mma(DftParams p, const unsigned char *B, int ny, int nx)
     const int nkt = (npx + MMA_KT - 1) / MMA_KT;
     p.nchunk = (npy + DFT_RC - 1) / DFT_RC;
     PDSB_REQUIRE(p.nsplit >= 1 && p.nsplit <= nkt, "mma split");
-    PDSB_REQUIRE(p.nf <= 65535, "grid z dimension");
+    PDSB_REQUIRE(p.nf <= 65535 * 8, "grid z dimension");
     switch (c.dft_variant) {
-        case 100: return launch_mma_variant<2, 1, 3, 1>(p, B, nkt, "dft_mma_mt2");
-        case 101: return launch_mma_variant<4, 1, 2, 1>(p, B, nkt, "dft_mma_mt4");
-        case 102: return launch_mma_variant<2, 3, 3, 1>(p, B, nkt, "dft_mma_mt2_acc3");
-        case 103: return launch_mma_variant<4, 1, 2, 2>(p, B, nkt, "dft_mma_mt4_unr2");
-        case 104: return launch_mma_variant<2, 1, 3, 2>(p, B, nkt, "dft_mma_mt2_unr2");
-        case 105: return launch_mma_variant<2, 3, 2, 2>(p, B, nkt, "dft_mma_mt2_acc3_unr2");
+        case 100: return launch_mma_variant<2, 3, 1>(p, B, nkt, "dft_mma_mt2");
+        case 101: return launch_mma_variant<4, 2, 1>(p, B, nkt, "dft_mma_mt4");
+        case 102: return launch_mma_variant<2, 3, 2>(p, B, nkt, "dft_mma_mt2_unr2");
+        case 103: return launch_mma_variant<4, 2, 2>(p, B, nkt, "dft_mma_mt4_unr2");
+        case 104: return launch_mma_variant<2, 2, 2>(p, B, nkt, "dft_mma_mt2_unr2_occ2");
     }
     set_error("unknown tensor-core DFT variant %d", c.dft_variant);
     return PDSB_ERR_ARG;
