@@ -544,6 +544,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
 
+    # ---- extra (not part of value / e2e): the experimental tensor-core variant on the same step ----
+    # mma.sync fp16 2-way-split operands (pdspy_b200/csrc/dft_mma.cu, opt-in via pdsb_set_dft_variant(103));
+    # same data flow and outputs, parity 2-5e-7 of max|V| (tests/test_gpu_dft.py).  Reported for context:
+    # the default and the headline stay on the FP32 pipe, as BASELINE.json's north star prescribes.
+    _lib.check(L.pdsb_set_dft_variant(103))
+    for _ in range(2):
+        ll_tc = step_device()
+    barrier()
+    tc_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in tc_evs:
+        flush.zero_()
+        e0.record()
+        ll_tc = step_device()
+        e1.record()
+    barrier()
+    _lib.check(L.pdsb_set_dft_variant(0))
+    tc_ms = sum(e0.elapsed_time(e1) for e0, e1 in tc_evs)
+    t = torch.tensor([tc_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tc_ms = float(t[0])
+
     if rank == 0:
         sm, khz = ctypes.c_int(), ctypes.c_int()
         L.pdsb_device_info(ctypes.byref(sm), ctypes.byref(khz), None, None, None)
@@ -596,6 +618,12 @@ def main():
                                   "launch (profiles/r01_dft_ncu_c3_default.md, r01_dft_ncu.md); null where not captured",
                 "algorithmic_bytes": float(n) * n * nf * 4 + like.ds.nuv_unique * 16.0 * (1 + nf)},
         }
+        line["extras"] = {"tensor_core_variant": {
+            "what": "same step with the experimental opt-in DFT kernel on the warp-level tensor-core path (mma.sync "
+                    "m16n8k16, fp16 hi+lo split operands, 3 MMAs per product, fp32 accumulate; dft_mma.cu variant 103); "
+                    "NOT used for value / e2e",
+            "ms_per_step": tc_ms / args.steps, "value": pairs_step * args.steps / (tc_ms * 1e-3), "unit": UNIT,
+            "speedup_vs_default": total_ms / tc_ms, "lnlike": ll_tc, "lnlike_rel_diff_vs_default": abs(ll_tc - ll) / abs(ll)}}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(cfg)
         emit(line)
