@@ -89,5 +89,13 @@ size_t mma_operand_bytes(int ny, int nx, int nf);
 int launch_fold_half(const double *img_dev, unsigned char *B, double *scale_ws, int ny, int nx, int nf);
 int mma_auto_split(int64_t nuvh, int nf, int nx);
 int launch_dft_mma(DftParams p, const unsigned char *B, int ny, int nx);
+int launch_plane_scale(const double *img_dev, double *scale_ws, int ny, int nx, int nf);
+
+// experimental tcgen05 / TMEM variant (dft_tc5.cu), selected with pdsb_set_dft_variant(200)
+constexpr int DFT_VARIANT_TC5 = 200;
+size_t tc5_operand_bytes(int ny, int nx, int nf);
+int launch_fold_tc5(const double *img_dev, unsigned char *B, double *scale_ws, int ny, int nx, int nf);
+int tc5_auto_split(int64_t nuvh, int nf, int nx);
+int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx);
 
 }  // namespace pdsb

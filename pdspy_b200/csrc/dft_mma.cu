@@ -374,27 +374,32 @@ size_t mma_operand_bytes(int ny, int nx, int nf)
     return (size_t)nf * nkt * nchunk * MMA_CHUNK_BYTES;
 }
 
+// per-plane power-of-two scale factors: scale_ws = [pmax (as u64) | scale | unscale], nf doubles each
+int launch_plane_scale(const double *img_dev, double *scale_ws, int ny, int nx, int nf)
+{
+    Context &c = ctx();
+    unsigned long long *pmax = reinterpret_cast<unsigned long long *>(scale_ws);
+    PDSB_CUDA(cudaMemsetAsync(pmax, 0, (size_t)nf * sizeof(unsigned long long), c.stream));
+    LaunchScope ls("plane_absmax");
+    const int64_t npix = (int64_t)ny * nx;
+    int64_t nstrips = ((int64_t)c.sm_count * 2048 + nf - 1) / nf;
+    if (nstrips > npix) nstrips = npix;
+    plane_absmax_kernel<<<ceil_div(nstrips * nf, 256), 256, 0, c.stream>>>(img_dev, npix, nf, nstrips, pmax);
+    plane_scale_kernel<<<ceil_div(nf, 128), 128, 0, c.stream>>>(pmax, nf, scale_ws + nf, scale_ws + 2 * nf);
+    PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
+}
+
 // image (device fp64 [ny,nx,nf]) -> fp16 operand tiles + per-plane unscale factors (device double[nf])
 int launch_fold_half(const double *img_dev, unsigned char *B, double *scale_ws /* [3*nf] */, int ny, int nx, int nf)
 {
     Context &c = ctx();
     const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
     const int nkt = (npx + MMA_KT - 1) / MMA_KT, nchunk = (npy + DFT_RC - 1) / DFT_RC;
-    unsigned long long *pmax = reinterpret_cast<unsigned long long *>(scale_ws);
-    double *scale = scale_ws + nf, *unscale = scale_ws + 2 * nf;
-    PDSB_CUDA(cudaMemsetAsync(pmax, 0, (size_t)nf * sizeof(unsigned long long), c.stream));
-    {
-        LaunchScope ls("plane_absmax");
-        const int64_t npix = (int64_t)ny * nx;
-        int64_t nstrips = ((int64_t)c.sm_count * 2048 + nf - 1) / nf;
-        if (nstrips > npix) nstrips = npix;
-        plane_absmax_kernel<<<ceil_div(nstrips * nf, 256), 256, 0, c.stream>>>(img_dev, npix, nf, nstrips, pmax);
-        plane_scale_kernel<<<ceil_div(nf, 128), 128, 0, c.stream>>>(pmax, nf, scale, unscale);
-        PDSB_CUDA(cudaGetLastError());
-    }
+    PDSB_CHECK(launch_plane_scale(img_dev, scale_ws, ny, nx, nf));
     const int64_t total = (int64_t)nf * nkt * MMA_KT * nchunk * DFT_RC;
     LaunchScope ls("fold_half");
-    fold_half_kernel<<<ceil_div(total, 256), 256, 0, c.stream>>>(img_dev, B, scale, ny, nx, nf, npx, npy, nkt, nchunk);
+    fold_half_kernel<<<ceil_div(total, 256), 256, 0, c.stream>>>(img_dev, B, scale_ws + nf, ny, nx, nf, npx, npy, nkt, nchunk);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }

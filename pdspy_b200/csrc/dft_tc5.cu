@@ -1,0 +1,414 @@
+// EXPERIMENTAL opt-in variant of the direct Fourier sampling on the 5th-generation tensor cores
+// (pdsb_set_dft_variant(200)): tcgen05.mma with TMEM accumulators, operands staged by bulk TMA.
+//
+// Same algorithm as dft.cu / dft_mma.cu: separable phases, mirror-folded real image, fp16 hi+lo split of
+// both operands (3 MMAs per product), per-plane power-of-two scaling, fp64-seeded phases, fp32 row-phase
+// rotation in the epilogue, fp64 partial sums in the same [split][plane][uv] layout.
+//
+//   CTA = 128 threads = 128 uv points (UMMA M = 128).  Thread r owns uv row r: it writes row r of the
+//   four A operand tiles (cos/sin x hi/lo, [128 x 32] fp16, canonical K-major no-swizzle core-matrix
+//   layout) once per K tile, and runs the row-phase epilogue on TMEM lane r.
+//   B operand chunks ([2 types][hi|lo][N = 128 rows = 64 row pairs x 2 comps][K = 32]) are written by the
+//   fold kernel directly in the canonical UMMA layout, so one 32 KB 1-D bulk TMA copy per chunk feeds
+//   12 MMAs (2 types x 2 k-steps x 3 split products) of shape 128 x 128 x 16.
+//   TMEM: 512 columns = 2 buffers x 2 types x 128 fp32 columns; the MMAs of chunk i run while all four
+//   warps do the epilogue of chunk i-1 (tcgen05.ld 32x32b: lane = uv point).
+//
+// NOT the default (see dft_mma.cu header); reported by bench.py under `extras`.
+#include "dft.cuh"
+#include <cuda_fp16.h>
+#include <algorithm>
+
+namespace pdsb {
+
+constexpr int T5_KT = 32;                       // column pairs per K tile (two UMMA k-steps of 16)
+constexpr int T5_RC = 64;                       // row pairs per chunk -> N = 128 per trig type
+constexpr int T5_N = 2 * T5_RC;                 // UMMA N
+constexpr int T5_M = 128;                       // UMMA M = uv points per CTA
+constexpr int T5_KCHUNK_BYTES = (T5_N / 8) * 128;        // 2048: one 8-wide K slab of a [128 x K] tile
+constexpr int T5_TILE_BYTES = (T5_KT / 8) * T5_KCHUNK_BYTES;   // 8192: [128 x 32] fp16
+constexpr int T5_CHUNK_BYTES = 4 * T5_TILE_BYTES;        // B chunk: [type][hi|lo]
+constexpr int T5_A_BYTES = 4 * T5_TILE_BYTES;            // A: [cos hi, cos lo, sin hi, sin lo]
+constexpr int T5_NSTAGE = 3;
+constexpr uint32_t T5_IDESC = (1u << 4) | ((uint32_t)(T5_N >> 3) << 17) | ((uint32_t)(T5_M >> 4) << 24);
+//                            D = f32      N                              M        (A, B = f16, K-major)
+
+// canonical K-major, no-swizzle layout of a [128 rows x 32 k] fp16 tile: 8x8 core matrices of 128
+// contiguous bytes; row groups 128 B apart (SBO), 8-wide K slabs 2048 B apart (LBO)
+__host__ __device__ __forceinline__ int t5_off(int r, int k)
+{
+    return (k >> 3) * T5_KCHUNK_BYTES + (r >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
+}
+
+__device__ __forceinline__ uint32_t t5_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t t5_desc(uint32_t saddr)
+{
+    const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (((uint32_t)(T5_KCHUNK_BYTES >> 4) & 0x3fffu) << 16);   // start, LBO
+    const uint32_t hi = ((uint32_t)(128 >> 4) & 0x3fffu) | (1u << 14);                                     // SBO, version 1
+    return ((uint64_t)hi << 32) | lo;                                                                      // layout: none
+}
+__device__ __forceinline__ void t5_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t5_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void t5_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t5_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool t5_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(t5_smem(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void t5_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!t5_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void t5_tma(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     t5_smem(dst)),
+                 "l"(src), "r"(bytes), "r"(t5_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void t5_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(T5_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void t5_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t5_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void t5_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void t5_split(float x, __half &hi, __half &lo)
+{
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+// ---- fold into the canonical UMMA B layout ----
+// B[plane][ktile][chunk][type][hi|lo][t5_off(r, k)], r = s_l*2 + c (row pair s_l of the chunk, component
+// c of the type: SS,SD | DS,DD), k = column pair within the K tile.
+__global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict__ img, unsigned char *__restrict__ B,
+                                                       const double *__restrict__ scale, int ny, int nx, int nf,
+                                                       int npx, int npy, int nkt, int nchunk)
+{
+    const int64_t tw = (int64_t)nkt * T5_KT, sw = (int64_t)nchunk * T5_RC;
+    const int64_t total = (int64_t)nf * tw * sw;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int p = (int)(idx % nf);
+    const int64_t rr = idx / nf;
+    const int t = (int)(rr % tw), s = (int)(rr / tw);
+    double pp = 0, mp = 0, pm = 0, mm = 0;
+    if (t < npx && s < npy) {
+        int c_hi, c_lo, j_lo, j_hi;
+        if (nx % 2 == 0) { c_hi = nx / 2 + t; c_lo = nx / 2 - 1 - t; }
+        else { c_hi = (nx - 1) / 2 + t; c_lo = (nx - 1) / 2 - t; }
+        if (ny % 2 == 0) { j_lo = ny / 2 - 1 - s; j_hi = ny / 2 + s; }
+        else { j_lo = (ny - 1) / 2 - s; j_hi = (ny - 1) / 2 + s; }
+        const bool selfc = (c_hi == c_lo), selfr = (j_lo == j_hi);
+        pp = img[((int64_t)j_lo * nx + c_hi) * nf + p];
+        if (!selfc) mp = img[((int64_t)j_lo * nx + c_lo) * nf + p];
+        if (!selfr) pm = img[((int64_t)j_hi * nx + c_hi) * nf + p];
+        if (!selfc && !selfr) mm = img[((int64_t)j_hi * nx + c_lo) * nf + p];
+    }
+    const double Sp = pp + mp, Dp = pp - mp, Sm = pm + mm, Dm = pm - mm;
+    const double comp[4] = {Sp + Sm, Sp - Sm, Dp + Dm, Dp - Dm};
+    const double sc = scale[p];
+    const int kt = t / T5_KT, k = t % T5_KT;
+    const int chunk = s / T5_RC, s_l = s % T5_RC;
+    unsigned char *base = B + (((int64_t)p * nkt + kt) * nchunk + chunk) * (int64_t)T5_CHUNK_BYTES;
+#pragma unroll
+    for (int cidx = 0; cidx < 4; cidx++) {
+        const int type = cidx >> 1, c = cidx & 1;
+        const int off = t5_off(s_l * 2 + c, k);
+        const double x = comp[cidx] * sc;
+        const __half hi = __double2half(x);
+        const __half lo = __double2half(x - (double)__half2float(hi));
+        *reinterpret_cast<__half *>(base + (type * 2 + 0) * T5_TILE_BYTES + off) = hi;
+        *reinterpret_cast<__half *>(base + (type * 2 + 1) * T5_TILE_BYTES + off) = lo;
+    }
+}
+
+// ---- the kernel ----
+__global__ void __launch_bounds__(T5_M, 1) dft_tc5_kernel(const DftParams P, const unsigned char *__restrict__ Bg, int nkt,
+                                                          int pg)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *As = smem;                                   // 4 x 8 KB
+    unsigned char *Bs = smem + T5_A_BYTES;                      // T5_NSTAGE x 32 KB
+    __shared__ __align__(8) uint64_t full_bar[T5_NSTAGE];
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int plane0 = blockIdx.z * pg, sp = blockIdx.y;
+    const int npl = (P.nf - plane0) < pg ? (P.nf - plane0) : pg;
+    const int kt0 = (int)(((int64_t)sp * nkt) / P.nsplit), kt1 = (int)(((int64_t)(sp + 1) * nkt) / P.nsplit);
+    const int nkl = kt1 - kt0;
+    const int per_k = npl * P.nchunk;
+    const int nit = nkl * per_k;
+    auto chunk_src = [&](int it) -> const unsigned char * {
+        const int kl = it / per_k, rem = it - kl * per_k;
+        const int pl = rem / P.nchunk, ch = rem - pl * P.nchunk;
+        return Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)P.nchunk + ch) * T5_CHUNK_BYTES;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < T5_NSTAGE; s++) t5_mbar_init(&full_bar[s], 1);
+        t5_mbar_init(&mma_bar[0], 1);
+        t5_mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {           // one warp allocates all 512 TMEM columns (this CTA is alone on its SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t5_smem(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        for (int s = 0; s < T5_NSTAGE; s++)
+            if (s < nit) {
+                t5_expect_tx(&full_bar[s], T5_CHUNK_BYTES);
+                t5_tma(Bs + (size_t)s * T5_CHUNK_BYTES, chunk_src(s), T5_CHUNK_BYTES, &full_bar[s]);
+            }
+    }
+
+    // this thread's uv point
+    const int64_t kuv = (int64_t)blockIdx.x * T5_M + tid;
+    const bool valid = kuv < P.nuvh;
+    const double fu = valid ? P.u[kuv] * P.dxy : 0.0, fv = valid ? P.v[kuv] * P.dxy : 0.0;
+    float D1r, D1i;                                  // row-phase step of one row pair
+    {
+        double s, c;
+        sincospi(2.0 * (fv - rint(fv)), &s, &c);
+        D1r = (float)c;
+        D1i = (float)s;
+    }
+    double Vr = 0.0, Vi = 0.0;                       // fp64 sums of the current (K tile, plane) pass
+
+    // epilogue of chunk `e`: TMEM lane tid -> row phases -> fp64 sums (-> partial sums at the end of a pass)
+    auto epilogue = [&](int e) {
+        const int b = e & 1;
+        const int kl = e / per_k, rem = e - kl * per_k;
+        const int pl = rem / P.nchunk, ch = rem - pl * P.nchunk;
+        t5_wait(&mma_bar[b], (uint32_t)((e >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 2 * T5_N);
+        float Er = 1.f, Ei = 0.f, vre = 0.f, vim = 0.f;
+#pragma unroll 1
+        for (int grp = 0; grp < T5_RC / 16; grp++) {
+            if ((grp & 1) == 0) {                    // fp64-reduced re-seed every 32 row pairs
+                double b0 = fv * ((double)(ch * T5_RC + grp * 16) + P.hy);
+                b0 -= rint(b0);
+                sincospif((float)(2.0 * b0), &Ei, &Er);
+            }
+            uint32_t cv[32], sv[32];
+            t5_ld32(tbase + (uint32_t)(grp * 32), cv);                 // cos-type tile: (SS, SD) of 16 row pairs
+            t5_ld32(tbase + (uint32_t)(T5_N + grp * 32), sv);          // sin-type tile: (DS, DD)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float SS = __uint_as_float(cv[2 * i]), SD = __uint_as_float(cv[2 * i + 1]);
+                const float DS = __uint_as_float(sv[2 * i]), DD = __uint_as_float(sv[2 * i + 1]);
+                vre = fmaf(Er, SS, vre);
+                vre = fmaf(-Ei, DD, vre);
+                vim = fmaf(Er, DS, vim);
+                vim = fmaf(Ei, SD, vim);
+                const float nr = Er * D1r - Ei * D1i;
+                Ei = Er * D1i + Ei * D1r;
+                Er = nr;
+            }
+        }
+        Vr += (double)vre;
+        Vi += (double)vim;
+        if (ch == P.nchunk - 1) {                    // end of this (K tile, plane) pass
+            if (valid) {
+                double2 *dst = P.part + ((size_t)sp * P.nf + (plane0 + pl)) * (size_t)P.nuvh + kuv;
+                if (kl == 0) *dst = make_double2(Vr, Vi);
+                else {
+                    const double2 o = *dst;
+                    *dst = make_double2(o.x + Vr, o.y + Vi);
+                }
+            }
+            Vr = 0.0;
+            Vi = 0.0;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    int it = 0;
+    for (int kl = 0; kl < nkl; kl++) {
+        // the MMAs of every earlier chunk read the A tiles: finish the pending epilogue (it waits for them)
+        if (it > 0) {
+            epilogue(it - 1);
+            __syncthreads();
+            if (tid == 0 && (it - 1) + T5_NSTAGE < nit) {
+                const int st = (it - 1) % T5_NSTAGE;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                t5_expect_tx(&full_bar[st], T5_CHUNK_BYTES);
+                t5_tma(Bs + (size_t)st * T5_CHUNK_BYTES, chunk_src(it - 1 + T5_NSTAGE), T5_CHUNK_BYTES, &full_bar[st]);
+            }
+        }
+        // ---- A tiles of this K tile: row tid = trig of this uv point at the 32 columns, fp16 hi + lo ----
+        {
+            double a0 = fu * ((double)((kt0 + kl) * T5_KT) + P.hx), a1 = fu;
+            a0 -= rint(a0);
+            a1 -= rint(a1);
+            float sf, cf;
+            sincospif((float)(2.0 * a0), &sf, &cf);
+            double cr = cf, ci = sf;
+            sincospif((float)(2.0 * a1), &sf, &cf);
+            const double rc = cf, rs = sf;
+#pragma unroll
+            for (int kc = 0; kc < T5_KT / 8; kc++) {
+                __align__(16) __half ch[8], cl[8], sh[8], sl[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    t5_split((float)cr, ch[e], cl[e]);
+                    t5_split((float)ci, sh[e], sl[e]);
+                    const double nr = cr * rc - ci * rs;
+                    ci = cr * rs + ci * rc;
+                    cr = nr;
+                }
+                const int off = t5_off(tid, kc * 8);
+                *reinterpret_cast<uint4 *>(As + 0 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(ch);
+                *reinterpret_cast<uint4 *>(As + 1 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(cl);
+                *reinterpret_cast<uint4 *>(As + 2 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sh);
+                *reinterpret_cast<uint4 *>(As + 3 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sl);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
+        __syncthreads();
+
+        const int it_first = it;
+        for (int r = 0; r < per_k; r++, it++) {
+            const int st = it % T5_NSTAGE;
+            if (tid == 0) {
+                t5_wait(&full_bar[st], (uint32_t)((it / T5_NSTAGE) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_s = t5_smem(As), b_s = t5_smem(Bs + (size_t)st * T5_CHUNK_BYTES);
+                const uint32_t dcol = tmem_base + (uint32_t)((it & 1) * 2 * T5_N);
+#pragma unroll
+                for (int ty = 0; ty < 2; ty++) {
+                    const uint32_t d = dcol + (uint32_t)(ty * T5_N);
+                    const uint32_t ahi = a_s + (ty * 2 + 0) * T5_TILE_BYTES, alo = a_s + (ty * 2 + 1) * T5_TILE_BYTES;
+                    const uint32_t bhi = b_s + (ty * 2 + 0) * T5_TILE_BYTES, blo = b_s + (ty * 2 + 1) * T5_TILE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ks++) {
+                        const uint32_t ko = ks * 2 * T5_KCHUNK_BYTES;        // 16 columns = two 8-wide K slabs
+                        t5_mma(d, t5_desc(ahi + ko), t5_desc(bhi + ko), ks ? 1u : 0u);
+                        t5_mma(d, t5_desc(ahi + ko), t5_desc(blo + ko), 1u);
+                        t5_mma(d, t5_desc(alo + ko), t5_desc(bhi + ko), 1u);
+                    }
+                }
+                t5_commit(&mma_bar[it & 1]);
+            }
+            // everyone: epilogue of the previous chunk while the tensor core works on this one
+            if (it > it_first) {
+                epilogue(it - 1);
+                __syncthreads();
+                if (tid == 0 && (it - 1) + T5_NSTAGE < nit) {
+                    const int stp = (it - 1) % T5_NSTAGE;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    t5_expect_tx(&full_bar[stp], T5_CHUNK_BYTES);
+                    t5_tma(Bs + (size_t)stp * T5_CHUNK_BYTES, chunk_src(it - 1 + T5_NSTAGE), T5_CHUNK_BYTES, &full_bar[stp]);
+                }
+            }
+        }
+    }
+    if (it > 0) epilogue(it - 1);
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// ---- host side ----
+size_t tc5_operand_bytes(int ny, int nx, int nf)
+{
+    const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
+    const int nkt = (npx + T5_KT - 1) / T5_KT, nchunk = (npy + T5_RC - 1) / T5_RC;
+    return (size_t)nf * nkt * nchunk * T5_CHUNK_BYTES;
+}
+
+static int tc5_pg(int nf) { return nf < 8 ? nf : 8; }
+
+int tc5_auto_split(int64_t nuvh, int nf, int nx)
+{
+    Context &c = ctx();
+    const int nkt = ((nx + 1) / 2 + T5_KT - 1) / T5_KT;
+    if (c.dft_split > 0) return c.dft_split < nkt ? c.dft_split : nkt;
+    const int64_t uvtiles = (nuvh + T5_M - 1) / T5_M;
+    const int pgroups = (nf + tc5_pg(nf) - 1) / tc5_pg(nf);
+    const int64_t capacity = (int64_t)c.sm_count, base = std::max<int64_t>(1, uvtiles * pgroups);
+    const int64_t ns = (20 * capacity + base - 1) / base;
+    return (int)(ns < 1 ? 1 : (ns > nkt ? nkt : ns));
+}
+
+// scale_ws: [pmax | scale | unscale] as in dft_mma.cu (plane_absmax / plane_scale kernels live there)
+int launch_plane_scale(const double *img_dev, double *scale_ws, int ny, int nx, int nf);
+
+int launch_fold_tc5(const double *img_dev, unsigned char *B, double *scale_ws, int ny, int nx, int nf)
+{
+    Context &c = ctx();
+    const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
+    const int nkt = (npx + T5_KT - 1) / T5_KT, nchunk = (npy + T5_RC - 1) / T5_RC;
+    PDSB_CHECK(launch_plane_scale(img_dev, scale_ws, ny, nx, nf));
+    const int64_t total = (int64_t)nf * nkt * T5_KT * nchunk * T5_RC;
+    LaunchScope ls("fold_tc5");
+    fold_tc5_kernel<<<ceil_div(total, 256), 256, 0, c.stream>>>(img_dev, B, scale_ws + nf, ny, nx, nf, npx, npy, nkt, nchunk);
+    PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
+}
+
+int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
+{
+    Context &c = ctx();
+    const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
+    const int nkt = (npx + T5_KT - 1) / T5_KT;
+    p.nchunk = (npy + T5_RC - 1) / T5_RC;
+    PDSB_REQUIRE(p.nsplit >= 1 && p.nsplit <= nkt, "tc5 split");
+    constexpr size_t smem_bytes = (size_t)T5_A_BYTES + (size_t)T5_NSTAGE * T5_CHUNK_BYTES + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        attr_set = true;
+    }
+    const int64_t uvtiles = (p.nuvh + T5_M - 1) / T5_M;
+    if (uvtiles <= 0) return PDSB_OK;
+    const int pg = tc5_pg(p.nf);
+    dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)((p.nf + pg - 1) / pg));
+    LaunchScope ls("dft_tc5_tcgen05");
+    dft_tc5_kernel<<<grid, T5_M, smem_bytes, c.stream>>>(p, B, nkt, pg);
+    PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
+}
+
+}  // namespace pdsb

@@ -260,12 +260,14 @@ static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf
     const double *img_dev = nullptr;
     PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
     if (c.dft_variant >= DFT_VARIANT_MMA) {
-        // experimental: fp16-split operands on the warp-level tensor-core path (dft_mma.cu)
+        // experimental: fp16-split operands on the tensor cores (dft_mma.cu: mma.sync; dft_tc5.cu: tcgen05)
+        const bool tc5 = c.dft_variant >= DFT_VARIANT_TC5;
         DftGeom g = make_geom(ny, nx, nf, 32, dxy);
-        PDSB_CHECK(c.folded.ensure(mma_operand_bytes(ny, nx, nf)));
+        PDSB_CHECK(c.folded.ensure(tc5 ? tc5_operand_bytes(ny, nx, nf) : mma_operand_bytes(ny, nx, nf)));
         PDSB_CHECK(c.mma_ws.ensure((size_t)3 * nf * sizeof(double)));
-        PDSB_CHECK(launch_fold_half(img_dev, c.folded.as<unsigned char>(), c.mma_ws.as<double>(), ny, nx, nf));
-        const int nsplit = mma_auto_split(ds->nuvh, nf, nx);
+        if (tc5) PDSB_CHECK(launch_fold_tc5(img_dev, c.folded.as<unsigned char>(), c.mma_ws.as<double>(), ny, nx, nf));
+        else PDSB_CHECK(launch_fold_half(img_dev, c.folded.as<unsigned char>(), c.mma_ws.as<double>(), ny, nx, nf));
+        const int nsplit = tc5 ? tc5_auto_split(ds->nuvh, nf, nx) : mma_auto_split(ds->nuvh, nf, nx);
         PDSB_CHECK(c.partial.ensure((size_t)nsplit * nf * ds->nuvh * sizeof(double2)));
         DftParams p;
         p.F = nullptr;
@@ -280,7 +282,8 @@ static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf
         p.hx = g.hx2 ? 0.5 : 0.0;
         p.hy = g.hy2 ? 0.5 : 0.0;
         p.part = c.partial.as<double2>();
-        PDSB_CHECK(launch_dft_mma(p, c.folded.as<unsigned char>(), ny, nx));
+        if (tc5) PDSB_CHECK(launch_dft_tc5(p, c.folded.as<unsigned char>(), ny, nx));
+        else PDSB_CHECK(launch_dft_mma(p, c.folded.as<unsigned char>(), ny, nx));
         run->g = g;
         run->nsplit = nsplit;
         run->plane_unscale = c.mma_ws.as<double>() + 2 * nf;
