@@ -5,14 +5,19 @@
 // both operands (3 MMAs per product), per-plane power-of-two scaling, fp64-seeded phases, fp32 row-phase
 // rotation in the epilogue, fp64 partial sums in the same [split][plane][uv] layout.
 //
-//   CTA = 128 threads = 128 uv points (UMMA M = 128).  Thread r owns uv row r: it writes row r of the
-//   four A operand tiles (cos/sin x hi/lo, [128 x 32] fp16, canonical K-major no-swizzle core-matrix
-//   layout) once per K tile, and runs the row-phase epilogue on TMEM lane r.
-//   B operand chunks ([2 types][hi|lo][N = 128 rows = 64 row pairs x 2 comps][K = 32]) are written by the
+//   CTA = 128 uv points (UMMA M = 128), 10 warps with fixed roles:
+//     warps 0-7  epilogue: thread (w & 3) * 32 + lane owns uv row r (TMEM lane r); warps 0-3 take row pairs
+//                0..31 of every chunk, warps 4-7 row pairs 32..63.  They also write row r of the four A
+//                operand tiles (cos/sin x hi/lo, [128 x 32] fp16, canonical K-major no-swizzle core-matrix
+//                layout), double buffered over K tiles.
+//     warp 8     one thread issues the bulk TMA copies of the B chunks (3-stage ring)
+//     warp 9     one thread issues the tcgen05.mma's and commits them to the mbarriers
+//   B operand chunks ([2 types][hi|lo][N = 128 rows = 2 comps x 64 row pairs][K = 32]) are written by the
 //   fold kernel directly in the canonical UMMA layout, so one 32 KB 1-D bulk TMA copy per chunk feeds
 //   12 MMAs (2 types x 2 k-steps x 3 split products) of shape 128 x 128 x 16.
-//   TMEM: 512 columns = 2 buffers x 2 types x 128 fp32 columns; the MMAs of chunk i run while all four
-//   warps do the epilogue of chunk i-1 (tcgen05.ld 32x32b: lane = uv point).
+//   TMEM: 512 columns = 2 buffers x 2 types x 128 fp32 columns; everything is handed over through
+//   mbarriers (stage full/empty, TMEM full/empty, A tile full), no CTA-wide barrier in the steady state.
+//   Epilogue arithmetic is packed fp32x2 (FFMA2) over adjacent row pairs, four independent phase chains.
 //
 // NOT the default (see dft_mma.cu header); reported by bench.py under `extras`.
 #include "dft.cuh"
@@ -104,6 +109,50 @@ __device__ __forceinline__ void t5_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void t5_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void t5_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t5_smem(bar)) : "memory");
+}
+typedef unsigned long long t5_u64;
+__device__ __forceinline__ t5_u64 t5_fma2(t5_u64 a, t5_u64 b, t5_u64 c)
+{
+    t5_u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ t5_u64 t5_mul2(t5_u64 a, t5_u64 b)
+{
+    t5_u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ t5_u64 t5_pack(float lo, float hi)
+{
+    t5_u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ t5_u64 t5_packu(uint32_t lo, uint32_t hi)
+{
+    t5_u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+__device__ __forceinline__ float t5_sum2(t5_u64 a)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+    return lo + hi;
+}
 __device__ __forceinline__ void t5_split(float x, __half &hi, __half &lo)
 {
     hi = __float2half_rn(x);
@@ -111,8 +160,8 @@ __device__ __forceinline__ void t5_split(float x, __half &hi, __half &lo)
 }
 
 // ---- fold into the canonical UMMA B layout ----
-// B[plane][ktile][chunk][type][hi|lo][t5_off(r, k)], r = s_l*2 + c (row pair s_l of the chunk, component
-// c of the type: SS,SD | DS,DD), k = column pair within the K tile.
+// B[plane][ktile][chunk][type][hi|lo][t5_off(r, k)], r = c*64 + s_l (component c of the type: SS,SD |
+// DS,DD; row pair s_l of the chunk), k = column pair within the K tile.
 __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict__ img, unsigned char *__restrict__ B,
                                                        const double *__restrict__ scale, int ny, int nx, int nf,
                                                        int npx, int npy, int nkt, int nchunk)
@@ -146,7 +195,7 @@ __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict_
 #pragma unroll
     for (int cidx = 0; cidx < 4; cidx++) {
         const int type = cidx >> 1, c = cidx & 1;
-        const int off = t5_off(s_l * 2 + c, k);
+        const int off = t5_off(c * T5_RC + s_l, k);
         const double x = comp[cidx] * sc;
         const __half hi = __double2half(x);
         const __half lo = __double2half(x - (double)__half2float(hi));
@@ -156,36 +205,43 @@ __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict_
 }
 
 // ---- the kernel ----
-__global__ void __launch_bounds__(T5_M, 1) dft_tc5_kernel(const DftParams P, const unsigned char *__restrict__ Bg, int nkt,
-                                                          int pg)
+constexpr int T5_EPI_THREADS = 256;             // warps 0-7
+constexpr int T5_THREADS = T5_EPI_THREADS + 64; // + TMA warp + MMA warp
+__global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams P, const unsigned char *__restrict__ Bg,
+                                                                int nkt, int pg)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *As = smem;                                   // 4 x 8 KB
-    unsigned char *Bs = smem + T5_A_BYTES;                      // T5_NSTAGE x 32 KB
-    __shared__ __align__(8) uint64_t full_bar[T5_NSTAGE];
-    __shared__ __align__(8) uint64_t mma_bar[2];
+    unsigned char *As = smem;                                   // 2 buffers x (4 x 8 KB)
+    unsigned char *Bs = smem + 2 * T5_A_BYTES;                  // T5_NSTAGE x 32 KB
+    __shared__ __align__(8) uint64_t full_bar[T5_NSTAGE];       // TMA landed           (producer -> MMA)
+    __shared__ __align__(8) uint64_t empty_bar[T5_NSTAGE];      // MMAs read the stage  (MMA commit -> producer)
+    __shared__ __align__(8) uint64_t tmem_full[2];              // accumulators ready   (MMA commit -> epilogue)
+    __shared__ __align__(8) uint64_t tmem_empty[2];             // accumulators read    (epilogue -> MMA)
+    __shared__ __align__(8) uint64_t a_full[2];                 // A tiles written      (epilogue -> MMA)
     __shared__ uint32_t tmem_base_s;
+    __shared__ double2 vx[T5_M];                 // pass-end exchange between the two halves of a uv point
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int plane0 = blockIdx.z * pg, sp = blockIdx.y;
     const int npl = (P.nf - plane0) < pg ? (P.nf - plane0) : pg;
     const int kt0 = (int)(((int64_t)sp * nkt) / P.nsplit), kt1 = (int)(((int64_t)(sp + 1) * nkt) / P.nsplit);
     const int nkl = kt1 - kt0;
     const int per_k = npl * P.nchunk;
     const int nit = nkl * per_k;
-    auto chunk_src = [&](int it) -> const unsigned char * {
-        const int kl = it / per_k, rem = it - kl * per_k;
-        const int pl = rem / P.nchunk, ch = rem - pl * P.nchunk;
-        return Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)P.nchunk + ch) * T5_CHUNK_BYTES;
-    };
 
     if (tid == 0) {
-        for (int s = 0; s < T5_NSTAGE; s++) t5_mbar_init(&full_bar[s], 1);
-        t5_mbar_init(&mma_bar[0], 1);
-        t5_mbar_init(&mma_bar[1], 1);
+        for (int s = 0; s < T5_NSTAGE; s++) {
+            t5_mbar_init(&full_bar[s], 1);
+            t5_mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            t5_mbar_init(&tmem_full[b], 1);
+            t5_mbar_init(&tmem_empty[b], T5_EPI_THREADS);
+            t5_mbar_init(&a_full[b], T5_EPI_THREADS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {           // one warp allocates all 512 TMEM columns (this CTA is alone on its SM)
+    if (warp == 9) {           // one warp allocates all 512 TMEM columns (this CTA is alone on its SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t5_smem(&tmem_base_s)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -193,93 +249,89 @@ __global__ void __launch_bounds__(T5_M, 1) dft_tc5_kernel(const DftParams P, con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    if (tid == 0) {
-        for (int s = 0; s < T5_NSTAGE; s++)
-            if (s < nit) {
-                t5_expect_tx(&full_bar[s], T5_CHUNK_BYTES);
-                t5_tma(Bs + (size_t)s * T5_CHUNK_BYTES, chunk_src(s), T5_CHUNK_BYTES, &full_bar[s]);
-            }
-    }
 
-    // this thread's uv point
-    const int64_t kuv = (int64_t)blockIdx.x * T5_M + tid;
-    const bool valid = kuv < P.nuvh;
-    const double fu = valid ? P.u[kuv] * P.dxy : 0.0, fv = valid ? P.v[kuv] * P.dxy : 0.0;
-    float D1r, D1i;                                  // row-phase step of one row pair
-    {
-        double s, c;
-        sincospi(2.0 * (fv - rint(fv)), &s, &c);
-        D1r = (float)c;
-        D1i = (float)s;
-    }
-    double Vr = 0.0, Vi = 0.0;                       // fp64 sums of the current (K tile, plane) pass
-
-    // epilogue of chunk `e`: TMEM lane tid -> row phases -> fp64 sums (-> partial sums at the end of a pass)
-    auto epilogue = [&](int e) {
-        const int b = e & 1;
-        const int kl = e / per_k, rem = e - kl * per_k;
-        const int pl = rem / P.nchunk, ch = rem - pl * P.nchunk;
-        t5_wait(&mma_bar[b], (uint32_t)((e >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 2 * T5_N);
-        float Er = 1.f, Ei = 0.f, vre = 0.f, vim = 0.f;
-#pragma unroll 1
-        for (int grp = 0; grp < T5_RC / 16; grp++) {
-            if ((grp & 1) == 0) {                    // fp64-reduced re-seed every 32 row pairs
-                double b0 = fv * ((double)(ch * T5_RC + grp * 16) + P.hy);
-                b0 -= rint(b0);
-                sincospif((float)(2.0 * b0), &Ei, &Er);
-            }
-            uint32_t cv[32], sv[32];
-            t5_ld32(tbase + (uint32_t)(grp * 32), cv);                 // cos-type tile: (SS, SD) of 16 row pairs
-            t5_ld32(tbase + (uint32_t)(T5_N + grp * 32), sv);          // sin-type tile: (DS, DD)
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const float SS = __uint_as_float(cv[2 * i]), SD = __uint_as_float(cv[2 * i + 1]);
-                const float DS = __uint_as_float(sv[2 * i]), DD = __uint_as_float(sv[2 * i + 1]);
-                vre = fmaf(Er, SS, vre);
-                vre = fmaf(-Ei, DD, vre);
-                vim = fmaf(Er, DS, vim);
-                vim = fmaf(Ei, SD, vim);
-                const float nr = Er * D1r - Ei * D1i;
-                Ei = Er * D1i + Ei * D1r;
-                Er = nr;
-            }
-        }
-        Vr += (double)vre;
-        Vi += (double)vim;
-        if (ch == P.nchunk - 1) {                    // end of this (K tile, plane) pass
-            if (valid) {
-                double2 *dst = P.part + ((size_t)sp * P.nf + (plane0 + pl)) * (size_t)P.nuvh + kuv;
-                if (kl == 0) *dst = make_double2(Vr, Vi);
-                else {
-                    const double2 o = *dst;
-                    *dst = make_double2(o.x + Vr, o.y + Vi);
+    if (warp == 8) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int kl = 0, pl = 0, ch = 0;
+            for (int it = 0; it < nit; it++) {
+                const int st = it % T5_NSTAGE;
+                if (it >= T5_NSTAGE) t5_wait(&empty_bar[st], (uint32_t)((it / T5_NSTAGE - 1) & 1));
+                const unsigned char *src =
+                    Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)P.nchunk + ch) * T5_CHUNK_BYTES;
+                t5_expect_tx(&full_bar[st], T5_CHUNK_BYTES);
+                t5_tma(Bs + (size_t)st * T5_CHUNK_BYTES, src, T5_CHUNK_BYTES, &full_bar[st]);
+                if (++ch == P.nchunk) {
+                    ch = 0;
+                    if (++pl == npl) {
+                        pl = 0;
+                        kl++;
+                    }
                 }
             }
-            Vr = 0.0;
-            Vi = 0.0;
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    };
-
-    int it = 0;
-    for (int kl = 0; kl < nkl; kl++) {
-        // the MMAs of every earlier chunk read the A tiles: finish the pending epilogue (it waits for them)
-        if (it > 0) {
-            epilogue(it - 1);
-            __syncthreads();
-            if (tid == 0 && (it - 1) + T5_NSTAGE < nit) {
-                const int st = (it - 1) % T5_NSTAGE;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                t5_expect_tx(&full_bar[st], T5_CHUNK_BYTES);
-                t5_tma(Bs + (size_t)st * T5_CHUNK_BYTES, chunk_src(it - 1 + T5_NSTAGE), T5_CHUNK_BYTES, &full_bar[st]);
+    } else if (warp == 9) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int it = 0;
+            for (int kl = 0; kl < nkl; kl++) {
+                t5_wait(&a_full[kl & 1], (uint32_t)((kl >> 1) & 1));
+                const uint32_t a_s = t5_smem(As + (size_t)(kl & 1) * T5_A_BYTES);
+                for (int r = 0; r < per_k; r++, it++) {
+                    const int st = it % T5_NSTAGE, b = it & 1;
+                    t5_wait(&full_bar[st], (uint32_t)((it / T5_NSTAGE) & 1));
+                    if (it >= 2) t5_wait(&tmem_empty[b], (uint32_t)(((it >> 1) - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t b_s = t5_smem(Bs + (size_t)st * T5_CHUNK_BYTES);
+                    const uint32_t dcol = tmem_base + (uint32_t)(b * 2 * T5_N);
+#pragma unroll
+                    for (int ty = 0; ty < 2; ty++) {
+                        const uint32_t d = dcol + (uint32_t)(ty * T5_N);
+                        const uint32_t ahi = a_s + (ty * 2 + 0) * T5_TILE_BYTES, alo = a_s + (ty * 2 + 1) * T5_TILE_BYTES;
+                        const uint32_t bhi = b_s + (ty * 2 + 0) * T5_TILE_BYTES, blo = b_s + (ty * 2 + 1) * T5_TILE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < 2; ks++) {
+                            const uint32_t ko = ks * 2 * T5_KCHUNK_BYTES;        // 16 columns = two 8-wide K slabs
+                            t5_mma(d, t5_desc(ahi + ko), t5_desc(bhi + ko), ks ? 1u : 0u);
+                            t5_mma(d, t5_desc(ahi + ko), t5_desc(blo + ko), 1u);
+                            t5_mma(d, t5_desc(alo + ko), t5_desc(bhi + ko), 1u);
+                        }
+                    }
+                    t5_commit(&empty_bar[st]);       // stage (and, at the end of a K tile, the A buffer) consumed
+                    t5_commit(&tmem_full[b]);
+                }
             }
         }
-        // ---- A tiles of this K tile: row tid = trig of this uv point at the 32 columns, fp16 hi + lo ----
+    } else {
+        // ================= epilogue warps =================
+        const int row = tid & (T5_M - 1), half_id = tid >> 7;      // uv row (TMEM lane), which half of the work
+        const int64_t kuv = (int64_t)blockIdx.x * T5_M + row;
+        const bool valid = kuv < P.nuvh;
+        const double fu = valid ? P.u[kuv] * P.dxy : 0.0, fv = valid ? P.v[kuv] * P.dxy : 0.0;
+        float D1r, D1i;                                  // row-phase step of one row pair
+        t5_u64 D2r, D2i, D2n, D8r, D8i, D8n;             // packed (x, x): steps of two and of eight row pairs
         {
-            double a0 = fu * ((double)((kt0 + kl) * T5_KT) + P.hx), a1 = fu;
+            double s, c;
+            sincospi(2.0 * (fv - rint(fv)), &s, &c);
+            D1r = (float)c;
+            D1i = (float)s;
+            double a = 2.0 * fv;
+            sincospi(2.0 * (a - rint(a)), &s, &c);
+            D2r = t5_pack((float)c, (float)c);
+            D2i = t5_pack((float)s, (float)s);
+            D2n = t5_pack(-(float)s, -(float)s);
+            a = 8.0 * fv;
+            sincospi(2.0 * (a - rint(a)), &s, &c);
+            D8r = t5_pack((float)c, (float)c);
+            D8i = t5_pack((float)s, (float)s);
+            D8n = t5_pack(-(float)s, -(float)s);
+        }
+
+        // A tiles of K tile kl: row `row` = trig of this uv point at the tile's 32 columns, fp16 hi + lo;
+        // this thread writes two of the four 8-wide K slabs
+        auto gen_a = [&](int kl) {
+            unsigned char *Ab = As + (size_t)(kl & 1) * T5_A_BYTES;
+            double a0 = fu * ((double)((kt0 + kl) * T5_KT + half_id * 16) + P.hx), a1 = fu;
             a0 -= rint(a0);
             a1 -= rint(a1);
             float sf, cf;
@@ -288,7 +340,7 @@ __global__ void __launch_bounds__(T5_M, 1) dft_tc5_kernel(const DftParams P, con
             sincospif((float)(2.0 * a1), &sf, &cf);
             const double rc = cf, rs = sf;
 #pragma unroll
-            for (int kc = 0; kc < T5_KT / 8; kc++) {
+            for (int kc = 0; kc < 2; kc++) {
                 __align__(16) __half ch[8], cl[8], sh[8], sl[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
@@ -298,55 +350,101 @@ __global__ void __launch_bounds__(T5_M, 1) dft_tc5_kernel(const DftParams P, con
                     ci = cr * rs + ci * rc;
                     cr = nr;
                 }
-                const int off = t5_off(tid, kc * 8);
-                *reinterpret_cast<uint4 *>(As + 0 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(ch);
-                *reinterpret_cast<uint4 *>(As + 1 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(cl);
-                *reinterpret_cast<uint4 *>(As + 2 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sh);
-                *reinterpret_cast<uint4 *>(As + 3 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sl);
+                const int off = t5_off(row, (half_id * 2 + kc) * 8);
+                *reinterpret_cast<uint4 *>(Ab + 0 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(ch);
+                *reinterpret_cast<uint4 *>(Ab + 1 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(cl);
+                *reinterpret_cast<uint4 *>(Ab + 2 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sh);
+                *reinterpret_cast<uint4 *>(Ab + 3 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sl);
             }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
-        __syncthreads();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
+            t5_arrive(&a_full[kl & 1]);
+        };
+        if (nkl > 0) gen_a(0);
+        if (nkl > 1) gen_a(1);
 
-        const int it_first = it;
-        for (int r = 0; r < per_k; r++, it++) {
-            const int st = it % T5_NSTAGE;
-            if (tid == 0) {
-                t5_wait(&full_bar[st], (uint32_t)((it / T5_NSTAGE) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_s = t5_smem(As), b_s = t5_smem(Bs + (size_t)st * T5_CHUNK_BYTES);
-                const uint32_t dcol = tmem_base + (uint32_t)((it & 1) * 2 * T5_N);
+        double Vr = 0.0, Vi = 0.0;                       // fp64 sums of the current (K tile, plane) pass
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        int kl = 0, pl = 0, ch = 0;
+        for (int e = 0; e < nit; e++) {
+            const int b = e & 1;
+            // phase seeds of this thread's 32 row pairs: E0 from an fp64-reduced phase, then packed chains
+            // c = 0..3 holding rows (2c, 2c+1) of every group of eight
+            t5_u64 Er[4], Ei[4];
+            {
+                double b0 = fv * ((double)(ch * T5_RC + half_id * 32) + P.hy);
+                b0 -= rint(b0);
+                float e0r, e0i;
+                sincospif((float)(2.0 * b0), &e0i, &e0r);
+                const float e1r = e0r * D1r - e0i * D1i, e1i = e0r * D1i + e0i * D1r;
+                Er[0] = t5_pack(e0r, e1r);
+                Ei[0] = t5_pack(e0i, e1i);
 #pragma unroll
-                for (int ty = 0; ty < 2; ty++) {
-                    const uint32_t d = dcol + (uint32_t)(ty * T5_N);
-                    const uint32_t ahi = a_s + (ty * 2 + 0) * T5_TILE_BYTES, alo = a_s + (ty * 2 + 1) * T5_TILE_BYTES;
-                    const uint32_t bhi = b_s + (ty * 2 + 0) * T5_TILE_BYTES, blo = b_s + (ty * 2 + 1) * T5_TILE_BYTES;
+                for (int c = 1; c < 4; c++) {
+                    Er[c] = t5_fma2(Ei[c - 1], D2n, t5_mul2(Er[c - 1], D2r));
+                    Ei[c] = t5_fma2(Ei[c - 1], D2r, t5_mul2(Er[c - 1], D2i));
+                }
+            }
+            t5_u64 aSS[2] = {0, 0}, aDD[2] = {0, 0}, aDS[2] = {0, 0}, aSD[2] = {0, 0};
+            t5_wait(&tmem_full[b], (uint32_t)((e >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tb = lane_base + (uint32_t)(b * 2 * T5_N + half_id * 32);
 #pragma unroll
-                    for (int ks = 0; ks < 2; ks++) {
-                        const uint32_t ko = ks * 2 * T5_KCHUNK_BYTES;        // 16 columns = two 8-wide K slabs
-                        t5_mma(d, t5_desc(ahi + ko), t5_desc(bhi + ko), ks ? 1u : 0u);
-                        t5_mma(d, t5_desc(ahi + ko), t5_desc(blo + ko), 1u);
-                        t5_mma(d, t5_desc(alo + ko), t5_desc(bhi + ko), 1u);
+            for (int grp = 0; grp < 2; grp++) {
+                uint32_t ss[16], sd[16], dsv[16], dd[16];
+                t5_ld16(tb + (uint32_t)(grp * 16), ss);                       // cos-type tile: SS | SD
+                t5_ld16(tb + (uint32_t)(T5_RC + grp * 16), sd);
+                t5_ld16(tb + (uint32_t)(T5_N + grp * 16), dsv);               // sin-type tile: DS | DD
+                t5_ld16(tb + (uint32_t)(T5_N + T5_RC + grp * 16), dd);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (grp == 1) {                                               // accumulators are in registers now
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    t5_arrive(&tmem_empty[b]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int c = j & 3, a = j & 1;
+                    aSS[a] = t5_fma2(Er[c], t5_packu(ss[2 * j], ss[2 * j + 1]), aSS[a]);
+                    aDD[a] = t5_fma2(Ei[c], t5_packu(dd[2 * j], dd[2 * j + 1]), aDD[a]);
+                    aDS[a] = t5_fma2(Er[c], t5_packu(dsv[2 * j], dsv[2 * j + 1]), aDS[a]);
+                    aSD[a] = t5_fma2(Ei[c], t5_packu(sd[2 * j], sd[2 * j + 1]), aSD[a]);
+                    if (!(grp == 1 && j >= 4)) {                               // advance the chain by eight row pairs
+                        const t5_u64 nr = t5_fma2(Ei[c], D8n, t5_mul2(Er[c], D8r));
+                        Ei[c] = t5_fma2(Ei[c], D8r, t5_mul2(Er[c], D8i));
+                        Er[c] = nr;
                     }
                 }
-                t5_commit(&mma_bar[it & 1]);
             }
-            // everyone: epilogue of the previous chunk while the tensor core works on this one
-            if (it > it_first) {
-                epilogue(it - 1);
-                __syncthreads();
-                if (tid == 0 && (it - 1) + T5_NSTAGE < nit) {
-                    const int stp = (it - 1) % T5_NSTAGE;
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    t5_expect_tx(&full_bar[stp], T5_CHUNK_BYTES);
-                    t5_tma(Bs + (size_t)stp * T5_CHUNK_BYTES, chunk_src(it - 1 + T5_NSTAGE), T5_CHUNK_BYTES, &full_bar[stp]);
+            Vr += (double)((t5_sum2(aSS[0]) + t5_sum2(aSS[1])) - (t5_sum2(aDD[0]) + t5_sum2(aDD[1])));
+            Vi += (double)((t5_sum2(aDS[0]) + t5_sum2(aDS[1])) + (t5_sum2(aSD[0]) + t5_sum2(aSD[1])));
+            if (++ch == P.nchunk) {                  // end of this (K tile, plane) pass: combine the two halves
+                ch = 0;
+                const int bar_id = 1 + (warp & 3);   // named barrier of the warp pair (w, w + 4)
+                if (half_id == 1) vx[row] = make_double2(Vr, Vi);
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                if (half_id == 0 && valid) {
+                    const double2 o2 = vx[row];
+                    const double vr = Vr + o2.x, vi = Vi + o2.y;
+                    double2 *dst = P.part + ((size_t)sp * P.nf + (plane0 + pl)) * (size_t)P.nuvh + kuv;
+                    if (kl == 0) *dst = make_double2(vr, vi);
+                    else {
+                        const double2 o = *dst;
+                        *dst = make_double2(o.x + vr, o.y + vi);
+                    }
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                Vr = 0.0;
+                Vi = 0.0;
+                if (++pl == npl) {                   // last chunk of K tile kl: its A buffer is free again
+                    pl = 0;
+                    if (kl + 2 < nkl) gen_a(kl + 2);
+                    kl++;
                 }
             }
         }
     }
-    if (it > 0) epilogue(it - 1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0)
+    if (warp == 9)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
@@ -395,7 +493,7 @@ int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
     const int nkt = (npx + T5_KT - 1) / T5_KT;
     p.nchunk = (npy + T5_RC - 1) / T5_RC;
     PDSB_REQUIRE(p.nsplit >= 1 && p.nsplit <= nkt, "tc5 split");
-    constexpr size_t smem_bytes = (size_t)T5_A_BYTES + (size_t)T5_NSTAGE * T5_CHUNK_BYTES + 1024;
+    constexpr size_t smem_bytes = 2 * (size_t)T5_A_BYTES + (size_t)T5_NSTAGE * T5_CHUNK_BYTES + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -406,7 +504,7 @@ int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
     const int pg = tc5_pg(p.nf);
     dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)((p.nf + pg - 1) / pg));
     LaunchScope ls("dft_tc5_tcgen05");
-    dft_tc5_kernel<<<grid, T5_M, smem_bytes, c.stream>>>(p, B, nkt, pg);
+    dft_tc5_kernel<<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
