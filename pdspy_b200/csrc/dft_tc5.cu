@@ -26,14 +26,16 @@
 
 namespace pdsb {
 
-constexpr int T5_KT = 32;                       // column pairs per K tile (two UMMA k-steps of 16)
+constexpr int T5_KSUB = 32;                     // column pairs per B sub-chunk (two UMMA k-steps of 16)
+constexpr int T5_NSUB = 2;                      // sub-chunks accumulated in TMEM before the epilogue reads them
+constexpr int T5_KT = T5_KSUB * T5_NSUB;        // column pairs per K tile (one set of A tiles)
 constexpr int T5_RC = 64;                       // row pairs per chunk -> N = 128 per trig type
 constexpr int T5_N = 2 * T5_RC;                 // UMMA N
 constexpr int T5_M = 128;                       // UMMA M = uv points per CTA
 constexpr int T5_KCHUNK_BYTES = (T5_N / 8) * 128;        // 2048: one 8-wide K slab of a [128 x K] tile
-constexpr int T5_TILE_BYTES = (T5_KT / 8) * T5_KCHUNK_BYTES;   // 8192: [128 x 32] fp16
-constexpr int T5_CHUNK_BYTES = 4 * T5_TILE_BYTES;        // B chunk: [type][hi|lo]
-constexpr int T5_A_BYTES = 4 * T5_TILE_BYTES;            // A: [cos hi, cos lo, sin hi, sin lo]
+constexpr int T5_TILE_BYTES = (T5_KSUB / 8) * T5_KCHUNK_BYTES; // 8192: [128 x 32] fp16
+constexpr int T5_CHUNK_BYTES = 4 * T5_TILE_BYTES;        // B sub-chunk: [type][hi|lo]
+constexpr int T5_A_BYTES = T5_NSUB * 4 * T5_TILE_BYTES;  // A: [sub][cos hi, cos lo, sin hi, sin lo]
 constexpr int T5_NSTAGE = 3;
 constexpr uint32_t T5_IDESC = (1u << 4) | ((uint32_t)(T5_N >> 3) << 17) | ((uint32_t)(T5_M >> 4) << 24);
 //                            D = f32      N                              M        (A, B = f16, K-major)
@@ -51,6 +53,18 @@ __device__ __forceinline__ uint64_t t5_desc(uint32_t saddr)
     const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (((uint32_t)(T5_KCHUNK_BYTES >> 4) & 0x3fffu) << 16);   // start, LBO
     const uint32_t hi = ((uint32_t)(128 >> 4) & 0x3fffu) | (1u << 14);                                     // SBO, version 1
     return ((uint64_t)hi << 32) | lo;                                                                      // layout: none
+}
+// low word of the descriptor of the tile at `saddr`; tiles at saddr + off have low word + (off >> 4)
+__device__ __forceinline__ uint32_t t5_desc_lo(uint32_t saddr)
+{
+    return ((saddr >> 4) & 0x3fffu) | (((uint32_t)(T5_KCHUNK_BYTES >> 4) & 0x3fffu) << 16);
+}
+constexpr uint32_t T5_DESC_HI = ((uint32_t)(128 >> 4) & 0x3fffu) | (1u << 14);      // SBO, version 1, no swizzle
+__device__ __forceinline__ bool t5_elect()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void t5_mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -82,15 +96,18 @@ __device__ __forceinline__ void t5_tma(void *dst, const void *src, uint32_t byte
                  "l"(src), "r"(bytes), "r"(t5_smem(bar))
                  : "memory");
 }
-__device__ __forceinline__ void t5_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+__device__ __forceinline__ void t5_mma(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(T5_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        "r"(adesc_lo), "r"(bdesc_lo), "r"(T5_IDESC), "r"(accumulate), "r"(T5_DESC_HI)
         : "memory");
 }
 __device__ __forceinline__ void t5_commit(uint64_t *bar)
@@ -117,6 +134,12 @@ __device__ __forceinline__ void t5_ld16(uint32_t taddr, uint32_t (&v)[16])
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
+}
+__device__ __forceinline__ void t5_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
 }
 __device__ __forceinline__ void t5_arrive(uint64_t *bar)
 {
@@ -147,6 +170,12 @@ __device__ __forceinline__ t5_u64 t5_packu(uint32_t lo, uint32_t hi)
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
     return d;
 }
+__device__ __forceinline__ t5_u64 t5_add2(t5_u64 a, t5_u64 b)
+{
+    t5_u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ float t5_sum2(t5_u64 a)
 {
     float lo, hi;
@@ -160,8 +189,8 @@ __device__ __forceinline__ void t5_split(float x, __half &hi, __half &lo)
 }
 
 // ---- fold into the canonical UMMA B layout ----
-// B[plane][ktile][chunk][type][hi|lo][t5_off(r, k)], r = c*64 + s_l (component c of the type: SS,SD |
-// DS,DD; row pair s_l of the chunk), k = column pair within the K tile.
+// B[plane][ktile][chunk][sub][type][hi|lo][t5_off(r, k)], r = c*64 + s_l (component c of the type: SS,SD |
+// DS,-DD; row pair s_l of the chunk), k = column pair within the sub-chunk.
 __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict__ img, unsigned char *__restrict__ B,
                                                        const double *__restrict__ scale, int ny, int nx, int nf,
                                                        int npx, int npy, int nkt, int nchunk)
@@ -187,11 +216,11 @@ __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict_
         if (!selfc && !selfr) mm = img[((int64_t)j_hi * nx + c_lo) * nf + p];
     }
     const double Sp = pp + mp, Dp = pp - mp, Sm = pm + mm, Dm = pm - mm;
-    const double comp[4] = {Sp + Sm, Sp - Sm, Dp + Dm, Dp - Dm};
+    const double comp[4] = {Sp + Sm, Sp - Sm, Dp + Dm, -(Dp - Dm)};      // SS, SD, DS, -DD
     const double sc = scale[p];
-    const int kt = t / T5_KT, k = t % T5_KT;
+    const int kt = t / T5_KT, sub = (t % T5_KT) / T5_KSUB, k = t % T5_KSUB;
     const int chunk = s / T5_RC, s_l = s % T5_RC;
-    unsigned char *base = B + (((int64_t)p * nkt + kt) * nchunk + chunk) * (int64_t)T5_CHUNK_BYTES;
+    unsigned char *base = B + ((((int64_t)p * nkt + kt) * nchunk + chunk) * T5_NSUB + sub) * (int64_t)T5_CHUNK_BYTES;
 #pragma unroll
     for (int cidx = 0; cidx < 4; cidx++) {
         const int type = cidx >> 1, c = cidx & 1;
@@ -210,7 +239,7 @@ constexpr int T5_THREADS = T5_EPI_THREADS + 64; // + TMA warp + MMA warp
 __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams P, const unsigned char *__restrict__ Bg,
                                                                 int nkt, int pg)
 {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *As = smem;                                   // 2 buffers x (4 x 8 KB)
     unsigned char *Bs = smem + 2 * T5_A_BYTES;                  // T5_NSTAGE x 32 KB
     __shared__ __align__(8) uint64_t full_bar[T5_NSTAGE];       // TMA landed           (producer -> MMA)
@@ -253,16 +282,18 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
     if (warp == 8) {
         // ================= TMA producer =================
         if (lane == 0) {
-            int kl = 0, pl = 0, ch = 0;
-            for (int it = 0; it < nit; it++) {
+            // the sub-chunks of one (K tile, plane) pass are contiguous: [chunk][sub]
+            int kl = 0, pl = 0, cs = 0;
+            const int ncs = P.nchunk * T5_NSUB;
+            for (int it = 0; it < nit * T5_NSUB; it++) {
                 const int st = it % T5_NSTAGE;
                 if (it >= T5_NSTAGE) t5_wait(&empty_bar[st], (uint32_t)((it / T5_NSTAGE - 1) & 1));
                 const unsigned char *src =
-                    Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)P.nchunk + ch) * T5_CHUNK_BYTES;
+                    Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)ncs + cs) * T5_CHUNK_BYTES;
                 t5_expect_tx(&full_bar[st], T5_CHUNK_BYTES);
                 t5_tma(Bs + (size_t)st * T5_CHUNK_BYTES, src, T5_CHUNK_BYTES, &full_bar[st]);
-                if (++ch == P.nchunk) {
-                    ch = 0;
+                if (++cs == ncs) {
+                    cs = 0;
                     if (++pl == npl) {
                         pl = 0;
                         kl++;
@@ -272,33 +303,42 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
         }
     } else if (warp == 9) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            int it = 0;
-            for (int kl = 0; kl < nkl; kl++) {
-                t5_wait(&a_full[kl & 1], (uint32_t)((kl >> 1) & 1));
-                const uint32_t a_s = t5_smem(As + (size_t)(kl & 1) * T5_A_BYTES);
-                for (int r = 0; r < per_k; r++, it++) {
-                    const int st = it % T5_NSTAGE, b = it & 1;
-                    t5_wait(&full_bar[st], (uint32_t)((it / T5_NSTAGE) & 1));
-                    if (it >= 2) t5_wait(&tmem_empty[b], (uint32_t)(((it >> 1) - 1) & 1));
+        // the whole warp walks the loops and waits (warp-uniform control flow); one elected lane issues
+        const bool leader = t5_elect();
+        const uint32_t a_lo0 = t5_desc_lo(t5_smem(As)), b_lo0 = t5_desc_lo(t5_smem(Bs));
+        int it = 0, is = 0, st = 0;                  // accumulator rounds, sub-chunks, ring stage
+        for (int kl = 0; kl < nkl; kl++) {
+            t5_wait(&a_full[kl & 1], (uint32_t)((kl >> 1) & 1));
+            const uint32_t a_buf = a_lo0 + (uint32_t)((kl & 1) * (T5_A_BYTES >> 4));
+            for (int r = 0; r < per_k; r++, it++) {
+                const int b = it & 1;
+                const uint32_t dcol = tmem_base + (uint32_t)(b * 2 * T5_N);
+                if (it >= 2) t5_wait(&tmem_empty[b], (uint32_t)(((it >> 1) - 1) & 1));
+#pragma unroll
+                for (int sub = 0; sub < T5_NSUB; sub++, is++) {
+                    t5_wait(&full_bar[st], (uint32_t)((is / T5_NSTAGE) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t b_s = t5_smem(Bs + (size_t)st * T5_CHUNK_BYTES);
-                    const uint32_t dcol = tmem_base + (uint32_t)(b * 2 * T5_N);
+                    if (leader) {
+                        const uint32_t a_s = a_buf + (uint32_t)(sub * ((4 * T5_TILE_BYTES) >> 4));
+                        const uint32_t b_s = b_lo0 + (uint32_t)st * (uint32_t)(T5_CHUNK_BYTES >> 4);
 #pragma unroll
-                    for (int ty = 0; ty < 2; ty++) {
-                        const uint32_t d = dcol + (uint32_t)(ty * T5_N);
-                        const uint32_t ahi = a_s + (ty * 2 + 0) * T5_TILE_BYTES, alo = a_s + (ty * 2 + 1) * T5_TILE_BYTES;
-                        const uint32_t bhi = b_s + (ty * 2 + 0) * T5_TILE_BYTES, blo = b_s + (ty * 2 + 1) * T5_TILE_BYTES;
+                        for (int ty = 0; ty < 2; ty++) {
+                            const uint32_t d = dcol + (uint32_t)(ty * T5_N);
 #pragma unroll
-                        for (int ks = 0; ks < 2; ks++) {
-                            const uint32_t ko = ks * 2 * T5_KCHUNK_BYTES;        // 16 columns = two 8-wide K slabs
-                            t5_mma(d, t5_desc(ahi + ko), t5_desc(bhi + ko), ks ? 1u : 0u);
-                            t5_mma(d, t5_desc(ahi + ko), t5_desc(blo + ko), 1u);
-                            t5_mma(d, t5_desc(alo + ko), t5_desc(bhi + ko), 1u);
+                            for (int ks = 0; ks < 2; ks++) {
+                                // tile (ty, hi|lo) at (ty*2 + part) * TILE_BYTES; 16 columns = two 8-wide K slabs
+                                const uint32_t hi = (uint32_t)(((ty * 2 + 0) * T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                const uint32_t lo = (uint32_t)(((ty * 2 + 1) * T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                t5_mma(d, a_s + hi, b_s + hi, (sub | ks) ? 1u : 0u);
+                                t5_mma(d, a_s + hi, b_s + lo, 1u);
+                                t5_mma(d, a_s + lo, b_s + hi, 1u);
+                            }
                         }
+                        t5_commit(&empty_bar[st]);   // stage (and, at the end of a K tile, the A buffer) consumed
+                        if (sub == T5_NSUB - 1) t5_commit(&tmem_full[b]);
                     }
-                    t5_commit(&empty_bar[st]);       // stage (and, at the end of a K tile, the A buffer) consumed
-                    t5_commit(&tmem_full[b]);
+                    __syncwarp();
+                    if (++st == T5_NSTAGE) st = 0;
                 }
             }
         }
@@ -331,7 +371,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
         // this thread writes two of the four 8-wide K slabs
         auto gen_a = [&](int kl) {
             unsigned char *Ab = As + (size_t)(kl & 1) * T5_A_BYTES;
-            double a0 = fu * ((double)((kt0 + kl) * T5_KT + half_id * 16) + P.hx), a1 = fu;
+            constexpr int SLABS = T5_KT / 8 / 2;     // 8-wide K slabs per thread (the other half does the rest)
+            double a0 = fu * ((double)((kt0 + kl) * T5_KT + half_id * SLABS * 8) + P.hx), a1 = fu;
             a0 -= rint(a0);
             a1 -= rint(a1);
             float sf, cf;
@@ -340,7 +381,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
             sincospif((float)(2.0 * a1), &sf, &cf);
             const double rc = cf, rs = sf;
 #pragma unroll
-            for (int kc = 0; kc < 2; kc++) {
+            for (int kc = 0; kc < SLABS; kc++) {
                 __align__(16) __half ch[8], cl[8], sh[8], sl[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
@@ -350,11 +391,13 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                     ci = cr * rs + ci * rc;
                     cr = nr;
                 }
-                const int off = t5_off(row, (half_id * 2 + kc) * 8);
-                *reinterpret_cast<uint4 *>(Ab + 0 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(ch);
-                *reinterpret_cast<uint4 *>(Ab + 1 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(cl);
-                *reinterpret_cast<uint4 *>(Ab + 2 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sh);
-                *reinterpret_cast<uint4 *>(Ab + 3 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sl);
+                const int slab = half_id * SLABS + kc;                       // -> sub-tile slab / 4, k = (slab % 4) * 8
+                unsigned char *At = Ab + (size_t)(slab >> 2) * 4 * T5_TILE_BYTES;
+                const int off = t5_off(row, (slab & 3) * 8);
+                *reinterpret_cast<uint4 *>(At + 0 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(ch);
+                *reinterpret_cast<uint4 *>(At + 1 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(cl);
+                *reinterpret_cast<uint4 *>(At + 2 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sh);
+                *reinterpret_cast<uint4 *>(At + 3 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sl);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
             t5_arrive(&a_full[kl & 1]);
@@ -364,17 +407,22 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
 
         double Vr = 0.0, Vi = 0.0;                       // fp64 sums of the current (K tile, plane) pass
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        // row phase of this thread's first row pair of the current chunk, advanced one chunk at a time in fp64
+        double S0r, S0i, DCr, DCi;
+        {
+            double a = fv * ((double)(half_id * 32) + P.hy);
+            sincospi(2.0 * (a - rint(a)), &S0i, &S0r);
+            a = fv * (double)T5_RC;
+            sincospi(2.0 * (a - rint(a)), &DCi, &DCr);
+        }
+        double Pr = S0r, Pi = S0i;
         int kl = 0, pl = 0, ch = 0;
         for (int e = 0; e < nit; e++) {
             const int b = e & 1;
-            // phase seeds of this thread's 32 row pairs: E0 from an fp64-reduced phase, then packed chains
-            // c = 0..3 holding rows (2c, 2c+1) of every group of eight
+            // packed phase chains c = 0..3 holding rows (2c, 2c+1) of every group of eight row pairs
             t5_u64 Er[4], Ei[4];
             {
-                double b0 = fv * ((double)(ch * T5_RC + half_id * 32) + P.hy);
-                b0 -= rint(b0);
-                float e0r, e0i;
-                sincospif((float)(2.0 * b0), &e0i, &e0r);
+                const float e0r = (float)Pr, e0i = (float)Pi;
                 const float e1r = e0r * D1r - e0i * D1i, e1i = e0r * D1i + e0i * D1r;
                 Er[0] = t5_pack(e0r, e1r);
                 Ei[0] = t5_pack(e0i, e1i);
@@ -383,39 +431,46 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                     Er[c] = t5_fma2(Ei[c - 1], D2n, t5_mul2(Er[c - 1], D2r));
                     Ei[c] = t5_fma2(Ei[c - 1], D2r, t5_mul2(Er[c - 1], D2i));
                 }
+                const double nr = Pr * DCr - Pi * DCi;
+                Pi = Pr * DCi + Pi * DCr;
+                Pr = nr;
             }
-            t5_u64 aSS[2] = {0, 0}, aDD[2] = {0, 0}, aDS[2] = {0, 0}, aSD[2] = {0, 0};
+            t5_u64 aRe[4] = {0, 0, 0, 0}, aIm[4] = {0, 0, 0, 0};
             t5_wait(&tmem_full[b], (uint32_t)((e >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tb = lane_base + (uint32_t)(b * 2 * T5_N + half_id * 32);
+            uint32_t ss[2][8], sd[2][8], dsv[2][8], dd[2][8];
+            auto load_grp = [&](int g, int q) {                               // eight row pairs x four components
+                t5_ld8(tb + (uint32_t)(g * 8), ss[q]);                        // cos-type tile: SS | SD
+                t5_ld8(tb + (uint32_t)(T5_RC + g * 8), sd[q]);
+                t5_ld8(tb + (uint32_t)(T5_N + g * 8), dsv[q]);                // sin-type tile: DS | -DD
+                t5_ld8(tb + (uint32_t)(T5_N + T5_RC + g * 8), dd[q]);
+            };
+            load_grp(0, 0);
 #pragma unroll
-            for (int grp = 0; grp < 2; grp++) {
-                uint32_t ss[16], sd[16], dsv[16], dd[16];
-                t5_ld16(tb + (uint32_t)(grp * 16), ss);                       // cos-type tile: SS | SD
-                t5_ld16(tb + (uint32_t)(T5_RC + grp * 16), sd);
-                t5_ld16(tb + (uint32_t)(T5_N + grp * 16), dsv);               // sin-type tile: DS | DD
-                t5_ld16(tb + (uint32_t)(T5_N + T5_RC + grp * 16), dd);
+            for (int g = 0; g < 4; g++) {
+                const int q = g & 1;
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (grp == 1) {                                               // accumulators are in registers now
+                if (g < 3) load_grp(g + 1, q ^ 1);                            // in flight during this group's math
+                else {                                                        // accumulators are in registers now
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     t5_arrive(&tmem_empty[b]);
                 }
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int c = j & 3, a = j & 1;
-                    aSS[a] = t5_fma2(Er[c], t5_packu(ss[2 * j], ss[2 * j + 1]), aSS[a]);
-                    aDD[a] = t5_fma2(Ei[c], t5_packu(dd[2 * j], dd[2 * j + 1]), aDD[a]);
-                    aDS[a] = t5_fma2(Er[c], t5_packu(dsv[2 * j], dsv[2 * j + 1]), aDS[a]);
-                    aSD[a] = t5_fma2(Ei[c], t5_packu(sd[2 * j], sd[2 * j + 1]), aSD[a]);
-                    if (!(grp == 1 && j >= 4)) {                               // advance the chain by eight row pairs
+                for (int c = 0; c < 4; c++) {
+                    aRe[c] = t5_fma2(Er[c], t5_packu(ss[q][2 * c], ss[q][2 * c + 1]), aRe[c]);
+                    aIm[c] = t5_fma2(Er[c], t5_packu(dsv[q][2 * c], dsv[q][2 * c + 1]), aIm[c]);
+                    aRe[c] = t5_fma2(Ei[c], t5_packu(dd[q][2 * c], dd[q][2 * c + 1]), aRe[c]);
+                    aIm[c] = t5_fma2(Ei[c], t5_packu(sd[q][2 * c], sd[q][2 * c + 1]), aIm[c]);
+                    if (g < 3) {                                              // advance the chain by eight row pairs
                         const t5_u64 nr = t5_fma2(Ei[c], D8n, t5_mul2(Er[c], D8r));
                         Ei[c] = t5_fma2(Ei[c], D8r, t5_mul2(Er[c], D8i));
                         Er[c] = nr;
                     }
                 }
             }
-            Vr += (double)((t5_sum2(aSS[0]) + t5_sum2(aSS[1])) - (t5_sum2(aDD[0]) + t5_sum2(aDD[1])));
-            Vi += (double)((t5_sum2(aDS[0]) + t5_sum2(aDS[1])) + (t5_sum2(aSD[0]) + t5_sum2(aSD[1])));
+            Vr += (double)t5_sum2(t5_add2(t5_add2(aRe[0], aRe[1]), t5_add2(aRe[2], aRe[3])));
+            Vi += (double)t5_sum2(t5_add2(t5_add2(aIm[0], aIm[1]), t5_add2(aIm[2], aIm[3])));
             if (++ch == P.nchunk) {                  // end of this (K tile, plane) pass: combine the two halves
                 ch = 0;
                 const int bar_id = 1 + (warp & 3);   // named barrier of the warp pair (w, w + 4)
@@ -434,6 +489,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                 asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
                 Vr = 0.0;
                 Vi = 0.0;
+                Pr = S0r;
+                Pi = S0i;
                 if (++pl == npl) {                   // last chunk of K tile kl: its A buffer is free again
                     pl = 0;
                     if (kl + 2 < nkl) gen_a(kl + 2);
@@ -453,7 +510,7 @@ size_t tc5_operand_bytes(int ny, int nx, int nf)
 {
     const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
     const int nkt = (npx + T5_KT - 1) / T5_KT, nchunk = (npy + T5_RC - 1) / T5_RC;
-    return (size_t)nf * nkt * nchunk * T5_CHUNK_BYTES;
+    return (size_t)nf * nkt * nchunk * T5_NSUB * T5_CHUNK_BYTES;
 }
 
 static int tc5_pg(int nf) { return nf < 8 ? nf : 8; }
@@ -493,7 +550,7 @@ int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
     const int nkt = (npx + T5_KT - 1) / T5_KT;
     p.nchunk = (npy + T5_RC - 1) / T5_RC;
     PDSB_REQUIRE(p.nsplit >= 1 && p.nsplit <= nkt, "tc5 split");
-    constexpr size_t smem_bytes = 2 * (size_t)T5_A_BYTES + (size_t)T5_NSTAGE * T5_CHUNK_BYTES + 1024;
+    constexpr size_t smem_bytes = 2 * (size_t)T5_A_BYTES + (size_t)T5_NSTAGE * T5_CHUNK_BYTES;
     static bool attr_set = false;
     if (!attr_set) {
         PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
