@@ -7,16 +7,20 @@
 //
 //   CTA = 128 uv points (UMMA M = 128), 10 warps with fixed roles:
 //     warps 0-7  epilogue: thread (w & 3) * 32 + lane owns uv row r (TMEM lane r); warps 0-3 take row pairs
-//                0..31 of every chunk, warps 4-7 row pairs 32..63.  They also write row r of the four A
-//                operand tiles (cos/sin x hi/lo, [128 x 32] fp16, canonical K-major no-swizzle core-matrix
-//                layout), double buffered over K tiles.
-//     warp 8     one thread issues the bulk TMA copies of the B chunks (3-stage ring)
-//     warp 9     one thread issues the tcgen05.mma's and commits them to the mbarriers
-//   B operand chunks ([2 types][hi|lo][N = 128 rows = 2 comps x 64 row pairs][K = 32]) are written by the
-//   fold kernel directly in the canonical UMMA layout, so one 32 KB 1-D bulk TMA copy per chunk feeds
-//   12 MMAs (2 types x 2 k-steps x 3 split products) of shape 128 x 128 x 16.
-//   TMEM: 512 columns = 2 buffers x 2 types x 128 fp32 columns; everything is handed over through
-//   mbarriers (stage full/empty, TMEM full/empty, A tile full), no CTA-wide barrier in the steady state.
+//                0..31 of every chunk, warps 4-7 row pairs 32..63.  They also write row r of the A operand
+//                (cos/sin x hi/lo of the K tile's 64 columns, fp16) straight into TMEM with tcgen05.st,
+//                double buffered over K tiles: the MMAs then read only B from shared memory, which is
+//                what keeps the shared-memory data pipe (128 B/clk, shared with the TMA writes) off the
+//                critical path.
+//     warp 8     one thread issues the bulk TMA copies of the B units (6-stage ring of 16 KB)
+//     warp 9     one elected thread issues the tcgen05.mma's and commits them to the mbarriers
+//   B units ([hi|lo][N = 128 rows = 2 comps x 64 row pairs][K = 32], one trig type, one K sub-tile) are
+//   written by the fold kernel directly in the canonical UMMA layout; one 16 KB 1-D bulk TMA copy feeds
+//   6 MMAs (2 k-steps x 3 split products) of shape 128 x 128 x 16.
+//   TMEM: 512 columns = [cos-type accumulator 128 | sin-type accumulator 128 | A buffer 0 128 | A buffer 1
+//   128].  The two accumulators are the two pipeline buffers: while the epilogue warps read the cos-type
+//   tile (SS, SD) the tensor core fills the sin-type tile (DS, -DD) and vice versa.  Everything is handed
+//   over through mbarriers (stage full/empty, TMEM full/empty, A full); no CTA-wide barrier in steady state.
 //   Epilogue arithmetic is packed fp32x2 (FFMA2) over adjacent row pairs, four independent phase chains.
 //
 // NOT the default (see dft_mma.cu header); reported by bench.py under `extras`.
@@ -34,9 +38,12 @@ constexpr int T5_N = 2 * T5_RC;                 // UMMA N
 constexpr int T5_M = 128;                       // UMMA M = uv points per CTA
 constexpr int T5_KCHUNK_BYTES = (T5_N / 8) * 128;        // 2048: one 8-wide K slab of a [128 x K] tile
 constexpr int T5_TILE_BYTES = (T5_KSUB / 8) * T5_KCHUNK_BYTES; // 8192: [128 x 32] fp16
-constexpr int T5_CHUNK_BYTES = 4 * T5_TILE_BYTES;        // B sub-chunk: [type][hi|lo]
-constexpr int T5_A_BYTES = T5_NSUB * 4 * T5_TILE_BYTES;  // A: [sub][cos hi, cos lo, sin hi, sin lo]
-constexpr int T5_NSTAGE = 3;
+constexpr int T5_UNIT_BYTES = 2 * T5_TILE_BYTES;         // B unit: [hi|lo] of one type, one K sub-tile (16 KB)
+constexpr int T5_NSTAGE = 6;
+constexpr int T5_ACOL = 2 * T5_N;                        // first TMEM column of the A buffers
+constexpr int T5_APART = T5_KT / 2;                      // TMEM columns of one A part (two fp16 per column)
+constexpr int T5_ABUF = 4 * T5_APART;                    // A buffer: [cos hi | cos lo | sin hi | sin lo]
+static_assert(T5_ACOL + 2 * T5_ABUF <= 512, "TMEM budget");
 constexpr uint32_t T5_IDESC = (1u << 4) | ((uint32_t)(T5_N >> 3) << 17) | ((uint32_t)(T5_M >> 4) << 24);
 //                            D = f32      N                              M        (A, B = f16, K-major)
 
@@ -110,6 +117,29 @@ __device__ __forceinline__ void t5_mma(uint32_t tmem_d, uint32_t adesc_lo, uint3
         "r"(adesc_lo), "r"(bdesc_lo), "r"(T5_IDESC), "r"(accumulate), "r"(T5_DESC_HI)
         : "memory");
 }
+// A operand from TMEM (lane = row, two fp16 per column along K), B from shared memory
+__device__ __forceinline__ void t5_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(bdesc_lo), "r"(T5_IDESC), "r"(accumulate), "r"(T5_DESC_HI)
+        : "memory");
+}
+__device__ __forceinline__ void t5_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t t5_h2(__half a, __half b)
+{
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
 __device__ __forceinline__ void t5_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t5_smem(bar)) : "memory");
@@ -182,6 +212,29 @@ __device__ __forceinline__ float t5_sum2(t5_u64 a)
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
     return lo + hi;
 }
+// Phases are kept as 64-bit fixed-point fractions of a turn (2^64 = one turn): H = frac(f / 2) so that the
+// phase of a pixel at half-integer offset n/2 is n * H (mod 2^64), exactly, in integer arithmetic.  The
+// plain-CUDA-core fp64 rate of this GPU is ~1/64 of fp32 (measured: DADD was 35% of all stall samples of
+// an earlier version), so nothing in the steady state may touch fp64.
+__device__ __forceinline__ unsigned long long t5_fix(double f)
+{
+    double h = 0.5 * f;
+    h -= rint(h);                                                    // [-0.5, 0.5]
+    return (unsigned long long)__double2ll_rn(h * 9223372036854775808.0) << 1;
+}
+__device__ __forceinline__ void t5_trig(unsigned long long H, int n, float &c, float &s)
+{
+    const unsigned long long ph = (unsigned long long)(long long)n * H;
+    const float t = (float)(int)(unsigned)(ph >> 32) * 4.656612873077393e-10f;      // turns * 2 in [-1, 1)
+    sincospif(t, &s, &c);
+}
+// (hi, lo) += x, error-free (Knuth two-sum)
+__device__ __forceinline__ void t5_dfadd(float &hi, float &lo, float x)
+{
+    const float s = hi + x, bb = s - hi;
+    lo += (hi - (s - bb)) + (x - bb);
+    hi = s;
+}
 __device__ __forceinline__ void t5_split(float x, __half &hi, __half &lo)
 {
     hi = __float2half_rn(x);
@@ -189,7 +242,7 @@ __device__ __forceinline__ void t5_split(float x, __half &hi, __half &lo)
 }
 
 // ---- fold into the canonical UMMA B layout ----
-// B[plane][ktile][chunk][sub][type][hi|lo][t5_off(r, k)], r = c*64 + s_l (component c of the type: SS,SD |
+// B[plane][ktile][chunk][type][sub][hi|lo][t5_off(r, k)], r = c*64 + s_l (component c of the type: SS,SD |
 // DS,-DD; row pair s_l of the chunk), k = column pair within the sub-chunk.
 __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict__ img, unsigned char *__restrict__ B,
                                                        const double *__restrict__ scale, int ny, int nx, int nf,
@@ -220,7 +273,7 @@ __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict_
     const double sc = scale[p];
     const int kt = t / T5_KT, sub = (t % T5_KT) / T5_KSUB, k = t % T5_KSUB;
     const int chunk = s / T5_RC, s_l = s % T5_RC;
-    unsigned char *base = B + ((((int64_t)p * nkt + kt) * nchunk + chunk) * T5_NSUB + sub) * (int64_t)T5_CHUNK_BYTES;
+    unsigned char *base = B + (((int64_t)p * nkt + kt) * nchunk + chunk) * (int64_t)(2 * T5_NSUB * T5_UNIT_BYTES);
 #pragma unroll
     for (int cidx = 0; cidx < 4; cidx++) {
         const int type = cidx >> 1, c = cidx & 1;
@@ -228,8 +281,9 @@ __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict_
         const double x = comp[cidx] * sc;
         const __half hi = __double2half(x);
         const __half lo = __double2half(x - (double)__half2float(hi));
-        *reinterpret_cast<__half *>(base + (type * 2 + 0) * T5_TILE_BYTES + off) = hi;
-        *reinterpret_cast<__half *>(base + (type * 2 + 1) * T5_TILE_BYTES + off) = lo;
+        unsigned char *unit = base + (type * T5_NSUB + sub) * T5_UNIT_BYTES;
+        *reinterpret_cast<__half *>(unit + off) = hi;
+        *reinterpret_cast<__half *>(unit + T5_TILE_BYTES + off) = lo;
     }
 }
 
@@ -239,23 +293,21 @@ constexpr int T5_THREADS = T5_EPI_THREADS + 64; // + TMA warp + MMA warp
 __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams P, const unsigned char *__restrict__ Bg,
                                                                 int nkt, int pg)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *As = smem;                                   // 2 buffers x (4 x 8 KB)
-    unsigned char *Bs = smem + 2 * T5_A_BYTES;                  // T5_NSTAGE x 32 KB
+    extern __shared__ __align__(128) unsigned char Bs[];        // T5_NSTAGE x 16 KB
     __shared__ __align__(8) uint64_t full_bar[T5_NSTAGE];       // TMA landed           (producer -> MMA)
     __shared__ __align__(8) uint64_t empty_bar[T5_NSTAGE];      // MMAs read the stage  (MMA commit -> producer)
-    __shared__ __align__(8) uint64_t tmem_full[2];              // accumulators ready   (MMA commit -> epilogue)
-    __shared__ __align__(8) uint64_t tmem_empty[2];             // accumulators read    (epilogue -> MMA)
-    __shared__ __align__(8) uint64_t a_full[2];                 // A tiles written      (epilogue -> MMA)
+    __shared__ __align__(8) uint64_t tmem_full[2];              // accumulator ready    (MMA commit -> epilogue)
+    __shared__ __align__(8) uint64_t tmem_empty[2];             // accumulator read     (epilogue -> MMA)
+    __shared__ __align__(8) uint64_t a_full[2];                 // A buffer written     (epilogue -> MMA)
     __shared__ uint32_t tmem_base_s;
-    __shared__ double2 vx[T5_M];                 // pass-end exchange between the two halves of a uv point
+    __shared__ float4 vx[T5_M];                  // pass-end exchange between the two halves of a uv point
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int plane0 = blockIdx.z * pg, sp = blockIdx.y;
     const int npl = (P.nf - plane0) < pg ? (P.nf - plane0) : pg;
     const int kt0 = (int)(((int64_t)sp * nkt) / P.nsplit), kt1 = (int)(((int64_t)(sp + 1) * nkt) / P.nsplit);
     const int nkl = kt1 - kt0;
-    const int per_k = npl * P.nchunk;
+    const int per_k = npl * P.nchunk;            // accumulator rounds per K tile
     const int nit = nkl * per_k;
 
     if (tid == 0) {
@@ -282,16 +334,17 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
     if (warp == 8) {
         // ================= TMA producer =================
         if (lane == 0) {
-            // the sub-chunks of one (K tile, plane) pass are contiguous: [chunk][sub]
+            // the units of one (K tile, plane) pass are contiguous: [chunk][type][sub]
             int kl = 0, pl = 0, cs = 0;
-            const int ncs = P.nchunk * T5_NSUB;
-            for (int it = 0; it < nit * T5_NSUB; it++) {
+            const int ncs = P.nchunk * 2 * T5_NSUB;
+            const int nunit = nit * 2 * T5_NSUB;
+            for (int it = 0; it < nunit; it++) {
                 const int st = it % T5_NSTAGE;
                 if (it >= T5_NSTAGE) t5_wait(&empty_bar[st], (uint32_t)((it / T5_NSTAGE - 1) & 1));
                 const unsigned char *src =
-                    Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)ncs + cs) * T5_CHUNK_BYTES;
-                t5_expect_tx(&full_bar[st], T5_CHUNK_BYTES);
-                t5_tma(Bs + (size_t)st * T5_CHUNK_BYTES, src, T5_CHUNK_BYTES, &full_bar[st]);
+                    Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)ncs + cs) * T5_UNIT_BYTES;
+                t5_expect_tx(&full_bar[st], T5_UNIT_BYTES);
+                t5_tma(Bs + (size_t)st * T5_UNIT_BYTES, src, T5_UNIT_BYTES, &full_bar[st]);
                 if (++cs == ncs) {
                     cs = 0;
                     if (++pl == npl) {
@@ -305,40 +358,39 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
         // ================= MMA issuer =================
         // the whole warp walks the loops and waits (warp-uniform control flow); one elected lane issues
         const bool leader = t5_elect();
-        const uint32_t a_lo0 = t5_desc_lo(t5_smem(As)), b_lo0 = t5_desc_lo(t5_smem(Bs));
-        int it = 0, is = 0, st = 0;                  // accumulator rounds, sub-chunks, ring stage
+        const uint32_t b_lo0 = t5_desc_lo(t5_smem(Bs));
+        int it = 0, is = 0, st = 0;                  // accumulator rounds, units, ring stage
         for (int kl = 0; kl < nkl; kl++) {
             t5_wait(&a_full[kl & 1], (uint32_t)((kl >> 1) & 1));
-            const uint32_t a_buf = a_lo0 + (uint32_t)((kl & 1) * (T5_A_BYTES >> 4));
+            const uint32_t a_buf = tmem_base + (uint32_t)(T5_ACOL + (kl & 1) * T5_ABUF);
             for (int r = 0; r < per_k; r++, it++) {
-                const int b = it & 1;
-                const uint32_t dcol = tmem_base + (uint32_t)(b * 2 * T5_N);
-                if (it >= 2) t5_wait(&tmem_empty[b], (uint32_t)(((it >> 1) - 1) & 1));
 #pragma unroll
-                for (int sub = 0; sub < T5_NSUB; sub++, is++) {
-                    t5_wait(&full_bar[st], (uint32_t)((is / T5_NSTAGE) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (leader) {
-                        const uint32_t a_s = a_buf + (uint32_t)(sub * ((4 * T5_TILE_BYTES) >> 4));
-                        const uint32_t b_s = b_lo0 + (uint32_t)st * (uint32_t)(T5_CHUNK_BYTES >> 4);
+                for (int ty = 0; ty < 2; ty++) {     // accumulator ty: cos-type, sin-type
+                    const uint32_t d = tmem_base + (uint32_t)(ty * T5_N);
+                    if (it >= 1) t5_wait(&tmem_empty[ty], (uint32_t)((it - 1) & 1));
 #pragma unroll
-                        for (int ty = 0; ty < 2; ty++) {
-                            const uint32_t d = dcol + (uint32_t)(ty * T5_N);
+                    for (int sub = 0; sub < T5_NSUB; sub++, is++) {
+                        t5_wait(&full_bar[st], (uint32_t)((is / T5_NSTAGE) & 1));
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (leader) {
+                            const uint32_t b_s = b_lo0 + (uint32_t)st * (uint32_t)(T5_UNIT_BYTES >> 4);
 #pragma unroll
                             for (int ks = 0; ks < 2; ks++) {
-                                // tile (ty, hi|lo) at (ty*2 + part) * TILE_BYTES; 16 columns = two 8-wide K slabs
-                                const uint32_t hi = (uint32_t)(((ty * 2 + 0) * T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
-                                const uint32_t lo = (uint32_t)(((ty * 2 + 1) * T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
-                                t5_mma(d, a_s + hi, b_s + hi, (sub | ks) ? 1u : 0u);
-                                t5_mma(d, a_s + hi, b_s + lo, 1u);
-                                t5_mma(d, a_s + lo, b_s + hi, 1u);
+                                // A part (ty, hi|lo) at column (ty*2 + part) * APART; 16 k = 8 columns
+                                const uint32_t ahi = a_buf + (uint32_t)((ty * 2 + 0) * T5_APART + sub * (T5_KSUB / 2) + ks * 8);
+                                const uint32_t alo = a_buf + (uint32_t)((ty * 2 + 1) * T5_APART + sub * (T5_KSUB / 2) + ks * 8);
+                                const uint32_t bhi = b_s + (uint32_t)((ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                const uint32_t blo = b_s + (uint32_t)((T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                t5_mma_ts(d, ahi, bhi, (sub | ks) ? 1u : 0u);
+                                t5_mma_ts(d, ahi, blo, 1u);
+                                t5_mma_ts(d, alo, bhi, 1u);
                             }
+                            t5_commit(&empty_bar[st]);   // stage (and, at the end of a K tile, the A buffer) consumed
+                            if (sub == T5_NSUB - 1) t5_commit(&tmem_full[ty]);
                         }
-                        t5_commit(&empty_bar[st]);   // stage (and, at the end of a K tile, the A buffer) consumed
-                        if (sub == T5_NSUB - 1) t5_commit(&tmem_full[b]);
+                        __syncwarp();
+                        if (++st == T5_NSTAGE) st = 0;
                     }
-                    __syncwarp();
-                    if (++st == T5_NSTAGE) st = 0;
                 }
             }
         }
@@ -347,138 +399,127 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
         const int row = tid & (T5_M - 1), half_id = tid >> 7;      // uv row (TMEM lane), which half of the work
         const int64_t kuv = (int64_t)blockIdx.x * T5_M + row;
         const bool valid = kuv < P.nuvh;
-        const double fu = valid ? P.u[kuv] * P.dxy : 0.0, fv = valid ? P.v[kuv] * P.dxy : 0.0;
+        const unsigned long long Hu = t5_fix(valid ? P.u[kuv] * P.dxy : 0.0), Hv = t5_fix(valid ? P.v[kuv] * P.dxy : 0.0);
+        const int hx2 = P.hx != 0.0 ? 1 : 0, hy2 = P.hy != 0.0 ? 1 : 0;    // pixel offsets in half pixels
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         float D1r, D1i;                                  // row-phase step of one row pair
         t5_u64 D2r, D2i, D2n, D8r, D8i, D8n;             // packed (x, x): steps of two and of eight row pairs
         {
-            double s, c;
-            sincospi(2.0 * (fv - rint(fv)), &s, &c);
-            D1r = (float)c;
-            D1i = (float)s;
-            double a = 2.0 * fv;
-            sincospi(2.0 * (a - rint(a)), &s, &c);
-            D2r = t5_pack((float)c, (float)c);
-            D2i = t5_pack((float)s, (float)s);
-            D2n = t5_pack(-(float)s, -(float)s);
-            a = 8.0 * fv;
-            sincospi(2.0 * (a - rint(a)), &s, &c);
-            D8r = t5_pack((float)c, (float)c);
-            D8i = t5_pack((float)s, (float)s);
-            D8n = t5_pack(-(float)s, -(float)s);
+            float s, c;
+            t5_trig(Hv, 2, D1r, D1i);
+            t5_trig(Hv, 4, c, s);
+            D2r = t5_pack(c, c);
+            D2i = t5_pack(s, s);
+            D2n = t5_pack(-s, -s);
+            t5_trig(Hv, 16, c, s);
+            D8r = t5_pack(c, c);
+            D8i = t5_pack(s, s);
+            D8n = t5_pack(-s, -s);
         }
 
-        // A tiles of K tile kl: row `row` = trig of this uv point at the tile's 32 columns, fp16 hi + lo;
-        // this thread writes two of the four 8-wide K slabs
+        // A operand of K tile kl: row `row` = trig of this uv point at the tile's 64 columns, fp16 hi + lo,
+        // written to TMEM lane `row`; this thread does half of the columns, each from its exact phase
         auto gen_a = [&](int kl) {
-            unsigned char *Ab = As + (size_t)(kl & 1) * T5_A_BYTES;
-            constexpr int SLABS = T5_KT / 8 / 2;     // 8-wide K slabs per thread (the other half does the rest)
-            double a0 = fu * ((double)((kt0 + kl) * T5_KT + half_id * SLABS * 8) + P.hx), a1 = fu;
-            a0 -= rint(a0);
-            a1 -= rint(a1);
-            float sf, cf;
-            sincospif((float)(2.0 * a0), &sf, &cf);
-            double cr = cf, ci = sf;
-            sincospif((float)(2.0 * a1), &sf, &cf);
-            const double rc = cf, rs = sf;
-#pragma unroll
-            for (int kc = 0; kc < SLABS; kc++) {
-                __align__(16) __half ch[8], cl[8], sh[8], sl[8];
+            constexpr int HALF_K = T5_KT / 2;
+            const uint32_t ab = lane_base + (uint32_t)(T5_ACOL + (kl & 1) * T5_ABUF + half_id * (HALF_K / 2));
+            const int n0 = 2 * ((kt0 + kl) * T5_KT + half_id * HALF_K) + hx2;
+#pragma unroll 1
+            for (int kc = 0; kc < HALF_K / 8; kc++) {
+                __half ch[8], cl[8], sh[8], sl[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
-                    t5_split((float)cr, ch[e], cl[e]);
-                    t5_split((float)ci, sh[e], sl[e]);
-                    const double nr = cr * rc - ci * rs;
-                    ci = cr * rs + ci * rc;
-                    cr = nr;
+                    float cf, sf;
+                    t5_trig(Hu, n0 + 2 * (kc * 8 + e), cf, sf);
+                    t5_split(cf, ch[e], cl[e]);
+                    t5_split(sf, sh[e], sl[e]);
                 }
-                const int slab = half_id * SLABS + kc;                       // -> sub-tile slab / 4, k = (slab % 4) * 8
-                unsigned char *At = Ab + (size_t)(slab >> 2) * 4 * T5_TILE_BYTES;
-                const int off = t5_off(row, (slab & 3) * 8);
-                *reinterpret_cast<uint4 *>(At + 0 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(ch);
-                *reinterpret_cast<uint4 *>(At + 1 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(cl);
-                *reinterpret_cast<uint4 *>(At + 2 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sh);
-                *reinterpret_cast<uint4 *>(At + 3 * T5_TILE_BYTES + off) = *reinterpret_cast<const uint4 *>(sl);
+                const uint32_t col = ab + (uint32_t)(kc * 4);
+                t5_st4(col + 0 * T5_APART, t5_h2(ch[0], ch[1]), t5_h2(ch[2], ch[3]), t5_h2(ch[4], ch[5]), t5_h2(ch[6], ch[7]));
+                t5_st4(col + 1 * T5_APART, t5_h2(cl[0], cl[1]), t5_h2(cl[2], cl[3]), t5_h2(cl[4], cl[5]), t5_h2(cl[6], cl[7]));
+                t5_st4(col + 2 * T5_APART, t5_h2(sh[0], sh[1]), t5_h2(sh[2], sh[3]), t5_h2(sh[4], sh[5]), t5_h2(sh[6], sh[7]));
+                t5_st4(col + 3 * T5_APART, t5_h2(sl[0], sl[1]), t5_h2(sl[2], sl[3]), t5_h2(sl[4], sl[5]), t5_h2(sl[6], sl[7]));
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core reads
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             t5_arrive(&a_full[kl & 1]);
         };
         if (nkl > 0) gen_a(0);
         if (nkl > 1) gen_a(1);
 
-        double Vr = 0.0, Vi = 0.0;                       // fp64 sums of the current (K tile, plane) pass
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        // row phase of this thread's first row pair of the current chunk, advanced one chunk at a time in fp64
-        double S0r, S0i, DCr, DCi;
-        {
-            double a = fv * ((double)(half_id * 32) + P.hy);
-            sincospi(2.0 * (a - rint(a)), &S0i, &S0r);
-            a = fv * (double)T5_RC;
-            sincospi(2.0 * (a - rint(a)), &DCi, &DCr);
-        }
-        double Pr = S0r, Pi = S0i;
+        float Vrh = 0.f, Vrl = 0.f, Vih = 0.f, Vil = 0.f;    // two-float sums of the current (K tile, plane) pass
         int kl = 0, pl = 0, ch = 0;
         for (int e = 0; e < nit; e++) {
-            const int b = e & 1;
-            // packed phase chains c = 0..3 holding rows (2c, 2c+1) of every group of eight row pairs
-            t5_u64 Er[4], Ei[4];
+            // packed phase chains c = 0..3 holding rows (2c, 2c+1) of every group of eight row pairs, seeded
+            // from the exact phase of this thread's first row pair of the chunk
+            t5_u64 Sr[4], Si[4];
             {
-                const float e0r = (float)Pr, e0i = (float)Pi;
+                float e0r, e0i;
+                t5_trig(Hv, 2 * (ch * T5_RC + half_id * 32) + hy2, e0r, e0i);
                 const float e1r = e0r * D1r - e0i * D1i, e1i = e0r * D1i + e0i * D1r;
-                Er[0] = t5_pack(e0r, e1r);
-                Ei[0] = t5_pack(e0i, e1i);
+                Sr[0] = t5_pack(e0r, e1r);
+                Si[0] = t5_pack(e0i, e1i);
 #pragma unroll
                 for (int c = 1; c < 4; c++) {
-                    Er[c] = t5_fma2(Ei[c - 1], D2n, t5_mul2(Er[c - 1], D2r));
-                    Ei[c] = t5_fma2(Ei[c - 1], D2r, t5_mul2(Er[c - 1], D2i));
+                    Sr[c] = t5_fma2(Si[c - 1], D2n, t5_mul2(Sr[c - 1], D2r));
+                    Si[c] = t5_fma2(Si[c - 1], D2r, t5_mul2(Sr[c - 1], D2i));
                 }
-                const double nr = Pr * DCr - Pi * DCi;
-                Pi = Pr * DCi + Pi * DCr;
-                Pr = nr;
             }
-            t5_u64 aRe[4] = {0, 0, 0, 0}, aIm[4] = {0, 0, 0, 0};
-            t5_wait(&tmem_full[b], (uint32_t)((e >> 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tb = lane_base + (uint32_t)(b * 2 * T5_N + half_id * 32);
-            uint32_t ss[2][8], sd[2][8], dsv[2][8], dd[2][8];
-            auto load_grp = [&](int g, int q) {                               // eight row pairs x four components
-                t5_ld8(tb + (uint32_t)(g * 8), ss[q]);                        // cos-type tile: SS | SD
-                t5_ld8(tb + (uint32_t)(T5_RC + g * 8), sd[q]);
-                t5_ld8(tb + (uint32_t)(T5_N + g * 8), dsv[q]);                // sin-type tile: DS | -DD
-                t5_ld8(tb + (uint32_t)(T5_N + T5_RC + g * 8), dd[q]);
-            };
-            load_grp(0, 0);
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const int q = g & 1;
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (g < 3) load_grp(g + 1, q ^ 1);                            // in flight during this group's math
-                else {                                                        // accumulators are in registers now
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    t5_arrive(&tmem_empty[b]);
-                }
+            for (int ty = 0; ty < 2; ty++) {
+                // tile ty holds components (X | Y) = (SS | SD) or (DS | -DD):  p += cos(b) X,  q += sin(b) Y
+                t5_u64 Er[4], Ei[4], aP[4] = {0, 0, 0, 0}, aQ[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    aRe[c] = t5_fma2(Er[c], t5_packu(ss[q][2 * c], ss[q][2 * c + 1]), aRe[c]);
-                    aIm[c] = t5_fma2(Er[c], t5_packu(dsv[q][2 * c], dsv[q][2 * c + 1]), aIm[c]);
-                    aRe[c] = t5_fma2(Ei[c], t5_packu(dd[q][2 * c], dd[q][2 * c + 1]), aRe[c]);
-                    aIm[c] = t5_fma2(Ei[c], t5_packu(sd[q][2 * c], sd[q][2 * c + 1]), aIm[c]);
-                    if (g < 3) {                                              // advance the chain by eight row pairs
-                        const t5_u64 nr = t5_fma2(Ei[c], D8n, t5_mul2(Er[c], D8r));
-                        Ei[c] = t5_fma2(Ei[c], D8r, t5_mul2(Er[c], D8i));
-                        Er[c] = nr;
+                    Er[c] = Sr[c];
+                    Ei[c] = Si[c];
+                }
+                t5_wait(&tmem_full[ty], (uint32_t)(e & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tb = lane_base + (uint32_t)(ty * T5_N + half_id * 32);
+                uint32_t xv[2][8], yv[2][8];
+                t5_ld8(tb, xv[0]);
+                t5_ld8(tb + (uint32_t)T5_RC, yv[0]);
+#pragma unroll
+                for (int g = 0; g < 4; g++) {                                     // eight row pairs each
+                    const int q = g & 1;
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (g < 3) {                                                  // in flight during this group's math
+                        t5_ld8(tb + (uint32_t)((g + 1) * 8), xv[q ^ 1]);
+                        t5_ld8(tb + (uint32_t)(T5_RC + (g + 1) * 8), yv[q ^ 1]);
+                    } else {                                                      // the tile is in registers now
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        t5_arrive(&tmem_empty[ty]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        aP[c] = t5_fma2(Er[c], t5_packu(xv[q][2 * c], xv[q][2 * c + 1]), aP[c]);
+                        aQ[c] = t5_fma2(Ei[c], t5_packu(yv[q][2 * c], yv[q][2 * c + 1]), aQ[c]);
+                        if (g < 3) {                                              // advance the chain by eight row pairs
+                            const t5_u64 nr = t5_fma2(Ei[c], D8n, t5_mul2(Er[c], D8r));
+                            Ei[c] = t5_fma2(Ei[c], D8r, t5_mul2(Er[c], D8i));
+                            Er[c] = nr;
+                        }
                     }
                 }
+                const float sp_ = t5_sum2(t5_add2(t5_add2(aP[0], aP[1]), t5_add2(aP[2], aP[3])));
+                const float sq_ = t5_sum2(t5_add2(t5_add2(aQ[0], aQ[1]), t5_add2(aQ[2], aQ[3])));
+                if (ty == 0) {
+                    t5_dfadd(Vrh, Vrl, sp_);
+                    t5_dfadd(Vih, Vil, sq_);
+                } else {
+                    t5_dfadd(Vih, Vil, sp_);
+                    t5_dfadd(Vrh, Vrl, sq_);
+                }
             }
-            Vr += (double)t5_sum2(t5_add2(t5_add2(aRe[0], aRe[1]), t5_add2(aRe[2], aRe[3])));
-            Vi += (double)t5_sum2(t5_add2(t5_add2(aIm[0], aIm[1]), t5_add2(aIm[2], aIm[3])));
             if (++ch == P.nchunk) {                  // end of this (K tile, plane) pass: combine the two halves
                 ch = 0;
                 const int bar_id = 1 + (warp & 3);   // named barrier of the warp pair (w, w + 4)
-                if (half_id == 1) vx[row] = make_double2(Vr, Vi);
+                if (half_id == 1) vx[row] = make_float4(Vrh, Vrl, Vih, Vil);
                 asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
                 if (half_id == 0 && valid) {
-                    const double2 o2 = vx[row];
-                    const double vr = Vr + o2.x, vi = Vi + o2.y;
+                    const float4 o2 = vx[row];
+                    const double vr = ((double)Vrh + (double)o2.x) + ((double)Vrl + (double)o2.y);
+                    const double vi = ((double)Vih + (double)o2.z) + ((double)Vil + (double)o2.w);
                     double2 *dst = P.part + ((size_t)sp * P.nf + (plane0 + pl)) * (size_t)P.nuvh + kuv;
                     if (kl == 0) *dst = make_double2(vr, vi);
                     else {
@@ -487,10 +528,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                     }
                 }
                 asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                Vr = 0.0;
-                Vi = 0.0;
-                Pr = S0r;
-                Pi = S0i;
+                Vrh = Vrl = Vih = Vil = 0.f;
                 if (++pl == npl) {                   // last chunk of K tile kl: its A buffer is free again
                     pl = 0;
                     if (kl + 2 < nkl) gen_a(kl + 2);
@@ -510,7 +548,7 @@ size_t tc5_operand_bytes(int ny, int nx, int nf)
 {
     const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
     const int nkt = (npx + T5_KT - 1) / T5_KT, nchunk = (npy + T5_RC - 1) / T5_RC;
-    return (size_t)nf * nkt * nchunk * T5_NSUB * T5_CHUNK_BYTES;
+    return (size_t)nf * nkt * nchunk * 2 * T5_NSUB * T5_UNIT_BYTES;
 }
 
 static int tc5_pg(int nf) { return nf < 8 ? nf : 8; }
@@ -550,7 +588,7 @@ int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
     const int nkt = (npx + T5_KT - 1) / T5_KT;
     p.nchunk = (npy + T5_RC - 1) / T5_RC;
     PDSB_REQUIRE(p.nsplit >= 1 && p.nsplit <= nkt, "tc5 split");
-    constexpr size_t smem_bytes = 2 * (size_t)T5_A_BYTES + (size_t)T5_NSTAGE * T5_CHUNK_BYTES;
+    constexpr size_t smem_bytes = (size_t)T5_NSTAGE * T5_UNIT_BYTES;
     static bool attr_set = false;
     if (!attr_set) {
         PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
