@@ -544,27 +544,32 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
 
-    # ---- extra (not part of value / e2e): the experimental tensor-core variant on the same step ----
-    # mma.sync fp16 2-way-split operands (pdspy_b200/csrc/dft_mma.cu, opt-in via pdsb_set_dft_variant(103));
-    # same data flow and outputs, parity 2-5e-7 of max|V| (tests/test_gpu_dft.py).  Reported for context:
-    # the default and the headline stay on the FP32 pipe, as BASELINE.json's north star prescribes.
-    _lib.check(L.pdsb_set_dft_variant(103))
-    for _ in range(2):
-        ll_tc = step_device()
-    barrier()
-    tc_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for e0, e1 in tc_evs:
-        flush.zero_()
-        e0.record()
-        ll_tc = step_device()
-        e1.record()
-    barrier()
-    _lib.check(L.pdsb_set_dft_variant(0))
-    tc_ms = sum(e0.elapsed_time(e1) for e0, e1 in tc_evs)
-    t = torch.tensor([tc_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tc_ms = float(t[0])
+    # ---- extras (not part of value / e2e): the experimental tensor-core variants on the same step ----
+    # 200: tcgen05.mma with TMEM accumulators and a TMEM A operand, bulk-TMA B ring (pdspy_b200/csrc/dft_tc5.cu);
+    # 103: mma.sync m16n8k16 (pdspy_b200/csrc/dft_mma.cu).  Both: fp16 hi+lo split operands, 3 MMAs per product,
+    # fp32 accumulate; same data flow and outputs, parity <= 1.1e-6 of max|V| (tests/test_gpu_dft.py).  Reported
+    # for context: the default and the headline stay on the FP32 pipe, as BASELINE.json's north star prescribes.
+    def time_variant(variant):
+        _lib.check(L.pdsb_set_dft_variant(variant))
+        for _ in range(2):
+            ll_v = step_device()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record()
+            ll_v = step_device()
+            e1.record()
+        barrier()
+        _lib.check(L.pdsb_set_dft_variant(0))
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0]), ll_v
+
+    tc5_ms, ll_tc5 = time_variant(200)
+    tc_ms, ll_tc = time_variant(103)
 
     if rank == 0:
         sm, khz = ctypes.c_int(), ctypes.c_int()
@@ -618,12 +623,18 @@ def main():
                                   "launch (profiles/r01_dft_ncu_c3_default.md, r01_dft_ncu.md); null where not captured",
                 "algorithmic_bytes": float(n) * n * nf * 4 + like.ds.nuv_unique * 16.0 * (1 + nf)},
         }
-        line["extras"] = {"tensor_core_variant": {
-            "what": "same step with the experimental opt-in DFT kernel on the warp-level tensor-core path (mma.sync "
-                    "m16n8k16, fp16 hi+lo split operands, 3 MMAs per product, fp32 accumulate; dft_mma.cu variant 103); "
-                    "NOT used for value / e2e",
-            "ms_per_step": tc_ms / args.steps, "value": pairs_step * args.steps / (tc_ms * 1e-3), "unit": UNIT,
-            "speedup_vs_default": total_ms / tc_ms, "lnlike": ll_tc, "lnlike_rel_diff_vs_default": abs(ll_tc - ll) / abs(ll)}}
+        def tc_entry(what, ms, llv):
+            return {"what": what + "; NOT used for value / e2e", "ms_per_step": ms / args.steps,
+                    "value": pairs_step * args.steps / (ms * 1e-3), "unit": UNIT, "speedup_vs_default": total_ms / ms,
+                    "lnlike": llv, "lnlike_rel_diff_vs_default": abs(llv - ll) / abs(ll)}
+        line["extras"] = {
+            "tensor_core_variant": tc_entry(
+                "same step with the experimental opt-in DFT kernel on the 5th-generation tensor cores (tcgen05.mma, "
+                "accumulators and A operand in TMEM, B through a bulk-TMA ring, warp-specialised; fp16 hi+lo split "
+                "operands, 3 MMAs per product, fp32 accumulate; dft_tc5.cu, pdsb_set_dft_variant(200))", tc5_ms, ll_tc5),
+            "mma_sync_variant": tc_entry(
+                "same step with the experimental opt-in DFT kernel on the warp-level tensor-core path (mma.sync "
+                "m16n8k16, same operand split; dft_mma.cu, pdsb_set_dft_variant(103))", tc_ms, ll_tc)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(cfg)
         emit(line)

@@ -218,7 +218,10 @@ int pdsb_invert_image(const double *g_real, const double *g_imag, const double *
                       int kind, double *image_out);
 
 /* ---- tuning / measurement ----------------------------------------------------------- */
-/* DFT kernel variant: 0 = auto, otherwise an index into the built variants. */
+/* DFT kernel variant: 0 = auto (the FP32-pipe kernel the north star asks for);
+ * 1..22 = FP32-pipe tilings; 100..104 = experimental mma.sync tensor-core kernels; 200 = experimental
+ * tcgen05/TMEM tensor-core kernel.  All variants meet the same 1e-5 parity bound; anything else is
+ * PDSB_ERR_ARG. */
 int pdsb_set_dft_variant(int variant);
 int pdsb_set_dft_split(int nsplit);          /* 0 = auto */
 /* Register-resident FMA microbenchmark on all SMs: variant 0 = FFMA, 1 = FFMA2 (f32x2).

@@ -290,6 +290,12 @@ __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict_
 // ---- the kernel ----
 constexpr int T5_EPI_THREADS = 256;             // warps 0-7
 constexpr int T5_THREADS = T5_EPI_THREADS + 64; // + TMA warp + MMA warp
+// MODE 0: the product.  MODE 1 / 2 exist only when compiled with -DPDSB_TC5_PROBES (variants 201 / 202;
+// timing experiments, results are garbage): 1 = the epilogue warps hand the accumulators straight back,
+// which leaves the TMA + MMA pipeline running alone; 2 = additionally no TMA copies, the MMAs alone.
+// Measured on C3/4 (250k uv): full kernel 7.66 ms, MODE 1 7.22 ms, MODE 2 7.23 ms -> the kernel is bound by
+// the tcgen05.mma rate itself (~82 cycles per 128x128x16 TS-mode MMA against the 64-cycle floor).
+template <int MODE>
 __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams P, const unsigned char *__restrict__ Bg,
                                                                 int nkt, int pg)
 {
@@ -343,8 +349,11 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                 if (it >= T5_NSTAGE) t5_wait(&empty_bar[st], (uint32_t)((it / T5_NSTAGE - 1) & 1));
                 const unsigned char *src =
                     Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)ncs + cs) * T5_UNIT_BYTES;
-                t5_expect_tx(&full_bar[st], T5_UNIT_BYTES);
-                t5_tma(Bs + (size_t)st * T5_UNIT_BYTES, src, T5_UNIT_BYTES, &full_bar[st]);
+                if (MODE >= 2) t5_arrive(&full_bar[st]);         // no copy: the MMAs read whatever is in the stage
+                else {
+                    t5_expect_tx(&full_bar[st], T5_UNIT_BYTES);
+                    t5_tma(Bs + (size_t)st * T5_UNIT_BYTES, src, T5_UNIT_BYTES, &full_bar[st]);
+                }
                 if (++cs == ncs) {
                     cs = 0;
                     if (++pl == npl) {
@@ -476,24 +485,25 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                 t5_wait(&tmem_full[ty], (uint32_t)(e & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tb = lane_base + (uint32_t)(ty * T5_N + half_id * 32);
-                uint32_t xv[2][8], yv[2][8];
-                t5_ld8(tb, xv[0]);
-                t5_ld8(tb + (uint32_t)T5_RC, yv[0]);
+                // the whole tile goes to registers first so that the accumulator is handed back to the tensor
+                // core after the TMEM load latency only, not after this thread's arithmetic
+                uint32_t xv[32], yv[32];
+                if (MODE >= 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    t5_arrive(&tmem_empty[ty]);
+                    continue;
+                }
+                t5_ld32(tb, xv);
+                t5_ld32(tb + (uint32_t)T5_RC, yv);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                t5_arrive(&tmem_empty[ty]);
 #pragma unroll
                 for (int g = 0; g < 4; g++) {                                     // eight row pairs each
-                    const int q = g & 1;
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (g < 3) {                                                  // in flight during this group's math
-                        t5_ld8(tb + (uint32_t)((g + 1) * 8), xv[q ^ 1]);
-                        t5_ld8(tb + (uint32_t)(T5_RC + (g + 1) * 8), yv[q ^ 1]);
-                    } else {                                                      // the tile is in registers now
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        t5_arrive(&tmem_empty[ty]);
-                    }
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-                        aP[c] = t5_fma2(Er[c], t5_packu(xv[q][2 * c], xv[q][2 * c + 1]), aP[c]);
-                        aQ[c] = t5_fma2(Ei[c], t5_packu(yv[q][2 * c], yv[q][2 * c + 1]), aQ[c]);
+                        aP[c] = t5_fma2(Er[c], t5_packu(xv[g * 8 + 2 * c], xv[g * 8 + 2 * c + 1]), aP[c]);
+                        aQ[c] = t5_fma2(Ei[c], t5_packu(yv[g * 8 + 2 * c], yv[g * 8 + 2 * c + 1]), aQ[c]);
                         if (g < 3) {                                              // advance the chain by eight row pairs
                             const t5_u64 nr = t5_fma2(Ei[c], D8n, t5_mul2(Er[c], D8r));
                             Ei[c] = t5_fma2(Ei[c], D8r, t5_mul2(Er[c], D8i));
@@ -591,7 +601,11 @@ int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
     constexpr size_t smem_bytes = (size_t)T5_NSTAGE * T5_UNIT_BYTES;
     static bool attr_set = false;
     if (!attr_set) {
-        PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+#ifdef PDSB_TC5_PROBES
+        PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+#endif
         attr_set = true;
     }
     const int64_t uvtiles = (p.nuvh + T5_M - 1) / T5_M;
@@ -599,7 +613,12 @@ int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
     const int pg = tc5_pg(p.nf);
     dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)((p.nf + pg - 1) / pg));
     LaunchScope ls("dft_tc5_tcgen05");
-    dft_tc5_kernel<<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
+#ifdef PDSB_TC5_PROBES
+    if (c.dft_variant == DFT_VARIANT_TC5 + 1) dft_tc5_kernel<1><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
+    else if (c.dft_variant == DFT_VARIANT_TC5 + 2) dft_tc5_kernel<2><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
+    else
+#endif
+        dft_tc5_kernel<0><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }

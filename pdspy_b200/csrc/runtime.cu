@@ -1,5 +1,6 @@
 // libpdsb runtime: context, stream, buffers, timing, profiling, FMA microbenchmark.
 #include "common.cuh"
+#include "dft.cuh"
 
 namespace pdsb {
 
@@ -584,6 +585,12 @@ int pdsb_launch_count(int64_t *count)
 
 int pdsb_set_dft_variant(int variant)
 {
+    bool ok = variant == 0 || (variant >= 1 && variant <= dft_variant_count()) ||
+              (variant >= DFT_VARIANT_MMA && variant <= DFT_VARIANT_MMA + 4) || variant == DFT_VARIANT_TC5;
+#ifdef PDSB_TC5_PROBES
+    ok = ok || variant == DFT_VARIANT_TC5 + 1 || variant == DFT_VARIANT_TC5 + 2;
+#endif
+    PDSB_REQUIRE(ok, "unknown DFT kernel variant");
     ctx().dft_variant = variant;
     return PDSB_OK;
 }

@@ -61,7 +61,7 @@ def test_parity_small_shapes(gpu, ny, nx, nf, nuv, herm):
     assert relerr(vis, ref) < TOL
 
 
-@pytest.mark.parametrize("variant", list(range(1, 23)) + [100, 101, 102, 103, 104])
+@pytest.mark.parametrize("variant", list(range(1, 23)) + [100, 101, 102, 103, 104, 200])
 @pytest.mark.parametrize("split", [1, 3])
 def test_every_kernel_variant_and_split(gpu, variant, split):
     gpu.pdsb_set_dft_variant(variant)
@@ -71,6 +71,30 @@ def test_every_kernel_variant_and_split(gpu, variant, split):
     ref = od.exact_dft(u, v, m.image, 0.05 * A, -0.11 * A, 0.07 * A)
     vis = interpolate_model(u, v, m.freq, m, dRA=-0.11, dDec=0.07)
     assert relerr(vis, ref) < TOL
+
+
+@pytest.mark.parametrize("shape", [(100, 400, 2, 300), (257, 129, 9, 131), (64, 64, 1, 1), (40, 520, 1, 700)])
+@pytest.mark.parametrize("split", [1, 0])
+def test_tcgen05_variant_shapes(gpu, shape, split):
+    """The tcgen05/TMEM kernel (variant 200) on shapes that exercise its pipeline: four and more K tiles
+    per CTA (A-operand double buffer reuse), plane groups (nf > 8), odd sizes (self-mirrored row / column),
+    uv counts that do not fill a 128-row tile, and a K-split grid."""
+    ny, nx, nf, nuv = shape
+    gpu.pdsb_set_dft_variant(200)
+    gpu.pdsb_set_dft_split(split)
+    rng = np.random.default_rng(ny * 7 + nx)
+    img = rng.random((ny, nx, nf, 1))
+    m = synth.SynthImage(img, 0.05, synth.synth_freq(nf))
+    u, v = rng.normal(0, 4e5, nuv), rng.normal(0, 4e5, nuv)
+    ref = od.exact_dft(u, v, img, 0.05 * A, 0.02 * A, -0.04 * A)
+    vis = interpolate_model(u, v, m.freq, m, dRA=0.02, dDec=-0.04)
+    assert relerr(vis, ref) < TOL
+
+
+def test_unknown_variant_is_rejected(gpu):
+    assert gpu.pdsb_set_dft_variant(23) != 0
+    assert gpu.pdsb_set_dft_variant(201) != 0
+    assert gpu.pdsb_set_dft_variant(0) == 0
 
 
 def test_against_literal_oracle_on_the_reference_fixture(gpu, fixture720):
