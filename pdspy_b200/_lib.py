@@ -112,6 +112,10 @@ def lib():
         dev = int(os.environ.get("PDSB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         check(L.pdsb_init(dev))
         _inited = True
+        kernel = os.environ.get("PDSPY_B200_DFT", "")          # initial DFT kernel: fp32 (default) | mma | tcgen05 | <int>
+        if kernel:
+            variants = {"fp32": 0, "mma": 103, "tcgen05": 200}
+            check(L.pdsb_set_dft_variant(variants[kernel] if kernel in variants else int(kernel)))
     return L
 
 

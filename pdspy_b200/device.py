@@ -109,3 +109,18 @@ def clear_cache():
     while _CACHE:
         _, (_, ds) = _CACHE.popitem()
         ds.destroy()
+
+
+DFT_KERNELS = {"fp32": 0, "mma": 103, "tcgen05": 200}
+
+
+def set_dft_kernel(kind="fp32"):
+    """Select the DFT kernel every later interpolate_model / likelihood call runs.
+
+    "fp32" (default): the FP32-pipe kernel of BASELINE.json's north star.  "tcgen05" / "mma": the
+    experimental tensor-core kernels (fp16 hi+lo split operands, same 1e-5 parity bound).
+    An int is passed to pdsb_set_dft_variant unchanged.  The environment variable PDSPY_B200_DFT
+    sets the initial choice."""
+    variant = DFT_KERNELS[kind] if isinstance(kind, str) else int(kind)
+    _lib.check(_lib.lib().pdsb_set_dft_variant(variant))
+    return variant
