@@ -209,6 +209,14 @@ int pdsb_center(const double *u, const double *v, const double *freq, const doub
                 int64_t nuv, int nf, double mean_freq, double x0_rad, double y0_rad, int kind,
                 double *out_real, double *out_imag);
 
+/* Channel post-processing of a model cube before interpolate_model
+ * (pdspy/modeling/run_flared_model.py:308-366): mean over blocks of `subsample` sub-channels, optional
+ * Hanning smoothing along the channel axis (numpy.hanning(5)/sum, zero-padded, mode="same"), mean over
+ * blocks of `averaging` channels.  image [npix, nf_in] (the [ny,nx,nf,1] cube or an unstructured
+ * [npts,nf] image), out [npix, nf_in/subsample/averaging]; both host or both device (`kind`). */
+int pdsb_channel_postprocess(const double *image, int64_t npix, int nf_in, int subsample, int hanning,
+                             int averaging, int kind, double *out);
+
 /* invert(): the per-channel image synthesis of pdspy/interferometry/invert.py:63-84 from gridded
  * visibilities (grid(..., imaging=True)): g_real, g_imag [imsize*imsize, nch]; conv [imsize, imsize] =
  * conv_func(u, v, binsize, binsize) of :94-121 evaluated by the caller on the grid; image_out

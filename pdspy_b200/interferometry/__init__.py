@@ -5,3 +5,4 @@ from .interpolate_model import interpolate_model, model_visibilities, loglike_im
 from .grid import grid, freqcorrect, chisq
 from .average import average, center
 from .invert import invert
+from .cube import postprocess_channels

@@ -14,6 +14,7 @@ from ..constants import arcsec
 from .. import _lib
 from ..device import dataset_for
 from .visibilities import Visibilities
+from .cube import postprocess_channels_device
 
 
 def _cube(model):
@@ -71,13 +72,26 @@ def _mods(nf, flux_unc, extinction, freefree, dRA, dDec):
     return scale, ff, float(dRA * arcsec), float(dDec * arcsec)
 
 
-def model_visibilities(u, v, freq, model, dRA=0., dDec=0., flux_unc=1.0, extinction=None, freefree=None):
-    """interpolate_model plus the host passes the reference wraps around it, in one device pass:
-    image *= flux_unc (run_disk_model.py:319), image[:,:,i] *= extinction[i] (run_flared_model.py:286-299),
-    real += point-source free-free flux at (dRA, dDec) (run_disk_model.py:329-334).  Returns Visibilities."""
-    dxy = (model.x[1] - model.x[0]) * arcsec
+def _staged_cube(model, subsample, averaging, hanning):
+    """(pointer, kind, ny, nx, nf, keepalive) of the cube the transform reads: the host cube as is, or, when
+    channel post-processing is asked for, its post-processed copy left on the device."""
     image = _cube(model)
     ny, nx, nf = image.shape[:3]
+    if subsample * averaging > 1 or hanning:                  # run_flared_model.py:308-309
+        buf, nf = postprocess_channels_device(image, subsample, averaging, hanning)
+        return _lib.ptr(buf), _lib.DEVICE, ny, nx, nf, buf
+    return _lib.ptr(image), _lib.HOST, ny, nx, nf, image
+
+
+def model_visibilities(u, v, freq, model, dRA=0., dDec=0., flux_unc=1.0, extinction=None, freefree=None,
+                       subsample=1, averaging=1, hanning=False):
+    """interpolate_model plus the host passes the reference wraps around it, in one device pass:
+    image *= flux_unc (run_disk_model.py:319), image[:,:,i] *= extinction[i] (run_flared_model.py:286-299),
+    the sub-sample mean / Hanning smoothing / channel binning of run_flared_model.py:308-366 (`freq` is then
+    the data's channel list, as there), real += point-source free-free flux at (dRA, dDec)
+    (run_disk_model.py:329-334).  Returns Visibilities."""
+    dxy = (model.x[1] - model.x[0]) * arcsec
+    image, image_kind, ny, nx, nf, _keep = _staged_cube(model, subsample, averaging, hanning)
     u = numpy.ascontiguousarray(u, dtype=numpy.float64)
     v = numpy.ascontiguousarray(v, dtype=numpy.float64)
     ds = dataset_for(u, v)
@@ -85,25 +99,25 @@ def model_visibilities(u, v, freq, model, dRA=0., dDec=0., flux_unc=1.0, extinct
     scale, ff, x0, y0 = _mods(nf, flux_unc, extinction, freefree, dRA, dDec)
     if u.size > 0:
         L = _lib.lib()
-        _lib.check(L.pdsb_sample_image_ex(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST, float(dxy), x0, y0,
+        _lib.check(L.pdsb_sample_image_ex(ds.handle, image, ny, nx, nf, image_kind, float(dxy), x0, y0,
                                           _lib.ptr(scale), ff, x0, y0, _lib.ptr(real), _lib.ptr(imag), _lib.HOST))
     return Visibilities(u, v, freq, real, imag, numpy.ones(real.shape))
 
 
-def loglike_image(data, model, dRA=0., dDec=0., flux_unc=1.0, extinction=None, freefree=None):
+def loglike_image(data, model, dRA=0., dDec=0., flux_unc=1.0, extinction=None, freefree=None,
+                  subsample=1, averaging=1, hanning=False):
     """Fused interpolate_model + visibility log-likelihood term (pdspy/utils/emcee.py:31-43) for
     one dataset: the model visibilities never leave the GPU.  `data` is a Visibilities with
     u, v, real, imag, weights; `model` an Image.  flux_unc / extinction / freefree as in
-    model_visibilities.  Returns (lnlike, chi2_per_channel)."""
+    model_visibilities (as are subsample / averaging / hanning).  Returns (lnlike, chi2_per_channel)."""
     dxy = (model.x[1] - model.x[0]) * arcsec
-    image = _cube(model)
-    ny, nx, nf = image.shape[:3]
+    image, image_kind, ny, nx, nf, _keep = _staged_cube(model, subsample, averaging, hanning)
     ds = dataset_for(data.u, data.v, (data.real, data.imag, data.weights))
     chi2 = numpy.empty(nf)
     out = ctypes.c_double()
     scale, ff, x0, y0 = _mods(nf, flux_unc, extinction, freefree, dRA, dDec)
     L = _lib.lib()
-    _lib.check(L.pdsb_loglike_ex(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST, float(dxy), x0, y0,
+    _lib.check(L.pdsb_loglike_ex(ds.handle, image, ny, nx, nf, image_kind, float(dxy), x0, y0,
                                  _lib.ptr(scale), ff, x0, y0, _lib.ptr(chi2),
                                  ctypes.cast(ctypes.byref(out), ctypes.c_void_p)))
     return out.value, chi2

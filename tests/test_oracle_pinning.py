@@ -147,3 +147,17 @@ def test_center_oracle_vs_reference_python_golden(average_golden):
     cr, ci = oa.center(u, v, freq, re, im, 0.31, -0.17)
     np.testing.assert_array_equal(cr, average_golden["center/real"])
     np.testing.assert_array_equal(ci, average_golden["center/imag"])
+
+
+@pytest.mark.parametrize("subsample,averaging,hanning", [(1, 1, True), (3, 1, False), (2, 2, True), (1, 4, False), (5, 1, True)])
+def test_channel_postprocess_oracle_vs_reference_expressions(subsample, averaging, hanning):
+    """oracle/cube.py against the reference's own expression sequence (run_flared_model.py:311-339, with
+    scipy.signal.fftconvolve); 1e-13 of the cube maximum (the FFT convolution is not exact)."""
+    from oracle import cube as oc
+    nfd = 6
+    rng = np.random.default_rng(subsample * 10 + averaging)
+    img = rng.random((9, 9, nfd * averaging * subsample, 1))
+    lit = oc.literal(img, nfd, subsample, averaging, hanning)
+    got = oc.post(img[:, :, :, 0], subsample, averaging, hanning)
+    assert got.shape == (9, 9, nfd)
+    assert np.abs(got - lit[:, :, :, 0]).max() < 1e-13 * img.max()
