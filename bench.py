@@ -549,11 +549,14 @@ def main():
     # 103: mma.sync m16n8k16 (pdspy_b200/csrc/dft_mma.cu).  Both: fp16 hi+lo split operands, 3 MMAs per product,
     # fp32 accumulate; same data flow and outputs, parity <= 1.1e-6 of max|V| (tests/test_gpu_dft.py).  Reported
     # for context: the default and the headline stay on the FP32 pipe, as BASELINE.json's north star prescribes.
-    def time_variant(variant):
+    def time_variant(variant, prefix):
+        """(device-resident ms, e2e seconds, DFT-kernel ms from in-library events, lnlike) over args.steps steps."""
         _lib.check(L.pdsb_set_dft_variant(variant))
         for _ in range(2):
             ll_v = step_device()
         barrier()
+        _lib.check(L.pdsb_profile_reset())
+        _lib.check(L.pdsb_profile_enable(1))
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         for e0, e1 in evs:
             flush.zero_()
@@ -561,15 +564,25 @@ def main():
             ll_v = step_device()
             e1.record()
         barrier()
+        _lib.check(L.pdsb_profile_enable(0))
+        k_ms, k_n = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(L.pdsb_profile_get(prefix, ctypes.byref(k_ms), ctypes.byref(k_n)))
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        e2e = time.perf_counter() - t0
         _lib.check(L.pdsb_set_dft_variant(0))
         ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([ms, e2e, k_ms.value], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt[0]), ll_v
+        return float(tt[0]), float(tt[1]), float(tt[2]) / max(1, k_n.value), ll_v
 
-    tc5_ms, ll_tc5 = time_variant(200)
-    tc_ms, ll_tc = time_variant(103)
+    tc5_ms, tc5_e2e_s, tc5_kernel_ms, ll_tc5 = time_variant(200, b"dft_tc5")
+    tc_ms, tc_e2e_s, tc_kernel_ms, ll_tc = time_variant(103, b"dft_mma")
 
     if rank == 0:
         sm, khz = ctypes.c_int(), ctypes.c_int()
@@ -623,18 +636,32 @@ def main():
                                   "launch (profiles/r01_dft_ncu_c3_default.md, r01_dft_ncu.md); null where not captured",
                 "algorithmic_bytes": float(n) * n * nf * 4 + like.ds.nuv_unique * 16.0 * (1 + nf)},
         }
-        def tc_entry(what, ms, llv):
+        def tc_entry(what, ms, e2e_s_, kernel_ms, llv, peak_key):
+            # the tensor cores execute 3 fp16 MACs (hi*hi, hi*lo, lo*hi) per pixel-visibility pair actually
+            # evaluated (the Hermitian half of the list, per rank)
+            macs = 3.0 * float(n) * n * nf * like.ds.nuv_unique
+            ach = 2.0 * macs / (kernel_ms * 1e-3) / 1e12
+            peak = peaks.get(peak_key)
             return {"what": what + "; NOT used for value / e2e", "ms_per_step": ms / args.steps,
                     "value": pairs_step * args.steps / (ms * 1e-3), "unit": UNIT, "speedup_vs_default": total_ms / ms,
+                    "e2e": {"value": pairs_step * args.steps / e2e_s_, "unit": UNIT, "ms_per_step": e2e_s_ / args.steps * 1e3,
+                            "h2d_bytes_per_step": int(cube.nbytes), "d2h_bytes_per_step": 8 * (nf + 1)},
+                    "roofline": {"bound": "tensor", "kernel_ms": kernel_ms, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                                 "frac": ach / peak if peak else None,
+                                 "peak_source": "MEASURED_PEAKS.json %s (cuBLAS bf16 GEMM, sustained figure: kernel timed "
+                                                "inside a long step)" % peak_key,
+                                 "counts": "2 flop x 3 split-product MACs per evaluated pixel-visibility pair, per rank"},
                     "lnlike": llv, "lnlike_rel_diff_vs_default": abs(llv - ll) / abs(ll)}
         line["extras"] = {
             "tensor_core_variant": tc_entry(
                 "same step with the experimental opt-in DFT kernel on the 5th-generation tensor cores (tcgen05.mma, "
                 "accumulators and A operand in TMEM, B through a bulk-TMA ring, warp-specialised; fp16 hi+lo split "
-                "operands, 3 MMAs per product, fp32 accumulate; dft_tc5.cu, pdsb_set_dft_variant(200))", tc5_ms, ll_tc5),
+                "operands, 3 MMAs per product, fp32 accumulate; dft_tc5.cu, pdsb_set_dft_variant(200))",
+                tc5_ms, tc5_e2e_s, tc5_kernel_ms, ll_tc5, "bf16_tflops_sustained"),
             "mma_sync_variant": tc_entry(
                 "same step with the experimental opt-in DFT kernel on the warp-level tensor-core path (mma.sync "
-                "m16n8k16, same operand split; dft_mma.cu, pdsb_set_dft_variant(103))", tc_ms, ll_tc)}
+                "m16n8k16, same operand split; dft_mma.cu, pdsb_set_dft_variant(103))",
+                tc_ms, tc_e2e_s, tc_kernel_ms, ll_tc, "bf16_tflops_sustained")}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_port(cfg)
         emit(line)
