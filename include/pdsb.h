@@ -225,6 +225,24 @@ int pdsb_channel_postprocess(const double *image, int64_t npix, int nf_in, int s
 int pdsb_invert_image(const double *g_real, const double *g_imag, const double *conv, int imsize, int nch,
                       int kind, double *image_out);
 
+/* clean(): the Hogbom loop of pdspy/interferometry/clean.py:51-106 and the restore step :108-113.
+ * Images are [ny, nx, nf] (the reference's image[:, :, :, 0]), beams [2ny, 2nx, nf]; all host or all
+ * device (`kind`).
+ *   pdsb_mad_std: astropy.stats.mad_std = 1.482602218505602 * median(|x - median(x)|), exact order
+ *       statistics (numpy.median's mean of the two middle elements for even n); no NaN handling.
+ *   pdsb_clean_loop: `dirty` in: dirty image, out: residuals.  beam_resid_max = (dirty_beam -
+ *       clean_beam).max() (:57).  Writes model and mask (0/1), the iteration count and the last mask
+ *       threshold.  Exactly equal maxima are resolved to the first in C order; the loop ends when
+ *       nothing positive is left under the mask (the reference would select every unmasked pixel).
+ *   pdsb_clean_restore: clean_image = fftconvolve(model, clean_beam, mode="same") + residuals as the
+ *       direct sum over the non-zero model components in index order. */
+int pdsb_mad_std(const double *x, int64_t n, int kind, double *out);
+int pdsb_clean_loop(double *dirty, const double *dirty_beam, int ny, int nx, int nf, double beam_resid_max,
+                    double gain, int maxiter, double nsigma, int kind, double *model, double *mask, int *niter,
+                    double *threshold_out);
+int pdsb_clean_restore(const double *model, const double *clean_beam, const double *residuals, int ny, int nx,
+                       int nf, int kind, double *clean_image);
+
 /* ---- tuning / measurement ----------------------------------------------------------- */
 /* DFT kernel variant: 0 = auto (the FP32-pipe kernel the north star asks for);
  * 1..22 = FP32-pipe tilings; 100..104 = experimental mma.sync tensor-core kernels; 200 = experimental

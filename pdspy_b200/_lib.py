@@ -73,6 +73,10 @@ SIGNATURES = {
     "pdsb_center": [_P, _P, _P, _P, _P, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_int, _P, _P],
     "pdsb_channel_postprocess": [_P, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "pdsb_invert_image": [_P, _P, _P, _c_int, _c_int, _c_int, _P],
+    "pdsb_mad_std": [_P, _c_i64, _c_int, ctypes.POINTER(_c_dbl)],
+    "pdsb_clean_loop": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _c_dbl, _c_int, _P, _P,
+                        ctypes.POINTER(_c_int), ctypes.POINTER(_c_dbl)],
+    "pdsb_clean_restore": [_P, _P, _P, _c_int, _c_int, _c_int, _c_int, _P],
     "pdsb_set_dft_variant": [_c_int],
     "pdsb_set_dft_split": [_c_int],
     "pdsb_bench_fma": [_c_int, _c_int, ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_dbl)],

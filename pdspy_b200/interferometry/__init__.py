@@ -6,3 +6,4 @@ from .grid import grid, freqcorrect, chisq
 from .average import average, center
 from .invert import invert
 from .cube import postprocess_channels
+from .clean import clean

@@ -130,6 +130,43 @@ def load_reference_invert(ref):
     return importlib.import_module("pdspy.interferometry.invert")
 
 
+CLEAN_CASES = {
+    "fx_expsinc_64": dict(imsize=64, pixel_size=1.0, convolution="expsinc", maxiter=60),
+    "fx_pillbox_robust_64": dict(imsize=64, pixel_size=0.5, convolution="pillbox", maxiter=60, weighting="robust",
+                                 robust=0.5),
+    "two_sources_line_32": dict(imsize=32, pixel_size=0.5, convolution="expsinc", maxiter=40, mode="spectralline",
+                                gain=0.2, nsigma=4.),
+}
+
+
+def two_source_set():
+    """Two point sources with different spectra plus noise, 2 channels (for clean() in spectral-line mode)."""
+    rng = np.random.default_rng(777)
+    n = 3000
+    u, v = rng.normal(0, 6e4, n), rng.normal(0, 6e4, n)
+    freq = 230e9 + 1e8 * np.arange(2)
+    vis = np.zeros((n, 2), dtype=complex)
+    for (x0, y0), flux in (((1.5, -2.0), (1.0, 0.4)), ((-3.0, 1.0), (0.5, 0.8))):
+        ph = np.exp(-2j * np.pi * (u * x0 * ARCSEC + v * y0 * ARCSEC))
+        vis += ph[:, None] * np.array(flux)[None, :]
+    vis += 0.3 * (rng.normal(size=vis.shape) + 1j * rng.normal(size=vis.shape))
+    return u, v, freq, vis.real.copy(), vis.imag.copy(), np.ones((n, 2))
+
+
+def load_reference_clean(ref):
+    """The reference's own clean.py; astropy.stats.mad_std (astropy is absent) is supplied from its
+    definition (oracle/clean.py:mad_std)."""
+    import importlib
+    import types
+    from oracle import clean as ocl
+    load_reference_invert(ref)
+    st = types.ModuleType("astropy.stats")
+    st.mad_std = ocl.mad_std
+    sys.modules.setdefault("astropy", types.ModuleType("astropy"))
+    sys.modules["astropy.stats"] = st
+    return importlib.import_module("pdspy.interferometry.clean")
+
+
 def sparse(a):
     """(indices, values) of the non-zero cells; sub-sampled for the dense expsinc maps so the
     committed file stays small.  The count and the plain sum of all non-zero cells are stored
@@ -206,6 +243,26 @@ def main():
         iv[name + "/stats"] = np.array([im.sum(), im.max(), im.min(), np.abs(im).sum()])
         iv[name + "/x"] = r.x
     np.savez_compressed(os.path.join(HERE, "invert_golden.npz"), **iv)
+
+    # clean() of the reference (clean.py + invert.py + scipy fftconvolve / leastsq) on the fixture and on a
+    # two-channel synthetic set: the loop's inputs (dirty image, dirty beam) and all its outputs
+    cl = load_reference_clean(ref)
+    cg = {}
+    for name, kw in CLEAN_CASES.items():
+        def fresh():
+            a = two_source_set() if name.startswith("two") else [fx[k] for k in ("u", "v", "freq", "real", "imag", "weights")]
+            return ref.Visibilities(*[np.array(x, dtype=np.float64) for x in a])
+        with contextlib.redirect_stdout(io.StringIO()):
+            ci, res, beam, model, mask = cl.clean(fresh(), **kw)
+            inv_kw = {k: v for k, v in kw.items() if k not in ("maxiter", "gain", "nsigma")}
+            dirty = inv.invert(fresh(), **inv_kw)
+        cg[name + "/dirty"] = dirty.image[:, :, :, 0]
+        cg[name + "/dirty_beam"] = beam.image[:, :, :, 0]
+        cg[name + "/clean_image"] = ci.image[:, :, :, 0]
+        cg[name + "/residuals"] = res.image[:, :, :, 0]
+        cg[name + "/model"] = model.image[:, :, :, 0]
+        cg[name + "/mask"] = mask.image[:, :, :, 0]
+    np.savez_compressed(os.path.join(HERE, "clean_golden.npz"), **cg)
 
     # chisq of the live reference (channel 0, float return)
     rng = np.random.default_rng(99)

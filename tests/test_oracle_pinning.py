@@ -161,3 +161,22 @@ def test_channel_postprocess_oracle_vs_reference_expressions(subsample, averagin
     got = oc.post(img[:, :, :, 0], subsample, averaging, hanning)
     assert got.shape == (9, 9, nfd)
     assert np.abs(got - lit[:, :, :, 0]).max() < 1e-13 * img.max()
+
+
+@pytest.mark.parametrize("name", ["fx_expsinc_64", "fx_pillbox_robust_64", "two_sources_line_32"])
+def test_clean_oracle_vs_reference_clean_golden(name):
+    """oracle/clean.py:loop against outputs of the reference's own clean.py (scipy fftconvolve, leastsq;
+    tests/golden/make_golden.py) from the same dirty image and beam."""
+    from make_golden import CLEAN_CASES
+    from oracle import clean as ocl
+    from pdspy_b200.interferometry.clean import fit_clean_beam
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clean_golden.npz"))
+    kw = CLEAN_CASES[name]
+    cb = fit_clean_beam(g[name + "/dirty_beam"])
+    ci, res, model, mask, n, thr = ocl.loop(g[name + "/dirty"], g[name + "/dirty_beam"], cb, gain=kw.get("gain", 0.1),
+                                            maxiter=kw["maxiter"], nsigma=kw.get("nsigma", 5.))
+    assert n > 5 and np.count_nonzero(model) >= 2
+    assert np.array_equal(mask, g[name + "/mask"])
+    peak = np.abs(g[name + "/clean_image"]).max()
+    for got, key in ((ci, "clean_image"), (res, "residuals"), (model, "model")):
+        assert np.abs(got - g[name + "/" + key]).max() < 1e-14 * peak, key
