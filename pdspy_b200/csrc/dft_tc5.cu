@@ -213,9 +213,11 @@ __device__ __forceinline__ float t5_sum2(t5_u64 a)
     return lo + hi;
 }
 // Phases are kept as 64-bit fixed-point fractions of a turn (2^64 = one turn): H = frac(f / 2) so that the
-// phase of a pixel at half-integer offset n/2 is n * H (mod 2^64), exactly, in integer arithmetic.  The
-// plain-CUDA-core fp64 rate of this GPU is ~1/64 of fp32 (measured: DADD was 35% of all stall samples of
-// an earlier version), so nothing in the steady state may touch fp64.
+// phase of a pixel at half-integer offset n/2 is n * H (mod 2^64), exactly, in integer arithmetic.
+// Nothing in the steady state touches fp64: a dense DFMA stream runs at 33.8 TFLOP/s on this GPU
+// (pdsb_bench_fma variant 13), but the handful of fp64 instructions per accumulator round an earlier
+// version had (two DADD + four DMUL/DFMA per thread) drew 35 % of all stall samples as
+// math_pipe_throttle -- sparse use of the fp64 pipe is far more expensive than its peak rate suggests.
 __device__ __forceinline__ unsigned long long t5_fix(double f)
 {
     double h = 0.5 * f;

@@ -158,6 +158,26 @@ __global__ void __launch_bounds__(256) fma_bench_kernel(float *out, int iters, f
     }
 }
 
+// fp64: 16 independent DFMA chains per thread (variant 13) -- measures the plain CUDA-core fp64 rate
+__global__ void __launch_bounds__(256) dfma_bench_kernel(float *out, int iters, float seed)
+{
+    constexpr int NCH = 16;
+    const double m = 1.0 + seed * 1e-12, b = seed * 1e-12;
+    double acc[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) acc[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int i = 0; i < NCH; i++) acc[i] = fma(acc[i], m, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+}
+
 // Pattern microbenchmarks for the DFT inner loop: acc[q][c] = fma2(x[c][t], trig[q][t], acc[q][c])
 // with the image operand x either register-resident (MODE 0) or re-loaded from shared memory by a
 // warp-broadcast LDS.128 every row (MODE 1).  UVT uv points per thread, TP trig pairs.
@@ -657,6 +677,10 @@ int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms_out)
                     mma_f16_bench_kernel<<<blocks, 256, 0, c.stream>>>(o, iters, 1.0f);
                     threads = 256;
                     fmas_per_thread_iter = 4.0 * 8.0 * (16.0 * 8.0 * 16.0) / 32.0;
+                    break;
+                case 13:
+                    dfma_bench_kernel<<<blocks, 256, 0, c.stream>>>(o, iters, 1.0f);
+                    threads = 256;
                     break;
                 default: set_error("unknown fma bench variant %d", variant); return PDSB_ERR_ARG;
             }
