@@ -37,7 +37,11 @@ def test_profile_and_launch_count(gpu):
     _lib.check(gpu.pdsb_profile_enable(1))
     c = synth.make_config("C1", nuv=4096)
     from pdspy_b200.interferometry import interpolate_model
-    interpolate_model(c["u"], c["v"], c["freq"], c["model"])
+    _lib.check(gpu.pdsb_set_dft_variant(11))        # the FP32-pipe kernel: the launch list below is its
+    try:
+        interpolate_model(c["u"], c["v"], c["freq"], c["model"])
+    finally:
+        _lib.check(gpu.pdsb_set_dft_variant(0))
     ms, cnt = ctypes.c_double(), ctypes.c_int64()
     _lib.check(gpu.pdsb_profile_get(b"dft_", ctypes.byref(ms), ctypes.byref(cnt)))
     assert cnt.value == 1 and ms.value > 0
