@@ -495,8 +495,12 @@ def main():
     def step_device():
         return like(dcube, dxy, dra, ddec, kind=_lib.DEVICE, shape=(n, n))
 
+    # end to end: on several GPUs every rank uploads its 1/world slab of the host cube and the slabs are
+    # all-gathered over NVLink (ShardedLikelihood.stage_cube); on one GPU the cube is uploaded whole
+    shard_upload = world > 1 and n % world == 0
+
     def step_e2e():
-        return like(pinned.array, dxy, dra, ddec, kind=_lib.HOST)
+        return like(pinned.array, dxy, dra, ddec, kind=_lib.HOST, cube="sharded" if shard_upload else None)
 
     # ---- device-resident leg: `value` ----
     for _ in range(args.warmup):
@@ -611,9 +615,12 @@ def main():
             "likelihood_evals_per_s": args.steps / (total_ms * 1e-3),
             "lnlike": ll,
             "e2e": {"value": pairs_step * args.steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": int(cube.nbytes), "d2h_bytes_per_step": int((nf + 1) * 8),
+                    "h2d_bytes_per_step": int(cube.nbytes) if shard_upload or world == 1 else int(cube.nbytes) * world,
+                    "d2h_bytes_per_step": int((nf + 1) * 8) * world,
+                    "h2d_bytes_per_step_per_rank": int(cube.nbytes) // world if shard_upload else int(cube.nbytes),
                     "ms_per_step": e2e_s / args.steps * 1e3, "likelihood_evals_per_s": args.steps / e2e_s,
-                    "api": "pdspy_b200.dist.ShardedLikelihood.__call__ (host fp64 cube in, host scalar out)",
+                    "api": "pdspy_b200.dist.ShardedLikelihood.__call__ (host fp64 cube in, host scalar out" +
+                           ("; each rank uploads 1/%d of the cube, NCCL all-gather over NVLink)" % world if shard_upload else ")"),
                     "timer": "host wall clock around K synchronous calls, max over ranks"},
             "gpu_launches": int(n1.value - n0.value),
             "clocks": clocks,
@@ -645,7 +652,8 @@ def main():
             return {"what": what + "; NOT used for value / e2e", "ms_per_step": ms / args.steps,
                     "value": pairs_step * args.steps / (ms * 1e-3), "unit": UNIT, "speedup_vs_default": total_ms / ms,
                     "e2e": {"value": pairs_step * args.steps / e2e_s_, "unit": UNIT, "ms_per_step": e2e_s_ / args.steps * 1e3,
-                            "h2d_bytes_per_step": int(cube.nbytes), "d2h_bytes_per_step": 8 * (nf + 1)},
+                            "h2d_bytes_per_step": int(cube.nbytes) if shard_upload or world == 1 else int(cube.nbytes) * world,
+                            "d2h_bytes_per_step": 8 * (nf + 1) * world},
                     "roofline": {"bound": "tensor", "kernel_ms": kernel_ms, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                                  "frac": ach / peak if peak else None,
                                  "peak_source": "MEASURED_PEAKS.json %s (cuBLAS bf16 GEMM, sustained figure: kernel timed "
