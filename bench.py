@@ -390,10 +390,23 @@ def run_walker_batch(args, cfg, rank, local_rank, world):
         step(pinned.array, _lib.HOST)
     barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    # extra (not in value / e2e): the same batch on the opt-in tcgen05 tensor-core kernel
+    lnlike0 = float(out[0])
+    _lib.check(L.pdsb_set_dft_variant(200))
+    step(dcubes, _lib.DEVICE)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(dcubes, _lib.DEVICE)
+    e1.record()
+    barrier()
+    tc_ms = e0.elapsed_time(e1)
+    lnlike0_tc = float(out[0])
+    _lib.check(L.pdsb_set_dft_variant(0))
+    t = torch.tensor([dev_ms, e2e_s, tc_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0]), float(t[1])
+    dev_ms, e2e_s, tc_ms = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         pairs = float(n) * n * cfg["nuv"] * nf * args.walkers * args.steps
         cfgd = describe(cfg, world)
@@ -409,7 +422,14 @@ def run_walker_batch(args, cfg, rank, local_rank, world):
                     "d2h_bytes_per_step": int(nw * nf * 8), "ms_per_step": e2e_s / args.steps * 1e3,
                     "likelihood_evals_per_s": args.walkers * args.steps / e2e_s,
                     "api": "pdsb_loglike_batch (host fp64 cubes in, host lnlike[W] out)"},
-            "gpu_launches": int(n1.value - n0.value), "lnlike0": float(out[0])})
+            "gpu_launches": int(n1.value - n0.value), "lnlike0": lnlike0,
+            "extras": {"tensor_core_variant": {
+                "what": "same batch with the experimental opt-in tcgen05 DFT kernel (pdsb_set_dft_variant(200)); "
+                        "NOT used for value / e2e",
+                "ms_per_step": tc_ms / args.steps, "value": pairs / (tc_ms * 1e-3), "unit": UNIT,
+                "likelihood_evals_per_s": args.walkers * args.steps / (tc_ms * 1e-3),
+                "speedup_vs_default": dev_ms / tc_ms, "lnlike0": lnlike0_tc,
+                "lnlike0_rel_diff_vs_default": abs(lnlike0_tc - lnlike0) / abs(lnlike0)}}})
 
 
 # ------------------------------------------------------------------------------------------

@@ -155,3 +155,28 @@ def test_model_modifiers_fused_into_the_epilogue(gpu):
     a = model_visibilities(c["u"], c["v"], c["freq"], c["model"], dRA=x0, dDec=y0)
     b = interpolate_model(c["u"], c["v"], c["freq"], c["model"], dRA=x0, dDec=y0)
     assert np.array_equal(a.real, b.real) and np.array_equal(a.imag, b.imag)
+
+
+def test_sharded_likelihood_single_rank_and_cube_staging(gpu):
+    """pdspy_b200.dist.ShardedLikelihood on one rank (no process group): equals the fused single call, for the
+    host cube, the device cube and the staged-cube paths (which degenerate to one upload here); the N-rank
+    behaviour is scripts/gpu_dist_cube.py under torchrun and the gloo tests of tests/test_dist.py."""
+    import torch
+    from pdspy_b200 import dist as pdist, DeviceBuffer
+    n, nf, nuv = 96, 2, 3000
+    u, v = synth.synth_uv(nuv, 0.03 * A)
+    re, im, w = synth.synth_data(nuv, nf)
+    data = Visibilities(u, v, synth.synth_freq(nf), re, im, w)
+    img = synth.synth_image(n, nf, 0.03)
+    m = synth.SynthImage(img, 0.03, synth.synth_freq(nf))
+    ll0, _ = loglike_image(data, m, dRA=0.02, dDec=-0.01)
+    try:
+        like = pdist.ShardedLikelihood(pdist.shard_visibilities(data, 0, 1))
+        cube = np.ascontiguousarray(img[:, :, :, 0])
+        dxy = (m.x[1] - m.x[0]) * A
+        vals = [like(cube, dxy, 0.02 * A, -0.01 * A, kind=0, cube=mode) for mode in (None, "sharded", "rank0")]
+        vals.append(like(DeviceBuffer.from_numpy(cube), dxy, 0.02 * A, -0.01 * A, kind=1, shape=(n, n)))
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(gpu.pdsb_reset_stream())
+    assert all(abs(x - ll0) <= 1e-12 * abs(ll0) for x in vals), (vals, ll0)
