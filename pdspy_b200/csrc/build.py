@@ -39,6 +39,7 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "_obj")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("PDSB_NVCC_EXTRA", "").split()          # e.g. -DPDSB_TC5_PROBES for timing experiments
     objs = []
     procs = []
     for src in SOURCES:

@@ -644,6 +644,171 @@ __global__ void __launch_bounds__(GT_THREADS) grid_tile_kernel(GridParams P, int
     }
 }
 
+// Second-generation tile kernel (the one used when the region side is one of the instantiated SIDEs).
+// The region update of one visibility is the outer product  FV[r] * (w, w re, w im) FU[c]  of its two
+// one-dimensional kernel factor rows, zero outside its footprint.  Instead of one thread per region cell
+// testing every visibility against its cell (21 % of the tests hit for expsinc), a "stream" of 16 lanes
+// owns the region COLUMNS and keeps all SIDE rows of the three maps in registers: per visibility each lane
+// reads its three column values and the SIDE row factors (broadcast) from shared memory and issues
+// 3*SIDE dependent-free DFMAs - no branches, no index arithmetic, 5x fewer instructions per visibility.
+// Eight streams per CTA take the staged visibilities round-robin; their private regions are summed
+// through shared memory at the end of the work item and flushed with one fp64 atomic per cell and map.
+// Two launch shapes share the work list: items of more than GT2_LIGHT visibilities (the dense central
+// tiles) run on CTAs of 8 streams, the tens of thousands of sparsely filled outer tiles on one-warp CTAs of
+// 2 streams, whose fixed cost (cross-stream sum, barriers) is a quarter and of which 20+ fit on an SM.
+constexpr int GT2_LIGHT = 128;
+
+template <int SIDE, int NSTREAM>
+__global__ void __launch_bounds__(NSTREAM * 16) grid_tile2_kernel(GridParams P, int mode, int lo, int hi, uint32_t tg,
+                                                                 const uint32_t *__restrict__ keys,
+                                                                 const uint32_t *__restrict__ order,
+                                                                 const uint2 *__restrict__ items,
+                                                                 const uint32_t *__restrict__ nitems,
+                                                                 double *out_re, double *out_im, double *out_w)
+{
+    constexpr int WIDTH = SIDE - 7;                                // footprint width lo + hi + 1
+    constexpr int GT2_THREADS = NSTREAM * 16, GT2_STREAMS = NSTREAM;
+    constexpr int GT2_STAGE = NSTREAM * 8;                         // visibilities staged per round (2 threads each)
+    constexpr int RED_ROWS = (3 * SIDE + 2) / 3;                   // the cross-stream sum reuses s_fu: >= 3*SIDE rows of 16
+    constexpr int FU_ROWS = GT2_STAGE > RED_ROWS ? GT2_STAGE : RED_ROWS;
+    __shared__ __align__(16) double s_fv[GT2_STAGE][16];          // row factors, zero outside the footprint
+    __shared__ __align__(16) double s_fu[FU_ROWS][3][16];         // column factors x (w, w re, w im)
+    if (blockIdx.x >= *nitems) return;
+    const uint2 item = items[blockIdx.x];
+    if (((item.y - item.x) > (uint32_t)GT2_LIGHT) != (NSTREAM > 2)) return;      // the other launch shape's item
+    const uint32_t key = keys[item.x];
+    const uint32_t chan = key / (tg * tg), tile = key % (tg * tg);
+    const int tl = (int)(tile / tg), tm = (int)(tile % tg);
+    const int l0 = tl * 8 - lo, m0 = tm * 8 - lo;                  // region origin
+    const int c = threadIdx.x & 15, stream = threadIdx.x >> 4;
+    const int q = threadIdx.x >> 1, sidev = threadIdx.x & 1;       // staging role: visibility q of the stage, u / v side
+    double aw[SIDE], ar[SIDE], ai[SIDE];
+#pragma unroll
+    for (int r = 0; r < SIDE; r++) aw[r] = ar[r] = ai[r] = 0.0;
+
+    // The staging inputs are gathered through the sort permutation (order -> idx -> u, v, w, re, im, gi,
+    // gj): two dependent global loads.  They are software-pipelined two stages deep - the permutation
+    // entry of stage s+2 and the data of stage s+1 are in flight while stage s is processed.
+    struct Raw {
+        double pos, w, wre, wim;
+        int home;
+    };
+    auto load_idx = [&](uint32_t base) -> int64_t {
+        return base + q < item.y ? (int64_t)order[base + q] : -1;
+    };
+    auto load_raw = [&](int64_t idx) -> Raw {
+        Raw x{0.0, 1.0, 0.0, 0.0, 0};
+        if (idx < 0) return x;
+        const int64_t k = idx / P.nf;
+        x.home = sidev ? (int)P.gj[idx] : (int)P.gi[idx];
+        if (!sidev) {
+            x.w = P.w[idx];
+            x.wre = P.re[idx];
+            x.wim = P.im[idx];
+        }
+        x.pos = __dmul_rn(__dmul_rn(sidev ? P.v[k] : P.u[k], P.freq[idx % P.nf]), P.inv_freq);
+        return x;
+    };
+    int64_t idx_next = load_idx(item.x + GT2_STAGE);
+    Raw cur = load_raw(load_idx(item.x));
+    const double *centres = sidev ? P.vv : P.uu;
+
+    for (uint32_t base = item.x; base < item.y; base += GT2_STAGE) {
+        const int n_here = (int)(item.y - base < GT2_STAGE ? item.y - base : GT2_STAGE);
+        // zero the stage rows (all threads, 16-byte stores)
+        {
+            double2 *z = reinterpret_cast<double2 *>(&s_fv[0][0]);
+            for (int i = threadIdx.x; i < GT2_STAGE * 8; i += GT2_THREADS) z[i] = make_double2(0.0, 0.0);
+            z = reinterpret_cast<double2 *>(&s_fu[0][0][0]);
+            for (int i = threadIdx.x; i < GT2_STAGE * 24; i += GT2_THREADS) z[i] = make_double2(0.0, 0.0);
+        }
+        // next stage's gather, issued before this stage's arithmetic
+        const Raw nxt = load_raw(idx_next);
+        idx_next = load_idx(base + 2 * GT2_STAGE);
+        __syncthreads();
+        // stage: two threads per visibility (u side: the three column rows; v side: the row factors)
+        if (q < n_here) {
+            const int first = cur.home - lo - (sidev ? l0 : m0);   // region row / column of footprint slot 0
+            const double wre = cur.wre * cur.w, wim = cur.wim * cur.w;
+            double g[WIDTH];
+#pragma unroll
+            for (int o = 0; o < WIDTH; o++) {
+                const int cell = cur.home - lo + o;
+                g[o] = 0.0;
+                if (cell >= 0 && cell < P.G) {
+                    if (mode == 0) {
+                        const double d = (cur.pos - centres[cell]) * P.inv_binsize;
+                        // 1/norm goes with the u factor
+                        g[o] = P.conv ? k_exp_sinc_1d(d) * (sidev ? 1.0 : (1. / 2.350016262343186))
+                                      : ((fabs(d) >= 0.5) ? 0.0 : 1.0);
+                    } else
+                        g[o] = 1.0;
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < WIDTH; o++) {
+                if (sidev) s_fv[q][first + o] = g[o];
+                else {
+                    s_fu[q][0][first + o] = g[o] * cur.w;
+                    s_fu[q][1][first + o] = g[o] * wre;
+                    s_fu[q][2][first + o] = g[o] * wim;
+                }
+            }
+        }
+        cur = nxt;
+        __syncthreads();
+        for (int v = stream; v < n_here; v += GT2_STREAMS) {
+            const double fw = s_fu[v][0][c];
+            if (mode == 0) {
+                const double fr = s_fu[v][1][c], fi = s_fu[v][2][c];
+#pragma unroll
+                for (int r = 0; r < SIDE; r++) {
+                    const double fv = s_fv[v][r];
+                    aw[r] = fma(fv, fw, aw[r]);
+                    ar[r] = fma(fv, fr, ar[r]);
+                    ai[r] = fma(fv, fi, ai[r]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < SIDE; r++) aw[r] = fma(s_fv[v][r], fw, aw[r]);
+            }
+        }
+        __syncthreads();
+    }
+    // sum the streams' private regions (stream order, deterministic within the item), then flush
+    double *red = &s_fu[0][0][0];                                  // [3][SIDE][16], reuses the stage buffer
+    for (int sidx = 0; sidx < GT2_STREAMS; sidx++) {
+        if (stream == sidx) {
+#pragma unroll
+            for (int r = 0; r < SIDE; r++) {
+                if (sidx == 0) {
+                    red[(0 * SIDE + r) * 16 + c] = aw[r];
+                    red[(1 * SIDE + r) * 16 + c] = ar[r];
+                    red[(2 * SIDE + r) * 16 + c] = ai[r];
+                } else {
+                    red[(0 * SIDE + r) * 16 + c] += aw[r];
+                    red[(1 * SIDE + r) * 16 + c] += ar[r];
+                    red[(2 * SIDE + r) * 16 + c] += ai[r];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < SIDE * 16; t += GT2_THREADS) {
+        const int r = t >> 4, cc = t & 15;
+        const int l = l0 + r, m = m0 + cc;
+        if (cc >= SIDE || l < 0 || m < 0 || l >= P.G || m >= P.G) continue;
+        const int64_t cell = ((int64_t)l * P.G + m) * P.nch + chan;
+        const double vw = red[(0 * SIDE + r) * 16 + cc];
+        if (mode == 0) {
+            const double vr = red[(1 * SIDE + r) * 16 + cc], vi = red[(2 * SIDE + r) * 16 + cc];
+            if (vr != 0.0) atomicAdd(out_re + cell, vr);
+            if (vi != 0.0) atomicAdd(out_im + cell, vi);
+        }
+        if (vw != 0.0) atomicAdd(out_w + cell, vw);
+    }
+}
+
 // ---- re-weighting, normalisation ---------------------------------------------------------------
 __global__ void __launch_bounds__(256) fill_kernel(double *a, int64_t n, double v)
 {
@@ -1006,8 +1171,23 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
                     PDSB_CUDA(cudaGetLastError());
                 }
                 LaunchScope ls("grid_tile_accum");
-                grid_tile_kernel<<<(unsigned)max_items, GT_THREADS, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko, vo,
-                                                                                 items, nitems, t_re, t_im, t_w);
+                switch (side) {
+#define PDSB_TILE2(S)                                                                                                  \
+    case S:                                                                                                            \
+        grid_tile2_kernel<S, 8><<<(unsigned)max_items, 128, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko, vo,     \
+                                                                          items, nitems, t_re, t_im, t_w);             \
+        grid_tile2_kernel<S, 2><<<(unsigned)max_items, 32, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko, vo,      \
+                                                                         items, nitems, t_re, t_im, t_w);              \
+        break;
+                    PDSB_TILE2(10)       // pillbox, box sums with npixels = 1
+                    PDSB_TILE2(12)       // box sums with npixels = 2
+                    PDSB_TILE2(13)       // expsinc
+                    PDSB_TILE2(14)       // box sums with npixels = 3 (superuniform)
+#undef PDSB_TILE2
+                    default:
+                        grid_tile_kernel<<<(unsigned)max_items, GT_THREADS, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko,
+                                                                                         vo, items, nitems, t_re, t_im, t_w);
+                }
                 PDSB_CUDA(cudaGetLastError());
                 return PDSB_OK;
             }
