@@ -182,6 +182,12 @@ int pdsb_grid(const double *u, const double *v, const double *freq,
               uint32_t *out_i, uint32_t *out_j, double *out_wmod, int out_kind,
               int64_t *n_outside);
 
+/* Multi-GPU gridding with bit-exact results: each process owns a band of
+ * output rows.  After pdsb_set_grid_band(row_lo, row_hi) the main scatter of pdsb_grid keeps only
+ * contributions to rows [row_lo, row_hi) (ordered mode, natural weighting, imaging = 2 raw sums only);
+ * the bands are then summed (adding exact zeros) and normalised with pdsb_grid_normalise.  (0, 0) lifts
+ * the restriction. */
+int pdsb_set_grid_band(int row_lo, int row_hi);
 /* Multi-GPU gridding (throughput mode): every rank grids its share of the
  * visibilities with imaging = 2 (raw sums, no normalisation) into device maps, the maps are summed
  * over ranks (NCCL all-reduce), then this applies the :525-533 normalisation on the device maps. */

@@ -71,6 +71,7 @@ SIGNATURES = {
     "pdsb_bin_average": [_P, _P, _P, _P, _P, _P, _P, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                          _P, _P, _P, _P, _P, _c_int],
     "pdsb_center": [_P, _P, _P, _P, _P, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_int, _P, _P],
+    "pdsb_set_grid_band": [_c_int, _c_int],
     "pdsb_channel_postprocess": [_P, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "pdsb_invert_image": [_P, _P, _P, _c_int, _c_int, _c_int, _P],
     "pdsb_mad_std": [_P, _c_i64, _c_int, ctypes.POINTER(_c_dbl)],

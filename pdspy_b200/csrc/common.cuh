@@ -67,6 +67,7 @@ struct Context {
     int64_t launches = 0;
     int dft_variant = 0;
     int dft_split = 0;
+    int grid_row_lo = 0, grid_row_hi = 0;      // pdsb_set_grid_band: output rows this process accumulates (0, 0 = all)
     // scratch
     Scratch img64, folded, partial, red, stage_a, stage_b, stage_c, stage_d, stage_e;
     Scratch small_dev;     // tiny per-call device arrays (channel scale factors)

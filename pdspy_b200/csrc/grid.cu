@@ -84,6 +84,7 @@ struct GridParams {
     double binsize, inv_binsize, inv_freq, half;   // half = G/2. or (G-1)/2.
     const double *uu, *vv;
     uint32_t nmin, nmax;    // footprint half-widths of the main scatter
+    uint32_t row_lo, row_hi;   // main scatter keeps output rows [row_lo, row_hi) only (multi-GPU row bands)
 };
 
 // :351-353 weights clamp/zeroing, :388-403 index maps, :421-423 good mask
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256) grid_emit_keys_kernel(GridParams P, int m
             uint32_t l, m;
             if (!slot_cell(P.gi[idx], P.gj[idx], f, lo, hi, P.G, &l, &m)) continue;
             bool live = true;
-            if (mode == 0) live = conv_value(P, idx / P.nf, n, l, m) != 0.0;
+            if (mode == 0) live = l >= P.row_lo && l < P.row_hi && conv_value(P, idx / P.nf, n, l, m) != 0.0;
             if (live) {
                 key = (l * (uint32_t)P.G + m) * (uint32_t)P.nch + (P.spectral ? (uint32_t)n : 0u);
                 break;
@@ -1113,6 +1114,16 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
     if (ninclude % 2 == 0) { P.nmin = (uint32_t)(ninclude * 0.5 - 1); P.nmax = (uint32_t)(ninclude * 0.5); }
     else { P.nmin = P.nmax = (uint32_t)((ninclude - 1) * 0.5); }
 
+    P.row_lo = 0;
+    P.row_hi = (uint32_t)G;
+    if (c.grid_row_hi > 0) {           // pdsb_set_grid_band: this process owns a band of output rows
+        PDSB_REQUIRE(deterministic && weighting == PDSB_WT_NATURAL && imaging == 2,
+                     "a row band needs the ordered mode, natural weighting and raw sums (imaging = 2)");
+        PDSB_REQUIRE(c.grid_row_lo >= 0 && c.grid_row_lo < c.grid_row_hi && c.grid_row_hi <= G, "row band");
+        P.row_lo = (uint32_t)c.grid_row_lo;
+        P.row_hi = (uint32_t)c.grid_row_hi;
+    }
+
     PDSB_CUDA(cudaMemsetAsync(d_nout, 0, sizeof(unsigned long long), c.stream));
     PDSB_CUDA(cudaMemsetAsync(o_re, 0, (size_t)ncell * 3 * sizeof(double), c.stream));
     if (nvis > 0) {
@@ -1460,6 +1471,16 @@ int pdsb_center(const double *u, const double *v, const double *freq, const doub
         PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
+    return PDSB_OK;
+}
+
+// Multi-GPU bit-exact gridding: restrict the main scatter of later pdsb_grid calls
+// to output rows [row_lo, row_hi); (0, 0) lifts the restriction.
+int pdsb_set_grid_band(int row_lo, int row_hi)
+{
+    PDSB_REQUIRE((row_lo == 0 && row_hi == 0) || (row_lo >= 0 && row_hi > row_lo), "row band");
+    ctx().grid_row_lo = row_lo;
+    ctx().grid_row_hi = row_hi;
     return PDSB_OK;
 }
 

@@ -200,3 +200,88 @@ def sharded_grid(data_shard, gridsize=256, binsize=2000.0, convolution="pillbox"
     out_freq = np.array([freq.sum() / freq.size]) if mode == "continuum" else freq
     return Visibilities(new_u.reshape(G * G), new_v.reshape(G * G), out_freq, np.ascontiguousarray(host[0]),
                         np.ascontiguousarray(host[1]), np.ascontiguousarray(host[2]))
+
+
+def band_rows(u, v, freq, gridsize, binsize, row_lo, row_hi, lo, hi, include_outside=False):
+    """Ascending indices of the visibility rows whose footprint can reach output rows [row_lo, row_hi) of
+    grid() (footprint rows j - lo .. j + hi around the home row j, libinterferometry.pyx:493-507).
+    Conservative by two cells: the exact row test is made on the device (pdsb_set_grid_band), this only
+    keeps a rank from streaming visibilities that cannot matter.  include_outside adds the rows with an
+    element off the grid, so that exactly one rank reports them (the WARNING of :424)."""
+    G = int(gridsize)
+    scale = np.asarray(freq, dtype=np.float64) / (np.sum(freq) / len(freq)) / binsize
+    jf = np.floor(np.asarray(v, dtype=np.float64)[:, None] * scale[None, :] + G / 2.)
+    sel = ((jf >= row_lo - hi - 2) & (jf < row_hi + lo + 2)).any(axis=1)
+    if include_outside:
+        xf = np.floor(np.asarray(u, dtype=np.float64)[:, None] * scale[None, :] + G / 2.)
+        sel |= ((jf < 0) | (jf >= G) | (xf < 0) | (xf >= G)).any(axis=1)
+    return np.flatnonzero(sel)
+
+
+def banded_grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", imaging=False, mode="continuum",
+                group=None, bands=None):
+    """grid() over several GPUs with results BIT-IDENTICAL to the single-GPU ordered mode (SURVEY.md section
+    8e (ii)).  Every rank sees the whole data set and owns a band of gridsize/world output rows: it streams
+    only the visibilities whose footprint can reach its band (in their original order, which is what fixes
+    the rounding), accumulates that band in the reference's (k, n) order (pdsb_set_grid_band + ordered
+    pdsb_grid with raw sums), the bands are summed over NCCL (every cell is non-zero on one rank only, so
+    the sum adds exact zeros) and normalised on the device.  Natural weighting only.
+
+    bands=(index, count) runs one band without a process group (tests; sum the raw maps yourself with
+    raw=True semantics by calling it for every index) - normally leave it None."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .interferometry import Visibilities
+    from .interferometry.grid import _WARNING
+    L = _lib.lib()
+    _lib.check(L.pdsb_set_stream(torch.cuda.current_stream().cuda_stream))
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if bands is not None:
+        rank, world = bands
+    elif multi:
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    u, v, freq = _lib.f64(data.u), _lib.f64(data.v), _lib.f64(data.freq)
+    nf = freq.size
+    nch = 1 if mode == "continuum" else nf
+    G = int(gridsize)
+    if G % 2 == 0:                                   # numpy.linspace of libinterferometry.pyx:370-381
+        uu = np.linspace(-G * binsize / 2, (G / 2 - 1) * binsize, G)
+    else:
+        uu = np.linspace(-(G - 1) * binsize / 2, (G - 1) * binsize / 2, G)
+    vv = uu.copy()
+    row_lo, row_hi = shard_bounds(G, rank, world)
+    lo, hi = (2, 3) if convolution == "expsinc" else (1, 1)          # nmin, nmax of :405-417
+    maps = torch.zeros((3, G * G, nch), dtype=torch.float64, device="cuda")
+    n_out = ctypes.c_int64(0)
+    if row_hi > row_lo:
+        rows = band_rows(u, v, freq, G, binsize, row_lo, row_hi, lo, hi, include_outside=(rank == 0))
+        take = (lambda a: np.ascontiguousarray(_lib.f64(a)[rows]))
+        _lib.check(L.pdsb_set_grid_band(row_lo, row_hi))
+        try:
+            _lib.check(L.pdsb_grid(_lib.ptr(take(u)), _lib.ptr(take(v)), _lib.ptr(freq), _lib.ptr(take(data.real)),
+                                   _lib.ptr(take(data.imag)), _lib.ptr(take(data.weights)), rows.size, nf, _lib.HOST,
+                                   G, float(binsize), _lib.ptr(uu), _lib.ptr(vv), _lib.CONV[convolution], 0, 2.0, 0,
+                                   _lib.MODE[mode], 2, 1,            # imaging = 2: raw sums; ordered mode
+                                   maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), None, None, None,
+                                   _lib.DEVICE, ctypes.byref(n_out)))
+        finally:
+            _lib.check(L.pdsb_set_grid_band(0, 0))
+    if bands is not None:
+        return maps, n_out.value                     # raw band maps on the device, for the caller to combine
+    nout = torch.tensor([n_out.value], dtype=torch.int64, device="cuda")
+    if multi:
+        dist.all_reduce(maps, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(nout, op=dist.ReduceOp.SUM, group=group)
+    _lib.check(L.pdsb_grid_normalise(maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), G, nch,
+                                     1 if imaging else 0))
+    host = maps.cpu().numpy()
+    if int(nout.item()) > 0:
+        print(_WARNING)
+    new_u, new_v = np.meshgrid(uu, vv)
+    out_freq = np.array([freq.sum() / freq.size]) if mode == "continuum" else freq
+    return Visibilities(new_u.reshape(G * G), new_v.reshape(G * G), out_freq, np.ascontiguousarray(host[0]),
+                        np.ascontiguousarray(host[1]), np.ascontiguousarray(host[2]))

@@ -195,3 +195,56 @@ def test_sharded_grid_single_rank_equals_grid(gpu):
             np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm))
         for nm in ("real", "imag", "weights"):
             assert np.abs(getattr(a, nm) - getattr(b, nm)).max() <= 1e-12 * np.abs(getattr(b, nm)).max()
+
+
+@pytest.mark.parametrize("kw", [dict(gridsize=128, binsize=8000., convolution="expsinc", mode="spectralline", imaging=True),
+                                dict(gridsize=128, binsize=8000., convolution="pillbox"),
+                                dict(gridsize=65, binsize=16000., convolution="expsinc")])
+@pytest.mark.parametrize("nbands", [1, 3, 8])
+def test_banded_grid_is_bit_identical_to_the_ordered_grid(gpu, kw, nbands):
+    """pdspy_b200.dist.banded_grid (multi-GPU bit-exact mode): the row bands of `nbands`
+    ranks, computed here one after the other on one GPU, summed and normalised, equal the single-GPU
+    ordered grid() bit for bit (the N-process version is scripts/gpu_dist_grid.py under torchrun)."""
+    import torch
+    from pdspy_b200 import dist as pdist, _lib
+    u, v, freq, re, im, w = multi_channel_set()
+    d = Visibilities(u, v, freq, re, im, w)
+    ref, _ = _quiet(grid, d, deterministic=True, **kw)
+    try:
+        if nbands == 1:
+            got, out = _quiet(pdist.banded_grid, d, **kw)
+            assert out.startswith("WARNING")
+        else:
+            total, nout = None, 0
+            for b in range(nbands):
+                maps, n = pdist.banded_grid(d, bands=(b, nbands), **kw)
+                others = maps.clone()
+                lo, hi = pdist.shard_bounds(kw["gridsize"], b, nbands)
+                others.view(3, kw["gridsize"], kw["gridsize"], -1)[:, lo:hi] = 0
+                assert not others.any()                                 # nothing outside the rank's own band
+                total = maps if total is None else total + maps
+                nout += n
+            nch = total.shape[2]
+            _lib.check(gpu.pdsb_grid_normalise(total[0].data_ptr(), total[1].data_ptr(), total[2].data_ptr(),
+                                               kw["gridsize"], nch, 1 if kw.get("imaging") else 0))
+            torch.cuda.synchronize()
+            host = total.cpu().numpy()
+            got = Visibilities(ref.u, ref.v, ref.freq, host[0], host[1], host[2])
+            assert nout > 0
+    finally:
+        _lib.check(gpu.pdsb_reset_stream())
+    for nm in ("real", "imag", "weights"):
+        np.testing.assert_array_equal(getattr(got, nm), getattr(ref, nm))
+
+
+def test_band_needs_ordered_raw_natural(gpu):
+    from pdspy_b200 import _lib
+    u, v, freq, re, im, w = multi_channel_set()
+    d = Visibilities(u, v, freq, re, im, w)
+    _lib.check(gpu.pdsb_set_grid_band(0, 16))
+    try:
+        with pytest.raises(_lib.PdsbError):
+            _quiet(grid, d, gridsize=64, binsize=8000.)                 # normalised output + a band: refused
+    finally:
+        _lib.check(gpu.pdsb_set_grid_band(0, 0))
+    assert gpu.pdsb_set_grid_band(5, 5) != 0
