@@ -74,16 +74,34 @@ __device__ __forceinline__ uint32_t pack_half2(__half a, __half b)
 __global__ void __launch_bounds__(256) plane_absmax_kernel(const double *__restrict__ img, int64_t npix, int nf,
                                                            int64_t nstrips, unsigned long long *__restrict__ planemax)
 {
-    // thread = (pixel strip, channel), channel fastest: coalesced over channels; one atomic per thread
+    // thread = (pixel strip, channel), channel fastest: coalesced over channels.  With few channels
+    // hundreds of thousands of threads would hit the same few addresses, so the block's values are first
+    // combined per channel in shared memory: one atomic per (block, channel).
+    __shared__ double sm[256];
     const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= nstrips * nf) return;
-    const int p = (int)(idx % nf);
     double m = 0.0;
-    for (int64_t pix = idx / nf; pix < npix; pix += nstrips) {
-        const double a = fabs(img[pix * nf + p]);
-        m = a > m ? a : m;            // NaNs are ignored (comparison false)
+    if (idx < nstrips * nf) {
+        const int p = (int)(idx % nf);
+        for (int64_t pix = idx / nf; pix < npix; pix += nstrips) {
+            const double a = fabs(img[pix * nf + p]);
+            m = a > m ? a : m;            // NaNs are ignored (comparison false)
+        }
+        if (nf > 256) {
+            if (m > 0.0) atomicMax(planemax + p, (unsigned long long)__double_as_longlong(m));
+            return;
+        }
     }
-    if (m > 0.0) atomicMax(planemax + p, (unsigned long long)__double_as_longlong(m));
+    if (nf > 256) return;
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    if ((int)threadIdx.x < nf) {
+        // entries j of this block with (blockIdx.x*256 + j) % nf == my channel
+        const int first = (int)(((int64_t)blockIdx.x * 256) % nf);
+        const int p = ((int)threadIdx.x + first) % nf;        // channel of entry j = threadIdx.x
+        double best = 0.0;
+        for (int j = threadIdx.x; j < 256; j += nf) best = sm[j] > best ? sm[j] : best;
+        if (best > 0.0) atomicMax(planemax + p, (unsigned long long)__double_as_longlong(best));
+    }
 }
 
 __global__ void plane_scale_kernel(const unsigned long long *__restrict__ planemax, int nf, double *__restrict__ scale,
