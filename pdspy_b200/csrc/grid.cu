@@ -399,12 +399,101 @@ __global__ void __launch_bounds__(256) grid_values_kernel(GridParams P, int mode
 constexpr int OS_LONG = 96;
 constexpr int OS_PER = 4;               // addends per lane per iteration
 constexpr int OS_CH = 32 * OS_PER;
+// Runs longer than OS_XLONG are not summed here: a warp would work through the very long runs of its 32
+// cells one after the other (the dense centre of the uv plane puts several multi-million-addend cells
+// next to each other).  They go on a list and grid_ordered_long_kernel gives each its own warp.
+constexpr int OS_XLONG = 8192;
+struct LongRun {
+    long long cell, p, e;
+};
+
+// the in-order sum of one run, streamed by a whole warp (see above); `owner` adds
+__device__ __forceinline__ void ordered_stream(int mode, int lane, int owner, int64_t rp, int64_t re_,
+                                               const double *__restrict__ v_re, const double *__restrict__ v_im,
+                                               const double *__restrict__ v_w, double (*sb)[OS_CH], double &sr,
+                                               double &si, double &sw)
+{
+    // OS_CH addends per iteration; the next iteration's loads are in flight (registers) while
+    // the owner adds the current ones out of shared memory
+    double nr[OS_PER], ni[OS_PER], nw[OS_PER];
+#pragma unroll
+    for (int t = 0; t < OS_PER; t++) {
+        const int64_t q = rp + t * 32 + lane;
+        nr[t] = (mode == 0 && q < re_) ? v_re[q] : 0.0;
+        ni[t] = (mode == 0 && q < re_) ? v_im[q] : 0.0;
+        nw[t] = q < re_ ? v_w[q] : 0.0;
+    }
+    for (int64_t base = rp; base < re_; base += OS_CH) {
+#pragma unroll
+        for (int t = 0; t < OS_PER; t++) {
+            sb[0][t * 32 + lane] = nr[t];
+            sb[1][t * 32 + lane] = ni[t];
+            sb[2][t * 32 + lane] = nw[t];
+        }
+#pragma unroll
+        for (int t = 0; t < OS_PER; t++) {
+            const int64_t q = base + OS_CH + t * 32 + lane;
+            nr[t] = (mode == 0 && q < re_) ? v_re[q] : 0.0;
+            ni[t] = (mode == 0 && q < re_) ? v_im[q] : 0.0;
+            nw[t] = q < re_ ? v_w[q] : 0.0;
+        }
+        __syncwarp();
+        if (lane == owner) {
+            const int n = (int)(re_ - base < OS_CH ? re_ - base : OS_CH);
+            if (mode == 0) {
+#pragma unroll 16
+                for (int t = 0; t < n; t++) {
+                    sr = __dadd_rn(sr, sb[0][t]);
+                    si = __dadd_rn(si, sb[1][t]);
+                    sw = __dadd_rn(sw, sb[2][t]);
+                }
+            } else {
+#pragma unroll 16
+                for (int t = 0; t < n; t++) sw = __dadd_rn(sw, sb[2][t]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32) grid_ordered_long_kernel(int mode, const LongRun *__restrict__ runs,
+                                                               const unsigned int *__restrict__ nruns,
+                                                               const double *__restrict__ v_re,
+                                                               const double *__restrict__ v_im,
+                                                               const double *__restrict__ v_w, double *out_re,
+                                                               double *out_im, double *out_w)
+{
+    __shared__ double sbuf[3][OS_CH];
+    const int lane = threadIdx.x;
+    for (unsigned int r = blockIdx.x; r < *nruns; r += gridDim.x) {
+        const LongRun run = runs[r];
+        double sr = 0, si = 0, sw = 0;
+        if (lane == 0) {
+            sw = out_w[run.cell];
+            if (mode == 0) {
+                sr = out_re[run.cell];
+                si = out_im[run.cell];
+            }
+        }
+        ordered_stream(mode, lane, 0, run.p, run.e, v_re, v_im, v_w, sbuf, sr, si, sw);
+        if (lane == 0) {
+            out_w[run.cell] = sw;
+            if (mode == 0) {
+                out_re[run.cell] = sr;
+                out_im[run.cell] = si;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t ncell,
                                                                const uint32_t *__restrict__ keys, int64_t ncontrib,
                                                                const double *__restrict__ v_re,
                                                                const double *__restrict__ v_im,
                                                                const double *__restrict__ v_w, double *out_re,
-                                                               double *out_im, double *out_w)
+                                                               double *out_im, double *out_w, LongRun *runs,
+                                                               unsigned int *nruns)
 {
     __shared__ double sbuf[4][3][OS_CH];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -431,7 +520,11 @@ __global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t
             p = e = 0;
         }
     }
-    const bool has = e > p;
+    bool has = e > p;
+    if (has && runs && e - p > OS_XLONG) {            // deferred to grid_ordered_long_kernel
+        runs[atomicAdd(nruns, 1u)] = LongRun{(long long)cell, (long long)p, (long long)e};
+        has = false;
+    }
     double sr = 0, si = 0, sw = 0;
     if (has) {
         sw = out_w[cell];
@@ -455,47 +548,7 @@ __global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t
         const int owner = __ffs(long_mask) - 1;
         long_mask &= long_mask - 1;
         const int64_t rp = __shfl_sync(0xffffffffu, p, owner), re_ = __shfl_sync(0xffffffffu, e, owner);
-        // OS_CH addends per iteration; the next iteration's loads are in flight (registers) while
-        // the owner adds the current ones out of shared memory
-        double nr[OS_PER], ni[OS_PER], nw[OS_PER];
-#pragma unroll
-        for (int t = 0; t < OS_PER; t++) {
-            const int64_t q = rp + t * 32 + lane;
-            nr[t] = (mode == 0 && q < re_) ? v_re[q] : 0.0;
-            ni[t] = (mode == 0 && q < re_) ? v_im[q] : 0.0;
-            nw[t] = q < re_ ? v_w[q] : 0.0;
-        }
-        for (int64_t base = rp; base < re_; base += OS_CH) {
-#pragma unroll
-            for (int t = 0; t < OS_PER; t++) {
-                sbuf[wid][0][t * 32 + lane] = nr[t];
-                sbuf[wid][1][t * 32 + lane] = ni[t];
-                sbuf[wid][2][t * 32 + lane] = nw[t];
-            }
-#pragma unroll
-            for (int t = 0; t < OS_PER; t++) {
-                const int64_t q = base + OS_CH + t * 32 + lane;
-                nr[t] = (mode == 0 && q < re_) ? v_re[q] : 0.0;
-                ni[t] = (mode == 0 && q < re_) ? v_im[q] : 0.0;
-                nw[t] = q < re_ ? v_w[q] : 0.0;
-            }
-            __syncwarp();
-            if (lane == owner) {
-                const int n = (int)(re_ - base < OS_CH ? re_ - base : OS_CH);
-                if (mode == 0) {
-#pragma unroll 8
-                    for (int t = 0; t < n; t++) {
-                        sr = __dadd_rn(sr, sbuf[wid][0][t]);
-                        si = __dadd_rn(si, sbuf[wid][1][t]);
-                        sw = __dadd_rn(sw, sbuf[wid][2][t]);
-                    }
-                } else {
-#pragma unroll 8
-                    for (int t = 0; t < n; t++) sw = __dadd_rn(sw, sbuf[wid][2][t]);
-                }
-            }
-            __syncwarp();
-        }
+        ordered_stream(mode, lane, owner, rp, re_, v_re, v_im, v_w, sbuf[wid], sr, si, sw);
     }
     if (has) {
         out_w[cell] = sw;
@@ -1241,9 +1294,17 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
                                                                                  ncontrib, val_re, val_im, val_w);
                 PDSB_CUDA(cudaGetLastError());
             }
+            // very long runs (> OS_XLONG addends) are listed, then summed one warp per run
+            const size_t max_runs = (size_t)(ncontrib / OS_XLONG) + 2;
+            PDSB_CHECK(c.folded.ensure(max_runs * sizeof(LongRun) + 64));      // (the DFT's scratch is free here)
+            unsigned int *nruns = c.folded.as<unsigned int>();
+            LongRun *runs = reinterpret_cast<LongRun *>(c.folded.as<unsigned char>() + 64);
+            PDSB_CUDA(cudaMemsetAsync(nruns, 0, sizeof(unsigned int), c.stream));
             LaunchScope ls("grid_ordered_sum");
             grid_ordered_sum_kernel<<<ceil_div(ncell, 128), 128, 0, c.stream>>>(smode, ncell, ko, ncontrib, val_re,
-                                                                               val_im, val_w, t_re, t_im, t_w);
+                                                                               val_im, val_w, t_re, t_im, t_w, runs, nruns);
+            grid_ordered_long_kernel<<<(unsigned)std::min<size_t>(max_runs, 16384), 32, 0, c.stream>>>(
+                smode, runs, nruns, val_re, val_im, val_w, t_re, t_im, t_w);
             PDSB_CUDA(cudaGetLastError());
         }
         return PDSB_OK;
@@ -1415,7 +1476,8 @@ int pdsb_bin_average(const uint32_t *bin_i, const uint32_t *bin_j, const double 
                 }
                 LaunchScope ls("grid_ordered_sum");
                 grid_ordered_sum_kernel<<<ceil_div(ncell, 128), 128, 0, c.stream>>>(
-                    0, ncell, ko, n, va, vb, vw, which ? m_u : m_re, which ? m_v : m_im, which ? m_w2 : m_w);
+                    0, ncell, ko, n, va, vb, vw, which ? m_u : m_re, which ? m_v : m_im, which ? m_w2 : m_w, nullptr,
+                    nullptr);
                 PDSB_CUDA(cudaGetLastError());
             }
         }
