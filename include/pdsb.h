@@ -223,6 +223,14 @@ int pdsb_center(const double *u, const double *v, const double *freq, const doub
 int pdsb_channel_postprocess(const double *image, int64_t npix, int nf_in, int subsample, int hanning,
                              int averaging, int kind, double *out);
 
+/* Piecewise-linear regridding of an unstructured image (interpolate_model code="galario-unstructured",
+ * pdspy/interferometry/interpolate_model.py:32-47; the scattered images of Model.py:536-558): values
+ * [npts, nf]; per output pixel the three vertices of its Delaunay triangle tri [npix, 3] (tri[p,0] < 0:
+ * outside the hull -> 0) and barycentric weights bary [npix, 3]; out [npix, nf] = scale * weighted sum.
+ * All host or all device (`kind`). */
+int pdsb_regrid_linear(const double *values, int64_t npts, const int *tri, const double *bary, int64_t npix,
+                       int nf, double scale, int kind, double *out);
+
 /* invert(): the per-channel image synthesis of pdspy/interferometry/invert.py:63-84 from gridded
  * visibilities (grid(..., imaging=True)): g_real, g_imag [imsize*imsize, nch]; conv [imsize, imsize] =
  * conv_func(u, v, binsize, binsize) of :94-121 evaluated by the caller on the grid; image_out

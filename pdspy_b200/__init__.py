@@ -10,7 +10,7 @@ loads the library and initialises the device, and raises if either is missing (n
 from . import constants
 from . import interferometry
 from . import utils
-from .imaging import Image
+from .imaging import Image, UnstructuredImage
 from .device import Dataset, clear_cache, set_dft_kernel
 from ._lib import PdsbError, DeviceBuffer, PinnedArray
 

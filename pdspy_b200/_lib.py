@@ -72,6 +72,7 @@ SIGNATURES = {
                          _P, _P, _P, _P, _P, _c_int],
     "pdsb_center": [_P, _P, _P, _P, _P, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_int, _P, _P],
     "pdsb_set_grid_band": [_c_int, _c_int],
+    "pdsb_regrid_linear": [_P, _c_i64, _P, _P, _c_i64, _c_int, _c_dbl, _c_int, _P],
     "pdsb_channel_postprocess": [_P, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "pdsb_invert_image": [_P, _P, _P, _c_int, _c_int, _c_int, _P],
     "pdsb_mad_std": [_P, _c_i64, _c_int, ctypes.POINTER(_c_dbl)],

@@ -35,3 +35,22 @@ class Image(object):
             self.freq = freq
         if wcs is not None:
             self.wcs = wcs
+
+
+class UnstructuredImage(object):
+    """Scattered-point image, mirroring pdspy/imaging/libimaging.pyx:186-222: image [npts, nfreq] (Jy/sr),
+    x, y [npts] in arcsec, freq/wave deriving each other through c."""
+
+    def __init__(self, image=None, x=None, y=None, wave=None, freq=None, unc=None, velocity=None):
+        if image is not None and (not isinstance(image, numpy.ndarray) or image.dtype != numpy.float64 or image.ndim != 2):
+            raise ValueError("image must be a 2-D float64 array [npts, nfreq]")
+        self.image, self.x, self.y, self.unc, self.velocity = image, x, y, unc, velocity
+        if (wave is None) and (freq is not None):
+            self.freq = freq
+            self.wave = _C / freq
+        elif (wave is not None) and (freq is None):
+            self.wave = wave
+            self.freq = _C / wave
+        elif (wave is not None) and (freq is not None):
+            self.wave = wave
+            self.freq = freq

@@ -15,6 +15,7 @@ from .. import _lib
 from ..device import dataset_for
 from .visibilities import Visibilities
 from .cube import postprocess_channels_device
+from .unstructured import regrid
 
 
 def _cube(model):
@@ -50,10 +51,19 @@ def interpolate_model(u, v, freq, model, nthreads=1, dRA=0., dDec=0.,
                                            float(dxy), float(dRA * arcsec), float(dDec * arcsec),
                                            _lib.ptr(real), _lib.ptr(imag), _lib.HOST))
 
-    elif code in ("galario-unstructured", "trift"):
+    elif code == "galario-unstructured":
+        # scattered points -> piecewise-linear interpolant on the nxy x nxy grid of dxy arcsec (Jy/pixel),
+        # then the same transform as above (unstructured.py; parity unpinned: galario fork not available)
+        from ..imaging import Image
+        cube = regrid(model, int(nxy), float(dxy))
+        x = (numpy.arange(int(nxy)) - int(nxy) // 2) * float(dxy)
+        return interpolate_model(u, v, freq, Image(cube, x=x, y=x.copy(), freq=numpy.asarray(model.freq)),
+                                 nthreads=nthreads, dRA=dRA, dDec=dDec, code="galario")
+
+    elif code == "trift":
         raise NotImplementedError(
-            "code=%r (unstructured images, interpolate_model.py:32-55) is not on the B200 path yet; "
-            "see DESIGN.md 'next'" % code)
+            "code='trift' (exact transform of the triangulated image, interpolate_model.py:49-55) is not on "
+            "the B200 path; code='galario-unstructured' handles the same images")
     else:
         # the reference falls through to an UnboundLocalError on `real`; be explicit instead
         raise ValueError("unknown code %r" % (code,))

@@ -89,3 +89,23 @@ def test_fingerprint_detects_in_place_change():
     f0 = device._fingerprint(a)
     a[0] = -1
     assert device._fingerprint(a) != f0
+
+
+def test_unstructured_triangulation_helper_vs_scipy_interpolator():
+    """pdspy_b200.interferometry.unstructured.triangulate (host side of code="galario-unstructured"): the
+    per-pixel triangles and barycentric weights reproduce scipy's LinearNDInterpolator (oracle/unstructured.py)."""
+    import numpy as np
+    from oracle import unstructured as ou
+    from pdspy_b200.interferometry.unstructured import triangulate
+    A = 4.84813681e-6
+    rng = np.random.default_rng(1)
+    r = np.concatenate([[0], np.sqrt(rng.random(2000)) * 1.2])
+    ph = rng.random(2001) * 2 * np.pi
+    x, y = -r * np.cos(ph), r * np.sin(ph)
+    vals = np.exp(-0.5 * (x ** 2 + y ** 2) / 0.3 ** 2)[:, None] * np.array([1.0, 0.5])
+    nxy, dxy = 48, 0.05
+    tri, bary = triangulate(x * A, -y * A, nxy, dxy * A)
+    got = np.where(tri[:, :1] >= 0, (bary[:, :, None] * vals[np.maximum(tri, 0)]).sum(axis=1), 0.0) * (dxy * A) ** 2
+    ref = ou.regrid(x, y, vals, nxy, dxy)[::-1, :, :, 0].reshape(nxy * nxy, 2)
+    assert (tri[:, 0] >= 0).mean() > 0.5
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
