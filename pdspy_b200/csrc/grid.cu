@@ -134,6 +134,18 @@ __device__ __forceinline__ double conv_value(const GridParams &P, int64_t k, int
     return P.conv ? k_exp_sinc(du, dv) : k_ones(du, dv);
 }
 
+// Whether slot (l, m) can receive a non-zero kernel value: the support test of the two kernels (:559-585)
+// without the polynomial.  (A value that is exactly 0 inside the support would only add 0.)
+__device__ __forceinline__ bool conv_live(const GridParams &P, int64_t k, int n, uint32_t l, uint32_t m)
+{
+    const double us = __dmul_rn(__dmul_rn(P.u[k], P.freq[n]), P.inv_freq);
+    const double vs = __dmul_rn(__dmul_rn(P.v[k], P.freq[n]), P.inv_freq);
+    const double du = __dmul_rn(__dsub_rn(us, P.uu[m]), P.inv_binsize);
+    const double dv = __dmul_rn(__dsub_rn(vs, P.vv[l]), P.inv_binsize);
+    const double lim = P.conv ? 3.0 : 0.5;
+    return fabs(du) < lim && fabs(dv) < lim;
+}
+
 // ---- contribution keys -------------------------------------------------------------------------
 // mode 0: main scatter (footprint nmin/nmax, slots with a zero kernel value are dead)
 // mode 1: box sum of weights for uniform/robust re-weighting (footprint npix/npix)
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(256) grid_emit_keys_kernel(GridParams P, int m
             uint32_t l, m;
             if (!slot_cell(P.gi[idx], P.gj[idx], f, lo, hi, P.G, &l, &m)) continue;
             bool live = true;
-            if (mode == 0) live = l >= P.row_lo && l < P.row_hi && conv_value(P, idx / P.nf, n, l, m) != 0.0;
+            if (mode == 0) live = l >= P.row_lo && l < P.row_hi && conv_live(P, idx / P.nf, n, l, m);
             if (live) {
                 key = (l * (uint32_t)P.G + m) * (uint32_t)P.nch + (P.spectral ? (uint32_t)n : 0u);
                 break;
