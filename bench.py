@@ -220,7 +220,7 @@ def cpu_baseline_port(cfg):
     from oracle import likelihood as ol
     L = olib()
     cores = L.oracle_num_threads()
-    nuv_s = {"C3": 384, "C2": 4096, "C1": 20000}[cfg["name"]]
+    nuv_s = {"C3": 6144, "C2": 98304, "C1": 50000}[cfg["name"]]          # about 10 s of work on 16 host cores
     u, v = synth.synth_uv(cfg["nuv"], cfg["pixelsize"] * A)
     u, v = np.ascontiguousarray(u[:nuv_s]), np.ascontiguousarray(v[:nuv_s])
     img = np.ascontiguousarray(synth.synth_image(cfg["npix"], cfg["nf"], cfg["pixelsize"])[:, :, :, 0])
