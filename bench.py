@@ -312,7 +312,7 @@ def run_gridding(args, cfg, rank, world):
                     "h2d_bytes_per_step": int(nvis * 40 + 2 * G * 8), "d2h_bytes_per_step": int(3 * G * G * 8),
                     "api": "pdspy_b200.interferometry.grid(data, ..., deterministic=False) (numpy in, Visibilities out)"},
             "gpu_launches": int(n1.value - n0.value), "clocks": clocks,
-            "roofline": {"kernel": "whole grid() step (prep + tile sort + grid_tile_kernel + normalise)", "bound": "hbm",
+            "roofline": {"kernel": "whole grid() step (prep + tile sort + grid_tile2_kernel + normalise)", "bound": "hbm",
                          "achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                          "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / hbm,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
