@@ -227,8 +227,9 @@ def banded_grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", imagi
     pdsb_grid with raw sums), the bands are summed over NCCL (every cell is non-zero on one rank only, so
     the sum adds exact zeros) and normalised on the device.  Natural weighting only.
 
-    bands=(index, count) runs one band without a process group (tests; sum the raw maps yourself with
-    raw=True semantics by calling it for every index) - normally leave it None."""
+    bands=(index, count) computes ONE band without a process group and returns (raw device maps [3, G*G,
+    nch], n_outside) for the caller to sum over all indices and pass to pdsb_grid_normalise (this is how
+    the single-GPU test emulates N ranks); normally leave it None."""
     import ctypes
     import torch
     import torch.distributed as dist
