@@ -724,7 +724,9 @@ __global__ void __launch_bounds__(GT_THREADS) grid_tile_kernel(GridParams P, int
 // 2 streams, whose fixed cost (cross-stream sum, barriers) is a quarter and of which 20+ fit on an SM.
 constexpr int GT2_LIGHT = 128;
 
-template <int SIDE, int NSTREAM>
+// SPLIT (the dense-tile shape): a stream is a whole warp whose two half-warps own the upper and the lower
+// rows of the region, which halves the accumulator registers per thread and lifts the occupancy.
+template <int SIDE, int NSTREAM, bool SPLIT = false>
 __global__ void __launch_bounds__(NSTREAM * 16) grid_tile2_kernel(GridParams P, int mode, int lo, int hi, uint32_t tg,
                                                                  const uint32_t *__restrict__ keys,
                                                                  const uint32_t *__restrict__ order,
@@ -733,8 +735,9 @@ __global__ void __launch_bounds__(NSTREAM * 16) grid_tile2_kernel(GridParams P, 
                                                                  double *out_re, double *out_im, double *out_w)
 {
     constexpr int WIDTH = SIDE - 7;                                // footprint width lo + hi + 1
-    constexpr int GT2_THREADS = NSTREAM * 16, GT2_STREAMS = NSTREAM;
+    constexpr int GT2_THREADS = NSTREAM * 16, GT2_STREAMS = SPLIT ? NSTREAM / 2 : NSTREAM;
     constexpr int GT2_STAGE = NSTREAM * 8;                         // visibilities staged per round (2 threads each)
+    constexpr int NROW = SPLIT ? (SIDE + 1) / 2 : SIDE;            // region rows this thread accumulates
     constexpr int RED_ROWS = (3 * SIDE + 2) / 3;                   // the cross-stream sum reuses s_fu: >= 3*SIDE rows of 16
     constexpr int FU_ROWS = GT2_STAGE > RED_ROWS ? GT2_STAGE : RED_ROWS;
     __shared__ __align__(16) double s_fv[GT2_STAGE][16];          // row factors, zero outside the footprint
@@ -746,11 +749,12 @@ __global__ void __launch_bounds__(NSTREAM * 16) grid_tile2_kernel(GridParams P, 
     const uint32_t chan = key / (tg * tg), tile = key % (tg * tg);
     const int tl = (int)(tile / tg), tm = (int)(tile % tg);
     const int l0 = tl * 8 - lo, m0 = tm * 8 - lo;                  // region origin
-    const int c = threadIdx.x & 15, stream = threadIdx.x >> 4;
+    const int c = threadIdx.x & 15, stream = SPLIT ? threadIdx.x >> 5 : threadIdx.x >> 4;
+    const int row0 = SPLIT ? ((threadIdx.x >> 4) & 1) * NROW : 0;  // first region row of this thread
     const int q = threadIdx.x >> 1, sidev = threadIdx.x & 1;       // staging role: visibility q of the stage, u / v side
-    double aw[SIDE], ar[SIDE], ai[SIDE];
+    double aw[NROW], ar[NROW], ai[NROW];
 #pragma unroll
-    for (int r = 0; r < SIDE; r++) aw[r] = ar[r] = ai[r] = 0.0;
+    for (int r = 0; r < NROW; r++) aw[r] = ar[r] = ai[r] = 0.0;
 
     // The staging inputs are gathered through the sort permutation (order -> idx -> u, v, w, re, im, gi,
     // gj): two dependent global loads.  They are software-pipelined two stages deep - the permutation
@@ -828,15 +832,15 @@ __global__ void __launch_bounds__(NSTREAM * 16) grid_tile2_kernel(GridParams P, 
             if (mode == 0) {
                 const double fr = s_fu[v][1][c], fi = s_fu[v][2][c];
 #pragma unroll
-                for (int r = 0; r < SIDE; r++) {
-                    const double fv = s_fv[v][r];
+                for (int r = 0; r < NROW; r++) {
+                    const double fv = s_fv[v][row0 + r];             // (rows past SIDE are zero padding of the 16-wide row)
                     aw[r] = fma(fv, fw, aw[r]);
                     ar[r] = fma(fv, fr, ar[r]);
                     ai[r] = fma(fv, fi, ai[r]);
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < SIDE; r++) aw[r] = fma(s_fv[v][r], fw, aw[r]);
+                for (int r = 0; r < NROW; r++) aw[r] = fma(s_fv[v][row0 + r], fw, aw[r]);
             }
         }
         __syncthreads();
@@ -846,15 +850,17 @@ __global__ void __launch_bounds__(NSTREAM * 16) grid_tile2_kernel(GridParams P, 
     for (int sidx = 0; sidx < GT2_STREAMS; sidx++) {
         if (stream == sidx) {
 #pragma unroll
-            for (int r = 0; r < SIDE; r++) {
+            for (int r = 0; r < NROW; r++) {
+                const int rr = row0 + r;
+                if (rr >= SIDE) continue;
                 if (sidx == 0) {
-                    red[(0 * SIDE + r) * 16 + c] = aw[r];
-                    red[(1 * SIDE + r) * 16 + c] = ar[r];
-                    red[(2 * SIDE + r) * 16 + c] = ai[r];
+                    red[(0 * SIDE + rr) * 16 + c] = aw[r];
+                    red[(1 * SIDE + rr) * 16 + c] = ar[r];
+                    red[(2 * SIDE + rr) * 16 + c] = ai[r];
                 } else {
-                    red[(0 * SIDE + r) * 16 + c] += aw[r];
-                    red[(1 * SIDE + r) * 16 + c] += ar[r];
-                    red[(2 * SIDE + r) * 16 + c] += ai[r];
+                    red[(0 * SIDE + rr) * 16 + c] += aw[r];
+                    red[(1 * SIDE + rr) * 16 + c] += ar[r];
+                    red[(2 * SIDE + rr) * 16 + c] += ai[r];
                 }
             }
         }
@@ -1250,8 +1256,8 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
                 switch (side) {
 #define PDSB_TILE2(S)                                                                                                  \
     case S:                                                                                                            \
-        grid_tile2_kernel<S, 8><<<(unsigned)max_items, 128, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko, vo,     \
-                                                                          items, nitems, t_re, t_im, t_w);             \
+        grid_tile2_kernel<S, 8, true><<<(unsigned)max_items, 128, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko,   \
+                                                                                vo, items, nitems, t_re, t_im, t_w);   \
         grid_tile2_kernel<S, 2><<<(unsigned)max_items, 32, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko, vo,      \
                                                                          items, nitems, t_re, t_im, t_w);              \
         break;
