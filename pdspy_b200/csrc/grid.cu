@@ -1258,7 +1258,7 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
     case S:                                                                                                            \
         grid_tile2_kernel<S, 8, true><<<(unsigned)max_items, 128, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko,   \
                                                                                 vo, items, nitems, t_re, t_im, t_w);   \
-        grid_tile2_kernel<S, 2><<<(unsigned)max_items, 32, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko, vo,      \
+        grid_tile2_kernel<S, 2, true><<<(unsigned)max_items, 32, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko, vo, \
                                                                          items, nitems, t_re, t_im, t_w);              \
         break;
                     PDSB_TILE2(10)       // pillbox, box sums with npixels = 1
