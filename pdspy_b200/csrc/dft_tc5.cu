@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
     __shared__ __align__(8) uint64_t a_full[2];                 // A buffer written     (epilogue -> MMA)
     __shared__ uint32_t tmem_base_s;
     __shared__ float4 vx[T5_M];                  // pass-end exchange between the two halves of a uv point
+    __shared__ float2 ctab[T5_KT / 2][T5_M];     // (cos, sin) of j column steps of uv row r: ctab[j][r], 32 KB
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int plane0 = blockIdx.z * pg, sp = blockIdx.y;
@@ -430,17 +431,32 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
 
         // A operand of K tile kl: row `row` = trig of this uv point at the tile's 64 columns, fp16 hi + lo,
         // written to TMEM lane `row`; this thread does half of the columns, each from its exact phase
+        // The column phase of this thread's first column is exact (fixed point -> sincospif); the other 31
+        // come from it by the angle-addition formulas with the per-uv step table ctab (one sincospif per K
+        // tile and thread instead of 32; 1.2e-7 instead of 6e-8 on a factor that is split to 22 bits anyway).
+        {
+            constexpr int HALF_K = T5_KT / 2;
+#pragma unroll 1
+            for (int j = half_id * (HALF_K / 2); j < (half_id + 1) * (HALF_K / 2); j++) {
+                float cj, sj;
+                t5_trig(Hu, 2 * j, cj, sj);
+                ctab[j][row] = make_float2(cj, sj);
+            }
+            asm volatile("bar.sync 5, %0;" ::"n"(T5_EPI_THREADS) : "memory");        // epilogue warps only
+        }
         auto gen_a = [&](int kl) {
             constexpr int HALF_K = T5_KT / 2;
             const uint32_t ab = lane_base + (uint32_t)(T5_ACOL + (kl & 1) * T5_ABUF + half_id * (HALF_K / 2));
             const int n0 = 2 * ((kt0 + kl) * T5_KT + half_id * HALF_K) + hx2;
+            float c0, s0;
+            t5_trig(Hu, n0, c0, s0);
 #pragma unroll 1
             for (int kc = 0; kc < HALF_K / 8; kc++) {
                 __half ch[8], cl[8], sh[8], sl[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
-                    float cf, sf;
-                    t5_trig(Hu, n0 + 2 * (kc * 8 + e), cf, sf);
+                    const float2 d = ctab[kc * 8 + e][row];
+                    const float cf = c0 * d.x - s0 * d.y, sf = s0 * d.x + c0 * d.y;
                     t5_split(cf, ch[e], cl[e]);
                     t5_split(sf, sh[e], sl[e]);
                 }
