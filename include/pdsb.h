@@ -264,8 +264,9 @@ int pdsb_clean_restore(const double *model, const double *clean_beam, const doub
  * PDSB_ERR_ARG. */
 int pdsb_set_dft_variant(int variant);
 int pdsb_set_dft_split(int nsplit);          /* 0 = auto */
-/* Register-resident FMA microbenchmark on all SMs: variant 0 = FFMA, 1 = FFMA2 (f32x2).
- * Returns achieved TFLOP/s (2 flop per FMA lane). */
+/* Register-resident microbenchmarks on all SMs: variant 0 = FFMA, 1 = FFMA2 (f32x2), 2-10 = the DFT inner
+ * loop's operand patterns (registers / LDS.128 broadcast / constant bank), 11 = mma.sync TF32, 12 = mma.sync
+ * fp16, 13 = DFMA (fp64).  Returns achieved TFLOP/s (2 flop per FMA lane). */
 int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms);
 
 #ifdef __cplusplus
