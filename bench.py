@@ -605,6 +605,32 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt[0]), float(tt[1]), float(tt[2]) / max(1, k_n.value), ll_v
 
+    # ---- extra: the reference's own algorithm (galario: FFT + bilinear interpolation) on the GPU, this rank's shard ----
+    fft_out = np.empty(4)
+
+    def step_fft(image, kind):
+        _lib.check(L.pdsb_loglike_fft(like.ds.handle, _lib.ptr(image), n, nf, kind, float(dxy), float(dra), float(ddec),
+                                      _lib.ptr(fft_out)))
+    for _ in range(2):
+        step_fft(dcube, _lib.DEVICE)
+    barrier()
+    fevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in fevs:
+        flush.zero_()
+        e0.record()
+        step_fft(dcube, _lib.DEVICE)
+        e1.record()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_fft(pinned.array, _lib.HOST)
+    barrier()
+    fft_e2e_s = time.perf_counter() - t0
+    tt = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in fevs), fft_e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    fft_ms, fft_e2e_s = float(tt[0]), float(tt[1])
+
     tc5_ms, tc5_e2e_s, tc5_kernel_ms, ll_tc5 = time_variant(200, b"dft_tc5")
     tc_ms, tc_e2e_s, tc_kernel_ms, ll_tc = time_variant(103, b"dft_mma")
 
@@ -686,6 +712,16 @@ def main():
                 "accumulators and A operand in TMEM, B through a bulk-TMA ring, warp-specialised; fp16 hi+lo split "
                 "operands, 3 MMAs per product, fp32 accumulate; dft_tc5.cu, pdsb_set_dft_variant(200))",
                 tc5_ms, tc5_e2e_s, tc5_kernel_ms, ll_tc5, "bf16_tflops_sustained"),
+            "galario_fft_algorithm": {
+                "what": "the reference's OWN algorithm for this step on the GPU - galario's FFT + bilinear interpolation "
+                        "(pdsb_loglike_fft, fp64, restated from galario's published algorithm) + the same chi^2; it "
+                        "carries galario's interpolation error (1e-3..4e-2 of max|V|), which the direct transform of "
+                        "value / e2e does not; pairs/s counts the pairs the result represents, as in --impl reference; "
+                        "NOT used for value / e2e; chi^2 of this rank's uv shard, no all-reduce",
+                "ms_per_step": fft_ms / args.steps, "value": pairs_step * args.steps / (fft_ms * 1e-3), "unit": UNIT,
+                "e2e": {"value": pairs_step * args.steps / fft_e2e_s, "unit": UNIT, "ms_per_step": fft_e2e_s / args.steps * 1e3,
+                        "h2d_bytes_per_step": int(cube.nbytes) * world, "d2h_bytes_per_step": 32 * world},
+                "lnlike_shard": float(fft_out[3])},
             "mma_sync_variant": tc_entry(
                 "same step with the experimental opt-in DFT kernel on the warp-level tensor-core path (mma.sync "
                 "m16n8k16, same operand split; dft_mma.cu, pdsb_set_dft_variant(103))",

@@ -138,6 +138,17 @@ int pdsb_sample_image_ex(pdsb_dataset *ds, const double *image, int ny, int nx, 
 int pdsb_loglike_ex(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind,
                     double dxy, double dRA, double dDec, const double *chan_scale, double ff_flux,
                     double ff_x0, double ff_y0, double *chi2, double *lnlike);
+/* The reference's OWN algorithm for the same call, for numerical continuity with galario-based runs:
+ * galario.double.sampleImage as interpolate_model.py:23-27 uses it - FFT of the (row-flipped, shifted)
+ * image, bilinear interpolation at (|u|/du, n/2 + v/du), conjugate for u < 0, phase shift, imag -> -imag -
+ * restated from galario's published algorithm (parity unpinned).  O(n^2 log n + nuv)
+ * instead of the direct transform's O(n^2 nuv), at the price of galario's interpolation error (1e-3..4e-2
+ * of max|V| off the FFT grid).  Square images, side a power of two <= 4096.
+ *   pdsb_loglike_fft: out[0..3] = sum (d.re-m.re)^2 w, sum (d.im-m.im)^2 w, L, lnlike (as pdsb_chi2). */
+int pdsb_sample_image_fft(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy,
+                          double dRA, double dDec, double *out_real, double *out_imag, int out_kind);
+int pdsb_loglike_fft(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy,
+                     double dRA, double dDec, double *out);
 /* Asynchronous variant for multi-GPU runs: chi2 per channel is left in DEVICE memory
  * (chi2_dev[nf]) on the library stream, ready for an NCCL all-reduce over uv shards; no host
  * synchronisation.  pdsb_dataset_logsum returns this shard's L. */

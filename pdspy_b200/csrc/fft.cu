@@ -14,20 +14,27 @@ __device__ __forceinline__ unsigned bitrev(unsigned x, int bits) { return __brev
 //   pass 0: row r' of the shifted input: element c comes from x[(r'+h)%n][(c+h)%n] (real/imag planes with
 //           element stride `estride`), result b goes to T[b][r']           (transpose)
 //   pass 1: row b of T, result a goes to Y[(a+h)%n][(b+h)%n]              (fftshift on output)
+// Batched over blockIdx.y = plane: pass-0 input plane p starts p * in_pstride elements further (1 for a
+// channel-fastest cube with estride = nf) and may be read with its rows reversed (flip); the transposed
+// intermediate of plane p is T + p n^2; the pass-1 result element (A, B) of plane p goes to
+// tout[(A n + B) * o_estride + p * o_pstride].
 __global__ void __launch_bounds__(512) ifft_rows_kernel(const double *__restrict__ in_re,
                                                         const double *__restrict__ in_im, int64_t estride,
                                                         const double2 *__restrict__ tin, double2 *__restrict__ tout,
-                                                        int n, int logn, int pass)
+                                                        int n, int logn, int pass, int flip = 0, int64_t in_pstride = 0,
+                                                        int64_t o_estride = 1, int64_t o_pstride = 0)
 {
     extern __shared__ double2 srow[];
     const int row = blockIdx.x, h = n / 2;
+    const int64_t plane = blockIdx.y, nn = (int64_t)n * n;
     for (int c = threadIdx.x; c < n; c += blockDim.x) {
         double2 val;
         if (pass == 0) {
-            const int64_t src = ((int64_t)((row + h) % n) * n + (c + h) % n) * estride;
+            const int rs = (row + h) % n;
+            const int64_t src = ((int64_t)(flip ? n - 1 - rs : rs) * n + (c + h) % n) * estride + plane * in_pstride;
             val = make_double2(in_re[src], in_im ? in_im[src] : 0.0);
         } else {
-            val = tin[(int64_t)row * n + c];
+            val = tin[plane * nn + (int64_t)row * n + c];
         }
         srow[bitrev((unsigned)c, logn)] = val;
     }
@@ -47,8 +54,8 @@ __global__ void __launch_bounds__(512) ifft_rows_kernel(const double *__restrict
         __syncthreads();
     }
     for (int b = threadIdx.x; b < n; b += blockDim.x) {
-        if (pass == 0) tout[(int64_t)b * n + row] = srow[b];
-        else tout[(int64_t)((b + h) % n) * n + (row + h) % n] = srow[b];
+        if (pass == 0) tout[plane * nn + (int64_t)b * n + row] = srow[b];
+        else tout[((int64_t)((b + h) % n) * n + (row + h) % n) * o_estride + plane * o_pstride] = srow[b];
     }
 }
 
@@ -63,6 +70,34 @@ __global__ void __launch_bounds__(256) invert_combine_kernel(const double2 *__re
     const double im = yim[q].x;                                   // ifft2 * imsize^2: the 1/n^2 cancels
     const double cv = yconv[q].x / ((double)n * (double)n);
     image[((int64_t)A * n + (n - 1 - B)) * nch + ch] = im / cv;
+}
+
+static int fft_attr()
+{
+    static bool attr = false;
+    if (!attr) {
+        PDSB_CUDA(cudaFuncSetAttribute(ifft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+        attr = true;
+    }
+    return PDSB_OK;
+}
+
+// Y[(A n + B) nf + i] = fftshift( sum_{r,c} X_i[r, c] exp(+2 pi i (A r + B c) / n) ) over both axes, where
+// X_i = ifftshift of plane i of the cube [n, n, nf] (rows reversed first when flip): the unnormalised
+// inverse-sign 2-D transform of every channel at once, channel fastest in the output.  T: [nf, n, n] scratch.
+int fft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Y)
+{
+    Context &c = ctx();
+    int logn = 0;
+    while ((1 << logn) < n) logn++;
+    PDSB_CHECK(fft_attr());
+    const int threads = n / 2 < 512 ? (n / 2 < 32 ? 32 : n / 2) : 512;
+    const size_t smem = (size_t)n * sizeof(double2);
+    LaunchScope ls("fft2_planes");
+    ifft_rows_kernel<<<dim3(n, nf), threads, smem, c.stream>>>(cube_dev, nullptr, nf, nullptr, T, n, logn, 0, flip, 1);
+    ifft_rows_kernel<<<dim3(n, nf), threads, smem, c.stream>>>(nullptr, nullptr, 0, T, Y, n, logn, 1, 0, 0, nf, 1);
+    PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
 }
 
 }  // namespace pdsb
@@ -101,11 +136,7 @@ extern "C" int pdsb_invert_image(const double *g_real, const double *g_imag, con
     double2 *T = c.stage_c.as<double2>(), *Yc = T + nn, *Yi = Yc + nn;
     const int threads = n / 2 < 512 ? (n / 2 < 32 ? 32 : n / 2) : 512;
     const size_t smem = (size_t)n * sizeof(double2);
-    static bool attr = false;
-    if (!attr) {
-        PDSB_CUDA(cudaFuncSetAttribute(ifft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-        attr = true;
-    }
+    PDSB_CHECK(fft_attr());
     auto ifft2 = [&](const double *re, const double *im, int64_t estride, double2 *Y) -> int {
         LaunchScope ls("invert_ifft2");
         ifft_rows_kernel<<<n, threads, smem, c.stream>>>(re, im, estride, nullptr, T, n, logn, 0);

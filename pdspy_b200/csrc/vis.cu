@@ -234,6 +234,48 @@ __global__ void __launch_bounds__(256) chisq_ch0_kernel(const double *__restrict
     if (threadIdx.x == 0) blockpart[blockIdx.x] = s;
 }
 
+// ---------------------------------------------------------------------------------
+// galario's algorithm, as the reference calls it (interpolate_model.py:23-27): bilinear interpolation of
+// F = fftshift_rows(rfft2(fftshift(A))), A = image[::-1, :, i, 0], at (row n/2 + v/du, column |u|/du),
+// du = 1/(n dxy); mirrored row and conjugate for u < 0; times exp(+2 pi i (u dRA + v dDec)); then the
+// reference's imag -> -imag.  Ysh is fft2_planes' output: F[R][b] = conj(Ysh[(R n + (b + n/2) % n) nf + i]);
+// row n of F is the periodic copy of row 0.  One thread per (visibility, channel), channel fastest.
+__global__ void __launch_bounds__(256) fft_sample_kernel(const double2 *__restrict__ Ysh, const double *__restrict__ u,
+                                                         const double *__restrict__ v, int64_t nuv, int64_t nuvh, int n,
+                                                         int nf, double dxy, double dRA, double dDec,
+                                                         double *__restrict__ out_re, double *__restrict__ out_im)
+{
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= nuv * nf) return;
+    const int64_t k = idx / nf;
+    const int i = (int)(idx % nf);
+    const double uu = k < nuvh ? u[k] : -u[k - nuvh], vv = k < nuvh ? v[k] : -v[k - nuvh];   // Hermitian second half
+    const double du = 1.0 / ((double)n * dxy);
+    const bool uneg = uu < 0.0;
+    const double indu = fabs(uu) / du, indv = (double)n / 2.0 + (uneg ? -vv : vv) / du;
+    double fu = floor(indu), fv = floor(indv);
+    const double t = indu - fu, sfrac = indv - fv;
+    // baselines beyond the image's Nyquist range have no cell: clamp (galario refuses them)
+    fu = fmin(fmax(fu, 0.0), (double)(n / 2));
+    fv = fmin(fmax(fv, 0.0), (double)n);
+    const int cu0 = (int)fu, cu1 = cu0 + 1 < n / 2 ? cu0 + 1 : n / 2;
+    const int rv0 = (int)fv, rv1 = rv0 + 1 < n ? rv0 + 1 : n;
+    const int h = n / 2;
+    auto F = [&](int R, int b) -> double2 {
+        const double2 y = Ysh[((int64_t)(R % n) * n + (b + h) % n) * nf + i];
+        return make_double2(y.x, -y.y);
+    };
+    const double2 f00 = F(rv0, cu0), f01 = F(rv0, cu1), f10 = F(rv1, cu0), f11 = F(rv1, cu1);
+    const double w00 = (1 - t) * (1 - sfrac), w01 = t * (1 - sfrac), w10 = (1 - t) * sfrac, w11 = t * sfrac;
+    double vr = w00 * f00.x + w01 * f01.x + w10 * f10.x + w11 * f11.x;
+    double vi = w00 * f00.y + w01 * f01.y + w10 * f10.y + w11 * f11.y;
+    if (uneg) vi = -vi;
+    double ps, pc;
+    sincos(kTwoPi * (uu * dRA + vv * dDec), &ps, &pc);
+    out_re[idx] = vr * pc - vi * ps;
+    out_im[idx] = -(vr * ps + vi * pc);
+}
+
 static int reduce_blocks(const double *blockpart, int nb, int ncol, double *out_dev)
 {
     LaunchScope ls("reduce_columns");
@@ -626,6 +668,86 @@ int pdsb_loglike_batch(pdsb_dataset *ds, const double *images, int nwalkers, int
                        double dxy, const double *dRA, const double *dDec, double *lnlike)
 {
     return loglike_impl(ds, images, nwalkers, ny, nx, nf, image_kind, dxy, dRA, dDec, nullptr, lnlike);
+}
+
+// model visibilities by galario's FFT + bilinear algorithm into device arrays [nuv, nf]
+static int run_fft_sample(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
+                          double dDec, double *ore, double *oim)
+{
+    Context &c = ctx();
+    PDSB_REQUIRE(ds && image, "dataset/image");
+    PDSB_REQUIRE(n >= 2 && n <= 4096 && (n & (n - 1)) == 0, "the FFT path needs a square image, side a power of two <= 4096");
+    PDSB_REQUIRE(nf > 0 && dxy > 0.0, "nf/dxy");
+    const double *img_dev = nullptr;
+    const size_t nn = (size_t)n * n;
+    PDSB_CHECK(to_device(image, image_kind, nn * nf * sizeof(double), c.img64, (const void **)&img_dev));
+    PDSB_CHECK(c.folded.ensure(2 * nn * nf * sizeof(double2)));            // [T | Y]: the DFT's scratch, free here
+    double2 *T = c.folded.as<double2>(), *Y = T + nn * nf;
+    PDSB_CHECK(fft2_planes(img_dev, n, nf, 1, T, Y));
+    LaunchScope ls("fft_sample");
+    fft_sample_kernel<<<ceil_div(ds->nuv * nf, 256), 256, 0, c.stream>>>(Y, ds->u, ds->v, ds->nuv, ds->nuvh, n, nf, dxy,
+                                                                        dRA, dDec, ore, oim);
+    PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
+}
+
+int pdsb_sample_image_fft(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
+                          double dDec, double *out_real, double *out_imag, int out_kind)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ds && out_real && out_imag, "dataset/outputs");
+    Context &c = ctx();
+    if (ds->nuv == 0) return PDSB_OK;
+    const size_t bytes = (size_t)ds->nuv * nf * sizeof(double);
+    double *ore = out_real, *oim = out_imag;
+    if (out_kind == PDSB_HOST) {
+        PDSB_CHECK(c.stage_a.ensure(bytes));
+        PDSB_CHECK(c.stage_b.ensure(bytes));
+        ore = c.stage_a.as<double>();
+        oim = c.stage_b.as<double>();
+    }
+    PDSB_CHECK(run_fft_sample(ds, image, n, nf, image_kind, dxy, dRA, dDec, ore, oim));
+    if (out_kind == PDSB_HOST) {
+        PDSB_CUDA(cudaMemcpyAsync(out_real, ore, bytes, cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, bytes, cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return PDSB_OK;
+}
+
+int pdsb_loglike_fft(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
+                     double dDec, double *out)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ds && out, "dataset/out");
+    PDSB_REQUIRE(ds->has_data && ds->nf == nf, "dataset has no data or a different channel count");
+    Context &c = ctx();
+    const int64_t cnt = ds->nuv * nf;
+    if (cnt == 0) {
+        out[0] = out[1] = out[2] = 0.0;
+        out[3] = -0.0;
+        return PDSB_OK;
+    }
+    PDSB_CHECK(c.stage_a.ensure((size_t)cnt * sizeof(double)));
+    PDSB_CHECK(c.stage_b.ensure((size_t)cnt * sizeof(double)));
+    double *mr = c.stage_a.as<double>(), *mi = c.stage_b.as<double>();
+    PDSB_CHECK(run_fft_sample(ds, image, n, nf, image_kind, dxy, dRA, dDec, mr, mi));
+    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (cnt + 255) / 256);
+    PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * 3 * sizeof(double)));
+    {
+        LaunchScope ls("chi2_flat");
+        chi2_flat_kernel<<<nb, 256, 0, c.stream>>>(ds->re, ds->im, ds->w, mr, mi, cnt, c.red.as<double>());
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CHECK(reduce_blocks(c.red.as<double>(), nb, 3, c.red.as<double>() + (size_t)nb * 3));
+    double h[3];
+    PDSB_CUDA(cudaMemcpyAsync(h, c.red.as<double>() + (size_t)nb * 3, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    out[0] = h[0];
+    out[1] = h[1];
+    out[2] = h[2];
+    out[3] = -0.5 * h[0] - h[2] + -0.5 * h[1] - h[2];
+    return PDSB_OK;
 }
 
 int pdsb_chi2(const double *d_real, const double *d_imag, const double *weights, const double *m_real,

@@ -1,7 +1,8 @@
 """GPU drop-ins for the hot-path members of pdspy.interferometry
 (pdspy/interferometry/__init__.py:1-18): same names and call signatures."""
 from .visibilities import Visibilities, VisibilitiesObject
-from .interpolate_model import interpolate_model, model_visibilities, loglike_image, loglike_images
+from .interpolate_model import (interpolate_model, model_visibilities, loglike_image, loglike_images,
+                                loglike_image_fft)
 from .grid import grid, freqcorrect, chisq
 from .average import average, center
 from .invert import invert

@@ -51,6 +51,27 @@ def interpolate_model(u, v, freq, model, nthreads=1, dRA=0., dDec=0.,
                                            float(dxy), float(dRA * arcsec), float(dDec * arcsec),
                                            _lib.ptr(real), _lib.ptr(imag), _lib.HOST))
 
+    elif code == "galario-fft":
+        # EXTENSION (not a value the reference knows): galario's own algorithm - FFT of the image + bilinear
+        # interpolation at the uv points (what code="galario" runs in the reference) - on the GPU, for numerical
+        # continuity with galario-based results; it carries galario's interpolation error, which the exact
+        # transform of code="galario" here does not.
+        dxy = (model.x[1] - model.x[0]) * arcsec
+        image = _cube(model)
+        ny, nx, nf = image.shape[:3]
+        if ny != nx:
+            raise ValueError("the FFT path needs a square image (as galario does)")
+        u = numpy.ascontiguousarray(u, dtype=numpy.float64)
+        v = numpy.ascontiguousarray(v, dtype=numpy.float64)
+        ds = dataset_for(u, v)
+        real = numpy.empty((u.size, nf))
+        imag = numpy.empty((u.size, nf))
+        if u.size > 0:
+            L = _lib.lib()
+            _lib.check(L.pdsb_sample_image_fft(ds.handle, _lib.ptr(image), nx, nf, _lib.HOST, float(dxy),
+                                               float(dRA * arcsec), float(dDec * arcsec), _lib.ptr(real),
+                                               _lib.ptr(imag), _lib.HOST))
+
     elif code == "galario-unstructured":
         # scattered points -> piecewise-linear interpolant on the nxy x nxy grid of dxy arcsec (Jy/pixel),
         # then the same transform as above (unstructured.py; parity unpinned: galario fork not available)
@@ -112,6 +133,21 @@ def model_visibilities(u, v, freq, model, dRA=0., dDec=0., flux_unc=1.0, extinct
         _lib.check(L.pdsb_sample_image_ex(ds.handle, image, ny, nx, nf, image_kind, float(dxy), x0, y0,
                                           _lib.ptr(scale), ff, x0, y0, _lib.ptr(real), _lib.ptr(imag), _lib.HOST))
     return Visibilities(u, v, freq, real, imag, numpy.ones(real.shape))
+
+
+def loglike_image_fft(data, model, dRA=0., dDec=0.):
+    """interpolate_model(code="galario-fft") + the visibility log-likelihood term in one device pass
+    (pdsb_loglike_fft).  Returns (lnlike, chi2_real, chi2_imag)."""
+    dxy = (model.x[1] - model.x[0]) * arcsec
+    image = _cube(model)
+    ny, nx, nf = image.shape[:3]
+    if ny != nx:
+        raise ValueError("the FFT path needs a square image (as galario does)")
+    ds = dataset_for(data.u, data.v, (data.real, data.imag, data.weights))
+    out = numpy.empty(4)
+    _lib.check(_lib.lib().pdsb_loglike_fft(ds.handle, _lib.ptr(image), nx, nf, _lib.HOST, float(dxy),
+                                          float(dRA * arcsec), float(dDec * arcsec), _lib.ptr(out)))
+    return float(out[3]), float(out[0]), float(out[1])
 
 
 def loglike_image(data, model, dRA=0., dDec=0., flux_unc=1.0, extinction=None, freefree=None,

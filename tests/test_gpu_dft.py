@@ -205,3 +205,50 @@ def test_dataset_cache_invalidation_on_in_place_change(gpu):
     b = interpolate_model(u, v, m.freq, m)
     ref = od.exact_dft(u, v, m.image, 0.1 * A)
     assert relerr(b, ref) < TOL and relerr(a, ref) > 1e-3
+
+
+@pytest.mark.parametrize("n,nf,nuv,herm", [(64, 2, 500, True), (128, 3, 1000, False), (256, 1, 3000, True)])
+def test_galario_fft_path_vs_restated_galario_algorithm(gpu, n, nf, nuv, herm):
+    """code="galario-fft": the reference's own algorithm (FFT + bilinear interpolation, oracle/dft.py:galario_like)
+    on the GPU, fp64 throughout: 1e-12 of max|V|; and the method gap to the exact transform is galario's."""
+    px = 0.05
+    img = synth.synth_image(n, nf, px, kind="disk")
+    m = synth.SynthImage(img, px, synth.synth_freq(nf))
+    if herm:
+        u, v = synth.synth_uv(nuv, px * A)
+    else:
+        rng = np.random.default_rng(n)
+        lim = 0.4 / (px * A)
+        u, v = rng.uniform(-lim, lim, nuv), rng.uniform(-lim, lim, nuv)
+    ref = od.galario_like(u, v, m.image, px * A, 0.04 * A, -0.03 * A)
+    vis = interpolate_model(u, v, m.freq, m, dRA=0.04, dDec=-0.03, code="galario-fft")
+    assert vis.real.shape == (nuv, nf)
+    assert relerr(vis, ref) < 1e-12
+    exact = interpolate_model(u, v, m.freq, m, dRA=0.04, dDec=-0.03)
+    gap = np.abs((vis.real - exact.real) + 1j * (vis.imag - exact.imag)).max() / np.abs(ref).max()
+    assert gap < 0.1                                   # the two methods describe the same sky
+
+
+def test_galario_fft_likelihood_and_grid_points(gpu):
+    """On FFT grid points (u, v multiples of du) interpolation is exact: the FFT path equals the exact transform
+    to rounding; and the fused likelihood equals the numpy expression on the FFT-path visibilities."""
+    from oracle import likelihood as ol
+    from pdspy_b200.interferometry import loglike_image_fft, Visibilities
+    n, px, nf = 64, 0.05, 2
+    img = synth.synth_image(n, nf, px, kind="disk")
+    m = synth.SynthImage(img, px, synth.synth_freq(nf))
+    du = 1.0 / (n * px * A)
+    rng = np.random.default_rng(8)
+    u = rng.integers(-n // 2 + 1, n // 2, 400) * du
+    v = rng.integers(-n // 2 + 1, n // 2, 400) * du
+    a = interpolate_model(u, v, m.freq, m, code="galario-fft")
+    b = interpolate_model(u, v, m.freq, m)
+    scale = np.abs(b.real + 1j * b.imag).max()
+    assert np.abs((a.real - b.real) + 1j * (a.imag - b.imag)).max() / scale < 2e-6     # fp32 products in b
+    u2, v2 = synth.synth_uv(800, px * A)
+    re, im, w = synth.synth_data(800, nf)
+    data = Visibilities(u2, v2, m.freq, re, im, w)
+    ll, c_re, c_im = loglike_image_fft(data, m, dRA=0.01, dDec=0.02)
+    vis = interpolate_model(u2, v2, m.freq, m, dRA=0.01, dDec=0.02, code="galario-fft")
+    ll_ref = ol.lnlike_vis_numpy(re, im, w, vis.real, vis.imag)
+    assert abs(ll - ll_ref) <= 1e-10 * abs(ll_ref)
