@@ -118,7 +118,8 @@ __device__ __forceinline__ void t5_mma(uint32_t tmem_d, uint32_t adesc_lo, uint3
         : "memory");
 }
 // A operand from TMEM (lane = row, two fp16 per column along K), B from shared memory
-__device__ __forceinline__ void t5_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t accumulate)
+__device__ __forceinline__ void t5_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t accumulate,
+                                          uint32_t bdesc_hi = T5_DESC_HI)
 {
     asm volatile(
         "{\n\t"
@@ -128,7 +129,7 @@ __device__ __forceinline__ void t5_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "r"(bdesc_lo), "r"(T5_IDESC), "r"(accumulate), "r"(T5_DESC_HI)
+        "r"(tmem_a), "r"(bdesc_lo), "r"(T5_IDESC), "r"(accumulate), "r"(bdesc_hi)
         : "memory");
 }
 __device__ __forceinline__ void t5_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
@@ -292,16 +293,17 @@ __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict_
 // ---- the kernel ----
 constexpr int T5_EPI_THREADS = 256;             // warps 0-7
 constexpr int T5_THREADS = T5_EPI_THREADS + 64; // + TMA warp + MMA warp
-// MODE 0: the product.  MODE 1 / 2 exist only when compiled with -DPDSB_TC5_PROBES (variants 201 / 202;
+// MODE 0: the product.  MODE 1 / 2 / 3 exist only when compiled with -DPDSB_TC5_PROBES (variants 201-203;
 // timing experiments, results are garbage): 1 = the epilogue warps hand the accumulators straight back,
-// which leaves the TMA + MMA pipeline running alone; 2 = additionally no TMA copies, the MMAs alone.
+// which leaves the TMA + MMA pipeline running alone; 2 = additionally no TMA copies, the MMAs alone;
+// 3 = as 2 with a 128-byte-swizzle B descriptor (same speed as the no-swizzle layout).
 // Measured on C3/4 (250k uv): full kernel 7.66 ms, MODE 1 7.22 ms, MODE 2 7.23 ms -> the kernel is bound by
 // the tcgen05.mma rate itself (~82 cycles per 128x128x16 TS-mode MMA against the 64-cycle floor).
 template <int MODE>
 __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams P, const unsigned char *__restrict__ Bg,
                                                                 int nkt, int pg)
 {
-    extern __shared__ __align__(128) unsigned char Bs[];        // T5_NSTAGE x 16 KB
+    extern __shared__ __align__(1024) unsigned char Bs[];       // T5_NSTAGE x 16 KB
     __shared__ __align__(8) uint64_t full_bar[T5_NSTAGE];       // TMA landed           (producer -> MMA)
     __shared__ __align__(8) uint64_t empty_bar[T5_NSTAGE];      // MMAs read the stage  (MMA commit -> producer)
     __shared__ __align__(8) uint64_t tmem_full[2];              // accumulator ready    (MMA commit -> epilogue)
@@ -393,6 +395,16 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                                 const uint32_t alo = a_buf + (uint32_t)((ty * 2 + 1) * T5_APART + sub * (T5_KSUB / 2) + ks * 8);
                                 const uint32_t bhi = b_s + (uint32_t)((ks * 2 * T5_KCHUNK_BYTES) >> 4);
                                 const uint32_t blo = b_s + (uint32_t)((T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                if (MODE == 3) {
+                                    // timing probe: the same MMAs with a 128-byte-swizzle K-major B descriptor
+                                    // (rows of 128 B, 8-row groups 1024 B apart, k-steps 32 B apart)
+                                    constexpr uint32_t dh = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+                                    const uint32_t b0 = (b_s & 0x3fffu) | (1u << 16);
+                                    t5_mma_ts(d, ahi, b0 + (uint32_t)((ks * 32) >> 4), (sub | ks) ? 1u : 0u, dh);
+                                    t5_mma_ts(d, ahi, b0 + (uint32_t)((T5_TILE_BYTES + ks * 32) >> 4), 1u, dh);
+                                    t5_mma_ts(d, alo, b0 + (uint32_t)((ks * 32) >> 4), 1u, dh);
+                                    continue;
+                                }
                                 t5_mma_ts(d, ahi, bhi, (sub | ks) ? 1u : 0u);
                                 t5_mma_ts(d, ahi, blo, 1u);
                                 t5_mma_ts(d, alo, bhi, 1u);
@@ -616,13 +628,18 @@ int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
     const int nkt = (npx + T5_KT - 1) / T5_KT;
     p.nchunk = (npy + T5_RC - 1) / T5_RC;
     PDSB_REQUIRE(p.nsplit >= 1 && p.nsplit <= nkt, "tc5 split");
+#ifdef PDSB_TC5_PROBES
+    constexpr size_t smem_bytes = (size_t)T5_NSTAGE * T5_UNIT_BYTES + 32768;     // slack: the swizzle probe reads wider
+#else
     constexpr size_t smem_bytes = (size_t)T5_NSTAGE * T5_UNIT_BYTES;
+#endif
     static bool attr_set = false;
     if (!attr_set) {
         PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
 #ifdef PDSB_TC5_PROBES
         PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
 #endif
         attr_set = true;
     }
@@ -634,6 +651,7 @@ int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
 #ifdef PDSB_TC5_PROBES
     if (c.dft_variant == DFT_VARIANT_TC5 + 1) dft_tc5_kernel<1><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
     else if (c.dft_variant == DFT_VARIANT_TC5 + 2) dft_tc5_kernel<2><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
+    else if (c.dft_variant == DFT_VARIANT_TC5 + 3) dft_tc5_kernel<3><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
     else
 #endif
         dft_tc5_kernel<0><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);

@@ -608,7 +608,7 @@ int pdsb_set_dft_variant(int variant)
     bool ok = variant == 0 || (variant >= 1 && variant <= dft_variant_count()) ||
               (variant >= DFT_VARIANT_MMA && variant <= DFT_VARIANT_MMA + 4) || variant == DFT_VARIANT_TC5;
 #ifdef PDSB_TC5_PROBES
-    ok = ok || variant == DFT_VARIANT_TC5 + 1 || variant == DFT_VARIANT_TC5 + 2;
+    ok = ok || (variant > DFT_VARIANT_TC5 && variant <= DFT_VARIANT_TC5 + 3);
 #endif
     PDSB_REQUIRE(ok, "unknown DFT kernel variant");
     ctx().dft_variant = variant;
