@@ -271,8 +271,8 @@ int pdsb_clean_restore(const double *model, const double *clean_beam, const doub
 /* ---- tuning / measurement ----------------------------------------------------------- */
 /* DFT kernel variant: 0 = auto (the FP32-pipe kernel the north star asks for);
  * 1..22 = FP32-pipe tilings; 100..104 = experimental mma.sync tensor-core kernels; 200 = experimental
- * tcgen05/TMEM tensor-core kernel.  All variants meet the same 1e-5 parity bound; anything else is
- * PDSB_ERR_ARG. */
+ * tcgen05/TMEM tensor-core kernel; 300 = all-fp64 reference kernel (1e-13, ~7x slower).  All variants meet
+ * the same 1e-5 parity bound; anything else is PDSB_ERR_ARG. */
 int pdsb_set_dft_variant(int variant);
 int pdsb_set_dft_split(int nsplit);          /* 0 = auto */
 /* Register-resident microbenchmarks on all SMs: variant 0 = FFMA, 1 = FFMA2 (f32x2), 2-10 = the DFT inner

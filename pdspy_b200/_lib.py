@@ -123,7 +123,7 @@ def lib():
         _inited = True
         kernel = os.environ.get("PDSPY_B200_DFT", "")          # initial DFT kernel: fp32 (default) | mma | tcgen05 | <int>
         if kernel:
-            variants = {"fp32": 0, "mma": 103, "tcgen05": 200}
+            variants = {"fp32": 0, "mma": 103, "tcgen05": 200, "fp64": 300}
             check(L.pdsb_set_dft_variant(variants[kernel] if kernel in variants else int(kernel)))
     return L
 

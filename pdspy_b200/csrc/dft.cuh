@@ -98,6 +98,11 @@ int launch_fold_tc5(const double *img_dev, unsigned char *B, double *scale_ws, i
 int tc5_auto_split(int64_t nuvh, int nf, int nx);
 int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx);
 
+// fp64 reference variant (dft_f64.cu), selected with pdsb_set_dft_variant(300)
+constexpr int DFT_VARIANT_F64 = 300;
+int launch_dft_f64(const double *img_dev, int ny, int nx, int nf, const double *u, const double *v, int64_t nuvh, double dxy,
+                   double2 *part);
+
 // fft.cu: inverse-sign 2-D transform of every channel of a cube, both-axes fftshift on input and output,
 // channel-fastest output (used by the galario-algorithm path of vis.cu)
 int fft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Y);

@@ -606,7 +606,8 @@ int pdsb_launch_count(int64_t *count)
 int pdsb_set_dft_variant(int variant)
 {
     bool ok = variant == 0 || (variant >= 1 && variant <= dft_variant_count()) ||
-              (variant >= DFT_VARIANT_MMA && variant <= DFT_VARIANT_MMA + 4) || variant == DFT_VARIANT_TC5;
+              (variant >= DFT_VARIANT_MMA && variant <= DFT_VARIANT_MMA + 4) || variant == DFT_VARIANT_TC5 ||
+              variant == DFT_VARIANT_F64;
 #ifdef PDSB_TC5_PROBES
     ok = ok || (variant > DFT_VARIANT_TC5 && variant <= DFT_VARIANT_TC5 + 3);
 #endif

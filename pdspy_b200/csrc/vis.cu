@@ -301,6 +301,15 @@ static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf
     PDSB_REQUIRE(dxy > 0.0, "dxy");
     const double *img_dev = nullptr;
     PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
+    if (c.dft_variant == DFT_VARIANT_F64) {
+        // fp64 throughout, straight from the fp64 cube (dft_f64.cu)
+        PDSB_CHECK(c.partial.ensure((size_t)nf * ds->nuvh * sizeof(double2)));
+        PDSB_CHECK(launch_dft_f64(img_dev, ny, nx, nf, ds->u, ds->v, ds->nuvh, dxy, c.partial.as<double2>()));
+        run->g = make_geom(ny, nx, nf, 32, dxy);
+        run->nsplit = 1;
+        run->plane_unscale = nullptr;
+        return PDSB_OK;
+    }
     if (c.dft_variant >= DFT_VARIANT_MMA) {
         // experimental: fp16-split operands on the tensor cores (dft_mma.cu: mma.sync; dft_tc5.cu: tcgen05)
         const bool tc5 = c.dft_variant >= DFT_VARIANT_TC5;
