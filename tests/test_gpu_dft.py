@@ -257,7 +257,7 @@ def test_galario_fft_likelihood_and_grid_points(gpu):
 @pytest.mark.parametrize("ny,nx,nf,nuv,herm", [(64, 64, 2, 400, True), (63, 65, 3, 333, False), (130, 34, 9, 64, True),
                                                (256, 256, 1, 2000, True), (17, 500, 1, 129, False)])
 def test_fp64_reference_kernel_vs_cpu_oracle(gpu, ny, nx, nf, nuv, herm):
-    """Variant 300 (all fp64, no fold): 1e-12 of max|V| from the exact CPU oracle - the on-device reference the
+    """Variant 300 (all fp64, no fold): 1e-11 of max|V| from the exact CPU oracle (both sum ~1e4-1e5 fp64 terms) - the on-device reference the
     full-size tests hold the other kernels to."""
     gpu.pdsb_set_dft_variant(300)
     rng = np.random.default_rng(ny * 31 + nx)
@@ -269,4 +269,4 @@ def test_fp64_reference_kernel_vs_cpu_oracle(gpu, ny, nx, nf, nuv, herm):
         u, v = rng.normal(0, 4e5, nuv), rng.normal(0, 4e5, nuv)
     ref = od.exact_dft(u, v, img, 0.05 * A, 0.021 * A, -0.034 * A)
     vis = interpolate_model(u, v, m.freq, m, dRA=0.021, dDec=-0.034)
-    assert relerr(vis, ref) < 1e-12
+    assert relerr(vis, ref) < 1e-11
