@@ -87,6 +87,31 @@ def test_every_uv_point_against_the_fp64_kernel(gpu, workload):
         assert err < 3e-6, (name, err)                 # what these kernels actually deliver
 
 
+@pytest.mark.parametrize("workload", ["C2", "C3"])
+def test_lnlike_against_the_fp64_kernel(gpu, workload):
+    """Full configs[1] / configs[2]: the fused log-likelihood and the per-channel chi^2 of the FP32-pipe default
+    against the same call on the fp64 kernel - 1e-9 (measured 1e-11 / 3e-9; north-star bound 1e-7); the
+    tensor-core kernels, whose fp32 accumulators round toward zero, stay within 1e-7 in the total."""
+    import pdspy_b200 as pb
+    c = synth.make_config(workload)
+    re, im, w = synth.synth_data(c["u"].size, c["nf"])
+    d = Visibilities(c["u"], c["v"], c["freq"], re, im, w)
+    out = {}
+    try:
+        for k in ("fp64", "fp32", "tcgen05", "mma"):
+            pb.set_dft_kernel(k)
+            out[k] = loglike_image(d, c["model"], dRA=c["dRA"], dDec=c["dDec"])
+    finally:
+        pb.set_dft_kernel("fp32")
+    ll0, chi0 = out["fp64"]
+    ll, chi = out["fp32"]
+    assert abs(ll - ll0) <= 1e-9 * abs(ll0)
+    assert np.all(np.abs(chi - chi0) <= 2e-8 * np.abs(chi0))
+    for k in ("tcgen05", "mma"):
+        assert abs(out[k][0] - ll0) <= 1e-7 * abs(ll0), k
+        assert np.all(np.abs(out[k][1] - chi0) <= 1e-6 * np.abs(chi0)), k
+
+
 def test_config4_full_gridding(gpu):
     """Full C4: 10M visibilities onto 2048^2.  Index maps equal numpy's; pillbox ordered == fast mode to
     rounding; total weight conserved; expsinc imaging map sums to 1; a 1%-subset re-gridded by the oracle
