@@ -631,6 +631,11 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     fft_ms, fft_e2e_s = float(tt[0]), float(tt[1])
 
+    # ---- parity of the timed step itself: the same likelihood on the all-fp64 kernel (dft_f64.cu, 1e-11 from the CPU oracle) ----
+    _lib.check(L.pdsb_set_dft_variant(300))
+    ll_f64 = step_device()
+    _lib.check(L.pdsb_set_dft_variant(0))
+
     tc5_ms, tc5_e2e_s, tc5_kernel_ms, ll_tc5 = time_variant(200, b"dft_tc5")
     tc_ms, tc_e2e_s, tc_kernel_ms, ll_tc = time_variant(103, b"dft_mma")
 
@@ -660,6 +665,7 @@ def main():
             "data": "synthetic", "config": describe(cfg, world),
             "likelihood_evals_per_s": args.steps / (total_ms * 1e-3),
             "lnlike": ll,
+            "lnlike_rel_diff_vs_fp64_kernel": abs(ll - ll_f64) / abs(ll_f64),
             "e2e": {"value": pairs_step * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(cube.nbytes) if shard_upload or world == 1 else int(cube.nbytes) * world,
                     "d2h_bytes_per_step": int((nf + 1) * 8) * world,
@@ -705,7 +711,8 @@ def main():
                                  "peak_source": "MEASURED_PEAKS.json %s (cuBLAS bf16 GEMM, sustained figure: kernel timed "
                                                 "inside a long step)" % peak_key,
                                  "counts": "2 flop x 3 split-product MACs per evaluated pixel-visibility pair, per rank"},
-                    "lnlike": llv, "lnlike_rel_diff_vs_default": abs(llv - ll) / abs(ll)}
+                    "lnlike": llv, "lnlike_rel_diff_vs_default": abs(llv - ll) / abs(ll),
+                    "lnlike_rel_diff_vs_fp64_kernel": abs(llv - ll_f64) / abs(ll_f64)}
         line["extras"] = {
             "tensor_core_variant": tc_entry(
                 "same step with the experimental opt-in DFT kernel on the 5th-generation tensor cores (tcgen05.mma, "
