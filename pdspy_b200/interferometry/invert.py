@@ -1,10 +1,14 @@
-"""invert(): dirty imaging, GPU drop-in for pdspy/interferometry/invert.py:8-92 (SURVEY.md section 8f
+"""invert(): dirty imaging on the GPU, drop-in for pdspy/interferometry/invert.py:8-92 (SURVEY.md section 8f
 rank 3; the reference's own smoke test tests/test.py:9 is exactly this call).
 
-grid(..., imaging=True), center() and the per-channel 2-D inverse FFT + gridding correction + x flip
-run in libpdsb (pdsb_grid, pdsb_center, pdsb_invert_image: a hand-written fp64 FFT); the pieces that are
-O(imsize^2) numpy set-up in the reference (image axes from fftfreq, the convolution function sampled on
-the uv grid :94-121) stay the reference's numpy expressions.  imsize must be a power of two."""
+Pipeline: grid(..., imaging=True) -> optional center() -> per-channel 2-D inverse FFT, division by the
+transform of the gridding kernel, x flip (pdsb_grid, pdsb_center, pdsb_invert_image: a hand-written fp64
+FFT).  Host side only prepares small things: the image axes and the gridding kernel sampled on the uv grid.
+
+Differences in HOW (not in what) from the reference: the beam / uv-taper variants of the data are built as
+a separate Visibilities instead of overwriting the caller's arrays and restoring them afterwards
+(invert.py:15-20, 24-29, 40-47), and the separable exp*sinc kernel map is formed as an outer product of
+two 1-D profiles.  imsize must be a power of two."""
 import numpy
 
 from .. import _lib
@@ -12,84 +16,73 @@ from ..constants import arcsec
 from ..imaging import Image
 from .average import center
 from .grid import grid
+from .visibilities import Visibilities
+
+_SINC_WIDTH, _EXP_WIDTH = 1.55, 2.52          # exp*sinc kernel of the gridder, in cells (invert.py:107-108)
+
+
+def _imaging_data(data, beam, uvtaper):
+    """The visibilities that actually get gridded: unit real part / zero imaginary part for the beam
+    (invert.py:15-20), weights times a Gaussian taper of width `uvtaper` kilo-lambda (invert.py:24-29)."""
+    if not beam and uvtaper is None:
+        return data
+    real, imag, weights = data.real, data.imag, data.weights
+    if beam:
+        real, imag = numpy.ones_like(data.real), numpy.zeros_like(data.imag)
+    if uvtaper is not None:
+        sigma = uvtaper * 1e3
+        weights = data.weights * numpy.exp(-0.5 * data.uvdist ** 2 / sigma ** 2)[:, numpy.newaxis]
+    return Visibilities(data.u, data.v, data.freq, real, imag, weights)
+
+
+def _axis(imsize, cell):
+    """Sky offsets of the image pixels in arcsec: fftshift(fftfreq(imsize, cell)) / arcsec (invert.py:57-58)."""
+    return numpy.fft.fftshift(numpy.fft.fftfreq(imsize, cell)) / arcsec
+
+
+def _profile_1d(x, cell, convolution):
+    """One-dimensional factor of the gridding kernel at uv offsets x (invert.py:94-121)."""
+    if convolution == "pillbox":
+        return numpy.where(numpy.abs(x) < 0.5 * cell, 1.0, 0.0)
+    g = numpy.sinc(x / (_SINC_WIDTH * cell)) * numpy.exp(-(x / (_EXP_WIDTH * cell)) ** 2)
+    return numpy.where(numpy.abs(x) < 3.0 * cell, g, 0.0)
+
+
+def kernel_map(convolution, uu, vv, cell):
+    """The gridding kernel sampled at the uv-grid points (rows follow vv, columns uu), scaled as the
+    reference scales it: pillbox = n_cells inside the central cell, exp*sinc normalised to sum n_cells."""
+    if convolution not in ("pillbox", "expsinc"):
+        raise ValueError("unknown convolution %r" % (convolution,))
+    m = numpy.outer(_profile_1d(vv, cell, convolution), _profile_1d(uu, cell, convolution))
+    if convolution == "pillbox":
+        return m * m.size
+    return m / m.sum() * m.size
 
 
 def invert(data, imsize=256, pixel_size=0.25, convolution="pillbox", mfs=False, weighting="natural",
            robust=2, npixels=0, centering=None, mode='continuum', beam=False, uvtaper=None,
            deterministic=True):
-
     if imsize & (imsize - 1) or imsize > 4096:
         raise NotImplementedError("the GPU invert() needs imsize to be a power of two <= 4096")
 
-    # If we are calculating the beam, set all of the real values to 1 and the imaginary data to 0
-    # (in place, restored below: exactly what the reference does, invert.py:15-20,40-42).
-    if beam:
-        real = data.real.copy()
-        imag = data.imag.copy()
-        data.real[:, :] = 1.
-        data.imag[:, :] = 0.
+    cell = 1.0 / (pixel_size * imsize * arcsec)              # uv cell of an image of imsize pixels (invert.py:33)
+    gridded = grid(_imaging_data(data, beam, uvtaper), gridsize=imsize, binsize=cell, convolution=convolution,
+                   mfs=mfs, imaging=True, weighting=weighting, robust=robust, npixels=npixels, mode=mode,
+                   deterministic=deterministic)
+    if centering is not None:
+        gridded = center(gridded, centering)
 
-    if type(uvtaper) != type(None):
-        taper = numpy.exp(-0.5 * data.uvdist ** 2 / (uvtaper * 1e3) ** 2)
-        weights = data.weights.copy()
-        for i in range(data.freq.size):
-            data.weights[:, i] *= taper
+    # grid() returns u, v flattened from meshgrid(uu, vv): the first row holds uu, the first column vv
+    uu = gridded.u[:imsize]
+    vv = gridded.v[::imsize]
+    conv = numpy.ascontiguousarray(kernel_map(convolution, uu, vv, cell))
 
-    binsize = 1.0 / (pixel_size * imsize * arcsec)
-    try:
-        gridded_data = grid(data, gridsize=imsize, binsize=binsize, convolution=convolution, mfs=mfs, imaging=True,
-                            weighting=weighting, robust=robust, npixels=npixels, mode=mode,
-                            deterministic=deterministic)
-    finally:
-        if beam:
-            data.real = real
-            data.imag = imag
-        if type(uvtaper) != type(None):
-            data.weights = weights
-
-    if type(centering) != type(None):
-        gridded_data = center(gridded_data, centering)
-
-    # fftfreq(n, d) = [0, 1, ..., n/2-1, -n/2, ..., -1] / (d*n)   (scipy.fftpack.fftfreq)
-    x = numpy.fft.fftshift(numpy.fft.fftfreq(imsize, binsize)) / arcsec
-    y = numpy.fft.fftshift(numpy.fft.fftfreq(imsize, binsize)) / arcsec
-
-    u = gridded_data.u.reshape((imsize, imsize))
-    v = gridded_data.v.reshape((imsize, imsize))
-    conv_func = {"pillbox": pillbox, "expsinc": exp_sinc}[convolution]
-    conv = numpy.ascontiguousarray(conv_func(u, v, binsize, binsize), dtype=numpy.float64)
-
-    nch = gridded_data.real.shape[1]
+    nch = gridded.real.shape[1]
     image = numpy.empty((imsize, imsize, nch, 1))
-    L = _lib.lib()
-    _lib.check(L.pdsb_invert_image(_lib.ptr(_lib.f64(gridded_data.real)), _lib.ptr(_lib.f64(gridded_data.imag)),
-                                   _lib.ptr(conv), imsize, nch, _lib.HOST, _lib.ptr(image)))
+    _lib.check(_lib.lib().pdsb_invert_image(_lib.ptr(_lib.f64(gridded.real)), _lib.ptr(_lib.f64(gridded.imag)),
+                                            _lib.ptr(conv), imsize, nch, _lib.HOST, _lib.ptr(image)))
+    if beam:                                                 # the beam peaks at exactly 1 (invert.py:84-87)
+        image /= image.max(axis=(0, 1), keepdims=True)
 
-    # Make sure the beam peaks at exactly 1 (invert.py:84-87).
-    if beam:
-        for i in range(nch):
-            image[:, :, i, 0] /= image[:, :, i, 0].max()
-
-    return Image(image, x=x, y=y, freq=gridded_data.freq)
-
-
-def pillbox(u, v, delta_u, delta_v):
-    """invert.py:94-103."""
-    m = 1
-    arr = numpy.ones(u.shape, dtype=float) * u.size
-    arr[numpy.abs(u) >= m * delta_u / 2] = 0
-    arr[numpy.abs(v) >= m * delta_v / 2] = 0
-    return arr
-
-
-def exp_sinc(u, v, delta_u, delta_v):
-    """invert.py:105-121."""
-    alpha1 = 1.55
-    alpha2 = 2.52
-    m = 6
-    arr = numpy.sinc(u / (alpha1 * delta_u)) * numpy.exp(-1 * (u / (alpha2 * delta_u)) ** 2) * \
-        numpy.sinc(v / (alpha1 * delta_v)) * numpy.exp(-1 * (v / (alpha2 * delta_v)) ** 2)
-    arr[numpy.abs(u) >= m * delta_u / 2] = 0
-    arr[numpy.abs(v) >= m * delta_v / 2] = 0
-    arr = arr / arr.sum() * arr.size
-    return arr
+    axis = _axis(imsize, cell)
+    return Image(image, x=axis, y=axis.copy(), freq=gridded.freq)
