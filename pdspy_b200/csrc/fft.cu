@@ -38,16 +38,23 @@ __global__ void __launch_bounds__(512) ifft_rows_kernel(const double *__restrict
         }
         srow[bitrev((unsigned)c, logn)] = val;
     }
+    // twiddle table tw[j] = exp(+2 pi i j / n), j < n/2, once per block (the butterflies of stage s use every
+    // (n / 2^s)-th entry) instead of one sincospi per butterfly
+    double2 *tw = srow + n;
+    for (int j = threadIdx.x; j < n / 2; j += blockDim.x) {
+        double ws, wc;
+        sincospi(2.0 * (double)j / (double)n, &ws, &wc);
+        tw[j] = make_double2(wc, ws);
+    }
     __syncthreads();
     for (int s = 1; s <= logn; s++) {
-        const int m = 1 << s, half = m >> 1;
+        const int m = 1 << s, half = m >> 1, tstep = n >> s;
         for (int idx = threadIdx.x; idx < n / 2; idx += blockDim.x) {
             const int k = idx & (half - 1);
             const int j = ((idx >> (s - 1)) << s) + k;
-            double ws, wc;
-            sincospi(2.0 * (double)k / (double)m, &ws, &wc);        // inverse transform: +i
+            const double2 w = tw[k * tstep];                        // inverse transform: +i
             const double2 a = srow[j], b = srow[j + half];
-            const double tr = wc * b.x - ws * b.y, ti = wc * b.y + ws * b.x;
+            const double tr = w.x * b.x - w.y * b.y, ti = w.x * b.y + w.y * b.x;
             srow[j] = make_double2(a.x + tr, a.y + ti);
             srow[j + half] = make_double2(a.x - tr, a.y - ti);
         }
@@ -76,7 +83,7 @@ static int fft_attr()
 {
     static bool attr = false;
     if (!attr) {
-        PDSB_CUDA(cudaFuncSetAttribute(ifft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+        PDSB_CUDA(cudaFuncSetAttribute(ifft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 24));
         attr = true;
     }
     return PDSB_OK;
@@ -92,7 +99,7 @@ int fft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, dou
     while ((1 << logn) < n) logn++;
     PDSB_CHECK(fft_attr());
     const int threads = n / 2 < 512 ? (n / 2 < 32 ? 32 : n / 2) : 512;
-    const size_t smem = (size_t)n * sizeof(double2);
+    const size_t smem = (size_t)n * sizeof(double2) * 3 / 2;          // row + twiddle table
     LaunchScope ls("fft2_planes");
     ifft_rows_kernel<<<dim3(n, nf), threads, smem, c.stream>>>(cube_dev, nullptr, nf, nullptr, T, n, logn, 0, flip, 1);
     ifft_rows_kernel<<<dim3(n, nf), threads, smem, c.stream>>>(nullptr, nullptr, 0, T, Y, n, logn, 1, 0, 0, nf, 1);
@@ -135,7 +142,7 @@ extern "C" int pdsb_invert_image(const double *g_real, const double *g_imag, con
     PDSB_CHECK(c.stage_c.ensure((size_t)3 * nn * sizeof(double2)));
     double2 *T = c.stage_c.as<double2>(), *Yc = T + nn, *Yi = Yc + nn;
     const int threads = n / 2 < 512 ? (n / 2 < 32 ? 32 : n / 2) : 512;
-    const size_t smem = (size_t)n * sizeof(double2);
+    const size_t smem = (size_t)n * sizeof(double2) * 3 / 2;          // row + twiddle table
     PDSB_CHECK(fft_attr());
     auto ifft2 = [&](const double *re, const double *im, int64_t estride, double2 *Y) -> int {
         LaunchScope ls("invert_ifft2");

@@ -1,0 +1,17 @@
+"""Driver for ncu: one C3 likelihood through the galario-algorithm path (pdsb_loglike_fft), device-resident cube."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pdspy_b200 as pb
+from pdspy_b200 import _lib, synth
+A = synth.ARCSEC
+c = synth.make_config("C3")
+re, im, w = synth.synth_data(c["u"].size, c["nf"])
+ds = pb.Dataset(c["u"], c["v"]); ds.set_data(re, im, w)
+cube = pb.DeviceBuffer.from_numpy(np.ascontiguousarray(c["model"].image[:, :, :, 0]))
+out = np.empty(4)
+L = _lib.lib()
+for _ in range(2):
+    _lib.check(L.pdsb_loglike_fft(ds.handle, _lib.ptr(cube), c["npix"], c["nf"], _lib.DEVICE, c["pixelsize"] * A, c["dRA"] * A,
+                                  c["dDec"] * A, _lib.ptr(out)))
+print("lnlike", out[3])
