@@ -240,17 +240,18 @@ __global__ void __launch_bounds__(256) chisq_ch0_kernel(const double *__restrict
 // du = 1/(n dxy); mirrored row and conjugate for u < 0; times exp(+2 pi i (u dRA + v dDec)); then the
 // reference's imag -> -imag.  Ysh is fft2_planes' output: F[R][b] = conj(Ysh[(R n + (b + n/2) % n) nf + i]);
 // row n of F is the periodic copy of row 0.  One thread per (visibility, channel), channel fastest.
-__global__ void __launch_bounds__(256) fft_sample_kernel(const double2 *__restrict__ Ysh, const double *__restrict__ u,
-                                                         const double *__restrict__ v, int64_t nuv, int64_t nuvh, int n,
-                                                         int nf, double dxy, double dRA, double dDec,
-                                                         double *__restrict__ out_re, double *__restrict__ out_im)
+struct FftSampleArgs {
+    const double2 *Ysh;
+    const double *u, *v;
+    int64_t nuv, nuvh;
+    int n, nf;
+    double dxy, dRA, dDec;
+};
+__device__ __forceinline__ double2 fft_sample_one(const FftSampleArgs &P, int64_t k, int i)
 {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= nuv * nf) return;
-    const int64_t k = idx / nf;
-    const int i = (int)(idx % nf);
-    const double uu = k < nuvh ? u[k] : -u[k - nuvh], vv = k < nuvh ? v[k] : -v[k - nuvh];   // Hermitian second half
-    const double du = 1.0 / ((double)n * dxy);
+    const int n = P.n;
+    const double uu = k < P.nuvh ? P.u[k] : -P.u[k - P.nuvh], vv = k < P.nuvh ? P.v[k] : -P.v[k - P.nuvh];   // Hermitian half
+    const double du = 1.0 / ((double)n * P.dxy);
     const bool uneg = uu < 0.0;
     const double indu = fabs(uu) / du, indv = (double)n / 2.0 + (uneg ? -vv : vv) / du;
     double fu = floor(indu), fv = floor(indv);
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(256) fft_sample_kernel(const double2 *__restri
     const int rv0 = (int)fv, rv1 = rv0 + 1 < n ? rv0 + 1 : n;
     const int h = n / 2;
     auto F = [&](int R, int b) -> double2 {
-        const double2 y = Ysh[((int64_t)(R % n) * n + (b + h) % n) * nf + i];
+        const double2 y = P.Ysh[((int64_t)(R % n) * n + (b + h) % n) * P.nf + i];
         return make_double2(y.x, -y.y);
     };
     const double2 f00 = F(rv0, cu0), f01 = F(rv0, cu1), f10 = F(rv1, cu0), f11 = F(rv1, cu1);
@@ -271,9 +272,44 @@ __global__ void __launch_bounds__(256) fft_sample_kernel(const double2 *__restri
     double vi = w00 * f00.y + w01 * f01.y + w10 * f10.y + w11 * f11.y;
     if (uneg) vi = -vi;
     double ps, pc;
-    sincos(kTwoPi * (uu * dRA + vv * dDec), &ps, &pc);
-    out_re[idx] = vr * pc - vi * ps;
-    out_im[idx] = -(vr * ps + vi * pc);
+    sincos(kTwoPi * (uu * P.dRA + vv * P.dDec), &ps, &pc);
+    return make_double2(vr * pc - vi * ps, -(vr * ps + vi * pc));
+}
+
+__global__ void __launch_bounds__(256) fft_sample_kernel(const FftSampleArgs P, double *__restrict__ out_re,
+                                                         double *__restrict__ out_im)
+{
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= P.nuv * P.nf) return;
+    const double2 m = fft_sample_one(P, idx / P.nf, (int)(idx % P.nf));
+    out_re[idx] = m.x;
+    out_im[idx] = m.y;
+}
+
+// the same sample fused with the likelihood sums of chi2_flat_kernel: the model visibilities never reach memory
+__global__ void __launch_bounds__(256) fft_chi2_kernel(const FftSampleArgs P, const double *__restrict__ dre,
+                                                       const double *__restrict__ dim, const double *__restrict__ w,
+                                                       double *__restrict__ blockpart)
+{
+    __shared__ double sh[8];
+    double sr = 0.0, si = 0.0, sl = 0.0;
+    const int64_t cnt = P.nuv * P.nf;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < cnt; idx += (int64_t)gridDim.x * 256) {
+        const double2 m = fft_sample_one(P, idx / P.nf, (int)(idx % P.nf));
+        const double ww = w[idx];
+        const double a = dre[idx] - m.x, b = dim[idx] - m.y;
+        sr += a * a * ww;
+        si += b * b * ww;
+        if (ww > 0.0) sl += log(ww / kTwoPi);
+    }
+    sr = block_sum<256>(sr, sh);
+    si = block_sum<256>(si, sh);
+    sl = block_sum<256>(sl, sh);
+    if (threadIdx.x == 0) {
+        blockpart[(size_t)blockIdx.x * 3 + 0] = sr;
+        blockpart[(size_t)blockIdx.x * 3 + 1] = si;
+        blockpart[(size_t)blockIdx.x * 3 + 2] = sl;
+    }
 }
 
 static int reduce_blocks(const double *blockpart, int nb, int ncol, double *out_dev)
@@ -679,9 +715,9 @@ int pdsb_loglike_batch(pdsb_dataset *ds, const double *images, int nwalkers, int
     return loglike_impl(ds, images, nwalkers, ny, nx, nf, image_kind, dxy, dRA, dDec, nullptr, lnlike);
 }
 
-// model visibilities by galario's FFT + bilinear algorithm into device arrays [nuv, nf]
-static int run_fft_sample(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
-                          double dDec, double *ore, double *oim)
+// galario's FFT stage: the transformed cube of every channel (fft2_planes) and the sampling arguments
+static int run_fft_transform(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
+                             double dDec, FftSampleArgs *a)
 {
     Context &c = ctx();
     PDSB_REQUIRE(ds && image, "dataset/image");
@@ -693,10 +729,7 @@ static int run_fft_sample(pdsb_dataset *ds, const double *image, int n, int nf, 
     PDSB_CHECK(c.folded.ensure(2 * nn * nf * sizeof(double2)));            // [T | Y]: the DFT's scratch, free here
     double2 *T = c.folded.as<double2>(), *Y = T + nn * nf;
     PDSB_CHECK(fft2_planes(img_dev, n, nf, 1, T, Y));
-    LaunchScope ls("fft_sample");
-    fft_sample_kernel<<<ceil_div(ds->nuv * nf, 256), 256, 0, c.stream>>>(Y, ds->u, ds->v, ds->nuv, ds->nuvh, n, nf, dxy,
-                                                                        dRA, dDec, ore, oim);
-    PDSB_CUDA(cudaGetLastError());
+    *a = FftSampleArgs{Y, ds->u, ds->v, ds->nuv, ds->nuvh, n, nf, dxy, dRA, dDec};
     return PDSB_OK;
 }
 
@@ -715,7 +748,13 @@ int pdsb_sample_image_fft(pdsb_dataset *ds, const double *image, int n, int nf, 
         ore = c.stage_a.as<double>();
         oim = c.stage_b.as<double>();
     }
-    PDSB_CHECK(run_fft_sample(ds, image, n, nf, image_kind, dxy, dRA, dDec, ore, oim));
+    FftSampleArgs fa;
+    PDSB_CHECK(run_fft_transform(ds, image, n, nf, image_kind, dxy, dRA, dDec, &fa));
+    {
+        LaunchScope ls("fft_sample");
+        fft_sample_kernel<<<ceil_div(ds->nuv * nf, 256), 256, 0, c.stream>>>(fa, ore, oim);
+        PDSB_CUDA(cudaGetLastError());
+    }
     if (out_kind == PDSB_HOST) {
         PDSB_CUDA(cudaMemcpyAsync(out_real, ore, bytes, cudaMemcpyDeviceToHost, c.stream));
         PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, bytes, cudaMemcpyDeviceToHost, c.stream));
@@ -737,15 +776,13 @@ int pdsb_loglike_fft(pdsb_dataset *ds, const double *image, int n, int nf, int i
         out[3] = -0.0;
         return PDSB_OK;
     }
-    PDSB_CHECK(c.stage_a.ensure((size_t)cnt * sizeof(double)));
-    PDSB_CHECK(c.stage_b.ensure((size_t)cnt * sizeof(double)));
-    double *mr = c.stage_a.as<double>(), *mi = c.stage_b.as<double>();
-    PDSB_CHECK(run_fft_sample(ds, image, n, nf, image_kind, dxy, dRA, dDec, mr, mi));
-    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (cnt + 255) / 256);
+    FftSampleArgs fa;
+    PDSB_CHECK(run_fft_transform(ds, image, n, nf, image_kind, dxy, dRA, dDec, &fa));
+    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 16, (cnt + 255) / 256);
     PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * 3 * sizeof(double)));
     {
-        LaunchScope ls("chi2_flat");
-        chi2_flat_kernel<<<nb, 256, 0, c.stream>>>(ds->re, ds->im, ds->w, mr, mi, cnt, c.red.as<double>());
+        LaunchScope ls("fft_chi2");
+        fft_chi2_kernel<<<nb, 256, 0, c.stream>>>(fa, ds->re, ds->im, ds->w, c.red.as<double>());
         PDSB_CUDA(cudaGetLastError());
     }
     PDSB_CHECK(reduce_blocks(c.red.as<double>(), nb, 3, c.red.as<double>() + (size_t)nb * 3));
