@@ -27,8 +27,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))          # tests/synth.py: the seeded synthetic inputs
 
-from pdspy_b200 import synth                      # noqa: E402
+import synth                      # noqa: E402
 
 A = synth.ARCSEC
 METRIC = "pixel_visibility_pairs_per_s"

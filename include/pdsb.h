@@ -269,16 +269,21 @@ int pdsb_clean_restore(const double *model, const double *clean_beam, const doub
                        int nf, int kind, double *clean_image);
 
 /* ---- tuning / measurement ----------------------------------------------------------- */
-/* DFT kernel variant: 0 = auto (the FP32-pipe kernel the north star asks for);
- * 1..22 = FP32-pipe tilings; 100..104 = experimental mma.sync tensor-core kernels; 200 = experimental
- * tcgen05/TMEM tensor-core kernel; 300 = all-fp64 reference kernel (1e-13, ~7x slower).  All variants meet
- * the same 1e-5 parity bound; anything else is PDSB_ERR_ARG. */
+/* DFT kernel: 0 = auto (the FP32-pipe kernel the north star asks for); 1..2 = its two tilings;
+ * 200 = the tcgen05/TMEM tensor-core kernel (lattice-split fp16 operands; 201 = the same with round 1's MMA issue
+ * order, kept to time the difference); 300 = all-fp64 reference kernel (1e-13, ~8x slower).  All meet the same
+ * 1e-5 parity bound; anything else is PDSB_ERR_ARG. */
 int pdsb_set_dft_variant(int variant);
 int pdsb_set_dft_split(int nsplit);          /* 0 = auto */
-/* Register-resident microbenchmarks on all SMs: variant 0 = FFMA, 1 = FFMA2 (f32x2), 2-10 = the DFT inner
- * loop's operand patterns (registers / LDS.128 broadcast / constant bank), 11 = mma.sync TF32, 12 = mma.sync
- * fp16, 13 = DFMA (fp64).  Returns achieved TFLOP/s (2 flop per FMA lane). */
+/* Register-resident FP32 FMA peak on all SMs (the roofline denominator bench.py reports beside the nominal one):
+ * variant 0 = FFMA, 1 = FFMA2 (f32x2).  Returns achieved TFLOP/s (2 flop per FMA lane). */
 int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms);
+/* One accumulator round of the tcgen05 DFT kernel's MMA sequence (M = N = 128, K = 64 as 12 MMAs of K = 16 on
+ * fp16 hi/lo operands) with the accumulator pre-loaded with c0, on HOST operands a_*[128][64], b_*[128][64]
+ * (fp16 bit patterns, row-major, k fastest); out[128][128] fp32 (host).  order 0 = the kernel's issue order,
+ * 1 = cross products first.  Measures how the tensor core rounds its accumulator. */
+int pdsb_tc5_accum_probe(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_t *b_hi, const uint16_t *b_lo,
+                         float c0, int order, float *out);
 
 #ifdef __cplusplus
 }

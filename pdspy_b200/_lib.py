@@ -84,6 +84,7 @@ SIGNATURES = {
     "pdsb_set_dft_variant": [_c_int],
     "pdsb_set_dft_split": [_c_int],
     "pdsb_bench_fma": [_c_int, _c_int, ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_dbl)],
+    "pdsb_tc5_accum_probe": [_P, _P, _P, _P, ctypes.c_float, _c_int, _P],
 }
 
 _lib = None
@@ -121,9 +122,9 @@ def lib():
         dev = int(os.environ.get("PDSB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         check(L.pdsb_init(dev))
         _inited = True
-        kernel = os.environ.get("PDSPY_B200_DFT", "")          # initial DFT kernel: fp32 (default) | mma | tcgen05 | <int>
+        kernel = os.environ.get("PDSPY_B200_DFT", "")          # initial DFT kernel: fp32 (default) | tcgen05 | fp64 | <int>
         if kernel:
-            variants = {"fp32": 0, "mma": 103, "tcgen05": 200, "fp64": 300}
+            variants = {"fp32": 0, "tcgen05": 200, "fp64": 300}
             check(L.pdsb_set_dft_variant(variants[kernel] if kernel in variants else int(kernel)))
     return L
 

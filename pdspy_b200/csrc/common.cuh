@@ -71,7 +71,7 @@ struct Context {
     // scratch
     Scratch img64, folded, partial, red, stage_a, stage_b, stage_c, stage_d, stage_e;
     Scratch small_dev;     // tiny per-call device arrays (channel scale factors)
-    Scratch mma_ws;        // per-plane scale factors of the experimental tensor-core variant
+    Scratch mma_ws;        // tensor-core kernel: per-round lattice quanta and per-plane unscale factors
 };
 
 Context &ctx();

@@ -369,259 +369,25 @@ __global__ void __launch_bounds__(DFT_THREADS, MINB) dft_kernel(const DftParams 
 }
 
 // ---------------------------------------------------------------------------------
-// DFT kernel, uv-paired form.  Same algorithm and data flow as dft_kernel; the packed fp32x2
-// lanes carry TWO UV POINTS instead of two adjacent columns:
-//     acc2[comp](q0,q1) = fma2( x[comp][t] (scalar, broadcast to both lanes), trig2[t](q0,q1), acc2 )
-// so (a) the shared-memory operand is read as a 32-bit scalar (FFMA2's .F32 broadcast operand
-// form) instead of a 64-bit pair, (b) the accumulators need no even/odd split, and the row-phase
-// epilogue and the row rotation run as pair x pair FFMA2 over the two uv points: 8 FMA-pipe cycles
-// per uv point per row instead of 12.
-__device__ __forceinline__ u64 neg2(u64 a) { return a ^ 0x8000000080000000ull; }
-__device__ __forceinline__ void unpack2(u64 a, float &lo, float &hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
-}
-
-__device__ __forceinline__ u64 add2(u64 a, u64 b)
-{
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-
-// NCH: independent accumulator chains per (component, uv pair); column t feeds chain t % NCH, so
-// dependent FFMA2 on one accumulator are NCH times further apart (the chains are added per row).
-template <int UVP, int TCP, int MINB, int NCH>
-__global__ void __launch_bounds__(DFT_THREADS, MINB) dft_qp_kernel(const DftParams P)
-{
-    constexpr int UVT = 2 * UVP;
-    constexpr int CHUNK_FLOATS = DFT_RC * 4 * TCP;
-    constexpr uint32_t CHUNK_BYTES = CHUNK_FLOATS * sizeof(float);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *stages = reinterpret_cast<float *>(smem_raw);
-    double *fst = reinterpret_cast<double *>(smem_raw + (size_t)DFT_NSTAGE * CHUNK_BYTES);
-    __shared__ __align__(8) uint64_t full_bar[DFT_NSTAGE];
-#define QFU(q) fst[(0 * UVT + (q)) * DFT_THREADS + tid]
-#define QFV(q) fst[(1 * UVT + (q)) * DFT_THREADS + tid]
-#define QVR(q) fst[(2 * UVT + (q)) * DFT_THREADS + tid]
-#define QVI(q) fst[(3 * UVT + (q)) * DFT_THREADS + tid]
-
-    const int tid = threadIdx.x;
-    const int plane = blockIdx.z, sp = blockIdx.y;
-    const int tile0 = (int)(((int64_t)sp * P.ntile) / P.nsplit);
-    const int tile1 = (int)(((int64_t)(sp + 1) * P.ntile) / P.nsplit);
-    const int ntl = tile1 - tile0;
-    const int nit = ntl * P.nchunk;
-    const float *gbase = P.F + ((size_t)plane * P.ntile + tile0) * (size_t)P.nchunk * CHUNK_FLOATS;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < DFT_NSTAGE; s++) mbar_init(&full_bar[s], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < DFT_NSTAGE; s++)
-            if (s < nit) {
-                mbar_expect_tx(&full_bar[s], CHUNK_BYTES);
-                tma_load_1d(stages + s * CHUNK_FLOATS, gbase + (size_t)s * CHUNK_FLOATS, CHUNK_BYTES, &full_bar[s]);
-            }
-    }
-
-    u64 Dr2[UVP], Di2[UVP];
-#pragma unroll
-    for (int qp = 0; qp < UVP; qp++) {
-        float dr[2], di[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int q = 2 * qp + h;
-            const int64_t k = (int64_t)blockIdx.x * (DFT_THREADS * UVT) + q * DFT_THREADS + tid;
-            const bool valid = k < P.nuvh;
-            const double fuq = valid ? P.u[k] * P.dxy : 0.0;
-            const double fvq = valid ? P.v[k] * P.dxy : 0.0;
-            QFU(q) = fuq;
-            QFV(q) = fvq;
-            QVR(q) = 0.0;
-            QVI(q) = 0.0;
-            double s, c;
-            sincospi(2.0 * (fvq - rint(fvq)), &s, &c);
-            dr[h] = (float)c;
-            di[h] = (float)s;
-        }
-        Dr2[qp] = pack2(dr[0], dr[1]);
-        Di2[qp] = pack2(di[0], di[1]);
-    }
-
-    int it = 0;
-    for (int tl = 0; tl < ntl; tl++) {
-        // column factors of this tile, paired over the two uv points of each pair
-        u64 tc2[UVP][TCP], ts2[UVP][TCP];
-#pragma unroll
-        for (int qp = 0; qp < UVP; qp++) {
-            double cr[2], ci[2], rc[2], rs[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const double fuq = QFU(2 * qp + h);
-                double a0 = fuq * ((double)((tile0 + tl) * TCP) + P.hx);
-                sincospi(2.0 * (a0 - rint(a0)), &ci[h], &cr[h]);
-                sincospi(2.0 * (fuq - rint(fuq)), &rs[h], &rc[h]);
-            }
-#pragma unroll
-            for (int t = 0; t < TCP; t++) {
-                tc2[qp][t] = pack2((float)cr[0], (float)cr[1]);
-                ts2[qp][t] = pack2((float)ci[0], (float)ci[1]);
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const double nr = cr[h] * rc[h] - ci[h] * rs[h];
-                    ci[h] = cr[h] * rs[h] + ci[h] * rc[h];
-                    cr[h] = nr;
-                }
-            }
-        }
-
-        for (int ch = 0; ch < P.nchunk; ch++, it++) {
-            const int st = it % DFT_NSTAGE;
-            const uint32_t parity = (uint32_t)((it / DFT_NSTAGE) & 1);
-            u64 Er2[UVP], Ei2[UVP];
-#pragma unroll
-            for (int qp = 0; qp < UVP; qp++) {
-                float er[2], ei[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    double b0 = QFV(2 * qp + h) * ((double)(ch * DFT_RC) + P.hy);
-                    b0 -= rint(b0);
-                    sincospif((float)(2.0 * b0), &ei[h], &er[h]);
-                }
-                Er2[qp] = pack2(er[0], er[1]);
-                Ei2[qp] = pack2(ei[0], ei[1]);
-            }
-            mbar_wait(&full_bar[st], parity);
-            const float *sm = stages + st * CHUNK_FLOATS;
-
-            u64 vre[UVP], vim[UVP];
-#pragma unroll
-            for (int qp = 0; qp < UVP; qp++) { vre[qp] = 0ull; vim[qp] = 0ull; }
-#pragma unroll 2
-            for (int r = 0; r < DFT_RC; r++) {
-                const float4 *row = reinterpret_cast<const float4 *>(sm + r * (4 * TCP));
-                u64 a1[UVP][NCH], a2[UVP][NCH], b1[UVP][NCH], b2[UVP][NCH];
-#pragma unroll
-                for (int g = 0; g < TCP / 4; g++) {
-                    const float4 ss = row[g], sd = row[TCP / 4 + g], ds = row[2 * (TCP / 4) + g],
-                                 dd = row[3 * (TCP / 4) + g];
-                    const float xs[4] = {ss.x, ss.y, ss.z, ss.w}, xsd[4] = {sd.x, sd.y, sd.z, sd.w},
-                                xds[4] = {ds.x, ds.y, ds.z, ds.w}, xdd[4] = {dd.x, dd.y, dd.z, dd.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int t = 4 * g + e;
-                        const int cn = t % NCH;
-                        const u64 vss = pack2(xs[e], xs[e]), vsd = pack2(xsd[e], xsd[e]), vds = pack2(xds[e], xds[e]),
-                                  vdd = pack2(xdd[e], xdd[e]);
-#pragma unroll
-                        for (int qp = 0; qp < UVP; qp++) {
-                            if (t < NCH) {
-                                a1[qp][cn] = mul2(vss, tc2[qp][t]);
-                                a2[qp][cn] = mul2(vsd, tc2[qp][t]);
-                                b1[qp][cn] = mul2(vds, ts2[qp][t]);
-                                b2[qp][cn] = mul2(vdd, ts2[qp][t]);
-                            } else {
-                                a1[qp][cn] = fma2(vss, tc2[qp][t], a1[qp][cn]);
-                                a2[qp][cn] = fma2(vsd, tc2[qp][t], a2[qp][cn]);
-                                b1[qp][cn] = fma2(vds, ts2[qp][t], b1[qp][cn]);
-                                b2[qp][cn] = fma2(vdd, ts2[qp][t], b2[qp][cn]);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int qp = 0; qp < UVP; qp++) {
-#pragma unroll
-                    for (int cn = 1; cn < NCH; cn++) {
-                        a1[qp][0] = add2(a1[qp][0], a1[qp][cn]);
-                        a2[qp][0] = add2(a2[qp][0], a2[qp][cn]);
-                        b1[qp][0] = add2(b1[qp][0], b1[qp][cn]);
-                        b2[qp][0] = add2(b2[qp][0], b2[qp][cn]);
-                    }
-                    const u64 nei = neg2(Ei2[qp]);
-                    vre[qp] = fma2(Er2[qp], a1[qp][0], vre[qp]);
-                    vre[qp] = fma2(nei, b2[qp][0], vre[qp]);
-                    vim[qp] = fma2(Er2[qp], b1[qp][0], vim[qp]);
-                    vim[qp] = fma2(Ei2[qp], a2[qp][0], vim[qp]);
-                    const u64 nr = fma2(nei, Di2[qp], mul2(Er2[qp], Dr2[qp]));
-                    Ei2[qp] = fma2(Er2[qp], Di2[qp], mul2(Ei2[qp], Dr2[qp]));
-                    Er2[qp] = nr;
-                }
-            }
-#pragma unroll
-            for (int qp = 0; qp < UVP; qp++) {
-                float r0, r1, i0, i1;
-                unpack2(vre[qp], r0, r1);
-                unpack2(vim[qp], i0, i1);
-                QVR(2 * qp) += (double)r0;
-                QVR(2 * qp + 1) += (double)r1;
-                QVI(2 * qp) += (double)i0;
-                QVI(2 * qp + 1) += (double)i1;
-            }
-
-            __syncthreads();
-            if (tid == 0 && it + DFT_NSTAGE < nit) {
-                fence_proxy_async();
-                mbar_expect_tx(&full_bar[st], CHUNK_BYTES);
-                tma_load_1d(stages + st * CHUNK_FLOATS, gbase + (size_t)(it + DFT_NSTAGE) * CHUNK_FLOATS,
-                            CHUNK_BYTES, &full_bar[st]);
-            }
-        }
-    }
-
-#pragma unroll
-    for (int q = 0; q < UVT; q++) {
-        const int64_t k = (int64_t)blockIdx.x * (DFT_THREADS * UVT) + q * DFT_THREADS + tid;
-        if (k < P.nuvh) P.part[((size_t)sp * P.nf + plane) * (size_t)P.nuvh + k] = make_double2(QVR(q), QVI(q));
-    }
-#undef QFU
-#undef QFV
-#undef QVR
-#undef QVI
-}
-
-// ---------------------------------------------------------------------------------
 struct VariantInfo {
     const char *name;
     int uvt, tcp, f2, minb, sms;
 };
+// Round 1 measured 22 tilings (2-6 uv points per thread, 16-32 column pairs, column- or uv-paired FFMA2, scalar
+// FFMA, 1-4 accumulator chains; profiles/r01_dft_ncu.md): all within 74-77 % FMA-pipe activity, the widest that
+// fits the register file was fastest.  Kept: that one, and the narrow tiling for images of <= 32 columns.
 static const VariantInfo kVariants[] = {
-    {"dft_f2_uv2_tc16", 2, 16, 1, 4, 0},       // 1
-    {"dft_f2_uv4_tc16", 4, 16, 1, 2, 0},       // 2
-    {"dft_f2_uv2_tc32", 2, 32, 1, 2, 0},       // 3
-    {"dft_f1_uv2_tc16", 2, 16, 0, 4, 0},       // 4
-    {"dft_f1_uv4_tc16", 4, 16, 0, 2, 0},       // 5
-    {"dft_f2_uv1_tc32", 1, 32, 1, 4, 0},       // 6
-    {"dft_f2_uv4_tc16_sms", 4, 16, 1, 2, 1},   // 7
-    {"dft_f2_uv3_tc16_sms", 3, 16, 1, 3, 1},   // 8
-    {"dft_f2_uv2_tc32_sms", 2, 32, 1, 2, 1},   // 9
-    {"dft_f2_uv2_tc16_sms", 2, 16, 1, 4, 1},   // 10
-    {"dft_f2_uv3_tc32_sms", 3, 32, 1, 2, 1},   // 11
-    {"dft_qp_uv4_tc16", 4, 16, 2, 2, 1},       // 12  (f2 == 2: uv-paired kernel)
-    {"dft_qp_uv2_tc32", 2, 32, 2, 2, 1},       // 13
-    {"dft_qp_uv4_tc20", 4, 20, 2, 2, 1},       // 14
-    {"dft_qp_uv4_tc24", 4, 24, 2, 2, 1},       // 15
-    {"dft_qp_uv6_tc16", 6, 16, 2, 2, 1},       // 16
-    {"dft_qp_uv2_tc16", 2, 16, 2, 4, 1},       // 17
-    {"dft_qp_uv4_tc16_c2", 4, 16, 2, 2, 1},    // 18  (cN: N accumulator chains per component)
-    {"dft_qp_uv2_tc32_c2", 2, 32, 2, 2, 1},    // 19
-    {"dft_qp_uv2_tc32_c4", 2, 32, 2, 2, 1},    // 20
-    {"dft_qp_uv4_tc16_c4", 4, 16, 2, 2, 1},    // 21
-    {"dft_qp_uv2_tc16_c4", 2, 16, 2, 4, 1},    // 22
+    {"dft_f2_uv3_tc32_sms", 3, 32, 1, 2, 1},   // 1  default
+    {"dft_f2_uv2_tc16", 2, 16, 1, 4, 0},       // 2  narrow images (column pairs <= 16)
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-constexpr int kDefaultVariant = 11;
 
 int dft_variant_count() { return kNumVariants; }
-int dft_pick_variant()
+int dft_pick_variant(int nx)
 {
-    int v = ctx().dft_variant;
-    return (v >= 1 && v <= kNumVariants) ? v : kDefaultVariant;
+    const int v = ctx().dft_variant;
+    if (v >= 1 && v <= kNumVariants) return v;
+    return (nx + 1) / 2 <= 16 ? 2 : 1;
 }
 int dft_variant_tcp(int variant) { return kVariants[variant - 1].tcp; }
 
@@ -660,56 +426,14 @@ static int launch_variant(const DftParams &p, const char *name)
     return PDSB_OK;
 }
 
-template <int UVP, int TCP, int MINB, int NCH>
-static int launch_qp_variant(const DftParams &p, const char *name)
-{
-    constexpr int UVT = 2 * UVP;
-    constexpr size_t smem = (size_t)DFT_NSTAGE * DFT_RC * 4 * TCP * sizeof(float) +
-                            (size_t)4 * UVT * DFT_THREADS * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PDSB_CUDA(cudaFuncSetAttribute(dft_qp_kernel<UVP, TCP, MINB, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-        attr_set = true;
-    }
-    int64_t uvtiles = (p.nuvh + (int64_t)DFT_THREADS * UVT - 1) / ((int64_t)DFT_THREADS * UVT);
-    if (uvtiles <= 0) return PDSB_OK;
-    PDSB_REQUIRE(p.nsplit <= 65535 && p.nf <= 65535, "grid y/z dimensions");
-    dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)p.nf);
-    LaunchScope ls(name);
-    dft_qp_kernel<UVP, TCP, MINB, NCH><<<grid, DFT_THREADS, smem, ctx().stream>>>(p);
-    PDSB_CUDA(cudaGetLastError());
-    return PDSB_OK;
-}
-
 int launch_dft(const DftParams &p, int variant, int *tcp_of_variant)
 {
     PDSB_REQUIRE(variant >= 1 && variant <= kNumVariants, "dft variant");
     if (tcp_of_variant) *tcp_of_variant = kVariants[variant - 1].tcp;
     const char *name = kVariants[variant - 1].name;
     switch (variant) {
-        case 1: return launch_variant<2, 16, true, 4, false>(p, name);
-        case 2: return launch_variant<4, 16, true, 2, false>(p, name);
-        case 3: return launch_variant<2, 32, true, 2, false>(p, name);
-        case 4: return launch_variant<2, 16, false, 4, false>(p, name);
-        case 5: return launch_variant<4, 16, false, 2, false>(p, name);
-        case 6: return launch_variant<1, 32, true, 4, false>(p, name);
-        case 7: return launch_variant<4, 16, true, 2, true>(p, name);
-        case 8: return launch_variant<3, 16, true, 3, true>(p, name);
-        case 9: return launch_variant<2, 32, true, 2, true>(p, name);
-        case 10: return launch_variant<2, 16, true, 4, true>(p, name);
-        case 11: return launch_variant<3, 32, true, 2, true>(p, name);
-        case 12: return launch_qp_variant<2, 16, 2, 1>(p, name);
-        case 13: return launch_qp_variant<1, 32, 2, 1>(p, name);
-        case 14: return launch_qp_variant<2, 20, 2, 1>(p, name);
-        case 15: return launch_qp_variant<2, 24, 2, 1>(p, name);
-        case 16: return launch_qp_variant<3, 16, 2, 1>(p, name);
-        case 17: return launch_qp_variant<1, 16, 4, 1>(p, name);
-        case 18: return launch_qp_variant<2, 16, 2, 2>(p, name);
-        case 19: return launch_qp_variant<1, 32, 2, 2>(p, name);
-        case 20: return launch_qp_variant<1, 32, 2, 4>(p, name);
-        case 21: return launch_qp_variant<2, 16, 2, 4>(p, name);
-        case 22: return launch_qp_variant<1, 16, 4, 4>(p, name);
+        case 1: return launch_variant<3, 32, true, 2, true>(p, name);
+        case 2: return launch_variant<2, 16, true, 4, false>(p, name);
     }
     return PDSB_ERR_ARG;
 }

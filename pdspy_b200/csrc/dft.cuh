@@ -80,23 +80,17 @@ int launch_fold(const double *img_dev, float *F, const DftGeom &g);
 int launch_dft(const DftParams &p, int variant, int *tcp_of_variant);
 int dft_variant_tcp(int variant);
 int dft_variant_count();
-int dft_pick_variant();
+int dft_pick_variant(int nx);
 int dft_auto_split(int variant, int64_t nuvh, int nf, int ntile);
 
-// experimental tensor-core variant (dft_mma.cu), selected with pdsb_set_dft_variant(100)
-constexpr int DFT_VARIANT_MMA = 100;
-size_t mma_operand_bytes(int ny, int nx, int nf);
-int launch_fold_half(const double *img_dev, unsigned char *B, double *scale_ws, int ny, int nx, int nf);
-int mma_auto_split(int64_t nuvh, int nf, int nx);
-int launch_dft_mma(DftParams p, const unsigned char *B, int ny, int nx);
-int launch_plane_scale(const double *img_dev, double *scale_ws, int ny, int nx, int nf);
-
-// experimental tcgen05 / TMEM variant (dft_tc5.cu), selected with pdsb_set_dft_variant(200)
+// tcgen05 / TMEM variant (dft_tc5.cu), selected with pdsb_set_dft_variant(200)
 constexpr int DFT_VARIANT_TC5 = 200;
 size_t tc5_operand_bytes(int ny, int nx, int nf);
-int launch_fold_tc5(const double *img_dev, unsigned char *B, double *scale_ws, int ny, int nx, int nf);
+size_t tc5_ws_bytes(int ny, int nx, int nf);
+const double *tc5_plane_unscale(void *ws, int ny, int nx, int nf);
+int launch_fold_tc5(const double *img_dev, unsigned char *B, void *ws, int ny, int nx, int nf);
 int tc5_auto_split(int64_t nuvh, int nf, int nx);
-int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx);
+int launch_dft_tc5(DftParams p, const unsigned char *B, void *ws, int ny, int nx);
 
 // fp64 reference variant (dft_f64.cu), selected with pdsb_set_dft_variant(300)
 constexpr int DFT_VARIANT_F64 = 300;

@@ -1,9 +1,24 @@
-// EXPERIMENTAL opt-in variant of the direct Fourier sampling on the 5th-generation tensor cores
-// (pdsb_set_dft_variant(200)): tcgen05.mma with TMEM accumulators, operands staged by bulk TMA.
+// Direct Fourier sampling on the 5th-generation tensor cores (opt-in: pdsb_set_dft_variant(200),
+// set_dft_kernel("tcgen05"), bench.py --dft tcgen05): tcgen05.mma with TMEM accumulators, operands staged by bulk TMA.
 //
-// Same algorithm as dft.cu / dft_mma.cu: separable phases, mirror-folded real image, fp16 hi+lo split of
-// both operands (3 MMAs per product), per-plane power-of-two scaling, fp64-seeded phases, fp32 row-phase
-// rotation in the epilogue, fp64 partial sums in the same [split][plane][uv] layout.
+// Same algorithm as dft.cu: separable phases, mirror-folded real image, fp64-seeded phases, fp32 row-phase
+// rotation in the epilogue, fp64 partial sums in the same [split][plane][uv] layout.  Both operands are
+// split into two fp16 limbs (3 MMAs per product: hi.lo, lo.hi, hi.hi).
+//
+// Accumulator rounding.  tcgen05.mma aligns the 16 products of an instruction and its fp32 accumulator to
+// the largest exponent and truncates toward zero (measured with pdsb_tc5_accum_probe: about 0.4 ulp per
+// instruction from the accumulator plus 0.04 ulp per product).  With fp16-rounded limbs and 12
+// instructions per accumulator round, sums of like-signed products (low spatial frequencies of a positive
+// image) came out 3.4e-7 low - a bias, not noise.  The split used here removes it:
+//   * the hi limbs live on a fixed-point LATTICE: trig factors on multiples of 2^-9, image values of one
+//     (plane, K tile, chunk) on integers <= 2047 after a power-of-two scale chosen so that the largest row
+//     sum of |hi| over the K tile stays below 2^15.  Every hi.hi product is a multiple of 2^-9 and every
+//     partial sum of them is below 2^15: exactly representable in the accumulator, nothing to truncate;
+//   * the cross products (2^-9 of the result) are issued FIRST, into the empty accumulator, where their
+//     rounding is 2^-9 smaller; the hi.hi products follow.
+// What remains is one truncation of the cross sum's low bits at the ulp of the result: measured -0.50 ulp
+// = -4.3e-8 on like-signed sums (was -4.0 ulp), i.e. chi^2 per channel within 1e-7 of the fp64 kernel.
+// The dropped lo.lo products are zero-mean and 2^-19 of (trig quantum x image quantum).
 //
 //   CTA = 128 uv points (UMMA M = 128), 10 warps with fixed roles:
 //     warps 0-7  epilogue: thread (w & 3) * 32 + lane owns uv row r (TMEM lane r); warps 0-3 take row pairs
@@ -23,7 +38,7 @@
 //   over through mbarriers (stage full/empty, TMEM full/empty, A full); no CTA-wide barrier in steady state.
 //   Epilogue arithmetic is packed fp32x2 (FFMA2) over adjacent row pairs, four independent phase chains.
 //
-// NOT the default (see dft_mma.cu header); reported by bench.py under `extras`.
+// NOT the default: BASELINE.json's north star prescribes the FP32 pipe for the headline kernel.
 #include "dft.cuh"
 #include <cuda_fp16.h>
 #include <algorithm>
@@ -238,26 +253,21 @@ __device__ __forceinline__ void t5_dfadd(float &hi, float &lo, float x)
     lo += (hi - (s - bb)) + (x - bb);
     hi = s;
 }
+// trig factor -> lattice hi limb (multiple of 2^-9, exact in fp16) + fp16 remainder
 __device__ __forceinline__ void t5_split(float x, __half &hi, __half &lo)
 {
-    hi = __float2half_rn(x);
-    lo = __float2half_rn(x - __half2float(hi));
+    const float h = rintf(x * 512.0f) * 0.001953125f;
+    hi = __float2half_rn(h);
+    lo = __float2half_rn(x - h);
 }
 
 // ---- fold into the canonical UMMA B layout ----
 // B[plane][ktile][chunk][type][sub][hi|lo][t5_off(r, k)], r = c*64 + s_l (component c of the type: SS,SD |
 // DS,-DD; row pair s_l of the chunk), k = column pair within the sub-chunk.
-__global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict__ img, unsigned char *__restrict__ B,
-                                                       const double *__restrict__ scale, int ny, int nx, int nf,
-                                                       int npx, int npy, int nkt, int nchunk)
+// Quad of mirror pixels -> the four parity components (SS, SD, DS, -DD) of column pair t, row pair s.
+__device__ __forceinline__ void t5_quad(const double *__restrict__ img, int ny, int nx, int nf, int npx, int npy, int p, int t,
+                                        int s, double (&comp)[4])
 {
-    const int64_t tw = (int64_t)nkt * T5_KT, sw = (int64_t)nchunk * T5_RC;
-    const int64_t total = (int64_t)nf * tw * sw;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int p = (int)(idx % nf);
-    const int64_t rr = idx / nf;
-    const int t = (int)(rr % tw), s = (int)(rr / tw);
     double pp = 0, mp = 0, pm = 0, mm = 0;
     if (t < npx && s < npy) {
         int c_hi, c_lo, j_lo, j_hi;
@@ -272,18 +282,104 @@ __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict_
         if (!selfc && !selfr) mm = img[((int64_t)j_hi * nx + c_lo) * nf + p];
     }
     const double Sp = pp + mp, Dp = pp - mp, Sm = pm + mm, Dm = pm - mm;
-    const double comp[4] = {Sp + Sm, Sp - Sm, Dp + Dm, -(Dp - Dm)};      // SS, SD, DS, -DD
-    const double sc = scale[p];
+    comp[0] = Sp + Sm;
+    comp[1] = Sp - Sm;
+    comp[2] = Dp + Dm;
+    comp[3] = -(Dp - Dm);
+}
+
+// Statistics of every accumulator round's B tiles (plane p, K tile kt, chunk): the largest |component| and the
+// largest row sum of |component| over the K tile's 64 column pairs; stats[((p nkt + kt) nchunk + chunk) 2 + {0,1}]
+// as the bit patterns of non-negative doubles (atomicMax on them orders like the values).  Thread = (plane,
+// row pair, K tile), plane fastest: coalesced over the channel-fastest cube.
+__global__ void __launch_bounds__(256) tc5_tile_stats_kernel(const double *__restrict__ img, unsigned long long *__restrict__ stats,
+                                                             int ny, int nx, int nf, int npx, int npy, int nkt, int nchunk)
+{
+    const int64_t sw = (int64_t)nchunk * T5_RC;
+    const int64_t total = (int64_t)nf * sw * nkt;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int p = (int)(idx % nf);
+    const int64_t rr = idx / nf;
+    const int s = (int)(rr % sw), kt = (int)(rr / sw);
+    double l1[4] = {0, 0, 0, 0}, mx = 0.0;
+    for (int k = 0; k < T5_KT; k++) {
+        double comp[4];
+        t5_quad(img, ny, nx, nf, npx, npy, p, kt * T5_KT + k, s, comp);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double a = fabs(comp[c]);
+            if (a <= 1.79e308) {           // NaN / inf pixels do not set the scale (they poison the result anyway)
+                l1[c] += a;
+                mx = a > mx ? a : mx;
+            }
+        }
+    }
+    const double l1m = fmax(fmax(l1[0], l1[1]), fmax(l1[2], l1[3]));
+    unsigned long long *o = stats + (((int64_t)p * nkt + kt) * nchunk + s / T5_RC) * 2;
+    if (mx > 0.0) {
+        atomicMax(o, (unsigned long long)__double_as_longlong(mx));
+        atomicMax(o + 1, (unsigned long long)__double_as_longlong(l1m));
+    }
+}
+
+constexpr double T5_HI_MAX = 2047.0;             // largest integer hi limb (exact in fp16)
+constexpr double T5_L1_MAX = 32768.0 - 1024.0;   // largest row sum of |hi| over a K tile: hi.hi sums stay below 2^15
+// Thread = plane.  Exponent e of every round's lattice quantum 2^e; the plane's unscale factor is the largest
+// quantum, and qrel[round] = quantum / that (a float power of two <= 1; clamped at 2^-100, where the tile no
+// longer matters against the plane).  inv_q[round] = 1 / quantum for the fold.
+__global__ void tc5_tile_scale_kernel(const unsigned long long *__restrict__ stats, int nf, int nround, float *__restrict__ qrel,
+                                      double *__restrict__ inv_q, double *__restrict__ plane_unscale)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nf) return;
+    int emax = -100000;
+    for (int r = 0; r < nround; r++) {
+        const double mx = __longlong_as_double((long long)stats[((int64_t)p * nround + r) * 2]);
+        const double l1 = __longlong_as_double((long long)stats[((int64_t)p * nround + r) * 2 + 1]);
+        if (mx > 0.0) {
+            const int e = (int)ceil(log2(fmax(mx / T5_HI_MAX, l1 / T5_L1_MAX)));
+            emax = e > emax ? e : emax;
+        }
+    }
+    if (emax == -100000) emax = 0;                // all-zero plane
+    plane_unscale[p] = exp2((double)emax);
+    for (int r = 0; r < nround; r++) {
+        const double mx = __longlong_as_double((long long)stats[((int64_t)p * nround + r) * 2]);
+        const double l1 = __longlong_as_double((long long)stats[((int64_t)p * nround + r) * 2 + 1]);
+        int e = emax;
+        if (mx > 0.0) e = (int)ceil(log2(fmax(mx / T5_HI_MAX, l1 / T5_L1_MAX)));
+        if (e < emax - 100) e = emax - 100;
+        qrel[(int64_t)p * nround + r] = exp2f((float)(e - emax));
+        inv_q[(int64_t)p * nround + r] = exp2((double)(-e));
+    }
+}
+
+__global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict__ img, unsigned char *__restrict__ B,
+                                                       const double *__restrict__ inv_q, int ny, int nx, int nf,
+                                                       int npx, int npy, int nkt, int nchunk)
+{
+    const int64_t tw = (int64_t)nkt * T5_KT, sw = (int64_t)nchunk * T5_RC;
+    const int64_t total = (int64_t)nf * tw * sw;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int p = (int)(idx % nf);
+    const int64_t rr = idx / nf;
+    const int t = (int)(rr % tw), s = (int)(rr / tw);
+    double comp[4];                                                      // SS, SD, DS, -DD
+    t5_quad(img, ny, nx, nf, npx, npy, p, t, s, comp);
     const int kt = t / T5_KT, sub = (t % T5_KT) / T5_KSUB, k = t % T5_KSUB;
     const int chunk = s / T5_RC, s_l = s % T5_RC;
+    const double sc = inv_q[((int64_t)p * nkt + kt) * nchunk + chunk];  // 1 / lattice quantum of this round
     unsigned char *base = B + (((int64_t)p * nkt + kt) * nchunk + chunk) * (int64_t)(2 * T5_NSUB * T5_UNIT_BYTES);
 #pragma unroll
     for (int cidx = 0; cidx < 4; cidx++) {
         const int type = cidx >> 1, c = cidx & 1;
         const int off = t5_off(c * T5_RC + s_l, k);
         const double x = comp[cidx] * sc;
-        const __half hi = __double2half(x);
-        const __half lo = __double2half(x - (double)__half2float(hi));
+        const double xh = rint(x);                                       // integer hi limb, |xh| <= 2047
+        const __half hi = __double2half(xh);
+        const __half lo = __double2half(x - xh);
         unsigned char *unit = base + (type * T5_NSUB + sub) * T5_UNIT_BYTES;
         *reinterpret_cast<__half *>(unit + off) = hi;
         *reinterpret_cast<__half *>(unit + T5_TILE_BYTES + off) = lo;
@@ -293,15 +389,14 @@ __global__ void __launch_bounds__(256) fold_tc5_kernel(const double *__restrict_
 // ---- the kernel ----
 constexpr int T5_EPI_THREADS = 256;             // warps 0-7
 constexpr int T5_THREADS = T5_EPI_THREADS + 64; // + TMA warp + MMA warp
-// MODE 0: the product.  MODE 1 / 2 / 3 exist only when compiled with -DPDSB_TC5_PROBES (variants 201-203;
-// timing experiments, results are garbage): 1 = the epilogue warps hand the accumulators straight back,
-// which leaves the TMA + MMA pipeline running alone; 2 = additionally no TMA copies, the MMAs alone;
-// 3 = as 2 with a 128-byte-swizzle B descriptor (same speed as the no-swizzle layout).
-// Measured on C3/4 (250k uv): full kernel 7.66 ms, MODE 1 7.22 ms, MODE 2 7.23 ms -> the kernel is bound by
-// the tcgen05.mma rate itself (~82 cycles per 128x128x16 TS-mode MMA against the 64-cycle floor).
-template <int MODE>
+// ORDER 1 (the product): per accumulator round all cross products first, then the hi.hi products (see the header).
+// ORDER 0: the three products of a k-step together (round 1's order; kept as variant 201 to time the difference -
+// it is NOT bias-free: every later instruction truncates an accumulator that already has full magnitude).
+// Round-1 timing probes (C3/4, 250k uv): full kernel 7.66 ms, epilogue removed 7.22 ms, TMA removed as well
+// 7.23 ms -> the kernel is bound by the tcgen05.mma rate itself (~82 cycles per 128x128x16 TS-mode MMA).
+template <int ORDER>
 __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams P, const unsigned char *__restrict__ Bg,
-                                                                int nkt, int pg)
+                                                                const float *__restrict__ qrel, int nkt, int pg)
 {
     extern __shared__ __align__(1024) unsigned char Bs[];       // T5_NSTAGE x 16 KB
     __shared__ __align__(8) uint64_t full_bar[T5_NSTAGE];       // TMA landed           (producer -> MMA)
@@ -354,11 +449,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                 if (it >= T5_NSTAGE) t5_wait(&empty_bar[st], (uint32_t)((it / T5_NSTAGE - 1) & 1));
                 const unsigned char *src =
                     Bg + (((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * (size_t)ncs + cs) * T5_UNIT_BYTES;
-                if (MODE >= 2) t5_arrive(&full_bar[st]);         // no copy: the MMAs read whatever is in the stage
-                else {
-                    t5_expect_tx(&full_bar[st], T5_UNIT_BYTES);
-                    t5_tma(Bs + (size_t)st * T5_UNIT_BYTES, src, T5_UNIT_BYTES, &full_bar[st]);
-                }
+                t5_expect_tx(&full_bar[st], T5_UNIT_BYTES);
+                t5_tma(Bs + (size_t)st * T5_UNIT_BYTES, src, T5_UNIT_BYTES, &full_bar[st]);
                 if (++cs == ncs) {
                     cs = 0;
                     if (++pl == npl) {
@@ -382,38 +474,69 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                 for (int ty = 0; ty < 2; ty++) {     // accumulator ty: cos-type, sin-type
                     const uint32_t d = tmem_base + (uint32_t)(ty * T5_N);
                     if (it >= 1) t5_wait(&tmem_empty[ty], (uint32_t)((it - 1) & 1));
+                    // A part (ty, hi|lo) at column (ty*2 + part) * APART; 16 k = 8 columns
+                    const uint32_t a_hi0 = a_buf + (uint32_t)((ty * 2 + 0) * T5_APART);
+                    const uint32_t a_lo0 = a_buf + (uint32_t)((ty * 2 + 1) * T5_APART);
+                    if (ORDER == 0) {
 #pragma unroll
-                    for (int sub = 0; sub < T5_NSUB; sub++, is++) {
+                        for (int sub = 0; sub < T5_NSUB; sub++, is++) {
+                            t5_wait(&full_bar[st], (uint32_t)((is / T5_NSTAGE) & 1));
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            if (leader) {
+                                const uint32_t b_s = b_lo0 + (uint32_t)st * (uint32_t)(T5_UNIT_BYTES >> 4);
+#pragma unroll
+                                for (int ks = 0; ks < 2; ks++) {
+                                    const uint32_t ahi = a_hi0 + (uint32_t)(sub * (T5_KSUB / 2) + ks * 8);
+                                    const uint32_t alo = a_lo0 + (uint32_t)(sub * (T5_KSUB / 2) + ks * 8);
+                                    const uint32_t bhi = b_s + (uint32_t)((ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                    const uint32_t blo = b_s + (uint32_t)((T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                    t5_mma_ts(d, ahi, bhi, (sub | ks) ? 1u : 0u);
+                                    t5_mma_ts(d, ahi, blo, 1u);
+                                    t5_mma_ts(d, alo, bhi, 1u);
+                                }
+                                t5_commit(&empty_bar[st]);   // stage (and, at the end of a K tile, the A buffer) consumed
+                                if (sub == T5_NSUB - 1) t5_commit(&tmem_full[ty]);
+                            }
+                            __syncwarp();
+                            if (++st == T5_NSTAGE) st = 0;
+                        }
+                    } else {
+                        // both units of the round stay until its hi.hi products have been issued
+                        static_assert(T5_NSUB == 2 && T5_NSTAGE % T5_NSUB == 0, "a round's units are adjacent ring stages");
                         t5_wait(&full_bar[st], (uint32_t)((is / T5_NSTAGE) & 1));
+                        t5_wait(&full_bar[st + 1], (uint32_t)(((is + 1) / T5_NSTAGE) & 1));
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (leader) {
-                            const uint32_t b_s = b_lo0 + (uint32_t)st * (uint32_t)(T5_UNIT_BYTES >> 4);
 #pragma unroll
-                            for (int ks = 0; ks < 2; ks++) {
-                                // A part (ty, hi|lo) at column (ty*2 + part) * APART; 16 k = 8 columns
-                                const uint32_t ahi = a_buf + (uint32_t)((ty * 2 + 0) * T5_APART + sub * (T5_KSUB / 2) + ks * 8);
-                                const uint32_t alo = a_buf + (uint32_t)((ty * 2 + 1) * T5_APART + sub * (T5_KSUB / 2) + ks * 8);
-                                const uint32_t bhi = b_s + (uint32_t)((ks * 2 * T5_KCHUNK_BYTES) >> 4);
-                                const uint32_t blo = b_s + (uint32_t)((T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
-                                if (MODE == 3) {
-                                    // timing probe: the same MMAs with a 128-byte-swizzle K-major B descriptor
-                                    // (rows of 128 B, 8-row groups 1024 B apart, k-steps 32 B apart)
-                                    constexpr uint32_t dh = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-                                    const uint32_t b0 = (b_s & 0x3fffu) | (1u << 16);
-                                    t5_mma_ts(d, ahi, b0 + (uint32_t)((ks * 32) >> 4), (sub | ks) ? 1u : 0u, dh);
-                                    t5_mma_ts(d, ahi, b0 + (uint32_t)((T5_TILE_BYTES + ks * 32) >> 4), 1u, dh);
-                                    t5_mma_ts(d, alo, b0 + (uint32_t)((ks * 32) >> 4), 1u, dh);
-                                    continue;
+                            for (int sub = 0; sub < T5_NSUB; sub++) {          // cross products into the empty accumulator
+                                const uint32_t b_s = b_lo0 + (uint32_t)(st + sub) * (uint32_t)(T5_UNIT_BYTES >> 4);
+#pragma unroll
+                                for (int ks = 0; ks < 2; ks++) {
+                                    const uint32_t ahi = a_hi0 + (uint32_t)(sub * (T5_KSUB / 2) + ks * 8);
+                                    const uint32_t alo = a_lo0 + (uint32_t)(sub * (T5_KSUB / 2) + ks * 8);
+                                    const uint32_t bhi = b_s + (uint32_t)((ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                    const uint32_t blo = b_s + (uint32_t)((T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                    t5_mma_ts(d, ahi, blo, (sub | ks) ? 1u : 0u);
+                                    t5_mma_ts(d, alo, bhi, 1u);
                                 }
-                                t5_mma_ts(d, ahi, bhi, (sub | ks) ? 1u : 0u);
-                                t5_mma_ts(d, ahi, blo, 1u);
-                                t5_mma_ts(d, alo, bhi, 1u);
                             }
-                            t5_commit(&empty_bar[st]);   // stage (and, at the end of a K tile, the A buffer) consumed
-                            if (sub == T5_NSUB - 1) t5_commit(&tmem_full[ty]);
+#pragma unroll
+                            for (int sub = 0; sub < T5_NSUB; sub++) {          // lattice products: exact sums
+                                const uint32_t b_s = b_lo0 + (uint32_t)(st + sub) * (uint32_t)(T5_UNIT_BYTES >> 4);
+#pragma unroll
+                                for (int ks = 0; ks < 2; ks++) {
+                                    const uint32_t ahi = a_hi0 + (uint32_t)(sub * (T5_KSUB / 2) + ks * 8);
+                                    const uint32_t bhi = b_s + (uint32_t)((ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                                    t5_mma_ts(d, ahi, bhi, 1u);
+                                }
+                                t5_commit(&empty_bar[st + sub]);   // stage (and, at the end of a K tile, the A buffer) consumed
+                            }
+                            t5_commit(&tmem_full[ty]);
                         }
                         __syncwarp();
-                        if (++st == T5_NSTAGE) st = 0;
+                        is += T5_NSUB;
+                        st += T5_NSUB;
+                        if (st == T5_NSTAGE) st = 0;
                     }
                 }
             }
@@ -494,6 +617,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
             {
                 float e0r, e0i;
                 t5_trig(Hv, 2 * (ch * T5_RC + half_id * 32) + hy2, e0r, e0i);
+                // the round's lattice quantum (relative to the plane's) rides on the row phases
+                const float qr = __ldg(qrel + ((size_t)(plane0 + pl) * nkt + (kt0 + kl)) * P.nchunk + ch);
+                e0r *= qr;
+                e0i *= qr;
                 const float e1r = e0r * D1r - e0i * D1i, e1i = e0r * D1i + e0i * D1r;
                 Sr[0] = t5_pack(e0r, e1r);
                 Si[0] = t5_pack(e0i, e1i);
@@ -518,11 +645,6 @@ __global__ void __launch_bounds__(T5_THREADS, 1) dft_tc5_kernel(const DftParams 
                 // the whole tile goes to registers first so that the accumulator is handed back to the tensor
                 // core after the TMEM load latency only, not after this thread's arithmetic
                 uint32_t xv[32], yv[32];
-                if (MODE >= 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    t5_arrive(&tmem_empty[ty]);
-                    continue;
-                }
                 t5_ld32(tb, xv);
                 t5_ld32(tb + (uint32_t)T5_RC, yv);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -605,58 +727,189 @@ int tc5_auto_split(int64_t nuvh, int nf, int nx)
     return (int)(ns < 1 ? 1 : (ns > nkt ? nkt : ns));
 }
 
-// scale_ws: [pmax | scale | unscale] as in dft_mma.cu (plane_absmax / plane_scale kernels live there)
-int launch_plane_scale(const double *img_dev, double *scale_ws, int ny, int nx, int nf);
+// Workspace of one fold: [stats: 2 u64 per round | inv_q: double per round | plane_unscale: double per plane |
+// qrel: float per round], rounds = nf * nkt * nchunk.
+size_t tc5_ws_bytes(int ny, int nx, int nf)
+{
+    const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
+    const size_t nround = (size_t)nf * ((npx + T5_KT - 1) / T5_KT) * ((npy + T5_RC - 1) / T5_RC);
+    return nround * (2 * sizeof(unsigned long long) + sizeof(double) + sizeof(float)) + (size_t)nf * sizeof(double) + 64;
+}
+struct Tc5Ws {
+    unsigned long long *stats;
+    double *inv_q, *plane_unscale;
+    float *qrel;
+};
+static Tc5Ws tc5_ws(void *ws, int ny, int nx, int nf)
+{
+    const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
+    const size_t nround = (size_t)nf * ((npx + T5_KT - 1) / T5_KT) * ((npy + T5_RC - 1) / T5_RC);
+    Tc5Ws w;
+    w.stats = reinterpret_cast<unsigned long long *>(ws);
+    w.inv_q = reinterpret_cast<double *>(w.stats + 2 * nround);
+    w.plane_unscale = w.inv_q + nround;
+    w.qrel = reinterpret_cast<float *>(w.plane_unscale + nf);
+    return w;
+}
+const double *tc5_plane_unscale(void *ws, int ny, int nx, int nf) { return tc5_ws(ws, ny, nx, nf).plane_unscale; }
 
-int launch_fold_tc5(const double *img_dev, unsigned char *B, double *scale_ws, int ny, int nx, int nf)
+int launch_fold_tc5(const double *img_dev, unsigned char *B, void *ws, int ny, int nx, int nf)
 {
     Context &c = ctx();
     const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
     const int nkt = (npx + T5_KT - 1) / T5_KT, nchunk = (npy + T5_RC - 1) / T5_RC;
-    PDSB_CHECK(launch_plane_scale(img_dev, scale_ws, ny, nx, nf));
+    const Tc5Ws w = tc5_ws(ws, ny, nx, nf);
+    const int nround = nkt * nchunk;
+    PDSB_CUDA(cudaMemsetAsync(w.stats, 0, (size_t)nf * nround * 2 * sizeof(unsigned long long), c.stream));
+    {
+        LaunchScope ls("tc5_tile_stats");
+        const int64_t total = (int64_t)nf * nchunk * T5_RC * nkt;
+        tc5_tile_stats_kernel<<<ceil_div(total, 256), 256, 0, c.stream>>>(img_dev, w.stats, ny, nx, nf, npx, npy, nkt, nchunk);
+        tc5_tile_scale_kernel<<<ceil_div(nf, 64), 64, 0, c.stream>>>(w.stats, nf, nround, w.qrel, w.inv_q, w.plane_unscale);
+        PDSB_CUDA(cudaGetLastError());
+    }
     const int64_t total = (int64_t)nf * nkt * T5_KT * nchunk * T5_RC;
     LaunchScope ls("fold_tc5");
-    fold_tc5_kernel<<<ceil_div(total, 256), 256, 0, c.stream>>>(img_dev, B, scale_ws + nf, ny, nx, nf, npx, npy, nkt, nchunk);
+    fold_tc5_kernel<<<ceil_div(total, 256), 256, 0, c.stream>>>(img_dev, B, w.inv_q, ny, nx, nf, npx, npy, nkt, nchunk);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
 
-int launch_dft_tc5(DftParams p, const unsigned char *B, int ny, int nx)
+int launch_dft_tc5(DftParams p, const unsigned char *B, void *ws, int ny, int nx)
 {
     Context &c = ctx();
     const int npx = (nx + 1) / 2, npy = (ny + 1) / 2;
     const int nkt = (npx + T5_KT - 1) / T5_KT;
     p.nchunk = (npy + T5_RC - 1) / T5_RC;
     PDSB_REQUIRE(p.nsplit >= 1 && p.nsplit <= nkt, "tc5 split");
-#ifdef PDSB_TC5_PROBES
-    constexpr size_t smem_bytes = (size_t)T5_NSTAGE * T5_UNIT_BYTES + 32768;     // slack: the swizzle probe reads wider
-#else
     constexpr size_t smem_bytes = (size_t)T5_NSTAGE * T5_UNIT_BYTES;
-#endif
     static bool attr_set = false;
     if (!attr_set) {
         PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-#ifdef PDSB_TC5_PROBES
         PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        PDSB_CUDA(cudaFuncSetAttribute(dft_tc5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-#endif
         attr_set = true;
     }
     const int64_t uvtiles = (p.nuvh + T5_M - 1) / T5_M;
     if (uvtiles <= 0) return PDSB_OK;
     const int pg = tc5_pg(p.nf);
+    const float *qrel = tc5_ws(ws, ny, nx, p.nf).qrel;
     dim3 grid((unsigned)uvtiles, (unsigned)p.nsplit, (unsigned)((p.nf + pg - 1) / pg));
     LaunchScope ls("dft_tc5_tcgen05");
-#ifdef PDSB_TC5_PROBES
-    if (c.dft_variant == DFT_VARIANT_TC5 + 1) dft_tc5_kernel<1><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
-    else if (c.dft_variant == DFT_VARIANT_TC5 + 2) dft_tc5_kernel<2><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
-    else if (c.dft_variant == DFT_VARIANT_TC5 + 3) dft_tc5_kernel<3><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
-    else
-#endif
-        dft_tc5_kernel<0><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, nkt, pg);
+    if (c.dft_variant == DFT_VARIANT_TC5 + 1) dft_tc5_kernel<0><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, qrel, nkt, pg);
+    else dft_tc5_kernel<1><<<grid, T5_THREADS, smem_bytes, c.stream>>>(p, B, qrel, nkt, pg);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
 
+// ---- accumulation probe --------------------------------------------------------------------------
+// One CTA, one accumulator round of the product kernel's MMA sequence (K = 64: 2 sub-tiles x 2 k-steps x
+// [hi.hi, hi.lo, lo.hi]) on caller-supplied fp16 operands, with the accumulator pre-loaded with `c0`.
+// It answers how the tensor core rounds its fp32 accumulator (the host compares against the exact
+// fp64 sum of the same fp16 products): tests/test_gpu_tc5_accum.py, scripts/gpu_tc5_accum.py.
+//   order 0: the product kernel's issue order;  1: all cross products first, the hi.hi products last.
+__global__ void __launch_bounds__(128, 1) tc5_probe_kernel(const __half *__restrict__ Ahi, const __half *__restrict__ Alo,
+                                                           const __half *__restrict__ Bhi, const __half *__restrict__ Blo,
+                                                           float c0, int order, float *__restrict__ out)
+{
+    extern __shared__ __align__(1024) unsigned char Bs[];       // 2 units of 16 KB
+    __shared__ __align__(8) uint64_t done_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        t5_mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t5_smem(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // B row `tid` of both sub-tiles, canonical layout
+    for (int k = 0; k < T5_KT; k++) {
+        const int sub = k / T5_KSUB, off = t5_off(tid, k % T5_KSUB);
+        *reinterpret_cast<__half *>(Bs + sub * T5_UNIT_BYTES + off) = Bhi[tid * T5_KT + k];
+        *reinterpret_cast<__half *>(Bs + sub * T5_UNIT_BYTES + T5_TILE_BYTES + off) = Blo[tid * T5_KT + k];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // A row `tid` -> TMEM lane tid: parts [hi | lo], two fp16 per column
+    for (int kc = 0; kc < T5_KT / 8; kc++) {
+        const __half *h = Ahi + tid * T5_KT + kc * 8, *l = Alo + tid * T5_KT + kc * 8;
+        const uint32_t col = lane_base + (uint32_t)(T5_ACOL + kc * 4);
+        t5_st4(col, t5_h2(h[0], h[1]), t5_h2(h[2], h[3]), t5_h2(h[4], h[5]), t5_h2(h[6], h[7]));
+        t5_st4(col + T5_APART, t5_h2(l[0], l[1]), t5_h2(l[2], l[3]), t5_h2(l[4], l[5]), t5_h2(l[6], l[7]));
+    }
+    const uint32_t cb = __float_as_uint(c0);
+    for (int c4 = 0; c4 < T5_N / 4; c4++) t5_st4(lane_base + (uint32_t)(c4 * 4), cb, cb, cb, cb);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        const uint32_t b_lo0 = t5_desc_lo(t5_smem(Bs));
+        const uint32_t a_buf = tmem_base + (uint32_t)T5_ACOL;
+        for (int pass = 0; pass < (order == 1 ? 2 : 1); pass++)
+            for (int sub = 0; sub < T5_NSUB; sub++)
+                for (int ks = 0; ks < 2; ks++) {
+                    const uint32_t ahi = a_buf + (uint32_t)(sub * (T5_KSUB / 2) + ks * 8);
+                    const uint32_t alo = ahi + (uint32_t)T5_APART;
+                    const uint32_t b_s = b_lo0 + (uint32_t)sub * (uint32_t)(T5_UNIT_BYTES >> 4);
+                    const uint32_t bhi = b_s + (uint32_t)((ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                    const uint32_t blo = b_s + (uint32_t)((T5_TILE_BYTES + ks * 2 * T5_KCHUNK_BYTES) >> 4);
+                    if (order == 0) {
+                        t5_mma_ts(tmem_base, ahi, bhi, 1u);
+                        t5_mma_ts(tmem_base, ahi, blo, 1u);
+                        t5_mma_ts(tmem_base, alo, bhi, 1u);
+                    } else if (pass == 0) {
+                        t5_mma_ts(tmem_base, ahi, blo, 1u);
+                        t5_mma_ts(tmem_base, alo, bhi, 1u);
+                    } else t5_mma_ts(tmem_base, ahi, bhi, 1u);
+                }
+        t5_commit(&done_bar);
+    }
+    t5_wait(&done_bar, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c32 = 0; c32 < T5_N / 32; c32++) {
+        uint32_t v[32];
+        t5_ld32(lane_base + (uint32_t)(c32 * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int e = 0; e < 32; e++) out[tid * T5_N + c32 * 32 + e] = __uint_as_float(v[e]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+int tc5_probe(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_t *b_hi, const uint16_t *b_lo, float c0, int order,
+              float *out)
+{
+    Context &c = ctx();
+    const size_t opb = (size_t)T5_M * T5_KT * sizeof(__half), outb = (size_t)T5_M * T5_N * sizeof(float);
+    PDSB_CHECK(c.stage_a.ensure(4 * opb + outb));
+    unsigned char *d = c.stage_a.as<unsigned char>();
+    const uint16_t *src[4] = {a_hi, a_lo, b_hi, b_lo};
+    for (int i = 0; i < 4; i++) PDSB_CUDA(cudaMemcpyAsync(d + i * opb, src[i], opb, cudaMemcpyHostToDevice, c.stream));
+    constexpr int smem_bytes = 2 * T5_UNIT_BYTES;
+    {
+        LaunchScope ls("tc5_probe");
+        tc5_probe_kernel<<<1, 128, smem_bytes, c.stream>>>((const __half *)d, (const __half *)(d + opb), (const __half *)(d + 2 * opb),
+                                                           (const __half *)(d + 3 * opb), c0, order, (float *)(d + 4 * opb));
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CUDA(cudaMemcpyAsync(out, d + 4 * opb, outb, cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    return PDSB_OK;
+}
+
 }  // namespace pdsb
+
+extern "C" int pdsb_tc5_accum_probe(const uint16_t *a_hi, const uint16_t *a_lo, const uint16_t *b_hi, const uint16_t *b_lo,
+                                    float c0, int order, float *out)
+{
+    PDSB_CHECK(pdsb::require_init());
+    PDSB_REQUIRE(a_hi && a_lo && b_hi && b_lo && out, "arguments");
+    return pdsb::tc5_probe(a_hi, a_lo, b_hi, b_lo, c0, order, out);
+}

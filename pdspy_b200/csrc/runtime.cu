@@ -1,4 +1,4 @@
-// libpdsb runtime: context, stream, buffers, timing, profiling, FMA microbenchmark.
+// libpdsb runtime: context, stream, buffers, timing, profiling, the FP32 FMA peak measurement.
 #include "common.cuh"
 #include "dft.cuh"
 
@@ -156,192 +156,6 @@ __global__ void __launch_bounds__(256) fma_bench_kernel(float *out, int iters, f
         }
         out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     }
-}
-
-// fp64: 16 independent DFMA chains per thread (variant 13) -- measures the plain CUDA-core fp64 rate
-__global__ void __launch_bounds__(256) dfma_bench_kernel(float *out, int iters, float seed)
-{
-    constexpr int NCH = 16;
-    const double m = 1.0 + seed * 1e-12, b = seed * 1e-12;
-    double acc[NCH];
-#pragma unroll
-    for (int i = 0; i < NCH; i++) acc[i] = threadIdx.x * 1e-3 + i;
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-#pragma unroll
-            for (int i = 0; i < NCH; i++) acc[i] = fma(acc[i], m, b);
-    }
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < NCH; i++) s += acc[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
-}
-
-// Pattern microbenchmarks for the DFT inner loop: acc[q][c] = fma2(x[c][t], trig[q][t], acc[q][c])
-// with the image operand x either register-resident (MODE 0) or re-loaded from shared memory by a
-// warp-broadcast LDS.128 every row (MODE 1).  UVT uv points per thread, TP trig pairs.
-template <int UVT, int TP, int MODE>
-__global__ void __launch_bounds__(128) fma_pattern_kernel(float *out, int iters, float seed)
-{
-    __shared__ __align__(16) float sm[4 * TP * 2 * 8];
-    for (int i = threadIdx.x; i < 4 * TP * 2 * 8; i += 128) sm[i] = 1.0f + 1e-6f * i * seed;
-    __syncthreads();
-    unsigned long long trig[UVT][TP], acc[UVT][4];
-#pragma unroll
-    for (int q = 0; q < UVT; q++) {
-#pragma unroll
-        for (int t = 0; t < TP; t++) {
-            float2 a = make_float2(1.0f + 1e-7f * (threadIdx.x + t + q), 1.0f - 1e-7f * (threadIdx.x + t));
-            trig[q][t] = *reinterpret_cast<unsigned long long *>(&a);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; c++) acc[q][c] = 0ull;
-    }
-    unsigned long long xr[4][TP];
-    if (MODE == 0) {
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int t = 0; t < TP; t++) xr[c][t] = reinterpret_cast<const unsigned long long *>(sm)[c * TP + t];
-    }
-#pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(sm + (it & 7) * (4 * TP * 2));
-#pragma unroll
-        for (int g = 0; g < TP / 2; g++) {
-            ulonglong2 x[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                if (MODE == 1) x[c] = row[c * (TP / 2) + g];
-                else x[c] = make_ulonglong2(xr[c][2 * g], xr[c][2 * g + 1]);
-            }
-#pragma unroll
-            for (int q = 0; q < UVT; q++)
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    acc[q][c] = fma2_(x[c].x, trig[q][2 * g], acc[q][c]);
-                    acc[q][c] = fma2_(x[c].y, trig[q][2 * g + 1], acc[q][c]);
-                }
-        }
-    }
-    float s = 0;
-#pragma unroll
-    for (int q = 0; q < UVT; q++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            float2 a = *reinterpret_cast<float2 *>(&acc[q][c]);
-            s += a.x + a.y;
-        }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// Same inner product with the image operand read from CONSTANT memory through a warp-uniform
-// index (uniform datapath: no per-lane register write, no shared-memory wavefront).  Feasibility
-// probe for a constant-bank-staged DFT kernel.
-__constant__ float c_probe[16384];
-
-template <int UVT, int TP>
-__global__ void __launch_bounds__(128) fma_const_kernel(float *out, const float *seedv, int iters)
-{
-    unsigned long long trig[UVT][TP], acc[UVT][4];
-#pragma unroll
-    for (int q = 0; q < UVT; q++) {
-#pragma unroll
-        for (int t = 0; t < TP; t++) {
-            float2 a = make_float2(seedv[(threadIdx.x + 7 * t + 3 * q) & 1023], seedv[(threadIdx.x * 3 + t + q) & 1023]);
-            trig[q][t] = *reinterpret_cast<unsigned long long *>(&a);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; c++) acc[q][c] = 0ull;
-    }
-    const unsigned long long *cimg = reinterpret_cast<const unsigned long long *>(c_probe);
-    const int rows = 16384 / (4 * TP * 2);          // rows of [4 comps][TP pairs]
-#pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-#pragma unroll 2
-        for (int r = 0; r < rows; r++) {
-            const unsigned long long *row = cimg + (size_t)r * (4 * TP);
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-#pragma unroll
-                for (int t = 0; t < TP; t++) {
-                    const unsigned long long x = row[c * TP + t];
-#pragma unroll
-                    for (int q = 0; q < UVT; q++) acc[q][c] = fma2_(x, trig[q][t], acc[q][c]);
-                }
-        }
-    }
-    float s = 0;
-#pragma unroll
-    for (int q = 0; q < UVT; q++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            float2 a = *reinterpret_cast<float2 *>(&acc[q][c]);
-            s += a.x + a.y;
-        }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// Legacy warp-level tensor-core path probe: mma.sync m16n8k8 TF32 (register fragments), 8 independent
-// accumulator tiles per warp.  Measures what the non-tcgen05 MMA path sustains on sm_100a.
-__global__ void __launch_bounds__(256) mma_tf32_bench_kernel(float *out, int iters, float seed)
-{
-    unsigned a[4], b[2];
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) a[i] = __float_as_uint(1.0f + seed * 1e-3f * (threadIdx.x + i));
-#pragma unroll
-    for (int i = 0; i < 2; i++) b[i] = __float_as_uint(1.0f - seed * 1e-3f * (threadIdx.x + i));
-#pragma unroll
-    for (int t = 0; t < 8; t++)
-#pragma unroll
-        for (int i = 0; i < 4; i++) acc[t][i] = 0.f;
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-            for (int t = 0; t < 8; t++)
-                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                             : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
-                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-    }
-    float s = 0;
-#pragma unroll
-    for (int t = 0; t < 8; t++)
-#pragma unroll
-        for (int i = 0; i < 4; i++) s += acc[t][i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// fp16 inputs, fp32 accumulate: mma.sync m16n8k16
-__global__ void __launch_bounds__(256) mma_f16_bench_kernel(float *out, int iters, float seed)
-{
-    unsigned a[4], b[2];
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) a[i] = 0x3c003c00u + (unsigned)(seed * (threadIdx.x + i));
-#pragma unroll
-    for (int i = 0; i < 2; i++) b[i] = 0x3c003c00u + (unsigned)(seed * (threadIdx.x * 3 + i));
-#pragma unroll
-    for (int t = 0; t < 8; t++)
-#pragma unroll
-        for (int i = 0; i < 4; i++) acc[t][i] = 0.f;
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-            for (int t = 0; t < 8; t++)
-                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                             : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
-                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-    }
-    float s = 0;
-#pragma unroll
-    for (int t = 0; t < 8; t++)
-#pragma unroll
-        for (int i = 0; i < 4; i++) s += acc[t][i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 }  // namespace pdsb
@@ -606,11 +420,7 @@ int pdsb_launch_count(int64_t *count)
 int pdsb_set_dft_variant(int variant)
 {
     bool ok = variant == 0 || (variant >= 1 && variant <= dft_variant_count()) ||
-              (variant >= DFT_VARIANT_MMA && variant <= DFT_VARIANT_MMA + 4) || variant == DFT_VARIANT_TC5 ||
-              variant == DFT_VARIANT_F64;
-#ifdef PDSB_TC5_PROBES
-    ok = ok || (variant > DFT_VARIANT_TC5 && variant <= DFT_VARIANT_TC5 + 3);
-#endif
+              variant == DFT_VARIANT_TC5 || variant == DFT_VARIANT_TC5 + 1 || variant == DFT_VARIANT_F64;
     PDSB_REQUIRE(ok, "unknown DFT kernel variant");
     ctx().dft_variant = variant;
     return PDSB_OK;
@@ -627,64 +437,18 @@ int pdsb_bench_fma(int variant, int iters, double *tflops, double *ms_out)
 {
     PDSB_CHECK(require_init());
     PDSB_REQUIRE(tflops && iters > 0, "tflops/iters");
+    PDSB_REQUIRE(variant == 0 || variant == 1, "variant (0 = FFMA, 1 = FFMA2)");
     Context &c = ctx();
-    int blocks = c.sm_count * 8, threads = variant < 2 ? 256 : 128;
-    PDSB_CHECK(c.red.ensure((size_t)(blocks * 256 + 1024) * sizeof(float)));
-    PDSB_CUDA(cudaMemsetAsync(c.red.as<float>() + (size_t)blocks * 256, 0x3c, 1024 * sizeof(float), c.stream));
-    if (variant >= 8) {
-        static bool filled = false;
-        if (!filled) {
-            std::vector<float> h(16384);
-            for (int i = 0; i < 16384; i++) h[i] = 1.0f + 1e-3f * (i % 97);
-            PDSB_CUDA(cudaMemcpyToSymbol(c_probe, h.data(), sizeof(float) * 16384));
-            filled = true;
-        }
-    }
-    double fmas_per_thread_iter = 8.0 * 16.0;
+    const int blocks = c.sm_count * 8, threads = 256;
+    PDSB_CHECK(c.red.ensure((size_t)blocks * 256 * sizeof(float)));
+    const double fmas_per_thread_iter = 8.0 * 16.0;
     for (int rep = 0; rep < 2; rep++) {
         if (rep == 1) PDSB_CUDA(cudaEventRecord(c.t0, c.stream));
         {
             LaunchScope ls("fma_bench");
             float *o = c.red.as<float>();
-            switch (variant) {
-                case 0: fma_bench_kernel<0><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); break;
-                case 1: fma_bench_kernel<1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); break;
-                // (UVT, trig pairs, operand source): lane-FMAs per iteration = UVT*4*TP*2
-                case 2: fma_pattern_kernel<2, 8, 0><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 2 * 4 * 8 * 2; break;
-                case 3: fma_pattern_kernel<2, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 2 * 4 * 8 * 2; break;
-                case 4: fma_pattern_kernel<4, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 4 * 4 * 8 * 2; break;
-                case 5: fma_pattern_kernel<1, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 1 * 4 * 8 * 2; break;
-                case 6: fma_pattern_kernel<4, 8, 0><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 4 * 4 * 8 * 2; break;
-                case 7: fma_pattern_kernel<3, 8, 1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f); fmas_per_thread_iter = 3 * 4 * 8 * 2; break;
-                case 8:
-                case 9:
-                case 10: {
-                    // iters here = passes over the 64 KB constant block
-                    const int passes = iters / 256 > 0 ? iters / 256 : 1;
-                    float *seedv = o + (size_t)blocks * 256;
-                    if (variant == 8) { fma_const_kernel<2, 8><<<blocks, 128, 0, c.stream>>>(o, seedv, passes); fmas_per_thread_iter = 2.0 * 4 * 8 * 2 * (16384 / 64); }
-                    if (variant == 9) { fma_const_kernel<4, 8><<<blocks, 128, 0, c.stream>>>(o, seedv, passes); fmas_per_thread_iter = 4.0 * 4 * 8 * 2 * (16384 / 64); }
-                    if (variant == 10) { fma_const_kernel<2, 16><<<blocks, 128, 0, c.stream>>>(o, seedv, passes); fmas_per_thread_iter = 2.0 * 4 * 16 * 2 * (16384 / 128); }
-                    iters = passes;
-                    break;
-                }
-                case 11:
-                    // per thread-iteration: 4*8 MMAs of 16x8x8 = 1024 MAC per warp each -> per thread 32 MAC
-                    mma_tf32_bench_kernel<<<blocks, 256, 0, c.stream>>>(o, iters, 1.0f);
-                    threads = 256;
-                    fmas_per_thread_iter = 4.0 * 8.0 * (16.0 * 8.0 * 8.0) / 32.0;
-                    break;
-                case 12:
-                    mma_f16_bench_kernel<<<blocks, 256, 0, c.stream>>>(o, iters, 1.0f);
-                    threads = 256;
-                    fmas_per_thread_iter = 4.0 * 8.0 * (16.0 * 8.0 * 16.0) / 32.0;
-                    break;
-                case 13:
-                    dfma_bench_kernel<<<blocks, 256, 0, c.stream>>>(o, iters, 1.0f);
-                    threads = 256;
-                    break;
-                default: set_error("unknown fma bench variant %d", variant); return PDSB_ERR_ARG;
-            }
+            if (variant == 0) fma_bench_kernel<0><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f);
+            else fma_bench_kernel<1><<<blocks, threads, 0, c.stream>>>(o, iters, 1.0f);
         }
         PDSB_CUDA(cudaGetLastError());
     }

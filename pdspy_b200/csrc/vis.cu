@@ -325,7 +325,7 @@ static int reduce_blocks(const double *blockpart, int nb, int ncol, double *out_
 struct DftRun {
     DftGeom g;
     int nsplit;
-    const double *plane_unscale = nullptr;   // experimental tensor-core variant: V_i *= plane_unscale[i]
+    const double *plane_unscale = nullptr;   // tensor-core kernel: V_i *= plane_unscale[i]
 };
 
 static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
@@ -346,15 +346,13 @@ static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf
         run->plane_unscale = nullptr;
         return PDSB_OK;
     }
-    if (c.dft_variant >= DFT_VARIANT_MMA) {
-        // experimental: fp16-split operands on the tensor cores (dft_mma.cu: mma.sync; dft_tc5.cu: tcgen05)
-        const bool tc5 = c.dft_variant >= DFT_VARIANT_TC5;
+    if (c.dft_variant >= DFT_VARIANT_TC5) {
+        // tensor-core kernel: lattice-split fp16 operands on tcgen05 (dft_tc5.cu)
         DftGeom g = make_geom(ny, nx, nf, 32, dxy);
-        PDSB_CHECK(c.folded.ensure(tc5 ? tc5_operand_bytes(ny, nx, nf) : mma_operand_bytes(ny, nx, nf)));
-        PDSB_CHECK(c.mma_ws.ensure((size_t)3 * nf * sizeof(double)));
-        if (tc5) PDSB_CHECK(launch_fold_tc5(img_dev, c.folded.as<unsigned char>(), c.mma_ws.as<double>(), ny, nx, nf));
-        else PDSB_CHECK(launch_fold_half(img_dev, c.folded.as<unsigned char>(), c.mma_ws.as<double>(), ny, nx, nf));
-        const int nsplit = tc5 ? tc5_auto_split(ds->nuvh, nf, nx) : mma_auto_split(ds->nuvh, nf, nx);
+        PDSB_CHECK(c.folded.ensure(tc5_operand_bytes(ny, nx, nf)));
+        PDSB_CHECK(c.mma_ws.ensure(tc5_ws_bytes(ny, nx, nf)));
+        PDSB_CHECK(launch_fold_tc5(img_dev, c.folded.as<unsigned char>(), c.mma_ws.ptr, ny, nx, nf));
+        const int nsplit = tc5_auto_split(ds->nuvh, nf, nx);
         PDSB_CHECK(c.partial.ensure((size_t)nsplit * nf * ds->nuvh * sizeof(double2)));
         DftParams p;
         p.F = nullptr;
@@ -369,14 +367,13 @@ static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf
         p.hx = g.hx2 ? 0.5 : 0.0;
         p.hy = g.hy2 ? 0.5 : 0.0;
         p.part = c.partial.as<double2>();
-        if (tc5) PDSB_CHECK(launch_dft_tc5(p, c.folded.as<unsigned char>(), ny, nx));
-        else PDSB_CHECK(launch_dft_mma(p, c.folded.as<unsigned char>(), ny, nx));
+        PDSB_CHECK(launch_dft_tc5(p, c.folded.as<unsigned char>(), c.mma_ws.ptr, ny, nx));
         run->g = g;
         run->nsplit = nsplit;
-        run->plane_unscale = c.mma_ws.as<double>() + 2 * nf;
+        run->plane_unscale = tc5_plane_unscale(c.mma_ws.ptr, ny, nx, nf);
         return PDSB_OK;
     }
-    const int variant = dft_pick_variant();
+    const int variant = dft_pick_variant(nx);
     const int tcp = dft_variant_tcp(variant);
     DftGeom g = make_geom(ny, nx, nf, tcp, dxy);
     PDSB_CHECK(c.folded.ensure(folded_floats(g) * sizeof(float)));

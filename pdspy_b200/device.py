@@ -111,15 +111,15 @@ def clear_cache():
         ds.destroy()
 
 
-DFT_KERNELS = {"fp32": 0, "mma": 103, "tcgen05": 200, "fp64": 300}
+DFT_KERNELS = {"fp32": 0, "tcgen05": 200, "fp64": 300}
 
 
 def set_dft_kernel(kind="fp32"):
     """Select the DFT kernel every later interpolate_model / likelihood call runs.
 
-    "fp32" (default): the FP32-pipe kernel of BASELINE.json's north star.  "tcgen05" / "mma": the
-    experimental tensor-core kernels (fp16 hi+lo split operands, same 1e-5 parity bound).
-    "fp64": the all-fp64 reference kernel (1e-13 of max|V| from the CPU oracle, ~7x slower than "fp32").
+    "fp32" (default): the FP32-pipe kernel of BASELINE.json's north star.  "tcgen05": the tensor-core
+    kernel (tcgen05.mma / TMEM, lattice-split fp16 operands, ~10x faster, same parity bounds).
+    "fp64": the all-fp64 reference kernel (1e-13 of max|V| from the CPU oracle, ~8x slower than "fp32").
     An int is passed to pdsb_set_dft_variant unchanged.  The environment variable PDSPY_B200_DFT
     sets the initial choice."""
     variant = DFT_KERNELS[kind] if isinstance(kind, str) else int(kind)

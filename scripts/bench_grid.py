@@ -2,8 +2,10 @@
 import ctypes, sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import pdspy_b200 as pb
-from pdspy_b200 import _lib, synth
+import synth
+from pdspy_b200 import _lib
 from oracle import grid as og
 L = _lib.lib()
 nvis = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000

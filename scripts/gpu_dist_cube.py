@@ -3,13 +3,15 @@ full upload == the single-process value, on N ranks."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch, torch.distributed as dist
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 os.environ["PDSB_DEVICE"] = str(lr)
 torch.cuda.set_device(lr)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-from pdspy_b200 import synth, dist as pdist, PinnedArray
+import synth
+from pdspy_b200 import dist as pdist, PinnedArray
 from pdspy_b200.interferometry import Visibilities
 A = synth.ARCSEC
 n, nf, nuv = 128, 3, 20000

@@ -2,13 +2,15 @@
 import contextlib, io, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch, torch.distributed as dist
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 os.environ["PDSB_DEVICE"] = str(lr)
 torch.cuda.set_device(lr)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-from pdspy_b200 import synth, dist as pdist
+import synth
+from pdspy_b200 import dist as pdist
 from pdspy_b200.interferometry import Visibilities, grid
 u, v = synth.synth_uv(2_000_000, 0.01 * synth.ARCSEC)
 re, im, w = synth.synth_data(2_000_000, 2)

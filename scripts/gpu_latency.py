@@ -2,8 +2,9 @@
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import pdspy_b200 as pb
-from pdspy_b200 import synth
+import synth
 from pdspy_b200.interferometry import interpolate_model, loglike_image, Visibilities
 for kern in ("fp32", "tcgen05"):
     pb.set_dft_kernel(kern)

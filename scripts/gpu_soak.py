@@ -2,8 +2,9 @@
 import ctypes, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import pdspy_b200 as pb
-from pdspy_b200 import synth
+import synth
 from pdspy_b200.interferometry import loglike_image, interpolate_model, Visibilities, grid
 import torch
 
@@ -13,7 +14,7 @@ def used():
     return (total - free) / 2 ** 20
 
 
-for kern in ("fp32", "tcgen05", "mma", "fp64"):
+for kern in ("fp32", "tcgen05", "fp64"):
     pb.set_dft_kernel(kern)
     c = synth.make_config("C1")
     re, im, w = synth.synth_data(c["u"].size, c["nf"])

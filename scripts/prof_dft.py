@@ -3,8 +3,10 @@ usage: prof_dft.py WORKLOAD VARIANT REPS [NUV]"""
 import ctypes, sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import pdspy_b200 as pb
-from pdspy_b200 import _lib, synth
+import synth
+from pdspy_b200 import _lib
 A = synth.ARCSEC
 wl, variant, reps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 nuv = int(sys.argv[4]) if len(sys.argv) > 4 else None

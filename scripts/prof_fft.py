@@ -2,8 +2,10 @@
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import pdspy_b200 as pb
-from pdspy_b200 import _lib, synth
+import synth
+from pdspy_b200 import _lib
 A = synth.ARCSEC
 c = synth.make_config("C3")
 re, im, w = synth.synth_data(c["u"].size, c["nf"])

@@ -22,12 +22,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))          # tests/synth.py: the seeded synthetic inputs
 sys.path.insert(0, HERE)
 
 from hdf5_mini import read_hdf5_flat          # noqa: E402
 from oracle import build_ref                  # noqa: E402
 from oracle import dft as od                  # noqa: E402
-from pdspy_b200 import synth                  # noqa: E402
+import synth                  # noqa: E402
 
 ARCSEC = 4.84813681e-6
 

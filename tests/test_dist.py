@@ -7,7 +7,8 @@ import socket
 import numpy as np
 import pytest
 
-from pdspy_b200 import synth, dist as pdist
+import synth
+from pdspy_b200 import dist as pdist
 from pdspy_b200.interferometry import Visibilities
 
 

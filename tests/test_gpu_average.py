@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gol
 from make_golden import AVERAGE_CASES, multi_channel_set           # noqa: E402
 
 from oracle import average as oa                                   # noqa: E402
-from pdspy_b200 import synth                                       # noqa: E402
+import synth                                       # noqa: E402
 from pdspy_b200.interferometry import average, center, Visibilities   # noqa: E402
 
 pytestmark = pytest.mark.gpu

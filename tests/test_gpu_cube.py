@@ -7,7 +7,7 @@ import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import cube as oc, dft as od                                # noqa: E402
-from pdspy_b200 import synth                                            # noqa: E402
+import synth                                            # noqa: E402
 from pdspy_b200.interferometry import postprocess_channels, model_visibilities, loglike_image, Visibilities  # noqa: E402
 
 pytestmark = pytest.mark.gpu

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 from oracle import dft as od
-from pdspy_b200 import synth, _lib, Dataset, DeviceBuffer
+import synth
+from pdspy_b200 import _lib, Dataset, DeviceBuffer
 from pdspy_b200.interferometry import interpolate_model, Visibilities
 
 pytestmark = pytest.mark.gpu
@@ -61,7 +62,7 @@ def test_parity_small_shapes(gpu, ny, nx, nf, nuv, herm):
     assert relerr(vis, ref) < TOL
 
 
-@pytest.mark.parametrize("variant", list(range(1, 23)) + [100, 101, 102, 103, 104, 200])
+@pytest.mark.parametrize("variant", [1, 2, 200, 201, 300])
 @pytest.mark.parametrize("split", [1, 3])
 def test_every_kernel_variant_and_split(gpu, variant, split):
     gpu.pdsb_set_dft_variant(variant)
@@ -92,8 +93,9 @@ def test_tcgen05_variant_shapes(gpu, shape, split):
 
 
 def test_unknown_variant_is_rejected(gpu):
-    assert gpu.pdsb_set_dft_variant(23) != 0
-    assert gpu.pdsb_set_dft_variant(201) != 0
+    assert gpu.pdsb_set_dft_variant(3) != 0
+    assert gpu.pdsb_set_dft_variant(103) != 0
+    assert gpu.pdsb_set_dft_variant(202) != 0
     assert gpu.pdsb_set_dft_variant(0) == 0
 
 

@@ -15,7 +15,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gol
 from make_golden import GRID_CASES_FIXTURE, GRID_CASES_MULTI, multi_channel_set      # noqa: E402
 
 from oracle import grid as og                                                        # noqa: E402
-from pdspy_b200 import synth, _lib                                                   # noqa: E402
+import synth
+from pdspy_b200 import _lib                                                   # noqa: E402
 from pdspy_b200.interferometry import grid, freqcorrect, Visibilities                # noqa: E402
 
 pytestmark = pytest.mark.gpu

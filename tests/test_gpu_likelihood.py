@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from oracle import dft as od, likelihood as ol
-from pdspy_b200 import synth, _lib, utils
+import synth
+from pdspy_b200 import _lib, utils
 from pdspy_b200.interferometry import (interpolate_model, Visibilities, chisq, loglike_image, loglike_images)
 
 pytestmark = pytest.mark.gpu

@@ -5,7 +5,8 @@ import ctypes
 import numpy as np
 import pytest
 
-from pdspy_b200 import _lib, synth, DeviceBuffer, PinnedArray, Dataset
+import synth
+from pdspy_b200 import _lib, DeviceBuffer, PinnedArray, Dataset
 
 pytestmark = pytest.mark.gpu
 
@@ -37,7 +38,7 @@ def test_profile_and_launch_count(gpu):
     _lib.check(gpu.pdsb_profile_enable(1))
     c = synth.make_config("C1", nuv=4096)
     from pdspy_b200.interferometry import interpolate_model
-    _lib.check(gpu.pdsb_set_dft_variant(11))        # the FP32-pipe kernel: the launch list below is its
+    _lib.check(gpu.pdsb_set_dft_variant(1))        # the FP32-pipe kernel: the launch list below is its
     try:
         interpolate_model(c["u"], c["v"], c["freq"], c["model"])
     finally:

@@ -8,7 +8,7 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import dft as od, unstructured as ou                        # noqa: E402
 import pdspy_b200 as pb                                                  # noqa: E402
-from pdspy_b200 import synth                                             # noqa: E402
+import synth                                             # noqa: E402
 from pdspy_b200.interferometry import interpolate_model                  # noqa: E402
 from pdspy_b200.interferometry.unstructured import regrid                # noqa: E402
 

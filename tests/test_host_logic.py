@@ -4,7 +4,8 @@ import pickle
 import numpy as np
 import pytest
 
-from pdspy_b200 import synth, Image
+import synth
+from pdspy_b200 import Image
 from pdspy_b200.interferometry import Visibilities, VisibilitiesObject
 from pdspy_b200.interferometry.interpolate_model import interpolate_model
 from pdspy_b200 import device

@@ -8,7 +8,7 @@ import pytest
 
 from oracle import dft as od
 from oracle.build import lib as olib
-from pdspy_b200 import synth
+import synth
 
 A = od.ARCSEC
 
