@@ -2,25 +2,31 @@
 """Headline benchmark: the fused model-to-visibility likelihood on synthetic data of the shapes
 BASELINE.json names.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dft fp32|tcgen05] [--workload C3|C2|C4|C5]
+                    [--impl reference] [--no-extras] [--no-cpu-baseline]
 
 N > 1 is launched by the driver as
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-one rank per GPU; the uv list is sharded over ranks (strong scaling: the likelihood of ONE
-dataset), the image cube is replicated, and chi^2[nf] + the log term are all-reduced over NCCL.
+one rank per GPU.  ONE synthetic data set is sharded over the ranks by uv points (strong scaling: the
+likelihood of one data set), the image cube is replicated, chi^2[nf] + the log term are all-reduced over
+NCCL, and rank 0 checks the sharded result against the same likelihood evaluated unsharded on its own GPU.
 
-A step = one likelihood evaluation: fold the fp64 cube -> direct Fourier sampling at every uv
-point -> weighted chi^2 against the data -> scalar (pdspy: interpolate_model.py:11-57 followed by
-utils/emcee.py:31-43).  Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement".
+A step = one likelihood evaluation: fold the fp64 cube -> direct Fourier sampling at every uv point ->
+weighted chi^2 against the data -> scalar (pdspy: interpolate_model.py:11-57 followed by
+utils/emcee.py:31-43).  Rank 0 prints ONE JSON line: value / e2e / roofline of the default workload
+(C3 = BASELINE.json configs[2]) and, under `extras.workloads`, the other BASELINE configurations
+(C2 = configs[1], C4 = configs[3] gridding, C5 = configs[4] walker batch) with value, e2e and roofline
+each.  See DESIGN.md "Measurement".
 """
 import argparse
+import contextlib
 import ctypes
+import io
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -36,8 +42,26 @@ METRIC = "pixel_visibility_pairs_per_s"
 UNIT = "pairs/s"
 FLOP_PER_PAIR = 4.0          # algorithmic: 2 FMA per (pixel, uv, channel) pair
 L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
-# DRAM bytes per DFT launch measured by ncu (bytes), keyed by (workload, n_gpus)
-NCU_TRAFFIC_BYTES = {("C3", 1): 571.6e6, ("C2", 1): 12.27e6}
+DFT_VARIANT = {"fp32": 0, "tcgen05": 200}
+DTYPE = {"fp32": "f32 products, f64 phase seeds and accumulation",
+         "tcgen05": "f16 x2 lattice-split operands on tcgen05 (22 bits), f32 accumulate, f64 partial sums"}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures
+    (profiles/traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep files); None where not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(key)
+    except Exception:
+        return None
 
 
 def workload_config(name, nuv_override=None):
@@ -49,31 +73,23 @@ def workload_config(name, nuv_override=None):
     return dict(name=name, npix=n, nf=nf, nuv=nuv, pixelsize=px, dRA=dra, dDec=ddec)
 
 
-def describe(cfg, world):
-    names = {"C3": "spectral-line cube 512x512x64 channels, 1M uv per channel, full chi^2 log-likelihood "
-                   "(BASELINE.json configs[2])",
-             "C2": "continuum 1024x1024 image onto 1M uv points with dRA/dDec offset + chi^2 "
-                   "(BASELINE.json configs[1])",
-             "C1": "256x256 single channel onto 50k uv points (BASELINE.json configs[0])",
-             "C5": "batched likelihood for emcee walkers x 512x512x64-channel cubes, walkers sharded over the GPUs "
-                   "(BASELINE.json configs[4])"}
-    return {"workload": names[cfg["name"]], "npix": cfg["npix"], "channels": cfg["nf"], "nuv": cfg["nuv"],
+WORKLOAD_NAMES = {
+    "C3": "spectral-line cube 512x512x64 channels, 1M uv per channel, full chi^2 log-likelihood (BASELINE.json configs[2])",
+    "C2": "continuum 1024x1024 image onto 1M uv points with dRA/dDec offset + chi^2 (BASELINE.json configs[1])",
+    "C1": "256x256 single channel onto 50k uv points (BASELINE.json configs[0])",
+    "C4": "grid() of 10M visibilities onto 2048x2048, exp*sinc convolution kernel, natural weights (BASELINE.json configs[3])",
+    "C5": "batched likelihood for emcee walkers x 512x512x64-channel cubes, walkers sharded over the GPUs "
+          "(BASELINE.json configs[4])"}
+
+
+def describe(cfg):
+    """config of the JSON line: identical for every N (the driver compares it across its runs)."""
+    return {"workload": WORKLOAD_NAMES[cfg["name"]], "npix": cfg["npix"], "channels": cfg["nf"], "nuv": cfg["nuv"],
             "pairs_per_step": float(cfg["npix"]) ** 2 * cfg["nuv"] * cfg["nf"],
-            "partition": "uv points sharded over %d rank(s), cube replicated, all-reduce of nf+1 doubles" % world,
+            "partition": "one data set, uv points sharded over the ranks (Hermitian pairs kept together), cube "
+                         "replicated, all-reduce of nf+1 doubles",
             "cache": "L2 flushed (256 MB memset) before every timed step",
-            "uv": "Hermitian-doubled synthetic ALMA-like list, seed 1234 (pdspy_b200/synth.py)"}
-
-
-def make_local_data(cfg, rank, world):
-    """This rank's uv shard + synthetic data for it (noise only; the value is irrelevant to timing)."""
-    from pdspy_b200 import dist
-    u, v = synth.synth_uv(cfg["nuv"], cfg["pixelsize"] * A)
-    rows = dist.shard_rows(u, v, rank, world)
-    us, vs = np.ascontiguousarray(u[rows]), np.ascontiguousarray(v[rows])
-    re, im, w = synth.synth_data(us.size, cfg["nf"], seed=4321 + 1000 * rank + world)
-    freq = synth.synth_freq(cfg["nf"])
-    from pdspy_b200.interferometry import Visibilities
-    return Visibilities(us, vs, freq, re, im, w), (u, v)
+            "uv": "Hermitian-doubled synthetic ALMA-like list, seed 1234 (tests/synth.py)"}
 
 
 class ClockSampler:
@@ -127,19 +143,19 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            # "under load": samples at or above the median (the idle edges are below it)
             out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
                    "samples": len(sm), "power_w_max": float(max(power))}
         return out
 
 
 # ------------------------------------------------------------------------------------------
+# reference arm
 def run_reference(args, cfg, rank, world):
     """Reference arm: the reference's CPU path for this workload on the host cores.  galario (the
     library pdspy calls, interpolate_model.py:23-24) is not installable here, so its algorithm is
     timed from the restatement oracle/dft.py:galario_like (rfft2 + bilinear + phase, per channel as
     interpolate_model.py:22 loops), followed by the verbatim numpy likelihood (emcee.py:31-43).
-    Bounded sample per step: NCH_SAMPLE of the channels, all uv points, all pixels."""
+    Bounded sample per step: one channel per host thread, all uv points, all pixels."""
     if rank != 0:
         return
     if cfg["name"] == "C4":
@@ -164,10 +180,8 @@ def run_reference(args, cfg, rank, world):
         value = ns * args.steps / dt
         emit({"impl": "reference", "metric": "gridded_visibilities_per_s", "value": value, "unit": "vis/s",
               "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-              "higher_is_better": True, "scaling": "replicas only (not sharded)", "vs_baseline": None, "dtype": "f64",
-              "data": "synthetic",
-              "config": {"workload": "grid() of 10M visibilities onto 2048x2048, exp*sinc convolution kernel, natural "
-                                     "weights (BASELINE.json configs[3])", "nvis": nvis, "gridsize": G},
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+              "data": "synthetic", "config": gridding_config(cfg),
               "cpu_baseline": {"value": value, "unit": "vis/s", "cores": 1, "kind": "reference",
                                "sample": "first %d of %d visibilities per step" % (ns, nvis)},
               "e2e": {"value": value, "unit": "vis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -200,15 +214,19 @@ def run_reference(args, cfg, rank, world):
     pairs = float(cfg["npix"]) ** 2 * cfg["nuv"] * nch * args.steps
     value = pairs / dt
     sample = "%d of %d channels, all %d uv points, all pixels per step" % (nch, cfg["nf"], cfg["nuv"])
+    cfgd = describe(cfg)
+    if cfg["name"] == "C5":
+        cfgd = walker_config(cfg, args.walkers)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": describe(cfg, 1),
+            "config": cfgd,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                              "what": "galario algorithm (rfft2 + bilinear interpolation, restated: galario itself is "
                                      "not installable offline) + numpy likelihood; pairs/s counts the pixel-visibility "
                                      "pairs the result represents, not operations executed (the FFT path is "
-                                     "O(n^2 log n + nuv))"},
+                                     "O(n^2 log n + nuv)); a stand-in for galario's C++/OpenMP library, which would "
+                                     "be several times faster: ratios against this line are upper bounds"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "likelihood_evals_per_s_equiv": args.steps / dt * nch / cfg["nf"]}
     emit(line)
@@ -222,6 +240,7 @@ def cpu_baseline_port(cfg):
     L = olib()
     cores = L.oracle_num_threads()
     nuv_s = {"C3": 6144, "C2": 98304, "C1": 50000}[cfg["name"]]          # about 10 s of work on 16 host cores
+    nuv_s = min(nuv_s, cfg["nuv"])
     u, v = synth.synth_uv(cfg["nuv"], cfg["pixelsize"] * A)
     u, v = np.ascontiguousarray(u[:nuv_s]), np.ascontiguousarray(v[:nuv_s])
     img = np.ascontiguousarray(synth.synth_image(cfg["npix"], cfg["nf"], cfg["pixelsize"])[:, :, :, 0])
@@ -239,119 +258,366 @@ def cpu_baseline_port(cfg):
                       "one sincos per pixel-visibility pair, OpenMP)" % (nuv_s, cfg["nuv"], cfg["nf"])}
 
 
-def run_gridding(args, cfg, rank, world):
+# ------------------------------------------------------------------------------------------
+class Env:
+    """Process-wide handles of one bench run."""
+
+    def __init__(self, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        from pdspy_b200 import _lib
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        self.torch, self.dist, self._lib = torch, dist, _lib
+        self.L = _lib.lib()
+        _lib.check(self.L.pdsb_set_stream(torch.cuda.current_stream().cuda_stream))
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def launches(self):
+        n = ctypes.c_int64()
+        self.L.pdsb_launch_count(ctypes.byref(n))
+        return int(n.value)
+
+    def profile(self, prefix):
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        self._lib.check(self.L.pdsb_profile_get(prefix, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, int(n.value)
+
+
+def timed_device_steps(env, step, steps, warmup, profile_prefix=None, sample_clocks=False):
+    """`warmup` untimed + `steps` timed calls of step(), each timed with CUDA events on the stream the kernels
+    run on, L2 flushed before every one, barrier + synchronize on both sides, max over ranks.
+    Returns (total ms, kernel ms per launch of `profile_prefix` (max over ranks), launches of it on this rank,
+    libpdsb launches in the timed region, clocks, last result)."""
+    torch, _lib, L = env.torch, env._lib, env.L
+    out = None
+    for _ in range(warmup):
+        env.flush.zero_()
+        out = step()
+    env.barrier()
+    sampler = ClockSampler(env.local_rank) if sample_clocks and env.rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.check(L.pdsb_profile_reset())
+    _lib.check(L.pdsb_profile_enable(1))
+    n0 = env.launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    env.barrier()
+    for e0, e1 in evs:
+        env.flush.zero_()
+        e0.record()
+        out = step()
+        e1.record()
+    env.barrier()
+    n1 = env.launches()
+    _lib.check(L.pdsb_profile_enable(0))
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    k_ms, k_n = env.profile(profile_prefix) if profile_prefix else (0.0, 0)
+    total_ms, k_ms_max = env.max_over_ranks([total_ms, k_ms])
+    return total_ms, (k_ms_max / k_n if k_n else None), k_n, n1 - n0, clocks, out
+
+
+def timed_host_steps(env, step, steps, warmup=2):
+    """End to end: host wall clock around `steps` synchronous calls, barrier on both sides, max over ranks."""
+    out = None
+    for _ in range(warmup):
+        out = step()
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = step()
+    env.barrier()
+    dt = time.perf_counter() - t0
+    return env.max_over_ranks([dt])[0], out
+
+
+# ------------------------------------------------------------------------------------------
+def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False):
+    """C2 / C3: the likelihood of ONE data set sharded over the ranks, on DFT kernel `dft`."""
+    from pdspy_b200 import DeviceBuffer, PinnedArray, dist as pdist
+    from pdspy_b200.device import Dataset
+    from pdspy_b200.dist import ShardedLikelihood
+    from pdspy_b200.interferometry import Visibilities
+    _lib, L, rank, world = env._lib, env.L, env.rank, env.world
+    n, nf, nuv = cfg["npix"], cfg["nf"], cfg["nuv"]
+    u, v = synth.synth_uv(nuv, cfg["pixelsize"] * A)
+    rows, re, im, w = synth.synth_data_shard(nuv, nf, rank, world)
+    assert np.array_equal(rows, pdist.shard_rows(u, v, rank, world))
+    freq = synth.synth_freq(nf)
+    shard = Visibilities(np.ascontiguousarray(u[rows]), np.ascontiguousarray(v[rows]), freq, re, im, w)
+    like = ShardedLikelihood(shard)
+    del re, im, w, shard
+    cube = np.ascontiguousarray(synth.synth_image(n, nf, cfg["pixelsize"])[:, :, :, 0])     # [n, n, nf] fp64
+    dxy, dra, ddec = cfg["pixelsize"] * A, cfg["dRA"] * A, cfg["dDec"] * A
+    dcube = DeviceBuffer.from_numpy(cube)
+    pinned = PinnedArray(cube.shape)
+    pinned.array[...] = cube
+    pairs_step = float(n) * n * nuv * nf
+    shard_upload = world > 1 and n % world == 0
+
+    def step_device():
+        return like(dcube, dxy, dra, ddec, kind=_lib.DEVICE, shape=(n, n))
+
+    # end to end: on several GPUs every rank uploads its 1/world slab of the host cube and the slabs are
+    # all-gathered over NVLink (ShardedLikelihood.stage_cube); on one GPU the cube is uploaded whole
+    def step_e2e():
+        return like(pinned.array, dxy, dra, ddec, kind=_lib.HOST, cube="sharded" if shard_upload else None)
+
+    _lib.check(L.pdsb_set_dft_variant(DFT_VARIANT[dft]))
+    prefix = b"dft_tc5" if dft == "tcgen05" else b"dft_f2"
+    total_ms, k_ms, k_n, launches, clocks, ll = timed_device_steps(env, step_device, steps, warmup, prefix,
+                                                                   sample_clocks=main)
+    e2e_s, ll_e2e = timed_host_steps(env, step_e2e, steps)
+    # parity of the timed step itself: the same sharded likelihood on the all-fp64 kernel (1e-11 from the CPU oracle)
+    _lib.check(L.pdsb_set_dft_variant(300))
+    ll_f64 = step_device()
+    _lib.check(L.pdsb_set_dft_variant(DFT_VARIANT[dft]))
+    # ... and the sharded sum against the SAME data set evaluated unsharded on rank 0's GPU
+    ll_single = None
+    if world > 1 and rank == 0:
+        _, fre, fim, fw = synth.synth_data_shard(nuv, nf, 0, 1)
+        full = Dataset(u, v)
+        full.set_data(fre, fim, fw)
+        del fre, fim, fw
+        out = ctypes.c_double()
+        _lib.check(L.pdsb_loglike(full.handle, _lib.ptr(dcube), n, n, nf, _lib.DEVICE, float(dxy), float(dra), float(ddec),
+                                  None, ctypes.cast(ctypes.byref(out), ctypes.c_void_p)))
+        ll_single = out.value
+        full.destroy()
+    env.barrier()
+    _lib.check(L.pdsb_set_dft_variant(0))
+    res = None
+    if rank == 0:
+        pk = peaks()
+        hermitian = like.ds.hermitian
+        pairs_launch = float(n) * n * nf * like.ds.nuv                    # this rank's share, per launch
+        h2d = int(cube.nbytes) if shard_upload or world == 1 else int(cube.nbytes) * world
+        res = {"dft_kernel": dft, "ms_per_step": total_ms / steps, "value": pairs_step * steps / (total_ms * 1e-3),
+               "unit": UNIT, "likelihood_evals_per_s": steps / (total_ms * 1e-3), "steps": steps,
+               "lnlike": ll, "lnlike_rel_diff_vs_fp64_kernel": abs(ll - ll_f64) / abs(ll_f64),
+               "lnlike_rel_diff_vs_single_rank": (abs(ll - ll_single) / abs(ll_single)) if ll_single is not None else None,
+               "lnlike_rel_diff_e2e_vs_device": abs(ll_e2e - ll) / abs(ll),
+               "e2e": {"value": pairs_step * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": int((nf + 1) * 8) * world,
+                       "h2d_bytes_per_step_per_rank": int(cube.nbytes) // world if shard_upload else int(cube.nbytes),
+                       "ms_per_step": e2e_s / steps * 1e3, "likelihood_evals_per_s": steps / e2e_s,
+                       "api": "pdspy_b200.dist.ShardedLikelihood.__call__ (host fp64 cube in, host scalar out" +
+                              ("; each rank uploads 1/N of the cube, NCCL all-gather over NVLink)" if shard_upload else ")"),
+                       "timer": "host wall clock around K synchronous calls, max over ranks"},
+               "gpu_launches": launches, "clocks": clocks}
+        if k_ms:
+            if dft == "fp32":
+                sm, khz = ctypes.c_int(), ctypes.c_int()
+                L.pdsb_device_info(ctypes.byref(sm), ctypes.byref(khz), None, None, None)
+                sm_max_mhz = pk.get("sm_max_mhz") or khz.value / 1e3
+                fp32_peak = sm.value * 128 * 2 * sm_max_mhz * 1e6 / 1e12          # TFLOP/s, non-tensor FMA pipe
+                achieved = pairs_launch * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12
+                executed = pairs_launch * (0.5 if hermitian else 1.0) * 2.0 / (k_ms * 1e-3) / 1e12
+                tf, ms = ctypes.c_double(), ctypes.c_double()
+                _lib.check(L.pdsb_bench_fma(1, 20000, ctypes.byref(tf), ctypes.byref(ms)))
+                res["roofline"] = {
+                    "kernel": "dft_kernel (direct Fourier sampling, FP32 FMA pipe; no tensor cores)",
+                    "bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp32_peak,
+                    "peak_source": "nominal non-tensor FP32: SMs x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has "
+                                   "no FP32 entry; its sm_max_mhz is used)",
+                    "peak_measured_fma_microbench": tf.value, "algorithmic_flop_per_pair": FLOP_PER_PAIR,
+                    "executed": executed, "executed_frac": executed / fp32_peak,
+                    "executed_note": "FMA-pipe flops the inner loop actually issues per launch: the real-image mirror "
+                                     "fold needs 1 FMA per pixel per uv point instead of 2, and a Hermitian-doubled uv "
+                                     "list is evaluated for one half; frac > 1 is those two algorithmic savings, "
+                                     "executed_frac is the pipe utilisation",
+                    "launch_ms": k_ms, "launches": k_n}
+            else:
+                # 3 fp16 MACs (hi.lo, lo.hi, hi.hi) per pixel-visibility pair actually evaluated
+                macs = 3.0 * float(n) * n * nf * like.ds.nuv_unique
+                ach = 2.0 * macs / (k_ms * 1e-3) / 1e12
+                peak = pk.get("bf16_tflops_sustained") or pk.get("bf16_tflops")
+                res["roofline"] = {
+                    "kernel": "dft_tc5_kernel (tcgen05.mma kind::f16, accumulators and A operand in TMEM, B through a "
+                              "bulk-TMA ring)",
+                    "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 GEMM back to back: the kernel is "
+                                   "timed inside a long step)",
+                    "counts": "2 flop x 3 split-product MACs per evaluated pixel-visibility pair (mirror-folded image, "
+                              "Hermitian half of the uv list), per rank",
+                    "algorithmic_flops_over_peak": (pairs_launch * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12 / peak) if peak else None,
+                    "launch_ms": k_ms, "launches": k_n}
+            res["roofline"]["traffic"] = ncu_traffic("%s:%s:%d" % (cfg["name"], dft, world))
+            res["roofline"]["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
+                                                 "capture of this launch, read from profiles/traffic.json; null where "
+                                                 "that (workload, kernel, N) was not captured")
+            res["roofline"]["algorithmic_bytes"] = float(n) * n * nf * 4 + like.ds.nuv_unique * 16.0 * (1 + nf)
+        if cpu_baseline:
+            res["cpu_baseline"] = cpu_baseline_port(cfg)
+    if main:
+        return res, (like, dcube, pinned, cube, (dxy, dra, ddec))
+    like.ds.destroy()
+    dcube.free()
+    pinned.free()
+    return res, None
+
+
+def galario_fft_leg(env, cfg, steps, handles):
+    """extra: the reference's own algorithm (galario: FFT + bilinear interpolation) on the GPU, this rank's shard."""
+    like, dcube, pinned, cube, (dxy, dra, ddec) = handles
+    _lib, L = env._lib, env.L
+    n, nf = cfg["npix"], cfg["nf"]
+    fft_out = np.empty(4)
+
+    def step(image, kind):
+        _lib.check(L.pdsb_loglike_fft(like.ds.handle, _lib.ptr(image), n, nf, kind, float(dxy), float(dra), float(ddec),
+                                      _lib.ptr(fft_out)))
+        return float(fft_out[3])
+    ms, _, _, _, _, _ = timed_device_steps(env, lambda: step(dcube, _lib.DEVICE), steps, 2)
+    e2e_s, _ = timed_host_steps(env, lambda: step(pinned.array, _lib.HOST), steps)
+    if env.rank != 0:
+        return None
+    pairs_step = float(n) * n * cfg["nuv"] * nf
+    return {"what": "the reference's OWN algorithm for this step on the GPU - galario's FFT + bilinear interpolation "
+                    "(pdsb_loglike_fft, fp64, restated from galario's published algorithm) + the same chi^2; it "
+                    "carries galario's interpolation error (1e-3..4e-2 of max|V|), which the direct transform of "
+                    "value / e2e does not; pairs/s counts the pairs the result represents, as in --impl reference; "
+                    "NOT used for value / e2e; chi^2 of this rank's uv shard, no all-reduce",
+            "ms_per_step": ms / steps, "value": pairs_step * steps / (ms * 1e-3), "unit": UNIT,
+            "e2e": {"value": pairs_step * steps / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / steps * 1e3,
+                    "h2d_bytes_per_step": int(cube.nbytes) * env.world, "d2h_bytes_per_step": 32 * env.world},
+            "lnlike_shard": float(fft_out[3])}
+
+
+# ------------------------------------------------------------------------------------------
+def gridding_config(cfg):
+    return {"workload": WORKLOAD_NAMES["C4"] + ", fast (sorted-tile) mode", "nvis": cfg["nuv"], "gridsize": cfg["npix"],
+            "partition": "visibilities sharded over the ranks, private raw-sum maps, all-reduce of 3 x G^2 doubles, "
+                         "normalise (pdspy_b200.dist.sharded_grid)",
+            "cache": "L2 flushed (256 MB memset) before every timed step"}
+
+
+def gridding_leg(env, cfg, steps, warmup, cpu_baseline=False, sample_clocks=False):
     """BASELINE.json configs[3]: grid() of 10M visibilities onto 2048^2 with the exp*sinc convolution
     kernel and weights (fast mode).  Metric: visibilities/s; roofline: HBM on the algorithmic bytes
-    (40 B per visibility + 24 B per cell)."""
-    if rank != 0:
-        return                                        # the path is not sharded: one GPU (DESIGN.md section 5)
-    from pdspy_b200 import _lib, DeviceBuffer
+    (40 B per visibility + 24 B per cell).  world > 1: the visibilities are sharded,
+    every rank grids its shard into private raw-sum maps, NCCL all-reduce, normalise."""
+    from pdspy_b200 import DeviceBuffer, dist as pdist
     from pdspy_b200.interferometry import grid as grid_py, Visibilities
     from oracle import grid as og
-    L = _lib.lib()
+    torch, dist, _lib, L, rank, world = env.torch, env.dist, env._lib, env.L, env.rank, env.world
     nvis, G = cfg["nuv"], cfg["npix"]
     u, v = synth.synth_uv(nvis, cfg["pixelsize"] * A)
-    re, im, w = synth.synth_data(nvis, 1)
-    freq = synth.synth_freq(1)
     binsize = 2.2 * np.hypot(u, v).max() / G
+    rows, re, im, w = synth.synth_data_shard(nvis, 1, rank, world, seed=777)
+    us, vs = np.ascontiguousarray(u[rows]), np.ascontiguousarray(v[rows])
+    freq = synth.synth_freq(1)
     uu, vv = og.cell_centres(G, binsize)               # numpy.linspace of libinterferometry.pyx:370-381
-    d = {k: DeviceBuffer.from_numpy(a) for k, a in dict(u=u, v=v, freq=freq, re=re, im=im, w=w, uu=uu, vv=vv).items()}
-    o_re, o_im, o_w = (DeviceBuffer(G * G * 8) for _ in range(3))
-    flush = DeviceBuffer(L2_FLUSH_BYTES)
-    nout = ctypes.c_int64()
+    d = {k: DeviceBuffer.from_numpy(a) for k, a in dict(u=us, v=vs, freq=freq, re=re, im=im, w=w, uu=uu, vv=vv).items()}
+    maps = torch.zeros((3, G * G, 1), dtype=torch.float64, device="cuda")
+    nloc = us.size
 
     def step():
         _lib.check(L.pdsb_grid(_lib.ptr(d["u"]), _lib.ptr(d["v"]), _lib.ptr(d["freq"]), _lib.ptr(d["re"]), _lib.ptr(d["im"]),
-                               _lib.ptr(d["w"]), nvis, 1, _lib.DEVICE, G, float(binsize), _lib.ptr(d["uu"]), _lib.ptr(d["vv"]),
-                               _lib.CONV["expsinc"], _lib.WEIGHTING["natural"], 2.0, 0, 0, 0, 0,
-                               _lib.ptr(o_re), _lib.ptr(o_im), _lib.ptr(o_w), None, None, None, _lib.DEVICE, None))
+                               _lib.ptr(d["w"]), nloc, 1, _lib.DEVICE, G, float(binsize), _lib.ptr(d["uu"]), _lib.ptr(d["vv"]),
+                               _lib.CONV["expsinc"], _lib.WEIGHTING["natural"], 2.0, 0, 0, 2 if world > 1 else 0, 0,
+                               maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), None, None, None, _lib.DEVICE, None))
+        if world > 1:
+            dist.all_reduce(maps, op=dist.ReduceOp.SUM)
+            _lib.check(L.pdsb_grid_normalise(maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), G, 1, 0))
+        return None
 
-    for _ in range(args.warmup):
-        step()
-    _lib.check(L.pdsb_profile_reset())
-    _lib.check(L.pdsb_profile_enable(1))
-    sampler = ClockSampler(0)
-    sampler.start()
-    n0 = ctypes.c_int64()
-    L.pdsb_launch_count(ctypes.byref(n0))
-    total_ms = 0.0
-    for _ in range(args.steps):
-        _lib.check(L.pdsb_memset(_lib.ptr(flush), 0, L2_FLUSH_BYTES))
-        _lib.check(L.pdsb_timer_start())
-        step()
-        ms = ctypes.c_double()
-        _lib.check(L.pdsb_timer_stop(ctypes.byref(ms)))
-        total_ms += ms.value
-    n1 = ctypes.c_int64()
-    L.pdsb_launch_count(ctypes.byref(n1))
-    _lib.check(L.pdsb_profile_enable(0))
-    clocks = sampler.stop()
-    tile_ms, tile_n = ctypes.c_double(), ctypes.c_int64()
-    _lib.check(L.pdsb_profile_get(b"grid_tile_accum", ctypes.byref(tile_ms), ctypes.byref(tile_n)))
+    total_ms, k_ms, k_n, launches, clocks, _ = timed_device_steps(env, step, steps, warmup, b"grid_tile",
+                                                                  sample_clocks=sample_clocks)
+    wsum = float(maps[2].sum().item())
     # end to end through the Python mirror: host numpy arrays in, gridded Visibilities out
-    data = Visibilities(u, v, freq, re, im, w)
-    grid_py(data, gridsize=G, binsize=binsize, convolution="expsinc", deterministic=False)
-    t0 = time.perf_counter()
-    for _ in range(max(1, args.steps // 2)):
-        grid_py(data, gridsize=G, binsize=binsize, convolution="expsinc", deterministic=False)
-    e2e_s = (time.perf_counter() - t0) / max(1, args.steps // 2)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    alg_bytes = nvis * 40.0 + G * G * 24.0
-    step_ms = total_ms / args.steps
-    line = {"metric": "gridded_visibilities_per_s", "value": nvis / (step_ms * 1e-3), "unit": "vis/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "replicas only (not sharded)", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "grid() of 10M visibilities onto 2048x2048, exp*sinc convolution kernel, natural "
-                                   "weights, fast (sorted-tile) mode (BASELINE.json configs[3])",
-                       "nvis": nvis, "gridsize": G, "cache": "L2 flushed (256 MB memset) before every timed step"},
-            "e2e": {"value": nvis / e2e_s, "unit": "vis/s", "ms_per_step": e2e_s * 1e3,
-                    "h2d_bytes_per_step": int(nvis * 40 + 2 * G * 8), "d2h_bytes_per_step": int(3 * G * G * 8),
-                    "api": "pdspy_b200.interferometry.grid(data, ..., deterministic=False) (numpy in, Visibilities out)"},
-            "gpu_launches": int(n1.value - n0.value), "clocks": clocks,
-            "roofline": {"kernel": "whole grid() step (prep + tile sort + grid_tile2_kernel + normalise)", "bound": "hbm",
-                         "achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / hbm,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                         "algorithmic_bytes": alg_bytes, "tile_kernel_ms": tile_ms.value / max(tile_n.value, 1),
-                         "traffic": None,
-                         "note": "36 fp64 read-modify-writes per visibility make on-chip accumulation, not HBM, the "
-                                 "limiter (SURVEY.md section 8d caveat)"}}
-    if not args.no_cpu_baseline:
-        from oracle import build_ref
-        ref = build_ref.load()
-        ns = 500_000
-        if ref is not None:
-            dd = ref.Visibilities(u[:ns].copy(), v[:ns].copy(), freq, re[:ns].copy(), im[:ns].copy(), w[:ns].copy())
-            t0 = time.perf_counter()
-            ref.grid(dd, gridsize=G, binsize=binsize, convolution="expsinc")
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": ns / dt, "unit": "vis/s", "cores": 1, "kind": "reference", "seconds": dt,
-                                    "sample": "first %d of %d visibilities, the reference's own compiled grid() "
-                                              "(oracle/_ref), serial by construction" % (ns, nvis)}
-    emit(line)
+    shard = Visibilities(us, vs, freq, re, im, w)
+
+    def step_e2e():
+        with contextlib.redirect_stdout(io.StringIO()):
+            if world > 1:
+                return pdist.sharded_grid(shard, gridsize=G, binsize=binsize, convolution="expsinc")
+            return grid_py(shard, gridsize=G, binsize=binsize, convolution="expsinc", deterministic=False)
+    ne2e = max(1, steps // 2)
+    e2e_s, g = timed_host_steps(env, step_e2e, ne2e, warmup=1)
+    e2e_s /= ne2e
+    res = None
+    if rank == 0:
+        hbm = peaks().get("hbm_gbs", 6650.0)
+        alg_bytes = nvis * 40.0 + G * G * 24.0
+        step_ms = total_ms / steps
+        res = {"metric": "gridded_visibilities_per_s", "value": nvis / (step_ms * 1e-3), "unit": "vis/s",
+               "ms_per_step": step_ms, "steps": steps, "dtype": "f64",
+               "config": gridding_config(cfg),
+               "e2e": {"value": nvis / e2e_s, "unit": "vis/s", "ms_per_step": e2e_s * 1e3,
+                       "h2d_bytes_per_step": int(nvis * 40 + 2 * G * 8), "d2h_bytes_per_step": int(3 * G * G * 8) * world,
+                       "api": "pdspy_b200.dist.sharded_grid(shard, ...)" if world > 1 else
+                              "pdspy_b200.interferometry.grid(data, ..., deterministic=False) (numpy in, Visibilities out)"},
+               "gpu_launches": launches, "clocks": clocks, "weight_sum": wsum,
+               "weight_sum_e2e_rel_diff": abs(float(g.weights.sum()) - wsum) / abs(wsum),
+               "roofline": {"kernel": "whole grid() step (prep + tile sort + tile kernel + normalise" +
+                                      (" + NCCL all-reduce of the maps)" if world > 1 else ")"),
+                            "bound": "hbm", "achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                            "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / hbm,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+                            "algorithmic_bytes": alg_bytes,
+                            "algorithmic_bytes_note": "40 B per visibility + 24 B per cell (SURVEY.md 8d), whole job",
+                            "tile_kernel_ms": k_ms,
+                            "traffic": ncu_traffic("C4:grid:%d" % world),
+                            "traffic_source": "sum of dram__bytes_read + dram__bytes_write over the step's launches in one "
+                                              "`ncu --set full` capture (profiles/traffic.json); null where not captured",
+                            "note": "36 fp64 read-modify-writes per visibility make on-chip accumulation, not HBM, the "
+                                    "limiter (SURVEY.md section 8d caveat)"}}
+        if cpu_baseline:
+            from oracle import build_ref
+            ref = build_ref.load()
+            ns = 500_000
+            if ref is not None:
+                cu, cv = np.ascontiguousarray(u[:ns]), np.ascontiguousarray(v[:ns])
+                cre, cim, cw = synth.synth_data(ns, 1)
+                dd = ref.Visibilities(cu, cv, freq, cre, cim, cw)
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    ref.grid(dd, gridsize=G, binsize=binsize, convolution="expsinc")
+                dt = time.perf_counter() - t0
+                res["cpu_baseline"] = {"value": ns / dt, "unit": "vis/s", "cores": 1, "kind": "reference", "seconds": dt,
+                                       "sample": "first %d of %d visibilities, the reference's own compiled grid() "
+                                                 "(oracle/_ref), serial by construction" % (ns, nvis)}
+    for b in d.values():
+        b.free()
+    del maps
+    return res
 
 
-def run_walker_batch(args, cfg, rank, local_rank, world):
-    """BASELINE.json configs[4]: W walkers' cubes against ONE dataset; walkers are split over the ranks,
-    every rank holds the whole dataset, no collective on the data path (one gather of W doubles)."""
-    import torch
-    import torch.distributed as dist
-    from pdspy_b200 import _lib, DeviceBuffer, PinnedArray, dist as pdist
+# ------------------------------------------------------------------------------------------
+def walker_config(cfg, walkers):
+    cfgd = describe(cfg)
+    cfgd.update({"workload": WORKLOAD_NAMES["C5"], "walkers": walkers,
+                 "partition": "walkers split over the ranks, data set replicated, no data-path collective",
+                 "cache": "each cube (134 MB fp64) exceeds the L2"})
+    return cfgd
+
+
+def walker_leg(env, cfg, walkers, dft, steps):
+    """BASELINE.json configs[4]: W walkers' cubes against ONE data set; walkers are split over the ranks,
+    every rank holds the whole data set, no collective on the data path (one gather of W doubles)."""
+    from pdspy_b200 import DeviceBuffer, PinnedArray, dist as pdist
     from pdspy_b200.device import Dataset
-    L = _lib.lib()
-    _lib.check(L.pdsb_set_stream(torch.cuda.current_stream().cuda_stream))
+    torch, _lib, L, rank, world = env.torch, env._lib, env.L, env.rank, env.world
     n, nf = cfg["npix"], cfg["nf"]
     u, v = synth.synth_uv(cfg["nuv"], cfg["pixelsize"] * A)
-    re, im, w = synth.synth_data(cfg["nuv"], nf)
+    _, re, im, w = synth.synth_data_shard(cfg["nuv"], nf, 0, 1)
     ds = Dataset(u, v)
     ds.set_data(re, im, w)
     del re, im, w
-    ws, we = pdist.shard_walkers(args.walkers, rank, world)
+    ws, we = pdist.shard_walkers(walkers, rank, world)
     nw = we - ws
     base = np.ascontiguousarray(synth.synth_image(n, nf, cfg["pixelsize"])[:, :, :, 0])
     pinned = PinnedArray((max(nw, 1), n, n, nf))
@@ -361,76 +627,53 @@ def run_walker_batch(args, cfg, rank, local_rank, world):
     dxy = cfg["pixelsize"] * A
     dra = np.ascontiguousarray(np.full(max(nw, 1), cfg["dRA"] * A))
     ddec = np.ascontiguousarray(np.full(max(nw, 1), cfg["dDec"] * A))
-    out = np.empty(max(nw, 1))
+    out = np.zeros(max(nw, 1))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step(cubes, kind):
-        if nw > 0:
-            _lib.check(L.pdsb_loglike_batch(ds.handle, _lib.ptr(cubes), nw, n, n, nf, kind, float(dxy), _lib.ptr(dra),
+    def step(cubes, kind, count=None):
+        cnt = nw if count is None else min(count, nw)
+        if cnt > 0:
+            _lib.check(L.pdsb_loglike_batch(ds.handle, _lib.ptr(cubes), cnt, n, n, nf, kind, float(dxy), _lib.ptr(dra),
                                             _lib.ptr(ddec), _lib.ptr(out)))
+        return float(out[0])
 
-    step(dcubes, _lib.DEVICE)                       # warm-up: one full batch
-    barrier()
-    n0 = ctypes.c_int64()
-    L.pdsb_launch_count(ctypes.byref(n0))
+    _lib.check(L.pdsb_set_dft_variant(DFT_VARIANT[dft]))
+    step(dcubes, _lib.DEVICE, 1)                    # warm-up: one walker
+    env.barrier()
+    n0 = env.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        step(dcubes, _lib.DEVICE)
+    for _ in range(steps):
+        lnlike0 = step(dcubes, _lib.DEVICE)
     e1.record()
-    barrier()
-    n1 = ctypes.c_int64()
-    L.pdsb_launch_count(ctypes.byref(n1))
+    env.barrier()
+    n1 = env.launches()
     dev_ms = e0.elapsed_time(e1)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(pinned.array, _lib.HOST)
-    barrier()
+    env.barrier()
     e2e_s = time.perf_counter() - t0
-    # extra (not in value / e2e): the same batch on the opt-in tcgen05 tensor-core kernel
-    lnlike0 = float(out[0])
-    _lib.check(L.pdsb_set_dft_variant(200))
-    step(dcubes, _lib.DEVICE)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step(dcubes, _lib.DEVICE)
-    e1.record()
-    barrier()
-    tc_ms = e0.elapsed_time(e1)
-    lnlike0_tc = float(out[0])
+    # the first walker of rank 0 once more on the all-fp64 kernel
+    _lib.check(L.pdsb_set_dft_variant(300))
+    ll_f64 = step(dcubes, _lib.DEVICE, 1)
     _lib.check(L.pdsb_set_dft_variant(0))
-    t = torch.tensor([dev_ms, e2e_s, tc_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, tc_ms = float(t[0]), float(t[1]), float(t[2])
+    dev_ms, e2e_s = env.max_over_ranks([dev_ms, e2e_s])
+    res = None
     if rank == 0:
-        pairs = float(n) * n * cfg["nuv"] * nf * args.walkers * args.steps
-        cfgd = describe(cfg, world)
-        cfgd.update({"walkers": args.walkers, "walkers_per_rank": nw,
-                     "partition": "%d walkers split over %d rank(s), dataset replicated, no data-path collective"
-                                  % (args.walkers, world), "cache": "each cube (134 MB fp64) exceeds the L2"})
-        emit({
-            "metric": METRIC, "value": pairs / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": 1, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 products, f64 phase seeds and accumulation", "data": "synthetic",
-            "config": cfgd, "likelihood_evals_per_s": args.walkers * args.steps / (dev_ms * 1e-3),
-            "e2e": {"value": pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nw * base.nbytes),
-                    "d2h_bytes_per_step": int(nw * nf * 8), "ms_per_step": e2e_s / args.steps * 1e3,
-                    "likelihood_evals_per_s": args.walkers * args.steps / e2e_s,
-                    "api": "pdsb_loglike_batch (host fp64 cubes in, host lnlike[W] out)"},
-            "gpu_launches": int(n1.value - n0.value), "lnlike0": lnlike0,
-            "extras": {"tensor_core_variant": {
-                "what": "same batch with the experimental opt-in tcgen05 DFT kernel (pdsb_set_dft_variant(200)); "
-                        "NOT used for value / e2e",
-                "ms_per_step": tc_ms / args.steps, "value": pairs / (tc_ms * 1e-3), "unit": UNIT,
-                "likelihood_evals_per_s": args.walkers * args.steps / (tc_ms * 1e-3),
-                "speedup_vs_default": dev_ms / tc_ms, "lnlike0": lnlike0_tc,
-                "lnlike0_rel_diff_vs_default": abs(lnlike0_tc - lnlike0) / abs(lnlike0)}}})
+        pairs = float(n) * n * cfg["nuv"] * nf * walkers * steps
+        res = {"metric": METRIC, "dft_kernel": dft, "value": pairs / (dev_ms * 1e-3), "unit": UNIT, "steps": steps,
+               "ms_per_step": dev_ms / steps, "dtype": DTYPE[dft], "config": walker_config(cfg, walkers),
+               "walkers_per_rank": nw, "likelihood_evals_per_s": walkers * steps / (dev_ms * 1e-3),
+               "e2e": {"value": pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nw * base.nbytes) * world,
+                       "d2h_bytes_per_step": int(nw * 8) * world, "ms_per_step": e2e_s / steps * 1e3,
+                       "likelihood_evals_per_s": walkers * steps / e2e_s,
+                       "api": "pdsb_loglike_batch (host fp64 cubes in, host lnlike[W] out)"},
+               "gpu_launches": n1 - n0, "lnlike0": lnlike0,
+               "lnlike0_rel_diff_vs_fp64_kernel": abs(lnlike0 - ll_f64) / abs(ll_f64)}
+    ds.destroy()
+    dcubes.free()
+    pinned.free()
+    return res
 
 
 # ------------------------------------------------------------------------------------------
@@ -460,9 +703,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--dft", default="fp32", choices=["fp32", "tcgen05"],
+                    help="DFT kernel of value / e2e / roofline: the FP32-pipe kernel BASELINE.json's north star "
+                         "prescribes (default) or the tcgen05 tensor-core kernel")
     ap.add_argument("--walkers", type=int, default=128, help="C5: total emcee walkers (sharded over ranks)")
     ap.add_argument("--nuv", type=int, default=0, help="override the uv count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no extras.workloads)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -474,10 +721,6 @@ def main():
     if args.impl == "reference":
         run_reference(args, cfg, rank, world)
         return
-    if args.workload == "C4":
-        os.environ["PDSB_DEVICE"] = str(local_rank)
-        run_gridding(args, cfg, rank, world)
-        return
 
     import torch
     import torch.distributed as dist
@@ -486,256 +729,74 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = Env(rank, local_rank, world)
+    cpu_base = world == 1 and not args.no_cpu_baseline
+    common = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+              "vs_baseline": None, "data": "synthetic"}
+    line = None
 
-    from pdspy_b200 import _lib, DeviceBuffer, PinnedArray
-    from pdspy_b200.dist import ShardedLikelihood
-    L = _lib.lib()
-    if args.workload == "C5":
-        run_walker_batch(args, cfg, rank, local_rank, world)
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    data, _ = make_local_data(cfg, rank, world)
-    like = ShardedLikelihood(data)            # uploads the shard; libpdsb now runs on torch's stream
-    n, nf = cfg["npix"], cfg["nf"]
-    cube = np.ascontiguousarray(synth.synth_image(n, nf, cfg["pixelsize"])[:, :, :, 0])     # [n, n, nf] fp64
-    dxy, dra, ddec = cfg["pixelsize"] * A, cfg["dRA"] * A, cfg["dDec"] * A
-    dcube = DeviceBuffer.from_numpy(cube)
-    pinned = PinnedArray(cube.shape)
-    pinned.array[...] = cube
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-    pairs_step = float(n) * n * cfg["nuv"] * nf
-
-    def step_device():
-        return like(dcube, dxy, dra, ddec, kind=_lib.DEVICE, shape=(n, n))
-
-    # end to end: on several GPUs every rank uploads its 1/world slab of the host cube and the slabs are
-    # all-gathered over NVLink (ShardedLikelihood.stage_cube); on one GPU the cube is uploaded whole
-    shard_upload = world > 1 and n % world == 0
-
-    def step_e2e():
-        return like(pinned.array, dxy, dra, ddec, kind=_lib.HOST, cube="sharded" if shard_upload else None)
-
-    # ---- device-resident leg: `value` ----
-    for _ in range(args.warmup):
-        flush.zero_()
-        ll = step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
+    if args.workload == "C4":
+        res = gridding_leg(env, cfg, args.steps, args.warmup, cpu_baseline=cpu_base, sample_clocks=True)
+        if rank == 0:
+            line = dict(res, **common, scaling="strong")
+    elif args.workload == "C5":
+        res = walker_leg(env, cfg, args.walkers, args.dft, max(1, min(args.steps, 2)))
+        if rank == 0:
+            line = dict(res, **common, scaling="strong")
+            line["steps"], line["warmup"] = res["steps"], 1
+    else:
+        res, keep = likelihood_leg(env, cfg, args.dft, args.steps, args.warmup, main=True, cpu_baseline=cpu_base)
+        if rank == 0:
+            line = {"metric": METRIC, "value": res.pop("value"), "unit": res.pop("unit"), **common,
+                    "ms_per_step": res.pop("ms_per_step"), "scaling": "strong", "dtype": DTYPE[args.dft],
+                    "config": describe(cfg)}
+            res.pop("steps")
+            line.update(res)
+        extras = {"note": "context for the headline: NOT part of value / e2e",
+                  "reference_arm_caveat": "`--impl reference` times a numpy restatement of galario's algorithm (galario is "
+                                          "not installable offline); galario's C++/OpenMP library would be several times "
+                                          "faster, so ratios against that arm are upper bounds"}
+        ksteps = max(3, min(args.steps, 5))
+        if not args.no_extras:
+            ff = galario_fft_leg(env, cfg, ksteps, keep)
+            if rank == 0:
+                ff["lnlike_gap_note"] = ("the direct transform (value / e2e) and galario's FFT + bilinear interpolation differ "
+                                         "by galario's interpolation error: at N=1 compare lnlike_shard with the headline lnlike")
+                extras["galario_fft_algorithm"] = ff
+        keep[0].ds.destroy()
+        keep[1].free()
+        keep[2].free()
+        keep = None
+        if not args.no_extras:
+            other = "tcgen05" if args.dft == "fp32" else "fp32"
+            r2, _ = likelihood_leg(env, cfg, other, ksteps, 3)
+            if rank == 0:
+                r2["what"] = ("the same step on the %s DFT kernel (`bench.py --dft %s` makes it the headline); NOT used for "
+                              "value / e2e" % (other, other))
+                r2["speedup_vs_headline_kernel"] = line["ms_per_step"] / r2["ms_per_step"]
+                extras["tensor_core_variant" if other == "tcgen05" else "fp32_pipe_variant"] = r2
+            workloads = {}
+            if args.workload == "C3":
+                c2 = workload_config("C2")
+                for k in (args.dft, other):
+                    r, _ = likelihood_leg(env, c2, k, ksteps, 3)
+                    if rank == 0:
+                        r["config"] = describe(c2)
+                        workloads["C2" if k == args.dft else "C2_" + k] = r
+            g = gridding_leg(env, workload_config("C4"), ksteps, 3, cpu_baseline=cpu_base)
+            if rank == 0:
+                workloads["C4"] = g
+            c5 = workload_config("C5")
+            for k in (args.dft, other):
+                r = walker_leg(env, c5, 16 * world, k, 1)
+                if rank == 0:
+                    r["note"] = ("16 walkers per GPU x %d GPU(s): configs[4]'s per-GPU share (128 walkers on 8 GPUs); "
+                                 "`--workload C5` runs all 128 at any N" % world)
+                    workloads["C5" if k == args.dft else "C5_" + k] = r
+            if rank == 0:
+                extras["workloads"] = workloads
+                line["extras"] = extras
     if rank == 0:
-        sampler.start()
-    _lib.check(L.pdsb_profile_reset())
-    _lib.check(L.pdsb_profile_enable(1))
-    n0 = ctypes.c_int64()
-    L.pdsb_launch_count(ctypes.byref(n0))
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for e0, e1 in evs:
-        flush.zero_()
-        e0.record()
-        ll = step_device()
-        e1.record()
-    barrier()
-    n1 = ctypes.c_int64()
-    L.pdsb_launch_count(ctypes.byref(n1))
-    _lib.check(L.pdsb_profile_enable(0))
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-    dft_ms, dft_n = ctypes.c_double(), ctypes.c_int64()
-    _lib.check(L.pdsb_profile_get(b"dft_", ctypes.byref(dft_ms), ctypes.byref(dft_n)))
-    t = torch.tensor([total_ms, dft_ms.value], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, dft_ms_max = float(t[0]), float(t[1])
-
-    # ---- end-to-end leg: host cube (pinned) -> H2D -> fold/DFT/chi^2 -> all-reduce -> host scalar ----
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ll_e2e = step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t[0])
-
-    # ---- extras (not part of value / e2e): the experimental tensor-core variants on the same step ----
-    # 200: tcgen05.mma with TMEM accumulators and a TMEM A operand, bulk-TMA B ring (pdspy_b200/csrc/dft_tc5.cu);
-    # 103: mma.sync m16n8k16 (pdspy_b200/csrc/dft_mma.cu).  Both: fp16 hi+lo split operands, 3 MMAs per product,
-    # fp32 accumulate; same data flow and outputs, parity <= 1.1e-6 of max|V| (tests/test_gpu_dft.py).  Reported
-    # for context: the default and the headline stay on the FP32 pipe, as BASELINE.json's north star prescribes.
-    def time_variant(variant, prefix):
-        """(device-resident ms, e2e seconds, DFT-kernel ms from in-library events, lnlike) over args.steps steps."""
-        _lib.check(L.pdsb_set_dft_variant(variant))
-        for _ in range(2):
-            ll_v = step_device()
-        barrier()
-        _lib.check(L.pdsb_profile_reset())
-        _lib.check(L.pdsb_profile_enable(1))
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for e0, e1 in evs:
-            flush.zero_()
-            e0.record()
-            ll_v = step_device()
-            e1.record()
-        barrier()
-        _lib.check(L.pdsb_profile_enable(0))
-        k_ms, k_n = ctypes.c_double(), ctypes.c_int64()
-        _lib.check(L.pdsb_profile_get(prefix, ctypes.byref(k_ms), ctypes.byref(k_n)))
-        step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        barrier()
-        e2e = time.perf_counter() - t0
-        _lib.check(L.pdsb_set_dft_variant(0))
-        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-        tt = torch.tensor([ms, e2e, k_ms.value], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt[0]), float(tt[1]), float(tt[2]) / max(1, k_n.value), ll_v
-
-    # ---- extra: the reference's own algorithm (galario: FFT + bilinear interpolation) on the GPU, this rank's shard ----
-    fft_out = np.empty(4)
-
-    def step_fft(image, kind):
-        _lib.check(L.pdsb_loglike_fft(like.ds.handle, _lib.ptr(image), n, nf, kind, float(dxy), float(dra), float(ddec),
-                                      _lib.ptr(fft_out)))
-    for _ in range(2):
-        step_fft(dcube, _lib.DEVICE)
-    barrier()
-    fevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for e0, e1 in fevs:
-        flush.zero_()
-        e0.record()
-        step_fft(dcube, _lib.DEVICE)
-        e1.record()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_fft(pinned.array, _lib.HOST)
-    barrier()
-    fft_e2e_s = time.perf_counter() - t0
-    tt = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in fevs), fft_e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    fft_ms, fft_e2e_s = float(tt[0]), float(tt[1])
-
-    # ---- parity of the timed step itself: the same likelihood on the all-fp64 kernel (dft_f64.cu, 1e-11 from the CPU oracle) ----
-    _lib.check(L.pdsb_set_dft_variant(300))
-    ll_f64 = step_device()
-    _lib.check(L.pdsb_set_dft_variant(0))
-
-    tc5_ms, tc5_e2e_s, tc5_kernel_ms, ll_tc5 = time_variant(200, b"dft_tc5")
-    tc_ms, tc_e2e_s, tc_kernel_ms, ll_tc = time_variant(103, b"dft_mma")
-
-    if rank == 0:
-        sm, khz = ctypes.c_int(), ctypes.c_int()
-        L.pdsb_device_info(ctypes.byref(sm), ctypes.byref(khz), None, None, None)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        sm_max_mhz = peaks.get("sm_max_mhz") or khz.value / 1e3
-        fp32_peak = sm.value * 128 * 2 * sm_max_mhz * 1e6 / 1e12          # TFLOP/s, non-tensor FMA pipe
-        tf, ms = ctypes.c_double(), ctypes.c_double()
-        _lib.check(L.pdsb_bench_fma(1, 20000, ctypes.byref(tf), ctypes.byref(ms)))
-        hermitian = like.ds.hermitian
-        pairs_launch = float(n) * n * nf * like.ds.nuv                    # this rank's share, per launch
-        dft_avg_ms = dft_ms_max / max(dft_n.value, 1)
-        achieved = pairs_launch * FLOP_PER_PAIR / (dft_avg_ms * 1e-3) / 1e12
-        executed_flop = pairs_launch * (0.5 if hermitian else 1.0) * 2.0   # 1 FMA per pixel per unique uv
-        executed = executed_flop / (dft_avg_ms * 1e-3) / 1e12
-        value = pairs_step * args.steps / (total_ms * 1e-3)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 products, f64 phase seeds and accumulation",
-            "data": "synthetic", "config": describe(cfg, world),
-            "likelihood_evals_per_s": args.steps / (total_ms * 1e-3),
-            "lnlike": ll,
-            "lnlike_rel_diff_vs_fp64_kernel": abs(ll - ll_f64) / abs(ll_f64),
-            "e2e": {"value": pairs_step * args.steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": int(cube.nbytes) if shard_upload or world == 1 else int(cube.nbytes) * world,
-                    "d2h_bytes_per_step": int((nf + 1) * 8) * world,
-                    "h2d_bytes_per_step_per_rank": int(cube.nbytes) // world if shard_upload else int(cube.nbytes),
-                    "ms_per_step": e2e_s / args.steps * 1e3, "likelihood_evals_per_s": args.steps / e2e_s,
-                    "api": "pdspy_b200.dist.ShardedLikelihood.__call__ (host fp64 cube in, host scalar out" +
-                           ("; each rank uploads 1/%d of the cube, NCCL all-gather over NVLink)" % world if shard_upload else ")"),
-                    "timer": "host wall clock around K synchronous calls, max over ranks"},
-            "gpu_launches": int(n1.value - n0.value),
-            "clocks": clocks,
-            "roofline": {
-                "kernel": "dft_kernel (direct Fourier sampling, FP32 FMA pipe; no tensor cores)",
-                "bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp32_peak,
-                "peak_source": "nominal non-tensor FP32: SMs x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json has "
-                               "no FP32 entry; its sm_max_mhz is used)",
-                "peak_measured_fma_microbench": tf.value,
-                "algorithmic_flop_per_pair": FLOP_PER_PAIR,
-                "executed": executed, "executed_frac": executed / fp32_peak,
-                "executed_note": "FMA-pipe flops the inner loop actually issues per launch: the real-image mirror "
-                                 "fold needs 1 FMA per pixel per uv point instead of 2, and a Hermitian-doubled uv "
-                                 "list is evaluated for one half; frac > 1 is those two algorithmic savings, "
-                                 "executed_frac is the pipe utilisation",
-                "launch_ms": dft_avg_ms, "launches": int(dft_n.value),
-                "traffic": NCU_TRAFFIC_BYTES.get((cfg["name"], world)),
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this "
-                                  "launch (profiles/r01_dft_ncu_c3_default.md, r01_dft_ncu.md); null where not captured",
-                "algorithmic_bytes": float(n) * n * nf * 4 + like.ds.nuv_unique * 16.0 * (1 + nf)},
-        }
-        def tc_entry(what, ms, e2e_s_, kernel_ms, llv, peak_key):
-            # the tensor cores execute 3 fp16 MACs (hi*hi, hi*lo, lo*hi) per pixel-visibility pair actually
-            # evaluated (the Hermitian half of the list, per rank)
-            macs = 3.0 * float(n) * n * nf * like.ds.nuv_unique
-            ach = 2.0 * macs / (kernel_ms * 1e-3) / 1e12
-            peak = peaks.get(peak_key)
-            return {"what": what + "; NOT used for value / e2e", "ms_per_step": ms / args.steps,
-                    "value": pairs_step * args.steps / (ms * 1e-3), "unit": UNIT, "speedup_vs_default": total_ms / ms,
-                    "e2e": {"value": pairs_step * args.steps / e2e_s_, "unit": UNIT, "ms_per_step": e2e_s_ / args.steps * 1e3,
-                            "h2d_bytes_per_step": int(cube.nbytes) if shard_upload or world == 1 else int(cube.nbytes) * world,
-                            "d2h_bytes_per_step": 8 * (nf + 1) * world},
-                    "roofline": {"bound": "tensor", "kernel_ms": kernel_ms, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                                 "frac": ach / peak if peak else None,
-                                 "peak_source": "MEASURED_PEAKS.json %s (cuBLAS bf16 GEMM, sustained figure: kernel timed "
-                                                "inside a long step)" % peak_key,
-                                 "counts": "2 flop x 3 split-product MACs per evaluated pixel-visibility pair, per rank"},
-                    "lnlike": llv, "lnlike_rel_diff_vs_default": abs(llv - ll) / abs(ll),
-                    "lnlike_rel_diff_vs_fp64_kernel": abs(llv - ll_f64) / abs(ll_f64)}
-        line["extras"] = {
-            "tensor_core_variant": tc_entry(
-                "same step with the experimental opt-in DFT kernel on the 5th-generation tensor cores (tcgen05.mma, "
-                "accumulators and A operand in TMEM, B through a bulk-TMA ring, warp-specialised; fp16 hi+lo split "
-                "operands, 3 MMAs per product, fp32 accumulate; dft_tc5.cu, pdsb_set_dft_variant(200))",
-                tc5_ms, tc5_e2e_s, tc5_kernel_ms, ll_tc5, "bf16_tflops_sustained"),
-            "galario_fft_algorithm": {
-                "what": "the reference's OWN algorithm for this step on the GPU - galario's FFT + bilinear interpolation "
-                        "(pdsb_loglike_fft, fp64, restated from galario's published algorithm) + the same chi^2; it "
-                        "carries galario's interpolation error (1e-3..4e-2 of max|V|), which the direct transform of "
-                        "value / e2e does not; pairs/s counts the pairs the result represents, as in --impl reference; "
-                        "NOT used for value / e2e; chi^2 of this rank's uv shard, no all-reduce",
-                "ms_per_step": fft_ms / args.steps, "value": pairs_step * args.steps / (fft_ms * 1e-3), "unit": UNIT,
-                "e2e": {"value": pairs_step * args.steps / fft_e2e_s, "unit": UNIT, "ms_per_step": fft_e2e_s / args.steps * 1e3,
-                        "h2d_bytes_per_step": int(cube.nbytes) * world, "d2h_bytes_per_step": 32 * world},
-                "lnlike_shard": float(fft_out[3])},
-            "mma_sync_variant": tc_entry(
-                "same step with the experimental opt-in DFT kernel on the warp-level tensor-core path (mma.sync "
-                "m16n8k16, same operand split; dft_mma.cu, pdsb_set_dft_variant(103))",
-                tc_ms, tc_e2e_s, tc_kernel_ms, ll_tc, "bf16_tflops_sustained")}
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_port(cfg)
         emit(line)
     if world > 1:
         dist.barrier()

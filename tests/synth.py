@@ -90,6 +90,49 @@ def synth_data(nuv, nf, seed=4321, model=None):
     return re, im, w
 
 
+_BLOCK = 8192
+
+
+def synth_data_half_rows(nuv, nf, start, stop, seed=4321):
+    """Rows [start, stop) of the FIRST half of a Hermitian-doubled synthetic data set of nuv points, generated
+    block by block from (seed, block) so that any partition of the rows over ranks sees the same values:
+    bench.py shards ONE data set this way.  Returns re, im, w of shape [stop - start, nf] (statistics as
+    synth_data, not the same numbers)."""
+    half = nuv // 2
+    assert 0 <= start <= stop <= half
+    re = np.empty((stop - start, nf))
+    im = np.empty((stop - start, nf))
+    w = np.empty((stop - start, nf))
+    for b in range(start // _BLOCK, (max(stop, 1) - 1) // _BLOCK + 1):
+        lo, hi = b * _BLOCK, min((b + 1) * _BLOCK, half)
+        rng = np.random.default_rng([seed, b])
+        wb = rng.uniform(0.5, 2.0, (hi - lo, nf))
+        wb[rng.random((hi - lo, nf)) < 0.01] = 0.0
+        neg = rng.random((hi - lo, nf)) < 0.001
+        wb[neg] = -wb[neg]
+        sig = 1.0 / np.sqrt(np.where(wb > 0, wb, 1.0))
+        rb = rng.normal(size=(hi - lo, nf)) * sig
+        ib = rng.normal(size=(hi - lo, nf)) * sig
+        a, z = max(lo, start), min(hi, stop)
+        if z > a:
+            re[a - start:z - start] = rb[a - lo:z - lo]
+            im[a - start:z - start] = ib[a - lo:z - lo]
+            w[a - start:z - start] = wb[a - lo:z - lo]
+    return re, im, w
+
+
+def synth_data_shard(nuv, nf, rank, world, seed=4321):
+    """(rows, re, im, w) of rank's shard of the Hermitian-doubled data set (both halves of its baselines, as
+    pdspy_b200.dist.shard_rows cuts them); the union over ranks is the world == 1 data set, bit for bit."""
+    half = nuv // 2
+    base, rem = divmod(half, world)
+    s = rank * base + min(rank, rem)
+    e = s + base + (1 if rank < rem else 0)
+    re, im, w = synth_data_half_rows(nuv, nf, s, e, seed)
+    rows = np.concatenate([np.arange(s, e), np.arange(half + s, half + e)])
+    return rows, np.concatenate([re, re]), np.concatenate([im, -im]), np.concatenate([w, w])
+
+
 class SynthImage:
     """Duck-typed stand-in for pdspy.imaging.Image (imaging/libimaging.pyx:7-48):
     only the attributes the hot path reads (image, x, y, freq)."""
