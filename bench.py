@@ -469,6 +469,51 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
     return res, None
 
 
+def chain_leg(env, cfg, dft, steps):
+    """The reference's own two calls, unchanged signatures, on this rank's shard:
+        m = interpolate_model(u, v, freq, model, dRA=, dDec=)          (interpolate_model.py:11-57)
+        visibility_lnlike(data, m)                                      (the emcee.py:31-43 term of utils.emcee.lnlike)
+    with a pageable host cube, as pdspy holds it.  The model visibilities stay on the device between the two calls
+    (lazy Visibilities); timed under both handle-cache policies (pdspy_b200/device.py)."""
+    import pdspy_b200 as pb
+    from pdspy_b200 import dist as pdist, utils
+    from pdspy_b200.interferometry import interpolate_model, Visibilities
+    _lib, L, rank, world = env._lib, env.L, env.rank, env.world
+    n, nf, nuv = cfg["npix"], cfg["nf"], cfg["nuv"]
+    u, v = synth.synth_uv(nuv, cfg["pixelsize"] * A)
+    rows, re, im, w = synth.synth_data_shard(nuv, nf, rank, world)
+    freq = synth.synth_freq(nf)
+    data = Visibilities(np.ascontiguousarray(u[rows]), np.ascontiguousarray(v[rows]), freq, re, im, w)
+    model = synth.SynthImage(synth.synth_image(n, nf, cfg["pixelsize"]), cfg["pixelsize"], freq)
+    _lib.check(L.pdsb_set_dft_variant(DFT_VARIANT[dft]))
+
+    def step():
+        m = interpolate_model(data.u, data.v, freq, model, dRA=cfg["dRA"], dDec=cfg["dDec"])
+        return utils.visibility_lnlike(data, m)
+    out = {}
+    for policy in ("hash", "freeze"):
+        pb.clear_cache()
+        pb.set_cache_policy(policy)
+        s, ll = timed_host_steps(env, step, steps, warmup=2)
+        out[policy] = (s, ll)
+    pb.set_cache_policy("hash")
+    pb.clear_cache()
+    _lib.check(L.pdsb_set_dft_variant(0))
+    if rank != 0:
+        return None
+    pairs_step = float(n) * n * nuv * nf
+    return {"what": "interpolate_model(u, v, freq, model, dRA=, dDec=) -> utils.visibility_lnlike(data, m): the reference's "
+                    "call signatures (what utils.emcee.lnlike runs), pageable host cube in, scalar out, each rank on its uv "
+                    "shard (no all-reduce); the [nuv, nf] model visibilities never leave the device",
+            "dft_kernel": dft, "lnlike_shard": out["hash"][1],
+            "cache_policy_hash": {"ms_per_step": out["hash"][0] / steps * 1e3, "value": pairs_step * steps / out["hash"][0],
+                                  "unit": UNIT, "note": "default: u, v, real, imag, weights re-hashed on the host every call"},
+            "cache_policy_freeze": {"ms_per_step": out["freeze"][0] / steps * 1e3,
+                                    "value": pairs_step * steps / out["freeze"][0], "unit": UNIT,
+                                    "note": "cached arrays made read-only instead of re-hashed"},
+            "h2d_bytes_per_step": int(model.image.nbytes) * world, "d2h_bytes_per_step": 32 * world}
+
+
 def galario_fft_leg(env, cfg, steps, handles):
     """extra: the reference's own algorithm (galario: FFT + bilinear interpolation) on the GPU, this rank's shard."""
     like, dcube, pinned, cube, (dxy, dra, ddec) = handles
@@ -768,6 +813,10 @@ def main():
         keep[2].free()
         keep = None
         if not args.no_extras:
+            ch = chain_leg(env, cfg, args.dft, ksteps)
+            if rank == 0:
+                ch["e2e_ms_per_step_ShardedLikelihood"] = line["e2e"]["ms_per_step"]
+                extras["dropin_chain"] = ch
             other = "tcgen05" if args.dft == "fp32" else "fp32"
             r2, _ = likelihood_leg(env, cfg, other, ksteps, 3)
             if rank == 0:

@@ -165,6 +165,11 @@ int pdsb_loglike_batch(pdsb_dataset *ds, const double *images, int nwalkers, int
  * out[2]=sum log(w[w>0]/2pi), out[3]=the emcee.py:31-43 value.  out is a host double[4]. */
 int pdsb_chi2(const double *d_real, const double *d_imag, const double *weights,
               const double *m_real, const double *m_imag, int64_t n, int kind, double *out);
+/* The same sums with the data side taken from the dataset handle's device-resident real / imag / weights
+ * (pdsb_dataset_set_data): only the model arrays [nuv*nf] are read from the caller (`kind`).  This is what
+ * utils.emcee.lnlike calls when the model Visibilities still live on the device (interpolate_model's lazy
+ * result): no host round trip between interpolate_model.py:57 and emcee.py:31-43. */
+int pdsb_chi2_dataset(pdsb_dataset *ds, const double *m_real, const double *m_imag, int kind, double *out);
 /* chisq(): channel 0 of [nuv, nf] arrays, result rounded through a C float as the
  * reference's `cdef float chisq_calc` does (libinterferometry.pyx:616). */
 int pdsb_chisq(const double *d_real, const double *d_imag, const double *weights,
@@ -233,6 +238,11 @@ int pdsb_center(const double *u, const double *v, const double *freq, const doub
  * [npts,nf] image), out [npix, nf_in/subsample/averaging]; both host or both device (`kind`). */
 int pdsb_channel_postprocess(const double *image, int64_t npix, int nf_in, int subsample, int hanning,
                              int averaging, int kind, double *out);
+/* The same with a per-INPUT-channel factor in_scale[nf_in] (HOST array, or NULL) applied before the sub-sample
+ * mean: the reference's extinction, image[:,:,i,:] *= extinction[i] (run_flared_model.py:286-299), which comes
+ * before the channel post-processing and does not commute with it. */
+int pdsb_channel_postprocess_scaled(const double *image, int64_t npix, int nf_in, int subsample, int hanning,
+                                    int averaging, const double *in_scale, int kind, double *out);
 
 /* Piecewise-linear regridding of an unstructured image (interpolate_model code="galario-unstructured",
  * pdspy/interferometry/interpolate_model.py:32-47; the scattered images of Model.py:536-558): values
@@ -267,6 +277,11 @@ int pdsb_clean_loop(double *dirty, const double *dirty_beam, int ny, int nx, int
                     double *threshold_out);
 int pdsb_clean_restore(const double *model, const double *clean_beam, const double *residuals, int ny, int nx,
                        int nf, int kind, double *clean_image);
+
+/* 64-bit content hash of a HOST array (multi-threaded, memory-bound; needs no device).  The Python handle
+ * cache compares it before trusting a device copy of caller-owned arrays (the reference mutates arrays in
+ * place, invert.py:15-47). */
+int pdsb_hash64(const void *host_ptr, int64_t bytes, uint64_t *out);
 
 /* ---- tuning / measurement ----------------------------------------------------------- */
 /* DFT kernel: 0 = auto (the FP32-pipe kernel the north star asks for); 1..2 = its two tilings;

@@ -11,7 +11,7 @@ from . import constants
 from . import interferometry
 from . import utils
 from .imaging import Image, UnstructuredImage
-from .device import Dataset, clear_cache, set_dft_kernel
+from .device import Dataset, clear_cache, release, set_cache_policy, set_dft_kernel
 from ._lib import PdsbError, DeviceBuffer, PinnedArray
 
 __version__ = "0.1.0"

@@ -62,6 +62,8 @@ SIGNATURES = {
     "pdsb_dataset_logsum": [_P, ctypes.POINTER(_c_dbl)],
     "pdsb_loglike_batch": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl, _P, _P, _P],
     "pdsb_chi2": [_P, _P, _P, _P, _P, _c_i64, _c_int, _P],
+    "pdsb_chi2_dataset": [_P, _P, _P, _c_int, _P],
+    "pdsb_hash64": [_P, _c_i64, ctypes.POINTER(ctypes.c_uint64)],
     "pdsb_chisq": [_P, _P, _P, _P, _P, _c_i64, _c_int, _c_int, ctypes.POINTER(ctypes.c_float)],
     "pdsb_grid": [_P, _P, _P, _P, _P, _P, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _P, _P, _c_int, _c_int,
                   _c_dbl, _c_int, _c_int, _c_int, _c_int, _P, _P, _P, _P, _P, _P, _c_int,
@@ -76,6 +78,7 @@ SIGNATURES = {
     "pdsb_loglike_fft": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P],
     "pdsb_regrid_linear": [_P, _c_i64, _P, _P, _c_i64, _c_int, _c_dbl, _c_int, _P],
     "pdsb_channel_postprocess": [_P, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
+    "pdsb_channel_postprocess_scaled": [_P, _c_i64, _c_int, _c_int, _c_int, _c_int, _P, _c_int, _P],
     "pdsb_invert_image": [_P, _P, _P, _c_int, _c_int, _c_int, _P],
     "pdsb_mad_std": [_P, _c_i64, _c_int, ctypes.POINTER(_c_dbl)],
     "pdsb_clean_loop": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _c_dbl, _c_int, _P, _P,
@@ -143,6 +146,14 @@ def ptr(a):
 
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def host_hash(a):
+    """64-bit content hash of a C-contiguous numpy array (pdsb_hash64; no device needed)."""
+    a = np.ascontiguousarray(a)
+    out = ctypes.c_uint64()
+    check(load().pdsb_hash64(a.ctypes.data_as(ctypes.c_void_p), a.nbytes, ctypes.byref(out)))
+    return out.value
 
 
 class DeviceBuffer:

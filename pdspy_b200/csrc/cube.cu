@@ -12,9 +12,13 @@
 
 namespace pdsb {
 
+// in_scale (device, [nf_in], may be null): per-INPUT-channel factor applied before step (1) - the reference's
+// extinction, image[:,:,i,:] *= extinction[i] (:286-299), which precedes the sub-sample mean and the smoothing
+// and does not commute with them.
 __global__ void __launch_bounds__(256) channel_post_kernel(const double *__restrict__ in, double *__restrict__ out,
                                                            int64_t npix, int nf_in, int subsample, int hanning,
-                                                           int averaging, int nf_mid, int nf_out)
+                                                           int averaging, int nf_mid, int nf_out,
+                                                           const double *__restrict__ in_scale)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= npix * nf_out) return;
@@ -22,7 +26,10 @@ __global__ void __launch_bounds__(256) channel_post_kernel(const double *__restr
     const double *src = in + (idx / nf_out) * nf_in;
     auto sub_mean = [&](int m) -> double {                  // step (1): sums in index order, then one division
         double s = 0.0;
-        for (int j = 0; j < subsample; j++) s += src[m * subsample + j];
+        if (in_scale)
+            for (int j = 0; j < subsample; j++) s += __dmul_rn(src[m * subsample + j], in_scale[m * subsample + j]);
+        else
+            for (int j = 0; j < subsample; j++) s += src[m * subsample + j];
         return s / (double)subsample;
     };
     double acc = 0.0;
@@ -110,6 +117,12 @@ int pdsb_regrid_linear(const double *values, int64_t npts, const int *tri, const
 int pdsb_channel_postprocess(const double *image, int64_t npix, int nf_in, int subsample, int hanning, int averaging,
                              int kind, double *out)
 {
+    return pdsb_channel_postprocess_scaled(image, npix, nf_in, subsample, hanning, averaging, nullptr, kind, out);
+}
+
+int pdsb_channel_postprocess_scaled(const double *image, int64_t npix, int nf_in, int subsample, int hanning, int averaging,
+                                    const double *in_scale, int kind, double *out)
+{
     PDSB_CHECK(require_init());
     Context &c = ctx();
     PDSB_REQUIRE(npix >= 0 && nf_in > 0 && subsample >= 1 && averaging >= 1, "sizes");
@@ -126,10 +139,17 @@ int pdsb_channel_postprocess(const double *image, int64_t npix, int nf_in, int s
         PDSB_CHECK(c.stage_b.ensure((size_t)npix * nf_out * sizeof(double)));
         dout = c.stage_b.as<double>();
     }
+    const double *dscale = nullptr;
+    if (in_scale) {                                           // always a host array: nf_in doubles
+        PDSB_CHECK(c.small_dev.ensure((size_t)nf_in * sizeof(double)));
+        PDSB_CUDA(cudaMemcpyAsync(c.small_dev.ptr, in_scale, (size_t)nf_in * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        dscale = c.small_dev.as<double>();
+    }
     {
         LaunchScope ls("channel_post");
         channel_post_kernel<<<ceil_div(npix * nf_out, 256), 256, 0, c.stream>>>(din, dout, npix, nf_in, subsample,
-                                                                               hanning ? 1 : 0, averaging, nf_mid, nf_out);
+                                                                               hanning ? 1 : 0, averaging, nf_mid, nf_out,
+                                                                               dscale);
         PDSB_CUDA(cudaGetLastError());
     }
     if (kind == PDSB_HOST) {

@@ -1,6 +1,7 @@
 // libpdsb runtime: context, stream, buffers, timing, profiling, the FP32 FMA peak measurement.
 #include "common.cuh"
 #include "dft.cuh"
+#include <thread>
 
 namespace pdsb {
 
@@ -414,6 +415,63 @@ int pdsb_launch_count(int64_t *count)
 {
     PDSB_REQUIRE(count, "count");
     *count = ctx().launches;
+    return PDSB_OK;
+}
+
+// Content hash of a host array: what the Python handle cache compares before it trusts a device copy
+// (pdspy_b200/device.py).  Memory-bound: 4 interleaved multiply-rotate lanes per thread, chunks of the array
+// on up to 32 host threads, chunk hashes combined in order.  Needs no CUDA device.
+static uint64_t hash_chunk(const unsigned char *p, size_t n)
+{
+    const uint64_t K = 0x9E3779B97F4A7C15ull;
+    uint64_t h[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+    const size_t nw = n / 8;
+    size_t i = 0;
+    for (; i + 4 <= nw; i += 4) {
+        uint64_t w[4];
+        memcpy(w, p + i * 8, 32);
+        for (int l = 0; l < 4; l++) {
+            h[l] = (h[l] ^ w[l]) * K;
+            h[l] = (h[l] << 29) | (h[l] >> 35);
+        }
+    }
+    uint64_t tail = 0;
+    for (; i < nw; i++) {
+        uint64_t w;
+        memcpy(&w, p + i * 8, 8);
+        h[i & 3] = ((h[i & 3] ^ w) * K);
+        h[i & 3] = (h[i & 3] << 29) | (h[i & 3] >> 35);
+    }
+    if (n % 8) memcpy(&tail, p + nw * 8, n % 8);
+    uint64_t r = (uint64_t)n * K ^ tail;
+    for (int l = 0; l < 4; l++) r = ((r ^ h[l]) * K) ^ (r >> 31);
+    return r;
+}
+
+int pdsb_hash64(const void *host_ptr, int64_t bytes, uint64_t *out)
+{
+    PDSB_REQUIRE(out && bytes >= 0 && (bytes == 0 || host_ptr), "hash arguments");
+    const unsigned char *p = static_cast<const unsigned char *>(host_ptr);
+    const size_t n = (size_t)bytes, chunk = (size_t)4 << 20;
+    const size_t nchunk = (n + chunk - 1) / chunk;
+    std::vector<uint64_t> hs(nchunk ? nchunk : 1, 0);
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 4;
+    if (nt > 32) nt = 32;
+    if (nt > nchunk) nt = (unsigned)(nchunk ? nchunk : 1);
+    auto work = [&](unsigned t) {
+        for (size_t c = t; c < nchunk; c += nt) {
+            const size_t o = c * chunk;
+            hs[c] = hash_chunk(p + o, n - o < chunk ? n - o : chunk);
+        }
+    };
+    if (nt <= 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
+    }
+    *out = hash_chunk(reinterpret_cast<const unsigned char *>(hs.data()), nchunk * sizeof(uint64_t)) ^ (uint64_t)n;
     return PDSB_OK;
 }
 

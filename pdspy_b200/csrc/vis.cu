@@ -830,6 +830,41 @@ int pdsb_chi2(const double *d_real, const double *d_imag, const double *weights,
     return PDSB_OK;
 }
 
+int pdsb_chi2_dataset(pdsb_dataset *ds, const double *m_real, const double *m_imag, int kind, double *out)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ds && out, "dataset/out");
+    PDSB_REQUIRE(ds->has_data, "dataset has no data (call pdsb_dataset_set_data)");
+    Context &c = ctx();
+    const int64_t n = ds->nuv * ds->nf;
+    if (n == 0) {
+        out[0] = out[1] = out[2] = 0.0;
+        out[3] = -0.0;
+        return PDSB_OK;
+    }
+    PDSB_REQUIRE(m_real && m_imag, "model arrays");
+    const size_t bytes = (size_t)n * sizeof(double);
+    const double *mr, *mi;
+    PDSB_CHECK(to_device(m_real, kind, bytes, c.stage_d, (const void **)&mr));
+    PDSB_CHECK(to_device(m_imag, kind, bytes, c.stage_e, (const void **)&mi));
+    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (n + 255) / 256);
+    PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * 3 * sizeof(double)));
+    {
+        LaunchScope ls("chi2_flat");
+        chi2_flat_kernel<<<nb, 256, 0, c.stream>>>(ds->re, ds->im, ds->w, mr, mi, n, c.red.as<double>());
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CHECK(reduce_blocks(c.red.as<double>(), nb, 3, c.red.as<double>() + (size_t)nb * 3));
+    double h[3];
+    PDSB_CUDA(cudaMemcpyAsync(h, c.red.as<double>() + (size_t)nb * 3, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    out[0] = h[0];
+    out[1] = h[1];
+    out[2] = h[2];
+    out[3] = -0.5 * h[0] - h[2] + -0.5 * h[1] - h[2];
+    return PDSB_OK;
+}
+
 int pdsb_chisq(const double *d_real, const double *d_imag, const double *weights, const double *m_real,
                const double *m_imag, int64_t nuv, int nf, int kind, float *out)
 {

@@ -7,6 +7,7 @@ import ctypes
 from collections import OrderedDict
 
 import numpy as np
+import numpy
 
 from . import _lib
 from ._lib import HOST, DEVICE, check, ptr, f64
@@ -14,15 +15,54 @@ from ._lib import HOST, DEVICE, check, ptr, f64
 _CACHE = OrderedDict()
 _CACHE_MAX = 8
 
+# How dataset_for decides that the device copy of caller-owned arrays is still valid.
+#   "hash"   (default) every call hashes the arrays in full on the host (pdsb_hash64: multi-threaded,
+#            memory-bound - about 30 GB/s, i.e. 1 ms for a uv list, 40 ms for 1M x 64 data) and compares with
+#            the hash taken at upload.  Any in-place edit is seen (the reference edits arrays in place:
+#            invert.py:15-47).
+#   "freeze" the arrays are made read-only (flags.writeable = False) when they are uploaded, and an array that
+#            is still read-only at the same address is trusted without reading it: an in-place edit raises
+#            numpy's "assignment destination is read-only" instead of going unnoticed.  clear_cache() /
+#            release(array) make them writeable again.  Zero cost per call; edits through an older writeable
+#            view of the same memory are NOT seen.
+_POLICY = "hash"
 
-def _fingerprint(a):
-    """Cheap content fingerprint (<= 4096 strided samples + the ends)."""
-    if a.size == 0:
-        return (0,)
-    step = max(1, a.size // 4096)
-    flat = a.reshape(-1)
-    s = flat[::step]
-    return (a.size, float(s.sum()), float(flat[0]), float(flat[-1]), float(flat[a.size // 2]))
+
+def set_cache_policy(policy):
+    """"hash" (default) or "freeze": see above."""
+    global _POLICY
+    if policy not in ("hash", "freeze"):
+        raise ValueError("cache policy must be 'hash' or 'freeze'")
+    _POLICY = policy
+
+
+class _Stamp:
+    """What is remembered about one uploaded host array."""
+
+    def __init__(self, a):
+        self.addr, self.shape, self.hash = a.ctypes.data, a.shape, _lib.host_hash(a)
+        self.frozen = None
+        if _POLICY == "freeze" and a.flags.writeable:
+            try:
+                a.flags.writeable = False
+                self.frozen = a
+            except ValueError:
+                pass
+
+    def valid_for(self, a):
+        if a.ctypes.data != self.addr or a.shape != self.shape:
+            return False
+        if _POLICY == "freeze" and self.frozen is a and not a.flags.writeable:
+            return True
+        return _lib.host_hash(a) == self.hash
+
+    def thaw(self):
+        if self.frozen is not None:
+            try:
+                self.frozen.flags.writeable = True
+            except ValueError:
+                pass
+            self.frozen = None
 
 
 class Dataset:
@@ -77,38 +117,97 @@ class Dataset:
 
 
 def dataset_for(u, v, data=None):
-    """Cached Dataset for the caller's u, v (and optionally data = (real, imag, weights))."""
-    key = (u.ctypes.data, v.ctypes.data, u.size) if isinstance(u, np.ndarray) and isinstance(v, np.ndarray) \
-        else None
-    fp = (_fingerprint(np.asarray(u)), _fingerprint(np.asarray(v)))
-    ent = _CACHE.get(key) if key is not None else None
-    if ent is None or ent[0] != fp:
-        if ent is not None:
-            ent[1].destroy()
-        ds = Dataset(np.asarray(u), np.asarray(v))
-        if key is not None:
-            _CACHE[key] = (fp, ds)
-            while len(_CACHE) > _CACHE_MAX:
-                _, (_, old) = _CACHE.popitem(last=False)
-                old.destroy()
+    """Cached Dataset for the caller's u, v (and optionally data = (real, imag, weights)): uploaded once, reused
+    while the arrays are unchanged (see the cache policy above)."""
+    u, v = f64(u), f64(v)
+    key = (u.ctypes.data, v.ctypes.data, u.size)
+    ent = _CACHE.get(key)
+    if ent is not None and not (ent["u"].valid_for(u) and ent["v"].valid_for(v)):
+        _drop(key)
+        ent = None
+    if ent is None:
+        ent = {"ds": Dataset(u, v), "u": _Stamp(u), "v": _Stamp(v), "data": None}
+        _CACHE[key] = ent
+        while len(_CACHE) > _CACHE_MAX:
+            _drop(next(iter(_CACHE)))
     else:
-        ds = ent[1]
         _CACHE.move_to_end(key)
+    ds = ent["ds"]
     if data is not None:
-        real, imag, weights = data
-        dkey = (real.ctypes.data, imag.ctypes.data, weights.ctypes.data, real.shape,
-                _fingerprint(real), _fingerprint(imag), _fingerprint(weights))
-        if ds.data_key != dkey:
-            ds.set_data(real, imag, weights)
-            ds.data_key = dkey
+        arrays = [f64(a) for a in data]
+        st = ent["data"]
+        if st is None or not all(s.valid_for(a) for s, a in zip(st, arrays)):
+            if st is not None:
+                for s in st:
+                    s.thaw()
+            ds.set_data(*arrays)
+            ent["data"] = [_Stamp(a) for a in arrays]
     return ds
 
 
+def _drop(key):
+    ent = _CACHE.pop(key)
+    for st in [ent["u"], ent["v"]] + list(ent["data"] or []):
+        st.thaw()
+    ent["ds"].destroy()
+
+
 def clear_cache():
-    """Drop every cached device handle (call after mutating u, v or data arrays in place)."""
+    """Drop every cached device handle (and un-freeze the arrays the "freeze" policy made read-only)."""
     while _CACHE:
-        _, (_, ds) = _CACHE.popitem()
-        ds.destroy()
+        _drop(next(iter(_CACHE)))
+    _POOL.clear()
+
+
+def release(array):
+    """Forget the device copies made from `array` (a u, v, real, imag or weights array handed to a likelihood
+    call) and make it writeable again."""
+    addr = array.ctypes.data
+    for key in [k for k, e in _CACHE.items()
+                if any(st.addr == addr for st in [e["u"], e["v"]] + list(e["data"] or []))]:
+        _drop(key)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Device-resident model visibilities (interpolate_model's result before anybody reads it on the host).
+# Visibilities objects carry only an integer token; the buffers live here, so nothing holding a CUDA
+# allocation is reachable from an object the samplers pickle.
+_MODELS = {}
+_POOL = {}            # nbytes -> [free DeviceBuffer, ...]  (cudaMalloc of 2 x 512 MB per likelihood call is not free)
+_next_token = [1]
+
+
+def _take(nbytes):
+    free = _POOL.get(nbytes)
+    if free:
+        return free.pop()
+    return _lib.DeviceBuffer(nbytes)
+
+
+def register_model(shape):
+    """Two device buffers (real, imag) of `shape` doubles; returns (token, real, imag)."""
+    nbytes = int(numpy.prod(shape)) * 8
+    re, im = _take(max(nbytes, 8)), _take(max(nbytes, 8))
+    token = _next_token[0]
+    _next_token[0] += 1
+    _MODELS[token] = (re, im, tuple(shape))
+    return token, re, im
+
+
+def model_buffers(token):
+    """(real DeviceBuffer, imag DeviceBuffer, shape) or None when the token is unknown (other process, released)."""
+    return _MODELS.get(token)
+
+
+def release_model(token):
+    ent = _MODELS.pop(token, None)
+    if ent is not None:
+        for b in ent[:2]:
+            free = _POOL.setdefault(b.nbytes, [])
+            if len(free) < 4:
+                free.append(b)
+            else:
+                b.free()
 
 
 DFT_KERNELS = {"fp32": 0, "tcgen05": 200, "fp64": 300}

@@ -99,7 +99,7 @@ class ShardedLikelihood:
         self.buf[self.nf:].copy_(self.logsum_dev)
         return self.buf
 
-    def stage_cube(self, image, cube="sharded"):
+    def stage_cube(self, image, cube="sharded", shape=None):
         """Put a HOST cube [ny, nx, nf] (fp64, C order; pinned memory makes the copies asynchronous DMA) on
         every rank's GPU and return the device tensor.
 
@@ -107,13 +107,24 @@ class ShardedLikelihood:
             the parameters, or a cube read from shared storage); each uploads only its 1/world slab of rows
             and the slabs are exchanged over NVLink with one NCCL all-gather - world times less PCIe traffic
             per rank than uploading the whole cube everywhere.
-        cube="rank0": only rank 0's `image` is read (the others may pass None with `shape`); rank 0 uploads
-            it and NCCL broadcasts it.
+        cube="rank0": only rank 0's `image` is read; the other ranks may pass image=None together with
+            shape=(ny, nx, nf) (needed on their first call; later calls remember it).  Rank 0 uploads the cube
+            and NCCL broadcasts it.
         Falls back to a plain full upload on one rank / without a process group."""
         import torch.distributed as dist
         torch = self.torch
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
-        shape = tuple(image.shape[:3]) if image is not None else self._cube_shape
+        if image is not None:
+            shape = tuple(image.shape[:3])
+        elif shape is not None:
+            shape = tuple(int(x) for x in shape)
+        else:
+            shape = getattr(self, "_cube_shape", None)
+        if shape is None or len(shape) != 3:
+            # every rank raises before any collective is entered: nobody is left waiting in a broadcast
+            raise ValueError("stage_cube needs the cube, or shape=(ny, nx, nf) when image is None")
+        if image is None and cube != "rank0":
+            raise ValueError("image=None is only meaningful with cube='rank0'")
         if getattr(self, "_cube_dev", None) is None or tuple(self._cube_dev.shape) != shape:
             self._cube_dev = torch.empty(shape, dtype=torch.float64, device="cuda")
             self._cube_shape = shape
@@ -140,9 +151,11 @@ class ShardedLikelihood:
 
     def __call__(self, image, dxy, dRA=0.0, dDec=0.0, kind=0, shape=None, cube=None):
         """kind 0: host cube, 1: device pointer / DeviceBuffer (then `shape` = (ny, nx)).  With a host cube,
-        cube="sharded" | "rank0" stages it through stage_cube; None keeps the per-rank full upload."""
+        cube="sharded" | "rank0" stages it through stage_cube (with "rank0" the other ranks may pass image=None
+        and shape=(ny, nx)); None keeps the per-rank full upload."""
         if kind == 0 and cube is not None:
-            dev = self.stage_cube(image, cube)
+            dev = self.stage_cube(image, cube, shape=(tuple(shape) + (self.nf,)) if shape is not None and len(shape) == 2
+                                  else shape)
             ny, nx = dev.shape[0], dev.shape[1]
             return combine_lnlike(self.chi2_device(int(dev.data_ptr()), ny, nx, 1, dxy, dRA, dDec), self.group)
         if shape is None:

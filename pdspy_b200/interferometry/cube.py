@@ -14,11 +14,22 @@ def _check(nf_in, subsample, averaging):
     return subsample, averaging
 
 
-def postprocess_channels(image, subsample=1, averaging=1, hanning=False):
+def _in_scale(in_scale, nf_in):
+    if in_scale is None:
+        return None
+    s = numpy.ascontiguousarray(in_scale, dtype=numpy.float64)
+    if s.shape != (nf_in,):
+        raise ValueError("the per-channel factor (extinction) must have one entry per cube channel before "
+                         "post-processing: expected %d, got shape %s" % (nf_in, s.shape))
+    return s
+
+
+def postprocess_channels(image, subsample=1, averaging=1, hanning=False, in_scale=None):
     """What the reference does to a freshly rendered cube before interpolate_model: mean over blocks of
     `subsample` sub-channels, Hanning smoothing along the channel axis when `hanning`
     (numpy.hanning(5)/sum through scipy.signal.fftconvolve(mode="same"), i.e. taps 1/4, 1/2, 1/4 with
-    zero padding), mean over blocks of `averaging` channels.
+    zero padding), mean over blocks of `averaging` channels.  in_scale [nf_in]: multiplied into the input channels
+    first (the reference's extinction, run_flared_model.py:286-299, which precedes all of this).
 
     image: [ny, nx, nf_in, 1] (regular cube) or [npts, nf_in] (unstructured image); returns the same
     rank with nf_in / subsample / averaging channels."""
@@ -34,22 +45,25 @@ def postprocess_channels(image, subsample=1, averaging=1, hanning=False):
     subsample, averaging = _check(nf_in, subsample, averaging)
     nf_out = nf_in // subsample // averaging
     out = numpy.empty(a.shape[:2] + (nf_out, 1) if a.ndim == 4 else (npix, nf_out))
+    scale = _in_scale(in_scale, nf_in)
     if npix > 0:
-        _lib.check(_lib.lib().pdsb_channel_postprocess(_lib.ptr(a), npix, nf_in, subsample, 1 if hanning else 0,
-                                                       averaging, _lib.HOST, _lib.ptr(out)))
+        _lib.check(_lib.lib().pdsb_channel_postprocess_scaled(_lib.ptr(a), npix, nf_in, subsample, 1 if hanning else 0,
+                                                              averaging, _lib.ptr(scale), _lib.HOST, _lib.ptr(out)))
     return out
 
 
-def postprocess_channels_device(image, subsample=1, averaging=1, hanning=False):
+def postprocess_channels_device(image, subsample=1, averaging=1, hanning=False, in_scale=None):
     """The same, host cube in, DeviceBuffer out (for chaining into pdsb_sample_image / pdsb_loglike without
     a round trip).  image: [ny, nx, nf_in, 1].  Returns (buffer, nf_out)."""
     a = numpy.ascontiguousarray(image, dtype=numpy.float64)
     ny, nx, nf_in = a.shape[:3]
     subsample, averaging = _check(nf_in, subsample, averaging)
     nf_out = nf_in // subsample // averaging
+    scale = _in_scale(in_scale, nf_in)
     src = _lib.DeviceBuffer.from_numpy(a)
     dst = _lib.DeviceBuffer(max(1, ny * nx * nf_out) * 8)
     if ny * nx > 0:
-        _lib.check(_lib.lib().pdsb_channel_postprocess(_lib.ptr(src), ny * nx, nf_in, subsample, 1 if hanning else 0,
-                                                       averaging, _lib.DEVICE, _lib.ptr(dst)))
+        _lib.check(_lib.lib().pdsb_channel_postprocess_scaled(_lib.ptr(src), ny * nx, nf_in, subsample,
+                                                              1 if hanning else 0, averaging, _lib.ptr(scale),
+                                                              _lib.DEVICE, _lib.ptr(dst)))
     return dst, nf_out

@@ -12,7 +12,7 @@ import numpy
 
 from ..constants import arcsec
 from .. import _lib
-from ..device import dataset_for
+from ..device import dataset_for, register_model
 from .visibilities import Visibilities
 from .cube import postprocess_channels_device
 from .unstructured import regrid
@@ -43,13 +43,16 @@ def interpolate_model(u, v, freq, model, nthreads=1, dRA=0., dDec=0.,
         v = numpy.ascontiguousarray(v, dtype=numpy.float64)
         ds = dataset_for(u, v)
 
-        real = numpy.empty((u.size, nf))
-        imag = numpy.empty((u.size, nf))
         if u.size > 0:
+            # the result stays on the device until somebody reads it (visibilities.py); utils.emcee.lnlike does not
             L = _lib.lib()
+            token, dre, dim_ = register_model((u.size, nf))
             _lib.check(L.pdsb_sample_image(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST,
                                            float(dxy), float(dRA * arcsec), float(dDec * arcsec),
-                                           _lib.ptr(real), _lib.ptr(imag), _lib.HOST))
+                                           _lib.ptr(dre), _lib.ptr(dim_), _lib.DEVICE))
+            return Visibilities._from_device(u, v, freq, token, (u.size, nf))
+        real = numpy.empty((u.size, nf))
+        imag = numpy.empty((u.size, nf))
 
     elif code == "galario-fft":
         # EXTENSION (not a value the reference knows): galario's own algorithm - FFT of the image + bilinear
@@ -103,15 +106,21 @@ def _mods(nf, flux_unc, extinction, freefree, dRA, dDec):
     return scale, ff, float(dRA * arcsec), float(dDec * arcsec)
 
 
-def _staged_cube(model, subsample, averaging, hanning):
-    """(pointer, kind, ny, nx, nf, keepalive) of the cube the transform reads: the host cube as is, or, when
-    channel post-processing is asked for, its post-processed copy left on the device."""
+def _staged_cube(model, subsample, averaging, hanning, extinction):
+    """(pointer, kind, ny, nx, nf, keepalive, extinction left for the epilogue) of the cube the transform reads:
+    the host cube as is, or, when channel post-processing is asked for, its post-processed copy left on the
+    device.  The reference multiplies the RENDERED channels by extinction[i] (run_flared_model.py:286-299) before
+    the sub-sample mean / Hanning smoothing / binning (:308-366); the two do not commute, so with
+    post-processing the extinction (one entry per rendered channel) goes into that pass, and only without it
+    can it ride on the transform's epilogue as a per-channel factor."""
     image = _cube(model)
     ny, nx, nf = image.shape[:3]
     if subsample * averaging > 1 or hanning:                  # run_flared_model.py:308-309
-        buf, nf = postprocess_channels_device(image, subsample, averaging, hanning)
-        return _lib.ptr(buf), _lib.DEVICE, ny, nx, nf, buf
-    return _lib.ptr(image), _lib.HOST, ny, nx, nf, image
+        buf, nf = postprocess_channels_device(image, subsample, averaging, hanning, in_scale=extinction)
+        return _lib.ptr(buf), _lib.DEVICE, ny, nx, nf, buf, None
+    if extinction is not None and numpy.shape(extinction) != (nf,):
+        raise ValueError("extinction must have one entry per cube channel (%d)" % nf)
+    return _lib.ptr(image), _lib.HOST, ny, nx, nf, image, extinction
 
 
 def model_visibilities(u, v, freq, model, dRA=0., dDec=0., flux_unc=1.0, extinction=None, freefree=None,
@@ -122,7 +131,7 @@ def model_visibilities(u, v, freq, model, dRA=0., dDec=0., flux_unc=1.0, extinct
     the data's channel list, as there), real += point-source free-free flux at (dRA, dDec)
     (run_disk_model.py:329-334).  Returns Visibilities."""
     dxy = (model.x[1] - model.x[0]) * arcsec
-    image, image_kind, ny, nx, nf, _keep = _staged_cube(model, subsample, averaging, hanning)
+    image, image_kind, ny, nx, nf, _keep, extinction = _staged_cube(model, subsample, averaging, hanning, extinction)
     u = numpy.ascontiguousarray(u, dtype=numpy.float64)
     v = numpy.ascontiguousarray(v, dtype=numpy.float64)
     ds = dataset_for(u, v)
@@ -157,7 +166,7 @@ def loglike_image(data, model, dRA=0., dDec=0., flux_unc=1.0, extinction=None, f
     u, v, real, imag, weights; `model` an Image.  flux_unc / extinction / freefree as in
     model_visibilities (as are subsample / averaging / hanning).  Returns (lnlike, chi2_per_channel)."""
     dxy = (model.x[1] - model.x[0]) * arcsec
-    image, image_kind, ny, nx, nf, _keep = _staged_cube(model, subsample, averaging, hanning)
+    image, image_kind, ny, nx, nf, _keep, extinction = _staged_cube(model, subsample, averaging, hanning, extinction)
     ds = dataset_for(data.u, data.v, (data.real, data.imag, data.weights))
     chi2 = numpy.empty(nf)
     out = ctypes.c_double()

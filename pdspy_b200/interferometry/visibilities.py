@@ -11,7 +11,16 @@ Same constructor signature, attributes and pickling behaviour:
   * __reduce__ rebuilds a *VisibilitiesObject* (the base class), as the reference's
     `rebuild` does (:46-52) - what crosses MPI / dynesty checkpoints is the base class.
 No CUDA handle is reachable from these objects (samplers pickle them).
+
+Device-resident results: interpolate_model leaves the model visibilities on the GPU and returns a Visibilities
+whose real / imag / weights are filled in on first read (`_device_token` is a plain integer naming the buffers in
+pdspy_b200.device; it means nothing in another process).  utils.emcee.lnlike / visibility_lnlike consume the
+device copy directly, so the unchanged-signature chain interpolate_model(...) -> lnlike(...) never moves the
+[nuv, nf] arrays over PCIe; anything else that touches .real / .imag / .weights / .amp / .phase, or pickles
+the object, gets ordinary numpy arrays.
 """
+import weakref
+
 import numpy
 
 
@@ -38,7 +47,10 @@ class VisibilitiesObject(object):
         real = _check("real", real, 2)
         imag = _check("imag", imag, 2)
         weights = _check("weights", weights, 2)
-        self.u = self.v = self.freq = self.real = self.imag = self.weights = None
+        self._real = self._imag = self._weights = None
+        self._device_token = None
+        self._shape = None
+        self.u = self.v = self.freq = None
         self._uvdist = self._amp = self._phase = None
 
         if (u is not None) and (v is not None):
@@ -58,6 +70,61 @@ class VisibilitiesObject(object):
 
         self.baseline = baseline
         self.array_name = array_name
+
+    # real / imag / weights: plain attributes in the reference; here they may still be on the device
+    def _materialise(self):
+        token = self._device_token
+        if token is None:
+            return
+        self._device_token = None
+        from .. import device
+        ent = device.model_buffers(token)
+        if ent is None:
+            raise RuntimeError("the device copy of these model visibilities is gone (cache cleared or another process)")
+        re, im, shape = ent
+        self._real = re.download(shape)
+        self._imag = im.download(shape)
+        device.release_model(token)
+
+    @property
+    def real(self):
+        self._materialise()
+        return self._real
+
+    @real.setter
+    def real(self, value):
+        self._materialise()
+        self._real = value
+
+    @property
+    def imag(self):
+        self._materialise()
+        return self._imag
+
+    @imag.setter
+    def imag(self, value):
+        self._materialise()
+        self._imag = value
+
+    @property
+    def weights(self):
+        if self._weights is None and self._shape is not None:
+            self._weights = numpy.ones(self._shape)          # interpolate_model.py:57
+        return self._weights
+
+    @weights.setter
+    def weights(self, value):
+        self._weights = value
+
+    @classmethod
+    def _from_device(cls, u, v, freq, token, shape):
+        """A result whose real / imag still live on the device (pdspy_b200.device.register_model)."""
+        self = cls(u, v, freq)
+        self._device_token = token
+        self._shape = tuple(shape)
+        from .. import device
+        weakref.finalize(self, device.release_model, token)
+        return self
 
     # derived arrays: same definitions as libinterferometry.pyx:27,35-36
     @property

@@ -49,4 +49,7 @@ def live_ref():
 def gpu():
     """libpdsb with a device initialised; GPU tests call through this (the C-ABI)."""
     from pdspy_b200 import _lib
-    return _lib.lib()
+    try:
+        return _lib.lib()
+    except _lib.PdsbError as e:                     # no CUDA device here: the GPU suite is for the B200 box
+        pytest.skip("no CUDA device (%s)" % e)

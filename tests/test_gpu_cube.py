@@ -73,3 +73,43 @@ def test_chained_into_the_transform_and_the_likelihood(gpu):
     mp = synth.SynthImage(np.ascontiguousarray(post), 0.05, freq)
     ll0, chi20 = loglike_image(data, mp, dRA=0.03, dDec=-0.02)
     assert abs(ll - ll0) <= 1e-12 * abs(ll0) and np.allclose(chi2, chi20, rtol=1e-12)
+
+
+@pytest.mark.parametrize("sub,avg,hanning", [(1, 1, True), (2, 2, True), (3, 1, False)])
+def test_extinction_goes_before_the_post_processing(gpu, sub, avg, hanning):
+    """The reference multiplies the rendered channels by extinction[i] (run_flared_model.py:286-299) and by
+    flux_unc (:303) BEFORE the sub-sample mean / Hanning smoothing / binning (:308-366).  The two do not commute
+    (with hanning and subsample = averaging = 1 the channel counts are even equal), so the chained calls must
+    follow that order: compare with the literal sequence on the host."""
+    nfd = 4
+    nf_in = nfd * sub * avg
+    rng = np.random.default_rng(sub * 10 + avg)
+    img = rng.random((40, 40, nf_in, 1))
+    ext = np.exp(-rng.uniform(0.0, 2.0, nf_in))                   # exp(-tau) per rendered channel
+    flux_unc = 1.07
+    m = synth.SynthImage(img, 0.05, synth.synth_freq(nf_in))
+    u, v = synth.synth_uv(500, 0.05 * A)
+    freq = synth.synth_freq(nfd)
+    lit = img * ext[None, None, :, None]                          # :286-299
+    lit = lit * flux_unc                                          # :303
+    post = oc.post(lit[:, :, :, 0], sub, avg, hanning)[:, :, :, None]
+    ref = od.exact_dft(u, v, post, 0.05 * A, 0.01 * A, 0.02 * A)
+    vis = model_visibilities(u, v, freq, m, dRA=0.01, dDec=0.02, flux_unc=flux_unc, extinction=ext, subsample=sub,
+                             averaging=avg, hanning=hanning)
+    assert np.abs(vis.real + 1j * vis.imag - ref).max() / np.abs(ref).max() < 1e-5
+    wrong = od.exact_dft(u, v, oc.post(img[:, :, :, 0], sub, avg, hanning)[:, :, :, None] * flux_unc, 0.05 * A, 0.01 * A,
+                         0.02 * A)
+    if nf_in == nfd:                                              # what round 1 computed: visibly different
+        wrong = wrong * ext[None, :]
+        assert np.abs(wrong - ref).max() / np.abs(ref).max() > 1e-3
+    w = rng.uniform(0.5, 2.0, (500, nfd))
+    data = Visibilities(u, v, freq, ref.real + rng.normal(0, 0.1, ref.shape), ref.imag + rng.normal(0, 0.1, ref.shape), w)
+    ll, _ = loglike_image(data, m, dRA=0.01, dDec=0.02, flux_unc=flux_unc, extinction=ext, subsample=sub, averaging=avg,
+                          hanning=hanning)
+    ll0, _ = loglike_image(data, synth.SynthImage(np.ascontiguousarray(post), 0.05, freq), dRA=0.01, dDec=0.02)
+    assert abs(ll - ll0) <= 1e-10 * abs(ll0)
+    got = postprocess_channels(img, sub, avg, hanning, in_scale=ext)
+    assert np.abs(got[:, :, :, 0] - oc.post((img * ext[None, None, :, None])[:, :, :, 0], sub, avg, hanning)).max() <= TOL
+    if sub * avg > 1:
+        with pytest.raises(ValueError):                           # a factor per OUTPUT channel is not what the reference has
+            model_visibilities(u, v, freq, m, extinction=ext[:nfd], subsample=sub, averaging=avg, hanning=hanning)

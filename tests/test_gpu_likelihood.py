@@ -181,3 +181,63 @@ def test_sharded_likelihood_single_rank_and_cube_staging(gpu):
     finally:
         _lib.check(gpu.pdsb_reset_stream())
     assert all(abs(x - ll0) <= 1e-12 * abs(ll0) for x in vals), (vals, ll0)
+
+
+def test_unchanged_signature_chain_stays_on_the_device(gpu):
+    """interpolate_model(...) -> utils.visibility_lnlike(data, model) (what utils.emcee.lnlike runs, emcee.py:31-43):
+    the model visibilities are consumed from the device; reading them afterwards, or pickling the object, gives
+    ordinary numpy arrays equal to what the likelihood saw."""
+    import pickle
+    from pdspy_b200 import device
+    c = synth.make_config("C3", nuv=20000)
+    re, im, w = synth.synth_data(c["u"].size, c["nf"])
+    data = Visibilities(c["u"], c["v"], c["freq"], re, im, w)
+    m = interpolate_model(c["u"], c["v"], c["freq"], c["model"], dRA=c["dRA"], dDec=c["dDec"])
+    assert m._device_token is not None and device.model_buffers(m._device_token) is not None
+    ll = utils.visibility_lnlike(data, m)
+    assert m._device_token is not None                      # the likelihood did not pull the arrays to the host
+    fused, _ = loglike_image(data, c["model"], dRA=c["dRA"], dDec=c["dDec"])
+    assert abs(ll - fused) <= 1e-12 * abs(fused)
+    clone = pickle.loads(pickle.dumps(m))                   # __reduce__ materialises
+    assert m._device_token is None and type(clone).__name__ == "VisibilitiesObject"
+    assert clone.real.shape == (c["u"].size, c["nf"]) and np.array_equal(clone.real, m.real) and np.all(clone.weights == 1)
+    ref = ol.lnlike_vis_numpy(re, im, w, m.real, m.imag)
+    assert abs(ll - ref) <= 1e-11 * abs(ref)
+    assert abs(utils.visibility_lnlike(data, m) - ll) <= 1e-13 * abs(ll)      # host arrays now: same value
+    # a result nobody reads gives its buffers back when it dies
+    t = interpolate_model(c["u"], c["v"], c["freq"], c["model"])._device_token
+    import gc
+    gc.collect()
+    assert device.model_buffers(t) is None
+
+
+@pytest.mark.parametrize("policy", ["hash", "freeze"])
+def test_in_place_edits_of_cached_arrays(gpu, policy):
+    """The reference edits arrays in place (invert.py:15-47).  Default policy: any single-element edit of the data
+    is seen by the next call.  "freeze": the arrays are read-only while cached, an edit raises instead of being
+    missed, release() hands them back."""
+    import pdspy_b200 as pb
+    c = synth.make_config("C1", nuv=30000)
+    re, im, w = synth.synth_data(c["u"].size, c["nf"], seed=5)
+    data = Visibilities(c["u"], c["v"], c["freq"], re, im, w)
+    pb.clear_cache()
+    pb.set_cache_policy(policy)
+    try:
+        ll0, _ = loglike_image(data, c["model"])
+        k = 12347                                            # not one of round 1's 4096 strided samples
+        if policy == "freeze":
+            assert not data.weights.flags.writeable
+            with pytest.raises(ValueError):
+                data.weights[k, 0] = 0.0
+            pb.release(data.weights)
+            assert data.weights.flags.writeable
+        assert data.weights[k, 0] > 0
+        data.weights[k, 0] = 0.0
+        data.real[k + 1, 0] += 1.0
+        ll1, _ = loglike_image(data, c["model"])
+        fresh = Visibilities(c["u"].copy(), c["v"].copy(), c["freq"], re.copy(), im.copy(), w.copy())
+        ll2, _ = loglike_image(fresh, c["model"])
+        assert ll1 != ll0 and ll1 == ll2
+    finally:
+        pb.set_cache_policy("hash")
+        pb.clear_cache()

@@ -85,11 +85,34 @@ def test_synthetic_uv_is_hermitian_doubled_and_nyquist_limited():
     assert (w == 0).any() and (w < 0).any()
 
 
-def test_fingerprint_detects_in_place_change():
-    a = np.arange(10000.0)
-    f0 = device._fingerprint(a)
-    a[0] = -1
-    assert device._fingerprint(a) != f0
+def test_host_hash_sees_any_single_element_edit():
+    """The handle cache's content hash (pdsb_hash64; no GPU needed): one changed element anywhere, a different
+    length and a different shape-preserving permutation all change it; equal content hashes equal."""
+    from pdspy_b200 import _lib
+    rng = np.random.default_rng(0)
+    a = rng.random((30011, 7))
+    h0 = _lib.host_hash(a)
+    assert _lib.host_hash(a.copy()) == h0
+    for idx in ((0, 0), (12345, 3), (30010, 6), (4097, 1)):         # incl. positions round 1's sampled fingerprint missed
+        b = a.copy()
+        b[idx] = np.nextafter(b[idx], 2.0)
+        assert _lib.host_hash(b) != h0, idx
+    assert _lib.host_hash(a[:-1]) != h0
+    b = a.copy()
+    b[[5, 6]] = b[[6, 5]]
+    assert _lib.host_hash(b) != h0
+    assert _lib.host_hash(np.zeros(0)) == _lib.host_hash(np.zeros(0))
+    assert _lib.host_hash(np.zeros(3)) != _lib.host_hash(np.zeros(4))
+
+
+def test_lazy_visibilities_without_a_device_copy_behave_like_plain_ones():
+    from pdspy_b200.interferometry import Visibilities
+    v = Visibilities(np.zeros(2), np.ones(2), np.ones(1), np.full((2, 1), 3.0), np.full((2, 1), 4.0))
+    assert v._device_token is None and np.all(v.weights == 1) and np.all(v.amp == 5)
+    v.real = np.zeros((2, 1))
+    assert np.all(v.real == 0)
+    w = pickle.loads(pickle.dumps(v))
+    assert type(w).__name__ == "VisibilitiesObject" and np.array_equal(w.imag, v.imag)
 
 
 def test_unstructured_triangulation_helper_vs_scipy_interpolator():
