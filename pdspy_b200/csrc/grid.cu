@@ -85,6 +85,12 @@ struct GridParams {
     const double *uu, *vv;
     uint32_t nmin, nmax;    // footprint half-widths of the main scatter
     uint32_t row_lo, row_hi;   // main scatter keeps output rows [row_lo, row_hi) only (multi-GPU row bands)
+    // fast mode: one packed 48-byte record per (visibility, channel) in input order,
+    //   [pos_u, w] [w re, w im] [pos_v, (gi | gj << 32)]      (pos = u f / mean_f as the reference forms it)
+    // written by the prep kernel (coalesced) so that the tile kernel fetches ONE record per visibility through
+    // the sort permutation instead of eight 8-byte gathers (each of which cost a 64-byte DRAM burst: 5.0 GB
+    // read per 10M visibilities in round 1, profiles/r01_grid_tile_ncu.md).  Null in the ordered mode.
+    double2 *rec;
 };
 
 // :351-353 weights clamp/zeroing, :388-403 index maps, :421-423 good mask
@@ -108,6 +114,21 @@ __global__ void __launch_bounds__(256) grid_prep_kernel(GridParams P, unsigned l
     const bool good = i < (uint32_t)P.G && j < (uint32_t)P.G;
     P.good[idx] = good ? 1 : 0;
     if (!good) atomicAdd(n_outside, 1ull);
+    if (P.rec) {
+        double2 *r = P.rec + 3 * idx;
+        if (good) {
+            r[0] = make_double2(__dmul_rn(__dmul_rn(P.u[k], f), P.inv_freq), w);
+            r[1] = make_double2(P.re[idx] * w, P.im[idx] * w);
+            r[2] = make_double2(__dmul_rn(__dmul_rn(P.v[k], f), P.inv_freq),
+                                __longlong_as_double((long long)((unsigned long long)i | ((unsigned long long)j << 32))));
+        } else {
+            // off the grid (:421-425): sorted into the first tile with zero weight, where it adds exact zeros;
+            // no dead key, so the tile sort needs only the bits of the tile index
+            r[0] = make_double2(P.uu[0], 0.0);
+            r[1] = make_double2(0.0, 0.0);
+            r[2] = make_double2(P.vv[0], 0.0);
+        }
+    }
 }
 
 // Footprint of contribution slot f of visibility idx.  lo/hi half-widths, side = lo+hi+1.
@@ -616,7 +637,6 @@ __global__ void __launch_bounds__(256) grid_tile_items_kernel(const uint32_t *__
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (p >= nvis) return;
     const uint32_t key = keys[p];
-    if (key == KEY_DEAD) return;
     if (p != 0 && keys[p - 1] == key) return;                 // not a run head
     const int64_t e = lower_bound_u32(keys, nvis, key + 1u);
     const uint32_t nitems = (uint32_t)((e - p + GT_SUBRUN - 1) / GT_SUBRUN);
@@ -656,12 +676,13 @@ __global__ void __launch_bounds__(GT_THREADS) grid_tile_kernel(GridParams P, int
             const int64_t idx = order[base + q];
             const int64_t k = idx / P.nf;
             const double f = P.freq[idx % P.nf];
-            const int home = sidev ? (int)P.gj[idx] : (int)P.gi[idx];
+            const bool live = P.good[idx] != 0;       // off-grid entries sit in the first tile's run with zero weight
+            const int home = live ? (sidev ? (int)P.gj[idx] : (int)P.gi[idx]) : -(1 << 20);
             if (sidev == 0) {
-                const double w = P.w[idx];
+                const double w = live ? P.w[idx] : 0.0;
                 s_w[q] = w;
-                s_re[q] = P.re[idx] * w;
-                s_im[q] = P.im[idx] * w;
+                s_re[q] = live ? P.re[idx] * w : 0.0;
+                s_im[q] = live ? P.im[idx] * w : 0.0;
                 s_i[q] = home;
             } else {
                 s_j[q] = home;
@@ -769,14 +790,20 @@ __global__ void __launch_bounds__(NSTREAM * 16) grid_tile2_kernel(GridParams P, 
     auto load_raw = [&](int64_t idx) -> Raw {
         Raw x{0.0, 1.0, 0.0, 0.0, 0};
         if (idx < 0) return x;
-        const int64_t k = idx / P.nf;
-        x.home = sidev ? (int)P.gj[idx] : (int)P.gi[idx];
-        if (!sidev) {
-            x.w = P.w[idx];
-            x.wre = P.re[idx];
-            x.wim = P.im[idx];
+        const double2 *r = P.rec + 3 * idx;
+        const double2 c2 = r[2];
+        const unsigned long long ij = (unsigned long long)__double_as_longlong(c2.y);
+        if (sidev) {
+            x.pos = c2.x;
+            x.home = (int)(uint32_t)(ij >> 32);
+        } else {
+            const double2 c0 = r[0], c1 = r[1];
+            x.pos = c0.x;
+            x.w = c0.y;
+            x.wre = c1.x;                              // already times w
+            x.wim = c1.y;
+            x.home = (int)(uint32_t)ij;
         }
-        x.pos = __dmul_rn(__dmul_rn(sidev ? P.v[k] : P.u[k], P.freq[idx % P.nf]), P.inv_freq);
         return x;
     };
     int64_t idx_next = load_idx(item.x + GT2_STAGE);
@@ -799,7 +826,7 @@ __global__ void __launch_bounds__(NSTREAM * 16) grid_tile2_kernel(GridParams P, 
         // stage: two threads per visibility (u side: the three column rows; v side: the row factors)
         if (q < n_here) {
             const int first = cur.home - lo - (sidev ? l0 : m0);   // region row / column of footprint slot 0
-            const double wre = cur.wre * cur.w, wim = cur.wim * cur.w;
+            const double wre = cur.wre, wim = cur.wim;
             double g[WIDTH];
 #pragma unroll
             for (int o = 0; o < WIDTH; o++) {
@@ -902,8 +929,15 @@ __global__ void __launch_bounds__(256) grid_reweight_kernel(GridParams P, const 
     int64_t q = ((int64_t)P.gj[idx] * P.G + P.gi[idx]) * P.nch + n;
     if (!P.spectral && q >= (int64_t)P.G * P.G) q = (int64_t)P.gj[idx] * P.G + P.gi[idx];
     const double b = binned[q];
-    if (f2) P.w[idx] = P.w[idx] / __dadd_rn(1.0, __dmul_rn(f2[n], b));
-    else P.w[idx] = P.w[idx] / b;
+    double w;
+    if (f2) w = P.w[idx] / __dadd_rn(1.0, __dmul_rn(f2[n], b));
+    else w = P.w[idx] / b;
+    P.w[idx] = w;
+    if (P.rec) {                                   // (visibilities off the grid returned above: their record stays zero)
+        double2 *r = P.rec + 3 * idx;
+        r[0].y = w;
+        r[1] = make_double2(P.re[idx] * w, P.im[idx] * w);
+    }
 }
 
 // Column sums with stride, stage 1: part[b][c] = sum over this block's rows of f(a[q*ncol + c]);
@@ -985,7 +1019,7 @@ __global__ void __launch_bounds__(256) grid_home_keys_kernel(GridParams P, uint3
     // coarse 8x8-cell tiles keep neighbouring visibilities together without a full-resolution sort
     const uint32_t tg = ((uint32_t)P.G + 7u) >> 3;
     const uint32_t chan = P.spectral ? (uint32_t)(idx % P.nf) : 0u;
-    keys[idx] = P.good[idx] ? (chan * tg * tg + (P.gj[idx] >> 3) * tg + (P.gi[idx] >> 3)) : KEY_DEAD;
+    keys[idx] = P.good[idx] ? (chan * tg * tg + (P.gj[idx] >> 3) * tg + (P.gi[idx] >> 3)) : chan * tg * tg;
     ids[idx] = (uint32_t)idx;
 }
 
@@ -1150,8 +1184,9 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
     }
 
     // ---- working arrays ----
-    const size_t work_bytes = (size_t)nvis * (sizeof(double) + 2 * sizeof(uint32_t) + 1) + 4 * 64 +
-                              (size_t)(3 * nf + 4) * sizeof(double) + sizeof(unsigned long long);
+    const size_t work_bytes = (size_t)nvis * (sizeof(double) + 2 * sizeof(uint32_t) + 1) + 6 * 64 +
+                              (size_t)(3 * nf + 4) * sizeof(double) + sizeof(unsigned long long) +
+                              (deterministic ? 0 : (size_t)nvis * 3 * sizeof(double2));
     PDSB_CHECK(c.stage_b.ensure(work_bytes + 256));
     char *wp = c.stage_b.as<char>();
     auto carve = [&](size_t bytes) {
@@ -1165,6 +1200,7 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
     double *small = (double *)carve((size_t)(3 * nf + 4) * sizeof(double));     // sumb2[nf], sumw[nf], f2[nf], wsum
     unsigned long long *d_nout = (unsigned long long *)carve(sizeof(unsigned long long));
     uint8_t *good = (uint8_t *)carve((size_t)nvis);
+    double2 *rec = deterministic ? nullptr : (double2 *)carve((size_t)nvis * 3 * sizeof(double2));
 
     double *o_re, *o_im, *o_w;
     PDSB_CHECK(c.stage_c.ensure((size_t)ncell * 4 * sizeof(double) + 256));
@@ -1175,7 +1211,7 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
 
     GridParams P;
     P.u = du; P.v = dv; P.freq = dfreq; P.re = dre; P.im = dim; P.w_in = dw;
-    P.w = w_work; P.gi = gi; P.gj = gj; P.good = good;
+    P.w = w_work; P.gi = gi; P.gj = gj; P.good = good; P.rec = rec;
     P.nuv = nuv; P.nf = nf; P.G = G; P.nch = nch; P.spectral = mode == PDSB_MODE_SPECTRALLINE;
     P.conv = convolution;
     P.binsize = binsize; P.inv_binsize = 1. / binsize; P.inv_freq = inv_freq;
@@ -1236,7 +1272,7 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
             uint32_t *ko, *vo;
             SortBufs sb{k0, v0, k1, v1, hist};
             const uint64_t nkeys = (uint64_t)tg * tg * (uint64_t)nch;
-            int tbits = bits_for(nkeys);
+            int tbits = bits_for(nkeys - 1);
             tbits = ((tbits + 7) / 8) * 8 > 32 ? 32 : ((tbits + 7) / 8) * 8;
             PDSB_CHECK(radix_sort(sb, nvis, tbits, &ko, &vo));
             const int side = 8 + (int)lo + (int)hi;
