@@ -214,17 +214,25 @@ int pdsb_freqcorrect(const double *u, const double *v, const double *freq, int64
                      double new_freq, int kind, double *out_u, double *out_v);
 
 /* ---- callers either side of the path --------------------------------------- */
-/* average(): the accumulation loop of libinterferometry.pyx:262-277.  The caller does the numpy
- * preamble exactly as the reference (weight clamp :179-181, uvdist/good filters :183-189,:254-260, bin
- * indices bin_i/bin_j [nuv] uint32 :221-248 - numpy.round / log10 rounding is part of the reference
- * result) and the normalisation/compaction afterwards (:279-311).  Outputs are the raw ordered sums
- * [gj, gi, nch] (gj = 1 for radial): sum u*w, sum v*w (NULL when radial), sum real*w, sum imag*w,
- * sum w, accumulated in the reference's (k, n) order: bit-exact. */
-int pdsb_bin_average(const uint32_t *bin_i, const uint32_t *bin_j, const double *u, const double *v,
-                     const double *real, const double *imag, const double *weights, int64_t nuv, int nf,
-                     int gi, int gj, int spectral, int radial, int in_kind,
-                     double *out_u, double *out_v, double *out_real, double *out_imag, double *out_weights,
-                     int out_kind);
+/* average() (libinterferometry.pyx:151-311), everything per element on the device: the weight clamp (:179-181),
+ * the uvdist != 0 and on-grid filters (:183-189, :250-260), the numpy.round bin indices (:221-248, numpy's operation
+ * order and float64 -> uint32 cast), the accumulation in the reference's (k, n) order (:262-277), the normalisation,
+ * the channel-weighted mean positions and the compaction of the non-empty cells in (j, i) order (:279-311).
+ * Every output is bit-identical to the reference.
+ *   HOST inputs: u, v, uvdist [nuv] (the object's own uvdist; ignored with mfs), freq [nf], real / imag / weights
+ *   [nuv, nf].  mfs != 0: rows become the (k, n) pairs at u freq[n] / mfs_freq with one channel each (freqcorrect,
+ *   :161-170).  radial: 0 = (u, v) grid of gridsize^2 cells of `binsize`; 1 = gridsize linear radial bins of
+ *   `binsize`; 2 = log radial bins - the caller passes log_uvdist = log10(uvdist) [nuv], log_min = log10(logmin) and
+ *   dtemp (:207-221) so that the one transcendental is the host libm's, as in the reference (not with mfs).
+ *   centres [gridsize] (HOST): the radial bin centres returned as u (:208-212); ignored for radial = 0.
+ *   HOST outputs with room for gridsize^2 (radial: gridsize) positions: out_u, out_v [n_out], out_real / out_imag /
+ *   out_weights [n_out, nch] with nch = nf (1 with mfs) when spectral, else 1.  n_dropped: rows with uvdist != 0
+ *   that fall off the grid (the reference prints its WARNING when this is non-zero, :256-257). */
+int pdsb_average(const double *u, const double *v, const double *uvdist, const double *log_uvdist, const double *freq,
+                 const double *real, const double *imag, const double *weights, int64_t nuv, int nf, int mfs,
+                 double mfs_freq, int gridsize, double binsize, int radial, double log_min, double dtemp,
+                 const double *centres, int spectral, double *out_u, double *out_v, double *out_real,
+                 double *out_imag, double *out_weights, int64_t *n_out, int64_t *n_dropped);
 /* center(): data * conj(point model at (x0, y0)), pdspy/interferometry/center.py:5-25 with
  * point_model of model.py:102-104 (incl. its literal 3.14159).  x0, y0 in radians. */
 int pdsb_center(const double *u, const double *v, const double *freq, const double *real, const double *imag,

@@ -70,8 +70,8 @@ SIGNATURES = {
                   ctypes.POINTER(_c_i64)],
     "pdsb_grid_normalise": [_P, _P, _P, _c_int, _c_int, _c_int],
     "pdsb_freqcorrect": [_P, _P, _P, _c_i64, _c_int, _c_dbl, _c_int, _P, _P],
-    "pdsb_bin_average": [_P, _P, _P, _P, _P, _P, _P, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
-                         _P, _P, _P, _P, _P, _c_int],
+    "pdsb_average": [_P, _P, _P, _P, _P, _P, _P, _P, _c_i64, _c_int, _c_int, _c_dbl, _c_int, _c_dbl, _c_int, _c_dbl, _c_dbl,
+                     _P, _c_int, _P, _P, _P, _P, _P, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)],
     "pdsb_center": [_P, _P, _P, _P, _P, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_int, _P, _P],
     "pdsb_set_grid_band": [_c_int, _c_int],
     "pdsb_sample_image_fft": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _P, _c_int],

@@ -1023,40 +1023,178 @@ __global__ void __launch_bounds__(256) grid_home_keys_kernel(GridParams P, uint3
     ids[idx] = (uint32_t)idx;
 }
 
-// ---- average(): nearest-cell binning with weighted mean positions (libinterferometry.pyx:262-277) ----
-__global__ void __launch_bounds__(256) avg_emit_keys_kernel(const uint32_t *__restrict__ bi,
-                                                            const uint32_t *__restrict__ bj, int64_t first,
-                                                            int64_t count, int nf, int gi, int nch, int spectral,
-                                                            uint32_t *keys, uint32_t *ids)
+// ---- average(): nearest-cell binning with weighted mean positions (libinterferometry.pyx:151-311) ----
+// Everything per element runs here: the weight clamp (:179-181), the uvdist != 0 and on-grid filters
+// (:183-189, :250-260), numpy.round bin indices (:221-248) with numpy's operation order and float64 -> uint32
+// cast, the ordered (k, n) accumulation (:262-277), the normalisation (:279-284), the channel-weighted mean
+// positions (:286-294) and the compaction of the non-empty cells (:296-311).
+struct AvgParams {
+    const double *u, *v, *uvdist, *log_uvdist, *freq, *re, *im, *w;
+    int64_t nuv;          // input rows
+    int nf;               // input channels
+    int mfs;              // rows are (k, n) pairs scaled to the mean frequency (freqcorrect, :161-170), one channel each
+    double mfs_inv_freq;
+    int64_t nrow;         // rows after mfs: nuv * nf or nuv
+    int nfe;              // channels per row after mfs: 1 or nf
+    int G, Gj, nch, spectral;
+    int radial;           // 0: (u, v) grid, 1: linear radial bins, 2: log radial bins
+    double binsize, half, log_min, dtemp;
+    uint32_t *row_cell;   // [nrow] j * G + i, or KEY_DEAD
+    double *row_u, *row_v;   // [nrow] (mfs only; otherwise u, v are read directly)
+};
+
+__global__ void __launch_bounds__(256) avg_prep_kernel(AvgParams P, unsigned long long *n_dropped)
+{
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= P.nrow) return;
+    double ur, vr, dist;
+    if (P.mfs) {
+        const double scale = __dmul_rn(P.freq[r % P.nf], P.mfs_inv_freq);       // data.freq * inv_freq  :598
+        ur = __dmul_rn(P.u[r / P.nf], scale);
+        vr = __dmul_rn(P.v[r / P.nf], scale);
+        dist = __dsqrt_rn(__dadd_rn(__dmul_rn(ur, ur), __dmul_rn(vr, vr)));     // Visibilities(): sqrt(u**2 + v**2)  :27
+        P.row_u[r] = ur;
+        P.row_v[r] = vr;
+    } else {
+        ur = P.u[r];
+        vr = P.v[r];
+        dist = P.uvdist[r];
+    }
+    uint32_t cell = KEY_DEAD;
+    if (dist != 0.0) {                                                          // good_data = uvdist != 0.0  :183
+        uint32_t i, j = 0u;
+        if (P.radial == 0) {
+            i = np_f64_to_u32(rint(__dadd_rn(__ddiv_rn(ur, P.binsize), P.half)));       // :243-248
+            j = np_f64_to_u32(rint(__dadd_rn(__ddiv_rn(vr, P.binsize), P.half)));
+        } else if (P.radial == 1) {
+            i = np_f64_to_u32(rint(__ddiv_rn(dist, P.binsize)));                // :225
+        } else {
+            // (log10(uvdist) - log10(logmin)) / dtemp - 0.5, log10(uvdist) from the host's libm  :221
+            i = np_f64_to_u32(rint(__dsub_rn(__ddiv_rn(__dsub_rn(P.log_uvdist[r], P.log_min), P.dtemp), 0.5)));
+        }
+        if (i < (uint32_t)P.G && j < (uint32_t)P.Gj) cell = j * (uint32_t)P.G + i;
+        else atomicAdd(n_dropped, 1ull);
+    }
+    P.row_cell[r] = cell;
+}
+
+__global__ void __launch_bounds__(256) avg_emit_keys_kernel(AvgParams P, int64_t first, int64_t count, uint32_t *keys,
+                                                            uint32_t *ids)
 {
     const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= count) return;
     const int64_t idx = first + t;
-    const int64_t k = idx / nf;
-    keys[t] = (bj[k] * (uint32_t)gi + bi[k]) * (uint32_t)nch + (spectral ? (uint32_t)(idx % nf) : 0u);
+    const uint32_t cell = P.row_cell[idx / P.nfe];
+    keys[t] = cell == KEY_DEAD ? KEY_DEAD : cell * (uint32_t)P.nch + (P.spectral ? (uint32_t)(idx % P.nfe) : 0u);
     ids[t] = (uint32_t)t;
 }
 
-// addends in sorted order: which = 0: (real*w, imag*w, w) ; which = 1: (u*w, v*w, w)
-__global__ void __launch_bounds__(256) avg_values_kernel(const double *__restrict__ u, const double *__restrict__ v,
-                                                         const double *__restrict__ re, const double *__restrict__ im,
-                                                         const double *__restrict__ w, int nf, int which, int64_t first,
+// addends in sorted order: which = 0: (real*w, imag*w, w) ; which = 1: (u*w, v*w, w), w clamped as :179-181
+__global__ void __launch_bounds__(256) avg_values_kernel(AvgParams P, int which, int64_t first,
                                                          const uint32_t *__restrict__ ids, int64_t ncontrib,
                                                          double *__restrict__ va, double *__restrict__ vb,
                                                          double *__restrict__ vw)
 {
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (p >= ncontrib) return;
-    const int64_t idx = first + ids[p];
-    const double ww = w[idx];
+    const int64_t idx = first + ids[p];               // element of the [nrow, nfe] view == element of [nuv, nf]
+    const double re = P.re[idx], im = P.im[idx];
+    double ww = P.w[idx];
+    ww = ww < 0 ? 0.0 : ww;
+    if (re == 0 && im == 0) ww = 0.0;
     if (which == 0) {
-        va[p] = __dmul_rn(re[idx], ww);
-        vb[p] = __dmul_rn(im[idx], ww);
+        va[p] = __dmul_rn(re, ww);
+        vb[p] = __dmul_rn(im, ww);
     } else {
-        va[p] = __dmul_rn(u[idx / nf], ww);
-        vb[p] = __dmul_rn(v[idx / nf], ww);
+        const int64_t r = idx / P.nfe;
+        va[p] = __dmul_rn(P.mfs ? P.row_u[r] : P.u[r], ww);
+        vb[p] = __dmul_rn(P.mfs ? P.row_v[r] : P.v[r], ww);
     }
     vw[p] = ww;
+}
+
+// numpy's pairwise sum of a contiguous run (what ndarray.sum(axis=-1) does per row): < 8 sequential, <= 128 in
+// eight interleaved partial sums, above that split in halves (multiples of 8)
+__device__ double np_pairwise_sum_dev(const double *a, int n)
+{
+    if (n < 8) {
+        double r = 0.;
+        for (int i = 0; i < n; i++) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int q = 0; q < 8; q++) r[q] = a[q];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int q = 0; q < 8; q++) r[q] = __dadd_rn(r[q], a[i + q]);
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(np_pairwise_sum_dev(a, n2), np_pairwise_sum_dev(a + n2, n - n2));
+}
+
+// :279-294 per position (j, i): normalise the channels that received weight, flag the position when any did,
+// and (2-D grid) form the channel-weighted mean position (new_u * new_weights).sum(axis=2) / new_weights.sum(axis=2).
+// m_u / m_v are overwritten with the products new_u * new_weights (scratch for the pairwise sums).
+__global__ void __launch_bounds__(128) avg_finish_kernel(int64_t npos, int nch, int radial, double *m_re, double *m_im,
+                                                         double *m_w, double *m_u, double *m_v, double *pos_u,
+                                                         double *pos_v, uint32_t *flag)
+{
+    const int64_t q = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (q >= npos) return;
+    bool any = false;
+    for (int c = 0; c < nch; c++) {
+        const int64_t e = q * nch + c;
+        const double w = m_w[e];
+        if (w != 0.0) {
+            any = true;
+            m_re[e] = __ddiv_rn(m_re[e], w);
+            m_im[e] = __ddiv_rn(m_im[e], w);
+            if (!radial) {
+                m_u[e] = __dmul_rn(__ddiv_rn(m_u[e], w), w);
+                m_v[e] = __dmul_rn(__ddiv_rn(m_v[e], w), w);
+            }
+        } else if (!radial) {
+            m_u[e] = __dmul_rn(m_u[e], w);
+            m_v[e] = __dmul_rn(m_v[e], w);
+        }
+    }
+    flag[q] = any ? 1u : 0u;
+    if (any && !radial) {
+        const double ws = np_pairwise_sum_dev(m_w + q * nch, nch);
+        pos_u[q] = __ddiv_rn(np_pairwise_sum_dev(m_u + q * nch, nch), ws);
+        pos_v[q] = __ddiv_rn(np_pairwise_sum_dev(m_v + q * nch, nch), ws);
+    }
+}
+
+// :296-311: the flagged positions, in row-major (j, i) order; `rank` is the exclusive scan of the flags
+__global__ void __launch_bounds__(256) avg_compact_kernel(int64_t npos, int nch, int radial, int G,
+                                                          const uint32_t *__restrict__ flag_rank,
+                                                          const uint32_t *__restrict__ flag,
+                                                          const double *__restrict__ m_re, const double *__restrict__ m_im,
+                                                          const double *__restrict__ m_w, const double *__restrict__ pos_u,
+                                                          const double *__restrict__ pos_v,
+                                                          const double *__restrict__ centres, double *o_u, double *o_v,
+                                                          double *o_re, double *o_im, double *o_w)
+{
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= npos * nch) return;
+    const int64_t q = t / nch;
+    const int c = (int)(t % nch);
+    if (!flag[q]) return;
+    const int64_t p = flag_rank[q];
+    o_re[p * nch + c] = m_re[t];
+    o_im[p * nch + c] = m_im[t];
+    o_w[p * nch + c] = m_w[t];
+    if (c == 0) {
+        o_u[p] = radial ? centres[q % G] : pos_u[q];
+        o_v[p] = radial ? 0.0 : pos_v[q];
+    }
 }
 
 // ---- center(): data * conj(point model)  (center.py:5-25, model.py:102-104) -------------------------
@@ -1461,47 +1599,83 @@ int pdsb_freqcorrect(const double *u, const double *v, const double *freq, int64
     return PDSB_OK;
 }
 
-int pdsb_bin_average(const uint32_t *bin_i, const uint32_t *bin_j, const double *u, const double *v,
-                     const double *real, const double *imag, const double *weights, int64_t nuv, int nf, int gi,
-                     int gj, int spectral, int radial, int in_kind, double *out_u, double *out_v, double *out_real,
-                     double *out_imag, double *out_weights, int out_kind)
+int pdsb_average(const double *u, const double *v, const double *uvdist, const double *log_uvdist, const double *freq,
+                 const double *real, const double *imag, const double *weights, int64_t nuv, int nf, int mfs,
+                 double mfs_freq, int gridsize, double binsize, int radial, double log_min, double dtemp,
+                 const double *centres, int spectral, double *out_u, double *out_v, double *out_real,
+                 double *out_imag, double *out_weights, int64_t *n_out, int64_t *n_dropped)
 {
     PDSB_CHECK(require_init());
     Context &c = ctx();
-    PDSB_REQUIRE(nuv >= 0 && nf > 0 && gi > 0 && gj > 0, "sizes");
-    PDSB_REQUIRE(out_real && out_imag && out_weights, "outputs");
-    PDSB_REQUIRE(radial || (out_u && out_v), "out_u/out_v");
-    const int nch = spectral ? nf : 1;
-    const int64_t ncell = (int64_t)gi * gj * nch;
+    PDSB_REQUIRE(nuv >= 0 && nf > 0 && gridsize > 0, "sizes");
+    PDSB_REQUIRE(radial >= 0 && radial <= 2, "radial");
+    PDSB_REQUIRE(out_u && out_v && out_real && out_imag && out_weights && n_out, "outputs");
+    PDSB_REQUIRE(radial == 2 || binsize > 0, "binsize");
+    PDSB_REQUIRE(radial != 2 || (log_uvdist && dtemp != 0 && !mfs), "log bins need log10(uvdist), dtemp, no mfs");
+    PDSB_REQUIRE(radial == 0 || centres, "radial bins need their centres");
+    PDSB_REQUIRE(!mfs || mfs_freq > 0, "mfs frequency");
+    const int G = gridsize, Gj = radial ? 1 : gridsize;
+    const int nfe = mfs ? 1 : nf;
+    const int64_t nrow = mfs ? nuv * nf : nuv;
+    const int nch = spectral ? nfe : 1;
+    const int64_t npos = (int64_t)G * Gj, ncell = npos * nch;
     PDSB_REQUIRE(ncell < (int64_t)KEY_DEAD, "grid too large");
     const int64_t nvis = nuv * nf;
     PDSB_REQUIRE(nvis < (int64_t)1 << 32, "nuv*nf must fit 32 bits");
-    // maps: re, im, w, u, v, scratch-w
-    PDSB_CHECK(c.stage_c.ensure((size_t)ncell * 6 * sizeof(double) + 256));
+    *n_out = 0;
+    if (n_dropped) *n_dropped = 0;
+
+    // maps: re, im, w, u, v, scratch-w, pos_u, pos_v (per position), flags + rank
+    const size_t map_bytes = (size_t)ncell * 6 * sizeof(double) + (size_t)npos * 2 * sizeof(double) +
+                             (size_t)npos * 2 * sizeof(uint32_t) + (size_t)(npos / SCAN_SEG + 16) * sizeof(uint32_t) + 1024;
+    PDSB_CHECK(c.stage_c.ensure(map_bytes));
     double *m_re = c.stage_c.as<double>(), *m_im = m_re + ncell, *m_w = m_im + ncell, *m_u = m_w + ncell,
-           *m_v = m_u + ncell, *m_w2 = m_v + ncell;
+           *m_v = m_u + ncell, *m_w2 = m_v + ncell, *pos_u = m_w2 + ncell, *pos_v = pos_u + npos;
+    uint32_t *flag = reinterpret_cast<uint32_t *>(pos_v + npos), *rank = flag + npos, *seg = rank + npos;
     PDSB_CUDA(cudaMemsetAsync(m_re, 0, (size_t)ncell * 6 * sizeof(double), c.stream));
+
+    // inputs (host) -> stage_a; per-row work arrays -> stage_b
+    AvgParams P;
+    {
+        const size_t nd = (size_t)2 * nuv + (radial == 2 ? nuv : 0) + (mfs ? 0 : nuv) + nf + (size_t)3 * nvis + (radial ? G : 0);
+        PDSB_CHECK(c.stage_a.ensure(nd * sizeof(double) + 64));
+        double *p = c.stage_a.as<double>();
+        auto put = [&](const double *src, size_t n, const double **dst) -> int {
+            *dst = p;
+            if (n == 0 || !src) return PDSB_OK;
+            PDSB_CUDA(cudaMemcpyAsync(p, src, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+            p += n;
+            return PDSB_OK;
+        };
+        if (nvis > 0) PDSB_REQUIRE(u && v && freq && real && imag && weights && (mfs || uvdist), "input arrays");
+        PDSB_CHECK(put(u, nuv, &P.u));
+        PDSB_CHECK(put(v, nuv, &P.v));
+        PDSB_CHECK(put(mfs ? nullptr : uvdist, nuv, &P.uvdist));
+        PDSB_CHECK(put(radial == 2 ? log_uvdist : nullptr, nuv, &P.log_uvdist));
+        PDSB_CHECK(put(freq, nf, &P.freq));
+        PDSB_CHECK(put(real, nvis, &P.re));
+        PDSB_CHECK(put(imag, nvis, &P.im));
+        PDSB_CHECK(put(weights, nvis, &P.w));
+        const double *dc = nullptr;
+        PDSB_CHECK(put(radial ? centres : nullptr, G, &dc));
+        centres = dc;
+    }
+    PDSB_CHECK(c.stage_b.ensure((size_t)nrow * (sizeof(uint32_t) + 2 * sizeof(double)) + 256));
+    P.row_u = c.stage_b.as<double>();
+    P.row_v = P.row_u + nrow;
+    P.row_cell = reinterpret_cast<uint32_t *>(P.row_v + nrow);
+    unsigned long long *d_drop = reinterpret_cast<unsigned long long *>(seg + (npos / SCAN_SEG + 8));
+    d_drop = reinterpret_cast<unsigned long long *>(((uintptr_t)d_drop + 7) & ~(uintptr_t)7);
+    PDSB_CUDA(cudaMemsetAsync(d_drop, 0, sizeof(unsigned long long), c.stream));
+    P.nuv = nuv; P.nf = nf; P.mfs = mfs; P.mfs_inv_freq = mfs ? 1. / mfs_freq : 0.0; P.nrow = nrow; P.nfe = nfe;
+    P.G = G; P.Gj = Gj; P.nch = nch; P.spectral = spectral; P.radial = radial;
+    P.binsize = binsize; P.half = (G % 2 == 0) ? G / 2. : (G - 1) / 2.; P.log_min = log_min; P.dtemp = dtemp;
+
     if (nvis > 0) {
-        PDSB_REQUIRE(bin_i && bin_j && u && v && real && imag && weights, "inputs");
-        const uint32_t *di = bin_i, *dj = bin_j;
-        const double *du = u, *dv = v, *dre = real, *dim = imag, *dw = weights;
-        if (in_kind == PDSB_HOST) {
-            const size_t bytes = (size_t)nuv * (2 * sizeof(uint32_t) + 2 * sizeof(double)) + (size_t)nvis * 3 * sizeof(double);
-            PDSB_CHECK(c.stage_a.ensure(bytes + 64));
-            double *p = c.stage_a.as<double>();
-            auto put = [&](const void *src, size_t nbytes, const void **dst) -> int {
-                PDSB_CUDA(cudaMemcpyAsync(p, src, nbytes, cudaMemcpyHostToDevice, c.stream));
-                *dst = p;
-                p += (nbytes + 7) / 8;
-                return PDSB_OK;
-            };
-            PDSB_CHECK(put(u, nuv * sizeof(double), (const void **)&du));
-            PDSB_CHECK(put(v, nuv * sizeof(double), (const void **)&dv));
-            PDSB_CHECK(put(real, nvis * sizeof(double), (const void **)&dre));
-            PDSB_CHECK(put(imag, nvis * sizeof(double), (const void **)&dim));
-            PDSB_CHECK(put(weights, nvis * sizeof(double), (const void **)&dw));
-            PDSB_CHECK(put(bin_i, nuv * sizeof(uint32_t), (const void **)&di));
-            PDSB_CHECK(put(bin_j, nuv * sizeof(uint32_t), (const void **)&dj));
+        {
+            LaunchScope ls("avg_prep");
+            avg_prep_kernel<<<ceil_div(nrow, 256), 256, 0, c.stream>>>(P, d_drop);
+            PDSB_CUDA(cudaGetLastError());
         }
         const int nbits = bits_for((uint64_t)ncell);
         const int sort_bits = ((nbits + 7) / 8) * 8 > 32 ? 32 : ((nbits + 7) / 8) * 8;
@@ -1515,7 +1689,7 @@ int pdsb_bin_average(const uint32_t *bin_i, const uint32_t *bin_j, const double 
             double *va = c.stage_e.as<double>(), *vb = va + n, *vw = vb + n;
             {
                 LaunchScope ls("avg_emit_keys");
-                avg_emit_keys_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(di, dj, first, n, nf, gi, nch, spectral, k0, v0);
+                avg_emit_keys_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(P, first, n, k0, v0);
                 PDSB_CUDA(cudaGetLastError());
             }
             uint32_t *ko, *vo;
@@ -1524,8 +1698,7 @@ int pdsb_bin_average(const uint32_t *bin_i, const uint32_t *bin_j, const double 
             for (int which = 0; which < (radial ? 1 : 2); which++) {
                 {
                     LaunchScope ls("avg_values");
-                    avg_values_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(du, dv, dre, dim, dw, nf, which, first, vo, n,
-                                                                              va, vb, vw);
+                    avg_values_kernel<<<ceil_div(n, 256), 256, 0, c.stream>>>(P, which, first, vo, n, va, vb, vw);
                     PDSB_CUDA(cudaGetLastError());
                 }
                 LaunchScope ls("grid_ordered_sum");
@@ -1536,14 +1709,43 @@ int pdsb_bin_average(const uint32_t *bin_i, const uint32_t *bin_j, const double 
             }
         }
     }
-    cudaMemcpyKind ok = out_kind == PDSB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    const size_t mb = (size_t)ncell * sizeof(double);
-    PDSB_CUDA(cudaMemcpyAsync(out_real, m_re, mb, ok, c.stream));
-    PDSB_CUDA(cudaMemcpyAsync(out_imag, m_im, mb, ok, c.stream));
-    PDSB_CUDA(cudaMemcpyAsync(out_weights, m_w, mb, ok, c.stream));
-    if (out_u) PDSB_CUDA(cudaMemcpyAsync(out_u, m_u, mb, ok, c.stream));
-    if (out_v) PDSB_CUDA(cudaMemcpyAsync(out_v, m_v, mb, ok, c.stream));
-    if (out_kind == PDSB_HOST) PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    {
+        LaunchScope ls("avg_finish");
+        avg_finish_kernel<<<ceil_div(npos, 128), 128, 0, c.stream>>>(npos, nch, radial ? 1 : 0, m_re, m_im, m_w, m_u, m_v,
+                                                                     pos_u, pos_v, flag);
+        PDSB_CUDA(cudaMemcpyAsync(rank, flag, (size_t)npos * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+        const int nseg = ceil_div(npos, SCAN_SEG);
+        rs_scan_seg_kernel<<<nseg, 1024, 0, c.stream>>>(rank, npos, seg);
+        rs_scan_totals_kernel<<<1, 1024, 0, c.stream>>>(seg, nseg);
+        rs_scan_add_kernel<<<nseg, 1024, 0, c.stream>>>(rank, npos, seg);
+        PDSB_CUDA(cudaGetLastError());
+    }
+    uint32_t last[2] = {0, 0};
+    unsigned long long hdrop = 0;
+    PDSB_CUDA(cudaMemcpyAsync(&last[0], rank + npos - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(&last[1], flag + npos - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(&hdrop, d_drop, sizeof(hdrop), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    const int64_t ngood = (int64_t)last[0] + last[1];
+    *n_out = ngood;
+    if (n_dropped) *n_dropped = (int64_t)hdrop;
+    if (ngood == 0) return PDSB_OK;
+    // compact into the sort scratch (free now), then to the caller's host arrays
+    PDSB_CHECK(c.stage_e.ensure((size_t)ngood * (2 + 3 * nch) * sizeof(double)));
+    double *o_u = c.stage_e.as<double>(), *o_v = o_u + ngood, *o_re = o_v + ngood, *o_im = o_re + ngood * nch,
+           *o_w = o_im + ngood * nch;
+    {
+        LaunchScope ls("avg_compact");
+        avg_compact_kernel<<<ceil_div(ncell, 256), 256, 0, c.stream>>>(npos, nch, radial ? 1 : 0, G, rank, flag, m_re, m_im, m_w,
+                                                                      pos_u, pos_v, centres, o_u, o_v, o_re, o_im, o_w);
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CUDA(cudaMemcpyAsync(out_u, o_u, (size_t)ngood * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(out_v, o_v, (size_t)ngood * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(out_real, o_re, (size_t)ngood * nch * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(out_imag, o_im, (size_t)ngood * nch * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(out_weights, o_w, (size_t)ngood * nch * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaStreamSynchronize(c.stream));
     return PDSB_OK;
 }
 
