@@ -204,6 +204,19 @@ int pdsb_grid(const double *u, const double *v, const double *freq,
  * the bands are then summed (adding exact zeros) and normalised with pdsb_grid_normalise.  (0, 0) lifts
  * the restriction. */
 int pdsb_set_grid_band(int row_lo, int row_hi);
+/* Re-weighting (uniform / superuniform / robust, :429-485) when the data or the output are split over processes.
+ * pdsb_grid_weights_map: the first half - box sums of the clamped weights over +-npixels cells (superuniform: 3)
+ * around every home cell into binned_dev [gridsize^2 * nch] (device), and the per-channel sums of the clamped
+ * weights into sumw_host [nf]; honours pdsb_set_grid_band.  with_ones = 0: raw sums (data split over the ranks:
+ * the caller all-reduces map and sums and adds the ones of :430); with_ones = 1: the rows of the band start at 1.0
+ * and the sums are added in (k, n) order on top, exactly as on one GPU (output rows split over the ranks: the
+ * all-reduce adds exact zeros).  The finished map goes back through pdsb_set_grid_reweight (NULL resets); while
+ * set, pdsb_grid with a re-weighting scheme skips its own box sums and uses the map (and, robust, the sums). */
+int pdsb_grid_weights_map(const double *u, const double *v, const double *freq, const double *real, const double *imag,
+                          const double *weights, int64_t nuv, int nf, int in_kind, int gridsize, double binsize,
+                          const double *uu, const double *vv, int weighting, int npixels, int mode, int deterministic,
+                          int with_ones, double *binned_dev, double *sumw_host, int64_t *n_outside);
+int pdsb_set_grid_reweight(const double *binned_dev, int64_t ncell, const double *sumw_host, int nf);
 /* Multi-GPU gridding (throughput mode): every rank grids its share of the
  * visibilities with imaging = 2 (raw sums, no normalisation) into device maps, the maps are summed
  * over ranks (NCCL all-reduce), then this applies the :525-533 normalisation on the device maps. */

@@ -74,6 +74,9 @@ SIGNATURES = {
                      _P, _c_int, _P, _P, _P, _P, _P, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)],
     "pdsb_center": [_P, _P, _P, _P, _P, _c_i64, _c_int, _c_dbl, _c_dbl, _c_dbl, _c_int, _P, _P],
     "pdsb_set_grid_band": [_c_int, _c_int],
+    "pdsb_grid_weights_map": [_P, _P, _P, _P, _P, _P, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _P, _P, _c_int, _c_int, _c_int,
+                              _c_int, _c_int, _P, _P, ctypes.POINTER(_c_i64)],
+    "pdsb_set_grid_reweight": [_P, _c_i64, _P, _c_int],
     "pdsb_sample_image_fft": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _P, _c_int],
     "pdsb_loglike_fft": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P],
     "pdsb_regrid_linear": [_P, _c_i64, _P, _P, _c_i64, _c_int, _c_dbl, _c_int, _P],

@@ -68,6 +68,9 @@ struct Context {
     int dft_variant = 0;
     int dft_split = 0;
     int grid_row_lo = 0, grid_row_hi = 0;      // pdsb_set_grid_band: output rows this process accumulates (0, 0 = all)
+    const double *grid_ext_binned = nullptr;   // pdsb_set_grid_reweight: binned weight map reduced over the ranks (device)
+    int64_t grid_ext_ncell = 0;
+    std::vector<double> grid_ext_sumw;         //   and the per-channel weight sums
     // scratch
     Scratch img64, folded, partial, red, stage_a, stage_b, stage_c, stage_d, stage_e;
     Scratch small_dev;     // tiny per-call device arrays (channel scale factors)

@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(256) grid_emit_keys_kernel(GridParams P, int m
         for (int f = f0; f < f1; f++) {
             uint32_t l, m;
             if (!slot_cell(P.gi[idx], P.gj[idx], f, lo, hi, P.G, &l, &m)) continue;
-            bool live = true;
-            if (mode == 0) live = l >= P.row_lo && l < P.row_hi && conv_live(P, idx / P.nf, n, l, m);
+            bool live = l >= P.row_lo && l < P.row_hi;                   // (the whole grid unless pdsb_set_grid_band)
+            if (live && mode == 0) live = conv_live(P, idx / P.nf, n, l, m);
             if (live) {
                 key = (l * (uint32_t)P.G + m) * (uint32_t)P.nch + (P.spectral ? (uint32_t)n : 0u);
                 break;
@@ -1233,11 +1233,15 @@ using namespace pdsb;
 
 extern "C" {
 
-int pdsb_grid(const double *u, const double *v, const double *freq, const double *real, const double *imag,
-              const double *weights, int64_t nuv, int nf, int in_kind, int gridsize, double binsize,
-              const double *uu, const double *vv, int convolution, int weighting, double robust, int npixels,
-              int mode, int imaging, int deterministic, double *out_real, double *out_imag, double *out_weights,
-              uint32_t *out_i, uint32_t *out_j, double *out_wmod, int out_kind, int64_t *n_outside)
+// weights_phase != 0: only the first half of the re-weighting (:429-461) - the box sums of the clamped weights
+// (WITHOUT the initial ones) into binned_out [G*G*nch] (device) and the per-channel weight sums into
+// sumw_out [nf] (host) - for the multi-GPU paths, which reduce both over the ranks before the second half.
+static int grid_impl(const double *u, const double *v, const double *freq, const double *real, const double *imag,
+                     const double *weights, int64_t nuv, int nf, int in_kind, int gridsize, double binsize,
+                     const double *uu, const double *vv, int convolution, int weighting, double robust, int npixels,
+                     int mode, int imaging, int deterministic, double *out_real, double *out_imag, double *out_weights,
+                     uint32_t *out_i, uint32_t *out_j, double *out_wmod, int out_kind, int64_t *n_outside,
+                     int weights_phase, double *binned_out, double *sumw_out)
 {
     PDSB_CHECK(require_init());
     Context &c = ctx();
@@ -1361,9 +1365,12 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
 
     P.row_lo = 0;
     P.row_hi = (uint32_t)G;
+    const bool ext_weights = !weights_phase && c.grid_ext_binned != nullptr;
     if (c.grid_row_hi > 0) {           // pdsb_set_grid_band: this process owns a band of output rows
-        PDSB_REQUIRE(deterministic && weighting == PDSB_WT_NATURAL && imaging == 2,
-                     "a row band needs the ordered mode, natural weighting and raw sums (imaging = 2)");
+        PDSB_REQUIRE(deterministic && (weights_phase || imaging == 2),
+                     "a row band needs the ordered mode and raw sums (imaging = 2)");
+        PDSB_REQUIRE(weights_phase || weighting == PDSB_WT_NATURAL || ext_weights,
+                     "re-weighting inside a row band needs the reduced weight map (pdsb_set_grid_reweight)");
         PDSB_REQUIRE(c.grid_row_lo >= 0 && c.grid_row_lo < c.grid_row_hi && c.grid_row_hi <= G, "row band");
         P.row_lo = (uint32_t)c.grid_row_lo;
         P.row_hi = (uint32_t)c.grid_row_hi;
@@ -1502,20 +1509,54 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
         return PDSB_OK;
     };
 
-    // ---- optional re-weighting (:429-485) ----
-    if (weighting != PDSB_WT_NATURAL) {
-        uint32_t npix = weighting == PDSB_WT_SUPERUNIFORM ? 3u : (uint32_t)npixels;
-        {
+    if (weights_phase) {
+        PDSB_REQUIRE(weighting != PDSB_WT_NATURAL && binned_out && sumw_out, "weights phase arguments");
+        const uint32_t npix = weighting == PDSB_WT_SUPERUNIFORM ? 3u : (uint32_t)npixels;
+        PDSB_CUDA(cudaMemsetAsync(binned, 0, (size_t)ncell * sizeof(double), c.stream));
+        if (weights_phase == 2) {
+            // the ones of :430 in the rows this process owns: the ordered sums then start from 1.0 exactly as on
+            // one GPU, and the all-reduce over the ranks adds exact zeros
+            const int64_t b0 = (int64_t)P.row_lo * G * nch, b1 = (int64_t)P.row_hi * G * nch;
             LaunchScope ls("grid_fill");
-            fill_kernel<<<ceil_div(ncell, 256), 256, 0, c.stream>>>(binned, ncell, 1.0);     // numpy.ones :430
+            fill_kernel<<<ceil_div(b1 - b0, 256), 256, 0, c.stream>>>(binned + b0, b1 - b0, 1.0);
             PDSB_CUDA(cudaGetLastError());
         }
         PDSB_CHECK(scatter(1, npix, npix, nullptr, nullptr, binned));
+        PDSB_CHECK(sum_columns(w_work, nuv, nf, 0, small + nf));
+        PDSB_CUDA(cudaMemcpyAsync(binned_out, binned, (size_t)ncell * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(sumw_out, small + nf, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        unsigned long long hn = 0;
+        PDSB_CUDA(cudaMemcpyAsync(&hn, d_nout, sizeof(hn), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+        if (n_outside) *n_outside = (int64_t)hn;
+        return PDSB_OK;
+    }
+
+    // ---- optional re-weighting (:429-485) ----
+    if (weighting != PDSB_WT_NATURAL) {
+        uint32_t npix = weighting == PDSB_WT_SUPERUNIFORM ? 3u : (uint32_t)npixels;
+        if (ext_weights) {
+            // multi-GPU: the box sums were made per rank (weights phase), reduced, and handed back with the ones added
+            PDSB_REQUIRE(c.grid_ext_ncell == ncell && (int)c.grid_ext_sumw.size() == nf, "pdsb_set_grid_reweight sizes");
+            PDSB_CUDA(cudaMemcpyAsync(binned, c.grid_ext_binned, (size_t)ncell * sizeof(double), cudaMemcpyDeviceToDevice,
+                                      c.stream));
+        } else {
+            {
+                LaunchScope ls("grid_fill");
+                fill_kernel<<<ceil_div(ncell, 256), 256, 0, c.stream>>>(binned, ncell, 1.0);     // numpy.ones :430
+                PDSB_CUDA(cudaGetLastError());
+            }
+            PDSB_CHECK(scatter(1, npix, npix, nullptr, nullptr, binned));
+        }
         const double *f2 = nullptr;
         if (weighting == PDSB_WT_ROBUST) {
             double *sumb2 = small, *sumw = small + nf, *f2w = small + 2 * nf;
             PDSB_CHECK(sum_columns(binned, (int64_t)G * G, nch, 1, sumb2));
-            PDSB_CHECK(sum_columns(w_work, nuv, nf, 0, sumw));
+            if (ext_weights)
+                PDSB_CUDA(cudaMemcpyAsync(sumw, c.grid_ext_sumw.data(), (size_t)nf * sizeof(double), cudaMemcpyHostToDevice,
+                                          c.stream));
+            else
+                PDSB_CHECK(sum_columns(w_work, nuv, nf, 0, sumw));
             PDSB_REQUIRE(nf <= 1024, "robust weighting supports at most 1024 channels");
             const double ra = 5 * pow(10.0, -robust);       // host libm, as Python's 5*10**(-robust)
             robust_f2_kernel<<<1, 1024, 0, c.stream>>>(sumb2, sumw, nf, P.spectral, ra * ra, f2w);
@@ -1563,6 +1604,43 @@ int pdsb_grid(const double *u, const double *v, const double *freq, const double
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
         if (n_outside) *n_outside = (int64_t)hn;
     }
+    return PDSB_OK;
+}
+
+int pdsb_grid(const double *u, const double *v, const double *freq, const double *real, const double *imag,
+              const double *weights, int64_t nuv, int nf, int in_kind, int gridsize, double binsize,
+              const double *uu, const double *vv, int convolution, int weighting, double robust, int npixels,
+              int mode, int imaging, int deterministic, double *out_real, double *out_imag, double *out_weights,
+              uint32_t *out_i, uint32_t *out_j, double *out_wmod, int out_kind, int64_t *n_outside)
+{
+    return grid_impl(u, v, freq, real, imag, weights, nuv, nf, in_kind, gridsize, binsize, uu, vv, convolution, weighting,
+                     robust, npixels, mode, imaging, deterministic, out_real, out_imag, out_weights, out_i, out_j, out_wmod,
+                     out_kind, n_outside, 0, nullptr, nullptr);
+}
+
+int pdsb_grid_weights_map(const double *u, const double *v, const double *freq, const double *real, const double *imag,
+                          const double *weights, int64_t nuv, int nf, int in_kind, int gridsize, double binsize,
+                          const double *uu, const double *vv, int weighting, int npixels, int mode, int deterministic,
+                          int with_ones, double *binned_dev, double *sumw_host, int64_t *n_outside)
+{
+    return grid_impl(u, v, freq, real, imag, weights, nuv, nf, in_kind, gridsize, binsize, uu, vv, PDSB_CONV_PILLBOX,
+                     weighting, 0.0, npixels, mode, 2, deterministic, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     PDSB_DEVICE, n_outside, with_ones ? 2 : 1, binned_dev, sumw_host);
+}
+
+int pdsb_set_grid_reweight(const double *binned_dev, int64_t ncell, const double *sumw_host, int nf)
+{
+    Context &c = ctx();
+    if (!binned_dev) {
+        c.grid_ext_binned = nullptr;
+        c.grid_ext_ncell = 0;
+        c.grid_ext_sumw.clear();
+        return PDSB_OK;
+    }
+    PDSB_REQUIRE(ncell > 0 && nf > 0 && sumw_host, "pdsb_set_grid_reweight arguments");
+    c.grid_ext_binned = binned_dev;
+    c.grid_ext_ncell = ncell;
+    c.grid_ext_sumw.assign(sumw_host, sumw_host + nf);
     return PDSB_OK;
 }
 

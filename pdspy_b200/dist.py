@@ -165,12 +165,39 @@ class ShardedLikelihood:
         return combine_lnlike(self.chi2_device(image, ny, nx, kind, dxy, dRA, dDec), self.group)
 
 
-def sharded_grid(data_shard, gridsize=256, binsize=2000.0, convolution="pillbox", imaging=False, mode="continuum",
-                 group=None):
+def _cell_centres(G, binsize):
+    """numpy.linspace of libinterferometry.pyx:370-381."""
+    if G % 2 == 0:
+        uu = np.linspace(-G * binsize / 2, (G / 2 - 1) * binsize, G)
+    else:
+        uu = np.linspace(-(G - 1) * binsize / 2, (G - 1) * binsize / 2, G)
+    return uu, uu.copy()
+
+
+def _reduced_weight_map(L, _lib, torch, dist, multi, group, arrays, nuv, nf, G, binsize, uu, vv, weighting, npixels, mode,
+                        deterministic, nch):
+    """First half of the re-weighting (libinterferometry.pyx:429-461) over all ranks: every rank box-sums the clamped
+    weights of ITS visibilities (pdsb_grid_weights_map; inside a row band when pdsb_set_grid_band is set), the maps
+    and the per-channel weight sums are all-reduced, and the ones of :430 are added.  Returns (device map, sumw)."""
+    import ctypes
+    binned = torch.zeros(G * G * nch, dtype=torch.float64, device="cuda")
+    sumw = np.zeros(nf)
+    n_out = ctypes.c_int64(0)
+    u, v, freq, re, im, w = arrays
+    _lib.check(L.pdsb_grid_weights_map(_lib.ptr(u), _lib.ptr(v), _lib.ptr(freq), _lib.ptr(re), _lib.ptr(im), _lib.ptr(w),
+                                       nuv, nf, _lib.HOST, G, float(binsize), _lib.ptr(uu), _lib.ptr(vv),
+                                       _lib.WEIGHTING[weighting], int(npixels), _lib.MODE[mode], 1 if deterministic else 0,
+                                       0, binned.data_ptr(), _lib.ptr(sumw), ctypes.byref(n_out)))
+    return binned, sumw
+
+
+def sharded_grid(data_shard, gridsize=256, binsize=2000.0, convolution="pillbox", imaging=False, weighting="natural",
+                 robust=2, npixels=0, mode="continuum", group=None):
     """grid() of a data set whose visibilities are split over the ranks (SURVEY.md section 8e,
     throughput mode): each rank grids its shard into private raw-sum maps on its GPU (fast mode), the
-    three maps are all-reduced over NCCL, then normalised on the device.  Natural weighting only
-    (uniform / robust weights need the global binned-weight map first).  Every rank returns the full
+    three maps are all-reduced over NCCL, then normalised on the device.  With uniform / superuniform / robust
+    weighting the binned-weight map (and, robust, the weight sums) are made per shard and all-reduced first
+    (libinterferometry.pyx:429-485 needs them for the whole data set).  Every rank returns the full
     gridded Visibilities.  Summation order differs from the serial reference: 1e-15-level differences,
     like the single-GPU fast mode.  The mean frequency must be the same on every rank (it is: the
     shards share `freq`)."""
@@ -182,26 +209,39 @@ def sharded_grid(data_shard, gridsize=256, binsize=2000.0, convolution="pillbox"
     from .interferometry.grid import _WARNING
     L = _lib.lib()
     _lib.check(L.pdsb_set_stream(torch.cuda.current_stream().cuda_stream))
-    u, v, freq = data_shard.u, data_shard.v, data_shard.freq
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    u, v, freq = _lib.f64(data_shard.u), _lib.f64(data_shard.v), _lib.f64(data_shard.freq)
+    re, im, w = _lib.f64(data_shard.real), _lib.f64(data_shard.imag), _lib.f64(data_shard.weights)
     nuv, nf = u.size, freq.size
     nch = 1 if mode == "continuum" else nf
     G = int(gridsize)
-    if G % 2 == 0:                                   # numpy.linspace of libinterferometry.pyx:370-381
-        uu = np.linspace(-G * binsize / 2, (G / 2 - 1) * binsize, G)
-    else:
-        uu = np.linspace(-(G - 1) * binsize / 2, (G - 1) * binsize / 2, G)
-    vv = uu.copy()
+    uu, vv = _cell_centres(G, binsize)
     maps = torch.zeros((3, G * G, nch), dtype=torch.float64, device="cuda")
     n_out = ctypes.c_int64(0)
-    _lib.check(L.pdsb_grid(_lib.ptr(_lib.f64(u)), _lib.ptr(_lib.f64(v)), _lib.ptr(_lib.f64(freq)),
-                           _lib.ptr(_lib.f64(data_shard.real)), _lib.ptr(_lib.f64(data_shard.imag)),
-                           _lib.ptr(_lib.f64(data_shard.weights)), nuv, nf, _lib.HOST, G, float(binsize),
-                           _lib.ptr(uu), _lib.ptr(vv), _lib.CONV[convolution], 0, 2.0, 0, _lib.MODE[mode],
-                           2, 0,                         # imaging = 2: raw sums; fast mode
-                           maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), None, None, None,
-                           _lib.DEVICE, ctypes.byref(n_out)))
+    binned = None
+    if weighting != "natural":
+        binned, sumw = _reduced_weight_map(L, _lib, torch, dist, multi, group, (u, v, freq, re, im, w), nuv, nf, G, binsize,
+                                           uu, vv, weighting, npixels, mode, False, nch)
+        sw = torch.from_numpy(sumw).cuda()
+        if multi:
+            dist.all_reduce(binned, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(sw, op=dist.ReduceOp.SUM, group=group)
+        binned += 1.0                                       # numpy.ones :430
+        sumw = np.ascontiguousarray(sw.cpu().numpy())
+        torch.cuda.synchronize()
+        _lib.check(L.pdsb_set_grid_reweight(binned.data_ptr(), binned.numel(), _lib.ptr(sumw), nf))
+    try:
+        _lib.check(L.pdsb_grid(_lib.ptr(u), _lib.ptr(v), _lib.ptr(freq), _lib.ptr(re), _lib.ptr(im), _lib.ptr(w), nuv, nf,
+                               _lib.HOST, G, float(binsize), _lib.ptr(uu), _lib.ptr(vv), _lib.CONV[convolution],
+                               _lib.WEIGHTING[weighting], float(robust), int(npixels), _lib.MODE[mode],
+                               2, 0,                         # imaging = 2: raw sums; fast mode
+                               maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), None, None, None,
+                               _lib.DEVICE, ctypes.byref(n_out)))
+    finally:
+        if binned is not None:
+            _lib.check(L.pdsb_set_grid_reweight(None, 0, None, 0))
     nout = torch.tensor([n_out.value], dtype=torch.int64, device="cuda")
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if multi:
         dist.all_reduce(maps, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(nout, op=dist.ReduceOp.SUM, group=group)
     _lib.check(L.pdsb_grid_normalise(maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), G, nch,
@@ -231,18 +271,25 @@ def band_rows(u, v, freq, gridsize, binsize, row_lo, row_hi, lo, hi, include_out
     return np.flatnonzero(sel)
 
 
-def banded_grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", imaging=False, mode="continuum",
-                group=None, bands=None):
+def banded_grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", imaging=False, weighting="natural", robust=2,
+                npixels=0, mode="continuum", group=None, bands=None, weight_map=None):
     """grid() over several GPUs with results BIT-IDENTICAL to the single-GPU ordered mode (SURVEY.md section
     8e (ii)).  Every rank sees the whole data set and owns a band of gridsize/world output rows: it streams
     only the visibilities whose footprint can reach its band (in their original order, which is what fixes
     the rounding), accumulates that band in the reference's (k, n) order (pdsb_set_grid_band + ordered
     pdsb_grid with raw sums), the bands are summed over NCCL (every cell is non-zero on one rank only, so
-    the sum adds exact zeros) and normalised on the device.  Natural weighting only.
+    the sum adds exact zeros) and normalised on the device.
+
+    Uniform / superuniform / robust weighting (libinterferometry.pyx:429-485): the binned-weight map is made the
+    same way first - every rank box-sums the weights into ITS band of the map in (k, n) order from the visibilities
+    within +-npixels rows of it, the bands are all-reduced (exact zeros elsewhere) - so every rank holds the map
+    the single-GPU run computes, bit for bit; robust's two global sums are then taken over the full map and the
+    full weight array exactly as on one GPU.
 
     bands=(index, count) computes ONE band without a process group and returns (raw device maps [3, G*G,
     nch], n_outside) for the caller to sum over all indices and pass to pdsb_grid_normalise (this is how
-    the single-GPU test emulates N ranks); normally leave it None."""
+    the single-GPU test emulates N ranks); with a re-weighting scheme `weight_map` must then be the summed
+    result of banded_weight_map over all bands.  Normally leave both None."""
     import ctypes
     import torch
     import torch.distributed as dist
@@ -262,28 +309,39 @@ def banded_grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", imagi
     nf = freq.size
     nch = 1 if mode == "continuum" else nf
     G = int(gridsize)
-    if G % 2 == 0:                                   # numpy.linspace of libinterferometry.pyx:370-381
-        uu = np.linspace(-G * binsize / 2, (G / 2 - 1) * binsize, G)
-    else:
-        uu = np.linspace(-(G - 1) * binsize / 2, (G - 1) * binsize / 2, G)
-    vv = uu.copy()
+    uu, vv = _cell_centres(G, binsize)
     row_lo, row_hi = shard_bounds(G, rank, world)
     lo, hi = (2, 3) if convolution == "expsinc" else (1, 1)          # nmin, nmax of :405-417
+    binned = sumw = None
+    if weighting != "natural":
+        if bands is not None:
+            if weight_map is None:
+                raise ValueError("bands=... with re-weighting needs weight_map (sum of banded_weight_map over the bands)")
+            binned, sumw = weight_map
+        else:
+            binned, sumw = banded_weight_map(data, G, binsize, weighting, npixels, mode, (rank, world))
+            if multi:
+                dist.all_reduce(binned, op=dist.ReduceOp.SUM, group=group)
     maps = torch.zeros((3, G * G, nch), dtype=torch.float64, device="cuda")
     n_out = ctypes.c_int64(0)
     if row_hi > row_lo:
         rows = band_rows(u, v, freq, G, binsize, row_lo, row_hi, lo, hi, include_outside=(rank == 0))
         take = (lambda a: np.ascontiguousarray(_lib.f64(a)[rows]))
         _lib.check(L.pdsb_set_grid_band(row_lo, row_hi))
+        if binned is not None:
+            torch.cuda.synchronize()
+            _lib.check(L.pdsb_set_grid_reweight(binned.data_ptr(), binned.numel(), _lib.ptr(sumw), nf))
         try:
             _lib.check(L.pdsb_grid(_lib.ptr(take(u)), _lib.ptr(take(v)), _lib.ptr(freq), _lib.ptr(take(data.real)),
                                    _lib.ptr(take(data.imag)), _lib.ptr(take(data.weights)), rows.size, nf, _lib.HOST,
-                                   G, float(binsize), _lib.ptr(uu), _lib.ptr(vv), _lib.CONV[convolution], 0, 2.0, 0,
+                                   G, float(binsize), _lib.ptr(uu), _lib.ptr(vv), _lib.CONV[convolution],
+                                   _lib.WEIGHTING[weighting], float(robust), int(npixels),
                                    _lib.MODE[mode], 2, 1,            # imaging = 2: raw sums; ordered mode
                                    maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), None, None, None,
                                    _lib.DEVICE, ctypes.byref(n_out)))
         finally:
             _lib.check(L.pdsb_set_grid_band(0, 0))
+            _lib.check(L.pdsb_set_grid_reweight(None, 0, None, 0))
     if bands is not None:
         return maps, n_out.value                     # raw band maps on the device, for the caller to combine
     nout = torch.tensor([n_out.value], dtype=torch.int64, device="cuda")
@@ -299,3 +357,35 @@ def banded_grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", imagi
     out_freq = np.array([freq.sum() / freq.size]) if mode == "continuum" else freq
     return Visibilities(new_u.reshape(G * G), new_v.reshape(G * G), out_freq, np.ascontiguousarray(host[0]),
                         np.ascontiguousarray(host[1]), np.ascontiguousarray(host[2]))
+
+
+def banded_weight_map(data, gridsize, binsize, weighting, npixels, mode, band):
+    """This band's rows of the binned-weight map (the ones of :430 plus the box sums added in the reference's (k, n)
+    order; exact zeros outside the band), and the per-channel sums of the clamped weights over the WHOLE data set
+    (the same on every rank, and the same arithmetic as the single-GPU run).  band = (index, count)."""
+    import ctypes
+    import torch
+    from . import _lib
+    L = _lib.lib()
+    rank, world = band
+    u, v, freq = _lib.f64(data.u), _lib.f64(data.v), _lib.f64(data.freq)
+    re, im, w = _lib.f64(data.real), _lib.f64(data.imag), _lib.f64(data.weights)
+    nuv, nf = u.size, freq.size
+    nch = 1 if mode == "continuum" else nf
+    G = int(gridsize)
+    uu, vv = _cell_centres(G, binsize)
+    row_lo, row_hi = shard_bounds(G, rank, world)
+    binned = torch.zeros(G * G * nch, dtype=torch.float64, device="cuda")
+    sumw = np.zeros(nf)
+    if row_hi > row_lo:
+        _lib.check(L.pdsb_set_grid_band(row_lo, row_hi))
+    try:
+        n_out = ctypes.c_int64(0)
+        if row_hi > row_lo:
+            _lib.check(L.pdsb_grid_weights_map(_lib.ptr(u), _lib.ptr(v), _lib.ptr(freq), _lib.ptr(re), _lib.ptr(im),
+                                               _lib.ptr(w), nuv, nf, _lib.HOST, G, float(binsize), _lib.ptr(uu),
+                                               _lib.ptr(vv), _lib.WEIGHTING[weighting], int(npixels), _lib.MODE[mode], 1,
+                                               1, binned.data_ptr(), _lib.ptr(sumw), ctypes.byref(n_out)))
+    finally:
+        _lib.check(L.pdsb_set_grid_band(0, 0))
+    return binned, sumw
