@@ -74,6 +74,8 @@ struct Context {
     // scratch
     Scratch img64, folded, partial, red, stage_a, stage_b, stage_c, stage_d, stage_e;
     Scratch small_dev;     // tiny per-call device arrays (channel scale factors)
+    Scratch fft_fb;        // invert(), sizes that are not a power of two: transform of Bluestein's chirp, for size fft_fb_n
+    int fft_fb_n = 0;
     Scratch mma_ws;        // tensor-core kernel: per-round lattice quanta and per-plane unscale factors
 };
 

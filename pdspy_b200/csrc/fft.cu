@@ -3,7 +3,9 @@
 //   convolve = fftshift(ifft2(ifftshift(conv_func(u, v)))).real
 //   image[:, :, i] = (im / convolve)[:, ::-1]
 // Hand-written fp64 radix-2 FFT: one CTA per row held in shared memory (n <= 4096), two passes with
-// the (i)fftshift index rotations and the transpose fused into the loads/stores.
+// the (i)fftshift index rotations and the transpose fused into the loads/stores.  Sizes that are not a
+// power of two (the reference takes any imsize: scipy's ifft2) go through Bluestein's chirp-z form of the
+// same row transform on the next power of two >= 2n - 1 (bluestein_rows_kernel).
 #include "common.cuh"
 
 namespace pdsb {
@@ -66,6 +68,112 @@ __global__ void __launch_bounds__(512) ifft_rows_kernel(const double *__restrict
     }
 }
 
+// ---- any length n: Bluestein ------------------------------------------------------------------------
+//   X[b] = sum_c x[c] e^{+2 pi i b c / n},  b c = (b^2 + c^2 - (b - c)^2) / 2
+//        = ch[b] * sum_c (x[c] ch[c]) conj(ch[b - c]),   ch[k] = e^{+i pi k^2 / n}
+// i.e. a circular convolution of length m = 2^logm >= 2n - 1, done with the radix-2 transform above:
+// conv = IFFT(FFT(a) FFT(b)), FFT(b) precomputed once per n (FB).  Same I/O conventions as ifft_rows_kernel.
+__device__ __forceinline__ double2 chirp(int k, int n)
+{
+    const long long q = ((long long)k * k) % (2LL * n);        // k^2 mod 2n keeps the argument exact
+    double s, c;
+    sincospi((double)q / (double)n, &s, &c);
+    return make_double2(c, s);
+}
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// in-place radix-2 DIT on bit-reversed input, kernel e^{+2 pi i jk/m}; tw[j] = e^{+2 pi i j/m}, j < m/2
+__device__ __forceinline__ void fft_plus_smem(double2 *w, const double2 *tw, int m, int logm)
+{
+    for (int s = 1; s <= logm; s++) {
+        const int half = 1 << (s - 1), tstep = m >> s;
+        for (int idx = threadIdx.x; idx < m / 2; idx += blockDim.x) {
+            const int k = idx & (half - 1);
+            const int j = ((idx >> (s - 1)) << s) + k;
+            const double2 t = cmul(tw[k * tstep], w[j + half]), a = w[j];
+            w[j] = make_double2(a.x + t.x, a.y + t.y);
+            w[j + half] = make_double2(a.x - t.x, a.y - t.y);
+        }
+        __syncthreads();
+    }
+}
+
+// FB = FFT+(b), b[k] = conj(ch[|k|]) for |k| < n (wrapped into [0, m)), 0 elsewhere.  One block.
+__global__ void __launch_bounds__(512) bluestein_setup_kernel(double2 *__restrict__ FB, int n, int m, int logm)
+{
+    extern __shared__ double2 srow[];
+    double2 *work = srow, *tw = srow + m;
+    for (int j = threadIdx.x; j < m / 2; j += blockDim.x) {
+        double ws, wc;
+        sincospi(2.0 * (double)j / (double)m, &ws, &wc);
+        tw[j] = make_double2(wc, ws);
+    }
+    for (int k = threadIdx.x; k < m; k += blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        const int d = k < n ? k : (m - k < n ? m - k : -1);
+        if (d >= 0) {
+            const double2 c = chirp(d, n);
+            v = make_double2(c.x, -c.y);
+        }
+        work[bitrev((unsigned)k, logm)] = v;
+    }
+    __syncthreads();
+    fft_plus_smem(work, tw, m, logm);
+    for (int k = threadIdx.x; k < m; k += blockDim.x) FB[k] = work[k];
+}
+
+__global__ void __launch_bounds__(512) bluestein_rows_kernel(const double *__restrict__ in_re,
+                                                             const double *__restrict__ in_im, int64_t estride,
+                                                             const double2 *__restrict__ tin, double2 *__restrict__ tout,
+                                                             int n, int m, int logm, int pass,
+                                                             const double2 *__restrict__ FB)
+{
+    extern __shared__ double2 srow[];
+    double2 *work = srow, *tw = srow + m;
+    const int row = blockIdx.x, h = n / 2;
+    for (int j = threadIdx.x; j < m / 2; j += blockDim.x) {
+        double ws, wc;
+        sincospi(2.0 * (double)j / (double)m, &ws, &wc);
+        tw[j] = make_double2(wc, ws);
+    }
+    for (int c = threadIdx.x; c < m; c += blockDim.x) {
+        double2 val = make_double2(0.0, 0.0);
+        if (c < n) {
+            if (pass == 0) {
+                const int64_t src = ((int64_t)((row + h) % n) * n + (c + h) % n) * estride;
+                val = make_double2(in_re[src], in_im ? in_im[src] : 0.0);
+            } else {
+                val = tin[(int64_t)row * n + c];
+            }
+            val = cmul(val, chirp(c, n));
+        }
+        work[bitrev((unsigned)c, logm)] = val;
+    }
+    __syncthreads();
+    fft_plus_smem(work, tw, m, logm);
+    // z = conj(FFT(a) FB), permuted to bit-reversed order in place for the second transform
+    for (int k = threadIdx.x; k < m; k += blockDim.x) {
+        const int r = (int)bitrev((unsigned)k, logm);
+        if (k < r) {
+            const double2 zk = cmul(work[k], FB[k]), zr = cmul(work[r], FB[r]);
+            work[r] = make_double2(zk.x, -zk.y);
+            work[k] = make_double2(zr.x, -zr.y);
+        } else if (k == r) {
+            const double2 zk = cmul(work[k], FB[k]);
+            work[k] = make_double2(zk.x, -zk.y);
+        }
+    }
+    __syncthreads();
+    fft_plus_smem(work, tw, m, logm);               // conj(work) / m is the convolution
+    const double inv_m = 1.0 / (double)m;
+    for (int b = threadIdx.x; b < n; b += blockDim.x) {
+        const double2 y = make_double2(work[b].x * inv_m, -work[b].y * inv_m);
+        const double2 X = cmul(y, chirp(b, n));
+        if (pass == 0) tout[(int64_t)b * n + row] = X;
+        else tout[(int64_t)((b + h) % n) * n + (row + h) % n] = X;
+    }
+}
+
 // image[A, n-1-B, ch] = Re(Y_im[A,B]) / (Re(Y_conv[A,B]) / n^2)        (invert.py:74-79)
 __global__ void __launch_bounds__(256) invert_combine_kernel(const double2 *__restrict__ yim,
                                                              const double2 *__restrict__ yconv, int n, int nch, int ch,
@@ -117,7 +225,7 @@ extern "C" int pdsb_invert_image(const double *g_real, const double *g_imag, con
     PDSB_CHECK(require_init());
     Context &c = ctx();
     PDSB_REQUIRE(g_real && g_imag && conv && image_out, "arrays");
-    PDSB_REQUIRE(imsize >= 2 && imsize <= 4096 && (imsize & (imsize - 1)) == 0, "imsize must be a power of two <= 4096");
+    PDSB_REQUIRE(imsize >= 2 && imsize <= 4096, "imsize must be in [2, 4096]");
     PDSB_REQUIRE(nch >= 1, "nch");
     const int n = imsize;
     int logn = 0;
@@ -144,10 +252,35 @@ extern "C" int pdsb_invert_image(const double *g_real, const double *g_imag, con
     const int threads = n / 2 < 512 ? (n / 2 < 32 ? 32 : n / 2) : 512;
     const size_t smem = (size_t)n * sizeof(double2) * 3 / 2;          // row + twiddle table
     PDSB_CHECK(fft_attr());
+    const bool pow2 = (n & (n - 1)) == 0;
+    int m = 1, logm = 0;
+    const double2 *FB = nullptr;
+    if (!pow2) {
+        while (m < 2 * n - 1) { m <<= 1; logm++; }
+        static bool battr = false;
+        if (!battr) {
+            PDSB_CUDA(cudaFuncSetAttribute(bluestein_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24));
+            PDSB_CUDA(cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 24));
+            battr = true;
+        }
+        PDSB_CHECK(c.fft_fb.ensure((size_t)m * sizeof(double2)));
+        if (c.fft_fb_n != n) {
+            LaunchScope ls("bluestein_setup");
+            bluestein_setup_kernel<<<1, 512, (size_t)m * 24, c.stream>>>(c.fft_fb.as<double2>(), n, m, logm);
+            PDSB_CUDA(cudaGetLastError());
+            c.fft_fb_n = n;
+        }
+        FB = c.fft_fb.as<double2>();
+    }
     auto ifft2 = [&](const double *re, const double *im, int64_t estride, double2 *Y) -> int {
         LaunchScope ls("invert_ifft2");
-        ifft_rows_kernel<<<n, threads, smem, c.stream>>>(re, im, estride, nullptr, T, n, logn, 0);
-        ifft_rows_kernel<<<n, threads, smem, c.stream>>>(nullptr, nullptr, 0, T, Y, n, logn, 1);
+        if (pow2) {
+            ifft_rows_kernel<<<n, threads, smem, c.stream>>>(re, im, estride, nullptr, T, n, logn, 0);
+            ifft_rows_kernel<<<n, threads, smem, c.stream>>>(nullptr, nullptr, 0, T, Y, n, logn, 1);
+        } else {
+            bluestein_rows_kernel<<<n, 512, (size_t)m * 24, c.stream>>>(re, im, estride, nullptr, T, n, m, logm, 0, FB);
+            bluestein_rows_kernel<<<n, 512, (size_t)m * 24, c.stream>>>(nullptr, nullptr, 0, T, Y, n, m, logm, 1, FB);
+        }
         PDSB_CUDA(cudaGetLastError());
         return PDSB_OK;
     };

@@ -228,8 +228,9 @@ int pdsb_shutdown(void)
     if (!c.inited) return PDSB_OK;
     cudaStreamSynchronize(c.stream);
     for (Scratch *s : {&c.img64, &c.folded, &c.partial, &c.red, &c.stage_a, &c.stage_b, &c.stage_c,
-                       &c.stage_d, &c.stage_e, &c.small_dev, &c.mma_ws})
+                       &c.stage_d, &c.stage_e, &c.small_dev, &c.mma_ws, &c.fft_fb})
         s->release();
+    c.fft_fb_n = 0;
     for (auto &p : c.prof) {
         cudaEventDestroy(p.start);
         cudaEventDestroy(p.stop);

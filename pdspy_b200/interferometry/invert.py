@@ -8,7 +8,8 @@ FFT).  Host side only prepares small things: the image axes and the gridding ker
 Differences in HOW (not in what) from the reference: the beam / uv-taper variants of the data are built as
 a separate Visibilities instead of overwriting the caller's arrays and restoring them afterwards
 (invert.py:15-20, 24-29, 40-47), and the separable exp*sinc kernel map is formed as an outer product of
-two 1-D profiles.  imsize must be a power of two."""
+two 1-D profiles.  Any imsize up to 4096 (powers of two run the radix-2 transform directly, other sizes go
+through Bluestein's algorithm on the same transform)."""
 import numpy
 
 from .. import _lib
@@ -62,8 +63,8 @@ def kernel_map(convolution, uu, vv, cell):
 def invert(data, imsize=256, pixel_size=0.25, convolution="pillbox", mfs=False, weighting="natural",
            robust=2, npixels=0, centering=None, mode='continuum', beam=False, uvtaper=None,
            deterministic=True):
-    if imsize & (imsize - 1) or imsize > 4096:
-        raise NotImplementedError("the GPU invert() needs imsize to be a power of two <= 4096")
+    if imsize < 2 or imsize > 4096:
+        raise NotImplementedError("the GPU invert() handles 2 <= imsize <= 4096 (one image row per thread block)")
 
     cell = 1.0 / (pixel_size * imsize * arcsec)              # uv cell of an image of imsize pixels (invert.py:33)
     gridded = grid(_imaging_data(data, beam, uvtaper), gridsize=imsize, binsize=cell, convolution=convolution,

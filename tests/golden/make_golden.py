@@ -113,6 +113,17 @@ INVERT_CASES = {
 }
 
 
+# image sizes that are not powers of two (the reference takes any: scipy's ifft2); kept in their own file,
+# written by `python make_golden.py --invert-anysize`
+INVERT_ANYSIZE_CASES = {
+    "expsinc_300": dict(imsize=300, pixel_size=0.5, convolution="expsinc"),
+    "pillbox_125": dict(imsize=125, pixel_size=1.0, convolution="pillbox"),
+    "robust_centered_90": dict(imsize=90, pixel_size=1.0, convolution="expsinc", weighting="robust", robust=0.5,
+                               centering=[0.3, -0.2, 1.0]),
+    "beam_77": dict(imsize=77, pixel_size=1.5, convolution="expsinc", beam=True, uvtaper=30.0),
+}
+
+
 def load_reference_invert(ref):
     """The reference's own invert.py (scipy.fftpack) with the compiled grid(); pdspy.imaging is replaced
     by a minimal Image stub (the real one needs h5py/astropy)."""
@@ -282,5 +293,30 @@ def main():
             print(" ", f, os.path.getsize(os.path.join(HERE, f)))
 
 
+def main_invert_anysize():
+    import contextlib
+    import io
+    ref = build_ref.load()
+    assert ref is not None, "reference tree not available"
+    d = np.load(os.path.join(HERE, "fixture_720.npz"))
+    fx = {k: d[k] for k in d.files}
+    inv = load_reference_invert(ref)
+    iv = {}
+    for name, kw in INVERT_ANYSIZE_CASES.items():
+        fxdata = ref.Visibilities(fx["u"].copy(), fx["v"].copy(), fx["freq"].copy(), fx["real"].copy(),
+                                  fx["imag"].copy(), fx["weights"].copy())
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = inv.invert(fxdata, **kw)
+        im = r.image[:, :, 0, 0]
+        iv[name + "/sample"] = im[::4, ::4].copy() if im.shape[0] > 128 else im.copy()
+        iv[name + "/stats"] = np.array([im.sum(), im.max(), im.min(), np.abs(im).sum()])
+        iv[name + "/x"] = r.x
+    np.savez_compressed(os.path.join(HERE, "invert_anysize_golden.npz"), **iv)
+    print("written", os.path.getsize(os.path.join(HERE, "invert_anysize_golden.npz")))
+
+
 if __name__ == "__main__":
-    main()
+    if "--invert-anysize" in sys.argv:
+        main_invert_anysize()
+    else:
+        main()
