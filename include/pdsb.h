@@ -160,6 +160,18 @@ int pdsb_loglike_batch(pdsb_dataset *ds, const double *images, int nwalkers, int
                        int image_kind, double dxy, const double *dRA, const double *dDec,
                        double *lnlike);
 
+/* interpolate_model(code="trift") (interpolate_model.py:49-55; the third-party `trift` package's "extended" mode:
+ * the exact transform of the Delaunay piecewise-linear interpolant of a scattered-point image, PARITY UNPINNED like
+ * sampleImage).  tri_records (HOST): ntri records of pdsb_triangle_record_bytes() bytes each =
+ *   { double x[3], y[3] (vertex coordinates, radians, in the frame V = Int I exp(+2 pi i (u x - v y)));
+ *     double B[9] (value at vertex a = sum_k B[3a + k] * values[idx[k]]: identity, or the barycentric rows of a
+ *     sub-divided triangle); double area2 (twice the area); int idx[3]; int pad }.
+ * The caller (pdspy_b200/interferometry/trift.py) triangulates once per geometry and sub-divides so that the
+ * vertex phases of a triangle stay within ~4 rad of their mean for the longest baseline.  values [npts, nf] Jy/sr. */
+int pdsb_sample_triangles(pdsb_dataset *ds, const void *tri_records, int ntri, const double *values, int64_t npts, int nf,
+                          int values_kind, double dRA, double dDec, double *out_real, double *out_imag, int out_kind);
+int pdsb_triangle_record_bytes(void);
+
 /* ---- likelihood on caller-supplied model arrays --------------------------------- */
 /* All arrays [n] fp64 (n = nuv*nf).  out[0]=sum (d.re-m.re)^2 w, out[1]=sum (d.im-m.im)^2 w,
  * out[2]=sum log(w[w>0]/2pi), out[3]=the emcee.py:31-43 value.  out is a host double[4]. */

@@ -61,6 +61,8 @@ SIGNATURES = {
     "pdsb_loglike_device": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P],
     "pdsb_dataset_logsum": [_P, ctypes.POINTER(_c_dbl)],
     "pdsb_loglike_batch": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl, _P, _P, _P],
+    "pdsb_sample_triangles": [_P, _P, _c_int, _P, _c_i64, _c_int, _c_int, _c_dbl, _c_dbl, _P, _P, _c_int],
+    "pdsb_triangle_record_bytes": [],
     "pdsb_chi2": [_P, _P, _P, _P, _P, _c_i64, _c_int, _P],
     "pdsb_chi2_dataset": [_P, _P, _P, _c_int, _P],
     "pdsb_hash64": [_P, _c_i64, ctypes.POINTER(ctypes.c_uint64)],

@@ -97,6 +97,11 @@ constexpr int DFT_VARIANT_F64 = 300;
 int launch_dft_f64(const double *img_dev, int ny, int nx, int nf, const double *u, const double *v, int64_t nuvh, double dxy,
                    double2 *part);
 
+// trift.cu: exact transform of a triangulated scattered-point image (interpolate_model code="trift")
+int launch_trift(const void *tris_dev, int ntri, const double *values_dev, int nf, const double *u, const double *v,
+                 int64_t nuvh, double2 *part);
+size_t trift_record_bytes();
+
 // fft.cu: inverse-sign 2-D transform of every channel of a cube, both-axes fftshift on input and output,
 // channel-fastest output (used by the galario-algorithm path of vis.cu)
 int fft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Y);

@@ -793,6 +793,52 @@ int pdsb_loglike_fft(pdsb_dataset *ds, const double *image, int n, int nf, int i
     return PDSB_OK;
 }
 
+// code="trift": exact transform of a triangulated scattered-point image (trift.cu); same epilogues as the pixel kernels
+int pdsb_sample_triangles(pdsb_dataset *ds, const void *tri_records, int ntri, const double *values, int64_t npts, int nf,
+                          int values_kind, double dRA, double dDec, double *out_real, double *out_imag, int out_kind)
+{
+    PDSB_CHECK(require_init());
+    PDSB_REQUIRE(ds && out_real && out_imag, "dataset/outputs");
+    PDSB_REQUIRE(ntri >= 0 && npts > 0 && nf > 0 && (ntri == 0 || tri_records) && values, "triangles/values");
+    Context &c = ctx();
+    if (ds->nuv == 0) return PDSB_OK;
+    const size_t tb = (size_t)ntri * trift_record_bytes();
+    PDSB_CHECK(c.folded.ensure(tb + 64));
+    if (ntri > 0) PDSB_CUDA(cudaMemcpyAsync(c.folded.ptr, tri_records, tb, cudaMemcpyHostToDevice, c.stream));
+    const double *vals = nullptr;
+    PDSB_CHECK(to_device(values, values_kind, (size_t)npts * nf * sizeof(double), c.img64, (const void **)&vals));
+    PDSB_CHECK(c.partial.ensure((size_t)nf * ds->nuvh * sizeof(double2)));
+    PDSB_CHECK(launch_trift(c.folded.ptr, ntri, vals, nf, ds->u, ds->v, ds->nuvh, c.partial.as<double2>()));
+    DftRun run;
+    run.g = make_geom(2, 2, nf, 32, 1.0);
+    run.g.xcen = run.g.ycen = 0.0;
+    run.nsplit = 1;
+    EpiParams e = make_epi(ds, run, dRA, dDec);
+    PDSB_CHECK(apply_mods(e, nf));
+    const size_t bytes = (size_t)ds->nuv * nf * sizeof(double);
+    double *ore = out_real, *oim = out_imag;
+    if (out_kind == PDSB_HOST) {
+        PDSB_CHECK(c.stage_a.ensure(bytes));
+        PDSB_CHECK(c.stage_b.ensure(bytes));
+        ore = c.stage_a.as<double>();
+        oim = c.stage_b.as<double>();
+    }
+    dim3 grid((unsigned)ceil_div(ds->nuvh, 32), (unsigned)ceil_div(nf, 32));
+    {
+        LaunchScope ls("finish_vis");
+        finish_vis_kernel<<<grid, dim3(32, 8), 0, c.stream>>>(e, ore, oim);
+        PDSB_CUDA(cudaGetLastError());
+    }
+    if (out_kind == PDSB_HOST) {
+        PDSB_CUDA(cudaMemcpyAsync(out_real, ore, bytes, cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, bytes, cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    return PDSB_OK;
+}
+
+int pdsb_triangle_record_bytes(void) { return (int)trift_record_bytes(); }
+
 int pdsb_chi2(const double *d_real, const double *d_imag, const double *weights, const double *m_real,
               const double *m_imag, int64_t n, int kind, double *out)
 {

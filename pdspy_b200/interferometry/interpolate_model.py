@@ -85,9 +85,19 @@ def interpolate_model(u, v, freq, model, nthreads=1, dRA=0., dDec=0.,
                                  nthreads=nthreads, dRA=dRA, dDec=dDec, code="galario")
 
     elif code == "trift":
-        raise NotImplementedError(
-            "code='trift' (exact transform of the triangulated image, interpolate_model.py:49-55) is not on "
-            "the B200 path; code='galario-unstructured' handles the same images")
+        # the exact transform of the Delaunay piecewise-linear interpolant of the scattered points (what the
+        # third-party `trift` package computes in its "extended" mode, :49-55; parity unpinned: trift.py)
+        from . import trift as _trift
+        u = numpy.ascontiguousarray(u, dtype=numpy.float64)
+        v = numpy.ascontiguousarray(v, dtype=numpy.float64)
+        ds = dataset_for(u, v)
+        nf = numpy.shape(model.image)[1] if numpy.ndim(model.image) == 2 else 0
+        if u.size > 0:
+            token, dre, dim_ = register_model((u.size, nf))
+            _trift.sample(ds, u, v, model, dRA, dDec, dre, dim_, _lib.DEVICE)
+            return Visibilities._from_device(u, v, freq, token, (u.size, nf))
+        real = numpy.empty((0, nf))
+        imag = numpy.empty((0, nf))
     else:
         # the reference falls through to an UnboundLocalError on `real`; be explicit instead
         raise ValueError("unknown code %r" % (code,))

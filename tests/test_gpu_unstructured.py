@@ -65,11 +65,60 @@ def test_grid_nodes_as_scattered_points_reproduce_the_structured_path(gpu):
     assert np.abs((vis.real - ref.real) + 1j * (vis.imag - ref.imag)).max() / scale < 1e-9
 
 
-def test_trift_is_refused_and_shapes_checked(gpu):
+def test_trift_vs_oracle(gpu):
+    """code="trift" (interpolate_model.py:49-55): the exact transform of the triangulated image against the
+    extended-precision oracle (explicit divided differences), same triangulation; baselines long enough that the
+    outer triangles get sub-divided, a Hermitian-doubled and a plain uv list, u = v = 0 (total flux)."""
+    from oracle import trift as ot
+    m = _circular_image(nr=14, nphi=12, nf=3, rmax=1.5)
+    rng = np.random.default_rng(8)
+    for herm in (True, False):
+        if herm:
+            u, v = synth.synth_uv(64, 0.02 * A)
+        else:
+            u, v = np.concatenate([[0.0], rng.normal(0, 4e5, 40)]), np.concatenate([[0.0], rng.normal(0, 4e5, 40)])
+        vis = interpolate_model(u, v, m.freq, m, dRA=0.05, dDec=-0.02, code="trift")
+        ref = ot.trift(m.x, m.y, m.image, u, v, 0.05 * A, -0.02 * A)
+        assert vis.real.shape == (u.size, 3) and np.all(vis.weights == 1)
+        assert np.abs(vis.real + 1j * vis.imag - ref).max() / np.abs(ref).max() < 1e-11
+
+
+def test_trift_is_the_small_pixel_limit_of_the_regridded_path(gpu):
+    """The same sky through the reference's three codes must give the same visibilities: code="trift" is what
+    code="galario-unstructured" converges to as its pixels shrink (O(dxy^2)); fixes trift's frame and sign."""
+    m = _circular_image(nr=40, nphi=36, nf=2, rmax=1.0)
+    u, v = synth.synth_uv(400, 0.03 * A)
+    t = interpolate_model(u, v, m.freq, m, dRA=0.03, dDec=0.01, code="trift")
+    tv = t.real + 1j * t.imag
+    errs = []
+    for nxy, dxy in ((256, 0.01), (512, 0.005)):
+        g = interpolate_model(u, v, m.freq, m, dRA=0.03, dDec=0.01, code="galario-unstructured", nxy=nxy, dxy=dxy)
+        errs.append(np.abs(g.real + 1j * g.imag - tv).max() / np.abs(tv).max())
+    assert errs[1] < 2e-3 and errs[1] < 0.4 * errs[0]
+
+
+def test_trift_subdivision_is_exact(gpu):
+    """Sub-dividing triangles (trift.py) must not change the result: the interpolant is linear on the parent."""
+    from pdspy_b200.interferometry import trift as tr
+    m = _circular_image(nr=10, nphi=8, nf=2, rmax=2.0)
+    u, v = synth.synth_uv(200, 0.02 * A)
+    a = interpolate_model(u, v, m.freq, m, code="trift")
+    old = tr.PHASE_SPAN
+    try:
+        tr.PHASE_SPAN = 1.0
+        tr._CACHE.clear()
+        b = interpolate_model(u, v, m.freq, m, code="trift")
+    finally:
+        tr.PHASE_SPAN = old
+        tr._CACHE.clear()
+    assert np.abs((a.real - b.real) + 1j * (a.imag - b.imag)).max() <= 1e-12 * np.abs(a.real + 1j * a.imag).max()
+
+
+def test_unstructured_shapes_checked(gpu):
     m = _circular_image()
     u, v = synth.synth_uv(10, 0.04 * A)
-    with pytest.raises(NotImplementedError):
-        interpolate_model(u, v, m.freq, m, code="trift")
     bad = pb.UnstructuredImage(m.image, x=m.x[:-1], y=m.y, freq=m.freq)
+    with pytest.raises(ValueError):
+        interpolate_model(u, v, m.freq, bad, code="trift")
     with pytest.raises(ValueError):
         interpolate_model(u, v, m.freq, bad, code="galario-unstructured", nxy=32, dxy=0.1)
