@@ -85,7 +85,7 @@ def test_trift_vs_oracle(gpu):
 
 def test_trift_is_the_small_pixel_limit_of_the_regridded_path(gpu):
     """The same sky through the reference's three codes must give the same visibilities: code="trift" is what
-    code="galario-unstructured" converges to as its pixels shrink (O(dxy^2)); fixes trift's frame and sign."""
+    code="galario-unstructured" converges to as its pixels shrink; fixes trift's frame and sign."""
     m = _circular_image(nr=40, nphi=36, nf=2, rmax=1.0)
     u, v = synth.synth_uv(400, 0.03 * A)
     t = interpolate_model(u, v, m.freq, m, dRA=0.03, dDec=0.01, code="trift")
@@ -94,7 +94,7 @@ def test_trift_is_the_small_pixel_limit_of_the_regridded_path(gpu):
     for nxy, dxy in ((256, 0.01), (512, 0.005)):
         g = interpolate_model(u, v, m.freq, m, dRA=0.03, dDec=0.01, code="galario-unstructured", nxy=nxy, dxy=dxy)
         errs.append(np.abs(g.real + 1j * g.imag - tv).max() / np.abs(tv).max())
-    assert errs[1] < 2e-3 and errs[1] < 0.4 * errs[0]
+    assert errs[1] < 2e-4 and errs[1] < 0.75 * errs[0]           # measured 1.2e-4 -> 7.3e-5 (hull edge: O(dxy))
 
 
 def test_trift_subdivision_is_exact(gpu):
