@@ -8,7 +8,7 @@
 // with p_k = q.r_k the vertex phases, pbar their mean, y_k = p_k - pbar, and h_k the complete homogeneous symmetric
 // polynomials (the Taylor expansion of the divided difference exp[i p_a, i p_a, i p_b, i p_c], Hermite-Genocchi):
 // no division by phase differences, so nothing special happens when q is perpendicular to an edge or zero.  The
-// host subdivides triangles until |y| stays below ~4 for the longest baseline (trift.py), so ~25 terms reach
+// host subdivides triangles until |y| stays below ~4 for the longest baseline (trift.py), so ~30 terms reach
 // 1e-15; all recurrences are REAL (the i^k only routes a term to the real or the imaginary sum).
 //
 // One thread per (unique) uv point, looping over all triangles (records staged in shared memory by the block);
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(TR_THREADS) trift_kernel(const TriRec *__restr
             const double pm = (p0 + p1 + p2) * (1.0 / 3.0);
             const double y0 = p0 - pm, y1 = p1 - pm, y2 = p2 - pm;
             const double ymax = fmax(fabs(y0), fmax(fabs(y1), fabs(y2)));
-            int K = (int)(2.8 * ymax) + 14;
+            int K = (int)(3.5 * ymax) + 16;                       // truncation below 1e-15 of the sum for ymax <= 6
             K = K > TR_KMAX ? TR_KMAX : K;
             // h_k over growing node sets, all real:  e1 = y0^k, e2 = h_k(y0, y1), s = h_k(y0, y1, y2),
             // g_a = h_k(y_a, y0, y1, y2) = s_k + y_a g_a(k-1)
