@@ -65,6 +65,75 @@ def test_point_source_and_hermitian_symmetry():
     np.testing.assert_allclose(V[h:], np.conj(V[:h]), rtol=0, atol=1e-13)
 
 
+def _sky_coordinates(n, px, over=1):
+    """(xi east, eta north) in arcsec of the (sub-)pixel centres in the oracle's frame: east = smaller column,
+    the row that carries Dec offset eta is j = n/2 - 1 + eta/px."""
+    sub = (np.arange(over) + 0.5) / over - 0.5
+    col = ((np.arange(n) - n / 2)[:, None] + sub[None, :]).ravel() * px
+    row = ((np.arange(n) - n / 2 + 1)[:, None] + sub[None, :]).ravel() * px
+    X, Y = np.meshgrid(col, row)
+    return -X, Y
+
+
+def _render(mask_fn, n, px, flux, over=8):
+    xi, eta = _sky_coordinates(n, px, over)
+    cover = mask_fn(xi, eta).astype(float).reshape(n, over, n, over).mean(axis=(1, 3))
+    return (cover * flux / cover.sum())[:, :, None, None]
+
+
+def test_circle_and_ring_known_answers_match_reference_model_convention():
+    """The other two analytic models of pdspy/interferometry/model.py: circle_model (:106-123, inclined uniform
+    disk, J1) and ring_model (:125-135).  Rendered off-centre, inclined and rotated, so that a wrong sign of u, v,
+    x0, y0 or theta, or a missing conjugation, changes the answer by order unity; the tolerance is the rendering's
+    (8 x 8 sub-pixel coverage of a hard edge), not the transform's."""
+    import scipy.special
+
+    def circle_model(u, v, xc, yc, radius, incline, theta, flux):              # model.py:106-123 verbatim arithmetic
+        urot = u * np.cos(theta) - v * np.sin(theta)
+        vrot = u * np.sin(theta) + v * np.cos(theta)
+        arg = np.sqrt(urot ** 2 + vrot ** 2 * np.cos(incline) ** 2)
+        return flux * scipy.special.j1(2 * np.pi * radius * arg) / (np.pi * radius * arg) * \
+            np.exp(-2 * np.pi * (0 + 1j * (u * xc + v * yc)))
+
+    n, px = 256, 0.04
+    x0, y0, R, Rin, inc, th, flux = 0.6, -0.35, 1.1, 0.55, np.deg2rad(50.0), np.deg2rad(35.0), 1.7
+
+    def ellipse(radius):
+        def f(xi, eta):
+            a, b = xi - x0, eta - y0
+            xr = a * np.cos(th) - b * np.sin(th)
+            yr = a * np.sin(th) + b * np.cos(th)
+            return (xr / radius) ** 2 + (yr / (radius * np.cos(inc))) ** 2 <= 1.0
+        return f
+    rng = np.random.default_rng(12)
+    u, v = rng.normal(0, 6e4, 300), rng.normal(0, 6e4, 300)
+    disk = _render(ellipse(R), n, px, flux)
+    V = od.exact_dft(u, v, disk, px * A)[:, 0]
+    ref = circle_model(u, v, x0 * A, y0 * A, R * A, inc, th, flux)
+    assert np.abs(V - ref).max() <= 3e-3 * flux
+    for wrong in (np.conj(ref), circle_model(-u, v, x0 * A, y0 * A, R * A, inc, th, flux),
+                  circle_model(u, v, x0 * A, y0 * A, R * A, inc, -th, flux), circle_model(u, v, x0 * A, -y0 * A, R * A, inc, th, flux)):
+        assert np.abs(V - wrong).max() > 0.2 * flux
+    ring = _render(lambda xi, eta: ellipse(R)(xi, eta) & ~ellipse(Rin)(xi, eta), n, px, flux)
+    Vr = od.exact_dft(u, v, ring, px * A)[:, 0]
+    Aq = (Rin / R) ** 2                                                        # model.py:125-135
+    ref_r = flux * (circle_model(u, v, x0 * A, y0 * A, R * A, inc, th, 1) - Aq * circle_model(u, v, x0 * A, y0 * A, Rin * A, inc, th, 1)) / (1 - Aq)
+    assert np.abs(Vr - ref_r).max() <= 5e-3 * flux
+
+
+def test_on_grid_magnitudes_equal_the_references_own_fft_path():
+    """pdspy/imaging/imtovis.py:6-27 is the reference's own (older) statement of image -> visibilities on the FFT
+    grid: fftshift(fft2(ifftshift(image))) at u = fftfreq(nx, dx) - no row flip and no conjugation there, so only
+    the magnitudes are comparable: |V(u, v)| of the oracle equals |imtovis| at the mirrored u."""
+    n, px = 32, 0.1
+    img = synth.synth_image(n, 1, px, kind="random")
+    vis = np.fft.fftshift(np.fft.fft2(np.fft.ifftshift(img[:, :, 0, 0])))       # imtovis.py:15
+    uu = np.fft.fftshift(np.fft.fftfreq(n, px * A))                             # imtovis.py:19-20
+    U, Vv = np.meshgrid(uu, uu)
+    mine = od.exact_dft(np.ascontiguousarray(-U.ravel()), np.ascontiguousarray(Vv.ravel()), img, px * A)[:, 0]
+    assert np.abs(np.abs(mine) - np.abs(vis.ravel())).max() <= 1e-11 * np.abs(vis).max()
+
+
 def test_galario_restatement_equals_exact_on_fft_grid_points():
     n, px = 64, 0.1
     img = synth.synth_image(n, 2, px, kind="random")
