@@ -17,81 +17,11 @@
 // Index maps reproduce numpy's left-to-right fp64 arithmetic and its float64->uint32 cast
 // (truncation through int64, wrap mod 2^32, NaN -> 0) exactly: __dmul_rn/__ddiv_rn/__dadd_rn keep
 // the compiler from contracting the expression into FMAs.
-#include "common.cuh"
+#include "grid.cuh"
 #include <algorithm>
 #include <cmath>
 
 namespace pdsb {
-
-constexpr uint32_t KEY_DEAD = 0xffffffffu;
-
-// ---- convolution kernels, term for term as libinterferometry.pyx:547-585 -----------------------
-__device__ __forceinline__ double k_sinc(double x)
-{
-    const double xp = x * 3.14159265358979323846;
-    const double x2 = xp * xp, x4 = x2 * x2, x6 = x4 * x2, x8 = x4 * x4, x10 = x8 * x2, x12 = x8 * x4,
-                 x14 = x8 * x6, x16 = x8 * x8;
-    // divisions by the literal factorials as reciprocal multiplies: the reference is built with
-    // -ffast-math (setup.py:11), under which gcc does the same, so neither form is "the" bit pattern.
-    return 1. - x2 * (1. / 6.) + x4 * (1. / 120.) - x6 * (1. / 5040.) + x8 * (1. / 362880.) -
-           x10 * (1. / 39916800.) + x12 * (1. / 6227020800.) - x14 * (1. / 1307674368000.) +
-           x16 * (1. / 355687428096000.);
-}
-__device__ __forceinline__ double k_exp(double x)
-{
-    const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2, x5 = x4 * x;
-    return 1 + x + x2 * 0.5 + x3 * (1. / 6.) + x4 * (1. / 24.) + x5 * (1. / 120.);
-}
-__device__ __forceinline__ double k_exp_sinc(double u, double v)
-{
-    const double inv_alpha1 = 1. / 1.55, inv_alpha2 = 1. / 2.52, norm = 2.350016262343186;
-    if (fabs(u) >= 3.0 || fabs(v) >= 3.0) return 0.;
-    const double a = u * inv_alpha2, b = v * inv_alpha2;
-    return k_sinc(u * inv_alpha1) * k_sinc(v * inv_alpha1) * k_exp(-1 * (a * a)) * k_exp(-1 * (b * b)) *
-           (1. / norm);
-}
-// exp_sinc is separable: exp_sinc(u,v) = g(u) g(v) / norm with g(x) = sinc(x/1.55) exp(-(x/2.52)^2)
-// inside |x| < 3.  The fast mode evaluates 6+6 one-dimensional factors per visibility instead of
-// 36 two-dimensional values (the product order differs from the reference's at the 1e-16 level,
-// which is below the fast mode's own summation-order noise).
-__device__ __forceinline__ double k_exp_sinc_1d(double x)
-{
-    if (fabs(x) >= 3.0) return 0.;
-    const double a = x * (1. / 2.52);
-    return k_sinc(x * (1. / 1.55)) * k_exp(-1 * (a * a));
-}
-__device__ __forceinline__ double k_ones(double u, double v)
-{
-    if (fabs(u) >= 0.5 || fabs(v) >= 0.5) return 0.;
-    return 1.0;
-}
-
-// numpy's float64 -> uint32 cast on x86-64: cvttsd2si to int64 (NaN / out of range ->
-// 0x8000000000000000), then the low 32 bits.
-__device__ __forceinline__ uint32_t np_f64_to_u32(double x)
-{
-    if (!(x > -9.2233720368547758e18 && x < 9.2233720368547758e18)) return 0u;
-    return (uint32_t)(unsigned long long)__double2ll_rz(x);
-}
-
-struct GridParams {
-    const double *u, *v, *freq, *re, *im, *w_in;
-    double *w;              // [nuv, nf] working weights (clamped, then re-weighted)
-    uint32_t *gi, *gj;      // [nuv, nf] index maps
-    uint8_t *good;
-    int64_t nuv;
-    int nf, G, nch, spectral, conv;
-    double binsize, inv_binsize, inv_freq, half;   // half = G/2. or (G-1)/2.
-    const double *uu, *vv;
-    uint32_t nmin, nmax;    // footprint half-widths of the main scatter
-    uint32_t row_lo, row_hi;   // main scatter keeps output rows [row_lo, row_hi) only (multi-GPU row bands)
-    // fast mode: one packed 48-byte record per (visibility, channel) in input order,
-    //   [pos_u, w] [w re, w im] [pos_v, (gi | gj << 32)]      (pos = u f / mean_f as the reference forms it)
-    // written by the prep kernel (coalesced) so that the tile kernel fetches ONE record per visibility through
-    // the sort permutation instead of eight 8-byte gathers (each of which cost a 64-byte DRAM burst: 5.0 GB
-    // read per 10M visibilities in round 1, profiles/r01_grid_tile_ncu.md).  Null in the ordered mode.
-    double2 *rec;
-};
 
 // :351-353 weights clamp/zeroing, :388-403 index maps, :421-423 good mask
 __global__ void __launch_bounds__(256) grid_prep_kernel(GridParams P, unsigned long long *n_outside)
@@ -114,21 +44,6 @@ __global__ void __launch_bounds__(256) grid_prep_kernel(GridParams P, unsigned l
     const bool good = i < (uint32_t)P.G && j < (uint32_t)P.G;
     P.good[idx] = good ? 1 : 0;
     if (!good) atomicAdd(n_outside, 1ull);
-    if (P.rec) {
-        double2 *r = P.rec + 3 * idx;
-        if (good) {
-            r[0] = make_double2(__dmul_rn(__dmul_rn(P.u[k], f), P.inv_freq), w);
-            r[1] = make_double2(P.re[idx] * w, P.im[idx] * w);
-            r[2] = make_double2(__dmul_rn(__dmul_rn(P.v[k], f), P.inv_freq),
-                                __longlong_as_double((long long)((unsigned long long)i | ((unsigned long long)j << 32))));
-        } else {
-            // off the grid (:421-425): sorted into the first tile with zero weight, where it adds exact zeros;
-            // no dead key, so the tile sort needs only the bits of the tile index
-            r[0] = make_double2(P.uu[0], 0.0);
-            r[1] = make_double2(0.0, 0.0);
-            r[2] = make_double2(P.vv[0], 0.0);
-        }
-    }
 }
 
 // Footprint of contribution slot f of visibility idx.  lo/hi half-widths, side = lo+hi+1.
@@ -593,321 +508,6 @@ __global__ void __launch_bounds__(128) grid_ordered_sum_kernel(int mode, int64_t
 }
 
 // ---- fast (atomic) scatter -------------------------------------------------------------------
-__global__ void __launch_bounds__(256) grid_scatter_atomic_kernel(GridParams P, int mode, uint32_t lo, uint32_t hi,
-                                                                  int fp, const uint32_t *__restrict__ order,
-                                                                  double *out_re, double *out_im, double *out_w)
-{
-    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t total = P.nuv * P.nf;
-    if (t >= total * fp) return;
-    const int64_t idx = order ? (int64_t)order[t / fp] : t / fp;
-    const int f = (int)(t % fp);
-    if (!P.good[idx]) return;
-    uint32_t l, m;
-    if (!slot_cell(P.gi[idx], P.gj[idx], f, lo, hi, P.G, &l, &m)) return;
-    const int n = (int)(idx % P.nf);
-    const int64_t cell = ((int64_t)l * P.G + m) * P.nch + (P.spectral ? n : 0);
-    const double w = P.w[idx];
-    if (mode == 0) {
-        const double cv = conv_value(P, idx / P.nf, n, l, m);
-        if (cv == 0.0) return;
-        atomicAdd(out_re + cell, P.re[idx] * w * cv);
-        atomicAdd(out_im + cell, P.im[idx] * w * cv);
-        atomicAdd(out_w + cell, w * cv);
-    } else {
-        atomicAdd(out_w + cell, w);
-    }
-}
-
-// ---- fast mode: sorted uv tiles, on-chip accumulation, then global atomics -------------------
-// Visibilities are sorted by (channel, 8x8-cell home tile).  One CTA takes one tile's run: the
-// visibilities are staged through shared memory 128 at a time; each thread owns ONE cell of the
-// tile's footprint region ((8+lo+hi)^2 cells: 13x13 for expsinc) and accumulates it in registers,
-// so there are no atomics on chip at all; only the finished region is added to the map with one
-// fp64 atomic per cell and map (neighbouring tiles overlap in the halo).
-constexpr int GT_THREADS = 256;
-constexpr int GT_STAGE = 128;
-constexpr int GT_SUBRUN = 2048;      // visibilities per work item (one CTA)
-
-// Work list: every non-empty tile's run in the sorted key array, cut into items of at most
-// GT_SUBRUN visibilities so that the dense central tiles spread over many CTAs.
-__global__ void __launch_bounds__(256) grid_tile_items_kernel(const uint32_t *__restrict__ keys, int64_t nvis,
-                                                              uint2 *__restrict__ items, uint32_t *count)
-{
-    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (p >= nvis) return;
-    const uint32_t key = keys[p];
-    if (p != 0 && keys[p - 1] == key) return;                 // not a run head
-    const int64_t e = lower_bound_u32(keys, nvis, key + 1u);
-    const uint32_t nitems = (uint32_t)((e - p + GT_SUBRUN - 1) / GT_SUBRUN);
-    uint32_t slot = atomicAdd(count, nitems);
-    for (int64_t b = p; b < e; b += GT_SUBRUN)
-        items[slot++] = make_uint2((uint32_t)b, (uint32_t)(b + GT_SUBRUN < e ? b + GT_SUBRUN : e));
-}
-
-__global__ void __launch_bounds__(GT_THREADS) grid_tile_kernel(GridParams P, int mode, int lo, int hi, uint32_t tg,
-                                                               const uint32_t *__restrict__ keys,
-                                                               const uint32_t *__restrict__ order,
-                                                               const uint2 *__restrict__ items,
-                                                               const uint32_t *__restrict__ nitems,
-                                                               double *out_re, double *out_im, double *out_w)
-{
-    constexpr int MAXW = 8;            // widest footprint handled here (expsinc: 6, superuniform box: 7)
-    __shared__ double s_re[GT_STAGE], s_im[GT_STAGE], s_w[GT_STAGE];
-    __shared__ double s_fu[GT_STAGE][MAXW], s_fv[GT_STAGE][MAXW];
-    __shared__ int s_i[GT_STAGE], s_j[GT_STAGE];
-    if (blockIdx.x >= *nitems) return;
-    const uint2 item = items[blockIdx.x];
-    const uint32_t key = keys[item.x];
-    const uint32_t chan = key / (tg * tg), tile = key % (tg * tg);
-    const int tl = (int)(tile / tg), tm = (int)(tile % tg);
-    const int width = lo + hi + 1;
-    const int side = 8 + lo + hi;
-    const int c = threadIdx.x;
-    const int l = tl * 8 - lo + c / side, m = tm * 8 - lo + c % side;
-    const bool active = c < side * side && l >= 0 && m >= 0 && l < P.G && m < P.G;
-    double ar = 0.0, ai = 0.0, aw = 0.0;
-    for (uint32_t base = item.x; base < item.y; base += GT_STAGE) {
-        const int n_here = (int)(item.y - base < GT_STAGE ? item.y - base : GT_STAGE);
-        // stage: per visibility the data and (mode 0) the one-dimensional kernel factors of its
-        // footprint columns / rows; two threads per visibility (u side, v side)
-        if (threadIdx.x < 2 * n_here) {
-            const int q = threadIdx.x >> 1, sidev = threadIdx.x & 1;
-            const int64_t idx = order[base + q];
-            const int64_t k = idx / P.nf;
-            const double f = P.freq[idx % P.nf];
-            const bool live = P.good[idx] != 0;       // off-grid entries sit in the first tile's run with zero weight
-            const int home = live ? (sidev ? (int)P.gj[idx] : (int)P.gi[idx]) : -(1 << 20);
-            if (sidev == 0) {
-                const double w = live ? P.w[idx] : 0.0;
-                s_w[q] = w;
-                s_re[q] = live ? P.re[idx] * w : 0.0;
-                s_im[q] = live ? P.im[idx] * w : 0.0;
-                s_i[q] = home;
-            } else {
-                s_j[q] = home;
-            }
-            if (mode == 0) {
-                const double pos = __dmul_rn(__dmul_rn(sidev ? P.v[k] : P.u[k], f), P.inv_freq);
-                const double *centres = sidev ? P.vv : P.uu;
-                double(*dst)[MAXW] = sidev ? s_fv : s_fu;
-                for (int o = 0; o < width; o++) {
-                    const int cell = home - lo + o;
-                    double g = 0.0;
-                    if (cell >= 0 && cell < P.G) {
-                        const double d = (pos - centres[cell]) * P.inv_binsize;
-                        // 1/norm goes with the u factor
-                        g = P.conv ? k_exp_sinc_1d(d) * (sidev ? 1.0 : (1. / 2.350016262343186))
-                                   : ((fabs(d) >= 0.5) ? 0.0 : 1.0);
-                    }
-                    dst[q][o] = g;
-                }
-            }
-        }
-        __syncthreads();
-        if (active) {
-            for (int q = 0; q < n_here; q++) {
-                const int dj = l - s_j[q] + lo, di = m - s_i[q] + lo;
-                if (dj < 0 || dj >= width || di < 0 || di >= width) continue;
-                if (mode == 0) {
-                    const double cv = s_fu[q][di] * s_fv[q][dj];
-                    ar += s_re[q] * cv;
-                    ai += s_im[q] * cv;
-                    aw += s_w[q] * cv;
-                } else {
-                    aw += s_w[q];
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (active) {
-        const int64_t cell = ((int64_t)l * P.G + m) * P.nch + chan;
-        if (mode == 0) {
-            if (ar != 0.0) atomicAdd(out_re + cell, ar);
-            if (ai != 0.0) atomicAdd(out_im + cell, ai);
-        }
-        if (aw != 0.0) atomicAdd(out_w + cell, aw);
-    }
-}
-
-// Second-generation tile kernel (the one used when the region side is one of the instantiated SIDEs).
-// The region update of one visibility is the outer product  FV[r] * (w, w re, w im) FU[c]  of its two
-// one-dimensional kernel factor rows, zero outside its footprint.  Instead of one thread per region cell
-// testing every visibility against its cell (21 % of the tests hit for expsinc), a "stream" of 16 lanes
-// owns the region COLUMNS and keeps all SIDE rows of the three maps in registers: per visibility each lane
-// reads its three column values and the SIDE row factors (broadcast) from shared memory and issues
-// 3*SIDE dependent-free DFMAs - no branches, no index arithmetic, 5x fewer instructions per visibility.
-// Eight streams per CTA take the staged visibilities round-robin; their private regions are summed
-// through shared memory at the end of the work item and flushed with one fp64 atomic per cell and map.
-// Two launch shapes share the work list: items of more than GT2_LIGHT visibilities (the dense central
-// tiles) run on CTAs of 8 streams, the tens of thousands of sparsely filled outer tiles on one-warp CTAs of
-// 2 streams, whose fixed cost (cross-stream sum, barriers) is a quarter and of which 20+ fit on an SM.
-constexpr int GT2_LIGHT = 128;
-
-// SPLIT (the dense-tile shape): a stream is a whole warp whose two half-warps own the upper and the lower
-// rows of the region, which halves the accumulator registers per thread and lifts the occupancy.
-template <int SIDE, int NSTREAM, bool SPLIT = false>
-__global__ void __launch_bounds__(NSTREAM * 16) grid_tile2_kernel(GridParams P, int mode, int lo, int hi, uint32_t tg,
-                                                                 const uint32_t *__restrict__ keys,
-                                                                 const uint32_t *__restrict__ order,
-                                                                 const uint2 *__restrict__ items,
-                                                                 const uint32_t *__restrict__ nitems,
-                                                                 double *out_re, double *out_im, double *out_w)
-{
-    constexpr int WIDTH = SIDE - 7;                                // footprint width lo + hi + 1
-    constexpr int GT2_THREADS = NSTREAM * 16, GT2_STREAMS = SPLIT ? NSTREAM / 2 : NSTREAM;
-    constexpr int GT2_STAGE = NSTREAM * 8;                         // visibilities staged per round (2 threads each)
-    constexpr int NROW = SPLIT ? (SIDE + 1) / 2 : SIDE;            // region rows this thread accumulates
-    constexpr int RED_ROWS = (3 * SIDE + 2) / 3;                   // the cross-stream sum reuses s_fu: >= 3*SIDE rows of 16
-    constexpr int FU_ROWS = GT2_STAGE > RED_ROWS ? GT2_STAGE : RED_ROWS;
-    __shared__ __align__(16) double s_fv[GT2_STAGE][16];          // row factors, zero outside the footprint
-    __shared__ __align__(16) double s_fu[FU_ROWS][3][16];         // column factors x (w, w re, w im)
-    if (blockIdx.x >= *nitems) return;
-    const uint2 item = items[blockIdx.x];
-    if (((item.y - item.x) > (uint32_t)GT2_LIGHT) != (NSTREAM > 2)) return;      // the other launch shape's item
-    const uint32_t key = keys[item.x];
-    const uint32_t chan = key / (tg * tg), tile = key % (tg * tg);
-    const int tl = (int)(tile / tg), tm = (int)(tile % tg);
-    const int l0 = tl * 8 - lo, m0 = tm * 8 - lo;                  // region origin
-    const int c = threadIdx.x & 15, stream = SPLIT ? threadIdx.x >> 5 : threadIdx.x >> 4;
-    const int row0 = SPLIT ? ((threadIdx.x >> 4) & 1) * NROW : 0;  // first region row of this thread
-    const int q = threadIdx.x >> 1, sidev = threadIdx.x & 1;       // staging role: visibility q of the stage, u / v side
-    double aw[NROW], ar[NROW], ai[NROW];
-#pragma unroll
-    for (int r = 0; r < NROW; r++) aw[r] = ar[r] = ai[r] = 0.0;
-
-    // The staging inputs are gathered through the sort permutation (order -> idx -> u, v, w, re, im, gi,
-    // gj): two dependent global loads.  They are software-pipelined two stages deep - the permutation
-    // entry of stage s+2 and the data of stage s+1 are in flight while stage s is processed.
-    struct Raw {
-        double pos, w, wre, wim;
-        int home;
-    };
-    auto load_idx = [&](uint32_t base) -> int64_t {
-        return base + q < item.y ? (int64_t)order[base + q] : -1;
-    };
-    auto load_raw = [&](int64_t idx) -> Raw {
-        Raw x{0.0, 1.0, 0.0, 0.0, 0};
-        if (idx < 0) return x;
-        const double2 *r = P.rec + 3 * idx;
-        const double2 c2 = r[2];
-        const unsigned long long ij = (unsigned long long)__double_as_longlong(c2.y);
-        if (sidev) {
-            x.pos = c2.x;
-            x.home = (int)(uint32_t)(ij >> 32);
-        } else {
-            const double2 c0 = r[0], c1 = r[1];
-            x.pos = c0.x;
-            x.w = c0.y;
-            x.wre = c1.x;                              // already times w
-            x.wim = c1.y;
-            x.home = (int)(uint32_t)ij;
-        }
-        return x;
-    };
-    int64_t idx_next = load_idx(item.x + GT2_STAGE);
-    Raw cur = load_raw(load_idx(item.x));
-    const double *centres = sidev ? P.vv : P.uu;
-
-    for (uint32_t base = item.x; base < item.y; base += GT2_STAGE) {
-        const int n_here = (int)(item.y - base < GT2_STAGE ? item.y - base : GT2_STAGE);
-        // zero the stage rows (all threads, 16-byte stores)
-        {
-            double2 *z = reinterpret_cast<double2 *>(&s_fv[0][0]);
-            for (int i = threadIdx.x; i < GT2_STAGE * 8; i += GT2_THREADS) z[i] = make_double2(0.0, 0.0);
-            z = reinterpret_cast<double2 *>(&s_fu[0][0][0]);
-            for (int i = threadIdx.x; i < GT2_STAGE * 24; i += GT2_THREADS) z[i] = make_double2(0.0, 0.0);
-        }
-        // next stage's gather, issued before this stage's arithmetic
-        const Raw nxt = load_raw(idx_next);
-        idx_next = load_idx(base + 2 * GT2_STAGE);
-        __syncthreads();
-        // stage: two threads per visibility (u side: the three column rows; v side: the row factors)
-        if (q < n_here) {
-            const int first = cur.home - lo - (sidev ? l0 : m0);   // region row / column of footprint slot 0
-            const double wre = cur.wre, wim = cur.wim;
-            double g[WIDTH];
-#pragma unroll
-            for (int o = 0; o < WIDTH; o++) {
-                const int cell = cur.home - lo + o;
-                g[o] = 0.0;
-                if (cell >= 0 && cell < P.G) {
-                    if (mode == 0) {
-                        const double d = (cur.pos - centres[cell]) * P.inv_binsize;
-                        // 1/norm goes with the u factor
-                        g[o] = P.conv ? k_exp_sinc_1d(d) * (sidev ? 1.0 : (1. / 2.350016262343186))
-                                      : ((fabs(d) >= 0.5) ? 0.0 : 1.0);
-                    } else
-                        g[o] = 1.0;
-                }
-            }
-#pragma unroll
-            for (int o = 0; o < WIDTH; o++) {
-                if (sidev) s_fv[q][first + o] = g[o];
-                else {
-                    s_fu[q][0][first + o] = g[o] * cur.w;
-                    s_fu[q][1][first + o] = g[o] * wre;
-                    s_fu[q][2][first + o] = g[o] * wim;
-                }
-            }
-        }
-        cur = nxt;
-        __syncthreads();
-        for (int v = stream; v < n_here; v += GT2_STREAMS) {
-            const double fw = s_fu[v][0][c];
-            if (mode == 0) {
-                const double fr = s_fu[v][1][c], fi = s_fu[v][2][c];
-#pragma unroll
-                for (int r = 0; r < NROW; r++) {
-                    const double fv = s_fv[v][row0 + r];             // (rows past SIDE are zero padding of the 16-wide row)
-                    aw[r] = fma(fv, fw, aw[r]);
-                    ar[r] = fma(fv, fr, ar[r]);
-                    ai[r] = fma(fv, fi, ai[r]);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < NROW; r++) aw[r] = fma(s_fv[v][row0 + r], fw, aw[r]);
-            }
-        }
-        __syncthreads();
-    }
-    // sum the streams' private regions (stream order, deterministic within the item), then flush
-    double *red = &s_fu[0][0][0];                                  // [3][SIDE][16], reuses the stage buffer
-    for (int sidx = 0; sidx < GT2_STREAMS; sidx++) {
-        if (stream == sidx) {
-#pragma unroll
-            for (int r = 0; r < NROW; r++) {
-                const int rr = row0 + r;
-                if (rr >= SIDE) continue;
-                if (sidx == 0) {
-                    red[(0 * SIDE + rr) * 16 + c] = aw[r];
-                    red[(1 * SIDE + rr) * 16 + c] = ar[r];
-                    red[(2 * SIDE + rr) * 16 + c] = ai[r];
-                } else {
-                    red[(0 * SIDE + rr) * 16 + c] += aw[r];
-                    red[(1 * SIDE + rr) * 16 + c] += ar[r];
-                    red[(2 * SIDE + rr) * 16 + c] += ai[r];
-                }
-            }
-        }
-        __syncthreads();
-    }
-    for (int t = threadIdx.x; t < SIDE * 16; t += GT2_THREADS) {
-        const int r = t >> 4, cc = t & 15;
-        const int l = l0 + r, m = m0 + cc;
-        if (cc >= SIDE || l < 0 || m < 0 || l >= P.G || m >= P.G) continue;
-        const int64_t cell = ((int64_t)l * P.G + m) * P.nch + chan;
-        const double vw = red[(0 * SIDE + r) * 16 + cc];
-        if (mode == 0) {
-            const double vr = red[(1 * SIDE + r) * 16 + cc], vi = red[(2 * SIDE + r) * 16 + cc];
-            if (vr != 0.0) atomicAdd(out_re + cell, vr);
-            if (vi != 0.0) atomicAdd(out_im + cell, vi);
-        }
-        if (vw != 0.0) atomicAdd(out_w + cell, vw);
-    }
-}
-
 // ---- re-weighting, normalisation ---------------------------------------------------------------
 __global__ void __launch_bounds__(256) fill_kernel(double *a, int64_t n, double v)
 {
@@ -933,11 +533,6 @@ __global__ void __launch_bounds__(256) grid_reweight_kernel(GridParams P, const 
     if (f2) w = P.w[idx] / __dadd_rn(1.0, __dmul_rn(f2[n], b));
     else w = P.w[idx] / b;
     P.w[idx] = w;
-    if (P.rec) {                                   // (visibilities off the grid returned above: their record stays zero)
-        double2 *r = P.rec + 3 * idx;
-        r[0].y = w;
-        r[1] = make_double2(P.re[idx] * w, P.im[idx] * w);
-    }
 }
 
 // Column sums with stride, stage 1: part[b][c] = sum over this block's rows of f(a[q*ncol + c]);
@@ -1009,18 +604,6 @@ __global__ void __launch_bounds__(256) freqcorrect_kernel(const double *__restri
     const double scale = __dmul_rn(freq[idx % nf], inv_freq);          // data.freq * inv_freq  :598
     ou[idx] = __dmul_rn(u[idx / nf], scale);
     ov[idx] = __dmul_rn(v[idx / nf], scale);
-}
-
-// home-cell key for the fast path ordering (dead for !good)
-__global__ void __launch_bounds__(256) grid_home_keys_kernel(GridParams P, uint32_t *keys, uint32_t *ids)
-{
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= P.nuv * P.nf) return;
-    // coarse 8x8-cell tiles keep neighbouring visibilities together without a full-resolution sort
-    const uint32_t tg = ((uint32_t)P.G + 7u) >> 3;
-    const uint32_t chan = P.spectral ? (uint32_t)(idx % P.nf) : 0u;
-    keys[idx] = P.good[idx] ? (chan * tg * tg + (P.gj[idx] >> 3) * tg + (P.gi[idx] >> 3)) : chan * tg * tg;
-    ids[idx] = (uint32_t)idx;
 }
 
 // ---- average(): nearest-cell binning with weighted mean positions (libinterferometry.pyx:151-311) ----
@@ -1327,8 +910,7 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
 
     // ---- working arrays ----
     const size_t work_bytes = (size_t)nvis * (sizeof(double) + 2 * sizeof(uint32_t) + 1) + 6 * 64 +
-                              (size_t)(3 * nf + 4) * sizeof(double) + sizeof(unsigned long long) +
-                              (deterministic ? 0 : (size_t)nvis * 3 * sizeof(double2));
+                              (size_t)(3 * nf + 4) * sizeof(double) + sizeof(unsigned long long);
     PDSB_CHECK(c.stage_b.ensure(work_bytes + 256));
     char *wp = c.stage_b.as<char>();
     auto carve = [&](size_t bytes) {
@@ -1342,7 +924,6 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
     double *small = (double *)carve((size_t)(3 * nf + 4) * sizeof(double));     // sumb2[nf], sumw[nf], f2[nf], wsum
     unsigned long long *d_nout = (unsigned long long *)carve(sizeof(unsigned long long));
     uint8_t *good = (uint8_t *)carve((size_t)nvis);
-    double2 *rec = deterministic ? nullptr : (double2 *)carve((size_t)nvis * 3 * sizeof(double2));
 
     double *o_re, *o_im, *o_w;
     PDSB_CHECK(c.stage_c.ensure((size_t)ncell * 4 * sizeof(double) + 256));
@@ -1353,7 +934,7 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
 
     GridParams P;
     P.u = du; P.v = dv; P.freq = dfreq; P.re = dre; P.im = dim; P.w_in = dw;
-    P.w = w_work; P.gi = gi; P.gj = gj; P.good = good; P.rec = rec;
+    P.w = w_work; P.gi = gi; P.gj = gj; P.good = good;
     P.nuv = nuv; P.nf = nf; P.G = G; P.nch = nch; P.spectral = mode == PDSB_MODE_SPECTRALLINE;
     P.conv = convolution;
     P.binsize = binsize; P.inv_binsize = 1. / binsize; P.inv_freq = inv_freq;
@@ -1378,7 +959,11 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
 
     PDSB_CUDA(cudaMemsetAsync(d_nout, 0, sizeof(unsigned long long), c.stream));
     PDSB_CUDA(cudaMemsetAsync(o_re, 0, (size_t)ncell * 3 * sizeof(double), c.stream));
-    if (nvis > 0) {
+    // The prep kernel (working weights, index maps, good mask) feeds the ordered mode, the re-weighting and the map
+    // outputs; the fast mode with natural weights forms everything it needs on the fly from the inputs.
+    const bool prepared = deterministic || weights_phase || weighting != PDSB_WT_NATURAL || out_i || out_j || out_wmod;
+    int counted_outside = 0;
+    if (nvis > 0 && prepared) {
         LaunchScope ls("grid_prep");
         grid_prep_kernel<<<ceil_div(nvis, 256), 256, 0, c.stream>>>(P, d_nout);
         PDSB_CUDA(cudaGetLastError());
@@ -1403,64 +988,9 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
     auto scatter = [&](int smode, uint32_t lo, uint32_t hi, double *t_re, double *t_im, double *t_w) -> int {
         if (nvis == 0) return PDSB_OK;
         const int fp = (int)((lo + hi + 1) * (lo + hi + 1));
-        if (!deterministic) {
-            // order visibilities by coarse home tile so concurrent atomics share L2 lines
-            const uint32_t tg = ((uint32_t)G + 7u) >> 3;
-            PDSB_CHECK(c.stage_d.ensure((size_t)nvis * 4 * sizeof(uint32_t) + hist_bytes(nvis)));
-            uint32_t *k0 = c.stage_d.as<uint32_t>(), *v0 = k0 + nvis, *k1 = v0 + nvis, *v1 = k1 + nvis;
-            uint32_t *hist = v1 + nvis;
-            {
-                LaunchScope ls("grid_home_keys");
-                grid_home_keys_kernel<<<ceil_div(nvis, 256), 256, 0, c.stream>>>(P, k0, v0);
-                PDSB_CUDA(cudaGetLastError());
-            }
-            uint32_t *ko, *vo;
-            SortBufs sb{k0, v0, k1, v1, hist};
-            const uint64_t nkeys = (uint64_t)tg * tg * (uint64_t)nch;
-            int tbits = bits_for(nkeys - 1);
-            tbits = ((tbits + 7) / 8) * 8 > 32 ? 32 : ((tbits + 7) / 8) * 8;
-            PDSB_CHECK(radix_sort(sb, nvis, tbits, &ko, &vo));
-            const int side = 8 + (int)lo + (int)hi;
-            if (side * side <= GT_THREADS && (int)(lo + hi + 1) <= 8) {
-                const uint64_t max_items = std::min<uint64_t>(nkeys, (uint64_t)nvis) + (uint64_t)nvis / GT_SUBRUN + 2;
-                PDSB_REQUIRE(max_items < (uint64_t)1 << 31, "too many gridding work items");
-                PDSB_CHECK(c.stage_e.ensure((max_items + 2) * sizeof(uint2)));
-                uint32_t *nitems = c.stage_e.as<uint32_t>();
-                uint2 *items = c.stage_e.as<uint2>() + 2;
-                PDSB_CUDA(cudaMemsetAsync(nitems, 0, sizeof(uint32_t), c.stream));
-                {
-                    LaunchScope ls("grid_tile_items");
-                    grid_tile_items_kernel<<<ceil_div(nvis, 256), 256, 0, c.stream>>>(ko, nvis, items, nitems);
-                    PDSB_CUDA(cudaGetLastError());
-                }
-                LaunchScope ls("grid_tile_accum");
-                switch (side) {
-#define PDSB_TILE2(S)                                                                                                  \
-    case S:                                                                                                            \
-        grid_tile2_kernel<S, 8, true><<<(unsigned)max_items, 128, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko,   \
-                                                                                vo, items, nitems, t_re, t_im, t_w);   \
-        grid_tile2_kernel<S, 2, true><<<(unsigned)max_items, 32, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko, vo, \
-                                                                         items, nitems, t_re, t_im, t_w);              \
-        break;
-                    PDSB_TILE2(10)       // pillbox, box sums with npixels = 1
-                    PDSB_TILE2(12)       // box sums with npixels = 2
-                    PDSB_TILE2(13)       // expsinc
-                    PDSB_TILE2(14)       // box sums with npixels = 3 (superuniform)
-#undef PDSB_TILE2
-                    default:
-                        grid_tile_kernel<<<(unsigned)max_items, GT_THREADS, 0, c.stream>>>(P, smode, (int)lo, (int)hi, tg, ko,
-                                                                                         vo, items, nitems, t_re, t_im, t_w);
-                }
-                PDSB_CUDA(cudaGetLastError());
-                return PDSB_OK;
-            }
-            // footprints wider than the tile kernel's region: plain atomics in tile order
-            LaunchScope ls("grid_scatter_atomic");
-            grid_scatter_atomic_kernel<<<ceil_div(nvis * fp, 256), 256, 0, c.stream>>>(P, smode, lo, hi, fp, vo, t_re,
-                                                                                       t_im, t_w);
-            PDSB_CUDA(cudaGetLastError());
-            return PDSB_OK;
-        }
+        if (!deterministic)
+            return grid_fast_scatter(P, smode, lo, hi, prepared ? w_work : nullptr, t_re, t_im, t_w,
+                                     (!prepared && !counted_outside++) ? d_nout : nullptr);
         // deterministic: batches of at most 2^27 contributions, processed in (k,n) order
         const int compact = (smode == 0 && convolution == PDSB_CONV_PILLBOX) ? 1 : 0;
         const int fp_emit = compact ? 1 : fp;

@@ -68,8 +68,6 @@ def test_image_container_derives_freq_and_wave():
 
 def test_interpolate_model_argument_errors_do_not_need_a_gpu():
     c = synth.make_config("C1", nuv=16)
-    with pytest.raises(NotImplementedError):
-        interpolate_model(c["u"], c["v"], c["freq"], c["model"], code="trift")
     with pytest.raises(ValueError):
         interpolate_model(c["u"], c["v"], c["freq"], c["model"], code="nope")
 
