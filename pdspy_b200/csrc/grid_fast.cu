@@ -11,8 +11,8 @@
 //                      the 64 K write streams, so DRAM sees full lines)
 //   gf_tile_kernel     persistent warps, one work item each:
 //        * the item's records are bucketed by home ROW inside the tile (8 buckets, ballot counting sort);
-//        * factor phase, one lane per visibility: the 2 x WIDTH one-dimensional kernel factors (the exp*sinc kernel
-//          is separable) in Horner form, staged in shared memory;
+//        * factor phase: the 2 x WIDTH one-dimensional kernel factors (the exp*sinc kernel is separable), staged in
+//          shared memory;
 //        * accumulate phase, one half-warp per visibility: lane = region column, registers = the WIDTH rows of the
 //          visibility's footprint x 3 maps.  Because the bucket fixes the rows, all WIDTH x 3 accumulators of a
 //          lane are live for every visibility (the round-1 kernel kept all 13 region rows in registers and issued
@@ -27,7 +27,7 @@
 
 namespace pdsb {
 
-constexpr int GF_ITEM = 256;        // visibilities per work item (one warp)
+constexpr int GF_ITEM = 512;        // visibilities per work item (one warp)
 constexpr int GF_WARPS = 4;         // warps per CTA, each on its own item
 constexpr int GF_SCAN_THREADS = 1024;
 constexpr int GF_SCAN_PER = 4;
@@ -63,24 +63,69 @@ __device__ __forceinline__ uint32_t gf_key(const GridParams &P, const GfVis &x, 
     return (P.spectral ? (uint32_t)(idx % P.nf) : 0u) * tg * tg + tile;
 }
 
+// Interferometric uv coverage peaks at the short baselines: the few tiles around the grid centre receive a large
+// share of all visibilities (26 % of BASELINE configs[3] land in the four central tiles), and the L2 serialises
+// atomics per address.  Both passes therefore count the central GF_WIN x GF_WIN tiles in a shared-memory window per
+// block first (one global atomic per block and window tile); the rest of the plane goes to global memory directly.
+// The window is used when the key has no channel part (nch == 1); otherwise equal keys are aggregated per warp.
+constexpr int GF_WIN = 32;
+constexpr int GF_PASS_ITEMS = 4;                   // visibilities per thread in the two passes
+constexpr int GF_PASS_TILE = 256 * GF_PASS_ITEMS;
+
+__device__ __forceinline__ int gf_window_index(uint32_t gi, uint32_t gj, uint32_t tg)
+{
+    const int org = (int)(tg / 2) - GF_WIN / 2 > 0 ? (int)(tg / 2) - GF_WIN / 2 : 0;
+    const int wr = (int)(gj >> 3) - org, wc = (int)(gi >> 3) - org;
+    return (wr >= 0 && wr < GF_WIN && wc >= 0 && wc < GF_WIN) ? wr * GF_WIN + wc : -1;
+}
+__device__ __forceinline__ uint32_t gf_window_key(int widx, uint32_t tg)
+{
+    const int org = (int)(tg / 2) - GF_WIN / 2 > 0 ? (int)(tg / 2) - GF_WIN / 2 : 0;
+    return (uint32_t)(org + widx / GF_WIN) * tg + (uint32_t)(org + widx % GF_WIN);
+}
+
 // ---- pass 1: histogram over the tiles ----------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gf_hist_kernel(GridParams P, uint32_t tg, uint32_t *__restrict__ hist,
                                                       unsigned long long *n_outside)
 {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    __shared__ uint32_t sh[GF_WIN * GF_WIN];
+    const bool use_win = P.nch == 1;
     const int lane = threadIdx.x & 31;
-    uint32_t key = GF_DEAD;
-    bool outside = false;
-    if (idx < P.nuv * P.nf) {
-        const GfVis x = gf_vis(P, idx);
-        if (x.good) key = gf_key(P, x, idx, tg);
-        else outside = true;
+    if (use_win) {
+        for (int i = threadIdx.x; i < GF_WIN * GF_WIN; i += 256) sh[i] = 0;
+        __syncthreads();
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, key);
-    if (key != GF_DEAD && (int)(__ffs(peers) - 1) == lane) atomicAdd(hist + key, (uint32_t)__popc(peers));
+    uint32_t n_out = 0;
+#pragma unroll
+    for (int it = 0; it < GF_PASS_ITEMS; it++) {
+        const int64_t idx = (int64_t)blockIdx.x * GF_PASS_TILE + it * 256 + threadIdx.x;
+        uint32_t key = GF_DEAD;
+        int widx = -1;
+        if (idx < P.nuv * P.nf) {
+            const GfVis x = gf_vis(P, idx);
+            if (x.good) {
+                key = gf_key(P, x, idx, tg);
+                if (use_win) widx = gf_window_index(x.gi, x.gj, tg);
+            } else
+                n_out++;
+        }
+        if (use_win) {
+            if (widx >= 0) atomicAdd(&sh[widx], 1u);
+            else if (key != GF_DEAD) atomicAdd(hist + key, 1u);
+        } else {
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            if (key != GF_DEAD && (int)(__ffs(peers) - 1) == lane) atomicAdd(hist + key, (uint32_t)__popc(peers));
+        }
+    }
     if (n_outside) {
-        const uint32_t m = __ballot_sync(0xffffffffu, outside);
-        if (lane == 0 && m) atomicAdd(n_outside, (unsigned long long)__popc(m));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_out += __shfl_xor_sync(0xffffffffu, n_out, o);
+        if (lane == 0 && n_out) atomicAdd(n_outside, (unsigned long long)n_out);
+    }
+    if (use_win) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < GF_WIN * GF_WIN; i += 256)
+            if (sh[i]) atomicAdd(hist + gf_window_key(i, tg), sh[i]);
     }
 }
 
@@ -197,68 +242,115 @@ __global__ void __launch_bounds__(256) gf_scatter_kernel(GridParams P, uint32_t 
                                                          const uint64_t *__restrict__ seg_off,
                                                          uint32_t *__restrict__ fill, double2 *__restrict__ rec)
 {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    __shared__ uint32_t sh[GF_WIN * GF_WIN];           // window counts, then the block's base slot in each window tile
+    const bool use_win = P.nch == 1;
     const int lane = threadIdx.x & 31;
-    uint32_t key = GF_DEAD;
-    GfVis x;
-    if (idx < P.nuv * P.nf) {
-        x = gf_vis(P, idx);
-        if (x.good) key = gf_key(P, x, idx, tg);
+    if (use_win) {
+        for (int i = threadIdx.x; i < GF_WIN * GF_WIN; i += 256) sh[i] = 0;
+        __syncthreads();
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (key != GF_DEAD && leader == lane) base = atomicAdd(fill + key, (uint32_t)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (key == GF_DEAD) return;
-    const uint32_t pos = (uint32_t)(gf_prefix(excl, seg_off, key) & GF_LOW40) + base + __popc(peers & ((1u << lane) - 1u));
-    double w;
-    const double re = P.re[idx], im = P.im[idx];
-    if (w_src) w = w_src[idx];
-    else {
-        w = P.w_in[idx];                                    // :351-353
-        w = w < 0 ? 0.0 : w;
-        if (re == 0 && im == 0) w = 0.0;
+    GfVis x[GF_PASS_ITEMS];
+    uint32_t key[GF_PASS_ITEMS], slot[GF_PASS_ITEMS];   // slot: rank inside the block's share of the tile run
+    int widx[GF_PASS_ITEMS];
+    double dre[GF_PASS_ITEMS], dim[GF_PASS_ITEMS], dw[GF_PASS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < GF_PASS_ITEMS; it++) {             // the data loads go out before the atomics' round trips
+        const int64_t idx = (int64_t)blockIdx.x * GF_PASS_TILE + it * 256 + threadIdx.x;
+        dre[it] = dim[it] = dw[it] = 0.0;
+        if (idx < P.nuv * P.nf) {
+            dre[it] = P.re[idx];
+            dim[it] = P.im[idx];
+            dw[it] = w_src ? w_src[idx] : P.w_in[idx];
+        }
     }
-    double2 *r = rec + 3 * (size_t)pos;
-    r[0] = make_double2(x.pu, w);
-    r[1] = make_double2(re * w, im * w);
-    r[2] = make_double2(x.pv, __longlong_as_double((long long)((unsigned long long)x.gi | ((unsigned long long)x.gj << 32))));
+#pragma unroll
+    for (int it = 0; it < GF_PASS_ITEMS; it++) {
+        const int64_t idx = (int64_t)blockIdx.x * GF_PASS_TILE + it * 256 + threadIdx.x;
+        key[it] = GF_DEAD;
+        widx[it] = -1;
+        slot[it] = 0;
+        if (idx < P.nuv * P.nf) {
+            x[it] = gf_vis(P, idx);
+            if (x[it].good) {
+                key[it] = gf_key(P, x[it], idx, tg);
+                if (use_win) widx[it] = gf_window_index(x[it].gi, x[it].gj, tg);
+            }
+        }
+        if (use_win) {
+            if (widx[it] >= 0) slot[it] = atomicAdd(&sh[widx[it]], 1u);
+            else if (key[it] != GF_DEAD) slot[it] = atomicAdd(fill + key[it], 1u);
+        } else {
+            const uint32_t peers = __match_any_sync(0xffffffffu, key[it]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (key[it] != GF_DEAD && leader == lane) base = atomicAdd(fill + key[it], (uint32_t)__popc(peers));
+            slot[it] = __shfl_sync(0xffffffffu, base, leader) + __popc(peers & ((1u << lane) - 1u));
+        }
+    }
+    if (use_win) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < GF_WIN * GF_WIN; i += 256) {
+            const uint32_t cnt = sh[i];
+            if (cnt) sh[i] = atomicAdd(fill + gf_window_key(i, tg), cnt);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int it = 0; it < GF_PASS_ITEMS; it++) {
+        if (key[it] == GF_DEAD) continue;
+        const uint32_t pos = (uint32_t)(gf_prefix(excl, seg_off, key[it]) & GF_LOW40) + slot[it] +
+                             (widx[it] >= 0 ? sh[widx[it]] : 0u);
+        const double re = dre[it], im = dim[it];
+        double w = dw[it];
+        if (!w_src) {                                           // :351-353
+            w = w < 0 ? 0.0 : w;
+            if (re == 0 && im == 0) w = 0.0;
+        }
+        double2 *r = rec + 3 * (size_t)pos;
+        r[0] = make_double2(x[it].pu, w);
+        r[1] = make_double2(re * w, im * w);
+        r[2] = make_double2(x[it].pv, __longlong_as_double((long long)((unsigned long long)x[it].gi |
+                                                                        ((unsigned long long)x[it].gj << 32))));
+    }
 }
 
-// ---- convolution kernel factors, Horner form ----------------------------------------------------------------
+// ---- convolution kernel factors ------------------------------------------------------------------------------
 // exp_sinc is separable: exp_sinc(u, v) = g(u) g(v) / norm, g(x) = sinc(x/1.55) exp(-(x/2.52)^2) inside |x| < 3,
-// with the reference's degree-16 Taylor polynomial for sinc and degree-5 polynomial for exp (:547-574).  Same
-// polynomials as k_exp_sinc (grid.cuh), evaluated by Horner's rule: 1e-16-level differences from the reference's
-// term-by-term form, below this mode's own summation-order noise.
+// with the reference's degree-16 Taylor polynomial for sinc and degree-5 polynomial for exp (:547-574).  The powers
+// and the sum are formed in the reference's order (like k_sinc / k_exp of grid.cuh), NOT by Horner's rule: where the
+// sinc polynomial crosses zero (x = 1.55) the factor is pure rounding residue, and a weighted mean over a cell fed by
+// such factors moves by 4e-11 when the residue changes - the same operation order keeps the residues correlated
+// with the reference's (measured: 1e-12 vs 4e-11 with Horner).  Coefficients live in the constant bank: as literals
+// every DFMA drags two UMOVs along to build its 64-bit operand.
+__constant__ double gf_poly[16] = {1. / 6., 1. / 120., 1. / 5040., 1. / 362880., 1. / 39916800., 1. / 6227020800.,
+                                   1. / 1307674368000., 1. / 355687428096000.,
+                                   0.5, 1. / 6., 1. / 24., 1. / 120.,
+                                   1. / 1.55, 3.14159265358979323846, 1. / 2.52, 0.};
 __device__ __forceinline__ double gf_exp_sinc_1d(double x)
 {
     if (fabs(x) >= 3.0) return 0.;
-    const double xp = x * (1. / 1.55) * 3.14159265358979323846;
-    const double y = xp * xp;
-    double s = 1. / 355687428096000.;
-    s = fma(s, y, -1. / 1307674368000.);
-    s = fma(s, y, 1. / 6227020800.);
-    s = fma(s, y, -1. / 39916800.);
-    s = fma(s, y, 1. / 362880.);
-    s = fma(s, y, -1. / 5040.);
-    s = fma(s, y, 1. / 120.);
-    s = fma(s, y, -1. / 6.);
-    s = fma(s, y, 1.);
-    const double a = x * (1. / 2.52);
-    const double z = -(a * a);
-    double e = 1. / 120.;
-    e = fma(e, z, 1. / 24.);
-    e = fma(e, z, 1. / 6.);
-    e = fma(e, z, 0.5);
-    e = fma(e, z, 1.);
-    e = fma(e, z, 1.);
+    const double xp = x * gf_poly[12] * gf_poly[13];
+    const double x2 = xp * xp, x4 = x2 * x2, x6 = x4 * x2, x8 = x4 * x4, x10 = x8 * x2, x12 = x8 * x4, x14 = x8 * x6,
+                 x16 = x8 * x8;
+    const double s = 1. - x2 * gf_poly[0] + x4 * gf_poly[1] - x6 * gf_poly[2] + x8 * gf_poly[3] - x10 * gf_poly[4] +
+                     x12 * gf_poly[5] - x14 * gf_poly[6] + x16 * gf_poly[7];
+    const double a = x * gf_poly[14];
+    const double z = -1 * (a * a);
+    const double z2 = z * z, z3 = z2 * z, z4 = z2 * z2, z5 = z4 * z;
+    const double e = 1 + z + z2 * gf_poly[8] + z3 * gf_poly[9] + z4 * gf_poly[10] + z5 * gf_poly[11];
     return s * e;
 }
 
 // ---- tile kernel ------------------------------------------------------------------------------------------------
-// WIDTH = footprint width lo + hi + 1 (pillbox 3, exp*sinc 6, box sums 3 / 5 / 7); MODE 0 = main sums (three maps),
+// WIDTH = footprint width lo + hi + 1 (pillbox 3, exp*sinc 6, box sums 1 / 3 / 5 / 7); MODE 0 = main sums (three maps),
 // MODE 1 = box sums of the weights (one map, all factors 1).
+//
+// One warp per work item.  The item's visibilities are put in home-row order (8 buckets); then per chunk of 32:
+//   A  lane = visibility: the 48-byte record into shared memory;
+//   B  lane = (visibility, axis): the WIDTH kernel factors of that axis, WIDTH independent polynomial evaluations per lane;
+//   C  half-warp = visibility, lane = region column: WIDTH x NMAP DFMAs per lane into registers, all of them live
+//      because the bucket (home row) fixes the rows.  When the bucket changes the two half-warps add their registers
+//      to the warp's private region in shared memory (plain read-modify-write, one half after the other).
 template <int WIDTH, int MODE>
 __global__ void __launch_bounds__(GF_WARPS * 32) gf_tile_kernel(GridParams P, int lo, uint32_t tg,
                                                                 const double2 *__restrict__ rec,
@@ -271,18 +363,25 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gf_tile_kernel(GridParams P, in
     constexpr int SIDE = 8 + WIDTH - 1;                 // region side (<= 14)
     constexpr int NMAP = MODE == 0 ? 3 : 1;
     constexpr int FUS = 33;                             // padded lane stride of the FU columns (bank-conflict free)
-    __shared__ double s_reg[GF_WARPS][NMAP][SIDE][16];  // the warp's private region: [map][row][column]
-    __shared__ double s_fu[GF_WARPS][WIDTH][FUS];       // column factors [slot][staged visibility]
-    __shared__ __align__(16) double s_b[GF_WARPS][32][12];   // per staged visibility: FV[0..6], w, w re, w im, meta
+    constexpr int SBS = 18;                             // doubles per staged visibility (16-byte aligned, spreads banks)
+    constexpr int RC = SIDE + (SIDE & 1);               // region columns held (even: rows stay 16-byte aligned)
+    __shared__ double s_reg[GF_WARPS][NMAP][SIDE][RC];  // the warp's private region: [map][row][column]
+    __shared__ double s_fu[GF_WARPS][WIDTH][FUS];       // column factors: [slot][visibility]
+    // per staged visibility: [0..6] row factors, [8] w, [9] w re, [10] w im, [11] meta, [12] pos_u, [13] pos_v
+    __shared__ __align__(16) double s_b[GF_WARPS][32][SBS];
+    __shared__ double s_cen[GF_WARPS][2][16];           // cell centres of the region's columns / rows
     __shared__ uint16_t s_ord[GF_WARPS][GF_ITEM];       // the item's visibilities in bucket (home row) order
+    __shared__ int s_cnt[GF_WARPS][12];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = lane >> 4, c = lane & 15;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t nitems = (uint32_t)(gf_prefix(excl, seg_off, nkeys) >> 40);
-    double(*reg)[SIDE][16] = s_reg[warp];
+    double(*reg)[SIDE][RC] = s_reg[warp];
     double(*fu)[FUS] = s_fu[warp];
-    double(*sb)[12] = s_b[warp];
+    double(*sb)[SBS] = s_b[warp];
     uint16_t *ord = s_ord[warp];
+    int *bcnt = s_cnt[warp];
+    const double *fu_lane = &fu[0][0] + c * FUS;
 
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(work_counter, 1u);
@@ -297,46 +396,51 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gf_tile_kernel(GridParams P, in
         const int n = (int)(item.end - item.begin);
         const double2 *irec = rec + 3 * (size_t)item.begin;
 
-        // zero the region
+        // zero the region and the bucket counters; centres of the region's cells
         {
             double *z = &reg[0][0][0];
-            for (int i = lane; i < NMAP * SIDE * 16; i += 32) z[i] = 0.0;
+            for (int i = lane; i < NMAP * SIDE * RC; i += 32) z[i] = 0.0;
+            if (lane < 12) bcnt[lane] = 0;
+            const int cell = (half ? tl : tm) * 8 - lo + c;
+            s_cen[warp][half][c] = (cell >= 0 && cell < P.G) ? (half ? P.vv[cell] : P.uu[cell]) : 0.0;
         }
-        // bucket = home row inside the tile: counting sort of the item's visibilities with ballots
-        int bk[GF_ITEM / 32];                          // (chunks past the item's end are skipped: uniform branches)
-        int cnt[8];
-#pragma unroll
-        for (int b = 0; b < 8; b++) cnt[b] = 0;
+        __syncwarp();
+        // bucket = home row inside the tile: counting sort of the item's visibilities
+        int bk[GF_ITEM / 32], rk[GF_ITEM / 32];
 #pragma unroll
         for (int q = 0; q < GF_ITEM / 32; q++) {
-            const int i = q * 32 + lane;
             bk[q] = 8;
+            rk[q] = 0;
             if (q * 32 >= n) continue;
+            const int i = q * 32 + lane;
             if (i < n) {
                 const unsigned long long ij = (unsigned long long)__double_as_longlong(irec[3 * i + 2].y);
                 bk[q] = (int)(uint32_t)(ij >> 32) - tl * 8;
             }
-#pragma unroll
-            for (int b = 0; b < 8; b++) cnt[b] += __popc(__ballot_sync(0xffffffffu, bk[q] == b));
+            const uint32_t peers = __match_any_sync(0xffffffffu, bk[q]);
+            const int before = bcnt[bk[q]];
+            __syncwarp();
+            if ((int)(__ffs(peers) - 1) == lane) bcnt[bk[q]] = before + __popc(peers);
+            __syncwarp();
+            rk[q] = before + __popc(peers & lt);
         }
+        // counts -> bucket starts (bcnt[b] = first sorted position of bucket b, bcnt[8] = n)
         {
-            int run = 0;
+            int x = lane < 9 ? bcnt[lane] : 0;
+            const int own = x;
 #pragma unroll
-            for (int b = 0; b < 8; b++) {
-                const int x = cnt[b];
-                cnt[b] = run;
-                run += x;
+            for (int o = 1; o < 16; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
             }
+            __syncwarp();
+            if (lane < 9) bcnt[lane] = x - own;
         }
+        __syncwarp();
 #pragma unroll
         for (int q = 0; q < GF_ITEM / 32; q++) {
             if (q * 32 >= n) continue;
-#pragma unroll
-            for (int b = 0; b < 8; b++) {
-                const uint32_t m = __ballot_sync(0xffffffffu, bk[q] == b);
-                if (bk[q] == b) ord[cnt[b] + __popc(m & lt)] = (uint16_t)(q * 32 + lane);
-                cnt[b] += __popc(m);
-            }
+            if (bk[q] < 8) ord[bcnt[bk[q]] + rk[q]] = (uint16_t)(q * 32 + lane);
         }
         __syncwarp();
 
@@ -345,93 +449,102 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gf_tile_kernel(GridParams P, in
         for (int m = 0; m < NMAP; m++)
 #pragma unroll
             for (int r = 0; r < WIDTH; r++) acc[m][r] = 0.0;
-        int cb = -1;                                     // bucket the accumulators of this half-warp belong to
+        int cb = -1;                                     // bucket the accumulators belong to (warp-uniform)
         auto flush = [&]() {
 #pragma unroll
-            for (int m = 0; m < NMAP; m++)
+            for (int hh = 0; hh < 2; hh++) {
+                if (half == hh && c < RC) {
 #pragma unroll
-                for (int r = 0; r < WIDTH; r++) {
-                    reg[m][cb + r][c] += acc[m][r];
-                    acc[m][r] = 0.0;
+                    for (int m = 0; m < NMAP; m++)
+#pragma unroll
+                        for (int r = 0; r < WIDTH; r++) {
+                            reg[m][cb + r][c] += acc[m][r];
+                            acc[m][r] = 0.0;
+                        }
                 }
+                __syncwarp();
+            }
         };
 
         for (int p0 = 0; p0 < n; p0 += 32) {
             const int nst = n - p0 < 32 ? n - p0 : 32;
-            // ---- factor phase: lane = visibility ----
+            // ---- A: lane = visibility ----
             if (lane < nst) {
                 const double2 *r = irec + 3 * (size_t)ord[p0 + lane];
                 const double2 c0 = r[0], c1 = r[1], c2 = r[2];
                 const unsigned long long ij = (unsigned long long)__double_as_longlong(c2.y);
-                const int gi = (int)(uint32_t)ij, gj = (int)(uint32_t)(ij >> 32);
-#pragma unroll
-                for (int o = 0; o < WIDTH; o++) {
-                    const int cu = gi - lo + o, cv = gj - lo + o;
-                    double gu = 0.0, gv = 0.0;
-                    if (MODE == 0) {
-                        if (cu >= 0 && cu < P.G) {
-                            const double d = (c0.x - P.uu[cu]) * P.inv_binsize;
-                            // 1/norm goes with the u factor
-                            gu = P.conv ? gf_exp_sinc_1d(d) * (1. / 2.350016262343186) : (fabs(d) >= 0.5 ? 0.0 : 1.0);
-                        }
-                        if (cv >= 0 && cv < P.G) {
-                            const double d = (c2.x - P.vv[cv]) * P.inv_binsize;
-                            gv = P.conv ? gf_exp_sinc_1d(d) : (fabs(d) >= 0.5 ? 0.0 : 1.0);
-                        }
-                    } else {
-                        gu = (cu >= 0 && cu < P.G) ? 1.0 : 0.0;
-                        gv = (cv >= 0 && cv < P.G) ? 1.0 : 0.0;
-                    }
-                    fu[o][lane] = gu;
-                    sb[lane][o] = gv;
-                }
-                sb[lane][7] = c0.y;
-                sb[lane][8] = c1.x;
-                sb[lane][9] = c1.y;
-                sb[lane][10] = __longlong_as_double((long long)((gi - tm * 8) | ((gj - tl * 8) << 8)));
+                const int di = (int)(uint32_t)ij - tm * 8, dj = (int)(uint32_t)(ij >> 32) - tl * 8;
+                // meta: low word = offset of this visibility's column factor for region column 0 (lane c adds c * FUS),
+                // high word = home column | home row << 4 (inside the tile)
+                const long long meta = (long long)(uint32_t)(lane - FUS * di) | ((long long)(di | (dj << 4)) << 32);
+                double2 *d = reinterpret_cast<double2 *>(sb[lane]);
+                d[4] = make_double2(c0.y, c1.x);
+                d[5] = make_double2(c1.y, __longlong_as_double(meta));
+                d[6] = make_double2(c0.x, c2.x);
             }
             __syncwarp();
-            // ---- accumulate phase: half-warp = visibility, lane = region column ----
-            for (int t0 = 0; t0 < nst; t0 += 2) {
-                const int v = t0 + half;
-                const bool valid = v < nst;
-                const double *vb = sb[valid ? v : 0];
-                const int meta = (int)__double_as_longlong(vb[10]);
-                const int di = meta & 0xff, b = meta >> 8;
-                const bool need = valid && cb >= 0 && b != cb;
-                if (__any_sync(0xffffffffu, need)) {
-                    if (need && half == 0) flush();
-                    __syncwarp();
-                    if (need && half == 1) flush();
-                    __syncwarp();
+            // ---- B: lane = (visibility, axis) ----
+            for (int v = lane >> 1; v < nst; v += 16) {
+                const int axis = lane & 1;
+                const int dd = (int)((unsigned long long)__double_as_longlong(sb[v][11]) >> 32);
+                const int home = axis ? (dd >> 4) : (dd & 15);
+                const int cell0 = (axis ? tl : tm) * 8 - lo + home;
+                const double pos = sb[v][12 + axis];
+                const double *cen = s_cen[warp][axis] + home;
+                double g[WIDTH];
+#pragma unroll
+                for (int o = 0; o < WIDTH; o++) {
+                    g[o] = 0.0;
+                    if (cell0 + o >= 0 && cell0 + o < P.G) {
+                        if (MODE == 0) {
+                            const double d = (pos - cen[o]) * P.inv_binsize;
+                            g[o] = P.conv ? gf_exp_sinc_1d(d) : (fabs(d) >= 0.5 ? 0.0 : 1.0);
+                        } else
+                            g[o] = 1.0;
+                    }
                 }
-                if (valid) {
+                if (axis) {
+#pragma unroll
+                    for (int o = 0; o < WIDTH; o++) sb[v][o] = g[o];
+                } else {
+                    const double norm = (MODE == 0 && P.conv) ? (1. / 2.350016262343186) : 1.0;   // 1/norm with the u factor
+#pragma unroll
+                    for (int o = 0; o < WIDTH; o++) fu[o][v] = g[o] * norm;
+                }
+            }
+            __syncwarp();
+            // ---- C: half-warp = visibility, lane = region column; bucket by bucket ----
+            for (int b = 0; b < 8; b++) {
+                const int s0 = (bcnt[b] > p0 ? bcnt[b] : p0) - p0;
+                const int e0 = (bcnt[b + 1] < p0 + nst ? bcnt[b + 1] : p0 + nst) - p0;
+                if (s0 >= e0) continue;
+                if (b != cb) {
+                    if (cb >= 0) flush();
                     cb = b;
-                    const int o = c - di;
-                    const double f = (o >= 0 && o < WIDTH) ? fu[o][v] : 0.0;
-                    const double xw = f * vb[7];
-                    if (MODE == 0) {
-                        const double xr = f * vb[8], xi = f * vb[9];
+                }
+                for (int v = s0 + half; v < e0; v += 2) {
+                    const double *vb = sb[v];
+                    const double2 wx = *reinterpret_cast<const double2 *>(vb + 8);       // w, w re
+                    const double2 ym = *reinterpret_cast<const double2 *>(vb + 10);      // w im, meta
+                    const long long meta = __double_as_longlong(ym.y);
+                    const int off = (int)meta, di = (int)(meta >> 32) & 15;
+                    double fv[8];
 #pragma unroll
-                        for (int r = 0; r < WIDTH; r++) {
-                            const double fv = vb[r];
-                            acc[0][r] = fma(fv, xw, acc[0][r]);
-                            acc[1][r] = fma(fv, xr, acc[1][r]);
-                            acc[2][r] = fma(fv, xi, acc[2][r]);
-                        }
-                    } else {
+                    for (int r = 0; r < (WIDTH + 1) / 2; r++)
+                        *reinterpret_cast<double2 *>(&fv[2 * r]) = *reinterpret_cast<const double2 *>(vb + 2 * r);
+                    const double f = (unsigned)(c - di) < (unsigned)WIDTH ? fu_lane[off] : 0.0;
 #pragma unroll
-                        for (int r = 0; r < WIDTH; r++) acc[0][r] = fma(vb[r], xw, acc[0][r]);
+                    for (int m = 0; m < NMAP; m++) {
+                        const double x = f * (m == 0 ? wx.x : m == 1 ? wx.y : ym.x);
+#pragma unroll
+                        for (int r = 0; r < WIDTH; r++) acc[m][r] = fma(fv[r], x, acc[m][r]);
                     }
                 }
             }
             __syncwarp();
         }
-        // the two half-warps' last accumulators, then the region to the map
-        if (cb >= 0 && half == 0) flush();
-        __syncwarp();
-        if (cb >= 0 && half == 1) flush();
-        __syncwarp();
+        if (cb >= 0) flush();
+        // the region to the map
         {
             const int m0 = tm * 8 - lo + c;
             for (int rr0 = 0; rr0 < SIDE; rr0 += 2) {
@@ -501,7 +614,7 @@ int grid_fast_scatter(const GridParams &P, int smode, uint32_t lo, uint32_t hi, 
         PDSB_CUDA(cudaGetLastError());
         return PDSB_OK;
     }
-    PDSB_REQUIRE((smode == 0 && (width == 3 || width == 6)) || (smode == 1 && (width == 3 || width == 5 || width == 7)),
+    PDSB_REQUIRE((smode == 0 && (width == 3 || width == 6)) || (smode == 1 && (width == 1 || width == 3 || width == 5 || width == 7)),
                  "footprint width of the fast gridding mode");
     const uint32_t tg = ((uint32_t)P.G + 7u) >> 3;
     const uint64_t nkeys64 = (uint64_t)tg * tg * (uint64_t)P.nch;
@@ -526,7 +639,7 @@ int grid_fast_scatter(const GridParams &P, int smode, uint32_t lo, uint32_t hi, 
     PDSB_CUDA(cudaMemsetAsync(base, 0, o_excl, c.stream));              // hist, fill, counter
     {
         LaunchScope ls("grid_tile_hist");
-        gf_hist_kernel<<<ceil_div(nvis, 256), 256, 0, c.stream>>>(P, tg, hist, n_outside);
+        gf_hist_kernel<<<ceil_div(nvis, GF_PASS_TILE), 256, 0, c.stream>>>(P, tg, hist, n_outside);
         PDSB_CUDA(cudaGetLastError());
     }
     {
@@ -538,7 +651,7 @@ int grid_fast_scatter(const GridParams &P, int smode, uint32_t lo, uint32_t hi, 
     }
     {
         LaunchScope ls("grid_tile_records");
-        gf_scatter_kernel<<<ceil_div(nvis, 256), 256, 0, c.stream>>>(P, tg, w_src, excl, seg_off, fill, rec);
+        gf_scatter_kernel<<<ceil_div(nvis, GF_PASS_TILE), 256, 0, c.stream>>>(P, tg, w_src, excl, seg_off, fill, rec);
         PDSB_CUDA(cudaGetLastError());
     }
     {
@@ -547,6 +660,7 @@ int grid_fast_scatter(const GridParams &P, int smode, uint32_t lo, uint32_t hi, 
     launch_tile<W, M>(P, (int)lo, tg, rec, items, excl, seg_off, nkeys, counter, t_re, t_im, t_w)
         if (smode == 0 && width == 3) PDSB_GF(3, 0);
         else if (smode == 0) PDSB_GF(6, 0);
+        else if (width == 1) PDSB_GF(1, 1);
         else if (width == 3) PDSB_GF(3, 1);
         else if (width == 5) PDSB_GF(5, 1);
         else PDSB_GF(7, 1);
