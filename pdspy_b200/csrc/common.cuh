@@ -76,6 +76,8 @@ struct Context {
     Scratch small_dev;     // tiny per-call device arrays (channel scale factors)
     Scratch fft_fb;        // invert(), sizes that are not a power of two: transform of Bluestein's chirp, for size fft_fb_n
     int fft_fb_n = 0;
+    Scratch fft_tw;        // galario path: twiddle table exp(+2 pi i j / n), j < n/2, for size fft_tw_n
+    int fft_tw_n = 0;
     Scratch mma_ws;        // tensor-core kernel: per-round lattice quanta and per-plane unscale factors
 };
 

@@ -105,5 +105,6 @@ size_t trift_record_bytes();
 // fft.cu: inverse-sign 2-D transform of every channel of a cube, both-axes fftshift on input and output,
 // channel-fastest output (used by the galario-algorithm path of vis.cu)
 int fft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Y);
+int rfft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Yh);
 
 }  // namespace pdsb

@@ -7,6 +7,7 @@
 // power of two (the reference takes any imsize: scipy's ifft2) go through Bluestein's chirp-z form of the
 // same row transform on the next power of two >= 2n - 1 (bluestein_rows_kernel).
 #include "common.cuh"
+#include <algorithm>
 
 namespace pdsb {
 
@@ -211,6 +212,173 @@ int fft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, dou
     LaunchScope ls("fft2_planes");
     ifft_rows_kernel<<<dim3(n, nf), threads, smem, c.stream>>>(cube_dev, nullptr, nf, nullptr, T, n, logn, 0, flip, 1);
     ifft_rows_kernel<<<dim3(n, nf), threads, smem, c.stream>>>(nullptr, nullptr, 0, T, Y, n, logn, 1, 0, 0, nf, 1);
+    PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
+}
+
+
+// ---- the galario path's forward transform: real planes -> half spectrum ----------------------------------------
+// rfft2_planes computes what fft2_planes computes, for the columns B = (b + n/2) % n, b = 0 .. n/2, that galario's
+// rfft2-based sampler reads (vis.cu: fft_sample_one), and stores them compactly:
+//     Yh[(A (n/2 + 1) + b) nf + i] = Ysh_i[A][(b + n/2) % n]
+// It does a quarter of the butterflies of the general routine and moves every byte in full 32-byte sectors:
+//   * the planes are real, so two adjacent channels (adjacent doubles of the channel-fastest cube) go through ONE
+//     complex row transform as z = x_p + i x_{p+1} and are separated afterwards,
+//     A_p[b] = (Z[b] + conj Z[n-b]) / 2,  A_{p+1}[b] = (Z[b] - conj Z[n-b]) / (2 i);
+//   * only b <= n/2 is kept (the other half is its conjugate), so the column pass transforms n/2 + 1 rows per plane;
+//   * a block works on 2 image rows x PB plane pairs (row pass) or PB planes (column pass) at once, so that the
+//     transposed stores of the row pass and the channel-fastest stores of the column pass are contiguous runs;
+//   * two radix-2 stages per barrier (radix-4 butterflies in registers, same operations as the radix-2 routine),
+//     twiddles from a table computed once per size.
+__global__ void __launch_bounds__(256) fft_twiddle_kernel(double2 *__restrict__ tw, int n)
+{
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= n / 2) return;
+    double ws, wc;
+    sincospi(2.0 * (double)j / (double)n, &ws, &wc);
+    tw[j] = make_double2(wc, ws);
+}
+
+// in-place transforms of nfft rows of length n (bit-reversed input) held at w + f * n, kernel e^{+2 pi i jk/n};
+// tpf threads per row, the block's threads are [row][tpf]
+__device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, int n, int logn, int nfft, int tpf)
+{
+    const int f = threadIdx.x / tpf, tl = threadIdx.x % tpf;
+    double2 *x = w + (size_t)f * n;
+    int s = 1;
+    for (; s + 1 <= logn; s += 2) {
+        const int half = 1 << (s - 1), ts1 = n >> s, ts2 = n >> (s + 1);
+        if (f < nfft)
+            for (int idx = tl; idx < n / 4; idx += tpf) {
+                const int k = idx & (half - 1);
+                const int j = ((idx >> (s - 1)) << (s + 1)) + k;
+                double2 a0 = x[j], a1 = x[j + half], a2 = x[j + 2 * half], a3 = x[j + 3 * half];
+                const double2 w1 = tw[k * ts1];
+                double2 t = cmul(w1, a1);
+                a1 = make_double2(a0.x - t.x, a0.y - t.y);
+                a0 = make_double2(a0.x + t.x, a0.y + t.y);
+                t = cmul(w1, a3);
+                a3 = make_double2(a2.x - t.x, a2.y - t.y);
+                a2 = make_double2(a2.x + t.x, a2.y + t.y);
+                const double2 w2a = tw[k * ts2], w2b = tw[(k + half) * ts2];
+                t = cmul(w2a, a2);
+                x[j] = make_double2(a0.x + t.x, a0.y + t.y);
+                x[j + 2 * half] = make_double2(a0.x - t.x, a0.y - t.y);
+                t = cmul(w2b, a3);
+                x[j + half] = make_double2(a1.x + t.x, a1.y + t.y);
+                x[j + 3 * half] = make_double2(a1.x - t.x, a1.y - t.y);
+            }
+        __syncthreads();
+    }
+    if (s <= logn) {                                       // odd number of stages: one radix-2 stage left
+        const int half = 1 << (s - 1), tstep = n >> s;
+        if (f < nfft)
+            for (int idx = tl; idx < n / 2; idx += tpf) {
+                const int k = idx & (half - 1);
+                const int j = ((idx >> (s - 1)) << s) + k;
+                const double2 t = cmul(tw[k * tstep], x[j + half]), a = x[j];
+                x[j] = make_double2(a.x + t.x, a.y + t.y);
+                x[j + half] = make_double2(a.x - t.x, a.y - t.y);
+            }
+        __syncthreads();
+    }
+}
+
+// row pass: block = rows (2 blockIdx.x, 2 blockIdx.x + 1) of the shifted planes x plane pairs [PB blockIdx.y, ...)
+// -> T[plane][b][row], b <= n/2  (T: [nf][n/2 + 1][n])
+__global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict__ cube, const double2 *__restrict__ twg,
+                                                        double2 *__restrict__ T, int n, int logn, int nf, int flip,
+                                                        int PB, int tpf)
+{
+    extern __shared__ double2 srow[];
+    const int h = n / 2, npair = (nf + 1) / 2;
+    const int pair0 = blockIdx.y * PB;
+    const int pb_n = npair - pair0 < PB ? npair - pair0 : PB;          // pairs this block really has
+    const int nfft = 2 * pb_n;                                          // [row 0..1][pair]
+    double2 *tw = srow + (size_t)2 * PB * n;
+    for (int j = threadIdx.x; j < h; j += blockDim.x) tw[j] = twg[j];
+    // loads: pair fastest (adjacent doubles of the cube), then column, then row
+    for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
+        const int pb = idx % pb_n, c = (idx / pb_n) % n, rb = idx / (pb_n * n);
+        const int rs = (2 * blockIdx.x + rb + h) % n;
+        const int64_t src = ((int64_t)(flip ? n - 1 - rs : rs) * n + (c + h) % n) * nf + 2 * (pair0 + pb);
+        const double re = cube[src], im = 2 * (pair0 + pb) + 1 < nf ? cube[src + 1] : 0.0;
+        srow[(size_t)(rb * pb_n + pb) * n + bitrev((unsigned)c, logn)] = make_double2(re, im);
+    }
+    __syncthreads();
+    fft_plus_rows_r4(srow, tw, n, logn, nfft, tpf);
+    // separate the two planes of every pair; stores: row fastest (adjacent double2 of T), then b, then pair
+    const int64_t ps = (int64_t)(h + 1) * n;                            // plane stride of T
+    for (int idx = threadIdx.x; idx < 2 * (h + 1) * pb_n; idx += blockDim.x) {
+        const int rb = idx & 1, b = (idx >> 1) % (h + 1), pb = (idx >> 1) / (h + 1);
+        const double2 *x = srow + (size_t)(rb * pb_n + pb) * n;
+        const double2 z = x[b], zc = x[(n - b) % n];
+        const int plane = 2 * (pair0 + pb);
+        const int64_t o = (int64_t)plane * ps + (int64_t)b * n + 2 * blockIdx.x + rb;
+        T[o] = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
+        if (plane + 1 < nf) T[o + ps] = make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
+    }
+}
+
+// column pass: block = row b of T for planes [PB blockIdx.y, ...) -> Yh[((a + h) % n (h + 1) + b) nf + plane]
+__global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restrict__ T, const double2 *__restrict__ twg,
+                                                        double2 *__restrict__ Yh, int n, int logn, int nf, int PB, int tpf)
+{
+    extern __shared__ double2 srow[];
+    const int h = n / 2, b = blockIdx.x;
+    const int plane0 = blockIdx.y * PB;
+    const int nfft = nf - plane0 < PB ? nf - plane0 : PB;
+    double2 *tw = srow + (size_t)PB * n;
+    for (int j = threadIdx.x; j < h; j += blockDim.x) tw[j] = twg[j];
+    const int64_t ps = (int64_t)(h + 1) * n;
+    for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
+        const int r = idx % n, pl = idx / n;
+        srow[(size_t)pl * n + bitrev((unsigned)r, logn)] = T[(int64_t)(plane0 + pl) * ps + (int64_t)b * n + r];
+    }
+    __syncthreads();
+    fft_plus_rows_r4(srow, tw, n, logn, nfft, tpf);
+    for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
+        const int pl = idx % nfft, a = idx / nfft;
+        Yh[((int64_t)((a + h) % n) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * n + a];
+    }
+}
+
+// T: [nf][n/2 + 1][n] scratch, Yh: [n][n/2 + 1][nf]
+int rfft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Yh)
+{
+    Context &c = ctx();
+    int logn = 0;
+    while ((1 << logn) < n) logn++;
+    PDSB_REQUIRE(n >= 2 && (1 << logn) == n && n <= 4096, "rfft2_planes: side must be a power of two in [2, 4096]");
+    static bool attr = false;
+    if (!attr) {
+        PDSB_CUDA(cudaFuncSetAttribute(rfft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PDSB_CUDA(cudaFuncSetAttribute(rfft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    PDSB_CHECK(c.fft_tw.ensure((size_t)(n / 2 + 1) * sizeof(double2)));
+    if (c.fft_tw_n != n) {
+        LaunchScope ls("fft_twiddle");
+        fft_twiddle_kernel<<<ceil_div(n / 2, 256), 256, 0, c.stream>>>(c.fft_tw.as<double2>(), n);
+        PDSB_CUDA(cudaGetLastError());
+        c.fft_tw_n = n;
+    }
+    const double2 *tw = c.fft_tw.as<double2>();
+    const int tpf = n / 4 < 1 ? 1 : (n / 4 > 256 ? 256 : n / 4);       // threads per transform
+    const int npair = (nf + 1) / 2;
+    // rows: 2 rows x PB pairs per block; columns: PB planes per block; <= 512 threads, shared memory <= 192 KB
+    auto fit = [&](int per_unit, int have) {
+        int pb = 512 / (per_unit * tpf);
+        pb = pb < 1 ? 1 : pb > 4 ? 4 : pb;
+        while (pb > 1 && (size_t)per_unit * pb * n * sizeof(double2) > 160 * 1024) pb--;
+        return pb > have ? have : pb;
+    };
+    const int pb0 = fit(2, npair), pb1 = fit(1, nf);
+    const int th0 = std::max(32, 2 * pb0 * tpf), th1 = std::max(32, pb1 * tpf);
+    const size_t sm0 = ((size_t)2 * pb0 * n + n / 2) * sizeof(double2), sm1 = ((size_t)pb1 * n + n / 2) * sizeof(double2);
+    LaunchScope ls("rfft2_planes");
+    rfft_rows_kernel<<<dim3(n / 2, ceil_div(npair, pb0)), th0, sm0, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip, pb0, tpf);
+    rfft_cols_kernel<<<dim3(n / 2 + 1, ceil_div(nf, pb1)), th1, sm1, c.stream>>>(T, tw, Yh, n, logn, nf, pb1, tpf);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }

@@ -931,6 +931,13 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
     o_im = o_re + ncell;
     o_w = o_im + ncell;
     double *binned = o_w + ncell;
+    // device outputs: accumulate straight into the caller's maps (no copy of 3 x G^2 x nch doubles at the end)
+    const bool direct_out = out_kind == PDSB_DEVICE && out_real && out_imag && out_weights;
+    if (direct_out) {
+        o_re = out_real;
+        o_im = out_imag;
+        o_w = out_weights;
+    }
 
     GridParams P;
     P.u = du; P.v = dv; P.freq = dfreq; P.re = dre; P.im = dim; P.w_in = dw;
@@ -958,7 +965,13 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
     }
 
     PDSB_CUDA(cudaMemsetAsync(d_nout, 0, sizeof(unsigned long long), c.stream));
-    PDSB_CUDA(cudaMemsetAsync(o_re, 0, (size_t)ncell * 3 * sizeof(double), c.stream));
+    if (direct_out) {
+        PDSB_CUDA(cudaMemsetAsync(o_re, 0, (size_t)ncell * sizeof(double), c.stream));
+        PDSB_CUDA(cudaMemsetAsync(o_im, 0, (size_t)ncell * sizeof(double), c.stream));
+        PDSB_CUDA(cudaMemsetAsync(o_w, 0, (size_t)ncell * sizeof(double), c.stream));
+    } else {
+        PDSB_CUDA(cudaMemsetAsync(o_re, 0, (size_t)ncell * 3 * sizeof(double), c.stream));
+    }
     // The prep kernel (working weights, index maps, good mask) feeds the ordered mode, the re-weighting and the map
     // outputs; the fast mode with natural weights forms everything it needs on the fly from the inputs.
     const bool prepared = deterministic || weights_phase || weighting != PDSB_WT_NATURAL || out_i || out_j || out_wmod;
@@ -1120,9 +1133,11 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
 
     // ---- outputs ----
     cudaMemcpyKind ok = out_kind == PDSB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    if (out_real) PDSB_CUDA(cudaMemcpyAsync(out_real, o_re, (size_t)ncell * sizeof(double), ok, c.stream));
-    if (out_imag) PDSB_CUDA(cudaMemcpyAsync(out_imag, o_im, (size_t)ncell * sizeof(double), ok, c.stream));
-    if (out_weights) PDSB_CUDA(cudaMemcpyAsync(out_weights, o_w, (size_t)ncell * sizeof(double), ok, c.stream));
+    if (!direct_out) {
+        if (out_real) PDSB_CUDA(cudaMemcpyAsync(out_real, o_re, (size_t)ncell * sizeof(double), ok, c.stream));
+        if (out_imag) PDSB_CUDA(cudaMemcpyAsync(out_imag, o_im, (size_t)ncell * sizeof(double), ok, c.stream));
+        if (out_weights) PDSB_CUDA(cudaMemcpyAsync(out_weights, o_w, (size_t)ncell * sizeof(double), ok, c.stream));
+    }
     if (nvis > 0) {
         if (out_i) PDSB_CUDA(cudaMemcpyAsync(out_i, gi, (size_t)nvis * sizeof(uint32_t), ok, c.stream));
         if (out_j) PDSB_CUDA(cudaMemcpyAsync(out_j, gj, (size_t)nvis * sizeof(uint32_t), ok, c.stream));

@@ -3,14 +3,18 @@
 // ->  shared-memory region  ->  one fp64 atomic per region cell and map.
 //
 // Pipeline (every kernel streams its inputs once; no gathers, no multi-pass radix sort):
-//   gf_hist_kernel     u, v -> home tile of every visibility, histogram over the tiles (warp-aggregated atomics)
-//   gf_scan_*          exclusive scan of (count, work items) per tile, packed in one 64-bit word
+//   gf_hist_kernel     u, v -> sort key of every visibility = (home tile, home row inside the tile); histogram over
+//                      the keys (shared-memory window for the hot central tiles, else warp-aggregated atomics).  The
+//                      atomics' return values give every visibility its rank inside its key's run (rank[idx]): the
+//                      only atomic pass of the pipeline.
+//   gf_scan_*          exclusive scan of (count per key, work items per tile), packed in one 64-bit word
 //   gf_items_kernel    work list: every tile's run cut into items of <= GF_ITEM visibilities
-//   gf_scatter_kernel  second pass over the inputs: 48-byte record [pos_u, w][w re, w im][pos_v, (gi | gj << 32)]
-//                      written at the visibility's slot of its tile run (warp-aggregated cursor atomics; the L2 merges
-//                      the 64 K write streams, so DRAM sees full lines)
-//   gf_tile_kernel     persistent warps, one work item each:
-//        * the item's records are bucketed by home ROW inside the tile (8 buckets, ballot counting sort);
+//   gf_scatter_kernel  second pass over the inputs, pure streaming: 48-byte record [pos_u, w][w re, w im][pos_v, (gi | gj << 32)]
+//                      written at prefix(key) + rank (the L2 merges the write streams, so DRAM sees full lines).
+//                      A tile's run is therefore already in home-row order.
+//   gf_tile_kernel     persistent warps, one work item each; the item's records are streamed in order (coalesced,
+//                      next chunk prefetched into registers while the current one is worked on):
+//        * the 8 row buckets of the item are read off the scan (no sorting in the kernel);
 //        * factor phase: the 2 x WIDTH one-dimensional kernel factors (the exp*sinc kernel is separable), staged in
 //          shared memory;
 //        * accumulate phase, one half-warp per visibility: lane = region column, registers = the WIDTH rows of the
@@ -30,7 +34,7 @@ namespace pdsb {
 constexpr int GF_ITEM = 512;        // visibilities per work item (one warp)
 constexpr int GF_WARPS = 4;         // warps per CTA, each on its own item
 constexpr int GF_SCAN_THREADS = 1024;
-constexpr int GF_SCAN_PER = 4;
+constexpr int GF_SCAN_PER = 8;          // = the 8 row keys of one tile: a scan thread owns a whole tile
 constexpr int GF_SCAN_SEG = GF_SCAN_THREADS * GF_SCAN_PER;
 constexpr uint32_t GF_DEAD = 0xffffffffu;
 
@@ -47,8 +51,9 @@ struct GfVis {
 __device__ __forceinline__ GfVis gf_vis(const GridParams &P, int64_t idx)
 {
     GfVis x;
-    const int64_t k = idx / P.nf;
-    const double f = P.freq[idx % P.nf];
+    // nuv * nf < 2^32 (checked by pdsb_grid): 32-bit division, an order of magnitude cheaper than the 64-bit routine
+    const uint32_t k = P.nf == 1 ? (uint32_t)idx : (uint32_t)idx / (uint32_t)P.nf;
+    const double f = P.freq[P.nf == 1 ? 0u : (uint32_t)idx - k * (uint32_t)P.nf];
     x.pu = __dmul_rn(__dmul_rn(P.u[k], f), P.inv_freq);
     x.pv = __dmul_rn(__dmul_rn(P.v[k], f), P.inv_freq);
     x.gi = np_f64_to_u32(__dadd_rn(__ddiv_rn(x.pu, P.binsize), P.half));        // :388-403
@@ -57,10 +62,12 @@ __device__ __forceinline__ GfVis gf_vis(const GridParams &P, int64_t idx)
     return x;
 }
 
+// sort key = (channel, home tile, home row inside the tile): 8 keys per tile, so that a tile's run arrives in the
+// row-bucket order the tile kernel accumulates in
 __device__ __forceinline__ uint32_t gf_key(const GridParams &P, const GfVis &x, int64_t idx, uint32_t tg)
 {
     const uint32_t tile = (x.gj >> 3) * tg + (x.gi >> 3);
-    return (P.spectral ? (uint32_t)(idx % P.nf) : 0u) * tg * tg + tile;
+    return (((P.spectral ? (uint32_t)idx % (uint32_t)P.nf : 0u) * tg * tg + tile) << 3) | (x.gj & 7u);
 }
 
 // Interferometric uv coverage peaks at the short baselines: the few tiles around the grid centre receive a large
@@ -68,7 +75,8 @@ __device__ __forceinline__ uint32_t gf_key(const GridParams &P, const GfVis &x, 
 // atomics per address.  Both passes therefore count the central GF_WIN x GF_WIN tiles in a shared-memory window per
 // block first (one global atomic per block and window tile); the rest of the plane goes to global memory directly.
 // The window is used when the key has no channel part (nch == 1); otherwise equal keys are aggregated per warp.
-constexpr int GF_WIN = 32;
+constexpr int GF_WIN = 16;
+constexpr int GF_WIN_KEYS = GF_WIN * GF_WIN * 8;
 constexpr int GF_PASS_ITEMS = 4;                   // visibilities per thread in the two passes
 constexpr int GF_PASS_TILE = 256 * GF_PASS_ITEMS;
 
@@ -76,45 +84,56 @@ __device__ __forceinline__ int gf_window_index(uint32_t gi, uint32_t gj, uint32_
 {
     const int org = (int)(tg / 2) - GF_WIN / 2 > 0 ? (int)(tg / 2) - GF_WIN / 2 : 0;
     const int wr = (int)(gj >> 3) - org, wc = (int)(gi >> 3) - org;
-    return (wr >= 0 && wr < GF_WIN && wc >= 0 && wc < GF_WIN) ? wr * GF_WIN + wc : -1;
+    return (wr >= 0 && wr < GF_WIN && wc >= 0 && wc < GF_WIN) ? ((wr * GF_WIN + wc) << 3) | (int)(gj & 7u) : -1;
 }
 __device__ __forceinline__ uint32_t gf_window_key(int widx, uint32_t tg)
 {
     const int org = (int)(tg / 2) - GF_WIN / 2 > 0 ? (int)(tg / 2) - GF_WIN / 2 : 0;
-    return (uint32_t)(org + widx / GF_WIN) * tg + (uint32_t)(org + widx % GF_WIN);
+    const int wt = widx >> 3;
+    return (((uint32_t)(org + wt / GF_WIN) * tg + (uint32_t)(org + wt % GF_WIN)) << 3) | (uint32_t)(widx & 7);
 }
 
-// ---- pass 1: histogram over the tiles ----------------------------------------------------------------------
+// ---- pass 1: histogram over the keys, and every visibility's rank inside its key's run ------------------------
+// The atomics that build the histogram return the old count: that IS the visibility's slot among the visibilities of
+// its key (window keys: the block's base from the global atomic + the slot inside the block from the shared one).
+// Stored as rank[idx] (0xffffffff = off the grid), it lets the second pass run without any atomic or barrier.
 __global__ void __launch_bounds__(256) gf_hist_kernel(GridParams P, uint32_t tg, uint32_t *__restrict__ hist,
-                                                      unsigned long long *n_outside)
+                                                      uint32_t *__restrict__ rank, unsigned long long *n_outside)
 {
-    __shared__ uint32_t sh[GF_WIN * GF_WIN];
+    __shared__ uint32_t sh[GF_WIN_KEYS];
     const bool use_win = P.nch == 1;
     const int lane = threadIdx.x & 31;
     if (use_win) {
-        for (int i = threadIdx.x; i < GF_WIN * GF_WIN; i += 256) sh[i] = 0;
+        for (int i = threadIdx.x; i < GF_WIN_KEYS; i += 256) sh[i] = 0;
         __syncthreads();
     }
     uint32_t n_out = 0;
+    uint32_t slot[GF_PASS_ITEMS];
+    int widx[GF_PASS_ITEMS];
 #pragma unroll
     for (int it = 0; it < GF_PASS_ITEMS; it++) {
         const int64_t idx = (int64_t)blockIdx.x * GF_PASS_TILE + it * 256 + threadIdx.x;
         uint32_t key = GF_DEAD;
-        int widx = -1;
+        widx[it] = -1;
+        slot[it] = GF_DEAD;
         if (idx < P.nuv * P.nf) {
             const GfVis x = gf_vis(P, idx);
             if (x.good) {
                 key = gf_key(P, x, idx, tg);
-                if (use_win) widx = gf_window_index(x.gi, x.gj, tg);
+                if (use_win) widx[it] = gf_window_index(x.gi, x.gj, tg);
             } else
                 n_out++;
         }
         if (use_win) {
-            if (widx >= 0) atomicAdd(&sh[widx], 1u);
-            else if (key != GF_DEAD) atomicAdd(hist + key, 1u);
+            if (widx[it] >= 0) slot[it] = atomicAdd(&sh[widx[it]], 1u);
+            else if (key != GF_DEAD) slot[it] = atomicAdd(hist + key, 1u);
         } else {
             const uint32_t peers = __match_any_sync(0xffffffffu, key);
-            if (key != GF_DEAD && (int)(__ffs(peers) - 1) == lane) atomicAdd(hist + key, (uint32_t)__popc(peers));
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (key != GF_DEAD && leader == lane) base = atomicAdd(hist + key, (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (key != GF_DEAD) slot[it] = base + __popc(peers & ((1u << lane) - 1u));
         }
     }
     if (n_outside) {
@@ -123,18 +142,32 @@ __global__ void __launch_bounds__(256) gf_hist_kernel(GridParams P, uint32_t tg,
         if (lane == 0 && n_out) atomicAdd(n_outside, (unsigned long long)n_out);
     }
     if (use_win) {
+        // the block's base slot in every window key: all atomics go out before the first result is needed (issue
+        // is in order: a store of the result right behind its atomic would serialise the round trips)
         __syncthreads();
-        for (int i = threadIdx.x; i < GF_WIN * GF_WIN; i += 256)
-            if (sh[i]) atomicAdd(hist + gf_window_key(i, tg), sh[i]);
+        constexpr int NQ = GF_WIN_KEYS / 256;
+        uint32_t cnt[NQ], base[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) cnt[q] = sh[q * 256 + threadIdx.x];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            base[q] = 0;
+            if (cnt[q]) base[q] = atomicAdd(hist + gf_window_key(q * 256 + threadIdx.x, tg), cnt[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++) sh[q * 256 + threadIdx.x] = base[q];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int it = 0; it < GF_PASS_ITEMS; it++) {
+        const int64_t idx = (int64_t)blockIdx.x * GF_PASS_TILE + it * 256 + threadIdx.x;
+        if (idx < P.nuv * P.nf) rank[idx] = slot[it] + (widx[it] >= 0 ? sh[widx[it]] : 0u);
     }
 }
 
 // ---- exclusive scan of packed (count | items << 40) ---------------------------------------------------------
-__device__ __forceinline__ uint64_t gf_pack(uint32_t cnt)
-{
-    return (uint64_t)cnt | ((uint64_t)((cnt + GF_ITEM - 1) / GF_ITEM) << 40);
-}
-
+// counts are per key (8 row keys per tile); work items are per TILE (its 8 runs together, cut into pieces of
+// GF_ITEM) and are attached to the tile's last key, so that prefix(8 T) >> 40 = items before tile T.
 __device__ __forceinline__ uint64_t gf_block_excl_scan(uint64_t x, uint64_t *warp_sums, uint64_t *total)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -173,9 +206,11 @@ __global__ void __launch_bounds__(GF_SCAN_THREADS) gf_scan_seg_kernel(const uint
     uint64_t v[GF_SCAN_PER], tsum = 0;
 #pragma unroll
     for (int q = 0; q < GF_SCAN_PER; q++) {
-        v[q] = (e0 + q < nkeys) ? gf_pack(hist[e0 + q]) : 0ull;
+        v[q] = (e0 + q < nkeys) ? (uint64_t)hist[e0 + q] : 0ull;
         tsum += v[q];
     }
+    v[GF_SCAN_PER - 1] += ((tsum + GF_ITEM - 1) / GF_ITEM) << 40;
+    tsum += ((tsum + GF_ITEM - 1) / GF_ITEM) << 40;
     uint64_t total;
     uint64_t ex = gf_block_excl_scan(tsum, warp_sums, &total);
 #pragma unroll
@@ -217,101 +252,49 @@ __global__ void __launch_bounds__(256) gf_items_kernel(const uint64_t *__restric
     const uint32_t t = blockIdx.x * 256 + threadIdx.x;
     const uint32_t total = (uint32_t)(gf_prefix(excl, seg_off, nkeys) >> 40);
     if (t >= total) return;
-    // the tile whose item range holds t: largest key with items_before(key) <= t  (empty tiles repeat the value of
+    // the tile whose item range holds t: largest tile T with items_before(T) <= t  (empty tiles repeat the value of
     // their successor, so the search lands on the non-empty one)
-    uint32_t lo = 0, hi = nkeys;                       // items_before(lo) <= t < items_before(hi)
+    uint32_t lo = 0, hi = nkeys >> 3;                  // items_before(lo) <= t < items_before(hi)
     while (hi - lo > 1) {
         const uint32_t mid = lo + (hi - lo) / 2;
-        if ((uint32_t)(gf_prefix(excl, seg_off, mid) >> 40) <= t) lo = mid;
+        if ((uint32_t)(gf_prefix(excl, seg_off, mid << 3) >> 40) <= t) lo = mid;
         else hi = mid;
     }
-    const uint64_t p0 = gf_prefix(excl, seg_off, lo), p1 = gf_prefix(excl, seg_off, lo + 1);
+    const uint64_t p0 = gf_prefix(excl, seg_off, lo << 3), p1 = gf_prefix(excl, seg_off, (lo + 1) << 3);
     const uint32_t j = t - (uint32_t)(p0 >> 40);
     const uint32_t start = (uint32_t)(p0 & GF_LOW40), stop = (uint32_t)(p1 & GF_LOW40);
     GfItem it;
     it.begin = start + j * GF_ITEM;
     it.end = it.begin + GF_ITEM < stop ? it.begin + GF_ITEM : stop;
-    it.key = lo;
+    it.key = lo;                                       // tile id (channel * tg^2 + tile)
     it.pad = 0;
     items[t] = it;
 }
 
-// ---- pass 2: records to their tile runs ---------------------------------------------------------------------
+// ---- pass 2: records to their key runs (streaming: no atomics, no barriers) -----------------------------------
 __global__ void __launch_bounds__(256) gf_scatter_kernel(GridParams P, uint32_t tg, const double *__restrict__ w_src,
                                                          const uint64_t *__restrict__ excl,
                                                          const uint64_t *__restrict__ seg_off,
-                                                         uint32_t *__restrict__ fill, double2 *__restrict__ rec)
+                                                         const uint32_t *__restrict__ rank, double2 *__restrict__ rec)
 {
-    __shared__ uint32_t sh[GF_WIN * GF_WIN];           // window counts, then the block's base slot in each window tile
-    const bool use_win = P.nch == 1;
-    const int lane = threadIdx.x & 31;
-    if (use_win) {
-        for (int i = threadIdx.x; i < GF_WIN * GF_WIN; i += 256) sh[i] = 0;
-        __syncthreads();
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= P.nuv * P.nf) return;
+    const uint32_t rk = rank[idx];
+    const double re = P.re[idx], im = P.im[idx];
+    double w = w_src ? w_src[idx] : P.w_in[idx];
+    if (rk == GF_DEAD) return;
+    const GfVis x = gf_vis(P, idx);
+    const uint32_t key = gf_key(P, x, idx, tg);
+    const uint32_t pos = (uint32_t)(gf_prefix(excl, seg_off, key) & GF_LOW40) + rk;
+    if (!w_src) {                                           // :351-353
+        w = w < 0 ? 0.0 : w;
+        if (re == 0 && im == 0) w = 0.0;
     }
-    GfVis x[GF_PASS_ITEMS];
-    uint32_t key[GF_PASS_ITEMS], slot[GF_PASS_ITEMS];   // slot: rank inside the block's share of the tile run
-    int widx[GF_PASS_ITEMS];
-    double dre[GF_PASS_ITEMS], dim[GF_PASS_ITEMS], dw[GF_PASS_ITEMS];
-#pragma unroll
-    for (int it = 0; it < GF_PASS_ITEMS; it++) {             // the data loads go out before the atomics' round trips
-        const int64_t idx = (int64_t)blockIdx.x * GF_PASS_TILE + it * 256 + threadIdx.x;
-        dre[it] = dim[it] = dw[it] = 0.0;
-        if (idx < P.nuv * P.nf) {
-            dre[it] = P.re[idx];
-            dim[it] = P.im[idx];
-            dw[it] = w_src ? w_src[idx] : P.w_in[idx];
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < GF_PASS_ITEMS; it++) {
-        const int64_t idx = (int64_t)blockIdx.x * GF_PASS_TILE + it * 256 + threadIdx.x;
-        key[it] = GF_DEAD;
-        widx[it] = -1;
-        slot[it] = 0;
-        if (idx < P.nuv * P.nf) {
-            x[it] = gf_vis(P, idx);
-            if (x[it].good) {
-                key[it] = gf_key(P, x[it], idx, tg);
-                if (use_win) widx[it] = gf_window_index(x[it].gi, x[it].gj, tg);
-            }
-        }
-        if (use_win) {
-            if (widx[it] >= 0) slot[it] = atomicAdd(&sh[widx[it]], 1u);
-            else if (key[it] != GF_DEAD) slot[it] = atomicAdd(fill + key[it], 1u);
-        } else {
-            const uint32_t peers = __match_any_sync(0xffffffffu, key[it]);
-            const int leader = __ffs(peers) - 1;
-            uint32_t base = 0;
-            if (key[it] != GF_DEAD && leader == lane) base = atomicAdd(fill + key[it], (uint32_t)__popc(peers));
-            slot[it] = __shfl_sync(0xffffffffu, base, leader) + __popc(peers & ((1u << lane) - 1u));
-        }
-    }
-    if (use_win) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < GF_WIN * GF_WIN; i += 256) {
-            const uint32_t cnt = sh[i];
-            if (cnt) sh[i] = atomicAdd(fill + gf_window_key(i, tg), cnt);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int it = 0; it < GF_PASS_ITEMS; it++) {
-        if (key[it] == GF_DEAD) continue;
-        const uint32_t pos = (uint32_t)(gf_prefix(excl, seg_off, key[it]) & GF_LOW40) + slot[it] +
-                             (widx[it] >= 0 ? sh[widx[it]] : 0u);
-        const double re = dre[it], im = dim[it];
-        double w = dw[it];
-        if (!w_src) {                                           // :351-353
-            w = w < 0 ? 0.0 : w;
-            if (re == 0 && im == 0) w = 0.0;
-        }
-        double2 *r = rec + 3 * (size_t)pos;
-        r[0] = make_double2(x[it].pu, w);
-        r[1] = make_double2(re * w, im * w);
-        r[2] = make_double2(x[it].pv, __longlong_as_double((long long)((unsigned long long)x[it].gi |
-                                                                        ((unsigned long long)x[it].gj << 32))));
-    }
+    double2 *r = rec + 3 * (size_t)pos;
+    r[0] = make_double2(x.pu, w);
+    r[1] = make_double2(re * w, im * w);
+    r[2] = make_double2(x.pv, __longlong_as_double((long long)((unsigned long long)x.gi |
+                                                               ((unsigned long long)x.gj << 32))));
 }
 
 // ---- convolution kernel factors ------------------------------------------------------------------------------
@@ -345,8 +328,8 @@ __device__ __forceinline__ double gf_exp_sinc_1d(double x)
 // WIDTH = footprint width lo + hi + 1 (pillbox 3, exp*sinc 6, box sums 1 / 3 / 5 / 7); MODE 0 = main sums (three maps),
 // MODE 1 = box sums of the weights (one map, all factors 1).
 //
-// One warp per work item.  The item's visibilities are put in home-row order (8 buckets); then per chunk of 32:
-//   A  lane = visibility: the 48-byte record into shared memory;
+// One warp per work item (<= GF_ITEM consecutive records of one tile, in home-row order).  Per chunk of 32 records:
+//   A  lane = visibility: the 48-byte record (prefetched into registers one chunk ahead) into shared memory;
 //   B  lane = (visibility, axis): the WIDTH kernel factors of that axis, WIDTH independent polynomial evaluations per lane;
 //   C  half-warp = visibility, lane = region column: WIDTH x NMAP DFMAs per lane into registers, all of them live
 //      because the bucket (home row) fixes the rows.  When the bucket changes the two half-warps add their registers
@@ -370,16 +353,13 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gf_tile_kernel(GridParams P, in
     // per staged visibility: [0..6] row factors, [8] w, [9] w re, [10] w im, [11] meta, [12] pos_u, [13] pos_v
     __shared__ __align__(16) double s_b[GF_WARPS][32][SBS];
     __shared__ double s_cen[GF_WARPS][2][16];           // cell centres of the region's columns / rows
-    __shared__ uint16_t s_ord[GF_WARPS][GF_ITEM];       // the item's visibilities in bucket (home row) order
     __shared__ int s_cnt[GF_WARPS][12];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = lane >> 4, c = lane & 15;
-    const uint32_t lt = (1u << lane) - 1u;
     const uint32_t nitems = (uint32_t)(gf_prefix(excl, seg_off, nkeys) >> 40);
     double(*reg)[SIDE][RC] = s_reg[warp];
     double(*fu)[FUS] = s_fu[warp];
     double(*sb)[SBS] = s_b[warp];
-    uint16_t *ord = s_ord[warp];
     int *bcnt = s_cnt[warp];
     const double *fu_lane = &fu[0][0] + c * FUS;
 
@@ -395,52 +375,25 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gf_tile_kernel(GridParams P, in
         const int tl = (int)(tile / tg), tm = (int)(tile % tg);
         const int n = (int)(item.end - item.begin);
         const double2 *irec = rec + 3 * (size_t)item.begin;
-
-        // zero the region and the bucket counters; centres of the region's cells
+        // first chunk of records: lane = visibility, 32 consecutive 48-byte records = one contiguous run
+        double2 c0 = make_double2(0., 0.), c1 = c0, c2 = c0;
+        if (lane < n) {
+            c0 = irec[3 * lane];
+            c1 = irec[3 * lane + 1];
+            c2 = irec[3 * lane + 2];
+        }
+        // zero the region; bucket starts (bcnt[b] = first record of home row b inside the item, bcnt[8] = n) read
+        // off the scan; centres of the region's cells
         {
             double *z = &reg[0][0][0];
             for (int i = lane; i < NMAP * SIDE * RC; i += 32) z[i] = 0.0;
-            if (lane < 12) bcnt[lane] = 0;
+            if (lane < 9) {
+                const long long s = (long long)(gf_prefix(excl, seg_off, (item.key << 3) + lane) & GF_LOW40) -
+                                    (long long)item.begin;
+                bcnt[lane] = s < 0 ? 0 : s > n ? n : (int)s;
+            }
             const int cell = (half ? tl : tm) * 8 - lo + c;
             s_cen[warp][half][c] = (cell >= 0 && cell < P.G) ? (half ? P.vv[cell] : P.uu[cell]) : 0.0;
-        }
-        __syncwarp();
-        // bucket = home row inside the tile: counting sort of the item's visibilities
-        int bk[GF_ITEM / 32], rk[GF_ITEM / 32];
-#pragma unroll
-        for (int q = 0; q < GF_ITEM / 32; q++) {
-            bk[q] = 8;
-            rk[q] = 0;
-            if (q * 32 >= n) continue;
-            const int i = q * 32 + lane;
-            if (i < n) {
-                const unsigned long long ij = (unsigned long long)__double_as_longlong(irec[3 * i + 2].y);
-                bk[q] = (int)(uint32_t)(ij >> 32) - tl * 8;
-            }
-            const uint32_t peers = __match_any_sync(0xffffffffu, bk[q]);
-            const int before = bcnt[bk[q]];
-            __syncwarp();
-            if ((int)(__ffs(peers) - 1) == lane) bcnt[bk[q]] = before + __popc(peers);
-            __syncwarp();
-            rk[q] = before + __popc(peers & lt);
-        }
-        // counts -> bucket starts (bcnt[b] = first sorted position of bucket b, bcnt[8] = n)
-        {
-            int x = lane < 9 ? bcnt[lane] : 0;
-            const int own = x;
-#pragma unroll
-            for (int o = 1; o < 16; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            __syncwarp();
-            if (lane < 9) bcnt[lane] = x - own;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < GF_ITEM / 32; q++) {
-            if (q * 32 >= n) continue;
-            if (bk[q] < 8) ord[bcnt[bk[q]] + rk[q]] = (uint16_t)(q * 32 + lane);
         }
         __syncwarp();
 
@@ -470,8 +423,6 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gf_tile_kernel(GridParams P, in
             const int nst = n - p0 < 32 ? n - p0 : 32;
             // ---- A: lane = visibility ----
             if (lane < nst) {
-                const double2 *r = irec + 3 * (size_t)ord[p0 + lane];
-                const double2 c0 = r[0], c1 = r[1], c2 = r[2];
                 const unsigned long long ij = (unsigned long long)__double_as_longlong(c2.y);
                 const int di = (int)(uint32_t)ij - tm * 8, dj = (int)(uint32_t)(ij >> 32) - tl * 8;
                 // meta: low word = offset of this visibility's column factor for region column 0 (lane c adds c * FUS),
@@ -481,6 +432,12 @@ __global__ void __launch_bounds__(GF_WARPS * 32) gf_tile_kernel(GridParams P, in
                 d[4] = make_double2(c0.y, c1.x);
                 d[5] = make_double2(c1.y, __longlong_as_double(meta));
                 d[6] = make_double2(c0.x, c2.x);
+            }
+            if (p0 + 32 + lane < n) {                    // next chunk: in flight during B and C
+                const double2 *r = irec + 3 * (size_t)(p0 + 32 + lane);
+                c0 = r[0];
+                c1 = r[1];
+                c2 = r[2];
             }
             __syncwarp();
             // ---- B: lane = (visibility, axis) ----
@@ -617,29 +574,29 @@ int grid_fast_scatter(const GridParams &P, int smode, uint32_t lo, uint32_t hi, 
     PDSB_REQUIRE((smode == 0 && (width == 3 || width == 6)) || (smode == 1 && (width == 1 || width == 3 || width == 5 || width == 7)),
                  "footprint width of the fast gridding mode");
     const uint32_t tg = ((uint32_t)P.G + 7u) >> 3;
-    const uint64_t nkeys64 = (uint64_t)tg * tg * (uint64_t)P.nch;
+    const uint64_t nkeys64 = (uint64_t)tg * tg * (uint64_t)P.nch * 8ull;          // 8 row keys per tile
     PDSB_REQUIRE(nkeys64 < (1ull << 31), "too many uv tiles");
     const uint32_t nkeys = (uint32_t)nkeys64;
     const int nseg = ceil_div((int64_t)nkeys + 1, GF_SCAN_SEG);
-    const uint64_t max_items = std::min<uint64_t>(nkeys64, (uint64_t)nvis) + (uint64_t)nvis / GF_ITEM + 2;
+    const uint64_t max_items = std::min<uint64_t>(nkeys64 >> 3, (uint64_t)nvis) + (uint64_t)nvis / GF_ITEM + 2;
     PDSB_REQUIRE(max_items < (1ull << 31), "too many gridding work items");
 
-    // scratch: stage_d = hist | fill | counter | excl | seg_off | items ; stage_e = records
+    // scratch: stage_d = hist | rank | counter | excl | seg_off | items ; stage_e = records
     auto up = [](size_t b) { return (b + 255) / 256 * 256; };
-    const size_t o_hist = 0, o_fill = o_hist + up((size_t)nkeys * 4), o_cnt = o_fill + up((size_t)nkeys * 4),
-                 o_excl = o_cnt + 256, o_seg = o_excl + up(((size_t)nseg * GF_SCAN_SEG + 1) * 8),
+    const size_t o_hist = 0, o_cnt = o_hist + up((size_t)nkeys * 4), o_rank = o_cnt + 256,
+                 o_excl = o_rank + up((size_t)nvis * 4), o_seg = o_excl + up(((size_t)nseg * GF_SCAN_SEG + 1) * 8),
                  o_items = o_seg + up((size_t)nseg * 8), total = o_items + up((size_t)max_items * sizeof(GfItem));
     PDSB_CHECK(c.stage_d.ensure(total));
     PDSB_CHECK(c.stage_e.ensure((size_t)nvis * 3 * sizeof(double2)));
     unsigned char *base = c.stage_d.as<unsigned char>();
-    uint32_t *hist = (uint32_t *)(base + o_hist), *fill = (uint32_t *)(base + o_fill), *counter = (uint32_t *)(base + o_cnt);
+    uint32_t *hist = (uint32_t *)(base + o_hist), *rank = (uint32_t *)(base + o_rank), *counter = (uint32_t *)(base + o_cnt);
     uint64_t *excl = (uint64_t *)(base + o_excl), *seg_off = (uint64_t *)(base + o_seg);
     GfItem *items = (GfItem *)(base + o_items);
     double2 *rec = c.stage_e.as<double2>();
-    PDSB_CUDA(cudaMemsetAsync(base, 0, o_excl, c.stream));              // hist, fill, counter
+    PDSB_CUDA(cudaMemsetAsync(base, 0, o_rank, c.stream));              // hist, counter
     {
         LaunchScope ls("grid_tile_hist");
-        gf_hist_kernel<<<ceil_div(nvis, GF_PASS_TILE), 256, 0, c.stream>>>(P, tg, hist, n_outside);
+        gf_hist_kernel<<<ceil_div(nvis, GF_PASS_TILE), 256, 0, c.stream>>>(P, tg, hist, rank, n_outside);
         PDSB_CUDA(cudaGetLastError());
     }
     {
@@ -651,7 +608,7 @@ int grid_fast_scatter(const GridParams &P, int smode, uint32_t lo, uint32_t hi, 
     }
     {
         LaunchScope ls("grid_tile_records");
-        gf_scatter_kernel<<<ceil_div(nvis, GF_PASS_TILE), 256, 0, c.stream>>>(P, tg, w_src, excl, seg_off, fill, rec);
+        gf_scatter_kernel<<<ceil_div(nvis, 256), 256, 0, c.stream>>>(P, tg, w_src, excl, seg_off, rank, rec);
         PDSB_CUDA(cudaGetLastError());
     }
     {

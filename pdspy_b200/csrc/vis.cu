@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(256) chisq_ch0_kernel(const double *__restrict
 // galario's algorithm, as the reference calls it (interpolate_model.py:23-27): bilinear interpolation of
 // F = fftshift_rows(rfft2(fftshift(A))), A = image[::-1, :, i, 0], at (row n/2 + v/du, column |u|/du),
 // du = 1/(n dxy); mirrored row and conjugate for u < 0; times exp(+2 pi i (u dRA + v dDec)); then the
-// reference's imag -> -imag.  Ysh is fft2_planes' output: F[R][b] = conj(Ysh[(R n + (b + n/2) % n) nf + i]);
-// row n of F is the periodic copy of row 0.  One thread per (visibility, channel), channel fastest.
+// reference's imag -> -imag.  Ysh is rfft2_planes' output (fft.cu; the half spectrum, channel fastest):
+// F[R][b] = conj(Ysh[(R (n/2 + 1) + b) nf + i]), b <= n/2; row n of F is the periodic copy of row 0.  One thread per (visibility, channel), channel fastest.
 struct FftSampleArgs {
     const double2 *Ysh;
     const double *u, *v;
@@ -247,68 +247,93 @@ struct FftSampleArgs {
     int n, nf;
     double dxy, dRA, dDec;
 };
-__device__ __forceinline__ double2 fft_sample_one(const FftSampleArgs &P, int64_t k, int i)
+// per-visibility part (shared by all channels): the four corners' offsets and weights, the conjugation flag, the
+// phase factor
+struct FftCorner {
+    int64_t o00, o01, o10, o11;        // element offsets of the corners' channel 0 in Ysh
+    double w00, w01, w10, w11;
+    double pc, ps;
+    bool uneg;
+};
+__device__ __forceinline__ FftCorner fft_corner(const FftSampleArgs &P, int64_t k)
 {
-    const int n = P.n;
+    const int n = P.n, h = n / 2;
     const double uu = k < P.nuvh ? P.u[k] : -P.u[k - P.nuvh], vv = k < P.nuvh ? P.v[k] : -P.v[k - P.nuvh];   // Hermitian half
     const double du = 1.0 / ((double)n * P.dxy);
-    const bool uneg = uu < 0.0;
-    const double indu = fabs(uu) / du, indv = (double)n / 2.0 + (uneg ? -vv : vv) / du;
+    FftCorner q;
+    q.uneg = uu < 0.0;
+    const double indu = fabs(uu) / du, indv = (double)n / 2.0 + (q.uneg ? -vv : vv) / du;
     double fu = floor(indu), fv = floor(indv);
     const double t = indu - fu, sfrac = indv - fv;
     // baselines beyond the image's Nyquist range have no cell: clamp (galario refuses them)
-    fu = fmin(fmax(fu, 0.0), (double)(n / 2));
+    fu = fmin(fmax(fu, 0.0), (double)h);
     fv = fmin(fmax(fv, 0.0), (double)n);
-    const int cu0 = (int)fu, cu1 = cu0 + 1 < n / 2 ? cu0 + 1 : n / 2;
+    const int cu0 = (int)fu, cu1 = cu0 + 1 < h ? cu0 + 1 : h;
     const int rv0 = (int)fv, rv1 = rv0 + 1 < n ? rv0 + 1 : n;
-    const int h = n / 2;
-    auto F = [&](int R, int b) -> double2 {
-        const double2 y = P.Ysh[((int64_t)(R % n) * n + (b + h) % n) * P.nf + i];
-        return make_double2(y.x, -y.y);
-    };
-    const double2 f00 = F(rv0, cu0), f01 = F(rv0, cu1), f10 = F(rv1, cu0), f11 = F(rv1, cu1);
-    const double w00 = (1 - t) * (1 - sfrac), w01 = t * (1 - sfrac), w10 = (1 - t) * sfrac, w11 = t * sfrac;
-    double vr = w00 * f00.x + w01 * f01.x + w10 * f10.x + w11 * f11.x;
-    double vi = w00 * f00.y + w01 * f01.y + w10 * f10.y + w11 * f11.y;
-    if (uneg) vi = -vi;
-    double ps, pc;
-    sincos(kTwoPi * (uu * P.dRA + vv * P.dDec), &ps, &pc);
-    return make_double2(vr * pc - vi * ps, -(vr * ps + vi * pc));
+    auto off = [&](int R, int b) -> int64_t { return ((int64_t)(R % n) * (h + 1) + b) * P.nf; };
+    q.o00 = off(rv0, cu0);
+    q.o01 = off(rv0, cu1);
+    q.o10 = off(rv1, cu0);
+    q.o11 = off(rv1, cu1);
+    q.w00 = (1 - t) * (1 - sfrac);
+    q.w01 = t * (1 - sfrac);
+    q.w10 = (1 - t) * sfrac;
+    q.w11 = t * sfrac;
+    sincos(kTwoPi * (uu * P.dRA + vv * P.dDec), &q.ps, &q.pc);
+    return q;
+}
+// channel i: F = conj(Ysh), bilinear sum, conjugate for u < 0, phase shift, the reference's imag -> -imag
+__device__ __forceinline__ double2 fft_sample_channel(const FftSampleArgs &P, const FftCorner &q, int i)
+{
+    const double2 f00 = P.Ysh[q.o00 + i], f01 = P.Ysh[q.o01 + i], f10 = P.Ysh[q.o10 + i], f11 = P.Ysh[q.o11 + i];
+    const double vr = q.w00 * f00.x + q.w01 * f01.x + q.w10 * f10.x + q.w11 * f11.x;
+    double vi = -(q.w00 * f00.y + q.w01 * f01.y + q.w10 * f10.y + q.w11 * f11.y);
+    if (q.uneg) vi = -vi;
+    return make_double2(vr * q.pc - vi * q.ps, -(vr * q.ps + vi * q.pc));
 }
 
-__global__ void __launch_bounds__(256) fft_sample_kernel(const FftSampleArgs P, double *__restrict__ out_re,
+// A group of gs lanes (a power of two <= 32, <= nf) shares one visibility: the per-visibility part is evaluated once
+// per group instruction instead of once per (visibility, channel); the lanes take the channels gs apart, so the
+// corner reads and the data reads are contiguous runs of the channel-fastest arrays.
+__global__ void __launch_bounds__(256) fft_sample_kernel(const FftSampleArgs P, int gs, double *__restrict__ out_re,
                                                          double *__restrict__ out_im)
 {
-    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= P.nuv * P.nf) return;
-    const double2 m = fft_sample_one(P, idx / P.nf, (int)(idx % P.nf));
-    out_re[idx] = m.x;
-    out_im[idx] = m.y;
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t k = t / gs;
+    if (k >= P.nuv) return;
+    const FftCorner q = fft_corner(P, k);
+    for (int i = (int)(t % gs); i < P.nf; i += gs) {
+        const double2 m = fft_sample_channel(P, q, i);
+        out_re[k * P.nf + i] = m.x;
+        out_im[k * P.nf + i] = m.y;
+    }
 }
 
-// the same sample fused with the likelihood sums of chi2_flat_kernel: the model visibilities never reach memory
-__global__ void __launch_bounds__(256) fft_chi2_kernel(const FftSampleArgs P, const double *__restrict__ dre,
+// the same sample fused with the chi^2 sums of chi2_flat_kernel: the model visibilities never reach memory
+__global__ void __launch_bounds__(256) fft_chi2_kernel(const FftSampleArgs P, int gs, const double *__restrict__ dre,
                                                        const double *__restrict__ dim, const double *__restrict__ w,
                                                        double *__restrict__ blockpart)
 {
     __shared__ double sh[8];
-    double sr = 0.0, si = 0.0, sl = 0.0;
-    const int64_t cnt = P.nuv * P.nf;
-    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < cnt; idx += (int64_t)gridDim.x * 256) {
-        const double2 m = fft_sample_one(P, idx / P.nf, (int)(idx % P.nf));
-        const double ww = w[idx];
-        const double a = dre[idx] - m.x, b = dim[idx] - m.y;
-        sr += a * a * ww;
-        si += b * b * ww;
-        if (ww > 0.0) sl += log(ww / kTwoPi);
+    double sr = 0.0, si = 0.0;
+    const int lg = threadIdx.x % gs;
+    const int64_t kstep = (int64_t)gridDim.x * (256 / gs);
+    for (int64_t k = (int64_t)blockIdx.x * (256 / gs) + threadIdx.x / gs; k < P.nuv; k += kstep) {
+        const FftCorner q = fft_corner(P, k);
+        for (int i = lg; i < P.nf; i += gs) {
+            const int64_t idx = k * P.nf + i;
+            const double ww = w[idx], a0 = dre[idx], b0 = dim[idx];
+            const double2 m = fft_sample_channel(P, q, i);
+            const double a = a0 - m.x, b = b0 - m.y;
+            sr += a * a * ww;
+            si += b * b * ww;
+        }
     }
     sr = block_sum<256>(sr, sh);
     si = block_sum<256>(si, sh);
-    sl = block_sum<256>(sl, sh);
     if (threadIdx.x == 0) {
-        blockpart[(size_t)blockIdx.x * 3 + 0] = sr;
-        blockpart[(size_t)blockIdx.x * 3 + 1] = si;
-        blockpart[(size_t)blockIdx.x * 3 + 2] = sl;
+        blockpart[(size_t)blockIdx.x * 2 + 0] = sr;
+        blockpart[(size_t)blockIdx.x * 2 + 1] = si;
     }
 }
 
@@ -712,7 +737,14 @@ int pdsb_loglike_batch(pdsb_dataset *ds, const double *images, int nwalkers, int
     return loglike_impl(ds, images, nwalkers, ny, nx, nf, image_kind, dxy, dRA, dDec, nullptr, lnlike);
 }
 
-// galario's FFT stage: the transformed cube of every channel (fft2_planes) and the sampling arguments
+static int fft_group_size(int nf)
+{
+    int gs = 1;
+    while (gs * 2 <= nf && gs < 32) gs *= 2;
+    return gs;
+}
+
+// galario's FFT stage: the transformed cube of every channel (rfft2_planes) and the sampling arguments
 static int run_fft_transform(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
                              double dDec, FftSampleArgs *a)
 {
@@ -723,9 +755,10 @@ static int run_fft_transform(pdsb_dataset *ds, const double *image, int n, int n
     const double *img_dev = nullptr;
     const size_t nn = (size_t)n * n;
     PDSB_CHECK(to_device(image, image_kind, nn * nf * sizeof(double), c.img64, (const void **)&img_dev));
-    PDSB_CHECK(c.folded.ensure(2 * nn * nf * sizeof(double2)));            // [T | Y]: the DFT's scratch, free here
-    double2 *T = c.folded.as<double2>(), *Y = T + nn * nf;
-    PDSB_CHECK(fft2_planes(img_dev, n, nf, 1, T, Y));
+    const size_t nh = (size_t)n * (n / 2 + 1);                             // half spectrum: columns 0 .. n/2
+    PDSB_CHECK(c.folded.ensure(2 * nh * nf * sizeof(double2)));            // [T | Y]: the DFT's scratch, free here
+    double2 *T = c.folded.as<double2>(), *Y = T + nh * nf;
+    PDSB_CHECK(rfft2_planes(img_dev, n, nf, 1, T, Y));
     *a = FftSampleArgs{Y, ds->u, ds->v, ds->nuv, ds->nuvh, n, nf, dxy, dRA, dDec};
     return PDSB_OK;
 }
@@ -749,7 +782,8 @@ int pdsb_sample_image_fft(pdsb_dataset *ds, const double *image, int n, int nf, 
     PDSB_CHECK(run_fft_transform(ds, image, n, nf, image_kind, dxy, dRA, dDec, &fa));
     {
         LaunchScope ls("fft_sample");
-        fft_sample_kernel<<<ceil_div(ds->nuv * nf, 256), 256, 0, c.stream>>>(fa, ore, oim);
+        const int gs = fft_group_size(nf);
+        fft_sample_kernel<<<ceil_div(ds->nuv * gs, 256), 256, 0, c.stream>>>(fa, gs, ore, oim);
         PDSB_CUDA(cudaGetLastError());
     }
     if (out_kind == PDSB_HOST) {
@@ -775,17 +809,19 @@ int pdsb_loglike_fft(pdsb_dataset *ds, const double *image, int n, int nf, int i
     }
     FftSampleArgs fa;
     PDSB_CHECK(run_fft_transform(ds, image, n, nf, image_kind, dxy, dRA, dDec, &fa));
-    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 16, (cnt + 255) / 256);
-    PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * 3 * sizeof(double)));
+    const int gs = fft_group_size(nf);
+    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 16, (ds->nuv * gs + 255) / 256);
+    PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * 2 * sizeof(double)));
     {
         LaunchScope ls("fft_chi2");
-        fft_chi2_kernel<<<nb, 256, 0, c.stream>>>(fa, ds->re, ds->im, ds->w, c.red.as<double>());
+        fft_chi2_kernel<<<nb, 256, 0, c.stream>>>(fa, gs, ds->re, ds->im, ds->w, c.red.as<double>());
         PDSB_CUDA(cudaGetLastError());
     }
-    PDSB_CHECK(reduce_blocks(c.red.as<double>(), nb, 3, c.red.as<double>() + (size_t)nb * 3));
+    PDSB_CHECK(reduce_blocks(c.red.as<double>(), nb, 2, c.red.as<double>() + (size_t)nb * 2));
     double h[3];
-    PDSB_CUDA(cudaMemcpyAsync(h, c.red.as<double>() + (size_t)nb * 3, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    PDSB_CUDA(cudaMemcpyAsync(h, c.red.as<double>() + (size_t)nb * 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     PDSB_CUDA(cudaStreamSynchronize(c.stream));
+    h[2] = ds->logsum;                           // sum log(w / 2 pi) over w > 0: data only, formed once at upload
     out[0] = h[0];
     out[1] = h[1];
     out[2] = h[2];

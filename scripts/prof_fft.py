@@ -13,7 +13,16 @@ ds = pb.Dataset(c["u"], c["v"]); ds.set_data(re, im, w)
 cube = pb.DeviceBuffer.from_numpy(np.ascontiguousarray(c["model"].image[:, :, :, 0]))
 out = np.empty(4)
 L = _lib.lib()
-for _ in range(2):
+import ctypes
+for rep in range(3):
+    if rep == 2:
+        _lib.check(L.pdsb_profile_reset()); _lib.check(L.pdsb_profile_enable(1))
     _lib.check(L.pdsb_loglike_fft(ds.handle, _lib.ptr(cube), c["npix"], c["nf"], _lib.DEVICE, c["pixelsize"] * A, c["dRA"] * A,
                                   c["dDec"] * A, _lib.ptr(out)))
 print("lnlike", out[3])
+_lib.check(L.pdsb_profile_enable(0))
+for name in (b"rfft2_planes", b"fft2_planes", b"fft_chi2", b"reduce_columns", b"fft_twiddle"):
+    t, n = ctypes.c_double(), ctypes.c_int64()
+    L.pdsb_profile_get(name, ctypes.byref(t), ctypes.byref(n))
+    if n.value:
+        print(name.decode(), "ms %.3f" % t.value, "launch scopes", n.value)
