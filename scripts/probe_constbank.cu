@@ -1,0 +1,196 @@
+// Feasibility probe (not part of libpdsb): the inner loop of the FP32 direct-Fourier kernel with the image operand
+// read from the CONSTANT bank (uniform datapath: no shared-memory wavefronts, no per-lane register write-back)
+// instead of warp-broadcast LDS.128, including everything the real loop carries per row: the row-phase combine and
+// the fp32 row rotation, re-seeded every 32 rows.  Prints useful FMA throughput (1 FMA per folded pixel per uv point)
+// against the FP32 pipe peak for several (uv points per thread, column pairs per tile) shapes.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/probe_constbank scripts/probe_constbank.cu
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+__constant__ float c_slab[16384];
+
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi)
+{
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack2(u64 a, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+}
+
+// slab layout: [row][t][ (ss, ds), (sd, dd) ]  -> per row 4 TCP floats; rows = 16384 / (4 TCP)
+template <int UVT, int TCP, int MINB>
+__global__ void __launch_bounds__(128, MINB) probe_kernel(const double *__restrict__ fu, const double *__restrict__ fv,
+                                                          int slabs, float *out)
+{
+    constexpr int ROWS = 16384 / (4 * TCP);
+    const int tid = threadIdx.x;
+    const u64 *cs = reinterpret_cast<const u64 *>(c_slab);
+    u64 trig[UVT][TCP];
+    float Dr[UVT], Di[UVT];
+    double fvq[UVT];
+    double Vr[UVT], Vi[UVT];
+#pragma unroll
+    for (int q = 0; q < UVT; q++) {
+        const int k = (blockIdx.x * 128 + tid) * UVT + q;
+        const double f = fu[k];
+        fvq[q] = fv[k];
+        double s, c;
+        sincospi(2.0 * fvq[q], &s, &c);
+        Dr[q] = (float)c;
+        Di[q] = (float)s;
+        Vr[q] = Vi[q] = 0.0;
+        double cr, ci, rc, rs;
+        sincospi(2.0 * f * 0.5, &ci, &cr);
+        sincospi(2.0 * f, &rs, &rc);
+#pragma unroll
+        for (int t = 0; t < TCP; t++) {
+            trig[q][t] = pack2((float)cr, (float)ci);
+            const double nr = cr * rc - ci * rs;
+            ci = cr * rs + ci * rc;
+            cr = nr;
+        }
+    }
+#pragma unroll 1
+    for (int sl = 0; sl < slabs; sl++) {
+#pragma unroll 1
+        for (int ch = 0; ch < ROWS / 32; ch++) {
+            u64 E1[UVT], E2[UVT], W1[UVT], W2[UVT];           // (Er, Er), (Ei, Ei); sums of Er (a1, b1), Ei (a2, b2)
+#pragma unroll
+            for (int q = 0; q < UVT; q++) {
+                double b0 = fvq[q] * (double)(ch * 32 + sl);
+                b0 -= rint(b0);
+                float er, ei;
+                sincospif((float)(2.0 * b0), &ei, &er);
+                E1[q] = pack2(er, er);
+                E2[q] = pack2(ei, ei);
+                W1[q] = 0ull;
+                W2[q] = 0ull;
+            }
+#pragma unroll 2
+            for (int r = 0; r < 32; r++) {
+                const u64 *row = cs + (size_t)(ch * 32 + r) * (2 * TCP);
+                u64 p1[UVT], p2[UVT];
+#pragma unroll
+                for (int t = 0; t < TCP; t++) {
+                    const u64 x1 = row[2 * t], x2 = row[2 * t + 1];
+#pragma unroll
+                    for (int q = 0; q < UVT; q++) {
+                        if (t == 0) {
+                            p1[q] = mul2(x1, trig[q][0]);
+                            p2[q] = mul2(x2, trig[q][0]);
+                        } else {
+                            p1[q] = fma2(x1, trig[q][t], p1[q]);
+                            p2[q] = fma2(x2, trig[q][t], p2[q]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < UVT; q++) {
+                    W1[q] = fma2(E1[q], p1[q], W1[q]);
+                    W2[q] = fma2(E2[q], p2[q], W2[q]);
+                    // (Er, Ei) <- (Er, Ei) (Dr + i Di), packed: (Er, Er) (Dr, Di) + (Ei, Ei) (-Di, Dr)
+                    const u64 n = fma2(E2[q], pack2(-Di[q], Dr[q]), mul2(E1[q], pack2(Dr[q], Di[q])));
+                    float nr, ni;
+                    unpack2(n, nr, ni);
+                    E1[q] = pack2(nr, nr);
+                    E2[q] = pack2(ni, ni);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < UVT; q++) {
+                float a, b, c, d;
+                unpack2(W1[q], a, b);
+                unpack2(W2[q], c, d);
+                Vr[q] += (double)(a - d);
+                Vi[q] += (double)(b + c);
+            }
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int q = 0; q < UVT; q++) s += (float)(Vr[q] + Vi[q]);
+    out[blockIdx.x * 128 + tid] = s;
+}
+
+template <int UVT, int TCP, int MINB>
+static void run(const double *fu, const double *fv, float *out, int sm, int slabs)
+{
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_kernel<UVT, TCP, MINB>, 128, 0);
+    const int blocks = sm * per_sm * 4;
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, probe_kernel<UVT, TCP, MINB>);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        probe_kernel<UVT, TCP, MINB><<<blocks, 128>>>(fu, fv, slabs, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    const double fma = (double)blocks * 128 * UVT * slabs * 4096.0;      // 16384 floats per slab / 4 comps... x4 comps
+    const double useful = fma * 4.0 / 4.0;                                 // one FMA per folded value per uv point
+    const double tf = 2.0 * (double)blocks * 128 * UVT * (double)slabs * 16384.0 / (best * 1e-3) / 1e12;
+    (void)useful;
+    printf("uv%d tcp%-2d minb%d  regs %3d  CTAs/SM %d  %.3f ms  useful %.2f TFLOP/s  = %.3f of 74.45  (err %s)\n", UVT, TCP, MINB,
+           fa.numRegs, per_sm, best, tf, tf / 74.45, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main()
+{
+    int sm = 0;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
+    const int n = sm * 16 * 4 * 128 * 8;
+    std::vector<double> hu(n), hv(n);
+    for (int i = 0; i < n; i++) {
+        hu[i] = 1e-3 * (double)((i * 7919) % 1000) + 1e-4;
+        hv[i] = 1e-3 * (double)((i * 104729) % 997) + 2e-4;
+    }
+    std::vector<float> hs(16384);
+    for (int i = 0; i < 16384; i++) hs[i] = 1.0f + 1e-3f * (float)(i % 97);
+    cudaMemcpyToSymbol(c_slab, hs.data(), sizeof(float) * 16384);
+    double *fu, *fv;
+    float *out;
+    cudaMalloc(&fu, n * sizeof(double));
+    cudaMalloc(&fv, n * sizeof(double));
+    cudaMalloc(&out, (size_t)n * sizeof(float));
+    cudaMemcpy(fu, hu.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(fv, hv.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+    const int slabs = 8;
+    run<4, 16, 2>(fu, fv, out, sm, slabs);
+    run<4, 16, 3>(fu, fv, out, sm, slabs);
+    run<3, 16, 3>(fu, fv, out, sm, slabs);
+    run<3, 16, 4>(fu, fv, out, sm, slabs);
+    run<2, 32, 3>(fu, fv, out, sm, slabs);
+    run<2, 32, 4>(fu, fv, out, sm, slabs);
+    run<3, 32, 2>(fu, fv, out, sm, slabs);
+    run<2, 16, 4>(fu, fv, out, sm, slabs);
+    run<2, 16, 6>(fu, fv, out, sm, slabs);
+    run<6, 8, 3>(fu, fv, out, sm, slabs);
+    run<4, 8, 4>(fu, fv, out, sm, slabs);
+    run<5, 16, 2>(fu, fv, out, sm, slabs);
+    return 0;
+}
