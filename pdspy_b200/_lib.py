@@ -11,7 +11,7 @@ WEIGHTING = {"natural": 0, "uniform": 1, "superuniform": 2, "robust": 3}
 MODE = {"continuum": 0, "spectralline": 1}
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpdsb.so")
+LIB_PATH = os.environ.get("PDSPY_B200_LIB") or os.path.join(_HERE, "libpdsb.so")     # override: tuning builds
 
 
 class PdsbError(RuntimeError):

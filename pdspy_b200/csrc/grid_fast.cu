@@ -31,8 +31,14 @@
 
 namespace pdsb {
 
-constexpr int GF_ITEM = 512;        // visibilities per work item (one warp)
+#ifndef GF_ITEM_N
+#define GF_ITEM_N 512
+#endif
+constexpr int GF_ITEM = GF_ITEM_N;  // visibilities per work item (one warp)
 constexpr int GF_WARPS = 4;         // warps per CTA, each on its own item
+#ifndef GF_MINB
+#define GF_MINB 4
+#endif
 constexpr int GF_SCAN_THREADS = 1024;
 constexpr int GF_SCAN_PER = 8;          // = the 8 row keys of one tile: a scan thread owns a whole tile
 constexpr int GF_SCAN_SEG = GF_SCAN_THREADS * GF_SCAN_PER;
@@ -335,7 +341,7 @@ __device__ __forceinline__ double gf_exp_sinc_1d(double x)
 //      because the bucket (home row) fixes the rows.  When the bucket changes the two half-warps add their registers
 //      to the warp's private region in shared memory (plain read-modify-write, one half after the other).
 template <int WIDTH, int MODE>
-__global__ void __launch_bounds__(GF_WARPS * 32) gf_tile_kernel(GridParams P, int lo, uint32_t tg,
+__global__ void __launch_bounds__(GF_WARPS * 32, GF_MINB) gf_tile_kernel(GridParams P, int lo, uint32_t tg,
                                                                 const double2 *__restrict__ rec,
                                                                 const GfItem *__restrict__ items,
                                                                 const uint64_t *__restrict__ excl,
