@@ -322,7 +322,9 @@ __global__ void __launch_bounds__(256) fft_chi2_kernel(const FftSampleArgs P, in
         const FftCorner q = fft_corner(P, k);
         for (int i = lg; i < P.nf; i += gs) {
             const int64_t idx = k * P.nf + i;
-            const double ww = w[idx], a0 = dre[idx], b0 = dim[idx];
+            // the 1.5 GB of data stream through once: evict-first, so that they do not push the transformed cube
+            // (the gathers' working set, about the size of the L2) out of the cache
+            const double ww = __ldcs(w + idx), a0 = __ldcs(dre + idx), b0 = __ldcs(dim + idx);
             const double2 m = fft_sample_channel(P, q, i);
             const double a = a0 - m.x, b = b0 - m.y;
             sr += a * a * ww;

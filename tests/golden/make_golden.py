@@ -315,8 +315,40 @@ def main_invert_anysize():
     print("written", os.path.getsize(os.path.join(HERE, "invert_anysize_golden.npz")))
 
 
+def main_galario():
+    """The pin SURVEY.md 8c says is missing: run on a machine where `galario` IS installed (it is not in this
+    container).  Writes galario_golden.npz = the literal statements of interpolate_model.py:18-27 on seeded inputs;
+    tests/test_oracle_dft.py::test_galario_restatement_against_real_galario holds oracle/dft.py:galario_like to it."""
+    import galario                                    # noqa: F401  (fails here: that is the point of the hook)
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE)))
+    import synth
+    arcsec = 4.84813681e-6                            # constants/astronomy.py:9
+    out = {}
+    d = np.load(os.path.join(HERE, "fixture_720.npz"))
+    cases = {"fixture64": (d["u"], d["v"], synth.synth_image(64, 2, 0.5, kind="disk"), 0.5, 0.05, -0.03),
+             "c1_256": (*synth.synth_uv(2000, 0.1 * arcsec), synth.synth_image(256, 1, 0.1, kind="disk"), 0.1, 0.05, -0.03),
+             "random128": (*synth.synth_uv(500, 0.1 * arcsec), synth.synth_image(128, 3, 0.1, kind="random"), 0.1, 0.0, 0.0)}
+    for name, (u, v, img, px, dra, ddec) in cases.items():
+        u, v = np.ascontiguousarray(u, np.float64), np.ascontiguousarray(v, np.float64)
+        dxy = px * arcsec
+        real, imag = [], []
+        galario.double.threads(1)                     # interpolate_model.py:18
+        for i in range(img.shape[2]):                 # interpolate_model.py:22-27, verbatim
+            vis = galario.double.sampleImage(img[::-1, :, i, 0].copy(order="C"), dxy, u, v, dRA=dra * arcsec,
+                                             dDec=ddec * arcsec)
+            real.append(vis.real.reshape((u.size, 1)))
+            imag.append(-vis.imag.reshape((u.size, 1)))
+        out[name + "/u"], out[name + "/v"] = u, v
+        out[name + "/args"] = np.array([px, dra, ddec, img.shape[0], img.shape[2], 0 if name != "random128" else 1])
+        out[name + "/real"], out[name + "/imag"] = np.concatenate(real, axis=1), np.concatenate(imag, axis=1)
+    np.savez_compressed(os.path.join(HERE, "galario_golden.npz"), **out)
+    print("written galario_golden.npz (galario %s)" % getattr(galario, "__version__", "?"))
+
+
 if __name__ == "__main__":
     if "--invert-anysize" in sys.argv:
         main_invert_anysize()
+    elif "--galario" in sys.argv:
+        main_galario()
     else:
         main()

@@ -209,7 +209,14 @@ def test_dataset_cache_invalidation_on_in_place_change(gpu):
     assert relerr(b, ref) < TOL and relerr(a, ref) > 1e-3
 
 
-@pytest.mark.parametrize("n,nf,nuv,herm", [(64, 2, 500, True), (128, 3, 1000, False), (256, 1, 3000, True)])
+@pytest.mark.parametrize("n,nf,nuv,herm", [(64, 2, 500, True), (128, 3, 1000, False), (256, 1, 3000, True),
+                                           # the half-spectrum transform's corners: smallest sides (one radix-2 stage,
+                                           # odd / even stage counts), odd channel counts (a pair without a partner,
+                                           # ragged last block), more channels than a lane group, a side that needs
+                                           # the strided per-thread loops and 128 KB of shared memory
+                                           (2, 1, 40, False), (4, 2, 60, True), (8, 5, 80, False), (16, 7, 100, True),
+                                           (32, 40, 200, False), (1024, 2, 300, True), (2048, 1, 200, False),
+                                           (4096, 1, 100, True)])
 def test_galario_fft_path_vs_restated_galario_algorithm(gpu, n, nf, nuv, herm):
     """code="galario-fft": the reference's own algorithm (FFT + bilinear interpolation, oracle/dft.py:galario_like)
     on the GPU, fp64 throughout: 1e-12 of max|V|; and the method gap to the exact transform is galario's."""
@@ -228,7 +235,8 @@ def test_galario_fft_path_vs_restated_galario_algorithm(gpu, n, nf, nuv, herm):
     assert relerr(vis, ref) < 1e-12
     exact = interpolate_model(u, v, m.freq, m, dRA=0.04, dDec=-0.03)
     gap = np.abs((vis.real - exact.real) + 1j * (vis.imag - exact.imag)).max() / np.abs(ref).max()
-    assert gap < 0.1                                   # the two methods describe the same sky
+    if n >= 64:
+        assert gap < 0.1                               # the two methods describe the same sky
 
 
 def test_galario_fft_likelihood_and_grid_points(gpu):
@@ -247,13 +255,16 @@ def test_galario_fft_likelihood_and_grid_points(gpu):
     b = interpolate_model(u, v, m.freq, m)
     scale = np.abs(b.real + 1j * b.imag).max()
     assert np.abs((a.real - b.real) + 1j * (a.imag - b.imag)).max() / scale < 2e-6     # fp32 products in b
-    u2, v2 = synth.synth_uv(800, px * A)
-    re, im, w = synth.synth_data(800, nf)
-    data = Visibilities(u2, v2, m.freq, re, im, w)
-    ll, c_re, c_im = loglike_image_fft(data, m, dRA=0.01, dDec=0.02)
-    vis = interpolate_model(u2, v2, m.freq, m, dRA=0.01, dDec=0.02, code="galario-fft")
-    ll_ref = ol.lnlike_vis_numpy(re, im, w, vis.real, vis.imag)
-    assert abs(ll - ll_ref) <= 1e-10 * abs(ll_ref)
+    for nf2 in (nf, 1, 3, 37):                         # lane groups of 2, 1, 2 and 32 channels
+        img2 = synth.synth_image(n, nf2, px, kind="disk")
+        m2 = synth.SynthImage(img2, px, synth.synth_freq(nf2))
+        u2, v2 = synth.synth_uv(800, px * A)
+        re, im, w = synth.synth_data(800, nf2)
+        data = Visibilities(u2, v2, m2.freq, re, im, w)
+        ll, c_re, c_im = loglike_image_fft(data, m2, dRA=0.01, dDec=0.02)
+        vis = interpolate_model(u2, v2, m2.freq, m2, dRA=0.01, dDec=0.02, code="galario-fft")
+        ll_ref = ol.lnlike_vis_numpy(re, im, w, vis.real, vis.imag)
+        assert abs(ll - ll_ref) <= 1e-10 * abs(ll_ref), nf2
 
 
 @pytest.mark.parametrize("ny,nx,nf,nuv,herm", [(64, 64, 2, 400, True), (63, 65, 3, 333, False), (130, 34, 9, 64, True),
