@@ -530,6 +530,8 @@ def galario_fft_leg(env, cfg, steps, handles):
     if env.rank != 0:
         return None
     pairs_step = float(n) * n * cfg["nuv"] * nf
+    hbm = peaks().get("hbm_gbs", 6650.0)
+    alg_bytes = float(cube.nbytes) + 24.0 * like.ds.nuv * nf          # per rank: whole cube + its uv shard's data
     return {"what": "the reference's OWN algorithm for this step on the GPU - galario's FFT + bilinear interpolation "
                     "(pdsb_loglike_fft, fp64, restated from galario's published algorithm) + the same chi^2; it "
                     "carries galario's interpolation error (1e-3..4e-2 of max|V|), which the direct transform of "
@@ -538,6 +540,17 @@ def galario_fft_leg(env, cfg, steps, handles):
             "ms_per_step": ms / steps, "value": pairs_step * steps / (ms * 1e-3), "unit": UNIT,
             "e2e": {"value": pairs_step * steps / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / steps * 1e3,
                     "h2d_bytes_per_step": int(cube.nbytes) * env.world, "d2h_bytes_per_step": 32 * env.world},
+            "roofline": {"kernel": "rfft2_planes (half-spectrum FFT of every channel) + fft_chi2_kernel (bilinear gather fused "
+                                   "with the chi^2 sums)", "bound": "hbm",
+                         "algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (ms / steps * 1e-3) / 1e9,
+                         "peak": hbm, "unit": "GB/s", "frac": alg_bytes / (ms / steps * 1e-3) / 1e9 / hbm,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+                         "algorithmic_bytes_note": "fp64 cube read once + real, imag, weights of this rank's shard read once "
+                                                   "(24 B per visibility and channel); the transformed half spectrum is "
+                                                   "scratch",
+                         "traffic": ncu_traffic("%s:galario_fft:%d" % (cfg["name"], env.world)),
+                         "traffic_source": "sum of dram__bytes_read + dram__bytes_write over the path's launches in one "
+                                           "`ncu --set full` capture (profiles/traffic.json); null where not captured"},
             "lnlike_shard": float(fft_out[3])}
 
 
@@ -582,6 +595,13 @@ def gridding_leg(env, cfg, steps, warmup, cpu_baseline=False, sample_clocks=Fals
     total_ms, k_ms, k_n, launches, clocks, _ = timed_device_steps(env, step, steps, warmup, b"grid_tile",
                                                                   sample_clocks=sample_clocks)
     wsum = float(maps[2].sum().item())
+    phases = {}
+    for name in (b"grid_tile_hist", b"grid_tile_scan", b"grid_tile_records", b"grid_tile_accum", b"grid_normalise"):
+        t_ms, t_n = env.profile(name)
+        if t_n:
+            phases[name.decode()] = t_ms / t_n
+    FP64_OPS_PER_VIS = 12 * 33 + 126
+    fp64_peak = 148 * 64 * peaks().get("sm_max_mhz", 1965.0) * 1e6 / 1e12
     # end to end through the Python mirror: host numpy arrays in, gridded Visibilities out
     shard = Visibilities(us, vs, freq, re, im, w)
 
@@ -614,12 +634,25 @@ def gridding_leg(env, cfg, steps, warmup, cpu_baseline=False, sample_clocks=Fals
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs",
                             "algorithmic_bytes": alg_bytes,
                             "algorithmic_bytes_note": "40 B per visibility + 24 B per cell (SURVEY.md 8d), whole job",
-                            "tile_kernel_ms": k_ms,
+                            "phase_ms": phases,
                             "traffic": ncu_traffic("C4:grid:%d" % world),
                             "traffic_source": "sum of dram__bytes_read + dram__bytes_write over the step's launches in one "
                                               "`ncu --set full` capture (profiles/traffic.json); null where not captured",
-                            "note": "36 fp64 read-modify-writes per visibility make on-chip accumulation, not HBM, the "
-                                    "limiter (SURVEY.md section 8d caveat)"}}
+                            "dominant_kernel": {
+                                "kernel": "gf_tile_kernel<6,0> (records -> register accumulation -> one fp64 atomic per region cell)",
+                                "bound": "fp64 pipe", "launch_ms": phases.get("grid_tile_accum"),
+                                "useful_fp64_ops_per_vis": FP64_OPS_PER_VIS,
+                                "achieved": (nloc * FP64_OPS_PER_VIS / (phases["grid_tile_accum"] * 1e-3) / 1e12
+                                             if phases.get("grid_tile_accum") else None),
+                                "peak": fp64_peak, "unit": "T fp64 instructions/s (FMA = 1)",
+                                "frac": (nloc * FP64_OPS_PER_VIS / (phases["grid_tile_accum"] * 1e-3) / 1e12 / fp64_peak
+                                         if phases.get("grid_tile_accum") else None),
+                                "peak_source": "nominal: SMs x 64 fp64 lanes x sm_max_mhz (a dense DFMA stream measured 0.91 of it)",
+                                "note": "12 exp*sinc factors per visibility in the reference's operation order (33 fp64 "
+                                        "instructions each) + the 6 x 6 x 3 outer-product accumulation (126): the "
+                                        "arithmetic alone is 0.28 ms of fp64 pipe per 10M visibilities, so HBM on the "
+                                        "algorithmic bytes (SURVEY.md 8d) is not the limiter of this step; ncu: "
+                                        "sm__pipe_fp64_cycles_active 54 %, DRAM 8 % (profiles/r02_grid_ncu.md)"}}}
         if cpu_baseline:
             from oracle import build_ref
             ref = build_ref.load()
