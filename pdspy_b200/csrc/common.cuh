@@ -94,6 +94,10 @@ struct LaunchScope {
 
 // Pointer staging: returns a device pointer for `p`; copies from host when kind==HOST.
 int to_device(const void *p, int kind, size_t bytes, Scratch &scratch, const void **dev);
+// host <-> device copies on the context's stream; large pageable arrays go through a multi-threaded pinned ring
+// (runtime.cu).  copy_h2d returns when the source may be reused, copy_d2h when the destination holds the data.
+int copy_h2d(void *dst_dev, const void *src_host, size_t bytes);
+int copy_d2h(void *dst_host, const void *src_dev, size_t bytes);
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

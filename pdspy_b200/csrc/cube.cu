@@ -91,13 +91,13 @@ int pdsb_regrid_linear(const double *values, int64_t npts, const int *tri, const
                      bt = (size_t)npix * 3 * sizeof(int);
         PDSB_CHECK(c.stage_a.ensure(bv + bb + bt + 256));
         unsigned char *p = c.stage_a.as<unsigned char>();
-        PDSB_CUDA(cudaMemcpyAsync(p, values, bv, cudaMemcpyHostToDevice, c.stream));
+        PDSB_CHECK(copy_h2d(p, values, bv));
         dv = reinterpret_cast<const double *>(p);
         p += (bv + 63) / 64 * 64;
-        PDSB_CUDA(cudaMemcpyAsync(p, bary, bb, cudaMemcpyHostToDevice, c.stream));
+        PDSB_CHECK(copy_h2d(p, bary, bb));
         db = reinterpret_cast<const double *>(p);
         p += (bb + 63) / 64 * 64;
-        PDSB_CUDA(cudaMemcpyAsync(p, tri, bt, cudaMemcpyHostToDevice, c.stream));
+        PDSB_CHECK(copy_h2d(p, tri, bt));
         dt = reinterpret_cast<const int *>(p);
         PDSB_CHECK(c.stage_b.ensure((size_t)npix * nf * sizeof(double)));
         dout = c.stage_b.as<double>();
@@ -108,7 +108,7 @@ int pdsb_regrid_linear(const double *values, int64_t npts, const int *tri, const
         PDSB_CUDA(cudaGetLastError());
     }
     if (kind == PDSB_HOST) {
-        PDSB_CUDA(cudaMemcpyAsync(out, dout, (size_t)npix * nf * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CHECK(copy_d2h(out, dout, (size_t)npix * nf * sizeof(double)));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
     return PDSB_OK;
@@ -142,7 +142,7 @@ int pdsb_channel_postprocess_scaled(const double *image, int64_t npix, int nf_in
     const double *dscale = nullptr;
     if (in_scale) {                                           // always a host array: nf_in doubles
         PDSB_CHECK(c.small_dev.ensure((size_t)nf_in * sizeof(double)));
-        PDSB_CUDA(cudaMemcpyAsync(c.small_dev.ptr, in_scale, (size_t)nf_in * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        PDSB_CHECK(copy_h2d(c.small_dev.ptr, in_scale, (size_t)nf_in * sizeof(double)));
         dscale = c.small_dev.as<double>();
     }
     {
@@ -153,7 +153,7 @@ int pdsb_channel_postprocess_scaled(const double *image, int64_t npix, int nf_in
         PDSB_CUDA(cudaGetLastError());
     }
     if (kind == PDSB_HOST) {
-        PDSB_CUDA(cudaMemcpyAsync(out, dout, (size_t)npix * nf_out * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CHECK(copy_d2h(out, dout, (size_t)npix * nf_out * sizeof(double)));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
     return PDSB_OK;

@@ -404,13 +404,13 @@ extern "C" int pdsb_invert_image(const double *g_real, const double *g_imag, con
     if (kind == PDSB_HOST) {
         PDSB_CHECK(c.stage_a.ensure((size_t)(2 * nn * nch + nn) * sizeof(double)));
         double *p = c.stage_a.as<double>();
-        PDSB_CUDA(cudaMemcpyAsync(p, g_real, (size_t)nn * nch * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        PDSB_CHECK(copy_h2d(p, g_real, (size_t)nn * nch * sizeof(double)));
         dre = p;
         p += nn * nch;
-        PDSB_CUDA(cudaMemcpyAsync(p, g_imag, (size_t)nn * nch * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        PDSB_CHECK(copy_h2d(p, g_imag, (size_t)nn * nch * sizeof(double)));
         dim = p;
         p += nn * nch;
-        PDSB_CUDA(cudaMemcpyAsync(p, conv, (size_t)nn * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        PDSB_CHECK(copy_h2d(p, conv, (size_t)nn * sizeof(double)));
         dconv = p;
         PDSB_CHECK(c.stage_b.ensure((size_t)nn * nch * sizeof(double)));
         dout = c.stage_b.as<double>();
@@ -460,7 +460,7 @@ extern "C" int pdsb_invert_image(const double *g_real, const double *g_imag, con
         PDSB_CUDA(cudaGetLastError());
     }
     if (kind == PDSB_HOST) {
-        PDSB_CUDA(cudaMemcpyAsync(image_out, dout, (size_t)nn * nch * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CHECK(copy_d2h(image_out, dout, (size_t)nn * nch * sizeof(double)));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
     return PDSB_OK;

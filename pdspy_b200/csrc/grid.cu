@@ -891,7 +891,7 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
                 *dst = src;
                 return PDSB_OK;
             }
-            PDSB_CUDA(cudaMemcpyAsync(p, src, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+            PDSB_CHECK(copy_h2d(p, src, n * sizeof(double)));
             *dst = p;
             p += n;
             return PDSB_OK;
@@ -1132,16 +1132,22 @@ static int grid_impl(const double *u, const double *v, const double *freq, const
     }
 
     // ---- outputs ----
-    cudaMemcpyKind ok = out_kind == PDSB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    auto give = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (out_kind == PDSB_DEVICE) {
+            PDSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.stream));
+            return PDSB_OK;
+        }
+        return copy_d2h(dst, src, bytes);
+    };
     if (!direct_out) {
-        if (out_real) PDSB_CUDA(cudaMemcpyAsync(out_real, o_re, (size_t)ncell * sizeof(double), ok, c.stream));
-        if (out_imag) PDSB_CUDA(cudaMemcpyAsync(out_imag, o_im, (size_t)ncell * sizeof(double), ok, c.stream));
-        if (out_weights) PDSB_CUDA(cudaMemcpyAsync(out_weights, o_w, (size_t)ncell * sizeof(double), ok, c.stream));
+        if (out_real) PDSB_CHECK(give(out_real, o_re, (size_t)ncell * sizeof(double)));
+        if (out_imag) PDSB_CHECK(give(out_imag, o_im, (size_t)ncell * sizeof(double)));
+        if (out_weights) PDSB_CHECK(give(out_weights, o_w, (size_t)ncell * sizeof(double)));
     }
     if (nvis > 0) {
-        if (out_i) PDSB_CUDA(cudaMemcpyAsync(out_i, gi, (size_t)nvis * sizeof(uint32_t), ok, c.stream));
-        if (out_j) PDSB_CUDA(cudaMemcpyAsync(out_j, gj, (size_t)nvis * sizeof(uint32_t), ok, c.stream));
-        if (out_wmod) PDSB_CUDA(cudaMemcpyAsync(out_wmod, w_work, (size_t)nvis * sizeof(double), ok, c.stream));
+        if (out_i) PDSB_CHECK(give(out_i, gi, (size_t)nvis * sizeof(uint32_t)));
+        if (out_j) PDSB_CHECK(give(out_j, gj, (size_t)nvis * sizeof(uint32_t)));
+        if (out_wmod) PDSB_CHECK(give(out_wmod, w_work, (size_t)nvis * sizeof(double)));
     }
     unsigned long long hn = 0;
     if (n_outside || out_kind == PDSB_HOST) {
@@ -1266,7 +1272,7 @@ int pdsb_average(const double *u, const double *v, const double *uvdist, const d
         auto put = [&](const double *src, size_t n, const double **dst) -> int {
             *dst = p;
             if (n == 0 || !src) return PDSB_OK;
-            PDSB_CUDA(cudaMemcpyAsync(p, src, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+            PDSB_CHECK(copy_h2d(p, src, n * sizeof(double)));
             p += n;
             return PDSB_OK;
         };
@@ -1388,7 +1394,7 @@ int pdsb_center(const double *u, const double *v, const double *freq, const doub
         PDSB_CHECK(c.stage_a.ensure((size_t)(2 * nuv + nf + 2 * n) * sizeof(double) + 64));
         double *p = c.stage_a.as<double>();
         auto put = [&](const double *src, size_t cnt, const double **dst) -> int {
-            PDSB_CUDA(cudaMemcpyAsync(p, src, cnt * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+            PDSB_CHECK(copy_h2d(p, src, cnt * sizeof(double)));
             *dst = p;
             p += cnt;
             return PDSB_OK;

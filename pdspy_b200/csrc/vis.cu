@@ -572,10 +572,15 @@ int pdsb_dataset_set_data(pdsb_dataset *ds, const double *real, const double *im
         cudaGetLastError();
         return PDSB_ERR_NOMEM;
     }
-    cudaMemcpyKind mk = kind == PDSB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    PDSB_CUDA(cudaMemcpyAsync(ds->re, real, n * sizeof(double), mk, c.stream));
-    PDSB_CUDA(cudaMemcpyAsync(ds->im, imag, n * sizeof(double), mk, c.stream));
-    PDSB_CUDA(cudaMemcpyAsync(ds->w, weights, n * sizeof(double), mk, c.stream));
+    if (kind == PDSB_DEVICE) {
+        PDSB_CUDA(cudaMemcpyAsync(ds->re, real, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(ds->im, imag, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(ds->w, weights, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    } else {
+        PDSB_CHECK(copy_h2d(ds->re, real, n * sizeof(double)));
+        PDSB_CHECK(copy_h2d(ds->im, imag, n * sizeof(double)));
+        PDSB_CHECK(copy_h2d(ds->w, weights, n * sizeof(double)));
+    }
     // data-only constant of the likelihood
     const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (int64_t)((n + 255) / 256));
     PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * sizeof(double)));
@@ -640,8 +645,8 @@ int pdsb_sample_image(pdsb_dataset *ds, const double *image, int ny, int nx, int
         PDSB_CUDA(cudaGetLastError());
     }
     if (out_kind == PDSB_HOST) {
-        PDSB_CUDA(cudaMemcpyAsync(out_real, ore, bytes, cudaMemcpyDeviceToHost, c.stream));
-        PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, bytes, cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CHECK(copy_d2h(out_real, ore, bytes));
+        PDSB_CHECK(copy_d2h(out_imag, oim, bytes));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
     return PDSB_OK;
@@ -789,8 +794,8 @@ int pdsb_sample_image_fft(pdsb_dataset *ds, const double *image, int n, int nf, 
         PDSB_CUDA(cudaGetLastError());
     }
     if (out_kind == PDSB_HOST) {
-        PDSB_CUDA(cudaMemcpyAsync(out_real, ore, bytes, cudaMemcpyDeviceToHost, c.stream));
-        PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, bytes, cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CHECK(copy_d2h(out_real, ore, bytes));
+        PDSB_CHECK(copy_d2h(out_imag, oim, bytes));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
     return PDSB_OK;
@@ -868,8 +873,8 @@ int pdsb_sample_triangles(pdsb_dataset *ds, const void *tri_records, int ntri, c
         PDSB_CUDA(cudaGetLastError());
     }
     if (out_kind == PDSB_HOST) {
-        PDSB_CUDA(cudaMemcpyAsync(out_real, ore, bytes, cudaMemcpyDeviceToHost, c.stream));
-        PDSB_CUDA(cudaMemcpyAsync(out_imag, oim, bytes, cudaMemcpyDeviceToHost, c.stream));
+        PDSB_CHECK(copy_d2h(out_real, ore, bytes));
+        PDSB_CHECK(copy_d2h(out_imag, oim, bytes));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
     return PDSB_OK;

@@ -77,3 +77,26 @@ def test_errors_surface_as_exceptions(gpu):
     with pytest.raises(_lib.PdsbError):
         _lib.check(gpu.pdsb_sample_image(ds.handle, _lib.ptr(img), 8, 8, 2, _lib.HOST, -1.0, 0.0, 0.0, _lib.ptr(out),
                                          _lib.ptr(out), _lib.HOST))
+
+
+def test_staged_copies_of_large_pageable_arrays(gpu):
+    """Host arrays of 16 MB and more travel through a ring of pinned buffers filled by several host threads
+    (runtime.cu: copy_h2d / copy_d2h); the bytes must arrive unchanged, for sizes that are not a multiple of the
+    4 MB chunk and for pinned memory (which goes straight through)."""
+    rng = np.random.default_rng(11)
+    for n in (2 * 1024 * 1024 + 7, 9 * 1024 * 1024 + 12345, 40 * 1024 * 1024 + 1):     # doubles: 16 MB+, 72 MB+, 320 MB+
+        a = rng.random(n)
+        d = DeviceBuffer.from_numpy(a)
+        back = np.empty_like(a)
+        _lib.check(gpu.pdsb_memcpy(_lib.ptr(back), _lib.HOST, _lib.ptr(d), _lib.DEVICE, a.nbytes))
+        _lib.check(gpu.pdsb_synchronize())
+        assert np.array_equal(a, back), n
+        d.free()
+    p = PinnedArray((3 * 1024 * 1024,))                  # 24 MB of pinned memory: not staged
+    p.array[:] = rng.random(p.array.size)
+    d = DeviceBuffer(p.array.nbytes)
+    _lib.check(gpu.pdsb_memcpy(_lib.ptr(d), _lib.DEVICE, _lib.ptr(p.array), _lib.HOST, p.array.nbytes))
+    _lib.check(gpu.pdsb_synchronize())
+    np.testing.assert_array_equal(d.download(p.array.shape), p.array)
+    p.free()
+    d.free()
