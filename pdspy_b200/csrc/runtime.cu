@@ -97,6 +97,25 @@ LaunchScope::~LaunchScope()
 // copies through the driver's own pinned buffer with one thread (8-12 GB/s here); several host threads copying
 // 4 MB chunks into a ring of pinned buffers of ours, each chunk going on with cudaMemcpyAsync as soon as it is
 // staged, keep the PCIe link busy instead.  Pinned / registered memory and small arrays go straight through.
+// work(t) for t < nt on nt threads (the caller is thread 0).  A thread that cannot be created (resource limits) must
+// not throw across the C ABI: its share runs on the calling thread instead.
+template <class F>
+static void run_threads(int nt, F &&work)
+{
+    std::vector<std::thread> th;
+    std::vector<int> inline_ids;
+    for (int t = 1; t < nt; t++) {
+        try {
+            th.emplace_back(work, t);
+        } catch (...) {
+            inline_ids.push_back(t);
+        }
+    }
+    work(0);
+    for (int t : inline_ids) work(t);
+    for (auto &t : th) t.join();
+}
+
 struct StagePool {
     static constexpr size_t CHUNK = (size_t)4 << 20;
     int nthreads = 0;
@@ -166,10 +185,7 @@ int copy_h2d(void *dst, const void *src, size_t bytes)
             if (e != cudaSuccess) err[t] = e;
         }
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto &t : th) t.join();
+    run_threads(nt, work);
     for (cudaError_t e : err) PDSB_CUDA(e);
     return PDSB_OK;
 }
@@ -209,10 +225,7 @@ int copy_d2h(void *dst, const void *src, size_t bytes)
         }
         if (k >= 1) drain(k - 1);
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto &t : th) t.join();
+    run_threads(nt, work);
     for (cudaError_t e : err) PDSB_CUDA(e);
     return PDSB_OK;
 }
@@ -594,12 +607,7 @@ int pdsb_hash64(const void *host_ptr, int64_t bytes, uint64_t *out)
             hs[c] = hash_chunk(p + o, n - o < chunk ? n - o : chunk);
         }
     };
-    if (nt <= 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
-        for (auto &t : th) t.join();
-    }
+    run_threads((int)nt, work);
     *out = hash_chunk(reinterpret_cast<const unsigned char *>(hs.data()), nchunk * sizeof(uint64_t)) ^ (uint64_t)n;
     return PDSB_OK;
 }

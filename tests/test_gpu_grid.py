@@ -307,3 +307,27 @@ def test_band_needs_ordered_raw_natural(gpu):
     finally:
         _lib.check(gpu.pdsb_set_grid_band(0, 0))
     assert gpu.pdsb_set_grid_band(5, 5) != 0
+
+
+@pytest.mark.parametrize("G", [5, 8, 24, 300])
+@pytest.mark.parametrize("convolution", ["pillbox", "expsinc"])
+def test_fast_mode_hot_cells_and_tiny_grids(gpu, G, convolution):
+    """The sorted-tile mode on what stresses its sort: 90 % of 200 k visibilities inside ONE cell (a key run cut
+    into hundreds of work items, every rank issued by the shared-memory window), grids smaller than the window
+    and smaller than one tile, sides that are not a multiple of the tile; against the ordered mode."""
+    rng = np.random.default_rng(G)
+    n, nf = 200_000, 1
+    binsize = 5000.0
+    hot = rng.random(n) < 0.9
+    u = np.where(hot, rng.uniform(0.1, 0.9, n) * binsize, rng.normal(0, 0.3 * G * binsize, n))
+    v = np.where(hot, rng.uniform(0.1, 0.9, n) * binsize, rng.normal(0, 0.3 * G * binsize, n))
+    freq = np.array([230e9])
+    re, im = rng.normal(size=(n, nf)), rng.normal(size=(n, nf))
+    w = rng.uniform(0.5, 2, (n, nf))
+    d = Visibilities(u, v, freq, re, im, w)
+    kw = dict(gridsize=G, binsize=binsize, convolution=convolution, imaging=True)
+    a, _ = _quiet(grid, d, deterministic=True, **kw)
+    b, _ = _quiet(grid, d, deterministic=False, **kw)
+    for nm in ("real", "imag", "weights"):
+        x, y = getattr(a, nm), getattr(b, nm)
+        assert np.abs(x - y).max() <= 1e-11 * np.abs(x).max(), (G, convolution, nm)
