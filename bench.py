@@ -514,16 +514,18 @@ def chain_leg(env, cfg, dft, steps):
             "h2d_bytes_per_step": int(model.image.nbytes) * world, "d2h_bytes_per_step": 32 * world}
 
 
-def galario_fft_leg(env, cfg, steps, handles):
-    """extra: the reference's own algorithm (galario: FFT + bilinear interpolation) on the GPU, this rank's shard."""
+def galario_fft_leg(env, cfg, steps, handles, nufft=False):
+    """extra: the reference's own algorithm (galario: FFT + bilinear interpolation) on the GPU, this rank's shard;
+    nufft=True: the exact transform through the 8-point non-uniform FFT instead (same FFT path, 8 x 8 taps)."""
     like, dcube, pinned, cube, (dxy, dra, ddec) = handles
     _lib, L = env._lib, env.L
     n, nf = cfg["npix"], cfg["nf"]
     fft_out = np.empty(4)
+    entry = L.pdsb_loglike_nufft if nufft else L.pdsb_loglike_fft
 
     def step(image, kind):
-        _lib.check(L.pdsb_loglike_fft(like.ds.handle, _lib.ptr(image), n, nf, kind, float(dxy), float(dra), float(ddec),
-                                      _lib.ptr(fft_out)))
+        _lib.check(entry(like.ds.handle, _lib.ptr(image), n, nf, kind, float(dxy), float(dra), float(ddec),
+                         _lib.ptr(fft_out)))
         return float(fft_out[3])
     ms, _, _, _, _, _ = timed_device_steps(env, lambda: step(dcube, _lib.DEVICE), steps, 2)
     e2e_s, _ = timed_host_steps(env, lambda: step(pinned.array, _lib.HOST), steps)
@@ -532,23 +534,33 @@ def galario_fft_leg(env, cfg, steps, handles):
     pairs_step = float(n) * n * cfg["nuv"] * nf
     hbm = peaks().get("hbm_gbs", 6650.0)
     alg_bytes = float(cube.nbytes) + 24.0 * like.ds.nuv * nf          # per rank: whole cube + its uv shard's data
-    return {"what": "the reference's OWN algorithm for this step on the GPU - galario's FFT + bilinear interpolation "
-                    "(pdsb_loglike_fft, fp64, restated from galario's published algorithm) + the same chi^2; it "
-                    "carries galario's interpolation error (1e-3..4e-2 of max|V|), which the direct transform of "
-                    "value / e2e does not; pairs/s counts the pairs the result represents, as in --impl reference; "
-                    "NOT used for value / e2e; chi^2 of this rank's uv shard, no all-reduce",
+    what = ("the reference's OWN algorithm for this step on the GPU - galario's FFT + bilinear interpolation "
+            "(pdsb_loglike_fft, fp64, restated from galario's published algorithm) + the same chi^2; it "
+            "carries galario's interpolation error (1e-3..4e-2 of max|V|), which the direct transform of "
+            "value / e2e does not; pairs/s counts the pairs the result represents, as in --impl reference; "
+            "NOT used for value / e2e; chi^2 of this rank's uv shard, no all-reduce")
+    if nufft:
+        what = ("the EXACT transform of value / e2e through a type-2 non-uniform FFT (pdsb_loglike_nufft, fp64: image / "
+                "kernel transform, zero-padded to 2n, FFT per channel, 8 x 8 exponential-of-semicircle taps per visibility "
+                "and channel) + the same chi^2: 4e-8 of max|V| from the exact oracle (tests/test_gpu_nufft.py), i.e. inside "
+                "the tolerances of the direct sum at the cost of an FFT path; pairs/s counts the pairs the result "
+                "represents; NOT used for value / e2e (the north star prescribes the direct sum); chi^2 of this rank's "
+                "uv shard, no all-reduce")
+    return {"what": what,
             "ms_per_step": ms / steps, "value": pairs_step * steps / (ms * 1e-3), "unit": UNIT,
             "e2e": {"value": pairs_step * steps / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / steps * 1e3,
                     "h2d_bytes_per_step": int(cube.nbytes) * env.world, "d2h_bytes_per_step": 32 * env.world},
-            "roofline": {"kernel": "rfft2_planes (half-spectrum FFT of every channel) + fft_chi2_kernel (bilinear gather fused "
-                                   "with the chi^2 sums)", "bound": "hbm",
+            "roofline": {"kernel": ("rfft2_planes_padded (half-spectrum FFT at 2n) + nufft_chi2_kernel (8 x 8 taps fused with the "
+                                    "chi^2 sums; one evaluation per Hermitian pair)") if nufft else
+                                   ("rfft2_planes (half-spectrum FFT of every channel) + fft_chi2_kernel (bilinear gather fused "
+                                    "with the chi^2 sums)"), "bound": "hbm",
                          "algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (ms / steps * 1e-3) / 1e9,
                          "peak": hbm, "unit": "GB/s", "frac": alg_bytes / (ms / steps * 1e-3) / 1e9 / hbm,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs",
                          "algorithmic_bytes_note": "fp64 cube read once + real, imag, weights of this rank's shard read once "
                                                    "(24 B per visibility and channel); the transformed half spectrum is "
                                                    "scratch",
-                         "traffic": ncu_traffic("%s:galario_fft:%d" % (cfg["name"], env.world)),
+                         "traffic": ncu_traffic("%s:%s:%d" % (cfg["name"], "nufft" if nufft else "galario_fft", env.world)),
                          "traffic_source": "sum of dram__bytes_read + dram__bytes_write over the path's launches in one "
                                            "`ncu --set full` capture (profiles/traffic.json); null where not captured"},
             "lnlike_shard": float(fft_out[3])}
@@ -841,6 +853,11 @@ def main():
                 ff["lnlike_gap_note"] = ("the direct transform (value / e2e) and galario's FFT + bilinear interpolation differ "
                                          "by galario's interpolation error: at N=1 compare lnlike_shard with the headline lnlike")
                 extras["galario_fft_algorithm"] = ff
+            nu = galario_fft_leg(env, cfg, ksteps, keep, nufft=True)
+            if rank == 0:
+                if world == 1 and line.get("lnlike"):
+                    nu["lnlike_rel_diff_vs_headline"] = abs(nu["lnlike_shard"] - line["lnlike"]) / abs(line["lnlike"])
+                extras["nufft_exact_transform"] = nu
         keep[0].ds.destroy()
         keep[1].free()
         keep[2].free()

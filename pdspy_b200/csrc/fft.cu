@@ -284,25 +284,36 @@ __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, 
     }
 }
 
-// row pass: block = rows (2 blockIdx.x, 2 blockIdx.x + 1) of the shifted planes x plane pairs [PB blockIdx.y, ...)
-// -> T[plane][b][row], b <= n/2  (T: [nf][n/2 + 1][n])
+// row pass: block = rows (rho, rho + 1), rho = 2 blockIdx.x, of the (row-flipped) source planes x plane pairs
+// [PB blockIdx.y, ...) -> T[plane][b][r'], b <= n/2  (T: [nf][n/2 + 1][n]).
+// The transform length n may exceed the source side nsrc (zero padding for the NUFFT path, nsrc = n otherwise):
+// the source pixel with centred coordinates (R, C) = (rho - nsrc/2, gamma - nsrc/2) sits at (R mod n, C mod n),
+// i.e. the image centre is the origin of the transform (the ifftshift of the unpadded case); corr (may be null)
+// multiplies pixel (rho, gamma) by corr[rho] corr[gamma] (the NUFFT's deapodisation).  Rows r' that hold no source row
+// are never written: the column pass knows they are zero.
 __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict__ cube, const double2 *__restrict__ twg,
                                                         double2 *__restrict__ T, int n, int logn, int nf, int flip,
-                                                        int PB, int tpf)
+                                                        int PB, int tpf, int nsrc, const double *__restrict__ corr)
 {
     extern __shared__ double2 srow[];
-    const int h = n / 2, npair = (nf + 1) / 2;
+    const int h = n / 2, hs = nsrc / 2, npair = (nf + 1) / 2;
     const int pair0 = blockIdx.y * PB;
     const int pb_n = npair - pair0 < PB ? npair - pair0 : PB;          // pairs this block really has
     const int nfft = 2 * pb_n;                                          // [row 0..1][pair]
+    const int rho0 = 2 * blockIdx.x;
     double2 *tw = srow + (size_t)2 * PB * n;
     for (int j = threadIdx.x; j < h; j += blockDim.x) tw[j] = twg[j];
     // loads: pair fastest (adjacent doubles of the cube), then column, then row
     for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
         const int pb = idx % pb_n, c = (idx / pb_n) % n, rb = idx / (pb_n * n);
-        const int rs = (2 * blockIdx.x + rb + h) % n;
-        const int64_t src = ((int64_t)(flip ? n - 1 - rs : rs) * n + (c + h) % n) * nf + 2 * (pair0 + pb);
-        const double re = cube[src], im = 2 * (pair0 + pb) + 1 < nf ? cube[src + 1] : 0.0;
+        const int rho = rho0 + rb, gamma = (c < h ? c : c - n) + hs;
+        double re = 0.0, im = 0.0;
+        if (gamma >= 0 && gamma < nsrc) {
+            const int64_t src = ((int64_t)(flip ? nsrc - 1 - rho : rho) * nsrc + gamma) * nf + 2 * (pair0 + pb);
+            const double f = corr ? corr[rho] * corr[gamma] : 1.0;
+            re = cube[src] * f;
+            if (2 * (pair0 + pb) + 1 < nf) im = cube[src + 1] * f;
+        }
         srow[(size_t)(rb * pb_n + pb) * n + bitrev((unsigned)c, logn)] = make_double2(re, im);
     }
     __syncthreads();
@@ -314,18 +325,20 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
         const double2 *x = srow + (size_t)(rb * pb_n + pb) * n;
         const double2 z = x[b], zc = x[(n - b) % n];
         const int plane = 2 * (pair0 + pb);
-        const int64_t o = (int64_t)plane * ps + (int64_t)b * n + 2 * blockIdx.x + rb;
+        const int64_t o = (int64_t)plane * ps + (int64_t)b * n + (rho0 + rb - hs + n) % n;      // adjacent for nsrc >= 4
         T[o] = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
         if (plane + 1 < nf) T[o + ps] = make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
     }
 }
 
-// column pass: block = row b of T for planes [PB blockIdx.y, ...) -> Yh[((a + h) % n (h + 1) + b) nf + plane]
+// column pass: block = row b of T for planes [PB blockIdx.y, ...) -> Yh[((a + h) % n (h + 1) + b) nf + plane];
+// entries r' of a row of T outside the source rows (centred coordinate not in [-nsrc/2, nsrc/2)) read as zero
 __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restrict__ T, const double2 *__restrict__ twg,
-                                                        double2 *__restrict__ Yh, int n, int logn, int nf, int PB, int tpf)
+                                                        double2 *__restrict__ Yh, int n, int logn, int nf, int PB, int tpf,
+                                                        int nsrc)
 {
     extern __shared__ double2 srow[];
-    const int h = n / 2, b = blockIdx.x;
+    const int h = n / 2, hs = nsrc / 2, b = blockIdx.x;
     const int plane0 = blockIdx.y * PB;
     const int nfft = nf - plane0 < PB ? nf - plane0 : PB;
     double2 *tw = srow + (size_t)PB * n;
@@ -333,7 +346,10 @@ __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restric
     const int64_t ps = (int64_t)(h + 1) * n;
     for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
         const int r = idx % n, pl = idx / n;
-        srow[(size_t)pl * n + bitrev((unsigned)r, logn)] = T[(int64_t)(plane0 + pl) * ps + (int64_t)b * n + r];
+        const int R = r < h ? r : r - n;
+        double2 val = make_double2(0.0, 0.0);
+        if (R >= -hs && R < hs) val = T[(int64_t)(plane0 + pl) * ps + (int64_t)b * n + r];
+        srow[(size_t)pl * n + bitrev((unsigned)r, logn)] = val;
     }
     __syncthreads();
     fft_plus_rows_r4(srow, tw, n, logn, nfft, tpf);
@@ -343,20 +359,24 @@ __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restric
     }
 }
 
-// T: [nf][n/2 + 1][n] scratch, Yh: [n][n/2 + 1][nf]
-int rfft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Yh)
+// T: [nf][n/2 + 1][n] scratch, Yh: [n][n/2 + 1][nf].  nsrc x nsrc source planes transformed at length n >= nsrc (both
+// powers of two; n = nsrc: no padding), corr_dev: per-axis pixel factors [nsrc] or null.
+int rfft2_planes_padded(const double *cube_dev, int nsrc, int n, int nf, int flip, const double *corr_dev, double2 *T,
+                        double2 *Yh)
 {
     Context &c = ctx();
     int logn = 0;
     while ((1 << logn) < n) logn++;
     PDSB_REQUIRE(n >= 2 && (1 << logn) == n && n <= 4096, "rfft2_planes: side must be a power of two in [2, 4096]");
+    PDSB_REQUIRE(nsrc >= 2 && nsrc <= n && (nsrc & (nsrc - 1)) == 0 ,
+                 "rfft2_planes: source side must be a power of two <= the transform length");
     static bool attr = false;
     if (!attr) {
         PDSB_CUDA(cudaFuncSetAttribute(rfft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         PDSB_CUDA(cudaFuncSetAttribute(rfft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    PDSB_CHECK(c.fft_tw.ensure((size_t)(n / 2 + 1) * sizeof(double2)));
+    PDSB_CHECK(c.fft_tw.ensure((size_t)(4096 / 2 + 1) * sizeof(double2)));
     if (c.fft_tw_n != n) {
         LaunchScope ls("fft_twiddle");
         fft_twiddle_kernel<<<ceil_div(n / 2, 256), 256, 0, c.stream>>>(c.fft_tw.as<double2>(), n);
@@ -377,10 +397,16 @@ int rfft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, do
     const int th0 = std::max(32, 2 * pb0 * tpf), th1 = std::max(32, pb1 * tpf);
     const size_t sm0 = ((size_t)2 * pb0 * n + n / 2) * sizeof(double2), sm1 = ((size_t)pb1 * n + n / 2) * sizeof(double2);
     LaunchScope ls("rfft2_planes");
-    rfft_rows_kernel<<<dim3(n / 2, ceil_div(npair, pb0)), th0, sm0, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip, pb0, tpf);
-    rfft_cols_kernel<<<dim3(n / 2 + 1, ceil_div(nf, pb1)), th1, sm1, c.stream>>>(T, tw, Yh, n, logn, nf, pb1, tpf);
+    rfft_rows_kernel<<<dim3(nsrc / 2, ceil_div(npair, pb0)), th0, sm0, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip, pb0,
+                                                                                   tpf, nsrc, corr_dev);
+    rfft_cols_kernel<<<dim3(n / 2 + 1, ceil_div(nf, pb1)), th1, sm1, c.stream>>>(T, tw, Yh, n, logn, nf, pb1, tpf, nsrc);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
+}
+
+int rfft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Yh)
+{
+    return rfft2_planes_padded(cube_dev, n, n, nf, flip, nullptr, T, Yh);
 }
 
 }  // namespace pdsb
