@@ -55,7 +55,9 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libpdsb")
-    subprocess.check_call([nvcc(), "-shared", "-cudart", "static", "-o", OUT] + objs)
+    tmp = OUT + ".tmp%d" % os.getpid()                  # link beside the target, then rename: a reader (or a snapshot
+    subprocess.check_call([nvcc(), "-shared", "-cudart", "static", "-o", tmp] + objs)      # of the tree) never sees half a file
+    os.replace(tmp, OUT)
     return OUT
 
 
