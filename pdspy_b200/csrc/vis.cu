@@ -392,9 +392,9 @@ __device__ __forceinline__ NufftPoint nufft_point(const NufftArgs &P, int64_t k)
     for (int t = 0; t < NUFFT_W; t++) {
         q.wx[t] = nufft_psi(a - (kx0 + t));
         q.wy[t] = nufft_psi(b - (ky0 + t));
-        long long kx = (long long)kx0 + t, ky = (long long)ky0 + t;
-        int kxm = (int)(((kx % N) + N) % N);
-        const int kyp = (int)(((ky % N) + N) % N), kyn = (N - kyp) % N;
+        // N is a power of two: mod N of a (possibly negative) index is a mask
+        int kxm = ((int)kx0 + t) & (N - 1);
+        const int kyp = ((int)ky0 + t) & (N - 1), kyn = (N - kyp) & (N - 1);
         const bool cj = kxm > h;
         if (cj) {
             kxm = N - kxm;
@@ -402,8 +402,8 @@ __device__ __forceinline__ NufftPoint nufft_point(const NufftArgs &P, int64_t k)
         }
         q.wxs[t] = cj ? -q.wx[t] : q.wx[t];
         q.colo[t] = kxm * P.nf;
-        q.rowp[t] = (int64_t)((kyp + h) % N) * (h + 1) * P.nf;
-        q.rown[t] = (int64_t)((kyn + h) % N) * (h + 1) * P.nf;
+        q.rowp[t] = (int64_t)((kyp + h) & (N - 1)) * (h + 1) * P.nf;
+        q.rown[t] = (int64_t)((kyn + h) & (N - 1)) * (h + 1) * P.nf;
     }
     sincos(kTwoPi * (uu * P.dRA + vv * P.dDec), &q.ps, &q.pc);
     return q;
@@ -495,9 +495,18 @@ __global__ void __launch_bounds__(256) nufft_chi2_kernel(const NufftArgs P, int 
 // staging - and the 64 taps of every (point, channel) are then 16-byte shared-memory reads (a half-warp = one point, its
 // lanes = the channels: 256 contiguous bytes, no bank conflicts).  Batches whose box exceeds NT_CAP cells (the sparse
 // outskirts of the uv plane) take the direct path of nufft_chi2_kernel.  L2 traffic per C3 likelihood: 33 GB -> ~6 GB.
-constexpr int NT_PTS = 32;
+#ifndef NT_PTS_N
+#define NT_PTS_N 32
+#endif
+#ifndef NT_CAP_N
+#define NT_CAP_N 400
+#endif
+#ifndef NT_MINB
+#define NT_MINB 2
+#endif
+constexpr int NT_PTS = NT_PTS_N;
 constexpr int NT_CG = 16;
-constexpr int NT_CAP = 400;
+constexpr int NT_CAP = NT_CAP_N;
 struct NtPoint {
     double wx[NUFFT_W], wy[NUFFT_W];
     double pc, ps;
@@ -506,7 +515,7 @@ struct NtPoint {
 };
 constexpr size_t NT_SMEM = (size_t)NT_CAP * NT_CG * sizeof(double2) + NT_PTS * sizeof(NtPoint) + 64;
 
-__global__ void __launch_bounds__(256, 2) nufft_chi2_tiled_kernel(const NufftArgs P, const double *__restrict__ dre,
+__global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const NufftArgs P, const double *__restrict__ dre,
                                                                   const double *__restrict__ dim,
                                                                   const double *__restrict__ w,
                                                                   double *__restrict__ blockpart)
@@ -525,8 +534,8 @@ __global__ void __launch_bounds__(256, 2) nufft_chi2_tiled_kernel(const NufftArg
         // ---- per-point part: thread = (point, tap) ----
         if (tid < 4) box[tid] = (tid & 1) ? INT_MIN : INT_MAX;
         __syncthreads();
-        {
-            const int p = tid >> 3, t = tid & 7;
+        for (int p = tid >> 3; p < NT_PTS; p += 32) {
+            const int t = tid & 7;
             const int64_t kk = b * NT_PTS + p;
             NtPoint &q = pts[p];
             if (kk < P.nuvh) {
@@ -556,24 +565,35 @@ __global__ void __launch_bounds__(256, 2) nufft_chi2_tiled_kernel(const NufftArg
         const bool staged = (int64_t)bw * bh <= NT_CAP;
         for (int cg0 = 0; cg0 < P.nf; cg0 += NT_CG) {
             if (staged) {
-                // ---- stage the box: thread = (cell, channel), channel fastest ----
-                for (int idx = tid; idx < bw * bh * NT_CG; idx += 256) {
-                    const int cell = idx / NT_CG, ch = idx % NT_CG;
-                    const int cy = cell / bw, cx = cell - cy * bw;
-                    int kxm = ((minx + cx) % N + N) % N;
-                    int ky = miny + cy;
-                    const bool cj = kxm > h;
-                    if (cj) {
-                        kxm = N - kxm;
-                        ky = -ky;
+                // ---- stage the box: thread = (cell, channel), channel fastest; four loads in flight per thread
+                // (issue is in order: a store right behind its load would serialise the round trips) ----
+                const int ncell16 = bw * bh * NT_CG;
+                const float inv_bw = 1.0f / (float)bw;
+                for (int idx0 = tid; idx0 < ncell16; idx0 += 4 * 256) {
+                    double2 val[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int idx = idx0 + j * 256;
+                        val[j] = make_double2(0.0, 0.0);
+                        if (idx >= ncell16) continue;
+                        const int cell = idx / NT_CG, ch = idx % NT_CG;
+                        const int cy = (int)(((float)cell + 0.5f) * inv_bw), cx = cell - cy * bw;      // cell < 400: exact
+                        int kxm = (minx + cx) & (N - 1);                 // N is a power of two
+                        int ky = miny + cy;
+                        const bool cj = kxm > h;
+                        if (cj) {
+                            kxm = N - kxm;
+                            ky = -ky;
+                        }
+                        const int row = ((ky & (N - 1)) + h) & (N - 1);
+                        if (cg0 + ch < P.nf) {
+                            val[j] = P.Yh[((int64_t)row * (h + 1) + kxm) * P.nf + cg0 + ch];
+                            if (cj) val[j].y = -val[j].y;
+                        }
                     }
-                    const int row = (((ky % N) + N) % N + h) % N;
-                    double2 val = make_double2(0.0, 0.0);
-                    if (cg0 + ch < P.nf) {
-                        val = P.Yh[((int64_t)row * (h + 1) + kxm) * P.nf + cg0 + ch];
-                        if (cj) val.y = -val.y;
-                    }
-                    patch[idx] = val;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (idx0 + j * 256 < ncell16) patch[idx0 + j * 256] = val[j];
                 }
                 __syncthreads();
             }
@@ -583,6 +603,15 @@ __global__ void __launch_bounds__(256, 2) nufft_chi2_tiled_kernel(const NufftArg
                 const int p = it * (256 / NT_CG) + tid / NT_CG, ch = tid % NT_CG, i = cg0 + ch;
                 const NtPoint &q = pts[p];
                 if (q.k < 0 || i >= P.nf) continue;
+                // the data of this (point, channel) and of its Hermitian twin: on their way while the taps are summed
+                const int64_t idx = q.k * P.nf + i, id2 = idx + P.nuvh * P.nf;
+                const double w0 = __ldcs(w + idx), a0 = __ldcs(dre + idx), b0 = __ldcs(dim + idx);
+                double w1 = 0.0, a1 = 0.0, b1 = 0.0;
+                if (twin) {
+                    w1 = __ldcs(w + id2);
+                    a1 = __ldcs(dre + id2);
+                    b1 = __ldcs(dim + id2);
+                }
                 double2 m;
                 if (staged) {
                     double wx[NUFFT_W];
@@ -606,22 +635,37 @@ __global__ void __launch_bounds__(256, 2) nufft_chi2_tiled_kernel(const NufftArg
                     }
                     m = make_double2(s_r * q.pc + s_i * q.ps, s_i * q.pc - s_r * q.ps);
                 } else {
-                    const NufftPoint qq = nufft_point(P, q.k);
-                    m = nufft_channel(P, qq, i);
+                    // the box of this batch does not fit: the same 64 taps straight from the spectrum (weights from pts)
+                    double s_r = 0.0, s_i = 0.0;
+#pragma unroll 1
+                    for (int ty = 0; ty < NUFFT_W; ty++) {
+                        const int kyp = (q.ky0 + ty) & (N - 1), kyn = (N - kyp) & (N - 1);
+                        const double2 *rp = P.Yh + (int64_t)((kyp + h) & (N - 1)) * (h + 1) * P.nf + i;
+                        const double2 *rn = P.Yh + (int64_t)((kyn + h) & (N - 1)) * (h + 1) * P.nf + i;
+                        double tr = 0.0, ti = 0.0;
+#pragma unroll
+                        for (int tx = 0; tx < NUFFT_W; tx++) {
+                            int kxm = (q.kx0 + tx) & (N - 1);
+                            const bool cj = kxm > h;
+                            if (cj) kxm = N - kxm;
+                            const double2 y = (cj ? rn : rp)[(int64_t)kxm * P.nf];
+                            const double wv = q.wx[tx];
+                            tr = fma(wv, y.x, tr);
+                            ti = fma(cj ? -wv : wv, y.y, ti);
+                        }
+                        const double wyv = q.wy[ty];
+                        s_r = fma(wyv, tr, s_r);
+                        s_i = fma(wyv, ti, s_i);
+                    }
+                    m = make_double2(s_r * q.pc + s_i * q.ps, s_i * q.pc - s_r * q.ps);
                 }
-                const int64_t idx = q.k * P.nf + i;
-                const double w0 = __ldcs(w + idx), a0 = __ldcs(dre + idx), b0 = __ldcs(dim + idx);
                 double a = a0 - m.x, bq = b0 - m.y;
                 sr += a * a * w0;
                 si += bq * bq * w0;
-                if (twin) {
-                    const int64_t id2 = idx + P.nuvh * P.nf;
-                    const double w1 = __ldcs(w + id2), a1 = __ldcs(dre + id2), b1 = __ldcs(dim + id2);
-                    a = a1 - m.x;
-                    bq = b1 + m.y;                       // the twin's model is the conjugate
-                    sr += a * a * w1;
-                    si += bq * bq * w1;
-                }
+                a = a1 - m.x;
+                bq = b1 + m.y;                           // the twin's model is the conjugate (w1 = 0 without a twin)
+                sr += a * a * w1;
+                si += bq * bq * w1;
             }
             __syncthreads();                             // the patch (and pts / box at the last group) are free again
         }
@@ -1277,7 +1321,7 @@ int pdsb_loglike_nufft(pdsb_dataset *ds, const double *image, int n, int nf, int
     const int gs = fft_group_size(nf);
     int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 16, (ds->nuvh * gs + 255) / 256);
     const bool tiled = nf >= NT_CG && !getenv("PDSB_NUFFT_DIRECT");            // (tuning switch: the untiled sampler)
-    if (tiled) nb = (int)std::min<int64_t>((int64_t)c.sm_count * 2, (ds->nuvh + NT_PTS - 1) / NT_PTS);       // persistent
+    if (tiled) nb = (int)std::min<int64_t>((int64_t)c.sm_count * NT_MINB, (ds->nuvh + NT_PTS - 1) / NT_PTS);       // persistent
     PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * 2 * sizeof(double)));
     {
         LaunchScope ls("nufft_chi2");
