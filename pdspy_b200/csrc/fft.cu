@@ -303,9 +303,10 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
     const int rho0 = 2 * blockIdx.x;
     double2 *tw = srow + (size_t)2 * PB * n;
     for (int j = threadIdx.x; j < h; j += blockDim.x) tw[j] = twg[j];
-    // loads: pair fastest (adjacent doubles of the cube), then column, then row
-    for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
-        const int pb = idx % pb_n, c = (idx / pb_n) % n, rb = idx / (pb_n * n);
+    // loads: pair fastest (adjacent doubles of the cube), then column, then row.  n is a power of two; the pair count of
+    // a block is 1 .. 4: a thread keeps its pair and strides over the columns (no division in the loop) when the
+    // block size allows it
+    auto load_one = [&](int rb, int pb, int c) {
         const int rho = rho0 + rb, gamma = (c < h ? c : c - n) + hs;
         double re = 0.0, im = 0.0;
         if (gamma >= 0 && gamma < nsrc) {
@@ -315,20 +316,29 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
             if (2 * (pair0 + pb) + 1 < nf) im = cube[src + 1] * f;
         }
         srow[(size_t)(rb * pb_n + pb) * n + bitrev((unsigned)c, logn)] = make_double2(re, im);
+    };
+    if (blockDim.x % pb_n == 0) {
+        const int pb = threadIdx.x % pb_n, cstep = blockDim.x / pb_n;
+        for (int rb = 0; rb < 2; rb++)
+            for (int c = threadIdx.x / pb_n; c < n; c += cstep) load_one(rb, pb, c);
+    } else {
+        for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x)
+            load_one(idx / (pb_n * n), idx % pb_n, (idx / pb_n) & (n - 1));
     }
     __syncthreads();
     fft_plus_rows_r4(srow, tw, n, logn, nfft, tpf);
     // separate the two planes of every pair; stores: row fastest (adjacent double2 of T), then b, then pair
     const int64_t ps = (int64_t)(h + 1) * n;                            // plane stride of T
-    for (int idx = threadIdx.x; idx < 2 * (h + 1) * pb_n; idx += blockDim.x) {
-        const int rb = idx & 1, b = (idx >> 1) % (h + 1), pb = (idx >> 1) / (h + 1);
-        const double2 *x = srow + (size_t)(rb * pb_n + pb) * n;
-        const double2 z = x[b], zc = x[(n - b) % n];
-        const int plane = 2 * (pair0 + pb);
-        const int64_t o = (int64_t)plane * ps + (int64_t)b * n + (rho0 + rb - hs + n) % n;      // adjacent for nsrc >= 4
-        T[o] = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
-        if (plane + 1 < nf) T[o + ps] = make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
-    }
+    for (int pb = 0; pb < pb_n; pb++)
+        for (int j = threadIdx.x; j < 2 * (h + 1); j += blockDim.x) {
+            const int rb = j & 1, b = j >> 1;
+            const double2 *x = srow + (size_t)(rb * pb_n + pb) * n;
+            const double2 z = x[b], zc = x[(n - b) & (n - 1)];
+            const int plane = 2 * (pair0 + pb);
+            const int64_t o = (int64_t)plane * ps + (int64_t)b * n + ((rho0 + rb - hs + n) & (n - 1));      // adjacent for nsrc >= 4
+            T[o] = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
+            if (plane + 1 < nf) T[o + ps] = make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
+        }
 }
 
 // column pass: block = row b of T for planes [PB blockIdx.y, ...) -> Yh[((a + h) % n (h + 1) + b) nf + plane];
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restric
     for (int j = threadIdx.x; j < h; j += blockDim.x) tw[j] = twg[j];
     const int64_t ps = (int64_t)(h + 1) * n;
     for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
-        const int r = idx % n, pl = idx / n;
+        const int r = idx & (n - 1), pl = idx >> logn;
         const int R = r < h ? r : r - n;
         double2 val = make_double2(0.0, 0.0);
         if (R >= -hs && R < hs) val = T[(int64_t)(plane0 + pl) * ps + (int64_t)b * n + r];
@@ -353,9 +363,15 @@ __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restric
     }
     __syncthreads();
     fft_plus_rows_r4(srow, tw, n, logn, nfft, tpf);
-    for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
-        const int pl = idx % nfft, a = idx / nfft;
-        Yh[((int64_t)((a + h) % n) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * n + a];
+    if (blockDim.x % nfft == 0) {                        // plane fastest (contiguous channels), no division in the loop
+        const int pl = threadIdx.x % nfft, astep = blockDim.x / nfft;
+        for (int a = threadIdx.x / nfft; a < n; a += astep)
+            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * n + a];
+    } else {
+        for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
+            const int pl = idx % nfft, a = idx / nfft;
+            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * n + a];
+        }
     }
 }
 
