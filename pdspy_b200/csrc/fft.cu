@@ -241,10 +241,17 @@ __global__ void __launch_bounds__(256) fft_twiddle_kernel(double2 *__restrict__ 
 
 // in-place transforms of nfft rows of length n (bit-reversed input) held at w + f * n, kernel e^{+2 pi i jk/n};
 // tpf threads per row, the block's threads are [row][tpf]
+// Shared-memory layout of one transform: element i at slot fft_pad(i) = i + i / 4 (row length fft_padlen(n)).  The
+// radix-4 butterflies of the first stages touch 4 consecutive / 4-strided elements per thread: without the padding a
+// quarter-warp's 16-byte accesses fall on 2 - 4 of the 8 bank groups (4-way / 2-way conflicts), with it they spread
+// over all 8; unit-stride accesses pay one extra wavefront in four.
+__device__ __forceinline__ int fft_pad(int i) { return i + (i >> 2); }
+__host__ __device__ __forceinline__ int fft_padlen(int n) { return n + (n >> 2); }
+
 __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, int n, int logn, int nfft, int tpf)
 {
     const int f = threadIdx.x / tpf, tl = threadIdx.x % tpf;
-    double2 *x = w + (size_t)f * n;
+    double2 *x = w + (size_t)f * fft_padlen(n);
     int s = 1;
     for (; s + 1 <= logn; s += 2) {
         const int half = 1 << (s - 1), ts1 = n >> s, ts2 = n >> (s + 1);
@@ -252,7 +259,8 @@ __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, 
             for (int idx = tl; idx < n / 4; idx += tpf) {
                 const int k = idx & (half - 1);
                 const int j = ((idx >> (s - 1)) << (s + 1)) + k;
-                double2 a0 = x[j], a1 = x[j + half], a2 = x[j + 2 * half], a3 = x[j + 3 * half];
+                const int p0 = fft_pad(j), p1 = fft_pad(j + half), p2 = fft_pad(j + 2 * half), p3 = fft_pad(j + 3 * half);
+                double2 a0 = x[p0], a1 = x[p1], a2 = x[p2], a3 = x[p3];
                 const double2 w1 = tw[k * ts1];
                 double2 t = cmul(w1, a1);
                 a1 = make_double2(a0.x - t.x, a0.y - t.y);
@@ -262,11 +270,11 @@ __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, 
                 a2 = make_double2(a2.x + t.x, a2.y + t.y);
                 const double2 w2a = tw[k * ts2], w2b = tw[(k + half) * ts2];
                 t = cmul(w2a, a2);
-                x[j] = make_double2(a0.x + t.x, a0.y + t.y);
-                x[j + 2 * half] = make_double2(a0.x - t.x, a0.y - t.y);
+                x[p0] = make_double2(a0.x + t.x, a0.y + t.y);
+                x[p2] = make_double2(a0.x - t.x, a0.y - t.y);
                 t = cmul(w2b, a3);
-                x[j + half] = make_double2(a1.x + t.x, a1.y + t.y);
-                x[j + 3 * half] = make_double2(a1.x - t.x, a1.y - t.y);
+                x[p1] = make_double2(a1.x + t.x, a1.y + t.y);
+                x[p3] = make_double2(a1.x - t.x, a1.y - t.y);
             }
         __syncthreads();
     }
@@ -276,9 +284,10 @@ __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, 
             for (int idx = tl; idx < n / 2; idx += tpf) {
                 const int k = idx & (half - 1);
                 const int j = ((idx >> (s - 1)) << s) + k;
-                const double2 t = cmul(tw[k * tstep], x[j + half]), a = x[j];
-                x[j] = make_double2(a.x + t.x, a.y + t.y);
-                x[j + half] = make_double2(a.x - t.x, a.y - t.y);
+                const int p0 = fft_pad(j), p1 = fft_pad(j + half);
+                const double2 t = cmul(tw[k * tstep], x[p1]), a = x[p0];
+                x[p0] = make_double2(a.x + t.x, a.y + t.y);
+                x[p1] = make_double2(a.x - t.x, a.y - t.y);
             }
         __syncthreads();
     }
@@ -301,12 +310,16 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
     const int pb_n = npair - pair0 < PB ? npair - pair0 : PB;          // pairs this block really has
     const int nfft = 2 * pb_n;                                          // [row 0..1][pair]
     const int rho0 = 2 * blockIdx.x;
-    double2 *tw = srow + (size_t)2 * PB * n;
+    const int npad = fft_padlen(n);
+    double2 *tw = srow + (size_t)2 * PB * npad;
     for (int j = threadIdx.x; j < h; j += blockDim.x) tw[j] = twg[j];
     // loads: pair fastest (adjacent doubles of the cube), then column, then row.  n is a power of two; the pair count of
     // a block is 1 .. 4: a thread keeps its pair and strides over the columns (no division in the loop) when the
     // block size allows it
-    auto load_one = [&](int rb, int pb, int c) {
+    // A thread that stores slot j of the (bit-reversed) work row fetches column bitrev(j): the stores are linear in
+    // shared memory, and the column order of the fetches is free (columns are nf * 8 bytes apart in the cube anyway).
+    auto load_one = [&](int rb, int pb, int j) {
+        const int c = (int)bitrev((unsigned)j, logn);
         const int rho = rho0 + rb, gamma = (c < h ? c : c - n) + hs;
         double re = 0.0, im = 0.0;
         if (gamma >= 0 && gamma < nsrc) {
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
             re = cube[src] * f;
             if (2 * (pair0 + pb) + 1 < nf) im = cube[src + 1] * f;
         }
-        srow[(size_t)(rb * pb_n + pb) * n + bitrev((unsigned)c, logn)] = make_double2(re, im);
+        srow[(size_t)(rb * pb_n + pb) * npad + fft_pad(j)] = make_double2(re, im);
     };
     if (blockDim.x % pb_n == 0) {
         const int pb = threadIdx.x % pb_n, cstep = blockDim.x / pb_n;
@@ -332,8 +345,8 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
     for (int pb = 0; pb < pb_n; pb++)
         for (int j = threadIdx.x; j < 2 * (h + 1); j += blockDim.x) {
             const int rb = j & 1, b = j >> 1;
-            const double2 *x = srow + (size_t)(rb * pb_n + pb) * n;
-            const double2 z = x[b], zc = x[(n - b) & (n - 1)];
+            const double2 *x = srow + (size_t)(rb * pb_n + pb) * npad;
+            const double2 z = x[fft_pad(b)], zc = x[fft_pad((n - b) & (n - 1))];
             const int plane = 2 * (pair0 + pb);
             const int64_t o = (int64_t)plane * ps + (int64_t)b * n + ((rho0 + rb - hs + n) & (n - 1));      // adjacent for nsrc >= 4
             T[o] = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
@@ -351,26 +364,30 @@ __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restric
     const int h = n / 2, hs = nsrc / 2, b = blockIdx.x;
     const int plane0 = blockIdx.y * PB;
     const int nfft = nf - plane0 < PB ? nf - plane0 : PB;
-    double2 *tw = srow + (size_t)PB * n;
+    const int npad = fft_padlen(n);
+    double2 *tw = srow + (size_t)PB * npad;
     for (int j = threadIdx.x; j < h; j += blockDim.x) tw[j] = twg[j];
     const int64_t ps = (int64_t)(h + 1) * n;
+    // slot j of the work row <- entry bitrev(j) of the row of T (linear shared-memory stores; the two halves of a
+    // 32-byte sector of T are fetched by two threads of the same block)
     for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
-        const int r = idx & (n - 1), pl = idx >> logn;
+        const int j = idx & (n - 1), pl = idx >> logn;
+        const int r = (int)bitrev((unsigned)j, logn);
         const int R = r < h ? r : r - n;
         double2 val = make_double2(0.0, 0.0);
         if (R >= -hs && R < hs) val = T[(int64_t)(plane0 + pl) * ps + (int64_t)b * n + r];
-        srow[(size_t)pl * n + bitrev((unsigned)r, logn)] = val;
+        srow[(size_t)pl * npad + fft_pad(j)] = val;
     }
     __syncthreads();
     fft_plus_rows_r4(srow, tw, n, logn, nfft, tpf);
     if (blockDim.x % nfft == 0) {                        // plane fastest (contiguous channels), no division in the loop
         const int pl = threadIdx.x % nfft, astep = blockDim.x / nfft;
         for (int a = threadIdx.x / nfft; a < n; a += astep)
-            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * n + a];
+            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * npad + fft_pad(a)];
     } else {
         for (int idx = threadIdx.x; idx < nfft * n; idx += blockDim.x) {
             const int pl = idx % nfft, a = idx / nfft;
-            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * n + a];
+            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * npad + fft_pad(a)];
         }
     }
 }
@@ -406,12 +423,13 @@ int rfft2_planes_padded(const double *cube_dev, int nsrc, int n, int nf, int fli
     auto fit = [&](int per_unit, int have) {
         int pb = 512 / (per_unit * tpf);
         pb = pb < 1 ? 1 : pb > 4 ? 4 : pb;
-        while (pb > 1 && (size_t)per_unit * pb * n * sizeof(double2) > 160 * 1024) pb--;
+        while (pb > 1 && (size_t)per_unit * pb * fft_padlen(n) * sizeof(double2) > 160 * 1024) pb--;
         return pb > have ? have : pb;
     };
     const int pb0 = fit(2, npair), pb1 = fit(1, nf);
     const int th0 = std::max(32, 2 * pb0 * tpf), th1 = std::max(32, pb1 * tpf);
-    const size_t sm0 = ((size_t)2 * pb0 * n + n / 2) * sizeof(double2), sm1 = ((size_t)pb1 * n + n / 2) * sizeof(double2);
+    const size_t sm0 = ((size_t)2 * pb0 * fft_padlen(n) + n / 2) * sizeof(double2),
+                 sm1 = ((size_t)pb1 * fft_padlen(n) + n / 2) * sizeof(double2);
     LaunchScope ls("rfft2_planes");
     rfft_rows_kernel<<<dim3(nsrc / 2, ceil_div(npair, pb0)), th0, sm0, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip, pb0,
                                                                                    tpf, nsrc, corr_dev);
