@@ -524,7 +524,8 @@ def galario_fft_leg(env, cfg, steps, handles, nufft=False):
     entry = L.pdsb_loglike_nufft if nufft else L.pdsb_loglike_fft
 
     def step(image, kind):
-        _lib.check(entry(like.ds.handle, _lib.ptr(image), n, nf, kind, float(dxy), float(dra), float(ddec),
+        size = (n, n) if nufft else (n,)
+        _lib.check(entry(like.ds.handle, _lib.ptr(image), *size, nf, kind, float(dxy), float(dra), float(ddec),
                          _lib.ptr(fft_out)))
         return float(fft_out[3])
     ms, _, _, _, _, _ = timed_device_steps(env, lambda: step(dcube, _lib.DEVICE), steps, 2)

@@ -153,10 +153,11 @@ int pdsb_loglike_fft(pdsb_dataset *ds, const double *image, int n, int nf, int i
  * type-2 non-uniform FFT: image divided by the transform of an 8-point "exponential of semicircle" kernel, zero-padded
  * to 2n, FFT of every channel, 8 x 8 kernel-weighted sum per (visibility, channel).  O(n^2 log n + 64 nuv) per channel
  * instead of O(n^2 nuv); 4e-8 of max|V| from the exact transform (galario's 2 x 2 bilinear scheme: 1e-3..4e-2).
- * Square images, side a power of two in [4, 2048].  Arguments and outputs as the two entry points above. */
-int pdsb_sample_image_nufft(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy,
+ * Image [ny, nx, nf] with even sides <= 2048 (any even size, rectangular included: the image is embedded in the
+ * power-of-two grid about its centre pixel (ny/2, nx/2)); other arguments and outputs as the two entry points above. */
+int pdsb_sample_image_nufft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
                             double dRA, double dDec, double *out_real, double *out_imag, int out_kind);
-int pdsb_loglike_nufft(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy,
+int pdsb_loglike_nufft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
                        double dRA, double dDec, double *out);
 /* Asynchronous variant for multi-GPU runs: chi2 per channel is left in DEVICE memory
  * (chi2_dev[nf]) on the library stream, ready for an NCCL all-reduce over uv shards; no host

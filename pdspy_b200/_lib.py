@@ -81,8 +81,8 @@ SIGNATURES = {
     "pdsb_set_grid_reweight": [_P, _c_i64, _P, _c_int],
     "pdsb_sample_image_fft": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _P, _c_int],
     "pdsb_loglike_fft": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P],
-    "pdsb_sample_image_nufft": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _P, _c_int],
-    "pdsb_loglike_nufft": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P],
+    "pdsb_sample_image_nufft": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P, _P, _c_int],
+    "pdsb_loglike_nufft": [_P, _P, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_dbl, _P],
     "pdsb_regrid_linear": [_P, _c_i64, _P, _P, _c_i64, _c_int, _c_dbl, _c_int, _P],
     "pdsb_channel_postprocess": [_P, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "pdsb_channel_postprocess_scaled": [_P, _c_i64, _c_int, _c_int, _c_int, _c_int, _P, _c_int, _P],

@@ -106,7 +106,7 @@ size_t trift_record_bytes();
 // channel-fastest output (used by the galario-algorithm path of vis.cu)
 int fft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Y);
 int rfft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Yh);
-int rfft2_planes_padded(const double *cube_dev, int nsrc, int n, int nf, int flip, const double *corr_dev, double2 *T,
-                        double2 *Yh);
+int rfft2_planes_padded(const double *cube_dev, int nsy, int nsx, int n, int nf, int flip, const double *corr_y,
+                        const double *corr_x, double2 *T, double2 *Yh);
 
 }  // namespace pdsb

@@ -295,17 +295,18 @@ __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, 
 
 // row pass: block = rows (rho, rho + 1), rho = 2 blockIdx.x, of the (row-flipped) source planes x plane pairs
 // [PB blockIdx.y, ...) -> T[plane][b][r'], b <= n/2  (T: [nf][n/2 + 1][n]).
-// The transform length n may exceed the source side nsrc (zero padding for the NUFFT path, nsrc = n otherwise):
-// the source pixel with centred coordinates (R, C) = (rho - nsrc/2, gamma - nsrc/2) sits at (R mod n, C mod n),
+// The transform length n may exceed the source sides nsy x nsx (zero padding for the NUFFT path, nsy = nsx = n otherwise):
+// the source pixel with centred coordinates (R, C) = (rho - nsy/2, gamma - nsx/2) sits at (R mod n, C mod n),
 // i.e. the image centre is the origin of the transform (the ifftshift of the unpadded case); corr (may be null)
 // multiplies pixel (rho, gamma) by corr[rho] corr[gamma] (the NUFFT's deapodisation).  Rows r' that hold no source row
 // are never written: the column pass knows they are zero.
 __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict__ cube, const double2 *__restrict__ twg,
                                                         double2 *__restrict__ T, int n, int logn, int nf, int flip,
-                                                        int PB, int tpf, int nsrc, const double *__restrict__ corr)
+                                                        int PB, int tpf, int nsy, int nsx, const double *__restrict__ corr_y,
+                                                        const double *__restrict__ corr_x)
 {
     extern __shared__ double2 srow[];
-    const int h = n / 2, hs = nsrc / 2, npair = (nf + 1) / 2;
+    const int h = n / 2, hsy = nsy / 2, hsx = nsx / 2, npair = (nf + 1) / 2;
     const int pair0 = blockIdx.y * PB;
     const int pb_n = npair - pair0 < PB ? npair - pair0 : PB;          // pairs this block really has
     const int nfft = 2 * pb_n;                                          // [row 0..1][pair]
@@ -320,11 +321,11 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
     // shared memory, and the column order of the fetches is free (columns are nf * 8 bytes apart in the cube anyway).
     auto load_one = [&](int rb, int pb, int j) {
         const int c = (int)bitrev((unsigned)j, logn);
-        const int rho = rho0 + rb, gamma = (c < h ? c : c - n) + hs;
+        const int rho = rho0 + rb, gamma = (c < h ? c : c - n) + hsx;
         double re = 0.0, im = 0.0;
-        if (gamma >= 0 && gamma < nsrc) {
-            const int64_t src = ((int64_t)(flip ? nsrc - 1 - rho : rho) * nsrc + gamma) * nf + 2 * (pair0 + pb);
-            const double f = corr ? corr[rho] * corr[gamma] : 1.0;
+        if (gamma >= 0 && gamma < nsx && rho < nsy) {
+            const int64_t src = ((int64_t)(flip ? nsy - 1 - rho : rho) * nsx + gamma) * nf + 2 * (pair0 + pb);
+            const double f = corr_y ? corr_y[rho] * corr_x[gamma] : 1.0;
             re = cube[src] * f;
             if (2 * (pair0 + pb) + 1 < nf) im = cube[src + 1] * f;
         }
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
             const double2 *x = srow + (size_t)(rb * pb_n + pb) * npad;
             const double2 z = x[fft_pad(b)], zc = x[fft_pad((n - b) & (n - 1))];
             const int plane = 2 * (pair0 + pb);
-            const int64_t o = (int64_t)plane * ps + (int64_t)b * n + ((rho0 + rb - hs + n) & (n - 1));      // adjacent for nsrc >= 4
+            const int64_t o = (int64_t)plane * ps + (int64_t)b * n + ((rho0 + rb - hsy + n) & (n - 1));      // adjacent for even nsy / 2
             T[o] = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
             if (plane + 1 < nf) T[o + ps] = make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
         }
@@ -358,10 +359,10 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
 // entries r' of a row of T outside the source rows (centred coordinate not in [-nsrc/2, nsrc/2)) read as zero
 __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restrict__ T, const double2 *__restrict__ twg,
                                                         double2 *__restrict__ Yh, int n, int logn, int nf, int PB, int tpf,
-                                                        int nsrc)
+                                                        int nsy)
 {
     extern __shared__ double2 srow[];
-    const int h = n / 2, hs = nsrc / 2, b = blockIdx.x;
+    const int h = n / 2, hs = nsy / 2, b = blockIdx.x;
     const int plane0 = blockIdx.y * PB;
     const int nfft = nf - plane0 < PB ? nf - plane0 : PB;
     const int npad = fft_padlen(n);
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restric
         const int r = (int)bitrev((unsigned)j, logn);
         const int R = r < h ? r : r - n;
         double2 val = make_double2(0.0, 0.0);
-        if (R >= -hs && R < hs) val = T[(int64_t)(plane0 + pl) * ps + (int64_t)b * n + r];
+        if (R >= -hs && R < nsy - hs) val = T[(int64_t)(plane0 + pl) * ps + (int64_t)b * n + r];
         srow[(size_t)pl * npad + fft_pad(j)] = val;
     }
     __syncthreads();
@@ -392,17 +393,18 @@ __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restric
     }
 }
 
-// T: [nf][n/2 + 1][n] scratch, Yh: [n][n/2 + 1][nf].  nsrc x nsrc source planes transformed at length n >= nsrc (both
-// powers of two; n = nsrc: no padding), corr_dev: per-axis pixel factors [nsrc] or null.
-int rfft2_planes_padded(const double *cube_dev, int nsrc, int n, int nf, int flip, const double *corr_dev, double2 *T,
-                        double2 *Yh)
+// T: [nf][n/2 + 1][n] scratch, Yh: [n][n/2 + 1][nf].  nsy x nsx source planes (even sides) transformed at length
+// n >= max(nsy, nsx), a power of two (n = nsy = nsx: no padding); corr_y [nsy], corr_x [nsx]: per-axis pixel factors, or null.
+int rfft2_planes_padded(const double *cube_dev, int nsy, int nsx, int n, int nf, int flip, const double *corr_y,
+                        const double *corr_x, double2 *T, double2 *Yh)
 {
     Context &c = ctx();
     int logn = 0;
     while ((1 << logn) < n) logn++;
     PDSB_REQUIRE(n >= 2 && (1 << logn) == n && n <= 4096, "rfft2_planes: side must be a power of two in [2, 4096]");
-    PDSB_REQUIRE(nsrc >= 2 && nsrc <= n && (nsrc & (nsrc - 1)) == 0 ,
-                 "rfft2_planes: source side must be a power of two <= the transform length");
+    PDSB_REQUIRE(nsy >= 2 && nsx >= 2 && nsy <= n && nsx <= n && nsy % 2 == 0 && nsx % 2 == 0,
+                 "rfft2_planes: source sides must be even and <= the transform length");
+    PDSB_REQUIRE((corr_y == nullptr) == (corr_x == nullptr), "rfft2_planes: both factor tables or none");
     static bool attr = false;
     if (!attr) {
         PDSB_CUDA(cudaFuncSetAttribute(rfft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -431,16 +433,16 @@ int rfft2_planes_padded(const double *cube_dev, int nsrc, int n, int nf, int fli
     const size_t sm0 = ((size_t)2 * pb0 * fft_padlen(n) + n / 2) * sizeof(double2),
                  sm1 = ((size_t)pb1 * fft_padlen(n) + n / 2) * sizeof(double2);
     LaunchScope ls("rfft2_planes");
-    rfft_rows_kernel<<<dim3(nsrc / 2, ceil_div(npair, pb0)), th0, sm0, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip, pb0,
-                                                                                   tpf, nsrc, corr_dev);
-    rfft_cols_kernel<<<dim3(n / 2 + 1, ceil_div(nf, pb1)), th1, sm1, c.stream>>>(T, tw, Yh, n, logn, nf, pb1, tpf, nsrc);
+    rfft_rows_kernel<<<dim3(nsy / 2, ceil_div(npair, pb0)), th0, sm0, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip, pb0,
+                                                                                  tpf, nsy, nsx, corr_y, corr_x);
+    rfft_cols_kernel<<<dim3(n / 2 + 1, ceil_div(nf, pb1)), th1, sm1, c.stream>>>(T, tw, Yh, n, logn, nf, pb1, tpf, nsy);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
 
 int rfft2_planes(const double *cube_dev, int n, int nf, int flip, double2 *T, double2 *Yh)
 {
-    return rfft2_planes_padded(cube_dev, n, n, nf, flip, nullptr, T, Yh);
+    return rfft2_planes_padded(cube_dev, n, n, n, nf, flip, nullptr, nullptr, T, Yh);
 }
 
 }  // namespace pdsb

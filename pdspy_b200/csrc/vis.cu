@@ -1179,30 +1179,33 @@ int pdsb_loglike_fft(pdsb_dataset *ds, const double *image, int n, int nf, int i
 // ---- NUFFT path (code="nufft") --------------------------------------------------
 // 1 / psi_hat(X / N), X = -n/2 .. n/2 - 1: psi_hat(xi) = (w/2) Int_{-pi/2}^{pi/2} exp(beta (cos th - 1)) cos(pi w xi sin th) cos th dth
 // (z = sin th removes the square-root end points; midpoint rule, 400 nodes: 1e-13)
-static int nufft_corr_table(int n, int N, const double **dev)
+static int nufft_corr_table(int ny, int nx, int N, const double **dev_y, const double **dev_x)
 {
     Context &c = ctx();
-    PDSB_CHECK(c.nufft_corr.ensure((size_t)n * sizeof(double)));
-    if (c.nufft_corr_n != n) {
+    PDSB_CHECK(c.nufft_corr.ensure((size_t)(ny + nx) * sizeof(double)));
+    if (c.nufft_corr_n != ny * 8192 + nx || c.nufft_corr_N != N) {
         constexpr int M = 400;
         const double pi = 3.14159265358979323846;
-        std::vector<double> h((size_t)n), f(M), sn(M);
+        std::vector<double> h((size_t)(ny + nx)), f(M), sn(M);
         for (int m = 0; m < M; m++) {
             const double th = (m + 0.5) * pi / M - 0.5 * pi;
             f[m] = exp(NUFFT_BETA * (cos(th) - 1.0)) * cos(th);
             sn[m] = sin(th);
         }
-        for (int x = 0; x < n; x++) {
-            const double xi = (double)(x - n / 2) / (double)N;
+        for (int x = 0; x < ny + nx; x++) {
+            const int n = x < ny ? ny : nx, X = (x < ny ? x : x - ny) - n / 2;
+            const double xi = (double)X / (double)N;
             double acc = 0.0;
             for (int m = 0; m < M; m++) acc += f[m] * cos(pi * NUFFT_W * xi * sn[m]);
             h[x] = 1.0 / (0.5 * NUFFT_W * (pi / M) * acc);
         }
-        PDSB_CUDA(cudaMemcpyAsync(c.nufft_corr.ptr, h.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(c.nufft_corr.ptr, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));            // h goes out of scope
-        c.nufft_corr_n = n;
+        c.nufft_corr_n = ny * 8192 + nx;
+        c.nufft_corr_N = N;
     }
-    *dev = c.nufft_corr.as<double>();
+    *dev_y = c.nufft_corr.as<double>();
+    *dev_x = c.nufft_corr.as<double>() + ny;
     return PDSB_OK;
 }
 
@@ -1252,28 +1255,30 @@ static int nufft_order(pdsb_dataset *ds)
     return PDSB_OK;
 }
 
-static int run_nufft_transform(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
-                               double dDec, NufftArgs *a)
+static int run_nufft_transform(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
+                               double dRA, double dDec, NufftArgs *a)
 {
     Context &c = ctx();
     PDSB_REQUIRE(ds && image, "dataset/image");
-    PDSB_REQUIRE(n >= 4 && n <= 2048 && (n & (n - 1)) == 0, "the NUFFT path needs a square image, side a power of two in [4, 2048]");
+    PDSB_REQUIRE(ny >= 2 && nx >= 2 && ny % 2 == 0 && nx % 2 == 0 && ny <= 2048 && nx <= 2048,
+                 "the NUFFT path needs even image sides in [2, 2048] (odd sides: use the direct transform)");
     PDSB_REQUIRE(nf > 0 && dxy > 0.0, "nf/dxy");
-    const int N = 2 * n;
-    const double *img_dev = nullptr, *corr = nullptr;
-    PDSB_CHECK(to_device(image, image_kind, (size_t)n * n * nf * sizeof(double), c.img64, (const void **)&img_dev));
-    PDSB_CHECK(nufft_corr_table(n, N, &corr));
+    int N = 4;                                           // oversampled grid: a power of two >= 2 max(ny, nx)
+    while (N < 2 * std::max(ny, nx)) N *= 2;
+    const double *img_dev = nullptr, *corr_y = nullptr, *corr_x = nullptr;
+    PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
+    PDSB_CHECK(nufft_corr_table(ny, nx, N, &corr_y, &corr_x));
     const size_t nh = (size_t)N * (N / 2 + 1);
     PDSB_CHECK(c.folded.ensure(2 * nh * nf * sizeof(double2)));            // [T | Yh]
     double2 *T = c.folded.as<double2>(), *Y = T + nh * nf;
-    PDSB_CHECK(rfft2_planes_padded(img_dev, n, N, nf, 1, corr, T, Y));
+    PDSB_CHECK(rfft2_planes_padded(img_dev, ny, nx, N, nf, 1, corr_y, corr_x, T, Y));
     PDSB_REQUIRE(ds->nuvh < ((int64_t)1 << 31), "more than 2^31 unique uv points");
     PDSB_CHECK(nufft_order(ds));
     *a = NufftArgs{Y, ds->u, ds->v, ds->order, ds->nuv, ds->nuvh, N, nf, dxy, dRA, dDec};
     return PDSB_OK;
 }
 
-int pdsb_sample_image_nufft(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
+int pdsb_sample_image_nufft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy, double dRA,
                             double dDec, double *out_real, double *out_imag, int out_kind)
 {
     PDSB_CHECK(require_init());
@@ -1289,7 +1294,7 @@ int pdsb_sample_image_nufft(pdsb_dataset *ds, const double *image, int n, int nf
         oim = c.stage_b.as<double>();
     }
     NufftArgs fa;
-    PDSB_CHECK(run_nufft_transform(ds, image, n, nf, image_kind, dxy, dRA, dDec, &fa));
+    PDSB_CHECK(run_nufft_transform(ds, image, ny, nx, nf, image_kind, dxy, dRA, dDec, &fa));
     {
         LaunchScope ls("nufft_sample");
         const int gs = fft_group_size(nf);
@@ -1304,7 +1309,7 @@ int pdsb_sample_image_nufft(pdsb_dataset *ds, const double *image, int n, int nf
     return PDSB_OK;
 }
 
-int pdsb_loglike_nufft(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
+int pdsb_loglike_nufft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy, double dRA,
                        double dDec, double *out)
 {
     PDSB_CHECK(require_init());
@@ -1317,7 +1322,7 @@ int pdsb_loglike_nufft(pdsb_dataset *ds, const double *image, int n, int nf, int
         return PDSB_OK;
     }
     NufftArgs fa;
-    PDSB_CHECK(run_nufft_transform(ds, image, n, nf, image_kind, dxy, dRA, dDec, &fa));
+    PDSB_CHECK(run_nufft_transform(ds, image, ny, nx, nf, image_kind, dxy, dRA, dDec, &fa));
     const int gs = fft_group_size(nf);
     int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 16, (ds->nuvh * gs + 255) / 256);
     const bool tiled = nf >= NT_CG && !getenv("PDSB_NUFFT_DIRECT");            // (tuning switch: the untiled sampler)

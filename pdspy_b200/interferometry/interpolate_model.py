@@ -82,15 +82,15 @@ def interpolate_model(u, v, freq, model, nthreads=1, dRA=0., dDec=0.,
         dxy = (model.x[1] - model.x[0]) * arcsec
         image = _cube(model)
         ny, nx, nf = image.shape[:3]
-        if ny != nx:
-            raise ValueError("the NUFFT path needs a square image")
+        if ny % 2 or nx % 2:
+            raise ValueError("the NUFFT path needs even image sides (odd sides: code=\"galario\", the direct transform)")
         u = numpy.ascontiguousarray(u, dtype=numpy.float64)
         v = numpy.ascontiguousarray(v, dtype=numpy.float64)
         ds = dataset_for(u, v)
         if u.size > 0:
             L = _lib.lib()
             token, dre, dim_ = register_model((u.size, nf))
-            _lib.check(L.pdsb_sample_image_nufft(ds.handle, _lib.ptr(image), nx, nf, _lib.HOST, float(dxy),
+            _lib.check(L.pdsb_sample_image_nufft(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST, float(dxy),
                                                  float(dRA * arcsec), float(dDec * arcsec), _lib.ptr(dre),
                                                  _lib.ptr(dim_), _lib.DEVICE))
             return Visibilities._from_device(u, v, freq, token, (u.size, nf))
@@ -197,11 +197,11 @@ def loglike_image_nufft(data, model, dRA=0., dDec=0.):
     dxy = (model.x[1] - model.x[0]) * arcsec
     image = _cube(model)
     ny, nx, nf = image.shape[:3]
-    if ny != nx:
-        raise ValueError("the NUFFT path needs a square image")
+    if ny % 2 or nx % 2:
+        raise ValueError("the NUFFT path needs even image sides")
     ds = dataset_for(data.u, data.v, (data.real, data.imag, data.weights))
     out = numpy.empty(4)
-    _lib.check(_lib.lib().pdsb_loglike_nufft(ds.handle, _lib.ptr(image), nx, nf, _lib.HOST, float(dxy),
+    _lib.check(_lib.lib().pdsb_loglike_nufft(ds.handle, _lib.ptr(image), ny, nx, nf, _lib.HOST, float(dxy),
                                             float(dRA * arcsec), float(dDec * arcsec), _lib.ptr(out)))
     return float(out[3]), float(out[0]), float(out[1])
 

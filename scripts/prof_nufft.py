@@ -17,7 +17,7 @@ import ctypes
 for rep in range(3):
     if rep == 2:
         _lib.check(L.pdsb_profile_reset()); _lib.check(L.pdsb_profile_enable(1))
-    _lib.check(L.pdsb_loglike_nufft(ds.handle, _lib.ptr(cube), c["npix"], c["nf"], _lib.DEVICE, c["pixelsize"] * A, c["dRA"] * A,
+    _lib.check(L.pdsb_loglike_nufft(ds.handle, _lib.ptr(cube), c["npix"], c["npix"], c["nf"], _lib.DEVICE, c["pixelsize"] * A, c["dRA"] * A,
                                   c["dDec"] * A, _lib.ptr(out)))
 print("lnlike", out[3])
 _lib.check(L.pdsb_profile_enable(0))

@@ -30,10 +30,19 @@ def relerr(vis, ref):
     (256, 7, 1500, False, "disk"),
     (1024, 1, 400, True, "disk"),        # transform length 2048
     (2048, 1, 200, False, "disk"),       # transform length 4096: the largest
+    (2, 1, 30, False, "random"),         # grid of 4 cells: every tap index occurs twice
+    (300, 2, 700, True, "disk"),         # sides that are not powers of two: embedded about the centre pixel
+    (90, 3, 300, False, "random"),       # n / 2 odd: the row pair straddles the origin of the transform
+    ((96, 250), 2, 400, False, "random"),    # rectangular, both ways
+    ((250, 96), 1, 400, True, "random"),
 ])
 def test_nufft_vs_exact_oracle(gpu, n, nf, nuv, herm, kind):
     px = 0.05
-    img = synth.synth_image(n, nf, px, kind=kind)
+    if isinstance(n, tuple):
+        img = np.random.default_rng(n[0]).random((n[0], n[1], nf, 1))
+        n = max(n)
+    else:
+        img = synth.synth_image(n, nf, px, kind=kind)
     m = synth.SynthImage(img, px, synth.synth_freq(nf))
     if herm:
         u, v = synth.synth_uv(nuv, px * A)
@@ -82,14 +91,16 @@ def test_nufft_likelihood_vs_oracle_chain_and_direct_transform(gpu):
 
 
 def test_nufft_rejects_what_it_cannot_do(gpu):
-    img = synth.synth_image(48, 1, 0.05, kind="random")            # not a power of two
-    m = synth.SynthImage(img, 0.05, synth.synth_freq(1))
     u, v = synth.synth_uv(10, 0.05 * A)
-    with pytest.raises(_lib.PdsbError):
-        interpolate_model(u, v, m.freq, m, code="nufft")
-    rect = synth.SynthImage(np.random.default_rng(0).random((32, 64, 1, 1)), 0.05, synth.synth_freq(1))
-    with pytest.raises(ValueError):
-        interpolate_model(u, v, rect.freq, rect, code="nufft")
+    odd = synth.SynthImage(np.random.default_rng(0).random((33, 64, 1, 1)), 0.05, synth.synth_freq(1))
+    with pytest.raises(ValueError):                                  # odd side: the direct transform's job
+        interpolate_model(u, v, odd.freq, odd, code="nufft")
+    m = synth.SynthImage(synth.synth_image(48, 1, 0.05, kind="random"), 0.05, synth.synth_freq(1))
+    out = np.empty((10, 1))
+    with pytest.raises(_lib.PdsbError):                              # the C-ABI refuses it as well
+        from pdspy_b200.device import dataset_for
+        _lib.check(gpu.pdsb_sample_image_nufft(dataset_for(u, v).handle, _lib.ptr(np.zeros((33, 64, 1))), 33, 64, 1,
+                                               _lib.HOST, 1e-7, 0.0, 0.0, _lib.ptr(out), _lib.ptr(out.copy()), _lib.HOST))
     e = interpolate_model(np.zeros(0), np.zeros(0), m.freq, synth.SynthImage(synth.synth_image(64, 2, 0.05), 0.05,
                                                                          synth.synth_freq(2)), code="nufft")
     assert e.real.shape == (0, 2)
