@@ -88,6 +88,11 @@ def test_every_uv_point_against_the_fp64_kernel(gpu, workload):
         del vr, vi
         assert err < 1e-5, (name, err)
         assert err < 3e-6, (name, err)                 # what these kernels actually deliver
+    # the NUFFT path (an FFT-cost route to the same exact transform) on every point as well
+    v = interpolate_model(c["u"], c["v"], c["freq"], c["model"], dRA=c["dRA"], dDec=c["dDec"], code="nufft")
+    vr, vi = v.real - rr, v.imag - ri
+    err = (np.sqrt((vr * vr + vi * vi).max(axis=0)) / scale).max()
+    assert err < 3e-7, ("nufft", err)
 
 
 def _star_cube(c):
