@@ -42,9 +42,10 @@ METRIC = "pixel_visibility_pairs_per_s"
 UNIT = "pairs/s"
 FLOP_PER_PAIR = 4.0          # algorithmic: 2 FMA per (pixel, uv, channel) pair
 L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
-DFT_VARIANT = {"fp32": 0, "tcgen05": 200}
+DFT_VARIANT = {"fp32": 0, "tcgen05": 200, "nufft": 400}
 DTYPE = {"fp32": "f32 products, f64 phase seeds and accumulation",
-         "tcgen05": "f16 x2 lattice-split operands on tcgen05 (22 bits), f32 accumulate, f64 partial sums"}
+         "tcgen05": "f16 x2 lattice-split operands on tcgen05 (22 bits), f32 accumulate, f64 partial sums",
+         "nufft": "f64 (type-2 non-uniform FFT: f64 transform, 8 x 8 f64 taps per visibility and channel)"}
 
 
 def peaks():
@@ -375,7 +376,7 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
         return like(pinned.array, dxy, dra, ddec, kind=_lib.HOST, cube="sharded" if shard_upload else None)
 
     _lib.check(L.pdsb_set_dft_variant(DFT_VARIANT[dft]))
-    prefix = b"dft_tc5" if dft == "tcgen05" else b"dft_f2"
+    prefix = {"tcgen05": b"dft_tc5", "nufft": b"nufft_sample"}.get(dft, b"dft_f2")
     total_ms, k_ms, k_n, launches, clocks, ll = timed_device_steps(env, step_device, steps, warmup, prefix,
                                                                    sample_clocks=main)
     e2e_s, ll_e2e = timed_host_steps(env, step_e2e, steps)
@@ -439,6 +440,19 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
                                      "list is evaluated for one half; frac > 1 is those two algorithmic savings, "
                                      "executed_frac is the pipe utilisation",
                     "launch_ms": k_ms, "launches": k_n}
+            elif dft == "nufft":
+                hbm = pk.get("hbm_gbs", 6650.0)
+                t_ms, t_n = env.profile(b"rfft2_planes")
+                path_ms = k_ms + (t_ms / t_n if t_n else 0.0)
+                alg = float(cube.nbytes) + 24.0 * like.ds.nuv * nf
+                res["roofline"] = {
+                    "kernel": "NUFFT path: rfft2_planes_padded (deapodised, zero-padded half-spectrum FFT of every channel) + "
+                              "nufft_chi2_tiled_kernel<PART> (8 x 8 taps per unique uv point and channel from shared memory) "
+                              "+ the likelihood epilogue shared with the direct-sum kernels",
+                    "bound": "hbm", "achieved": alg / (path_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                    "frac": alg / (path_ms * 1e-3) / 1e9 / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+                    "algorithmic_bytes_note": "fp64 cube read once + real, imag, weights of this rank's shard read once",
+                    "launch_ms": path_ms, "sampler_ms": k_ms, "transform_ms": (t_ms / t_n if t_n else None), "launches": k_n}
             else:
                 # 3 fp16 MACs (hi.lo, lo.hi, hi.hi) per pixel-visibility pair actually evaluated
                 macs = 3.0 * float(n) * n * nf * like.ds.nuv_unique
@@ -458,7 +472,8 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
             res["roofline"]["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
                                                  "capture of this launch, read from profiles/traffic.json; null where "
                                                  "that (workload, kernel, N) was not captured")
-            res["roofline"]["algorithmic_bytes"] = float(n) * n * nf * 4 + like.ds.nuv_unique * 16.0 * (1 + nf)
+            res["roofline"]["algorithmic_bytes"] = (float(cube.nbytes) + 24.0 * like.ds.nuv * nf if dft == "nufft" else
+                                                    float(n) * n * nf * 4 + like.ds.nuv_unique * 16.0 * (1 + nf))
         if cpu_baseline:
             res["cpu_baseline"] = cpu_baseline_port(cfg)
     if main:
@@ -794,7 +809,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
-    ap.add_argument("--dft", default="fp32", choices=["fp32", "tcgen05"],
+    ap.add_argument("--dft", default="fp32", choices=["fp32", "tcgen05", "nufft"],
                     help="DFT kernel of value / e2e / roofline: the FP32-pipe kernel BASELINE.json's north star "
                          "prescribes (default) or the tcgen05 tensor-core kernel")
     ap.add_argument("--walkers", type=int, default=128, help="C5: total emcee walkers (sharded over ranks)")

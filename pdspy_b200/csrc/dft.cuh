@@ -92,6 +92,9 @@ int launch_fold_tc5(const double *img_dev, unsigned char *B, void *ws, int ny, i
 int tc5_auto_split(int64_t nuvh, int nf, int nx);
 int launch_dft_tc5(DftParams p, const unsigned char *B, void *ws, int ny, int nx);
 
+// NUFFT variant (vis.cu: type-2 non-uniform FFT, the exact transform at FFT cost), selected with pdsb_set_dft_variant(400)
+constexpr int DFT_VARIANT_NUFFT = 400;
+
 // fp64 reference variant (dft_f64.cu), selected with pdsb_set_dft_variant(300)
 constexpr int DFT_VARIANT_F64 = 300;
 int launch_dft_f64(const double *img_dev, int ny, int nx, int nf, const double *u, const double *v, int64_t nuvh, double dxy,

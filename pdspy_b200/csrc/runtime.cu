@@ -615,7 +615,8 @@ int pdsb_hash64(const void *host_ptr, int64_t bytes, uint64_t *out)
 int pdsb_set_dft_variant(int variant)
 {
     bool ok = variant == 0 || (variant >= 1 && variant <= dft_variant_count()) ||
-              variant == DFT_VARIANT_TC5 || variant == DFT_VARIANT_TC5 + 1 || variant == DFT_VARIANT_F64;
+              variant == DFT_VARIANT_TC5 || variant == DFT_VARIANT_TC5 + 1 || variant == DFT_VARIANT_F64 ||
+              variant == DFT_VARIANT_NUFFT;
     PDSB_REQUIRE(ok, "unknown DFT kernel variant");
     ctx().dft_variant = variant;
     return PDSB_OK;

@@ -430,7 +430,7 @@ __device__ __forceinline__ double2 nufft_channel(const NufftArgs &P, const Nufft
 
 // lane groups as in fft_sample_kernel; a group evaluates one UNIQUE uv point and writes both Hermitian halves
 __global__ void __launch_bounds__(256) nufft_sample_kernel(const NufftArgs P, int gs, double *__restrict__ out_re,
-                                                           double *__restrict__ out_im)
+                                                           double *__restrict__ out_im, double2 *__restrict__ part)
 {
     const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t kk = t / gs;
@@ -440,6 +440,10 @@ __global__ void __launch_bounds__(256) nufft_sample_kernel(const NufftArgs P, in
     const bool twin = P.nuv > P.nuvh;
     for (int i = (int)(t % gs); i < P.nf; i += gs) {
         const double2 m = nufft_channel(P, q, i);
+        if (part) {                                      // S without the phase: V = m (pc + i ps)
+            part[(size_t)i * P.nuvh + k] = make_double2(m.x * q.pc - m.y * q.ps, m.y * q.pc + m.x * q.ps);
+            continue;
+        }
         out_re[k * P.nf + i] = m.x;
         out_im[k * P.nf + i] = m.y;
         if (twin) {
@@ -515,10 +519,14 @@ struct NtPoint {
 };
 constexpr size_t NT_SMEM = (size_t)NT_CAP * NT_CG * sizeof(double2) + NT_PTS * sizeof(NtPoint) + 64;
 
+// PART: instead of the chi^2 sums, write S (without the dRA / dDec phase) as the partial sums part[channel][unique uv]
+// that the epilogues shared with the direct-sum kernels consume (run_dft with the NUFFT variant).
+template <bool PART>
 __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const NufftArgs P, const double *__restrict__ dre,
                                                                   const double *__restrict__ dim,
                                                                   const double *__restrict__ w,
-                                                                  double *__restrict__ blockpart)
+                                                                  double *__restrict__ blockpart,
+                                                                  double2 *__restrict__ part)
 {
     extern __shared__ __align__(16) unsigned char nt_smem[];
     double2 *patch = reinterpret_cast<double2 *>(nt_smem);
@@ -605,9 +613,13 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
                 if (q.k < 0 || i >= P.nf) continue;
                 // the data of this (point, channel) and of its Hermitian twin: on their way while the taps are summed
                 const int64_t idx = q.k * P.nf + i, id2 = idx + P.nuvh * P.nf;
-                const double w0 = __ldcs(w + idx), a0 = __ldcs(dre + idx), b0 = __ldcs(dim + idx);
-                double w1 = 0.0, a1 = 0.0, b1 = 0.0;
-                if (twin) {
+                double w0 = 0.0, a0 = 0.0, b0 = 0.0, w1 = 0.0, a1 = 0.0, b1 = 0.0;
+                if (!PART) {
+                    w0 = __ldcs(w + idx);
+                    a0 = __ldcs(dre + idx);
+                    b0 = __ldcs(dim + idx);
+                }
+                if (!PART && twin) {
                     w1 = __ldcs(w + id2);
                     a1 = __ldcs(dre + id2);
                     b1 = __ldcs(dim + id2);
@@ -633,7 +645,7 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
                         s_r = fma(wyv, tr, s_r);
                         s_i = fma(wyv, ti, s_i);
                     }
-                    m = make_double2(s_r * q.pc + s_i * q.ps, s_i * q.pc - s_r * q.ps);
+                    m = PART ? make_double2(s_r, s_i) : make_double2(s_r * q.pc + s_i * q.ps, s_i * q.pc - s_r * q.ps);
                 } else {
                     // the box of this batch does not fit: the same 64 taps straight from the spectrum (weights from pts)
                     double s_r = 0.0, s_i = 0.0;
@@ -657,7 +669,11 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
                         s_r = fma(wyv, tr, s_r);
                         s_i = fma(wyv, ti, s_i);
                     }
-                    m = make_double2(s_r * q.pc + s_i * q.ps, s_i * q.pc - s_r * q.ps);
+                    m = PART ? make_double2(s_r, s_i) : make_double2(s_r * q.pc + s_i * q.ps, s_i * q.pc - s_r * q.ps);
+                }
+                if (PART) {
+                    part[(size_t)i * P.nuvh + q.k] = m;
+                    continue;
                 }
                 double a = a0 - m.x, bq = b0 - m.y;
                 sr += a * a * w0;
@@ -670,6 +686,7 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
             __syncthreads();                             // the patch (and pts / box at the last group) are free again
         }
     }
+    if (PART) return;
     sr = block_sum<256>(sr, sh);
     si = block_sum<256>(si, sh);
     if (threadIdx.x == 0) {
@@ -694,6 +711,9 @@ struct DftRun {
     const double *plane_unscale = nullptr;   // tensor-core kernel: V_i *= plane_unscale[i]
 };
 
+// NUFFT variant: S(u, v) of every channel as partial sums part[channel][unique uv] (defined with the NUFFT path below)
+static int nufft_partials(pdsb_dataset *ds, const double *img_dev, int ny, int nx, int nf, double dxy, double2 *part);
+
 static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
                    DftRun *run)
 {
@@ -703,6 +723,17 @@ static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf
     PDSB_REQUIRE(dxy > 0.0, "dxy");
     const double *img_dev = nullptr;
     PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
+    // (odd or oversized images are outside the NUFFT path's domain: they take the FP32 direct sum below)
+    if (c.dft_variant == DFT_VARIANT_NUFFT && ny % 2 == 0 && nx % 2 == 0 && ny <= 2048 && nx <= 2048) {
+        // the exact transform through the 8-point non-uniform FFT; sums relative to pixel (ny/2, nx/2): no centre phase
+        PDSB_CHECK(c.partial.ensure((size_t)nf * ds->nuvh * sizeof(double2)));
+        PDSB_CHECK(nufft_partials(ds, img_dev, ny, nx, nf, dxy, c.partial.as<double2>()));
+        run->g = make_geom(ny, nx, nf, 32, dxy);
+        run->g.xcen = run->g.ycen = 0.0;
+        run->nsplit = 1;
+        run->plane_unscale = nullptr;
+        return PDSB_OK;
+    }
     if (c.dft_variant == DFT_VARIANT_F64) {
         // fp64 throughout, straight from the fp64 cube (dft_f64.cu)
         PDSB_CHECK(c.partial.ensure((size_t)nf * ds->nuvh * sizeof(double2)));
@@ -712,7 +743,7 @@ static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf
         run->plane_unscale = nullptr;
         return PDSB_OK;
     }
-    if (c.dft_variant >= DFT_VARIANT_TC5) {
+    if (c.dft_variant >= DFT_VARIANT_TC5 && c.dft_variant < DFT_VARIANT_F64) {
         // tensor-core kernel: lattice-split fp16 operands on tcgen05 (dft_tc5.cu)
         DftGeom g = make_geom(ny, nx, nf, 32, dxy);
         PDSB_CHECK(c.folded.ensure(tc5_operand_bytes(ny, nx, nf)));
@@ -1255,18 +1286,30 @@ static int nufft_order(pdsb_dataset *ds)
     return PDSB_OK;
 }
 
+static int nufft_transform_dev(pdsb_dataset *ds, const double *img_dev, int ny, int nx, int nf, double dxy, double dRA,
+                               double dDec, NufftArgs *a);
 static int run_nufft_transform(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
                                double dRA, double dDec, NufftArgs *a)
 {
     Context &c = ctx();
     PDSB_REQUIRE(ds && image, "dataset/image");
+    const double *img_dev = nullptr;
+    PDSB_REQUIRE(ny > 0 && nx > 0 && nf > 0, "image shape");
+    PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
+    return nufft_transform_dev(ds, img_dev, ny, nx, nf, dxy, dRA, dDec, a);
+}
+
+static int nufft_transform_dev(pdsb_dataset *ds, const double *img_dev, int ny, int nx, int nf, double dxy, double dRA,
+                               double dDec, NufftArgs *a)
+{
+    Context &c = ctx();
+    PDSB_REQUIRE(ds && img_dev, "dataset/image");
     PDSB_REQUIRE(ny >= 2 && nx >= 2 && ny % 2 == 0 && nx % 2 == 0 && ny <= 2048 && nx <= 2048,
                  "the NUFFT path needs even image sides in [2, 2048] (odd sides: use the direct transform)");
     PDSB_REQUIRE(nf > 0 && dxy > 0.0, "nf/dxy");
     int N = 4;                                           // oversampled grid: a power of two >= 2 max(ny, nx)
     while (N < 2 * std::max(ny, nx)) N *= 2;
-    const double *img_dev = nullptr, *corr_y = nullptr, *corr_x = nullptr;
-    PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
+    const double *corr_y = nullptr, *corr_x = nullptr;
     PDSB_CHECK(nufft_corr_table(ny, nx, N, &corr_y, &corr_x));
     const size_t nh = (size_t)N * (N / 2 + 1);
     PDSB_CHECK(c.folded.ensure(2 * nh * nf * sizeof(double2)));            // [T | Yh]
@@ -1275,6 +1318,30 @@ static int run_nufft_transform(pdsb_dataset *ds, const double *image, int ny, in
     PDSB_REQUIRE(ds->nuvh < ((int64_t)1 << 31), "more than 2^31 unique uv points");
     PDSB_CHECK(nufft_order(ds));
     *a = NufftArgs{Y, ds->u, ds->v, ds->order, ds->nuv, ds->nuvh, N, nf, dxy, dRA, dDec};
+    return PDSB_OK;
+}
+
+static int nufft_partials(pdsb_dataset *ds, const double *img_dev, int ny, int nx, int nf, double dxy, double2 *part)
+{
+    Context &c = ctx();
+    if (ds->nuvh == 0) return PDSB_OK;
+    NufftArgs fa;
+    PDSB_CHECK(nufft_transform_dev(ds, img_dev, ny, nx, nf, dxy, 0.0, 0.0, &fa));
+    LaunchScope ls("nufft_sample");
+    if (nf >= NT_CG && !getenv("PDSB_NUFFT_DIRECT")) {
+        static bool attr = false;
+        if (!attr) {
+            PDSB_CUDA(cudaFuncSetAttribute(nufft_chi2_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)NT_SMEM));
+            attr = true;
+        }
+        const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * NT_MINB, (ds->nuvh + NT_PTS - 1) / NT_PTS);
+        nufft_chi2_tiled_kernel<true><<<nb, 256, NT_SMEM, c.stream>>>(fa, nullptr, nullptr, nullptr, nullptr, part);
+    } else {
+        const int gs = fft_group_size(nf);
+        nufft_sample_kernel<<<ceil_div(ds->nuvh * gs, 256), 256, 0, c.stream>>>(fa, gs, nullptr, nullptr, part);
+    }
+    PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
 
@@ -1298,7 +1365,7 @@ int pdsb_sample_image_nufft(pdsb_dataset *ds, const double *image, int ny, int n
     {
         LaunchScope ls("nufft_sample");
         const int gs = fft_group_size(nf);
-        nufft_sample_kernel<<<ceil_div(ds->nuvh * gs, 256), 256, 0, c.stream>>>(fa, gs, ore, oim);
+        nufft_sample_kernel<<<ceil_div(ds->nuvh * gs, 256), 256, 0, c.stream>>>(fa, gs, ore, oim, nullptr);
         PDSB_CUDA(cudaGetLastError());
     }
     if (out_kind == PDSB_HOST) {
@@ -1333,11 +1400,12 @@ int pdsb_loglike_nufft(pdsb_dataset *ds, const double *image, int ny, int nx, in
         if (tiled) {
             static bool attr = false;
             if (!attr) {
-                PDSB_CUDA(cudaFuncSetAttribute(nufft_chi2_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                PDSB_CUDA(cudaFuncSetAttribute(nufft_chi2_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)NT_SMEM));
                 attr = true;
             }
-            nufft_chi2_tiled_kernel<<<nb, 256, NT_SMEM, c.stream>>>(fa, ds->re, ds->im, ds->w, c.red.as<double>());
+            nufft_chi2_tiled_kernel<false><<<nb, 256, NT_SMEM, c.stream>>>(fa, ds->re, ds->im, ds->w, c.red.as<double>(),
+                                                                         nullptr);
         } else {
             nufft_chi2_kernel<<<nb, 256, 0, c.stream>>>(fa, gs, ds->re, ds->im, ds->w, c.red.as<double>());
         }

@@ -210,7 +210,7 @@ def release_model(token):
                 b.free()
 
 
-DFT_KERNELS = {"fp32": 0, "tcgen05": 200, "fp64": 300}
+DFT_KERNELS = {"fp32": 0, "tcgen05": 200, "fp64": 300, "nufft": 400}
 
 
 def set_dft_kernel(kind="fp32"):
@@ -219,6 +219,9 @@ def set_dft_kernel(kind="fp32"):
     "fp32" (default): the FP32-pipe kernel of BASELINE.json's north star.  "tcgen05": the tensor-core
     kernel (tcgen05.mma / TMEM, lattice-split fp16 operands, ~10x faster, same parity bounds).
     "fp64": the all-fp64 reference kernel (1e-13 of max|V| from the CPU oracle, ~8x slower than "fp32").
+    "nufft": not a direct sum at all - the same exact transform through a type-2 non-uniform FFT with an 8-point kernel
+    (4e-8 of max|V|, ~100x faster than "fp32" on cubes; even image sides up to 2048, other shapes take "fp32";
+    DESIGN.md 4.2f).
     An int is passed to pdsb_set_dft_variant unchanged.  The environment variable PDSPY_B200_DFT
     sets the initial choice."""
     variant = DFT_KERNELS[kind] if isinstance(kind, str) else int(kind)

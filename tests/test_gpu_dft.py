@@ -62,7 +62,7 @@ def test_parity_small_shapes(gpu, ny, nx, nf, nuv, herm):
     assert relerr(vis, ref) < TOL
 
 
-@pytest.mark.parametrize("variant", [1, 2, 200, 201, 300])
+@pytest.mark.parametrize("variant", [1, 2, 200, 201, 300, 400])
 @pytest.mark.parametrize("split", [1, 3])
 def test_every_kernel_variant_and_split(gpu, variant, split):
     gpu.pdsb_set_dft_variant(variant)

@@ -121,7 +121,7 @@ def test_lnlike_against_the_fp64_kernel(gpu, workload, star):
     d = Visibilities(c["u"], c["v"], c["freq"], re, im, w)
     out = {}
     try:
-        for k in ("fp64", "fp32", "tcgen05"):
+        for k in ("fp64", "fp32", "tcgen05", "nufft"):
             pb.set_dft_kernel(k)
             out[k] = loglike_image(d, c["model"], dRA=c["dRA"], dDec=c["dDec"])
     finally:
@@ -129,10 +129,12 @@ def test_lnlike_against_the_fp64_kernel(gpu, workload, star):
     ll0, chi0 = out["fp64"]
     assert np.all(np.isfinite(chi0))
     bound = 4e-7 if star else 1e-7
-    for k in ("fp32", "tcgen05"):
+    for k in ("fp32", "tcgen05", "nufft"):
         ll, chi = out[k]
         assert abs(ll - ll0) <= bound * abs(ll0), (k, abs(ll - ll0) / abs(ll0))
         assert np.all(np.abs(chi - chi0) <= bound * np.abs(chi0)), (k, (np.abs(chi - chi0) / np.abs(chi0)).max())
+    ll, chi = out["nufft"]                             # fp64 throughout; kernel accuracy 4e-8 of max|V|
+    assert abs(ll - ll0) <= 1e-7 * abs(ll0) and np.all(np.abs(chi - chi0) <= 1e-7 * np.abs(chi0))
     if not star:
         ll, chi = out["fp32"]
         assert abs(ll - ll0) <= 1e-9 * abs(ll0)
@@ -146,7 +148,7 @@ def test_star_cube_visibilities(gpu):
     c = synth.make_config("C3", nuv=200_000)
     _star_cube(c)
     out = {}
-    for name, var in (("fp64", 300), ("fp32", 0), ("tcgen05", 200)):
+    for name, var in (("fp64", 300), ("fp32", 0), ("tcgen05", 200), ("nufft", 400)):
         _lib.check(gpu.pdsb_set_dft_variant(var))
         try:
             v = interpolate_model(c["u"], c["v"], c["freq"], c["model"], dRA=c["dRA"], dDec=c["dDec"])
@@ -156,7 +158,7 @@ def test_star_cube_visibilities(gpu):
     scale = np.abs(out["fp64"]).max(axis=0)
     assert scale[3] == 0.0
     scale[3] = 1.0
-    for name in ("fp32", "tcgen05"):
+    for name in ("fp32", "tcgen05", "nufft"):
         assert np.all(out[name][:, 3] == 0.0), name
         assert (np.abs(out[name] - out["fp64"]) / scale).max() < 1e-5, name
 
