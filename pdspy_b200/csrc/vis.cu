@@ -21,6 +21,12 @@ struct pdsb_dataset {
     int *order = nullptr;                        // device [nuvh]: the unique points along a Morton curve of the uv plane
 };
 
+// NUFFT variant of run_dft: S(u, v) of every channel as partial sums part[channel][unique uv] (defined with the NUFFT
+// path at the end of this file, at global scope like the entry points)
+extern "C" {
+static int nufft_partials(pdsb_dataset *ds, const double *img_dev, int ny, int nx, int nf, double dxy, double2 *part);
+}
+
 namespace pdsb {
 
 constexpr double kTwoPi = 6.283185307179586476925286766559;
@@ -710,9 +716,6 @@ struct DftRun {
     int nsplit;
     const double *plane_unscale = nullptr;   // tensor-core kernel: V_i *= plane_unscale[i]
 };
-
-// NUFFT variant: S(u, v) of every channel as partial sums part[channel][unique uv] (defined with the NUFFT path below)
-static int nufft_partials(pdsb_dataset *ds, const double *img_dev, int ny, int nx, int nf, double dxy, double2 *part);
 
 static int run_dft(pdsb_dataset *ds, const double *image, int ny, int nx, int nf, int image_kind, double dxy,
                    DftRun *run)
