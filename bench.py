@@ -883,17 +883,18 @@ def main():
             if rank == 0:
                 ch["e2e_ms_per_step_ShardedLikelihood"] = line["e2e"]["ms_per_step"]
                 extras["dropin_chain"] = ch
-            other = "tcgen05" if args.dft == "fp32" else "fp32"
-            r2, _ = likelihood_leg(env, cfg, other, ksteps, 3)
-            if rank == 0:
-                r2["what"] = ("the same step on the %s DFT kernel (`bench.py --dft %s` makes it the headline); NOT used for "
-                              "value / e2e" % (other, other))
-                r2["speedup_vs_headline_kernel"] = line["ms_per_step"] / r2["ms_per_step"]
-                extras["tensor_core_variant" if other == "tcgen05" else "fp32_pipe_variant"] = r2
+            others = [k for k in ("fp32", "tcgen05", "nufft") if k != args.dft]
+            for other in others:
+                r2, _ = likelihood_leg(env, cfg, other, ksteps, 3)
+                if rank == 0:
+                    r2["what"] = ("the same step on the %s kernel (`bench.py --dft %s` makes it the headline); NOT used for "
+                                  "value / e2e" % (other, other))
+                    r2["speedup_vs_headline_kernel"] = line["ms_per_step"] / r2["ms_per_step"]
+                    extras[{"tcgen05": "tensor_core_variant", "fp32": "fp32_pipe_variant", "nufft": "nufft_variant"}[other]] = r2
             workloads = {}
             if args.workload == "C3":
                 c2 = workload_config("C2")
-                for k in (args.dft, other):
+                for k in [args.dft] + others:
                     r, _ = likelihood_leg(env, c2, k, ksteps, 3)
                     if rank == 0:
                         r["config"] = describe(c2)
@@ -902,7 +903,7 @@ def main():
             if rank == 0:
                 workloads["C4"] = g
             c5 = workload_config("C5")
-            for k in (args.dft, other):
+            for k in [args.dft] + others:
                 r = walker_leg(env, c5, 16 * world, k, 1)
                 if rank == 0:
                     r["note"] = ("16 walkers per GPU x %d GPU(s): configs[4]'s per-GPU share (128 walkers on 8 GPUs); "
