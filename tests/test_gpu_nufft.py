@@ -52,6 +52,9 @@ def test_nufft_vs_exact_oracle(gpu, n, nf, nuv, herm, kind):
         u, v = rng.uniform(-lim, lim, nuv), rng.uniform(-lim, lim, nuv)
         u[:4] = [0.0, lim * (1 - 1e-12), -lim * (1 - 1e-12), 1e-3 * lim]
         v[:4] = [0.0, -lim * (1 - 1e-12), lim * (1 - 1e-12), -1e-3 * lim]
+        if nuv > 8:                         # beyond the image's Nyquist frequency: the sum is periodic in u dxy, so is the torus
+            u[4:8] = [1.6 * lim, -2.3 * lim, 0.2 * lim, 7.9 * lim]
+            v[4:8] = [0.3 * lim, 1.1 * lim, -3.7 * lim, -7.2 * lim]
     ref = od.exact_dft(u, v, m.image, px * A, 0.04 * A, -0.03 * A)
     vis = interpolate_model(u, v, m.freq, m, dRA=0.04, dDec=-0.03, code="nufft")
     assert vis.real.shape == (nuv, nf) and np.all(vis.weights == 1)
