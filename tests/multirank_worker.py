@@ -47,8 +47,8 @@ data = Visibilities(c["u"], c["v"], c["freq"], re, im, w)
 like = pdist.ShardedLikelihood(pdist.shard_visibilities(data, rank, world))
 cube = np.ascontiguousarray(c["model"].image[:, :, :, 0])
 dxy = c["pixelsize"] * A
-for kernel in ("fp32", "tcgen05"):
-    _lib.check(_lib.lib().pdsb_set_dft_variant({"fp32": 0, "tcgen05": 200}[kernel]))
+for kernel in ("fp32", "tcgen05", "nufft"):
+    _lib.check(_lib.lib().pdsb_set_dft_variant({"fp32": 0, "tcgen05": 200, "nufft": 400}[kernel]))
     vals = {mode: like(cube, dxy, c["dRA"] * A, c["dDec"] * A, kind=0, cube=mode) for mode in (None, "sharded", "rank0")}
     single, _ = loglike_image(data, c["model"], dRA=c["dRA"], dDec=c["dDec"])
     for mode, val in vals.items():
