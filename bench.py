@@ -376,7 +376,7 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
         return like(pinned.array, dxy, dra, ddec, kind=_lib.HOST, cube="sharded" if shard_upload else None)
 
     _lib.check(L.pdsb_set_dft_variant(DFT_VARIANT[dft]))
-    prefix = {"tcgen05": b"dft_tc5", "nufft": b"nufft_sample"}.get(dft, b"dft_f2")
+    prefix = {"tcgen05": b"dft_tc5", "nufft": b"nufft_chi2"}.get(dft, b"dft_f2")
     total_ms, k_ms, k_n, launches, clocks, ll = timed_device_steps(env, step_device, steps, warmup, prefix,
                                                                    sample_clocks=main)
     e2e_s, ll_e2e = timed_host_steps(env, step_e2e, steps)
@@ -447,8 +447,8 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
                 alg = float(cube.nbytes) + 24.0 * like.ds.nuv * nf
                 res["roofline"] = {
                     "kernel": "NUFFT path: rfft2_planes_padded (deapodised, zero-padded half-spectrum FFT of every channel) + "
-                              "nufft_chi2_tiled_kernel<PART> (8 x 8 taps per unique uv point and channel from shared memory) "
-                              "+ the likelihood epilogue shared with the direct-sum kernels",
+                              "nufft_chi2_tiled_kernel<2> (8 x 8 taps per unique uv point and channel from shared memory, "
+                              "chi^2 per channel summed in the same kernel)",
                     "bound": "hbm", "achieved": alg / (path_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                     "frac": alg / (path_ms * 1e-3) / 1e9 / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
                     "algorithmic_bytes_note": "fp64 cube read once + real, imag, weights of this rank's shard read once",

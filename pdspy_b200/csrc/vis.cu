@@ -25,6 +25,9 @@ struct pdsb_dataset {
 // path at the end of this file, at global scope like the entry points)
 extern "C" {
 static int nufft_partials(pdsb_dataset *ds, const double *img_dev, int ny, int nx, int nf, double dxy, double2 *part);
+// chi^2 per channel straight from the NUFFT sampler (no partial sums); *done = 0 when the shape is outside its domain
+static int nufft_chi2_channels(pdsb_dataset *ds, const double *img_dev, int ny, int nx, int nf, double dxy, double dRA,
+                               double dDec, double *chi2_dev, int *done);
 }
 
 namespace pdsb {
@@ -525,9 +528,12 @@ struct NtPoint {
 };
 constexpr size_t NT_SMEM = (size_t)NT_CAP * NT_CG * sizeof(double2) + NT_PTS * sizeof(NtPoint) + 64;
 
-// PART: instead of the chi^2 sums, write S (without the dRA / dDec phase) as the partial sums part[channel][unique uv]
-// that the epilogues shared with the direct-sum kernels consume (run_dft with the NUFFT variant).
-template <bool PART>
+// MODE 0: the two chi^2 sums of pdsb_loglike_nufft (real and imaginary part, all channels together).
+// MODE 1: instead of chi^2, write S (without the dRA / dDec phase) as the partial sums part[channel][unique uv] that
+//         the epilogues shared with the direct-sum kernels consume (run_dft with the NUFFT variant).
+// MODE 2: chi^2 per channel (real + imaginary), what pdsb_loglike* return: blockpart[block][channel] (nf <= 16 NT_MAXG).
+constexpr int NT_MAXG = 8;
+template <int MODE>
 __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const NufftArgs P, const double *__restrict__ dre,
                                                                   const double *__restrict__ dim,
                                                                   const double *__restrict__ w,
@@ -541,9 +547,13 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
     __shared__ double sh[8];
     const int tid = threadIdx.x;
     const int N = P.N, h = N / 2;
+    constexpr bool PART = MODE == 1;
     const bool twin = P.nuv > P.nuvh;
     const int64_t nbatch = (P.nuvh + NT_PTS - 1) / NT_PTS;
     double sr = 0.0, si = 0.0;
+    double accg[NT_MAXG];                        // MODE 2: this thread's channels tid % 16 + 16 g
+#pragma unroll
+    for (int g = 0; g < NT_MAXG; g++) accg[g] = 0.0;
     for (int64_t b = blockIdx.x; b < nbatch; b += gridDim.x) {
         // ---- per-point part: thread = (point, tap) ----
         if (tid < 4) box[tid] = (tid & 1) ? INT_MIN : INT_MAX;
@@ -682,17 +692,36 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
                     continue;
                 }
                 double a = a0 - m.x, bq = b0 - m.y;
-                sr += a * a * w0;
-                si += bq * bq * w0;
+                double t_re = a * a * w0, t_im = bq * bq * w0;
                 a = a1 - m.x;
                 bq = b1 + m.y;                           // the twin's model is the conjugate (w1 = 0 without a twin)
-                sr += a * a * w1;
-                si += bq * bq * w1;
+                t_re += a * a * w1;
+                t_im += bq * bq * w1;
+                if (MODE == 2) accg[cg0 / NT_CG] += t_re + t_im;
+                else {
+                    sr += t_re;
+                    si += t_im;
+                }
             }
             __syncthreads();                             // the patch (and pts / box at the last group) are free again
         }
     }
     if (PART) return;
+    if (MODE == 2) {
+        // per channel: the 16 threads that share tid % 16 hold the same channels
+        double *red = reinterpret_cast<double *>(nt_smem);           // the patch is free now
+        for (int g = 0; g * NT_CG < P.nf; g++) {
+            __syncthreads();
+            red[tid] = accg[g];
+            __syncthreads();
+            if (tid < NT_CG && g * NT_CG + tid < P.nf) {
+                double t = 0.0;
+                for (int j = 0; j < 256 / NT_CG; j++) t += red[j * NT_CG + tid];
+                blockpart[(size_t)blockIdx.x * P.nf + g * NT_CG + tid] = t;
+            }
+        }
+        return;
+    }
     sr = block_sum<256>(sr, sh);
     si = block_sum<256>(si, sh);
     if (threadIdx.x == 0) {
@@ -847,6 +876,18 @@ static int run_loglike_dev(pdsb_dataset *ds, const double *image, int ny, int nx
     Context &c = ctx();
     PDSB_REQUIRE(ds && ds->has_data, "dataset has no data (call pdsb_dataset_set_data)");
     PDSB_REQUIRE(nf == ds->nf, "image channel count != dataset channel count");
+    if (c.dft_variant == DFT_VARIANT_NUFFT && !g_mods.chan_scale_host && g_mods.ff_flux == 0.0) {
+        // NUFFT kernel, no model modifiers: the sampler sums chi^2 per channel itself (no 16 bytes of partial sum per
+        // (uv, channel) written and read back)
+        PDSB_REQUIRE(ny > 0 && nx > 0 && nf > 0 && dxy > 0.0, "image shape / dxy");
+        const double *img_dev = nullptr;
+        int done = 0;
+        PDSB_CHECK(to_device(image, image_kind, (size_t)ny * nx * nf * sizeof(double), c.img64, (const void **)&img_dev));
+        PDSB_CHECK(nufft_chi2_channels(ds, img_dev, ny, nx, nf, dxy, dRA, dDec, chi2_dev, &done));
+        if (done) return PDSB_OK;
+        image = img_dev;                                 // already on the device for the general route below
+        image_kind = PDSB_DEVICE;
+    }
     DftRun run;
     PDSB_CHECK(run_dft(ds, image, ny, nx, nf, image_kind, dxy, &run));
     EpiParams e = make_epi(ds, run, dRA, dDec);
@@ -1334,17 +1375,45 @@ static int nufft_partials(pdsb_dataset *ds, const double *img_dev, int ny, int n
     if (nf >= NT_CG && !getenv("PDSB_NUFFT_DIRECT")) {
         static bool attr = false;
         if (!attr) {
-            PDSB_CUDA(cudaFuncSetAttribute(nufft_chi2_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            PDSB_CUDA(cudaFuncSetAttribute(nufft_chi2_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)NT_SMEM));
             attr = true;
         }
         const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * NT_MINB, (ds->nuvh + NT_PTS - 1) / NT_PTS);
-        nufft_chi2_tiled_kernel<true><<<nb, 256, NT_SMEM, c.stream>>>(fa, nullptr, nullptr, nullptr, nullptr, part);
+        nufft_chi2_tiled_kernel<1><<<nb, 256, NT_SMEM, c.stream>>>(fa, nullptr, nullptr, nullptr, nullptr, part);
     } else {
         const int gs = fft_group_size(nf);
         nufft_sample_kernel<<<ceil_div(ds->nuvh * gs, 256), 256, 0, c.stream>>>(fa, gs, nullptr, nullptr, part);
     }
     PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
+}
+
+static int nufft_chi2_channels(pdsb_dataset *ds, const double *img_dev, int ny, int nx, int nf, double dxy, double dRA,
+                               double dDec, double *chi2_dev, int *done)
+{
+    Context &c = ctx();
+    *done = 0;
+    if (ny % 2 || nx % 2 || ny > 2048 || nx > 2048 || nf < NT_CG || nf > NT_CG * NT_MAXG || ds->nuvh == 0 ||
+        getenv("PDSB_NUFFT_DIRECT"))
+        return PDSB_OK;
+    NufftArgs fa;
+    PDSB_CHECK(nufft_transform_dev(ds, img_dev, ny, nx, nf, dxy, dRA, dDec, &fa));
+    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * NT_MINB, (ds->nuvh + NT_PTS - 1) / NT_PTS);
+    PDSB_CHECK(c.red.ensure((size_t)nb * nf * sizeof(double)));
+    {
+        LaunchScope ls("nufft_chi2");
+        static bool attr = false;
+        if (!attr) {
+            PDSB_CUDA(cudaFuncSetAttribute(nufft_chi2_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)NT_SMEM));
+            attr = true;
+        }
+        nufft_chi2_tiled_kernel<2><<<nb, 256, NT_SMEM, c.stream>>>(fa, ds->re, ds->im, ds->w, c.red.as<double>(), nullptr);
+        PDSB_CUDA(cudaGetLastError());
+    }
+    PDSB_CHECK(reduce_blocks(c.red.as<double>(), nb, nf, chi2_dev));
+    *done = 1;
     return PDSB_OK;
 }
 
@@ -1403,11 +1472,11 @@ int pdsb_loglike_nufft(pdsb_dataset *ds, const double *image, int ny, int nx, in
         if (tiled) {
             static bool attr = false;
             if (!attr) {
-                PDSB_CUDA(cudaFuncSetAttribute(nufft_chi2_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                PDSB_CUDA(cudaFuncSetAttribute(nufft_chi2_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)NT_SMEM));
                 attr = true;
             }
-            nufft_chi2_tiled_kernel<false><<<nb, 256, NT_SMEM, c.stream>>>(fa, ds->re, ds->im, ds->w, c.red.as<double>(),
+            nufft_chi2_tiled_kernel<0><<<nb, 256, NT_SMEM, c.stream>>>(fa, ds->re, ds->im, ds->w, c.red.as<double>(),
                                                                          nullptr);
         } else {
             nufft_chi2_kernel<<<nb, 256, 0, c.stream>>>(fa, gs, ds->re, ds->im, ds->w, c.red.as<double>());
