@@ -254,21 +254,25 @@ __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, 
     double2 *x = w + (size_t)f * fft_padlen(n);
     int s = 1;
     for (; s + 1 <= logn; s += 2) {
-        const int half = 1 << (s - 1), ts1 = n >> s, ts2 = n >> (s + 1);
+        const int half = 1 << (s - 1), ts2 = n >> (s + 1);
         if (f < nfft)
             for (int idx = tl; idx < n / 4; idx += tpf) {
                 const int k = idx & (half - 1);
                 const int j = ((idx >> (s - 1)) << (s + 1)) + k;
                 const int p0 = fft_pad(j), p1 = fft_pad(j + half), p2 = fft_pad(j + 2 * half), p3 = fft_pad(j + 3 * half);
                 double2 a0 = x[p0], a1 = x[p1], a2 = x[p2], a3 = x[p3];
-                const double2 w1 = tw[k * ts1];
+                // one table read per butterfly: w2a = e^{2 pi i k / 4 half}; the inner stage's twiddle is its square
+                // (k ts1 = 2 k ts2), the second outer one is i w2a ((k + half) ts2 = k ts2 + n / 4)
+                // (first pass: half = 1, k = 0, all three are 1, 1, i - no table read)
+                const double2 w2a = s == 1 ? make_double2(1.0, 0.0) : tw[k * ts2];
+                const double2 w1 = make_double2(w2a.x * w2a.x - w2a.y * w2a.y, 2.0 * w2a.x * w2a.y);
+                const double2 w2b = make_double2(-w2a.y, w2a.x);
                 double2 t = cmul(w1, a1);
                 a1 = make_double2(a0.x - t.x, a0.y - t.y);
                 a0 = make_double2(a0.x + t.x, a0.y + t.y);
                 t = cmul(w1, a3);
                 a3 = make_double2(a2.x - t.x, a2.y - t.y);
                 a2 = make_double2(a2.x + t.x, a2.y + t.y);
-                const double2 w2a = tw[k * ts2], w2b = tw[(k + half) * ts2];
                 t = cmul(w2a, a2);
                 x[p0] = make_double2(a0.x + t.x, a0.y + t.y);
                 x[p2] = make_double2(a0.x - t.x, a0.y - t.y);
