@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(256) chisq_ch0_kernel(const double *__restrict
 struct FftSampleArgs {
     const double2 *Ysh;
     const double *u, *v;
+    const int *order;          // visiting order of the unique points (Morton curve of the uv plane), or null
     int64_t nuv, nuvh;
     int n, nf;
     double dxy, dRA, dDec;
@@ -307,17 +308,27 @@ __device__ __forceinline__ double2 fft_sample_channel(const FftSampleArgs &P, co
 // A group of gs lanes (a power of two <= 32, <= nf) shares one visibility: the per-visibility part is evaluated once
 // per group instruction instead of once per (visibility, channel); the lanes take the channels gs apart, so the
 // corner reads and the data reads are contiguous runs of the channel-fastest arrays.
+// A lane group evaluates one UNIQUE uv point; the second half of a Hermitian-doubled list gets the conjugate (galario's
+// own rule for u < 0: mirrored interpolation point, conjugated value and phase - the same numbers).  The unique
+// points are visited along the Morton curve of the uv plane (P.order), so that neighbouring groups read neighbouring
+// corners of the transformed cube.
 __global__ void __launch_bounds__(256) fft_sample_kernel(const FftSampleArgs P, int gs, double *__restrict__ out_re,
                                                          double *__restrict__ out_im)
 {
     const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t k = t / gs;
-    if (k >= P.nuv) return;
+    const int64_t kk = t / gs;
+    if (kk >= P.nuvh) return;
+    const int64_t k = P.order ? P.order[kk] : kk;
     const FftCorner q = fft_corner(P, k);
+    const bool twin = P.nuv > P.nuvh;
     for (int i = (int)(t % gs); i < P.nf; i += gs) {
         const double2 m = fft_sample_channel(P, q, i);
         out_re[k * P.nf + i] = m.x;
         out_im[k * P.nf + i] = m.y;
+        if (twin) {
+            out_re[(k + P.nuvh) * P.nf + i] = m.x;
+            out_im[(k + P.nuvh) * P.nf + i] = -m.y;
+        }
     }
 }
 
@@ -329,18 +340,30 @@ __global__ void __launch_bounds__(256) fft_chi2_kernel(const FftSampleArgs P, in
     __shared__ double sh[8];
     double sr = 0.0, si = 0.0;
     const int lg = threadIdx.x % gs;
+    const bool twin = P.nuv > P.nuvh;
     const int64_t kstep = (int64_t)gridDim.x * (256 / gs);
-    for (int64_t k = (int64_t)blockIdx.x * (256 / gs) + threadIdx.x / gs; k < P.nuv; k += kstep) {
+    for (int64_t kk = (int64_t)blockIdx.x * (256 / gs) + threadIdx.x / gs; kk < P.nuvh; kk += kstep) {
+        const int64_t k = P.order ? P.order[kk] : kk;
         const FftCorner q = fft_corner(P, k);
         for (int i = lg; i < P.nf; i += gs) {
-            const int64_t idx = k * P.nf + i;
+            const int64_t idx = k * P.nf + i, id2 = idx + P.nuvh * P.nf;
             // the 1.5 GB of data stream through once: evict-first, so that they do not push the transformed cube
             // (the gathers' working set, about the size of the L2) out of the cache
-            const double ww = __ldcs(w + idx), a0 = __ldcs(dre + idx), b0 = __ldcs(dim + idx);
+            const double w0 = __ldcs(w + idx), a0 = __ldcs(dre + idx), b0 = __ldcs(dim + idx);
+            double w1 = 0.0, a1 = 0.0, b1 = 0.0;
+            if (twin) {
+                w1 = __ldcs(w + id2);
+                a1 = __ldcs(dre + id2);
+                b1 = __ldcs(dim + id2);
+            }
             const double2 m = fft_sample_channel(P, q, i);
-            const double a = a0 - m.x, b = b0 - m.y;
-            sr += a * a * ww;
-            si += b * b * ww;
+            double a = a0 - m.x, b = b0 - m.y;
+            sr += a * a * w0;
+            si += b * b * w0;
+            a = a1 - m.x;
+            b = b1 + m.y;
+            sr += a * a * w1;
+            si += b * b * w1;
         }
     }
     sr = block_sum<256>(sr, sh);
@@ -1166,6 +1189,8 @@ static int fft_group_size(int nf)
     return gs;
 }
 
+static int nufft_order(pdsb_dataset *ds);               // the Morton visiting order (defined with the NUFFT path)
+
 // galario's FFT stage: the transformed cube of every channel (rfft2_planes) and the sampling arguments
 static int run_fft_transform(pdsb_dataset *ds, const double *image, int n, int nf, int image_kind, double dxy, double dRA,
                              double dDec, FftSampleArgs *a)
@@ -1181,7 +1206,9 @@ static int run_fft_transform(pdsb_dataset *ds, const double *image, int n, int n
     PDSB_CHECK(c.folded.ensure(2 * nh * nf * sizeof(double2)));            // [T | Y]: the DFT's scratch, free here
     double2 *T = c.folded.as<double2>(), *Y = T + nh * nf;
     PDSB_CHECK(rfft2_planes(img_dev, n, nf, 1, T, Y));
-    *a = FftSampleArgs{Y, ds->u, ds->v, ds->nuv, ds->nuvh, n, nf, dxy, dRA, dDec};
+    PDSB_REQUIRE(ds->nuvh < ((int64_t)1 << 31), "more than 2^31 unique uv points");
+    PDSB_CHECK(nufft_order(ds));
+    *a = FftSampleArgs{Y, ds->u, ds->v, ds->order, ds->nuv, ds->nuvh, n, nf, dxy, dRA, dDec};
     return PDSB_OK;
 }
 
@@ -1205,7 +1232,7 @@ int pdsb_sample_image_fft(pdsb_dataset *ds, const double *image, int n, int nf, 
     {
         LaunchScope ls("fft_sample");
         const int gs = fft_group_size(nf);
-        fft_sample_kernel<<<ceil_div(ds->nuv * gs, 256), 256, 0, c.stream>>>(fa, gs, ore, oim);
+        fft_sample_kernel<<<ceil_div(ds->nuvh * gs, 256), 256, 0, c.stream>>>(fa, gs, ore, oim);
         PDSB_CUDA(cudaGetLastError());
     }
     if (out_kind == PDSB_HOST) {
@@ -1232,7 +1259,7 @@ int pdsb_loglike_fft(pdsb_dataset *ds, const double *image, int n, int nf, int i
     FftSampleArgs fa;
     PDSB_CHECK(run_fft_transform(ds, image, n, nf, image_kind, dxy, dRA, dDec, &fa));
     const int gs = fft_group_size(nf);
-    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 16, (ds->nuv * gs + 255) / 256);
+    const int nb = (int)std::min<int64_t>((int64_t)c.sm_count * 16, (ds->nuvh * gs + 255) / 256);
     PDSB_CHECK(c.red.ensure((size_t)(nb + 1) * 2 * sizeof(double)));
     {
         LaunchScope ls("fft_chi2");
