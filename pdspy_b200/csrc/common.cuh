@@ -78,6 +78,7 @@ struct Context {
     int fft_fb_n = 0;
     Scratch fft_tw;        // galario path: twiddle table exp(+2 pi i j / n), j < n/2, for size fft_tw_n
     int fft_tw_n = 0;
+    Scratch fft_flags;     // per-plane "holds a non-zero value" flags of the cube being transformed
     Scratch nufft_corr;    // NUFFT path: deapodisation factors 1 / psi_hat(X / N) for image side nufft_corr_n
     int nufft_corr_n = 0, nufft_corr_N = 0;
     Scratch mma_ws;        // tensor-core kernel: per-round lattice quanta and per-plane unscale factors

@@ -81,7 +81,12 @@ __device__ __forceinline__ double2 chirp(int k, int n)
     sincospi((double)q / (double)n, &s, &c);
     return make_double2(c, s);
 }
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// Complex product with the contraction fixed (first product fused, second rounded), so that a result does not depend
+// on which product nvcc decides to fuse at a given call site.
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+    return make_double2(fma(a.x, b.x, -__dmul_rn(a.y, b.y)), fma(a.x, b.y, __dmul_rn(a.y, b.x)));
+}
 
 // in-place radix-2 DIT on bit-reversed input, kernel e^{+2 pi i jk/m}; tw[j] = e^{+2 pi i j/m}, j < m/2
 __device__ __forceinline__ void fft_plus_smem(double2 *w, const double2 *tw, int m, int logm)
@@ -234,9 +239,21 @@ __global__ void __launch_bounds__(256) fft_twiddle_kernel(double2 *__restrict__ 
 {
     const int j = blockIdx.x * 256 + threadIdx.x;
     if (j >= n / 2) return;
+    // Built from the first octant only, so that the table has the symmetries of the exponential exactly:
+    // tw[j + n/4] = i tw[j] (the butterflies rely on it: one table read stands for two twiddles), tw[n/4 - j] = swap(tw[j]).
+    int jq = j;
+    const bool rot = 4 * jq > n;
+    if (rot) jq -= n / 4;
+    const bool swp = 8 * jq > n;
+    const int jb = swp ? n / 4 - jq : jq;
     double ws, wc;
-    sincospi(2.0 * (double)j / (double)n, &ws, &wc);
-    tw[j] = make_double2(wc, ws);
+    sincospi(2.0 * (double)jb / (double)n, &ws, &wc);
+    if (swp) {
+        const double t = wc;
+        wc = ws;
+        ws = t;
+    }
+    tw[j] = rot ? make_double2(-ws, wc) : make_double2(wc, ws);
 }
 
 // in-place transforms of nfft rows of length n (bit-reversed input) held at w + f * n, kernel e^{+2 pi i jk/n};
@@ -262,8 +279,8 @@ __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, 
                 const int p0 = fft_pad(j), p1 = fft_pad(j + half), p2 = fft_pad(j + 2 * half), p3 = fft_pad(j + 3 * half);
                 double2 a0 = x[p0], a1 = x[p1], a2 = x[p2], a3 = x[p3];
                 // one table read per butterfly: w2a = e^{2 pi i k / 4 half}; the inner stage's twiddle is its square
-                // (k ts1 = 2 k ts2), the second outer one is i w2a ((k + half) ts2 = k ts2 + n / 4)
-                // (first pass: half = 1, k = 0, all three are 1, 1, i - no table read)
+                // (k ts1 = 2 k ts2), the second outer one is i w2a ((k + half) ts2 = k ts2 + n / 4).
+                // First pass: half = 1, k = 0: 1, 1, i - no table read.
                 const double2 w2a = s == 1 ? make_double2(1.0, 0.0) : tw[k * ts2];
                 const double2 w1 = make_double2(w2a.x * w2a.x - w2a.y * w2a.y, 2.0 * w2a.x * w2a.y);
                 const double2 w2b = make_double2(-w2a.y, w2a.x);
@@ -297,6 +314,20 @@ __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, 
     }
 }
 
+// flags[p] = 1 when plane p of the channel-fastest cube holds a non-zero value.  A channel pair shares one complex
+// transform; its separation returns the rounding residue of the partner (1e-16 of the partner's values) for an
+// all-zero channel unless the zero is known: with the flags an empty channel transforms to exact zeros, like it
+// does in the direct-sum kernels.
+// (the grid is a multiple of nf blocks, so the grid stride is a multiple of nf and a thread stays on one channel)
+__global__ void __launch_bounds__(256) plane_nonzero_kernel(const double *__restrict__ cube, int64_t npix, int nf,
+                                                            int *__restrict__ flags)
+{
+    const int64_t total = npix * nf, i0 = (int64_t)blockIdx.x * 256 + threadIdx.x, stride = (int64_t)gridDim.x * 256;
+    bool any = false;
+    for (int64_t i = i0; i < total; i += stride) any |= cube[i] != 0.0;
+    if (any) flags[(int)(i0 % nf)] = 1;                  // benign race: every writer stores 1
+}
+
 // row pass: block = rows (rho, rho + 1), rho = 2 blockIdx.x, of the (row-flipped) source planes x plane pairs
 // [PB blockIdx.y, ...) -> T[plane][b][r'], b <= n/2  (T: [nf][n/2 + 1][n]).
 // The transform length n may exceed the source sides nsy x nsx (zero padding for the NUFFT path, nsy = nsx = n otherwise):
@@ -307,7 +338,7 @@ __device__ __forceinline__ void fft_plus_rows_r4(double2 *w, const double2 *tw, 
 __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict__ cube, const double2 *__restrict__ twg,
                                                         double2 *__restrict__ T, int n, int logn, int nf, int flip,
                                                         int PB, int tpf, int nsy, int nsx, const double *__restrict__ corr_y,
-                                                        const double *__restrict__ corr_x)
+                                                        const double *__restrict__ corr_x, const int *__restrict__ nonzero)
 {
     extern __shared__ double2 srow[];
     const int h = n / 2, hsy = nsy / 2, hsx = nsx / 2, npair = (nf + 1) / 2;
@@ -354,8 +385,12 @@ __global__ void __launch_bounds__(512) rfft_rows_kernel(const double *__restrict
             const double2 z = x[fft_pad(b)], zc = x[fft_pad((n - b) & (n - 1))];
             const int plane = 2 * (pair0 + pb);
             const int64_t o = (int64_t)plane * ps + (int64_t)b * n + ((rho0 + rb - hsy + n) & (n - 1));      // adjacent for even nsy / 2
-            T[o] = make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
-            if (plane + 1 < nf) T[o + ps] = make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
+            const bool nz0 = nonzero[plane] != 0, nz1 = plane + 1 < nf && nonzero[plane + 1] != 0;
+            // an empty channel is exactly zero, and its partner is then the whole transform (Z, or Z / i)
+            T[o] = !nz0 ? make_double2(0.0, 0.0) : !nz1 ? z : make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
+            if (plane + 1 < nf)
+                T[o + ps] = !nz1 ? make_double2(0.0, 0.0)
+                                 : !nz0 ? make_double2(z.y, -z.x) : make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
         }
 }
 
@@ -437,8 +472,13 @@ int rfft2_planes_padded(const double *cube_dev, int nsy, int nsx, int n, int nf,
     const size_t sm0 = ((size_t)2 * pb0 * fft_padlen(n) + n / 2) * sizeof(double2),
                  sm1 = ((size_t)pb1 * fft_padlen(n) + n / 2) * sizeof(double2);
     LaunchScope ls("rfft2_planes");
+    PDSB_CHECK(c.fft_flags.ensure((size_t)nf * sizeof(int)));
+    PDSB_CUDA(cudaMemsetAsync(c.fft_flags.ptr, 0, (size_t)nf * sizeof(int), c.stream));
+    plane_nonzero_kernel<<<nf * ceil_div(c.sm_count * 8, nf), 256, 0, c.stream>>>(cube_dev, (int64_t)nsy * nsx, nf,
+                                                                                  c.fft_flags.as<int>());
     rfft_rows_kernel<<<dim3(nsy / 2, ceil_div(npair, pb0)), th0, sm0, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip, pb0,
-                                                                                  tpf, nsy, nsx, corr_y, corr_x);
+                                                                                  tpf, nsy, nsx, corr_y, corr_x,
+                                                                                  c.fft_flags.as<int>());
     rfft_cols_kernel<<<dim3(n / 2 + 1, ceil_div(nf, pb1)), th1, sm1, c.stream>>>(T, tw, Yh, n, logn, nf, pb1, tpf, nsy);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
