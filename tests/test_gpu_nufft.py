@@ -107,3 +107,24 @@ def test_nufft_rejects_what_it_cannot_do(gpu):
     e = interpolate_model(np.zeros(0), np.zeros(0), m.freq, synth.SynthImage(synth.synth_image(64, 2, 0.05), 0.05,
                                                                          synth.synth_freq(2)), code="nufft")
     assert e.real.shape == (0, 2)
+
+
+@pytest.mark.parametrize("code", ["nufft", "galario-fft"])
+def test_empty_channels_are_exactly_zero(gpu, code):
+    """Two channels share one complex transform in the FFT-based paths; an all-zero channel must still come out as exact
+    zeros (as it does from the direct-sum kernels), whether it is the first or the second of its pair, and its partner
+    must be what it is next to a non-empty channel."""
+    n, px, nf = 64, 0.05, 6
+    img = synth.synth_image(n, nf, px, kind="random")
+    img[n // 2, n // 2, :, 0] += 1e5                       # a bright pixel: the partner's rounding residue would be ~1e-11
+    full = synth.SynthImage(img.copy(), px, synth.synth_freq(nf))
+    img[:, :, 1, 0] = 0.0                                  # second of pair (0, 1)
+    img[:, :, 4, 0] = 0.0                                  # first of pair (4, 5)
+    m = synth.SynthImage(img, px, synth.synth_freq(nf))
+    u, v = synth.synth_uv(500, px * A)
+    a = interpolate_model(u, v, m.freq, m, dRA=0.02, dDec=-0.01, code=code)
+    b = interpolate_model(u, v, full.freq, full, dRA=0.02, dDec=-0.01, code=code)
+    va, vb = a.real + 1j * a.imag, b.real + 1j * b.imag
+    assert np.all(va[:, 1] == 0.0) and np.all(va[:, 4] == 0.0)
+    for i in (0, 2, 3, 5):
+        assert np.abs(va[:, i] - vb[:, i]).max() <= 1e-13 * np.abs(vb[:, i]).max(), i
