@@ -31,6 +31,8 @@ def relerr(vis, ref):
     (1024, 1, 400, True, "disk"),        # transform length 2048
     (2048, 1, 200, False, "disk"),       # transform length 4096: the largest
     (2, 1, 30, False, "random"),         # grid of 4 cells: every tap index occurs twice
+    (2, 32, 64, True, "random"),         # the same through the shared-memory-staged sampler (>= 16 channels)
+    (4, 17, 70, False, "random"),
     (300, 2, 700, True, "disk"),         # sides that are not powers of two: embedded about the centre pixel
     (90, 3, 300, False, "random"),       # n / 2 odd: the row pair straddles the origin of the transform
     ((96, 250), 2, 400, False, "random"),    # rectangular, both ways
