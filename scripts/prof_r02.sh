@@ -10,7 +10,9 @@ $NCU -k regex:dft_kernel -c 1 -o $O/r02_dft_fp32 -f python scripts/prof_dft.py C
 $NCU -k regex:dft_tc5_kernel -c 1 -o $O/r02_dft_tc5 -f python scripts/prof_dft.py C3 200 1 > $O/r02_prof_dft_tc5.log 2>&1
 # one whole fast-mode grid() step (second repetition): hist, scans, work list, record pass, tile kernel, normalise
 $NCU -k regex:'gf_|grid_normalise' -s 7 -c 7 -o $O/r02_grid -f python scripts/prof_grid.py 2 > $O/r02_prof_grid.log 2>&1
-# one whole galario-path likelihood (third repetition): row pass, column pass, fused sampler + chi^2
-$NCU -k regex:'rfft_|fft_chi2' -s 6 -c 3 -o $O/r02_fft -f python scripts/prof_fft.py > $O/r02_prof_fft.log 2>&1
+# one whole galario-path likelihood (third repetition): plane flags, row pass, column pass, fused sampler + chi^2
+$NCU -k regex:'plane_nonzero|rfft_|fft_chi2' -s 8 -c 4 -o $O/r02_fft -f python scripts/prof_fft.py > $O/r02_prof_fft.log 2>&1
+# one whole NUFFT-path likelihood (third repetition), fused entry point
+$NCU -k regex:'plane_nonzero|rfft_|nufft_chi2' -s 8 -c 4 -o $O/r02_nufft -f python scripts/prof_nufft.py C3 > $O/r02_prof_nufft.log 2>&1
 ls -la $O | tail -20
-tail -3 $O/r02_prof_grid.log $O/r02_prof_fft.log
+tail -n 3 $O/r02_prof_grid.log; tail -n 3 $O/r02_prof_fft.log; tail -n 3 $O/r02_prof_nufft.log
