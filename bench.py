@@ -773,7 +773,7 @@ def walker_leg(env, cfg, walkers, dft, steps):
                "e2e": {"value": pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nw * base.nbytes) * world,
                        "d2h_bytes_per_step": int(nw * 8) * world, "ms_per_step": e2e_s / steps * 1e3,
                        "likelihood_evals_per_s": walkers * steps / e2e_s,
-                       "api": "pdsb_loglike_batch (host fp64 cubes in, host lnlike[W] out)"},
+                       "api": "pdsb_loglike_batch (host fp64 cubes in pinned memory, host lnlike[W] out; cube k+1 uploads on a copy stream while cube k is evaluated)"},
                "gpu_launches": n1 - n0, "lnlike0": lnlike0,
                "lnlike0_rel_diff_vs_fp64_kernel": abs(lnlike0 - ll_f64) / abs(ll_f64)}
     ds.destroy()

@@ -60,6 +60,8 @@ struct Context {
     int cc_major = 0, cc_minor = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;        // walker batches: the next cube travels while the current one is evaluated
+    cudaEvent_t cube_ready[2] = {nullptr, nullptr}, cube_free[2] = {nullptr, nullptr};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     bool profiling = false;
     std::vector<ProfileEntry> prof;
@@ -72,7 +74,7 @@ struct Context {
     int64_t grid_ext_ncell = 0;
     std::vector<double> grid_ext_sumw;         //   and the per-channel weight sums
     // scratch
-    Scratch img64, folded, partial, red, stage_a, stage_b, stage_c, stage_d, stage_e;
+    Scratch img64, img64_b, folded, partial, red, stage_a, stage_b, stage_c, stage_d, stage_e;
     Scratch small_dev;     // tiny per-call device arrays (channel scale factors)
     Scratch fft_fb;        // invert(), sizes that are not a power of two: transform of Bluestein's chirp, for size fft_fb_n
     int fft_fb_n = 0;
@@ -100,6 +102,7 @@ int to_device(const void *p, int kind, size_t bytes, Scratch &scratch, const voi
 // host <-> device copies on the context's stream; large pageable arrays go through a multi-threaded pinned ring
 // (runtime.cu).  copy_h2d returns when the source may be reused, copy_d2h when the destination holds the data.
 int copy_h2d(void *dst_dev, const void *src_host, size_t bytes);
+int copy_h2d_on(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream);      // the same on another stream
 int copy_d2h(void *dst_host, const void *src_dev, size_t bytes);
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -155,13 +155,15 @@ static bool pageable(const void *p)
 }
 static constexpr size_t STAGED_MIN_BYTES = (size_t)16 << 20;
 
-int copy_h2d(void *dst, const void *src, size_t bytes)
+int copy_h2d(void *dst, const void *src, size_t bytes) { return copy_h2d_on(dst, src, bytes, ctx().stream); }
+
+int copy_h2d_on(void *dst, const void *src, size_t bytes, cudaStream_t stream)
 {
     Context &c = ctx();
     if (bytes == 0) return PDSB_OK;
     StagePool *sp = bytes >= STAGED_MIN_BYTES && pageable(src) ? &stage_pool() : nullptr;
     if (!sp || sp->nthreads < 1) {
-        PDSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
+        PDSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
         return PDSB_OK;
     }
     const size_t nchunk = (bytes + StagePool::CHUNK - 1) / StagePool::CHUNK;
@@ -176,8 +178,8 @@ int copy_h2d(void *dst, const void *src, size_t bytes)
             cudaError_t e = k >= 2 ? cudaEventSynchronize(sp->evs[b]) : cudaSuccess;     // buffer free again?
             memcpy(sp->bufs[b], static_cast<const char *>(src) + off, len);
             if (e == cudaSuccess)
-                e = cudaMemcpyAsync(static_cast<char *>(dst) + off, sp->bufs[b], len, cudaMemcpyHostToDevice, c.stream);
-            if (e == cudaSuccess) e = cudaEventRecord(sp->evs[b], c.stream);
+                e = cudaMemcpyAsync(static_cast<char *>(dst) + off, sp->bufs[b], len, cudaMemcpyHostToDevice, stream);
+            if (e == cudaSuccess) e = cudaEventRecord(sp->evs[b], stream);
             if (e != cudaSuccess) err[t] = e;
         }
         for (int q = 0; q < 2 && q < k; q++) {                                          // leave the ring idle
@@ -355,6 +357,11 @@ int pdsb_init(int device)
     c.cc_minor = p.minor;
     PDSB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
+    PDSB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        PDSB_CUDA(cudaEventCreateWithFlags(&c.cube_ready[i], cudaEventDisableTiming));
+        PDSB_CUDA(cudaEventCreateWithFlags(&c.cube_free[i], cudaEventDisableTiming));
+    }
     PDSB_CUDA(cudaEventCreate(&c.t0));
     PDSB_CUDA(cudaEventCreate(&c.t1));
     c.inited = true;
@@ -366,8 +373,9 @@ int pdsb_shutdown(void)
     Context &c = ctx();
     if (!c.inited) return PDSB_OK;
     cudaStreamSynchronize(c.stream);
-    for (Scratch *s : {&c.img64, &c.folded, &c.partial, &c.red, &c.stage_a, &c.stage_b, &c.stage_c,
-                       &c.stage_d, &c.stage_e, &c.small_dev, &c.mma_ws, &c.fft_fb})
+    cudaStreamSynchronize(c.copy_stream);
+    for (Scratch *s : {&c.img64, &c.img64_b, &c.folded, &c.partial, &c.red, &c.stage_a, &c.stage_b, &c.stage_c,
+                       &c.stage_d, &c.stage_e, &c.small_dev, &c.mma_ws, &c.fft_fb, &c.fft_tw, &c.fft_flags, &c.nufft_corr})
         s->release();
     c.fft_fb_n = 0;
     for (auto &p : c.prof) {
@@ -379,6 +387,11 @@ int pdsb_shutdown(void)
     c.event_pool.clear();
     cudaEventDestroy(c.t0);
     cudaEventDestroy(c.t1);
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(c.cube_ready[i]);
+        cudaEventDestroy(c.cube_free[i]);
+    }
+    cudaStreamDestroy(c.copy_stream);
     cudaStreamDestroy(c.own_stream);
     c = Context();
     return PDSB_OK;

@@ -1105,9 +1105,44 @@ static int loglike_impl(pdsb_dataset *ds, const double *images, int nwalkers, in
         PDSB_CHECK(c.stage_c.ensure((size_t)nwalkers * nf * sizeof(double)));
         double *chi2_dev = c.stage_c.as<double>();
         const size_t cube = (size_t)ny * nx * nf;
-        for (int wk = 0; wk < nwalkers; wk++)
-            PDSB_CHECK(run_loglike_dev(ds, images + (size_t)wk * cube, ny, nx, nf, image_kind, dxy, dRA[wk],
-                                       dDec[wk], chi2_dev + (size_t)wk * nf));
+        if (nwalkers > 1 && image_kind == PDSB_HOST) {
+            // Walker batch from host memory: cube wk + 1 travels on the copy stream into the other of two device
+            // buffers while cube wk is evaluated on the compute stream.  cube_ready[b]: buffer b holds its cube
+            // (compute waits); cube_free[b]: the evaluation that read buffer b is done (the next copy into b waits).
+            const size_t bytes = cube * sizeof(double);
+            PDSB_CHECK(c.img64.ensure(bytes));
+            PDSB_CHECK(c.img64_b.ensure(bytes));
+            double *buf[2] = {c.img64.as<double>(), c.img64_b.as<double>()};
+            PDSB_CUDA(cudaEventRecord(c.cube_free[0], c.stream));          // earlier work on the stream may read buffer 0
+            PDSB_CUDA(cudaStreamWaitEvent(c.copy_stream, c.cube_free[0], 0));
+            int rc = copy_h2d_on(buf[0], images, bytes, c.copy_stream);
+            if (rc == PDSB_OK && cudaEventRecord(c.cube_ready[0], c.copy_stream) != cudaSuccess) rc = PDSB_ERR_CUDA;
+            for (int wk = 0; wk < nwalkers && rc == PDSB_OK; wk++) {
+                const int b = wk & 1;
+                if (cudaStreamWaitEvent(c.stream, c.cube_ready[b], 0) != cudaSuccess) rc = PDSB_ERR_CUDA;
+                if (rc == PDSB_OK)
+                    rc = run_loglike_dev(ds, buf[b], ny, nx, nf, PDSB_DEVICE, dxy, dRA[wk], dDec[wk],
+                                         chi2_dev + (size_t)wk * nf);
+                if (rc == PDSB_OK && cudaEventRecord(c.cube_free[b], c.stream) != cudaSuccess) rc = PDSB_ERR_CUDA;
+                if (rc == PDSB_OK && wk + 1 < nwalkers) {
+                    if (wk >= 1 && cudaStreamWaitEvent(c.copy_stream, c.cube_free[b ^ 1], 0) != cudaSuccess)
+                        rc = PDSB_ERR_CUDA;
+                    if (rc == PDSB_OK) rc = copy_h2d_on(buf[b ^ 1], images + (size_t)(wk + 1) * cube, bytes, c.copy_stream);
+                    if (rc == PDSB_OK && cudaEventRecord(c.cube_ready[b ^ 1], c.copy_stream) != cudaSuccess)
+                        rc = PDSB_ERR_CUDA;
+                }
+            }
+            if (rc != PDSB_OK) {                                           // leave both streams idle before reporting
+                cudaStreamSynchronize(c.copy_stream);
+                cudaStreamSynchronize(c.stream);
+                if (rc == PDSB_ERR_CUDA) PDSB_CUDA(cudaGetLastError());
+                return rc;
+            }
+        } else {
+            for (int wk = 0; wk < nwalkers; wk++)
+                PDSB_CHECK(run_loglike_dev(ds, images + (size_t)wk * cube, ny, nx, nf, image_kind, dxy, dRA[wk],
+                                           dDec[wk], chi2_dev + (size_t)wk * nf));
+        }
         PDSB_CUDA(cudaMemcpyAsync(h.data(), chi2_dev, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }

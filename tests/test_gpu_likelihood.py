@@ -100,6 +100,38 @@ def test_walker_batch_matches_single_calls(gpu):
         assert ll[k] == one
 
 
+@pytest.mark.parametrize("kernel", ["fp32", "tcgen05", "nufft"])
+@pytest.mark.parametrize("n,nf", [(256, 32), (64, 4)])
+def test_walker_batch_pipeline_keeps_cubes_apart(gpu, kernel, n, nf):
+    """pdsb_loglike_batch uploads cube k+1 on a copy stream while cube k is evaluated (two device buffers): seven
+    different cubes, every likelihood bit-identical to its own single call.  256x256x32 cubes (16.8 MB) travel
+    through the staged pinned ring, 64x64x4 ones directly."""
+    import pdspy_b200
+    rng = np.random.default_rng(5)
+    nuv, W = 1500, 7
+    px = 0.02
+    u, v = synth.synth_uv(nuv, px * A, seed=3)
+    freq = synth.synth_freq(nf)
+    re, im, w = synth.synth_data(nuv, nf)
+    data = Visibilities(u, v, freq, re, im, w)
+    base = synth.synth_image(n, nf, px)[:, :, :, 0]
+    cubes = np.stack([base * rng.uniform(0.5, 1.5) + 1e-3 * rng.random(base.shape) for _ in range(W)])
+    dra, ddec = rng.uniform(-0.05, 0.05, W), rng.uniform(-0.05, 0.05, W)
+    m0 = synth.SynthImage(np.ascontiguousarray(cubes[0][:, :, :, None]), px, freq)
+    pxm = m0.x[1] - m0.x[0]                         # what the single call derives dxy from (an ulp from px)
+    pdspy_b200.set_dft_kernel(kernel)
+    try:
+        ll = loglike_images(data, cubes, dra, ddec, pixelsize=pxm)
+        again = loglike_images(data, cubes, dra, ddec, pixelsize=pxm)
+        for k in range(W):
+            m = synth.SynthImage(np.ascontiguousarray(cubes[k][:, :, :, None]), px, freq)
+            one, _ = loglike_image(data, m, dRA=dra[k], dDec=ddec[k])
+            assert ll[k] == one and again[k] == one
+        assert len(set(ll.tolist())) == W
+    finally:
+        pdspy_b200.set_dft_kernel("fp32")
+
+
 def test_lnlike_signature_with_injected_model_runner(gpu):
     """utils.emcee.lnlike keeps the reference's signature (emcee.py:6-9); the model runner
     (RADMC-3D orchestration, out of scope) is injected."""
