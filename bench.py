@@ -353,11 +353,22 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
     _lib, L, rank, world = env._lib, env.L, env.rank, env.world
     n, nf, nuv = cfg["npix"], cfg["nf"], cfg["nuv"]
     u, v = synth.synth_uv(nuv, cfg["pixelsize"] * A)
-    rows, re, im, w = synth.synth_data_shard(nuv, nf, rank, world)
-    assert np.array_equal(rows, pdist.shard_rows(u, v, rank, world))
+    # the FFT-based kernel transforms the cube per channel: over several GPUs its channels are split as far as the
+    # fused sampler allows (>= 16 channels per rank) and the uv points over what is left of the ranks; the
+    # direct-sum kernels split the uv points only (their per-uv phase work is shared by all channels)
+    cw = 1
+    if dft == "nufft":
+        while cw * 2 <= world and world % (cw * 2) == 0 and nf % (cw * 2) == 0 and nf // (cw * 2) >= 16:
+            cw *= 2
+    uw, crank, urank = world // cw, rank % cw, rank // cw
+    rows, re, im, w = synth.synth_data_shard(nuv, nf, urank, uw)
+    assert np.array_equal(rows, pdist.shard_rows(u, v, urank, uw))
     freq = synth.synth_freq(nf)
-    shard = Visibilities(np.ascontiguousarray(u[rows]), np.ascontiguousarray(v[rows]), freq, re, im, w)
-    like = ShardedLikelihood(shard)
+    c0, c1 = pdist.shard_channels(nf, crank, cw)
+    if cw > 1:
+        re, im, w = (np.ascontiguousarray(x[:, c0:c1]) for x in (re, im, w))
+    shard = Visibilities(np.ascontiguousarray(u[rows]), np.ascontiguousarray(v[rows]), freq[c0:c1], re, im, w)
+    like = ShardedLikelihood(shard, channels=(c0, nf) if cw > 1 else None)
     del re, im, w, shard
     cube = np.ascontiguousarray(synth.synth_image(n, nf, cfg["pixelsize"])[:, :, :, 0])     # [n, n, nf] fp64
     dxy, dra, ddec = cfg["pixelsize"] * A, cfg["dRA"] * A, cfg["dDec"] * A
@@ -404,7 +415,9 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
         hermitian = like.ds.hermitian
         pairs_launch = float(n) * n * nf * like.ds.nuv                    # this rank's share, per launch
         h2d = int(cube.nbytes) if shard_upload or world == 1 else int(cube.nbytes) * world
-        res = {"dft_kernel": dft, "ms_per_step": total_ms / steps, "value": pairs_step * steps / (total_ms * 1e-3),
+        res = {"dft_kernel": dft,
+               "partition_used": ("%d channel group(s) x %d uv shard(s)" % (cw, uw)) if cw > 1 else "%d uv shard(s)" % world,
+               "ms_per_step": total_ms / steps, "value": pairs_step * steps / (total_ms * 1e-3),
                "unit": UNIT, "likelihood_evals_per_s": steps / (total_ms * 1e-3), "steps": steps,
                "lnlike": ll, "lnlike_rel_diff_vs_fp64_kernel": abs(ll - ll_f64) / abs(ll_f64),
                "lnlike_rel_diff_vs_single_rank": (abs(ll - ll_single) / abs(ll_single)) if ll_single is not None else None,
@@ -444,14 +457,15 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
                 hbm = pk.get("hbm_gbs", 6650.0)
                 t_ms, t_n = env.profile(b"rfft2_planes")
                 path_ms = k_ms + (t_ms / t_n if t_n else 0.0)
-                alg = float(cube.nbytes) + 24.0 * like.ds.nuv * nf
+                alg = float(cube.nbytes) * like.nf_local / nf + 24.0 * like.ds.nuv * like.nf_local
                 res["roofline"] = {
                     "kernel": "NUFFT path: rfft2_planes_padded (deapodised, zero-padded half-spectrum FFT of every channel) + "
                               "nufft_chi2_tiled_kernel<2> (8 x 8 taps per unique uv point and channel from shared memory, "
                               "chi^2 per channel summed in the same kernel)",
                     "bound": "hbm", "achieved": alg / (path_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                     "frac": alg / (path_ms * 1e-3) / 1e9 / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
-                    "algorithmic_bytes_note": "fp64 cube read once + real, imag, weights of this rank's shard read once",
+                    "algorithmic_bytes_note": "this rank's channels of the fp64 cube read once + real, imag, weights of "
+                                              "its shard read once",
                     "launch_ms": path_ms, "sampler_ms": k_ms, "transform_ms": (t_ms / t_n if t_n else None), "launches": k_n}
             else:
                 # 3 fp16 MACs (hi.lo, lo.hi, hi.hi) per pixel-visibility pair actually evaluated
@@ -472,7 +486,8 @@ def likelihood_leg(env, cfg, dft, steps, warmup, main=False, cpu_baseline=False)
             res["roofline"]["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
                                                  "capture of this launch, read from profiles/traffic.json; null where "
                                                  "that (workload, kernel, N) was not captured")
-            res["roofline"]["algorithmic_bytes"] = (float(cube.nbytes) + 24.0 * like.ds.nuv * nf if dft == "nufft" else
+            res["roofline"]["algorithmic_bytes"] = (float(cube.nbytes) * like.nf_local / nf + 24.0 * like.ds.nuv * like.nf_local
+                                                    if dft == "nufft" else
                                                     float(n) * n * nf * 4 + like.ds.nuv_unique * 16.0 * (1 + nf))
         if cpu_baseline:
             res["cpu_baseline"] = cpu_baseline_port(cfg)

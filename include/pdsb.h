@@ -287,6 +287,12 @@ int pdsb_channel_postprocess(const double *image, int64_t npix, int nf_in, int s
 int pdsb_channel_postprocess_scaled(const double *image, int64_t npix, int nf_in, int subsample, int hanning,
                                     int averaging, const double *in_scale, int kind, double *out);
 
+/* Channels [c0, c0 + nf_out) of a cube image [npix, nf_in] (HOST or DEVICE, `kind`) as a compact DEVICE array
+ * out_dev [npix, nf_out]: the cube a rank evaluates when the likelihood is partitioned over the box by frequency
+ * channels (BASELINE.json north_star; pdspy_b200.dist.ShardedLikelihood(channels=...)).  The reference's per-channel
+ * loop (pdspy/interferometry/interpolate_model.py:22-30) is what makes channels independent units. */
+int pdsb_channel_slice(const double *image, int kind, int64_t npix, int nf_in, int c0, int nf_out, double *out_dev);
+
 /* Piecewise-linear regridding of an unstructured image (interpolate_model code="galario-unstructured",
  * pdspy/interferometry/interpolate_model.py:32-47; the scattered images of Model.py:536-558): values
  * [npts, nf]; per output pixel the three vertices of its Delaunay triangle tri [npix, 3] (tri[p,0] < 0:

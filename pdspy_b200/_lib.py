@@ -86,6 +86,7 @@ SIGNATURES = {
     "pdsb_regrid_linear": [_P, _c_i64, _P, _P, _c_i64, _c_int, _c_dbl, _c_int, _P],
     "pdsb_channel_postprocess": [_P, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _P],
     "pdsb_channel_postprocess_scaled": [_P, _c_i64, _c_int, _c_int, _c_int, _c_int, _P, _c_int, _P],
+    "pdsb_channel_slice": [_P, _c_int, _c_i64, _c_int, _c_int, _c_int, _P],
     "pdsb_invert_image": [_P, _P, _P, _c_int, _c_int, _c_int, _P],
     "pdsb_mad_std": [_P, _c_i64, _c_int, ctypes.POINTER(_c_dbl)],
     "pdsb_clean_loop": [_P, _P, _c_int, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _c_dbl, _c_int, _P, _P,

@@ -12,6 +12,17 @@
 
 namespace pdsb {
 
+// out[p][c] = in[p][c0 + c]: the compact cube of a channel shard
+__global__ void __launch_bounds__(256) channel_slice_kernel(const double *__restrict__ in, double *__restrict__ out,
+                                                            int64_t npix, int nf_in, int c0, int nf_out)
+{
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= npix * nf_out) return;
+    const int64_t p = t / nf_out;
+    const int ch = (int)(t - p * nf_out);
+    out[t] = in[p * nf_in + c0 + ch];
+}
+
 // in_scale (device, [nf_in], may be null): per-INPUT-channel factor applied before step (1) - the reference's
 // extinction, image[:,:,i,:] *= extinction[i] (:286-299), which precedes the sub-sample mean and the smoothing
 // and does not commute with them.
@@ -111,6 +122,22 @@ int pdsb_regrid_linear(const double *values, int64_t npts, const int *tri, const
         PDSB_CHECK(copy_d2h(out, dout, (size_t)npix * nf * sizeof(double)));
         PDSB_CUDA(cudaStreamSynchronize(c.stream));
     }
+    return PDSB_OK;
+}
+
+int pdsb_channel_slice(const double *image, int kind, int64_t npix, int nf_in, int c0, int nf_out, double *out_dev)
+{
+    PDSB_CHECK(require_init());
+    Context &c = ctx();
+    PDSB_REQUIRE(npix >= 0 && nf_in > 0 && nf_out > 0 && c0 >= 0 && c0 + nf_out <= nf_in, "channel window");
+    if (npix == 0) return PDSB_OK;
+    PDSB_REQUIRE(image && out_dev, "arrays");
+    const void *p = nullptr;
+    PDSB_CHECK(to_device(image, kind, (size_t)npix * nf_in * sizeof(double), c.img64, &p));
+    LaunchScope ls("channel_slice");
+    channel_slice_kernel<<<ceil_div(npix * nf_out, 256), 256, 0, c.stream>>>(static_cast<const double *>(p), out_dev, npix,
+                                                                           nf_in, c0, nf_out);
+    PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }
 

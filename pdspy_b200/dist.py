@@ -3,6 +3,10 @@
 One process per GPU.  The uv list is split across ranks; every rank holds the whole image cube
 (it is small: 67 MB fp32 for 512^2 x 64) and computes chi^2[nf] over its uv shard; the only
 exchange is one all-reduce of nf + 1 doubles (chi^2 per channel and the data-only log term).
+Alternatively the FREQUENCY CHANNELS are split (by="channels"): every rank holds all uv points of its
+channels and evaluates only its channels of the cube - the partition that also divides the per-cube
+work of the FFT-based kernels (the transform is per channel), which the uv split replicates on
+every rank.  The exchange is the same all-reduce.
 Walker batches are split by walker and need no reduction at all.
 
 Host logic only: works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU
@@ -38,9 +42,22 @@ def shard_rows(u, v, rank, world):
     return np.arange(s, e)
 
 
-def shard_visibilities(data, rank, world):
-    """This rank's part of a Visibilities-like object (u, v, freq, real, imag, weights)."""
+def shard_channels(nf, rank, world):
+    """[c0, c1) of this rank's contiguous block of the nf frequency channels (may be empty when world > nf)."""
+    return shard_bounds(nf, rank, world)
+
+
+def shard_visibilities(data, rank, world, by="uv"):
+    """This rank's part of a Visibilities-like object (u, v, freq, real, imag, weights): a block of uv rows
+    (by="uv", Hermitian pairs kept together) or all rows of a block of channels (by="channels")."""
     from .interferometry import Visibilities
+    if by == "channels":
+        c0, c1 = shard_channels(len(data.freq), rank, world)
+        return Visibilities(np.ascontiguousarray(data.u), np.ascontiguousarray(data.v),
+                            np.ascontiguousarray(data.freq[c0:c1]), np.ascontiguousarray(data.real[:, c0:c1]),
+                            np.ascontiguousarray(data.imag[:, c0:c1]), np.ascontiguousarray(data.weights[:, c0:c1]))
+    if by != "uv":
+        raise ValueError("by must be 'uv' or 'channels'")
     rows = shard_rows(data.u, data.v, rank, world)
     return Visibilities(np.ascontiguousarray(data.u[rows]), np.ascontiguousarray(data.v[rows]), data.freq,
                         np.ascontiguousarray(data.real[rows]), np.ascontiguousarray(data.imag[rows]),
@@ -69,9 +86,16 @@ class ShardedLikelihood:
 
         like = ShardedLikelihood(shard_visibilities(data, rank, world))
         lnlike = like(image_cube, dxy_rad, dRA_rad, dDec_rad)      # same value on every rank
+
+    Channel partition: the shard holds all uv points of channels [c0, c0 + nf_local) of cubes with nf_total
+    channels; every call slices those channels out of the cube on the device (pdsb_channel_slice) and writes
+    its chi^2 into its own window of the nf_total + 1 doubles that are all-reduced:
+
+        c0, c1 = shard_channels(nf_total, rank, world)
+        like = ShardedLikelihood(shard_visibilities(data, rank, world, by="channels"), channels=(c0, nf_total))
     """
 
-    def __init__(self, data_shard, group=None):
+    def __init__(self, data_shard, group=None, channels=None):
         import ctypes
         import torch
         from . import _lib
@@ -83,10 +107,18 @@ class ShardedLikelihood:
         # run libpdsb on torch's current stream so the collective is ordered behind the kernels
         _lib.check(self.L.pdsb_set_stream(torch.cuda.current_stream().cuda_stream))
         self.ds = Dataset(data_shard.u, data_shard.v)
-        self.ds.set_data(data_shard.real, data_shard.imag, data_shard.weights)
-        self.nf = data_shard.real.shape[1]
-        ls = ctypes.c_double()
-        _lib.check(self.L.pdsb_dataset_logsum(self.ds.handle, ctypes.byref(ls)))
+        if data_shard.real.shape[1] > 0:                     # (a channel shard is empty when world > nf)
+            self.ds.set_data(data_shard.real, data_shard.imag, data_shard.weights)
+        self.nf_local = data_shard.real.shape[1]
+        self.c0, self.nf = (0, self.nf_local) if channels is None else (int(channels[0]), int(channels[1]))
+        self.channels = channels is not None
+        if self.c0 < 0 or self.c0 + self.nf_local > self.nf:
+            raise ValueError("channel window [%d, %d) outside the cube's %d channels" % (self.c0, self.c0 + self.nf_local,
+                                                                                         self.nf))
+        self._slice = None
+        ls = ctypes.c_double(0.0)
+        if self.nf_local > 0:
+            _lib.check(self.L.pdsb_dataset_logsum(self.ds.handle, ctypes.byref(ls)))
         self.logsum = ls.value
         self.buf = torch.zeros(self.nf + 1, dtype=torch.float64, device="cuda")
         self.logsum_dev = torch.tensor([ls.value], dtype=torch.float64, device="cuda")
@@ -94,6 +126,19 @@ class ShardedLikelihood:
     def chi2_device(self, image, ny, nx, kind, dxy, dRA, dDec):
         """Launch the local part; result (chi2[nf], logsum) stays in self.buf on the device."""
         _lib = self._lib
+        if self.channels:
+            # this rank's channels of the cube, compact on the device; chi^2 into its window of the reduced vector
+            self.buf.zero_()
+            if self.nf_local > 0:
+                if self._slice is None or self._slice.numel() != ny * nx * self.nf_local:
+                    self._slice = self.torch.empty(ny * nx * self.nf_local, dtype=self.torch.float64, device="cuda")
+                _lib.check(self.L.pdsb_channel_slice(_lib.ptr(image), kind, ny * nx, self.nf, self.c0, self.nf_local,
+                                                     self._slice.data_ptr()))
+                _lib.check(self.L.pdsb_loglike_device(self.ds.handle, self._slice.data_ptr(), ny, nx, self.nf_local,
+                                                      _lib.DEVICE, float(dxy), float(dRA), float(dDec),
+                                                      self.buf.data_ptr() + 8 * self.c0))
+            self.buf[self.nf:].copy_(self.logsum_dev)
+            return self.buf
         _lib.check(self.L.pdsb_loglike_device(self.ds.handle, _lib.ptr(image), ny, nx, self.nf, kind, float(dxy),
                                               float(dRA), float(dDec), self.buf.data_ptr()))
         self.buf[self.nf:].copy_(self.logsum_dev)

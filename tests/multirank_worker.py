@@ -54,6 +54,17 @@ for kernel in ("fp32", "tcgen05", "nufft"):
     for mode, val in vals.items():
         check("sharded likelihood (%s, cube=%s) == single GPU" % (kernel, mode), abs(val - single) <= 1e-12 * abs(single),
               "rel %.1e" % (abs(val - single) / abs(single)))
+# ---- (e1') the same data set split by frequency channels (the partition that also divides the FFT-based kernels' transform) ----
+c0, c1 = pdist.shard_channels(c["nf"], rank, world)
+likec = pdist.ShardedLikelihood(pdist.shard_visibilities(data, rank, world, by="channels"), channels=(c0, c["nf"]))
+for kernel in ("fp32", "nufft"):
+    _lib.check(_lib.lib().pdsb_set_dft_variant({"fp32": 0, "nufft": 400}[kernel]))
+    single, _ = loglike_image(data, c["model"], dRA=c["dRA"], dDec=c["dDec"])
+    for mode in (None, "sharded"):
+        val = likec(cube, dxy, c["dRA"] * A, c["dDec"] * A, kind=0, cube=mode)
+        check("channel-sharded likelihood (%s, cube=%s) == single GPU" % (kernel, mode), abs(val - single) <= 1e-12 * abs(single),
+              "rel %.1e" % (abs(val - single) / abs(single)))
+likec.ds.destroy()
 _lib.check(_lib.lib().pdsb_set_dft_variant(0))
 
 # ---- (e2) walker batch: walkers split over the ranks, gathered, against single calls ----

@@ -40,6 +40,23 @@ def test_shards_partition_the_rows_and_stay_hermitian(world, hermitian):
     assert max(sizes) - min(sizes) <= 2
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_channel_shards_partition_the_channels(world):
+    d = _data(400, 5)
+    cols = []
+    for r in range(world):
+        c0, c1 = pdist.shard_channels(5, r, world)
+        s = pdist.shard_visibilities(d, r, world, by="channels")
+        assert s.real.shape == (400, c1 - c0) and s.real.flags.c_contiguous
+        np.testing.assert_array_equal(s.u, d.u)
+        np.testing.assert_array_equal(s.freq, d.freq[c0:c1])
+        np.testing.assert_array_equal(s.weights, d.weights[:, c0:c1])
+        cols.extend(range(c0, c1))
+    assert cols == list(range(5))                 # world = 8 > nf = 5: three ranks hold nothing
+    with pytest.raises(ValueError):
+        pdist.shard_visibilities(d, 0, world, by="rows")
+
+
 def test_shard_bounds_edge_cases():
     assert pdist.shard_bounds(0, 0, 4) == (0, 0)
     assert [pdist.shard_bounds(5, r, 4) for r in range(4)] == [(0, 2), (2, 3), (3, 4), (4, 5)]
@@ -72,6 +89,15 @@ def _worker(rank, world, port, q):
     t = torch.tensor(np.concatenate([chi2, [logsum]]))
     ll = pdist.combine_lnlike(t)
     full = ol.lnlike_vis_numpy(d.real, d.imag, d.weights, m_re, m_im)
+    # the same data set split by channels: every rank fills its window of the nf + 1 reduced doubles
+    c0, c1 = pdist.shard_channels(d.real.shape[1], rank, world)
+    sc = pdist.shard_visibilities(d, rank, world, by="channels")
+    tc = np.zeros(d.real.shape[1] + 1)
+    tc[c0:c1] = ol.chi2_per_channel_numpy(sc.real, sc.imag, sc.weights, m_re[:, c0:c1], m_im[:, c0:c1])
+    goodc = sc.weights > 0
+    tc[-1] = np.sum(np.log(sc.weights[goodc] / (2 * np.pi)))
+    llc = pdist.combine_lnlike(torch.tensor(tc))
+    assert abs(llc - full) <= 1e-12 * abs(full)
     q.put((rank, ll, full))
     dist.destroy_process_group()
 

@@ -215,6 +215,50 @@ def test_sharded_likelihood_single_rank_and_cube_staging(gpu):
     assert all(abs(x - ll0) <= 1e-12 * abs(ll0) for x in vals), (vals, ll0)
 
 
+@pytest.mark.parametrize("kernel", ["fp32", "nufft"])
+@pytest.mark.parametrize("world", [1, 3, 4])
+def test_channel_partition_emulated_on_one_gpu(gpu, kernel, world):
+    """ShardedLikelihood(channels=...) for every rank of a `world`-way channel split, run one after the other on
+    this GPU: the nf + 1 doubles the ranks would all-reduce sum to the unsharded likelihood, each rank's chi^2 sits
+    in its own channel window, and pdsb_channel_slice hands out exactly the cube's channels."""
+    import pdspy_b200
+    import torch
+    from pdspy_b200 import dist as pdist
+    n, nf, nuv = 64, 32, 4000
+    u, v = synth.synth_uv(nuv, 0.03 * A)
+    re, im, w = synth.synth_data(nuv, nf)
+    freq = synth.synth_freq(nf)
+    data = Visibilities(u, v, freq, re, im, w)
+    img = synth.synth_image(n, nf, 0.03) + 1e-4
+    m = synth.SynthImage(img, 0.03, freq)
+    cube = np.ascontiguousarray(img[:, :, :, 0])
+    dxy = (m.x[1] - m.x[0]) * A
+    pdspy_b200.set_dft_kernel(kernel)
+    try:
+        ll0, chi2_0 = loglike_image(data, m, dRA=0.02, dDec=-0.01)
+        total = torch.zeros(nf + 1, dtype=torch.float64, device="cuda")
+        for r in range(world):
+            c0, c1 = pdist.shard_channels(nf, r, world)
+            like = pdist.ShardedLikelihood(pdist.shard_visibilities(data, r, world, by="channels"), channels=(c0, nf))
+            buf = like.chi2_device(cube, n, n, _lib.HOST, dxy, 0.02 * A, -0.01 * A)
+            got = buf.cpu().numpy()
+            assert np.all(got[:c0] == 0) and np.all(got[c1:nf] == 0)
+            np.testing.assert_allclose(got[c0:c1], chi2_0[c0:c1], rtol=1e-12)
+            sl = like._slice.cpu().numpy().reshape(n, n, c1 - c0)
+            assert np.array_equal(sl, cube[:, :, c0:c1])
+            total += buf
+            like.ds.destroy()
+        t = total.cpu().numpy()
+        ll = -0.5 * t[:-1].sum() - 2.0 * t[-1]
+        assert abs(ll - ll0) <= 1e-12 * abs(ll0)
+    finally:
+        pdspy_b200.set_dft_kernel("fp32")
+        _lib.check(gpu.pdsb_reset_stream())
+    with pytest.raises(ValueError):
+        pdist.ShardedLikelihood(pdist.shard_visibilities(data, 0, 2, by="channels"), channels=(20, nf))
+    _lib.check(gpu.pdsb_reset_stream())
+
+
 def test_unchanged_signature_chain_stays_on_the_device(gpu):
     """interpolate_model(...) -> utils.visibility_lnlike(data, model) (what utils.emcee.lnlike runs, emcee.py:31-43):
     the model visibilities are consumed from the device; reading them afterwards, or pickling the object, gives
