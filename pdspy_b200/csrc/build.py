@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libpdsb.so")
 SOURCES = ["runtime.cu", "dft.cu", "dft_tc5.cu", "dft_f64.cu", "trift.cu", "vis.cu", "grid.cu", "grid_fast.cu", "fft.cu", "cube.cu", "clean.cu"]
-HEADERS = ["common.cuh", "dft.cuh", "grid.cuh", os.path.join("..", "..", "include", "pdsb.h")]
+HEADERS = ["common.cuh", "dft.cuh", "grid.cuh", "fft_r16.cuh", os.path.join("..", "..", "include", "pdsb.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

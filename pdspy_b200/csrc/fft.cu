@@ -7,6 +7,7 @@
 // power of two (the reference takes any imsize: scipy's ifft2) go through Bluestein's chirp-z form of the
 // same row transform on the next power of two >= 2n - 1 (bluestein_rows_kernel).
 #include "common.cuh"
+#include "fft_r16.cuh"
 #include <algorithm>
 
 namespace pdsb {
@@ -432,6 +433,163 @@ __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restric
     }
 }
 
+// ---- the same two passes with the transforms held in registers (fft_r16.cuh), 256 <= n <= 2048 ----
+// A block of 256 threads works on F = 4096 / n transforms (n / 16 threads each): 2 image rows x F / 2 channel pairs
+// (row pass), F planes (column pass).  The first pass reads the cube / T straight into registers (16 independent loads
+// in flight per thread), the data goes through shared memory once per later pass, and the results leave through the
+// shared row once more so that the stores are the same contiguous runs as in the kernels above.
+// Rows of the shared buffer are rowlen(n) + 8 / F slots apart, so that the plane-fastest read-out is conflict-free too.
+__host__ __device__ __forceinline__ int r16_rowstride(int n)
+{
+    const int F = 4096 / n;
+    return r16::rowlen(n) + (F >= 8 ? 1 : 8 / F);
+}
+
+// all passes but the first read phase: v holds the transform's input (element t + k n/16 in v[k]); on return the
+// spectrum is in x (natural order, slot()-padded).  Every thread of the block must call this (barriers inside).
+template <int RL>
+__device__ __forceinline__ void r16_transform(double2 *x, const double2 *__restrict__ tw, int n, int logn, int t, double2 *v)
+{
+    int Ns = 1;
+    const int full = r16::full_passes(logn);
+    for (int p = 0; p < full; p++) {
+        if (p > 0) {
+            r16::pass_load<16>(x, n, t, v);
+            __syncthreads();
+        }
+        r16::pass_compute<16>(tw, n, Ns, t, v);
+        r16::pass_store<16>(x, n, Ns, t, v);
+        __syncthreads();
+        Ns <<= 4;
+    }
+    r16::pass_load<RL>(x, n, t, v);
+    __syncthreads();
+    r16::pass_compute<RL>(tw, n, Ns, t, v);
+    r16::pass_store<RL>(x, n, Ns, t, v);
+    __syncthreads();
+}
+
+template <int RL>
+__global__ void __launch_bounds__(256, 2) rfft_rows16_kernel(const double *__restrict__ cube, const double2 *__restrict__ twg,
+                                                             double2 *__restrict__ T, int n, int logn, int nf, int flip,
+                                                             int nsy, int nsx, const double *__restrict__ corr_y,
+                                                             const double *__restrict__ corr_x,
+                                                             const int *__restrict__ nonzero)
+{
+    extern __shared__ double2 srow[];
+    const int Tn = n >> 4, F = 256 / Tn, PBp = F >> 1;
+    const int h = n / 2, hsy = nsy / 2, hsx = nsx / 2, npair = (nf + 1) / 2;
+    const int pair0 = blockIdx.y * PBp;
+    const int pb_n = npair - pair0 < PBp ? npair - pair0 : PBp;         // pairs this block really has
+    const int f = threadIdx.x / Tn, t = threadIdx.x % Tn;
+    const int rb = f / PBp, pb = f % PBp;                               // transform f = (row rb, pair pb)
+    const int rho0 = 2 * blockIdx.x, rho = rho0 + rb;
+    const int rs = r16_rowstride(n);
+    double2 *x = srow + (size_t)f * rs;
+    double2 v[16];
+    {
+        const bool live = pb < pb_n && rho < nsy;
+        const int plane = 2 * (pair0 + pb);
+        const bool second = plane + 1 < nf;
+        const bool vec = second && (nf & 1) == 0 && (reinterpret_cast<uintptr_t>(cube) & 15) == 0;
+        const int64_t rowbase = (int64_t)(flip ? nsy - 1 - rho : rho) * nsx;
+        const double fy = live && corr_y ? corr_y[rho] : 1.0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int c = t + k * Tn;
+            const int gamma = (c < h ? c : c - n) + hsx;
+            double2 val = make_double2(0.0, 0.0);
+            if (live && gamma >= 0 && gamma < nsx) {
+                const int64_t src = (rowbase + gamma) * nf + plane;
+                if (vec) val = *reinterpret_cast<const double2 *>(cube + src);
+                else {
+                    val.x = cube[src];
+                    if (second) val.y = cube[src + 1];
+                }
+                if (corr_y) {
+                    const double fc = fy * corr_x[gamma];
+                    val.x *= fc;
+                    val.y *= fc;
+                }
+            }
+            v[k] = val;
+        }
+    }
+    r16_transform<RL>(x, twg, n, logn, t, v);
+    // separate the two planes of every pair; stores: row fastest (adjacent double2 of T), then b, then pair
+    const int64_t ps = (int64_t)(h + 1) * n;                            // plane stride of T
+    for (int q = 0; q < pb_n; q++)
+        for (int j = threadIdx.x; j < 2 * (h + 1); j += 256) {
+            const int r2 = j & 1, b = j >> 1;
+            if (rho0 + r2 >= nsy) continue;
+            const double2 *xr = srow + (size_t)(r2 * PBp + q) * rs;
+            const double2 z = xr[r16::slot(b)], zc = xr[r16::slot((n - b) & (n - 1))];
+            const int plane = 2 * (pair0 + q);
+            const int64_t o = (int64_t)plane * ps + (int64_t)b * n + ((rho0 + r2 - hsy + n) & (n - 1));
+            const bool nz0 = nonzero[plane] != 0, nz1 = plane + 1 < nf && nonzero[plane + 1] != 0;
+            T[o] = !nz0 ? make_double2(0.0, 0.0) : !nz1 ? z : make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
+            if (plane + 1 < nf)
+                T[o + ps] = !nz1 ? make_double2(0.0, 0.0)
+                                 : !nz0 ? make_double2(z.y, -z.x) : make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
+        }
+}
+
+template <int RL>
+__global__ void __launch_bounds__(256, 2) rfft_cols16_kernel(const double2 *__restrict__ T, const double2 *__restrict__ twg,
+                                                             double2 *__restrict__ Yh, int n, int logn, int nf, int nsy)
+{
+    extern __shared__ double2 srow[];
+    const int Tn = n >> 4, F = 256 / Tn;
+    const int h = n / 2, hs = nsy / 2, b = blockIdx.x;
+    const int plane0 = blockIdx.y * F;
+    const int nfft = nf - plane0 < F ? nf - plane0 : F;
+    const int f = threadIdx.x / Tn, t = threadIdx.x % Tn;
+    const int rs = r16_rowstride(n);
+    double2 *x = srow + (size_t)f * rs;
+    const int64_t ps = (int64_t)(h + 1) * n;
+    double2 v[16];
+    {
+        const double2 *src = T + (int64_t)(plane0 + f) * ps + (int64_t)b * n;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int r = t + k * Tn;
+            const int R = r < h ? r : r - n;
+            v[k] = (f < nfft && R >= -hs && R < nsy - hs) ? src[r] : make_double2(0.0, 0.0);
+        }
+    }
+    r16_transform<RL>(x, twg, n, logn, t, v);
+    if (256 % nfft == 0) {                               // plane fastest (contiguous channels), no division in the loop
+        const int pl = threadIdx.x % nfft, astep = 256 / nfft;
+        for (int a = threadIdx.x / nfft; a < n; a += astep)
+            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * rs + r16::slot(a)];
+    } else {
+        for (int idx = threadIdx.x; idx < nfft * n; idx += 256) {
+            const int pl = idx % nfft, a = idx / nfft;
+            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * rs + r16::slot(a)];
+        }
+    }
+}
+
+template <int RL>
+static int launch_rfft16(const double *cube_dev, const double2 *tw, double2 *T, double2 *Yh, int n, int logn, int nf, int flip,
+                         int nsy, int nsx, const double *corr_y, const double *corr_x, const int *flags)
+{
+    Context &c = ctx();
+    const int F = 4096 / n, npair = (nf + 1) / 2;
+    const size_t smem = (size_t)F * r16_rowstride(n) * sizeof(double2);
+    static bool attr = false;
+    if (!attr) {
+        PDSB_CUDA(cudaFuncSetAttribute(rfft_rows16_kernel<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        PDSB_CUDA(cudaFuncSetAttribute(rfft_cols16_kernel<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr = true;
+    }
+    rfft_rows16_kernel<RL><<<dim3(nsy / 2, ceil_div(npair, F / 2)), 256, smem, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip,
+                                                                                         nsy, nsx, corr_y, corr_x, flags);
+    rfft_cols16_kernel<RL><<<dim3(n / 2 + 1, ceil_div(nf, F)), 256, smem, c.stream>>>(T, tw, Yh, n, logn, nf, nsy);
+    PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
+}
+
 // T: [nf][n/2 + 1][n] scratch, Yh: [n][n/2 + 1][nf].  nsy x nsx source planes (even sides) transformed at length
 // n >= max(nsy, nsx), a power of two (n = nsy = nsx: no padding); corr_y [nsy], corr_x [nsx]: per-axis pixel factors, or null.
 int rfft2_planes_padded(const double *cube_dev, int nsy, int nsx, int n, int nf, int flip, const double *corr_y,
@@ -476,6 +634,15 @@ int rfft2_planes_padded(const double *cube_dev, int nsy, int nsx, int n, int nf,
     PDSB_CUDA(cudaMemsetAsync(c.fft_flags.ptr, 0, (size_t)nf * sizeof(int), c.stream));
     plane_nonzero_kernel<<<nf * ceil_div(c.sm_count * 8, nf), 256, 0, c.stream>>>(cube_dev, (int64_t)nsy * nsx, nf,
                                                                                   c.fft_flags.as<int>());
+    if (n >= 256 && n <= 2048 && !getenv("PDSB_FFT_SMEM_PASSES")) {       // register-resident passes (fft_r16.cuh)
+        const int *fl = c.fft_flags.as<int>();
+        switch (r16::last_radix(logn)) {
+        case 2: return launch_rfft16<2>(cube_dev, tw, T, Yh, n, logn, nf, flip, nsy, nsx, corr_y, corr_x, fl);
+        case 4: return launch_rfft16<4>(cube_dev, tw, T, Yh, n, logn, nf, flip, nsy, nsx, corr_y, corr_x, fl);
+        case 8: return launch_rfft16<8>(cube_dev, tw, T, Yh, n, logn, nf, flip, nsy, nsx, corr_y, corr_x, fl);
+        default: return launch_rfft16<16>(cube_dev, tw, T, Yh, n, logn, nf, flip, nsy, nsx, corr_y, corr_x, fl);
+        }
+    }
     rfft_rows_kernel<<<dim3(nsy / 2, ceil_div(npair, pb0)), th0, sm0, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip, pb0,
                                                                                   tpf, nsy, nsx, corr_y, corr_x,
                                                                                   c.fft_flags.as<int>());

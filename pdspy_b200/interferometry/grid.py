@@ -5,6 +5,7 @@ Same names, arguments, defaults, return types and the same warning text.  The nu
 whose rounding is part of the reference result (numpy.linspace cell centres :370-381) stay
 numpy on the host; everything per-visibility runs in libpdsb (include/pdsb.h:pdsb_grid)."""
 import ctypes
+import threading
 
 import numpy
 
@@ -76,9 +77,16 @@ def grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", mfs=False, c
     else:
         uu = numpy.linspace(-(gridsize - 1) * binsize / 2, (gridsize - 1) * binsize / 2, gridsize)
         vv = numpy.linspace(-(gridsize - 1) * binsize / 2, (gridsize - 1) * binsize / 2, gridsize)
-    new_u, new_v = numpy.meshgrid(uu, vv)
-
     G2 = gridsize ** 2
+    # the [G, G] coordinate arrays of the result (:383): for large grids they are filled on a second host thread while
+    # pdsb_grid runs (ctypes releases the GIL; at G = 2048 the 67 MB cost as much host time as the whole device step)
+    mesh = []
+    filler = threading.Thread(target=lambda: mesh.extend(numpy.meshgrid(uu, vv))) if G2 >= 1 << 18 else None
+    if filler is not None:
+        filler.start()
+    else:
+        mesh.extend(numpy.meshgrid(uu, vv))
+
     new_real = numpy.empty((G2, nchannels))
     new_imag = numpy.empty((G2, nchannels))
     new_weights = numpy.empty((G2, nchannels))
@@ -88,13 +96,18 @@ def grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", mfs=False, c
     n_out = ctypes.c_int64(0)
 
     L = _lib.lib()
-    _lib.check(L.pdsb_grid(_lib.ptr(_lib.f64(u)), _lib.ptr(_lib.f64(v)), _lib.ptr(_lib.f64(freq)),
-                           _lib.ptr(_lib.f64(real)), _lib.ptr(_lib.f64(imag)), _lib.ptr(_lib.f64(weights)),
-                           nuv, nf, _lib.HOST, int(gridsize), float(binsize), _lib.ptr(uu), _lib.ptr(vv),
-                           _lib.CONV[convolution], wt, float(robust), int(npixels), _lib.MODE[mode],
-                           1 if imaging else 0, 1 if deterministic else 0,
-                           _lib.ptr(new_real), _lib.ptr(new_imag), _lib.ptr(new_weights),
-                           _lib.ptr(gi), _lib.ptr(gj), _lib.ptr(wmod), _lib.HOST, ctypes.byref(n_out)))
+    try:
+        _lib.check(L.pdsb_grid(_lib.ptr(_lib.f64(u)), _lib.ptr(_lib.f64(v)), _lib.ptr(_lib.f64(freq)),
+                               _lib.ptr(_lib.f64(real)), _lib.ptr(_lib.f64(imag)), _lib.ptr(_lib.f64(weights)),
+                               nuv, nf, _lib.HOST, int(gridsize), float(binsize), _lib.ptr(uu), _lib.ptr(vv),
+                               _lib.CONV[convolution], wt, float(robust), int(npixels), _lib.MODE[mode],
+                               1 if imaging else 0, 1 if deterministic else 0,
+                               _lib.ptr(new_real), _lib.ptr(new_imag), _lib.ptr(new_weights),
+                               _lib.ptr(gi), _lib.ptr(gj), _lib.ptr(wmod), _lib.HOST, ctypes.byref(n_out)))
+    finally:
+        if filler is not None:
+            filler.join()
+    new_u, new_v = mesh
     if n_out.value > 0:
         print(_WARNING)
 
