@@ -434,16 +434,13 @@ __global__ void __launch_bounds__(512) rfft_cols_kernel(const double2 *__restric
 }
 
 // ---- the same two passes with the transforms held in registers (fft_r16.cuh), 256 <= n <= 2048 ----
-// A block of 256 threads works on F = 4096 / n transforms (n / 16 threads each): 2 image rows x F / 2 channel pairs
-// (row pass), F planes (column pass).  The first pass reads the cube / T straight into registers (16 independent loads
+// A block of NT threads works on F = 16 NT / n transforms (n / 16 threads each): 2 image rows x F / 2 channel pairs
+// (row pass), F planes (column pass); blocks that share 32-byte sectors of the cube / of Yh (neighbouring channel groups)
+// are neighbours in launch order (blockIdx.x), so the halves meet in the L2.  The first pass reads the cube / T straight into registers (16 independent loads
 // in flight per thread), the data goes through shared memory once per later pass, and the results leave through the
 // shared row once more so that the stores are the same contiguous runs as in the kernels above.
 // Rows of the shared buffer are rowlen(n) + 8 / F slots apart, so that the plane-fastest read-out is conflict-free too.
-__host__ __device__ __forceinline__ int r16_rowstride(int n)
-{
-    const int F = 4096 / n;
-    return r16::rowlen(n) + (F >= 8 ? 1 : 8 / F);
-}
+__host__ __device__ __forceinline__ int r16_rowstride(int n, int F) { return r16::rowlen(n) + (F >= 8 ? 1 : 8 / F); }
 
 // all passes but the first read phase: v holds the transform's input (element t + k n/16 in v[k]); on return the
 // spectrum is in x (natural order, slot()-padded).  Every thread of the block must call this (barriers inside).
@@ -469,22 +466,22 @@ __device__ __forceinline__ void r16_transform(double2 *x, const double2 *__restr
     __syncthreads();
 }
 
-template <int RL>
-__global__ void __launch_bounds__(256, 2) rfft_rows16_kernel(const double *__restrict__ cube, const double2 *__restrict__ twg,
+template <int RL, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) rfft_rows16_kernel(const double *__restrict__ cube, const double2 *__restrict__ twg,
                                                              double2 *__restrict__ T, int n, int logn, int nf, int flip,
                                                              int nsy, int nsx, const double *__restrict__ corr_y,
                                                              const double *__restrict__ corr_x,
                                                              const int *__restrict__ nonzero)
 {
     extern __shared__ double2 srow[];
-    const int Tn = n >> 4, F = 256 / Tn, PBp = F >> 1;
+    const int Tn = n >> 4, F = NT / Tn, PBp = F >> 1;
     const int h = n / 2, hsy = nsy / 2, hsx = nsx / 2, npair = (nf + 1) / 2;
-    const int pair0 = blockIdx.y * PBp;
+    const int pair0 = blockIdx.x * PBp;
     const int pb_n = npair - pair0 < PBp ? npair - pair0 : PBp;         // pairs this block really has
     const int f = threadIdx.x / Tn, t = threadIdx.x % Tn;
     const int rb = f / PBp, pb = f % PBp;                               // transform f = (row rb, pair pb)
-    const int rho0 = 2 * blockIdx.x, rho = rho0 + rb;
-    const int rs = r16_rowstride(n);
+    const int rho0 = 2 * blockIdx.y, rho = rho0 + rb;
+    const int rs = r16_rowstride(n, F);
     double2 *x = srow + (size_t)f * rs;
     double2 v[16];
     {
@@ -519,7 +516,7 @@ __global__ void __launch_bounds__(256, 2) rfft_rows16_kernel(const double *__res
     // separate the two planes of every pair; stores: row fastest (adjacent double2 of T), then b, then pair
     const int64_t ps = (int64_t)(h + 1) * n;                            // plane stride of T
     for (int q = 0; q < pb_n; q++)
-        for (int j = threadIdx.x; j < 2 * (h + 1); j += 256) {
+        for (int j = threadIdx.x; j < 2 * (h + 1); j += NT) {
             const int r2 = j & 1, b = j >> 1;
             if (rho0 + r2 >= nsy) continue;
             const double2 *xr = srow + (size_t)(r2 * PBp + q) * rs;
@@ -534,17 +531,17 @@ __global__ void __launch_bounds__(256, 2) rfft_rows16_kernel(const double *__res
         }
 }
 
-template <int RL>
-__global__ void __launch_bounds__(256, 2) rfft_cols16_kernel(const double2 *__restrict__ T, const double2 *__restrict__ twg,
+template <int RL, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) rfft_cols16_kernel(const double2 *__restrict__ T, const double2 *__restrict__ twg,
                                                              double2 *__restrict__ Yh, int n, int logn, int nf, int nsy)
 {
     extern __shared__ double2 srow[];
-    const int Tn = n >> 4, F = 256 / Tn;
-    const int h = n / 2, hs = nsy / 2, b = blockIdx.x;
-    const int plane0 = blockIdx.y * F;
+    const int Tn = n >> 4, F = NT / Tn;
+    const int h = n / 2, hs = nsy / 2, b = blockIdx.y;
+    const int plane0 = blockIdx.x * F;
     const int nfft = nf - plane0 < F ? nf - plane0 : F;
     const int f = threadIdx.x / Tn, t = threadIdx.x % Tn;
-    const int rs = r16_rowstride(n);
+    const int rs = r16_rowstride(n, F);
     double2 *x = srow + (size_t)f * rs;
     const int64_t ps = (int64_t)(h + 1) * n;
     double2 v[16];
@@ -558,36 +555,49 @@ __global__ void __launch_bounds__(256, 2) rfft_cols16_kernel(const double2 *__re
         }
     }
     r16_transform<RL>(x, twg, n, logn, t, v);
-    if (256 % nfft == 0) {                               // plane fastest (contiguous channels), no division in the loop
-        const int pl = threadIdx.x % nfft, astep = 256 / nfft;
+    if (NT % nfft == 0) {                                // plane fastest (contiguous channels), no division in the loop
+        const int pl = threadIdx.x % nfft, astep = NT / nfft;
         for (int a = threadIdx.x / nfft; a < n; a += astep)
             Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * rs + r16::slot(a)];
     } else {
-        for (int idx = threadIdx.x; idx < nfft * n; idx += 256) {
+        for (int idx = threadIdx.x; idx < nfft * n; idx += NT) {
             const int pl = idx % nfft, a = idx / nfft;
             Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * rs + r16::slot(a)];
         }
     }
 }
 
+template <int RL, int NT>
+static int launch_rfft16_nt(const double *cube_dev, const double2 *tw, double2 *T, double2 *Yh, int n, int logn, int nf, int flip,
+                            int nsy, int nsx, const double *corr_y, const double *corr_x, const int *flags)
+{
+    Context &c = ctx();
+    const int F = 16 * NT / n, npair = (nf + 1) / 2;
+    const size_t smem = (size_t)F * r16_rowstride(n, F) * sizeof(double2);
+    static bool attr = false;
+    if (!attr) {
+        PDSB_CUDA(cudaFuncSetAttribute(rfft_rows16_kernel<RL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        PDSB_CUDA(cudaFuncSetAttribute(rfft_cols16_kernel<RL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr = true;
+    }
+    rfft_rows16_kernel<RL, NT><<<dim3(ceil_div(npair, F / 2), nsy / 2), NT, smem, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip,
+                                                                                            nsy, nsx, corr_y, corr_x, flags);
+    rfft_cols16_kernel<RL, NT><<<dim3(ceil_div(nf, F), n / 2 + 1), NT, smem, c.stream>>>(T, tw, Yh, n, logn, nf, nsy);
+    PDSB_CUDA(cudaGetLastError());
+    return PDSB_OK;
+}
+
+// threads per block: 128 (four blocks per SM in different phases of load / transform / store) while that still gives
+// the row pass its two rows (n <= 1024), else 256
 template <int RL>
 static int launch_rfft16(const double *cube_dev, const double2 *tw, double2 *T, double2 *Yh, int n, int logn, int nf, int flip,
                          int nsy, int nsx, const double *corr_y, const double *corr_x, const int *flags)
 {
-    Context &c = ctx();
-    const int F = 4096 / n, npair = (nf + 1) / 2;
-    const size_t smem = (size_t)F * r16_rowstride(n) * sizeof(double2);
-    static bool attr = false;
-    if (!attr) {
-        PDSB_CUDA(cudaFuncSetAttribute(rfft_rows16_kernel<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        PDSB_CUDA(cudaFuncSetAttribute(rfft_cols16_kernel<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
-    }
-    rfft_rows16_kernel<RL><<<dim3(nsy / 2, ceil_div(npair, F / 2)), 256, smem, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip,
-                                                                                         nsy, nsx, corr_y, corr_x, flags);
-    rfft_cols16_kernel<RL><<<dim3(n / 2 + 1, ceil_div(nf, F)), 256, smem, c.stream>>>(T, tw, Yh, n, logn, nf, nsy);
-    PDSB_CUDA(cudaGetLastError());
-    return PDSB_OK;
+    static const char *env = getenv("PDSB_FFT_NT");
+    const int nt = env ? atoi(env) : 128;
+    if (n <= 1024 && nt == 128)
+        return launch_rfft16_nt<RL, 128>(cube_dev, tw, T, Yh, n, logn, nf, flip, nsy, nsx, corr_y, corr_x, flags);
+    return launch_rfft16_nt<RL, 256>(cube_dev, tw, T, Yh, n, logn, nf, flip, nsy, nsx, corr_y, corr_x, flags);
 }
 
 // T: [nf][n/2 + 1][n] scratch, Yh: [n][n/2 + 1][nf].  nsy x nsx source planes (even sides) transformed at length
