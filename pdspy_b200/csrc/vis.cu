@@ -590,7 +590,10 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
                 const double uu = P.u[k], vv = P.v[k];
                 const double a = uu * P.dxy * (double)N, bb = vv * P.dxy * (double)N;
                 const double kx0 = ceil(a - 0.5 * NUFFT_W), ky0 = ceil(bb - 0.5 * NUFFT_W);
-                q.wx[t] = nufft_psi(a - (kx0 + t));
+                // wx carries the sign of the conjugation: a tap on the mirrored half (kx mod N > N/2) reads conj G[-ky][-kx];
+                // the staged patch holds G unconjugated, the weight is psi >= 0, so |wx| serves the real part
+                const double px = nufft_psi(a - (kx0 + t));
+                q.wx[t] = ((((int)kx0 + t) & (N - 1)) > h) ? -px : px;
                 q.wy[t] = nufft_psi(bb - (ky0 + t));
                 if (t == 0) {
                     q.kx0 = (int)kx0;
@@ -610,37 +613,42 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
         const int minx = box[0], miny = box[2];
         const int bw = box[1] - minx + NUFFT_W, bh = box[3] - miny + NUFFT_W;
         const bool staged = (int64_t)bw * bh <= NT_CAP;
-        for (int cg0 = 0; cg0 < P.nf; cg0 += NT_CG) {
+        // A box of at most NT_CAP / 2 cells (three batches in four on C3) leaves room for two patches: the next channel
+        // group's patch is then on its way (cp.async, no registers involved) while the current one is summed.
+        const bool dbl = staged && 2 * bw * bh <= NT_CAP;
+        // ---- stage the box of one channel group: thread = (cell, channel), channel fastest; wrap around the torus and
+        // the mirror of the half spectrum (row -ky, column N - kx) resolved in the source address, the conjugation of
+        // mirrored cells left to the weights' sign ----
+        auto stage = [&](int cg0, double2 *dst) {
+            const int ncell16 = bw * bh * NT_CG;
+            const float inv_bw = 1.0f / (float)bw;
+            for (int idx = tid; idx < ncell16; idx += 256) {
+                const int cell = idx / NT_CG, ch = idx % NT_CG;
+                if (cg0 + ch >= P.nf) continue;                      // never read
+                const int cy = (int)(((float)cell + 0.5f) * inv_bw), cx = cell - cy * bw;          // cell < 400: exact
+                int kxm = (minx + cx) & (N - 1);                     // N is a power of two
+                int ky = miny + cy;
+                if (kxm > h) {
+                    kxm = N - kxm;
+                    ky = -ky;
+                }
+                const int row = ((ky & (N - 1)) + h) & (N - 1);
+                const double2 *src = P.Yh + ((int64_t)row * (h + 1) + kxm) * P.nf + cg0 + ch;
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + idx);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        double2 *const buf1 = patch + (size_t)(NT_CAP / 2) * NT_CG;
+        if (staged) stage(0, patch);
+        for (int cg0 = 0, g = 0; cg0 < P.nf; cg0 += NT_CG, g++) {
+            const double2 *cur = dbl && (g & 1) ? buf1 : patch;
             if (staged) {
-                // ---- stage the box: thread = (cell, channel), channel fastest; four loads in flight per thread
-                // (issue is in order: a store right behind its load would serialise the round trips) ----
-                const int ncell16 = bw * bh * NT_CG;
-                const float inv_bw = 1.0f / (float)bw;
-                for (int idx0 = tid; idx0 < ncell16; idx0 += 4 * 256) {
-                    double2 val[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int idx = idx0 + j * 256;
-                        val[j] = make_double2(0.0, 0.0);
-                        if (idx >= ncell16) continue;
-                        const int cell = idx / NT_CG, ch = idx % NT_CG;
-                        const int cy = (int)(((float)cell + 0.5f) * inv_bw), cx = cell - cy * bw;      // cell < 400: exact
-                        int kxm = (minx + cx) & (N - 1);                 // N is a power of two
-                        int ky = miny + cy;
-                        const bool cj = kxm > h;
-                        if (cj) {
-                            kxm = N - kxm;
-                            ky = -ky;
-                        }
-                        const int row = ((ky & (N - 1)) + h) & (N - 1);
-                        if (cg0 + ch < P.nf) {
-                            val[j] = P.Yh[((int64_t)row * (h + 1) + kxm) * P.nf + cg0 + ch];
-                            if (cj) val[j].y = -val[j].y;
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (idx0 + j * 256 < ncell16) patch[idx0 + j * 256] = val[j];
+                if (dbl && cg0 + NT_CG < P.nf) {
+                    stage(cg0 + NT_CG, (g & 1) ? patch : buf1);      // free since the barrier that closed group g - 1
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
                 __syncthreads();
             }
@@ -668,7 +676,7 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
                     double wx[NUFFT_W];
 #pragma unroll
                     for (int t = 0; t < NUFFT_W; t++) wx[t] = q.wx[t];
-                    const double2 *base = patch + ((size_t)(q.ky0 - miny) * bw + (q.kx0 - minx)) * NT_CG + ch;
+                    const double2 *base = cur + ((size_t)(q.ky0 - miny) * bw + (q.kx0 - minx)) * NT_CG + ch;
                     double s_r = 0.0, s_i = 0.0;
 #pragma unroll
                     for (int ty = 0; ty < NUFFT_W; ty++) {
@@ -677,7 +685,7 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
 #pragma unroll
                         for (int tx = 0; tx < NUFFT_W; tx++) {
                             const double2 y = rowp[tx * NT_CG];
-                            tr = fma(wx[tx], y.x, tr);
+                            tr = fma(fabs(wx[tx]), y.x, tr);
                             ti = fma(wx[tx], y.y, ti);
                         }
                         const double wyv = q.wy[ty];
@@ -700,9 +708,9 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
                             const bool cj = kxm > h;
                             if (cj) kxm = N - kxm;
                             const double2 y = (cj ? rn : rp)[(int64_t)kxm * P.nf];
-                            const double wv = q.wx[tx];
-                            tr = fma(wv, y.x, tr);
-                            ti = fma(cj ? -wv : wv, y.y, ti);
+                            const double wv = q.wx[tx];              // signed like cj
+                            tr = fma(fabs(wv), y.x, tr);
+                            ti = fma(wv, y.y, ti);
                         }
                         const double wyv = q.wy[ty];
                         s_r = fma(wyv, tr, s_r);
@@ -727,6 +735,7 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
                 }
             }
             __syncthreads();                             // the patch (and pts / box at the last group) are free again
+            if (staged && !dbl && cg0 + NT_CG < P.nf) stage(cg0 + NT_CG, patch);
         }
     }
     if (PART) return;
