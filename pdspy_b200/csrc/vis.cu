@@ -549,7 +549,7 @@ struct NtPoint {
     int kx0, ky0;
     int64_t k;                                   // index of the unique point (-1: past the end of the list)
 };
-constexpr size_t NT_SMEM = (size_t)NT_CAP * NT_CG * sizeof(double2) + NT_PTS * sizeof(NtPoint) + 64;
+constexpr size_t NT_SMEM = (size_t)NT_CAP * NT_CG * sizeof(double2) + 2 * NT_PTS * sizeof(NtPoint) + 64;      // two (pts, box) slots
 
 // MODE 0: the two chi^2 sums of pdsb_loglike_nufft (real and imaginary part, all channels together).
 // MODE 1: instead of chi^2, write S (without the dRA / dDec phase) as the partial sums part[channel][unique uv] that
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
     extern __shared__ __align__(16) unsigned char nt_smem[];
     double2 *patch = reinterpret_cast<double2 *>(nt_smem);
     NtPoint *pts = reinterpret_cast<NtPoint *>(nt_smem + (size_t)NT_CAP * NT_CG * sizeof(double2));
-    int *box = reinterpret_cast<int *>(pts + NT_PTS);            // min kx0, max kx0, min ky0, max ky0
+    int *box = reinterpret_cast<int *>(pts + 2 * NT_PTS);        // per slot: min kx0, max kx0, min ky0, max ky0
     __shared__ double sh[8];
     const int tid = threadIdx.x;
     const int N = P.N, h = N / 2;
@@ -577,86 +577,114 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
     double accg[NT_MAXG];                        // MODE 2: this thread's channels tid % 16 + 16 g
 #pragma unroll
     for (int g = 0; g < NT_MAXG; g++) accg[g] = 0.0;
-    for (int64_t b = blockIdx.x; b < nbatch; b += gridDim.x) {
-        // ---- per-point part: thread = (point, tap) ----
-        if (tid < 4) box[tid] = (tid & 1) ? INT_MIN : INT_MAX;
-        __syncthreads();
+    // ---- per-point part of batch bb into a (pts, box) slot: thread = (point, tap); the box must have been reset ----
+    auto points = [&](int64_t bb, NtPoint *pp, int *bx) {
         for (int p = tid >> 3; p < NT_PTS; p += 32) {
             const int t = tid & 7;
-            const int64_t kk = b * NT_PTS + p;
-            NtPoint &q = pts[p];
+            const int64_t kk = bb * NT_PTS + p;
+            NtPoint &q = pp[p];
             if (kk < P.nuvh) {
                 const int64_t k = P.order ? P.order[kk] : kk;
                 const double uu = P.u[k], vv = P.v[k];
-                const double a = uu * P.dxy * (double)N, bb = vv * P.dxy * (double)N;
-                const double kx0 = ceil(a - 0.5 * NUFFT_W), ky0 = ceil(bb - 0.5 * NUFFT_W);
+                const double a = uu * P.dxy * (double)N, bb2 = vv * P.dxy * (double)N;
+                const double kx0 = ceil(a - 0.5 * NUFFT_W), ky0 = ceil(bb2 - 0.5 * NUFFT_W);
                 // wx carries the sign of the conjugation: a tap on the mirrored half (kx mod N > N/2) reads conj G[-ky][-kx];
                 // the staged patch holds G unconjugated, the weight is psi >= 0, so |wx| serves the real part
                 const double px = nufft_psi(a - (kx0 + t));
                 q.wx[t] = ((((int)kx0 + t) & (N - 1)) > h) ? -px : px;
-                q.wy[t] = nufft_psi(bb - (ky0 + t));
+                q.wy[t] = nufft_psi(bb2 - (ky0 + t));
                 if (t == 0) {
                     q.kx0 = (int)kx0;
                     q.ky0 = (int)ky0;
                     q.k = k;
                     sincos(kTwoPi * (uu * P.dRA + vv * P.dDec), &q.ps, &q.pc);
-                    atomicMin(&box[0], q.kx0);
-                    atomicMax(&box[1], q.kx0);
-                    atomicMin(&box[2], q.ky0);
-                    atomicMax(&box[3], q.ky0);
+                    atomicMin(&bx[0], q.kx0);
+                    atomicMax(&bx[1], q.kx0);
+                    atomicMin(&bx[2], q.ky0);
+                    atomicMax(&bx[3], q.ky0);
                 }
             } else if (t == 0) {
                 q.k = -1;
             }
         }
+    };
+    // ---- stage the box (minx, miny, bw x bh cells) of one channel group: thread = (cell, channel), channel fastest; wrap
+    // around the torus and the mirror of the half spectrum (row -ky, column N - kx) resolved in the source address, the
+    // conjugation of mirrored cells left to the weights' sign; cp.async: no registers involved, one commit group ----
+    auto stage = [&](int minx, int miny, int bw, int bh, int cg0, double2 *dst) {
+        const int ncell16 = bw * bh * NT_CG;
+        const float inv_bw = 1.0f / (float)bw;
+        for (int idx = tid; idx < ncell16; idx += 256) {
+            const int cell = idx / NT_CG, ch = idx % NT_CG;
+            if (cg0 + ch >= P.nf) continue;                          // never read
+            const int cy = (int)(((float)cell + 0.5f) * inv_bw), cx = cell - cy * bw;              // cell < 400: exact
+            int kxm = (minx + cx) & (N - 1);                         // N is a power of two
+            int ky = miny + cy;
+            if (kxm > h) {
+                kxm = N - kxm;
+                ky = -ky;
+            }
+            const int row = ((ky & (N - 1)) + h) & (N - 1);
+            const double2 *src = P.Yh + ((int64_t)row * (h + 1) + kxm) * P.nf + cg0 + ch;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + idx);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double2 *const buf1 = patch + (size_t)(NT_CAP / 2) * NT_CG;
+    // Two (pts, box) slots: the per-point part of the NEXT batch of this block runs during the first channel group of the
+    // current one, and when both boxes fit half the patch buffer the next batch's first patch is requested before the
+    // current batch's last group is summed - the sampler then never waits for a patch except at its very first batch.
+    int slot = 0, par = 0;                               // par: which half holds channel group 0 of the current batch
+    bool prefetched = false;
+    if (blockIdx.x < nbatch) {
+        if (tid < 4) box[tid] = (tid & 1) ? INT_MIN : INT_MAX;
         __syncthreads();
-        const int minx = box[0], miny = box[2];
-        const int bw = box[1] - minx + NUFFT_W, bh = box[3] - miny + NUFFT_W;
+        points(blockIdx.x, pts, box);
+        __syncthreads();
+    }
+    for (int64_t b = blockIdx.x; b < nbatch; b += gridDim.x, slot ^= 1) {
+        const NtPoint *pcur = pts + slot * NT_PTS;
+        int *bnext = box + (slot ^ 1) * 4;
+        const int64_t bn = b + gridDim.x;
+        const bool has_next = bn < nbatch;
+        const int minx = box[slot * 4 + 0], miny = box[slot * 4 + 2];
+        const int bw = box[slot * 4 + 1] - minx + NUFFT_W, bh = box[slot * 4 + 3] - miny + NUFFT_W;
         const bool staged = (int64_t)bw * bh <= NT_CAP;
         // A box of at most NT_CAP / 2 cells (three batches in four on C3) leaves room for two patches: the next channel
-        // group's patch is then on its way (cp.async, no registers involved) while the current one is summed.
+        // group's patch is then on its way while the current one is summed.
         const bool dbl = staged && 2 * bw * bh <= NT_CAP;
-        // ---- stage the box of one channel group: thread = (cell, channel), channel fastest; wrap around the torus and
-        // the mirror of the half spectrum (row -ky, column N - kx) resolved in the source address, the conjugation of
-        // mirrored cells left to the weights' sign ----
-        auto stage = [&](int cg0, double2 *dst) {
-            const int ncell16 = bw * bh * NT_CG;
-            const float inv_bw = 1.0f / (float)bw;
-            for (int idx = tid; idx < ncell16; idx += 256) {
-                const int cell = idx / NT_CG, ch = idx % NT_CG;
-                if (cg0 + ch >= P.nf) continue;                      // never read
-                const int cy = (int)(((float)cell + 0.5f) * inv_bw), cx = cell - cy * bw;          // cell < 400: exact
-                int kxm = (minx + cx) & (N - 1);                     // N is a power of two
-                int ky = miny + cy;
-                if (kxm > h) {
-                    kxm = N - kxm;
-                    ky = -ky;
-                }
-                const int row = ((ky & (N - 1)) + h) & (N - 1);
-                const double2 *src = P.Yh + ((int64_t)row * (h + 1) + kxm) * P.nf + cg0 + ch;
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + idx);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        double2 *const buf1 = patch + (size_t)(NT_CAP / 2) * NT_CG;
-        if (staged) stage(0, patch);
+        if (tid < 4) bnext[tid] = (tid & 1) ? INT_MIN : INT_MAX;     // (its old content was consumed a batch ago)
+        if (staged && !prefetched) stage(minx, miny, bw, bh, 0, dbl && (par & 1) ? buf1 : patch);
+        bool prefetched_next = false;
+        const int G = (P.nf + NT_CG - 1) / NT_CG;
         for (int cg0 = 0, g = 0; cg0 < P.nf; cg0 += NT_CG, g++) {
-            const double2 *cur = dbl && (g & 1) ? buf1 : patch;
+            const double2 *cur = dbl && ((par + g) & 1) ? buf1 : patch;
             if (staged) {
-                if (dbl && cg0 + NT_CG < P.nf) {
-                    stage(cg0 + NT_CG, (g & 1) ? patch : buf1);      // free since the barrier that closed group g - 1
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                } else {
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                double2 *const other = ((par + g) & 1) ? patch : buf1;       // free since the barrier that closed group g - 1
+                bool more = false;
+                if (dbl && g + 1 < G) {
+                    stage(minx, miny, bw, bh, cg0 + NT_CG, other);
+                    more = true;
+                } else if (dbl && has_next && g >= 1) {
+                    // last group: the next batch's box is known since the barrier that closed group 0
+                    const int nminx = bnext[0], nminy = bnext[2];
+                    const int nbw = bnext[1] - nminx + NUFFT_W, nbh = bnext[3] - nminy + NUFFT_W;
+                    if (2 * (int64_t)nbw * nbh <= NT_CAP) {
+                        stage(nminx, nminy, nbw, nbh, 0, other);
+                        more = prefetched_next = true;
+                    }
                 }
-                __syncthreads();
+                if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
+            if (staged || g == 0) __syncthreads();       // patch of group g complete; the reset of the next box visible
+            if (g == 0 && has_next) points(bn, pts + (slot ^ 1) * NT_PTS, bnext);
             // ---- (point, channel) pairs: half-warp = point, lane = channel ----
 #pragma unroll 1
             for (int it = 0; it < NT_PTS * NT_CG / 256; it++) {
                 const int p = it * (256 / NT_CG) + tid / NT_CG, ch = tid % NT_CG, i = cg0 + ch;
-                const NtPoint &q = pts[p];
+                const NtPoint &q = pcur[p];
                 if (q.k < 0 || i >= P.nf) continue;
                 // the data of this (point, channel) and of its Hermitian twin: on their way while the taps are summed
                 const int64_t idx = q.k * P.nf + i, id2 = idx + P.nuvh * P.nf;
@@ -734,9 +762,11 @@ __global__ void __launch_bounds__(256, NT_MINB) nufft_chi2_tiled_kernel(const Nu
                     si += t_im;
                 }
             }
-            __syncthreads();                             // the patch (and pts / box at the last group) are free again
-            if (staged && !dbl && cg0 + NT_CG < P.nf) stage(cg0 + NT_CG, patch);
+            __syncthreads();                             // the patch of this group is free again
+            if (staged && !dbl && cg0 + NT_CG < P.nf) stage(minx, miny, bw, bh, cg0 + NT_CG, patch);
         }
+        par = (par + G) & 1;
+        prefetched = prefetched_next;
     }
     if (PART) return;
     if (MODE == 2) {
