@@ -342,9 +342,13 @@ __global__ void __launch_bounds__(256) fft_chi2_kernel(const FftSampleArgs P, in
     const int lg = threadIdx.x % gs;
     const bool twin = P.nuv > P.nuvh;
     const int64_t kstep = (int64_t)gridDim.x * (256 / gs);
-    for (int64_t kk = (int64_t)blockIdx.x * (256 / gs) + threadIdx.x / gs; kk < P.nuvh; kk += kstep) {
-        const int64_t k = P.order ? P.order[kk] : kk;
+    int64_t kk = (int64_t)blockIdx.x * (256 / gs) + threadIdx.x / gs;
+    int64_t knext = kk < P.nuvh ? (P.order ? P.order[kk] : kk) : 0;      // the visiting order is read one point ahead
+    for (; kk < P.nuvh; kk += kstep) {
+        const int64_t k = knext;
+        if (kk + kstep < P.nuvh) knext = P.order ? P.order[kk + kstep] : kk + kstep;
         const FftCorner q = fft_corner(P, k);
+#pragma unroll 2
         for (int i = lg; i < P.nf; i += gs) {
             const int64_t idx = k * P.nf + i, id2 = idx + P.nuvh * P.nf;
             // the 1.5 GB of data stream through once: evict-first, so that they do not push the transformed cube
