@@ -324,9 +324,19 @@ __global__ void __launch_bounds__(256) plane_nonzero_kernel(const double *__rest
                                                             int *__restrict__ flags)
 {
     const int64_t total = npix * nf, i0 = (int64_t)blockIdx.x * 256 + threadIdx.x, stride = (int64_t)gridDim.x * 256;
-    bool any = false;
-    for (int64_t i = i0; i < total; i += stride) any |= cube[i] != 0.0;
-    if (any) flags[(int)(i0 % nf)] = 1;                  // benign race: every writer stores 1
+    volatile int *flag = flags + (int)(i0 % nf);
+    // four loads in flight per thread; a plane is settled by its first non-zero value, whoever finds it: the other
+    // threads of that channel stop at their next look at the flag (an all-zero plane is the only one read in full)
+    for (int64_t i = i0; i < total; i += 4 * stride) {
+        if (*flag) return;
+        const double a = cube[i], b = i + stride < total ? cube[i + stride] : 0.0,
+                     c = i + 2 * stride < total ? cube[i + 2 * stride] : 0.0,
+                     d = i + 3 * stride < total ? cube[i + 3 * stride] : 0.0;
+        if (a != 0.0 || b != 0.0 || c != 0.0 || d != 0.0) {
+            *flag = 1;                                   // benign race: every writer stores 1
+            return;
+        }
+    }
 }
 
 // row pass: block = rows (rho, rho + 1), rho = 2 blockIdx.x, of the (row-flipped) source planes x plane pairs
