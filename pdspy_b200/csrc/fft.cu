@@ -324,19 +324,14 @@ __global__ void __launch_bounds__(256) plane_nonzero_kernel(const double *__rest
                                                             int *__restrict__ flags)
 {
     const int64_t total = npix * nf, i0 = (int64_t)blockIdx.x * 256 + threadIdx.x, stride = (int64_t)gridDim.x * 256;
-    volatile int *flag = flags + (int)(i0 % nf);
-    // four loads in flight per thread; a plane is settled by its first non-zero value, whoever finds it: the other
-    // threads of that channel stop at their next look at the flag (an all-zero plane is the only one read in full)
-    for (int64_t i = i0; i < total; i += 4 * stride) {
-        if (*flag) return;
-        const double a = cube[i], b = i + stride < total ? cube[i + stride] : 0.0,
-                     c = i + 2 * stride < total ? cube[i + 2 * stride] : 0.0,
-                     d = i + 3 * stride < total ? cube[i + 3 * stride] : 0.0;
-        if (a != 0.0 || b != 0.0 || c != 0.0 || d != 0.0) {
-            *flag = 1;                                   // benign race: every writer stores 1
-            return;
-        }
+    bool any = false;
+    int64_t i = i0;
+    for (; i + 3 * stride < total; i += 4 * stride) {    // four loads in flight per thread
+        const double a = cube[i], b = cube[i + stride], c = cube[i + 2 * stride], d = cube[i + 3 * stride];
+        any |= a != 0.0 || b != 0.0 || c != 0.0 || d != 0.0;
     }
+    for (; i < total; i += stride) any |= cube[i] != 0.0;
+    if (any) flags[(int)(i0 % nf)] = 1;                  // benign race: every writer stores 1
 }
 
 // row pass: block = rows (rho, rho + 1), rho = 2 blockIdx.x, of the (row-flipped) source planes x plane pairs
@@ -476,6 +471,9 @@ __device__ __forceinline__ void r16_transform(double2 *x, const double2 *__restr
     __syncthreads();
 }
 
+// Both kernels are persistent: a block takes the work items blockIdx.x, blockIdx.x + gridDim.x, ... and issues the 16 loads
+// of its NEXT item right after the transform of the current one (the registers are free then: the spectrum sits in shared
+// memory), so that they are in flight while the current item is separated / stored.
 template <int RL, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT) rfft_rows16_kernel(const double *__restrict__ cube, const double2 *__restrict__ twg,
                                                              double2 *__restrict__ T, int n, int logn, int nf, int flip,
@@ -486,19 +484,20 @@ __global__ void __launch_bounds__(NT, 512 / NT) rfft_rows16_kernel(const double 
     extern __shared__ double2 srow[];
     const int Tn = n >> 4, F = NT / Tn, PBp = F >> 1;
     const int h = n / 2, hsy = nsy / 2, hsx = nsx / 2, npair = (nf + 1) / 2;
-    const int pair0 = blockIdx.x * PBp;
-    const int pb_n = npair - pair0 < PBp ? npair - pair0 : PBp;         // pairs this block really has
+    const int npg = (npair + PBp - 1) / PBp;                            // pair groups; item = pair group + npg * row pair
+    const int nitems = npg * (nsy / 2);
     const int f = threadIdx.x / Tn, t = threadIdx.x % Tn;
     const int rb = f / PBp, pb = f % PBp;                               // transform f = (row rb, pair pb)
-    const int rho0 = 2 * blockIdx.y, rho = rho0 + rb;
     const int rs = r16_rowstride(n, F);
     double2 *x = srow + (size_t)f * rs;
+    const bool aligned = (nf & 1) == 0 && (reinterpret_cast<uintptr_t>(cube) & 15) == 0;
     double2 v[16];
-    {
-        const bool live = pb < pb_n && rho < nsy;
+    auto load_item = [&](int item) {
+        const int pair0 = (item % npg) * PBp, rho = 2 * (item / npg) + rb;
         const int plane = 2 * (pair0 + pb);
+        const bool live = pair0 + pb < npair && rho < nsy;
         const bool second = plane + 1 < nf;
-        const bool vec = second && (nf & 1) == 0 && (reinterpret_cast<uintptr_t>(cube) & 15) == 0;
+        const bool vec = second && aligned;
         const int64_t rowbase = (int64_t)(flip ? nsy - 1 - rho : rho) * nsx;
         const double fy = live && corr_y ? corr_y[rho] : 1.0;
 #pragma unroll
@@ -521,24 +520,31 @@ __global__ void __launch_bounds__(NT, 512 / NT) rfft_rows16_kernel(const double 
             }
             v[k] = val;
         }
-    }
-    r16_transform<RL>(x, twg, n, logn, t, v);
-    // separate the two planes of every pair; stores: row fastest (adjacent double2 of T), then b, then pair
+    };
     const int64_t ps = (int64_t)(h + 1) * n;                            // plane stride of T
-    for (int q = 0; q < pb_n; q++)
-        for (int j = threadIdx.x; j < 2 * (h + 1); j += NT) {
-            const int r2 = j & 1, b = j >> 1;
-            if (rho0 + r2 >= nsy) continue;
-            const double2 *xr = srow + (size_t)(r2 * PBp + q) * rs;
-            const double2 z = xr[r16::slot(b)], zc = xr[r16::slot((n - b) & (n - 1))];
-            const int plane = 2 * (pair0 + q);
-            const int64_t o = (int64_t)plane * ps + (int64_t)b * n + ((rho0 + r2 - hsy + n) & (n - 1));
-            const bool nz0 = nonzero[plane] != 0, nz1 = plane + 1 < nf && nonzero[plane + 1] != 0;
-            T[o] = !nz0 ? make_double2(0.0, 0.0) : !nz1 ? z : make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
-            if (plane + 1 < nf)
-                T[o + ps] = !nz1 ? make_double2(0.0, 0.0)
-                                 : !nz0 ? make_double2(z.y, -z.x) : make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
-        }
+    if ((int)blockIdx.x < nitems) load_item(blockIdx.x);
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        r16_transform<RL>(x, twg, n, logn, t, v);
+        if (item + (int)gridDim.x < nitems) load_item(item + gridDim.x);
+        // separate the two planes of every pair; stores: row fastest (adjacent double2 of T), then b, then pair
+        const int pair0 = (item % npg) * PBp, rho0 = 2 * (item / npg);
+        const int pb_n = npair - pair0 < PBp ? npair - pair0 : PBp;     // pairs this item really has
+        for (int q = 0; q < pb_n; q++)
+            for (int j = threadIdx.x; j < 2 * (h + 1); j += NT) {
+                const int r2 = j & 1, b = j >> 1;
+                if (rho0 + r2 >= nsy) continue;
+                const double2 *xr = srow + (size_t)(r2 * PBp + q) * rs;
+                const double2 z = xr[r16::slot(b)], zc = xr[r16::slot((n - b) & (n - 1))];
+                const int plane = 2 * (pair0 + q);
+                const int64_t o = (int64_t)plane * ps + (int64_t)b * n + ((rho0 + r2 - hsy + n) & (n - 1));
+                const bool nz0 = nonzero[plane] != 0, nz1 = plane + 1 < nf && nonzero[plane + 1] != 0;
+                T[o] = !nz0 ? make_double2(0.0, 0.0) : !nz1 ? z : make_double2(0.5 * (z.x + zc.x), 0.5 * (z.y - zc.y));
+                if (plane + 1 < nf)
+                    T[o + ps] = !nz1 ? make_double2(0.0, 0.0)
+                                     : !nz0 ? make_double2(z.y, -z.x) : make_double2(0.5 * (z.y + zc.y), -0.5 * (z.x - zc.x));
+            }
+        __syncthreads();                                 // the shared rows are free for the next item
+    }
 }
 
 template <int RL, int NT>
@@ -547,33 +553,41 @@ __global__ void __launch_bounds__(NT, 512 / NT) rfft_cols16_kernel(const double2
 {
     extern __shared__ double2 srow[];
     const int Tn = n >> 4, F = NT / Tn;
-    const int h = n / 2, hs = nsy / 2, b = blockIdx.y;
-    const int plane0 = blockIdx.x * F;
-    const int nfft = nf - plane0 < F ? nf - plane0 : F;
+    const int h = n / 2, hs = nsy / 2;
+    const int ngr = (nf + F - 1) / F;                                   // plane groups; item = plane group + ngr * b
+    const int nitems = ngr * (h + 1);
     const int f = threadIdx.x / Tn, t = threadIdx.x % Tn;
     const int rs = r16_rowstride(n, F);
     double2 *x = srow + (size_t)f * rs;
     const int64_t ps = (int64_t)(h + 1) * n;
     double2 v[16];
-    {
-        const double2 *src = T + (int64_t)(plane0 + f) * ps + (int64_t)b * n;
+    auto load_item = [&](int item) {
+        const int plane = (item % ngr) * F + f, b = item / ngr;
+        const double2 *src = T + (int64_t)plane * ps + (int64_t)b * n;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const int r = t + k * Tn;
             const int R = r < h ? r : r - n;
-            v[k] = (f < nfft && R >= -hs && R < nsy - hs) ? src[r] : make_double2(0.0, 0.0);
+            v[k] = (plane < nf && R >= -hs && R < nsy - hs) ? src[r] : make_double2(0.0, 0.0);
         }
-    }
-    r16_transform<RL>(x, twg, n, logn, t, v);
-    if (NT % nfft == 0) {                                // plane fastest (contiguous channels), no division in the loop
-        const int pl = threadIdx.x % nfft, astep = NT / nfft;
-        for (int a = threadIdx.x / nfft; a < n; a += astep)
-            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * rs + r16::slot(a)];
-    } else {
-        for (int idx = threadIdx.x; idx < nfft * n; idx += NT) {
-            const int pl = idx % nfft, a = idx / nfft;
-            Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * rs + r16::slot(a)];
+    };
+    if ((int)blockIdx.x < nitems) load_item(blockIdx.x);
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        r16_transform<RL>(x, twg, n, logn, t, v);
+        if (item + (int)gridDim.x < nitems) load_item(item + gridDim.x);
+        const int plane0 = (item % ngr) * F, b = item / ngr;
+        const int nfft = nf - plane0 < F ? nf - plane0 : F;
+        if (NT % nfft == 0) {                            // plane fastest (contiguous channels), no division in the loop
+            const int pl = threadIdx.x % nfft, astep = NT / nfft;
+            for (int a = threadIdx.x / nfft; a < n; a += astep)
+                Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * rs + r16::slot(a)];
+        } else {
+            for (int idx = threadIdx.x; idx < nfft * n; idx += NT) {
+                const int pl = idx % nfft, a = idx / nfft;
+                Yh[((int64_t)((a + h) & (n - 1)) * (h + 1) + b) * nf + plane0 + pl] = srow[(size_t)pl * rs + r16::slot(a)];
+            }
         }
+        __syncthreads();                                 // the shared rows are free for the next item
     }
 }
 
@@ -590,9 +604,13 @@ static int launch_rfft16_nt(const double *cube_dev, const double2 *tw, double2 *
         PDSB_CUDA(cudaFuncSetAttribute(rfft_cols16_kernel<RL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr = true;
     }
-    rfft_rows16_kernel<RL, NT><<<dim3(ceil_div(npair, F / 2), nsy / 2), NT, smem, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip,
-                                                                                            nsy, nsx, corr_y, corr_x, flags);
-    rfft_cols16_kernel<RL, NT><<<dim3(ceil_div(nf, F), n / 2 + 1), NT, smem, c.stream>>>(T, tw, Yh, n, logn, nf, nsy);
+    // persistent blocks (one wave, next-item loads under the current item's stores) once there are at least four items per
+    // block to balance; fewer items: one block each (measured: C3 transforms 4 - 5 % faster, C2's single plane 4 % slower)
+    const int wave = c.sm_count * (512 / NT);
+    const int items_r = ceil_div(npair, F / 2) * (nsy / 2), items_c = ceil_div(nf, F) * (n / 2 + 1);
+    rfft_rows16_kernel<RL, NT><<<items_r >= 4 * wave ? wave : items_r, NT, smem, c.stream>>>(cube_dev, tw, T, n, logn, nf, flip,
+                                                                                           nsy, nsx, corr_y, corr_x, flags);
+    rfft_cols16_kernel<RL, NT><<<items_c >= 4 * wave ? wave : items_c, NT, smem, c.stream>>>(T, tw, Yh, n, logn, nf, nsy);
     PDSB_CUDA(cudaGetLastError());
     return PDSB_OK;
 }

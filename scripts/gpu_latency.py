@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import pdspy_b200 as pb
 import synth
 from pdspy_b200.interferometry import interpolate_model, loglike_image, Visibilities
-for kern in ("fp32", "tcgen05"):
+for kern in ("fp32", "tcgen05", "nufft"):
     pb.set_dft_kernel(kern)
     for wl in ("C1", "C2"):
         c = synth.make_config(wl, nuv=None if wl == "C1" else 200_000)
