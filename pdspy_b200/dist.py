@@ -219,6 +219,24 @@ def _cell_centres(G, binsize):
     return uu, uu.copy()
 
 
+def _gridded_to_host(L, _lib, maps, G, nch, uu, vv):
+    """The three normalised device maps [3, G*G, nch] as host arrays (read back through libpdsb's multi-threaded pinned
+    ring straight into their final arrays) and the flattened coordinate arrays of the result (numpy.meshgrid,
+    libinterferometry.pyx:383, filled on a second host thread meanwhile)."""
+    import threading
+    mesh = []
+    filler = threading.Thread(target=lambda: mesh.extend(np.meshgrid(uu, vv)))
+    filler.start()
+    host = [np.empty((G * G, nch)) for _ in range(3)]
+    try:
+        for k in range(3):
+            _lib.check(L.pdsb_memcpy(_lib.ptr(host[k]), _lib.HOST, maps[k].data_ptr(), _lib.DEVICE, host[k].nbytes))
+        _lib.check(L.pdsb_synchronize())
+    finally:
+        filler.join()
+    return mesh[0].reshape(G * G), mesh[1].reshape(G * G), host
+
+
 def _reduced_weight_map(L, _lib, torch, dist, multi, group, arrays, nuv, nf, G, binsize, uu, vv, weighting, npixels, mode,
                         deterministic, nch):
     """First half of the re-weighting (libinterferometry.pyx:429-461) over all ranks: every rank box-sums the clamped
@@ -291,13 +309,11 @@ def sharded_grid(data_shard, gridsize=256, binsize=2000.0, convolution="pillbox"
         dist.all_reduce(nout, op=dist.ReduceOp.SUM, group=group)
     _lib.check(L.pdsb_grid_normalise(maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), G, nch,
                                      1 if imaging else 0))
-    host = maps.cpu().numpy()
+    new_u, new_v, host = _gridded_to_host(L, _lib, maps, G, nch, uu, vv)
     if int(nout.item()) > 0:
         print(_WARNING)
-    new_u, new_v = np.meshgrid(uu, vv)
     out_freq = np.array([freq.sum() / freq.size]) if mode == "continuum" else freq
-    return Visibilities(new_u.reshape(G * G), new_v.reshape(G * G), out_freq, np.ascontiguousarray(host[0]),
-                        np.ascontiguousarray(host[1]), np.ascontiguousarray(host[2]))
+    return Visibilities(new_u, new_v, out_freq, host[0], host[1], host[2])
 
 
 def band_rows(u, v, freq, gridsize, binsize, row_lo, row_hi, lo, hi, include_outside=False):
@@ -395,13 +411,11 @@ def banded_grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", imagi
         dist.all_reduce(nout, op=dist.ReduceOp.SUM, group=group)
     _lib.check(L.pdsb_grid_normalise(maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), G, nch,
                                      1 if imaging else 0))
-    host = maps.cpu().numpy()
+    new_u, new_v, host = _gridded_to_host(L, _lib, maps, G, nch, uu, vv)
     if int(nout.item()) > 0:
         print(_WARNING)
-    new_u, new_v = np.meshgrid(uu, vv)
     out_freq = np.array([freq.sum() / freq.size]) if mode == "continuum" else freq
-    return Visibilities(new_u.reshape(G * G), new_v.reshape(G * G), out_freq, np.ascontiguousarray(host[0]),
-                        np.ascontiguousarray(host[1]), np.ascontiguousarray(host[2]))
+    return Visibilities(new_u, new_v, out_freq, host[0], host[1], host[2])
 
 
 def banded_weight_map(data, gridsize, binsize, weighting, npixels, mode, band):
