@@ -1529,6 +1529,15 @@ int pdsb_sample_image_nufft(pdsb_dataset *ds, const double *image, int ny, int n
     PDSB_REQUIRE(ds && out_real && out_imag, "dataset/outputs");
     Context &c = ctx();
     if (ds->nuv == 0) return PDSB_OK;
+    if (nf >= NT_CG && ny > 0 && nx > 0 && ny % 2 == 0 && nx % 2 == 0 && ny <= 2048 && nx <= 2048 && !getenv("PDSB_NUFFT_DIRECT")) {
+        // cubes: the shared-memory-staged sampler (partial sums into the epilogue shared with the direct-sum kernels),
+        // the same route set_dft_kernel("nufft") takes
+        const int keep = c.dft_variant;
+        c.dft_variant = DFT_VARIANT_NUFFT;
+        const int rc = pdsb_sample_image(ds, image, ny, nx, nf, image_kind, dxy, dRA, dDec, out_real, out_imag, out_kind);
+        c.dft_variant = keep;
+        return rc;
+    }
     const size_t bytes = (size_t)ds->nuv * nf * sizeof(double);
     double *ore = out_real, *oim = out_imag;
     if (out_kind == PDSB_HOST) {
