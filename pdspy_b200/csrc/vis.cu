@@ -1178,7 +1178,10 @@ static int loglike_impl(pdsb_dataset *ds, const double *images, int nwalkers, in
             if (rc != PDSB_OK) {                                           // leave both streams idle before reporting
                 cudaStreamSynchronize(c.copy_stream);
                 cudaStreamSynchronize(c.stream);
-                if (rc == PDSB_ERR_CUDA) PDSB_CUDA(cudaGetLastError());
+                if (rc == PDSB_ERR_CUDA) {
+                    const cudaError_t e = cudaGetLastError();
+                    if (e != cudaSuccess) set_error("walker batch: %s", cudaGetErrorString(e));
+                }
                 return rc;
             }
         } else {

@@ -223,10 +223,8 @@ def _gridded_to_host(L, _lib, maps, G, nch, uu, vv):
     """The three normalised device maps [3, G*G, nch] as host arrays (read back through libpdsb's multi-threaded pinned
     ring straight into their final arrays) and the flattened coordinate arrays of the result (numpy.meshgrid,
     libinterferometry.pyx:383, filled on a second host thread meanwhile)."""
-    import threading
-    mesh = []
-    filler = threading.Thread(target=lambda: mesh.extend(np.meshgrid(uu, vv)))
-    filler.start()
+    from .interferometry.grid import MeshFiller
+    filler = MeshFiller(uu, vv)
     host = [np.empty((G * G, nch)) for _ in range(3)]
     try:
         for k in range(3):
@@ -234,7 +232,8 @@ def _gridded_to_host(L, _lib, maps, G, nch, uu, vv):
         _lib.check(L.pdsb_synchronize())
     finally:
         filler.join()
-    return mesh[0].reshape(G * G), mesh[1].reshape(G * G), host
+    new_u, new_v = filler.result()
+    return new_u.reshape(G * G), new_v.reshape(G * G), host
 
 
 def _reduced_weight_map(L, _lib, torch, dist, multi, group, arrays, nuv, nf, G, binsize, uu, vv, weighting, npixels, mode,

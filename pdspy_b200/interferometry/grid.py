@@ -40,6 +40,35 @@ def freqcorrect(data, freq=None):
     return Visibilities(new_u, new_v, new_freq, new_real, new_imag, new_weights)
 
 
+class MeshFiller:
+    """numpy.meshgrid(uu, vv) of the result's coordinates (libinterferometry.pyx:383), optionally on a second host
+    thread while the device works; an exception raised there (MemoryError) resurfaces in result()."""
+
+    def __init__(self, uu, vv, threaded=True):
+        self._out, self._err = None, None
+        self._thread = threading.Thread(target=self._run, args=(uu, vv)) if threaded else None
+        if self._thread is not None:
+            self._thread.start()
+        else:
+            self._run(uu, vv)
+
+    def _run(self, uu, vv):
+        try:
+            self._out = numpy.meshgrid(uu, vv)
+        except BaseException as e:                   # noqa: BLE001 - handed to the caller's thread
+            self._err = e
+
+    def join(self):
+        if self._thread is not None:
+            self._thread.join()
+
+    def result(self):
+        self.join()
+        if self._err is not None:
+            raise self._err
+        return self._out
+
+
 def grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", mfs=False, channel=None,
          imaging=False, weighting="natural", robust=2, npixels=0, mode="continuum",
          deterministic=True, return_maps=False):
@@ -80,12 +109,7 @@ def grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", mfs=False, c
     G2 = gridsize ** 2
     # the [G, G] coordinate arrays of the result (:383): for large grids they are filled on a second host thread while
     # pdsb_grid runs (ctypes releases the GIL; at G = 2048 the 67 MB cost as much host time as the whole device step)
-    mesh = []
-    filler = threading.Thread(target=lambda: mesh.extend(numpy.meshgrid(uu, vv))) if G2 >= 1 << 18 else None
-    if filler is not None:
-        filler.start()
-    else:
-        mesh.extend(numpy.meshgrid(uu, vv))
+    filler = MeshFiller(uu, vv, threaded=G2 >= 1 << 18)
 
     new_real = numpy.empty((G2, nchannels))
     new_imag = numpy.empty((G2, nchannels))
@@ -105,9 +129,8 @@ def grid(data, gridsize=256, binsize=2000.0, convolution="pillbox", mfs=False, c
                                _lib.ptr(new_real), _lib.ptr(new_imag), _lib.ptr(new_weights),
                                _lib.ptr(gi), _lib.ptr(gj), _lib.ptr(wmod), _lib.HOST, ctypes.byref(n_out)))
     finally:
-        if filler is not None:
-            filler.join()
-    new_u, new_v = mesh
+        filler.join()
+    new_u, new_v = filler.result()
     if n_out.value > 0:
         print(_WARNING)
 
