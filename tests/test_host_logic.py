@@ -131,3 +131,18 @@ def test_unstructured_triangulation_helper_vs_scipy_interpolator():
     ref = ou.regrid(x, y, vals, nxy, dxy)[::-1, :, :, 0].reshape(nxy * nxy, 2)
     assert (tri[:, 0] >= 0).mean() > 0.5
     assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_mesh_filler_matches_meshgrid_and_hands_over_exceptions():
+    """grid() / sharded_grid() fill the result's coordinate arrays (numpy.meshgrid, libinterferometry.pyx:383) on a
+    second host thread while the device works; a failure there must surface in the caller, not vanish."""
+    from pdspy_b200.interferometry.grid import MeshFiller
+    uu, vv = np.linspace(-3, 2, 6), np.linspace(-1, 1, 5)
+    for threaded in (True, False):
+        a, b = MeshFiller(uu, vv, threaded=threaded).result()
+        ra, rb = np.meshgrid(uu, vv)
+        assert np.array_equal(a, ra) and np.array_equal(b, rb)
+    huge = np.broadcast_to(np.float64(0.0), (1 << 40,))      # a view: the 2-D copies cannot be allocated
+    bad = MeshFiller(huge, huge[:4], threaded=True)
+    with pytest.raises(MemoryError):
+        bad.result()
